@@ -1,0 +1,124 @@
+/* rofl_b200 -- C ABI of the B200-native implementation of RoFL's rofl_crypto client-prove / server-verify hot path.
+ *
+ * This header is the drop-in boundary: every entry point replaces one function of the
+ * reference's Rust API (the surface rofl_service/src/flserver/params.rs links) and, where one exists, the matching
+ * `extern "C"` export of rofl_crypto/src/bindings32.rs.  INTEGRATION.md shows the Rust `-sys` binding and the
+ * shim that maps these calls back onto the reference's module paths and types.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; points are 32-byte compressed ristretto255 encodings, scalars are 32-byte
+ *     little-endian canonical integers mod l, values are IEEE f32, proofs are the reference's byte serialisations
+ *     (RangeProof::to_bytes, SquareProof::to_bytes 160 B, SquareProofCommitments 64 B, ElGamalPair 64 B).
+ *   - functions without suffix take HOST buffers (the reference-facing calls; copies are inside the call);
+ *     `_dev` variants take DEVICE pointers for every array marked [dev] (inputs already resident in HBM).
+ *   - the fixed-point configuration the reference selects with cargo features (rofl_crypto/src/fp.rs:35-137) is the
+ *     runtime pair (n_bits in {8,16,32,64}, frac in 0..12).
+ *   - every nonce the reference draws from rand::thread_rng() is drawn from ChaCha20 streams derived from `seed`
+ *     (32 bytes) in the reference's draw order, so outputs are a pure function of (inputs, seed).
+ *   - return codes: prove calls return 0 on success; verify calls return 1 (valid) / 0 (invalid, the reference's
+ *     Ok(false)); negative values are errors (the reference's Err(..) or panic), positive prove codes are the
+ *     reference's domain errors.  rofl_last_error() gives a message for the calling thread.
+ *   - there is no CPU fallback: every call needs a CUDA device (sm_100a) and fails with ROFL_ERR_CUDA otherwise.
+ */
+#ifndef ROFL_B200_H
+#define ROFL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rofl_ctx rofl_ctx;
+
+enum {
+    ROFL_OK = 0,
+    ROFL_ERR_VALUE_OUT_OF_RANGE = 2,   /* RangeProofError::ValueOutOfRangeError (range_proof_vec/errors.rs:5-19)          */
+    ROFL_ERR_OVERFLOW = 3,             /* L2RangeProofError::OverflowError      (l2_range_proof_vec/errors.rs:4-31)       */
+    ROFL_ERR_NORM_OUT_OF_RANGE = 4,    /* L2RangeProofError::NormOutOfRangeError                                         */
+    ROFL_ERR_FORMAT = -1,              /* ProofError::FormatError (malformed proof / non-canonical scalar)               */
+    ROFL_ERR_BITSIZE = -1,             /* prove side: ProofError::InvalidBitsize (range not in {8,16,32,64})             */
+    ROFL_ERR_ARGS = -2,                /* bad arguments; verify side: ProofError::InvalidBitsize                          */
+    ROFL_ERR_GENS = -3,                /* ProofError::InvalidGeneratorsLength                                             */
+    ROFL_ERR_POINT = -4,               /* a commitment does not decode (the reference's decompress().unwrap() panics)    */
+    ROFL_ERR_DLOG = -5,                /* no discrete log in range (bsgs32.rs:69-70 unwrap panic)                         */
+    ROFL_ERR_NAN = -98,                /* NaN input (Fix::saturating_from_float panics)                                   */
+    ROFL_ERR_PARTITION = -99,          /* n_partition gives non power-of-two chunks (range_proof_vec/mod.rs:137-140 panic) */
+    ROFL_ERR_CUDA = -100               /* CUDA runtime error / no device                                                   */
+};
+
+/* process-wide context: device, stream, cached generator tables and BSGS tables (SURVEY.md section 8b "threading").
+ * Thread-safe: concurrent callers are serialised per context; create one context per GPU (or per worker thread). */
+int rofl_ctx_create(rofl_ctx **out, int device);
+void rofl_ctx_destroy(rofl_ctx *ctx);
+const char *rofl_last_error(void);
+void rofl_set_host_threads(rofl_ctx *ctx, int n);          /* host threads used for the per-chunk Merlin transcripts */
+
+/* ---- sizes ---------------------------------------------------------------------------------------------------- */
+size_t rofl_next_pow2(size_t v);                           /* range_proof_vec/mod.rs:237-246                          */
+size_t rofl_range_proof_len(size_t n_times_m);             /* 32*(9 + 2 lg(n*m)) : RangeProof::to_bytes length         */
+/* number of proofs and bytes per proof create_rangeproof produces for (D, range, n_partition) */
+void rofl_range_proof_shape(size_t D, int range, size_t n_partition, size_t *n_proofs, size_t *proof_len);
+
+/* ---- conversion32.rs / range_proof_vec::clip_f32_to_range_vec -------------------------------------------------- */
+int rofl_f32_to_scalar_vec(rofl_ctx *, const float *v, size_t D, int n_bits, int frac, uint8_t *out_scalars32);       /* conversion32.rs:11-22 */
+int rofl_scalar_to_f32_vec(rofl_ctx *, const uint8_t *scalars32, size_t D, int n_bits, int frac, float *out);         /* conversion32.rs:24-38 */
+void rofl_clip_bounds(int range, int n_bits, int frac, float *mn, float *mx);                                        /* conversion32.rs:56-60 */
+float rofl_l2_clip_bound(int range, int n_bits, int frac);                                                            /* conversion32.rs:62-64 */
+void rofl_clip_f32_to_range_vec(const float *v, size_t D, int range, int n_bits, int frac, float *out);              /* range_proof_vec/mod.rs:104-111 (host; O(D) f32 min/max) */
+void rofl_rnd_scalar_vec(const uint8_t seed[32], size_t D, uint8_t *out_scalars32);                                  /* pedersen_ops.rs:124-127, seeded   */
+
+/* ---- commitments: pedersen_ops::commit_vec / commit_no_blinding_vec (pedersen_ops.rs:9-25) and the ElGamal right
+ *      halves R = r*B (el_gamal.rs:57-69, compressed_rand_proof/party.rs:23-24).  blind32 may be NULL (zero blinding,
+ *      then out_R32 must be NULL); out_R32 may be NULL.  bindings32.rs:118,130 (`commit_no_blinding`, `commit`). */
+int rofl_commit(rofl_ctx *, const float *v, const uint8_t *blind32, size_t D, int n_bits, int frac, uint8_t *out_L32, uint8_t *out_R32);
+int rofl_commit_dev(rofl_ctx *, const float *v /*dev*/, const uint8_t *blind32 /*dev*/, size_t D, int n_bits, int frac, uint8_t *out_L32 /*dev*/, uint8_t *out_R32 /*dev*/);
+
+/* ---- range_proof_vec::create_rangeproof (range_proof_vec/mod.rs:16-102; bindings32.rs:228 `create_rangeproof`).
+ *      out_proofs: n_proofs*proof_len bytes (see rofl_range_proof_shape), out_commits32: D*32 bytes. */
+int rofl_range_prove(rofl_ctx *, const float *v, const uint8_t *blind32, size_t D, int range, size_t n_partition, int n_bits, int frac,
+                     const uint8_t seed[32], uint8_t *out_proofs, size_t *out_proof_len, size_t *out_n_proofs, uint8_t *out_commits32);
+int rofl_range_prove_dev(rofl_ctx *, const float *v /*dev*/, const uint8_t *blind32 /*dev*/, size_t D, int range, size_t n_partition, int n_bits, int frac,
+                         const uint8_t seed[32], uint8_t *out_proofs /*host*/, size_t *out_proof_len, size_t *out_n_proofs, uint8_t *out_commits32 /*dev*/);
+/* ---- range_proof_vec::verify_rangeproof (range_proof_vec/mod.rs:149-191; bindings32.rs:265 `verify_rangeproof`).
+ *      seed feeds the verifier's random batching scalar (RangeProof::verify_multiple draws it from thread_rng). */
+int rofl_range_verify(rofl_ctx *, const uint8_t *proofs, size_t proof_len, size_t n_proofs, const uint8_t *commits32, size_t D, int range, const uint8_t seed[32]);
+int rofl_range_verify_dev(rofl_ctx *, const uint8_t *proofs /*host*/, size_t proof_len, size_t n_proofs, const uint8_t *commits32 /*dev*/, size_t D, int range, const uint8_t seed[32]);
+
+/* ---- l2_range_proof_vec::{create_rangeproof_l2, verify_rangeproof_l2} (l2_range_proof_vec/mod.rs:15-140,185-228;
+ *      bindings32.rs:441,507).  out_proof: rofl_range_proof_len(range) bytes; out_commit32: 32 bytes (not shifted). */
+int rofl_l2_prove(rofl_ctx *, const float *v, const uint8_t *blind32, size_t D, int range, int n_bits, int frac, const uint8_t seed[32],
+                  uint8_t *out_proof, size_t *out_proof_len, uint8_t *out_commit32);
+int rofl_l2_verify(rofl_ctx *, const uint8_t *proof, size_t proof_len, const uint8_t commit32[32], int range, const uint8_t seed[32]);
+
+/* ---- square_proof_vec::{create_l2rangeproof_vec_existing, verify_l2rangeproof_vec} (square_proof_vec/mod.rs:19-75,130-160).
+ *      value_com32: D commitments c_l; r1/r2: D blindings each; out_proofs: D*160; out_commits: D*64 (c_l | c_sq). */
+int rofl_square_prove(rofl_ctx *, const float *v, const uint8_t *value_com32, const uint8_t *r1_32, const uint8_t *r2_32, size_t D, int n_bits, int frac,
+                      const uint8_t seed[32], uint8_t *out_proofs160, uint8_t *out_commits64);
+int rofl_square_prove_dev(rofl_ctx *, const float *v, const uint8_t *value_com32, const uint8_t *r1_32, const uint8_t *r2_32, size_t D, int n_bits, int frac,
+                          const uint8_t seed[32], uint8_t *out_proofs160, uint8_t *out_commits64);     /* all arrays [dev] */
+int rofl_square_verify(rofl_ctx *, const uint8_t *proofs160, const uint8_t *commits64, size_t D);
+int rofl_square_verify_dev(rofl_ctx *, const uint8_t *proofs160 /*dev*/, const uint8_t *commits64 /*dev*/, size_t D);
+
+/* ---- aggregation: EncModelParamsAccumulator::accumulate_other (params.rs:81-124) / pedersen_ops::add_rp_vec_vec
+ *      (pedersen_ops.rs:56-69; bindings32.rs:64 `add_commitments`).  points32: n_clients x D encodings, client-major.
+ *      init_unity = 1 starts every element at the basepoint (ElGamalPair::unity, el_gamal.rs:83-88), 0 at the identity. */
+int rofl_aggregate(rofl_ctx *, const uint8_t *points32, size_t n_clients, size_t D, int init_unity, uint8_t *out32);
+int rofl_aggregate_dev(rofl_ctx *, const uint8_t *points32 /*dev*/, size_t n_clients, size_t D, int init_unity, uint8_t *out32 /*dev*/);
+
+/* ---- decryption: pedersen_ops::discrete_log_vec_table + BSGSTable (pedersen_ops.rs:47-53, bsgs32.rs:20-73;
+ *      bindings32.rs:213 `extract_values`).  table_size = BSGSTable::new(m); bsgs_bits = width of BSGS_URawFix
+ *      (8 for fp8, else 16).  out_scalars32 / out_f32 may be NULL.  The table is built once per (table_size, bsgs_bits). */
+int rofl_dlog(rofl_ctx *, const uint8_t *points32, size_t D, uint64_t table_size, int bsgs_bits, int n_bits, int frac, uint8_t *out_scalars32, float *out_f32);
+int rofl_dlog_dev(rofl_ctx *, const uint8_t *points32 /*dev*/, size_t D, uint64_t table_size, int bsgs_bits, int n_bits, int frac, uint8_t *out_scalars32 /*dev*/, float *out_f32 /*dev*/);
+
+/* ---- measurement hooks (bench.py): CUDA-event time per kernel family and launch counts since the last reset ------- */
+enum { ROFL_PROF_FOLD = 0, ROFL_PROF_MSM = 1, ROFL_PROF_COMMIT = 2, ROFL_PROF_SQUARE = 3 };
+void rofl_prof_enable(int on);
+void rofl_prof_reset(void);
+double rofl_prof_ms(int slot);            /* summed device time of that kernel family, milliseconds */
+long rofl_prof_launches(int slot);        /* launches of that family; slot -1 = all kernels launched by the library */
+void *rofl_ctx_stream(rofl_ctx *);        /* the cudaStream_t the context launches on */
+#ifdef __cplusplus
+}
+#endif
+#endif

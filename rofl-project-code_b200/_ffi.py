@@ -1,0 +1,198 @@
+"""ctypes binding of include/rofl_b200.h (the C ABI of librofl_b200.so) plus a thin numpy-facing wrapper.
+
+`Api(cdll)` is agnostic of where the handle came from; the package (`__init__.py`) only ever hands it the CUDA
+library.  Array arguments are numpy arrays (host-buffer calls) or integer device addresses (`*_dev` calls, e.g.
+`tensor.data_ptr()` of a torch CUDA tensor)."""
+import ctypes as C
+import numpy as np
+
+c_sz, c_u8p, c_f32p, c_vp = C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p
+
+_SIGS = {
+    "rofl_ctx_create": (C.c_int, [C.POINTER(c_vp), C.c_int]),
+    "rofl_ctx_destroy": (None, [c_vp]),
+    "rofl_last_error": (C.c_char_p, []),
+    "rofl_set_host_threads": (None, [c_vp, C.c_int]),
+    "rofl_next_pow2": (c_sz, [c_sz]),
+    "rofl_range_proof_len": (c_sz, [c_sz]),
+    "rofl_range_proof_shape": (None, [c_sz, C.c_int, c_sz, C.POINTER(c_sz), C.POINTER(c_sz)]),
+    "rofl_f32_to_scalar_vec": (C.c_int, [c_vp, c_f32p, c_sz, C.c_int, C.c_int, c_u8p]),
+    "rofl_scalar_to_f32_vec": (C.c_int, [c_vp, c_u8p, c_sz, C.c_int, C.c_int, c_f32p]),
+    "rofl_clip_bounds": (None, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "rofl_l2_clip_bound": (C.c_float, [C.c_int, C.c_int, C.c_int]),
+    "rofl_clip_f32_to_range_vec": (None, [c_f32p, c_sz, C.c_int, C.c_int, C.c_int, c_f32p]),
+    "rofl_rnd_scalar_vec": (None, [c_u8p, c_sz, c_u8p]),
+    "rofl_commit": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p]),
+    "rofl_commit_dev": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p]),
+    "rofl_range_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, C.POINTER(c_sz), C.POINTER(c_sz), c_u8p]),
+    "rofl_range_prove_dev": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, C.POINTER(c_sz), C.POINTER(c_sz), c_u8p]),
+    "rofl_range_verify": (C.c_int, [c_vp, c_u8p, c_sz, c_sz, c_u8p, c_sz, C.c_int, c_u8p]),
+    "rofl_range_verify_dev": (C.c_int, [c_vp, c_u8p, c_sz, c_sz, c_u8p, c_sz, C.c_int, c_u8p]),
+    "rofl_l2_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, C.c_int, C.c_int, c_u8p, c_u8p, C.POINTER(c_sz), c_u8p]),
+    "rofl_l2_verify": (C.c_int, [c_vp, c_u8p, c_sz, c_u8p, C.c_int, c_u8p]),
+    "rofl_square_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_u8p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p]),
+    "rofl_square_prove_dev": (C.c_int, [c_vp, c_f32p, c_u8p, c_u8p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p]),
+    "rofl_square_verify": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz]),
+    "rofl_square_verify_dev": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz]),
+    "rofl_aggregate": (C.c_int, [c_vp, c_u8p, c_sz, c_sz, C.c_int, c_u8p]),
+    "rofl_aggregate_dev": (C.c_int, [c_vp, c_u8p, c_sz, c_sz, C.c_int, c_u8p]),
+    "rofl_dlog": (C.c_int, [c_vp, c_u8p, c_sz, C.c_uint64, C.c_int, C.c_int, C.c_int, c_u8p, c_f32p]),
+    "rofl_dlog_dev": (C.c_int, [c_vp, c_u8p, c_sz, C.c_uint64, C.c_int, C.c_int, C.c_int, c_u8p, c_f32p]),
+    "rofl_prof_enable": (None, [C.c_int]),
+    "rofl_prof_reset": (None, []),
+    "rofl_prof_ms": (C.c_double, [C.c_int]),
+    "rofl_prof_launches": (C.c_long, [C.c_int]),
+    "rofl_ctx_stream": (c_vp, [c_vp]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def bind(lib):
+    for name, (res, args) in _SIGS.items():
+        f = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
+        f.restype, f.argtypes = res, args
+    return lib
+
+
+class RoflError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__(f"rofl_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    return a.ctypes.data
+
+
+def _u8(x, n=None):
+    if isinstance(x, (bytes, bytearray)):
+        x = np.frombuffer(bytes(x), dtype=np.uint8)
+    a = np.ascontiguousarray(x, dtype=np.uint8)
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} bytes, got {a.size}")
+    return a
+
+
+def _f32(x):
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+SEED0 = bytes(32)
+
+
+class Api:
+    """One context (= one GPU) of the library."""
+
+    def __init__(self, lib, device=0):
+        self.lib = bind(lib)
+        h = c_vp()
+        rc = self.lib.rofl_ctx_create(C.byref(h), device)
+        if rc != 0:
+            raise RoflError(rc, (self.lib.rofl_last_error() or b"").decode())
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.rofl_ctx_destroy(self.h); self.h = None
+
+    def _err(self, rc):
+        return RoflError(rc, (self.lib.rofl_last_error() or b"").decode())
+
+    # ---- sizes / conversions
+    def next_pow2(self, v): return self.lib.rofl_next_pow2(v)
+    def range_proof_len(self, N): return self.lib.rofl_range_proof_len(N)
+    def range_proof_shape(self, D, rng, n_partition):
+        a, b = c_sz(), c_sz(); self.lib.rofl_range_proof_shape(D, rng, n_partition, C.byref(a), C.byref(b)); return a.value, b.value
+    def clip_bounds(self, rng, n_bits, frac):
+        mn, mx = C.c_float(), C.c_float(); self.lib.rofl_clip_bounds(rng, n_bits, frac, C.byref(mn), C.byref(mx)); return mn.value, mx.value
+    def l2_clip_bound(self, rng, n_bits, frac): return self.lib.rofl_l2_clip_bound(rng, n_bits, frac)
+    def clip_f32_to_range_vec(self, v, rng, n_bits, frac):
+        v = _f32(v); o = np.empty_like(v); self.lib.rofl_clip_f32_to_range_vec(_ptr(v), v.size, rng, n_bits, frac, _ptr(o)); return o
+    def rnd_scalar_vec(self, seed, D):
+        o = np.zeros((D, 32), np.uint8); self.lib.rofl_rnd_scalar_vec(_ptr(_u8(seed, 32)), D, _ptr(o)); return o
+    def f32_to_scalar_vec(self, v, n_bits, frac):
+        v = _f32(v); o = np.zeros((v.size, 32), np.uint8)
+        rc = self.lib.rofl_f32_to_scalar_vec(self.h, _ptr(v), v.size, n_bits, frac, _ptr(o))
+        if rc: raise self._err(rc)
+        return o
+    def scalar_to_f32_vec(self, s, n_bits, frac):
+        s = _u8(s).reshape(-1, 32); o = np.zeros(s.shape[0], np.float32)
+        rc = self.lib.rofl_scalar_to_f32_vec(self.h, _ptr(s), s.shape[0], n_bits, frac, _ptr(o))
+        if rc: raise self._err(rc)
+        return o
+
+    # ---- commitments
+    def commit(self, v, blind, n_bits, frac, want_R=False):
+        v = _f32(v); D = v.size; b = _u8(blind, 32 * D) if blind is not None else None
+        L = np.zeros((D, 32), np.uint8); R = np.zeros((D, 32), np.uint8) if (want_R and b is not None) else None
+        rc = self.lib.rofl_commit(self.h, _ptr(v), _ptr(b), D, n_bits, frac, _ptr(L), _ptr(R))
+        if rc: raise self._err(rc)
+        return (L, R) if want_R else L
+
+    # ---- range proofs; return (rc, proofs[n_proofs, proof_len], commits[D, 32])
+    def range_prove(self, v, blind, rng, n_partition, n_bits, frac, seed=SEED0):
+        v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
+        npf, plen = self.range_proof_shape(D, rng, n_partition)
+        proofs = np.zeros((npf, max(plen, 1)), np.uint8); commits = np.zeros((D, 32), np.uint8)
+        a, c = c_sz(), c_sz()
+        rc = self.lib.rofl_range_prove(self.h, _ptr(v), _ptr(b), D, rng, n_partition, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proofs), C.byref(a), C.byref(c), _ptr(commits))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc, proofs, commits
+    def range_prove_dev(self, v_ptr, blind_ptr, D, rng, n_partition, n_bits, frac, seed, commits_ptr):
+        npf, plen = self.range_proof_shape(D, rng, n_partition)
+        proofs = np.zeros((npf, max(plen, 1)), np.uint8); a, c = c_sz(), c_sz()
+        rc = self.lib.rofl_range_prove_dev(self.h, v_ptr, blind_ptr, D, rng, n_partition, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proofs), C.byref(a), C.byref(c), commits_ptr)
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc, proofs
+    def range_verify(self, proofs, commits, rng, seed=SEED0):
+        p = _u8(proofs); p = p.reshape(p.shape[0], -1); c = _u8(commits).reshape(-1, 32)
+        rc = self.lib.rofl_range_verify(self.h, _ptr(p), p.shape[1], p.shape[0], _ptr(c), c.shape[0], rng, _ptr(_u8(seed, 32)))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc
+    def range_verify_dev(self, proofs, commits_ptr, D, rng, seed=SEED0):
+        p = _u8(proofs); p = p.reshape(p.shape[0], -1)
+        rc = self.lib.rofl_range_verify_dev(self.h, _ptr(p), p.shape[1], p.shape[0], commits_ptr, D, rng, _ptr(_u8(seed, 32)))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc
+    def l2_prove(self, v, blind, rng, n_bits, frac, seed=SEED0):
+        v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
+        proof = np.zeros(self.range_proof_len(max(rng, 1)), np.uint8); commit = np.zeros(32, np.uint8); a = c_sz()
+        rc = self.lib.rofl_l2_prove(self.h, _ptr(v), _ptr(b), D, rng, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proof), C.byref(a), _ptr(commit))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc, proof, commit
+    def l2_verify(self, proof, commit, rng, seed=SEED0):
+        p = _u8(proof)
+        rc = self.lib.rofl_l2_verify(self.h, _ptr(p), p.size, _ptr(_u8(commit, 32)), rng, _ptr(_u8(seed, 32)))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc
+    # ---- square proofs
+    def square_prove(self, v, value_com, r1, r2, n_bits, frac, seed=SEED0):
+        v = _f32(v); D = v.size
+        proofs = np.zeros((D, 160), np.uint8); commits = np.zeros((D, 64), np.uint8)
+        rc = self.lib.rofl_square_prove(self.h, _ptr(v), _ptr(_u8(value_com, 32 * D)), _ptr(_u8(r1, 32 * D)), _ptr(_u8(r2, 32 * D)), D, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proofs), _ptr(commits))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc, proofs, commits
+    def square_verify(self, proofs, commits):
+        p = _u8(proofs).reshape(-1, 160); c = _u8(commits).reshape(-1, 64)
+        rc = self.lib.rofl_square_verify(self.h, _ptr(p), _ptr(c), p.shape[0])
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc
+    # ---- aggregate / decrypt
+    def aggregate(self, pts, init_unity=0):
+        a = _u8(pts); assert a.ndim == 3 and a.shape[2] == 32
+        o = np.zeros((a.shape[1], 32), np.uint8)
+        rc = self.lib.rofl_aggregate(self.h, _ptr(a), a.shape[0], a.shape[1], init_unity, _ptr(o))
+        if rc: raise self._err(rc)
+        return o
+    def dlog(self, pts, table_size=1 << 16, bsgs_bits=16, n_bits=16, frac=7):
+        a = _u8(pts).reshape(-1, 32); s = np.zeros_like(a); f = np.zeros(a.shape[0], np.float32)
+        rc = self.lib.rofl_dlog(self.h, _ptr(a), a.shape[0], table_size, bsgs_bits, n_bits, frac, _ptr(s), _ptr(f))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc, s, f
+
+
+ROFL_ERR_CUDA = -100

@@ -1,0 +1,172 @@
+// extern "C" entry points declared in include/rofl_b200.h.  Host-buffer variants stage through device scratch and call
+// the same engine functions as the _dev variants.
+#pragma once
+#include "engine.cuh"
+#include "../../include/rofl_b200.h"
+
+struct rofl_ctx { rofl_engine e; };
+static thread_local std::string g_last_error;
+#define API_TRY try {
+#define API_CATCH } catch (const std::exception &ex) { g_last_error = ex.what(); return ROFL_ERR_CUDA; }
+
+extern "C" const char *rofl_last_error(void) { return g_last_error.c_str(); }
+extern "C" void rofl_set_host_threads(rofl_ctx *c, int n) { if (c && n > 0) c->e.host_threads = n; }
+extern "C" size_t rofl_next_pow2(size_t v) { return next_pow2_sz(v); }
+extern "C" size_t rofl_range_proof_len(size_t N) { return 32 * (9 + 2 * (size_t)ilog2_sz(N)); }
+extern "C" void rofl_range_proof_shape(size_t D, int range, size_t n_partition, size_t *n_proofs, size_t *proof_len) {
+    size_t Dp = next_pow2_sz(D ? D : 1), C = std::min(Dp, n_partition ? n_partition : 1), m = Dp / C;
+    if (n_proofs) *n_proofs = C;
+    if (proof_len) *proof_len = rofl_range_proof_len((size_t)range * m);
+}
+extern "C" void rofl_clip_bounds(int range, int n_bits, int frac, float *mn, float *mx) { float m = clip_max_f(range, n_bits, frac); if (mx) *mx = m; if (mn) *mn = -m; }
+extern "C" float rofl_l2_clip_bound(int range, int n_bits, int frac) { return l2_clip_max_f(range, n_bits, frac); }
+extern "C" void rofl_clip_f32_to_range_vec(const float *v, size_t D, int range, int n_bits, int frac, float *out) {
+    float mx = clip_max_f(range, n_bits, frac), mn = -mx;
+    for (size_t i = 0; i < D; i++) out[i] = fminf(mx, fmaxf(mn, v[i]));
+}
+extern "C" void rofl_rnd_scalar_vec(const uint8_t seed[32], size_t D, uint8_t *out) {
+    uint8_t key[32]; derive_key(key, seed, DOM_RND_VEC, 0); uint32_t kw[8]; key_words(kw, key);
+    for (size_t i = 0; i < D; i++) { sc s; nonce_scalar(s, kw, i); sc_tobytes(out + 32 * i, s); }
+}
+
+// host <-> device staging helpers
+struct staged_in { dev_buf b; staged_in(const void *h, size_t n, cudaStream_t s) : b(n ? n : 16, s) { if (h && n) rt_h2d(b.p, h, n, s); } };
+
+extern "C" int rofl_f32_to_scalar_vec(rofl_ctx *c, const float *v, size_t D, int n_bits, int frac, uint8_t *out) {
+    API_TRY
+    if (!fp_ok(n_bits, frac)) return ROFL_ERR_ARGS;
+    if (!D) return 0;
+    std::lock_guard<std::mutex> lk(c->e.mu); cudaStream_t s = c->e.stream;
+    staged_in dv(v, 4 * D, s); dev_buf o(32 * D, s), fl(sizeof(int), s); rt_memset(fl.p, 0, sizeof(int), s);
+    LAUNCH(k_f32_to_scalar, dim3((unsigned)((D + 255) / 256)), dim3(256), s, o.as<uint8_t>(), dv.b.as<float>(), D, n_bits, frac, fl.as<int>());
+    int f = 0; rt_d2h(out, o.p, 32 * D, s); rt_d2h(&f, fl.p, sizeof(int), s); rt_sync(s);
+    return f ? ROFL_ERR_NAN : 0;
+    API_CATCH
+}
+extern "C" int rofl_scalar_to_f32_vec(rofl_ctx *c, const uint8_t *sc32, size_t D, int n_bits, int frac, float *out) {
+    API_TRY
+    if (!fp_ok(n_bits, frac)) return ROFL_ERR_ARGS;
+    if (!D) return 0;
+    std::lock_guard<std::mutex> lk(c->e.mu); cudaStream_t s = c->e.stream;
+    staged_in ds(sc32, 32 * D, s); dev_buf o(4 * D, s);
+    LAUNCH(k_scalar_to_f32, dim3((unsigned)((D + 255) / 256)), dim3(256), s, o.as<float>(), ds.b.as<uint8_t>(), D, n_bits, frac);
+    rt_d2h(out, o.p, 4 * D, s); rt_sync(s);
+    return 0;
+    API_CATCH
+}
+extern "C" int rofl_commit_dev(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, uint8_t *L, uint8_t *R) {
+    API_TRY return engine_commit(c->e, v, blind, D, n_bits, frac, L, R); API_CATCH
+}
+extern "C" int rofl_commit(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, uint8_t *L, uint8_t *R) {
+    API_TRY
+    if (!D) return 0;
+    cudaStream_t s = c->e.stream;
+    staged_in dv(v, 4 * D, s), db(blind, blind ? 32 * D : 0, s); dev_buf dL(32 * D, s), dR(32 * D, s);
+    int rc = engine_commit(c->e, dv.b.as<float>(), blind ? db.b.as<uint8_t>() : nullptr, D, n_bits, frac, dL.as<uint8_t>(), (R && blind) ? dR.as<uint8_t>() : nullptr);
+    if (rc) return rc;
+    rt_d2h(L, dL.p, 32 * D, s); if (R && blind) rt_d2h(R, dR.p, 32 * D, s); rt_sync(s);
+    return 0;
+    API_CATCH
+}
+extern "C" int rofl_range_prove_dev(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D, int range, size_t P, int n_bits, int frac, const uint8_t seed[32],
+                                    uint8_t *proofs, size_t *plen, size_t *np, uint8_t *commits) {
+    API_TRY
+    size_t a = 0, b = 0;
+    int rc = engine_range_prove(c->e, v, blind, D, range, P, n_bits, frac, seed, proofs, &a, &b, commits);
+    if (plen) *plen = a; if (np) *np = b;
+    return rc;
+    API_CATCH
+}
+extern "C" int rofl_range_prove(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D, int range, size_t P, int n_bits, int frac, const uint8_t seed[32],
+                                uint8_t *proofs, size_t *plen, size_t *np, uint8_t *commits) {
+    API_TRY
+    if (!D) return ROFL_ERR_ARGS;
+    cudaStream_t s = c->e.stream;
+    staged_in dv(v, 4 * D, s), db(blind, 32 * D, s); dev_buf dC(32 * D, s);
+    size_t a = 0, b = 0;
+    int rc = engine_range_prove(c->e, dv.b.as<float>(), db.b.as<uint8_t>(), D, range, P, n_bits, frac, seed, proofs, &a, &b, dC.as<uint8_t>());
+    if (plen) *plen = a; if (np) *np = b;
+    if (rc) return rc;
+    rt_d2h(commits, dC.p, 32 * D, s); rt_sync(s);
+    return 0;
+    API_CATCH
+}
+extern "C" int rofl_range_verify_dev(rofl_ctx *c, const uint8_t *proofs, size_t plen, size_t np, const uint8_t *commits, size_t D, int range, const uint8_t seed[32]) {
+    API_TRY return engine_range_verify(c->e, proofs, plen, np, commits, D, range, seed); API_CATCH
+}
+extern "C" int rofl_range_verify(rofl_ctx *c, const uint8_t *proofs, size_t plen, size_t np, const uint8_t *commits, size_t D, int range, const uint8_t seed[32]) {
+    API_TRY
+    if (!D) return ROFL_ERR_ARGS;
+    staged_in dc(commits, 32 * D, c->e.stream);
+    return engine_range_verify(c->e, proofs, plen, np, dc.b.as<uint8_t>(), D, range, seed);
+    API_CATCH
+}
+extern "C" int rofl_l2_prove(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D, int range, int n_bits, int frac, const uint8_t seed[32],
+                             uint8_t *proof, size_t *plen, uint8_t *commit) {
+    API_TRY
+    if (!D) return ROFL_ERR_ARGS;
+    cudaStream_t s = c->e.stream;
+    staged_in dv(v, 4 * D, s), db(blind, 32 * D, s);
+    size_t a = 0;
+    int rc = engine_l2_prove(c->e, v, dv.b.as<float>(), db.b.as<uint8_t>(), D, range, n_bits, frac, seed, proof, &a, commit);
+    if (plen) *plen = a;
+    return rc;
+    API_CATCH
+}
+extern "C" int rofl_l2_verify(rofl_ctx *c, const uint8_t *proof, size_t plen, const uint8_t commit[32], int range, const uint8_t seed[32]) {
+    API_TRY return engine_l2_verify(c->e, proof, plen, commit, range, seed); API_CATCH
+}
+extern "C" int rofl_square_prove_dev(rofl_ctx *c, const float *v, const uint8_t *vc, const uint8_t *r1, const uint8_t *r2, size_t D, int n_bits, int frac,
+                                     const uint8_t seed[32], uint8_t *proofs, uint8_t *commits) {
+    API_TRY return engine_square_prove(c->e, v, vc, r1, r2, D, n_bits, frac, seed, proofs, commits); API_CATCH
+}
+extern "C" int rofl_square_prove(rofl_ctx *c, const float *v, const uint8_t *vc, const uint8_t *r1, const uint8_t *r2, size_t D, int n_bits, int frac,
+                                 const uint8_t seed[32], uint8_t *proofs, uint8_t *commits) {
+    API_TRY
+    if (!D) return 0;
+    cudaStream_t s = c->e.stream;
+    staged_in dv(v, 4 * D, s), dvc(vc, 32 * D, s), d1(r1, 32 * D, s), d2(r2, 32 * D, s); dev_buf dp(160 * D, s), dc(64 * D, s);
+    int rc = engine_square_prove(c->e, dv.b.as<float>(), dvc.b.as<uint8_t>(), d1.b.as<uint8_t>(), d2.b.as<uint8_t>(), D, n_bits, frac, seed, dp.as<uint8_t>(), dc.as<uint8_t>());
+    if (rc) return rc;
+    rt_d2h(proofs, dp.p, 160 * D, s); rt_d2h(commits, dc.p, 64 * D, s); rt_sync(s);
+    return 0;
+    API_CATCH
+}
+extern "C" int rofl_square_verify_dev(rofl_ctx *c, const uint8_t *proofs, const uint8_t *commits, size_t D) {
+    API_TRY return engine_square_verify(c->e, proofs, commits, D); API_CATCH
+}
+extern "C" int rofl_square_verify(rofl_ctx *c, const uint8_t *proofs, const uint8_t *commits, size_t D) {
+    API_TRY
+    if (!D) return 1;
+    cudaStream_t s = c->e.stream;
+    staged_in dp(proofs, 160 * D, s), dc(commits, 64 * D, s);
+    return engine_square_verify(c->e, dp.b.as<uint8_t>(), dc.b.as<uint8_t>(), D);
+    API_CATCH
+}
+extern "C" int rofl_aggregate_dev(rofl_ctx *c, const uint8_t *pts, size_t nc, size_t D, int init, uint8_t *out) {
+    API_TRY return engine_aggregate(c->e, pts, nc, D, init, out); API_CATCH
+}
+extern "C" int rofl_aggregate(rofl_ctx *c, const uint8_t *pts, size_t nc, size_t D, int init, uint8_t *out) {
+    API_TRY
+    if (!D) return 0;
+    cudaStream_t s = c->e.stream;
+    staged_in dp(pts, 32 * nc * D, s); dev_buf o(32 * D, s);
+    int rc = engine_aggregate(c->e, dp.b.as<uint8_t>(), nc, D, init, o.as<uint8_t>());
+    if (rc) return rc;
+    rt_d2h(out, o.p, 32 * D, s); rt_sync(s);
+    return 0;
+    API_CATCH
+}
+extern "C" int rofl_dlog_dev(rofl_ctx *c, const uint8_t *pts, size_t D, uint64_t ts, int bb, int n_bits, int frac, uint8_t *osc, float *of) {
+    API_TRY return engine_dlog(c->e, pts, D, ts, bb, n_bits, frac, osc, of); API_CATCH
+}
+extern "C" int rofl_dlog(rofl_ctx *c, const uint8_t *pts, size_t D, uint64_t ts, int bb, int n_bits, int frac, uint8_t *osc, float *of) {
+    API_TRY
+    if (!D) return 0;
+    cudaStream_t s = c->e.stream;
+    staged_in dp(pts, 32 * D, s); dev_buf o(32 * D, s), f(4 * D, s);
+    int rc = engine_dlog(c->e, dp.b.as<uint8_t>(), D, ts, bb, n_bits, frac, o.as<uint8_t>(), f.as<float>());
+    if (osc) rt_d2h(osc, o.p, 32 * D, s); if (of) rt_d2h(of, f.p, 4 * D, s); rt_sync(s);
+    return rc;
+    API_CATCH
+}

@@ -1,0 +1,648 @@
+// Host orchestration of the rofl_crypto prove / verify hot path on one GPU (C++; the reference's host side is Rust).
+// Mirrors, function for function, the vector API that rofl_service links:
+//   range_proof_vec::{create_rangeproof, verify_rangeproof}      range_proof_vec/mod.rs:16-102,149-191
+//   l2_range_proof_vec::{create_rangeproof_l2, verify_rangeproof_l2}   l2_range_proof_vec/mod.rs:15-140,185-228
+//   square_proof_vec::{create_l2rangeproof_vec_existing, verify_l2rangeproof_vec}   square_proof_vec/mod.rs:19-75,130-160
+//   pedersen_ops::{commit_vec, add_rp_vec_vec, discrete_log_vec_table}, ElGamal R halves, bsgs32::BSGSTable
+// All chunks of one update advance in lock step: one kernel launch per phase covers every chunk, the sequential
+// Fiat-Shamir transcripts (Merlin) stay on the host, one small device<->host exchange per challenge.
+#pragma once
+#include "kernels.cuh"
+#include "rt.cuh"
+#include <map>
+#include <mutex>
+#include <thread>
+#include <algorithm>
+
+enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE = 4, DOM_L2_VERIFY = 5, DOM_CRP = 6, DOM_RND_VEC = 7 };
+enum { PROF_FOLD = 0, PROF_MSM = 1, PROF_COMMIT = 2, PROF_SQUARE = 3, PROF_SLOTS = 8 };
+
+struct gens_entry { int n = 0; int cap = 0; niels_st *G = nullptr, *H = nullptr; };
+struct bsgs_entry { unsigned long long *keys = nullptr; uint32_t *vals = nullptr; uint32_t cap = 0; uint64_t size = 0; };
+struct rofl_engine {
+    int device = 0;
+    cudaStream_t stream = 0;
+    niels_st *tabB = nullptr, *tabH = nullptr;
+    uint8_t B32[32], H32[32];
+    std::map<int, gens_entry> gens;
+    std::map<std::pair<uint64_t, int>, bsgs_entry> bsgs;
+    std::mutex mu;
+    int host_threads = 8;
+};
+
+// ---- small host helpers ---------------------------------------------------------------------------------------------------
+static inline size_t next_pow2_sz(size_t v) { if (v <= 1) return 1; size_t n = v - 1; while (n & (n - 1)) n &= n - 1; return n << 1; }   // range_proof_vec/mod.rs:237-246
+static inline int ilog2_sz(size_t x) { int l = 0; while (((size_t)1 << l) < x) l++; return l; }
+static inline bool fp_ok(int n_bits, int frac) { return (n_bits == 8 || n_bits == 16 || n_bits == 32 || n_bits == 64) && frac >= 0 && frac <= 12; }
+static inline float clip_max_f(int range, int n_bits, int frac) {                  // conversion32.rs:56-60
+    uint64_t raw = (range - 1 >= 64) ? ~0ULL : ((1ULL << (range - 1)) - 1);
+    return fix_to_f32(raw & fix_max(n_bits), frac);
+}
+static inline float l2_clip_max_f(int range, int n_bits, int frac) {               // conversion32.rs:62-64
+    uint64_t raw = (range >= 64) ? ~0ULL : ((1ULL << range) - 1);
+    return fix_to_f32(raw & fix_max(n_bits), frac);
+}
+static inline void derive_key(uint8_t out[32], const uint8_t seed[32], uint32_t domain, uint64_t index) {
+    uint8_t buf[44]; memcpy(buf, seed, 32);
+    for (int i = 0; i < 4; i++) buf[32 + i] = (uint8_t)(domain >> (8 * i));
+    for (int i = 0; i < 8; i++) buf[36 + i] = (uint8_t)(index >> (8 * i));
+    sha3_256(out, buf, 44);
+}
+static inline void key_words(uint32_t w[8], const uint8_t k[32]) { for (int i = 0; i < 8; i++) w[i] = (uint32_t)k[4 * i] | ((uint32_t)k[4 * i + 1] << 8) | ((uint32_t)k[4 * i + 2] << 16) | ((uint32_t)k[4 * i + 3] << 24); }
+static inline void sc_to_st(sc_st &o, const sc &s) { for (int i = 0; i < 8; i++) o.w[i] = s.v[i]; }
+static inline void st_to_sc(sc &s, const sc_st &o) { for (int i = 0; i < 8; i++) s.v[i] = o.w[i]; }
+template <class F> static void parallel_for(size_t n, int threads, F f) {
+    if (n <= 1 || threads <= 1) { for (size_t i = 0; i < n; i++) f(i); return; }
+    size_t nt = std::min<size_t>(threads, n); std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++) th.emplace_back([=] { for (size_t i = t; i < n; i += nt) f(i); });
+    for (auto &x : th) x.join();
+}
+// Montgomery's trick: v[i] <- v[i]^-1 (all non-zero)
+static inline void sc_batch_invert(std::vector<sc> &v) {
+    size_t n = v.size(); if (!n) return;
+    std::vector<sc> pre(n); sc acc; sc_from_u64(acc, 1);
+    for (size_t i = 0; i < n; i++) { pre[i] = acc; sc_mul(acc, acc, v[i]); }
+    sc inv; sc_invert(inv, acc);
+    for (size_t i = n; i-- > 0;) { sc t; sc_mul(t, inv, pre[i]); sc_mul(inv, inv, v[i]); v[i] = t; }
+}
+static inline void ts_challenge_scalar(transcript &t, const char *label, sc &out) { uint8_t b[64]; transcript_challenge(t, label, b, 64); sc_from_bytes_wide(out, b); }
+static inline void ts_append_sc(transcript &t, const char *label, const sc &s) { uint8_t b[32]; sc_tobytes(b, s); transcript_append(t, label, b, 32); }
+static inline bool is_zero32(const uint8_t *b) { uint8_t z = 0; for (int i = 0; i < 32; i++) z |= b[i]; return z == 0; }
+// pow2[b] = s^(2^b), b < 32
+static inline void sc_pow2_table(sc_st *tab, const sc &s) { sc c = s; for (int b = 0; b < 32; b++) { sc_to_st(tab[b], c); sc_mul(c, c, c); } }
+
+// ---- engine lifetime ------------------------------------------------------------------------------------------------------
+static inline void engine_init(rofl_engine &e) {
+    ge_p3 B, H; ge_base(B); ge_compress(e.B32, B);
+    uint8_t h[64]; sha3_512(h, e.B32, 32); ge_from_uniform_bytes(H, h); ge_compress(e.H32, H);     // PedersenGens::default / el_gamal.rs:31-40
+    cudaStream_t s = e.stream;
+    e.tabB = (niels_st *)rt_malloc(sizeof(niels_st) * FB_WINDOWS * FB_ENTRIES, s);
+    e.tabH = (niels_st *)rt_malloc(sizeof(niels_st) * FB_WINDOWS * FB_ENTRIES, s);
+    dev_buf pts(64, s);
+    rt_h2d(pts.as<uint8_t>(), e.B32, 32, s); rt_h2d(pts.as<uint8_t>() + 32, e.H32, 32, s);
+    int nent = FB_WINDOWS * FB_ENTRIES;
+    LAUNCH(k_fb_table_build, dim3((nent + 63) / 64), dim3(64), s, e.tabB, pts.as<uint8_t>());
+    LAUNCH(k_fb_table_build, dim3((nent + 63) / 64), dim3(64), s, e.tabH, pts.as<uint8_t>() + 32);
+    rt_sync(s);
+}
+static inline void engine_destroy(rofl_engine &e) {
+    cudaStream_t s = e.stream;
+    rt_sync(s);
+    rt_free(e.tabB, s); rt_free(e.tabH, s);
+    for (auto &g : e.gens) { rt_free(g.second.G, s); rt_free(g.second.H, s); }
+    for (auto &b : e.bsgs) { rt_free(b.second.keys, s); rt_free(b.second.vals, s); }
+    e.gens.clear(); e.bsgs.clear();
+    rt_sync(s);
+}
+// BulletproofGens::new(n, m): cached per n, capacity grows (the reference rebuilds them per chunk per call,
+// range_proof_vec/mod.rs:126,201)
+static inline gens_entry &engine_gens(rofl_engine &e, int n, int m) {
+    gens_entry &g = e.gens[n];
+    if (g.cap >= m) return g;
+    cudaStream_t s = e.stream;
+    int newcap = std::max(m, g.cap * 2);
+    niels_st *G = (niels_st *)rt_malloc(sizeof(niels_st) * (size_t)n * newcap, s);
+    niels_st *H = (niels_st *)rt_malloc(sizeof(niels_st) * (size_t)n * newcap, s);
+    if (g.cap) { rt_d2d(G, g.G, sizeof(niels_st) * (size_t)n * g.cap, s); rt_d2d(H, g.H, sizeof(niels_st) * (size_t)n * g.cap, s); }
+    int cnt = 2 * (newcap - g.cap);
+    LAUNCH(k_gens_build, dim3((cnt + 63) / 64), dim3(64), s, G, H, n, g.cap, newcap);
+    rt_sync(s);
+    rt_free(g.G, s); rt_free(g.H, s);
+    g.n = n; g.cap = newcap; g.G = G; g.H = H;
+    return g;
+}
+
+// ---- MSM front end ----------------------------------------------------------------------------------------------------------
+static inline void run_msm(rofl_engine &e, const msm_args &a, uint32_t n_msm) {
+    rt_prof_begin(PROF_MSM, e.stream);
+    LAUNCH_COOP(k_msm, dim3(MSM_WINDOWS, n_msm), dim3(MSM_BUCKETS), e.stream, a);
+    rt_prof_end(PROF_MSM, e.stream);
+}
+static inline msm_seg mk_seg(const void *base, uint32_t count, uint32_t stride, int kind) { msm_seg s; s.base = base; s.count = count; s.stride = stride; s.kind = kind; return s; }
+
+// =============================================================================================================================
+// RangeProof::prove_multiple for C chunks in lock step.  All pointers are device pointers except
+// h_proofs (host).  d_vals: C*m shifted values, d_blind: C*m blindings (reduced), d_V32: C*m compressed commitments.
+// label = transcript label ("RangeProof" / "L2RangeProof"); keys = C ChaCha20 keys (host).
+// =============================================================================================================================
+static void prove_chunks(rofl_engine &e, const char *label, int n, int m, int C, const gens_entry &g, const uint64_t *d_vals,
+                         const sc_st *d_blind, const uint8_t *d_V32, const std::vector<uint8_t> &keys, uint8_t *h_proofs) {
+    cudaStream_t s = e.stream;
+    const size_t N = (size_t)n * m, NT = N * C;
+    const int lgN = ilog2_sz(N);
+    const size_t plen = 32 * (9 + 2 * (size_t)lgN);
+    // ---- device scratch
+    dev_buf d_keys(32 * (size_t)C, s), d_sLR(sizeof(sc_st) * 2 * NT, s), d_sums(sizeof(sc_st) * 5 * C, s);
+    { std::vector<uint32_t> kw(8 * (size_t)C); for (int c = 0; c < C; c++) key_words(&kw[8 * c], &keys[32 * c]); rt_h2d(d_keys.p, kw.data(), 32 * (size_t)C, s); }
+    LAUNCH(k_nonces, dim3((unsigned)((NT + 255) / 256)), dim3(256), s, d_sLR.as<sc_st>(), d_keys.as<uint32_t>(), n, m, NT);
+    LAUNCH_COOP(k_party_sums, dim3(C), dim3(256), s, d_sums.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, (const sc_st *)nullptr, n, m, 0);
+    // ---- A
+    const int nbA = (int)std::min<size_t>(64, (N + 511) / 512);
+    dev_buf d_partA(sizeof(p3_st) * (size_t)C * nbA, s), d_AS(64 * (size_t)C, s), d_win(sizeof(p3_st) * MSM_WINDOWS * 2 * (size_t)C, s);
+    LAUNCH_COOP(k_bits_sum, dim3(nbA, C), dim3(128), s, d_partA.as<p3_st>(), d_vals, g.G, g.H, n, m);
+    {
+        finalize_args f = {}; f.partial = d_partA.as<p3_st>(); f.npartial = nbA; f.sHa = d_sums.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
+        f.out32 = d_AS.as<uint8_t>(); f.count = C;
+        LAUNCH(k_finalize, dim3((C + 31) / 32), dim3(32), s, f);
+    }
+    // ---- S = (sum s_bl) H + <s_L, G> + <s_R, H>
+    {
+        msm_args a = {}; a.scalars = d_sLR.as<sc_st>(); a.T = (uint32_t)(2 * N); a.scalar_stride = (uint32_t)(2 * N);
+        a.seg[0] = mk_seg(g.G, (uint32_t)N, 0, 0); a.seg[1] = mk_seg(g.H, (uint32_t)N, 0, 0); a.nseg = 2; a.out = d_win.as<p3_st>();
+        run_msm(e, a, C);
+        finalize_args f = {}; f.windows = d_win.as<p3_st>(); f.sHa = d_sums.as<sc_st>() + C; f.tabB = e.tabB; f.tabH = e.tabH;
+        f.out32 = d_AS.as<uint8_t>() + 32 * (size_t)C; f.count = C;
+        LAUNCH(k_finalize, dim3((C + 31) / 32), dim3(32), s, f);
+    }
+    std::vector<uint8_t> hV(32 * (size_t)C * m), hAS(64 * (size_t)C);
+    rt_d2h(hV.data(), d_V32, hV.size(), s); rt_d2h(hAS.data(), d_AS.p, hAS.size(), s);
+    rt_sync(s);
+    // ---- transcripts: V..., A, S -> y, z
+    std::vector<transcript> ts(C);
+    std::vector<sc> y(C), z(C), yinv(C);
+    parallel_for(C, e.host_threads, [&](size_t c) {
+        transcript &t = ts[c]; transcript_init(t, label);
+        transcript_append(t, "dom-sep", (const uint8_t *)"rangeproof v1", 13);
+        transcript_append_u64(t, "n", (uint64_t)n); transcript_append_u64(t, "m", (uint64_t)m);
+        for (int j = 0; j < m; j++) transcript_append(t, "V", &hV[32 * (c * m + j)], 32);
+        uint8_t *o = h_proofs + plen * c;
+        memcpy(o, &hAS[32 * c], 32); memcpy(o + 32, &hAS[32 * (C + c)], 32);
+        transcript_append(t, "A", o, 32); transcript_append(t, "S", o + 32, 32);
+        ts_challenge_scalar(t, "y", y[c]); ts_challenge_scalar(t, "z", z[c]);
+    });
+    yinv = y; sc_batch_invert(yinv);
+    std::vector<sc_st> h_ypow2(32 * (size_t)C), h_zpow2(32 * (size_t)C), h_yinvpow2(32 * (size_t)C), h_z(C);
+    for (int c = 0; c < C; c++) { sc_pow2_table(&h_ypow2[32 * c], y[c]); sc_pow2_table(&h_zpow2[32 * c], z[c]); sc_pow2_table(&h_yinvpow2[32 * c], yinv[c]); sc_to_st(h_z[c], z[c]); }
+    dev_buf d_ypow2(sizeof(sc_st) * 32 * C, s), d_zpow2(sizeof(sc_st) * 32 * C, s), d_yinvpow2(sizeof(sc_st) * 32 * C, s), d_z(sizeof(sc_st) * C, s);
+    rt_h2d(d_ypow2.p, h_ypow2.data(), sizeof(sc_st) * 32 * C, s); rt_h2d(d_zpow2.p, h_zpow2.data(), sizeof(sc_st) * 32 * C, s);
+    rt_h2d(d_yinvpow2.p, h_yinvpow2.data(), sizeof(sc_st) * 32 * C, s); rt_h2d(d_z.p, h_z.data(), sizeof(sc_st) * C, s);
+    // ---- polynomials
+    const int nbP = (int)std::min<size_t>(256, (N + 255) / 256);
+    dev_buf d_a(sizeof(sc_st) * NT, s), d_b(sizeof(sc_st) * NT, s), d_part(sizeof(sc_st) * 3 * (size_t)C * nbP, s), d_tsum(sizeof(sc_st) * 3 * C, s);
+    LAUNCH_COOP(k_poly, dim3(nbP, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_part.as<sc_st>(), d_vals, d_ypow2.as<sc_st>(), d_zpow2.as<sc_st>(), n, m);
+    LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_tsum.as<sc_st>(), d_part.as<sc_st>(), nbP, 3);
+    LAUNCH_COOP(k_party_sums, dim3(C), dim3(256), s, d_sums.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, d_z.as<sc_st>(), n, m, 1);
+    std::vector<sc_st> h_tsum(3 * (size_t)C), h_sums(5 * (size_t)C);
+    rt_d2h(h_tsum.data(), d_tsum.p, sizeof(sc_st) * 3 * C, s); rt_d2h(h_sums.data(), d_sums.p, sizeof(sc_st) * 5 * C, s);
+    rt_sync(s);
+    std::vector<sc> t0(C), t1(C), t2(C);
+    std::vector<sc_st> h_t12(2 * (size_t)C);
+    for (int c = 0; c < C; c++) {
+        sc tt; st_to_sc(t0[c], h_tsum[c]); st_to_sc(tt, h_tsum[C + c]); st_to_sc(t2[c], h_tsum[2 * C + c]);
+        sc_sub(tt, tt, t0[c]); sc_sub(t1[c], tt, t2[c]);
+        sc_to_st(h_t12[c], t1[c]); sc_to_st(h_t12[C + c], t2[c]);
+    }
+    dev_buf d_t12(sizeof(sc_st) * 2 * C, s), d_T12(64 * (size_t)C, s);
+    rt_h2d(d_t12.p, h_t12.data(), sizeof(sc_st) * 2 * C, s);
+    {
+        finalize_args f = {}; f.sBa = d_t12.as<sc_st>(); f.sHa = d_sums.as<sc_st>() + 2 * C; f.tabB = e.tabB; f.tabH = e.tabH;
+        f.out32 = d_T12.as<uint8_t>(); f.count = 2 * C;
+        LAUNCH(k_finalize, dim3((2 * C + 31) / 32), dim3(32), s, f);
+    }
+    std::vector<uint8_t> hT(64 * (size_t)C);
+    rt_d2h(hT.data(), d_T12.p, hT.size(), s);
+    rt_sync(s);
+    // ---- x, shares, w
+    std::vector<sc> x(C), w(C);
+    std::vector<sc_st> h_x(C), h_w2(2 * (size_t)C);
+    parallel_for(C, e.host_threads, [&](size_t c) {
+        transcript &t = ts[c]; uint8_t *o = h_proofs + plen * c;
+        memcpy(o + 64, &hT[32 * c], 32); memcpy(o + 96, &hT[32 * (C + c)], 32);
+        transcript_append(t, "T_1", o + 64, 32); transcript_append(t, "T_2", o + 96, 32);
+        ts_challenge_scalar(t, "x", x[c]);
+        sc xx, tx, txb, eb, tmp, sa, ss, st1, st2, szg;
+        sc_mul(xx, x[c], x[c]);
+        st_to_sc(sa, h_sums[c]); st_to_sc(ss, h_sums[C + c]); st_to_sc(st1, h_sums[2 * C + c]); st_to_sc(st2, h_sums[3 * C + c]); st_to_sc(szg, h_sums[4 * C + c]);
+        sc_mul(tmp, t1[c], x[c]); sc_add(tx, t0[c], tmp); sc_mul(tmp, t2[c], xx); sc_add(tx, tx, tmp);
+        sc_mul(tmp, st1, x[c]); sc_add(txb, szg, tmp); sc_mul(tmp, st2, xx); sc_add(txb, txb, tmp);
+        sc_mul(tmp, ss, x[c]); sc_add(eb, sa, tmp);
+        sc_tobytes(o + 128, tx); sc_tobytes(o + 160, txb); sc_tobytes(o + 192, eb);
+        transcript_append(t, "t_x", o + 128, 32); transcript_append(t, "t_x_blinding", o + 160, 32); transcript_append(t, "e_blinding", o + 192, 32);
+        ts_challenge_scalar(t, "w", w[c]);
+        transcript_append(t, "dom-sep", (const uint8_t *)"ipp v1", 6); transcript_append_u64(t, "n", (uint64_t)N);
+        sc_to_st(h_x[c], x[c]); sc_to_st(h_w2[c], w[c]); sc_to_st(h_w2[C + c], w[c]);
+    });
+    dev_buf d_x(sizeof(sc_st) * C, s), d_w2(sizeof(sc_st) * 2 * C, s), d_yinv(sizeof(sc_st) * NT, s);
+    rt_h2d(d_x.p, h_x.data(), sizeof(sc_st) * C, s); rt_h2d(d_w2.p, h_w2.data(), sizeof(sc_st) * 2 * C, s);
+    LAUNCH(k_lr, dim3((unsigned)((NT + 255) / 256)), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_yinv.as<sc_st>(), d_x.as<sc_st>(), d_yinvpow2.as<sc_st>(), N, NT);
+    // ---- inner product argument
+    const size_t half = N / 2 ? N / 2 : 1;
+    dev_buf d_Gf(sizeof(p3_st) * half * C, s), d_Hf(sizeof(p3_st) * half * C, s);
+    sc_st *msmL = d_sLR.as<sc_st>(), *msmR = d_sLR.as<sc_st>() + NT;         // s_L / s_R are dead after k_lr: reuse as MSM scalar buffers
+    dev_buf d_cLR(sizeof(sc_st) * 2 * C, s), d_LR(64 * (size_t)C, s), d_u2(sizeof(sc_st) * C, s), d_uinv2(sizeof(sc_st) * C, s), d_nafs(512 * (size_t)C, s);
+    std::vector<sc> uprod(C), uinvprod(C);
+    for (int c = 0; c < C; c++) { sc_from_u64(uprod[c], 1); sc_from_u64(uinvprod[c], 1); }
+    std::vector<uint8_t> hLR(64 * (size_t)C);
+    std::vector<sc> u(C), uinv(C);
+    std::vector<sc_st> h_u2(C), h_uinv2(C); std::vector<int8_t> h_nafs(512 * (size_t)C);
+    int round = 0;
+    for (size_t np = N / 2; np >= 1; np /= 2, round++) {
+        const int nbI = (int)std::min<size_t>(256, (np + 255) / 256);
+        LAUNCH_COOP(k_ipp_scalars, dim3(nbI, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), msmL, msmR, d_part.as<sc_st>(), N, (uint32_t)np);
+        LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_part.as<sc_st>(), nbI, 2);
+        msm_args aL = {}, aR = {};
+        aL.scalars = msmL; aL.T = (uint32_t)(2 * np); aL.scalar_stride = (uint32_t)(2 * np); aL.nseg = 2; aL.out = d_win.as<p3_st>();
+        aR = aL; aR.scalars = msmR; aR.out = d_win.as<p3_st>() + (size_t)C * MSM_WINDOWS;
+        if (round == 0) {
+            aL.seg[0] = mk_seg(g.G + np, (uint32_t)np, 0, 0); aL.seg[1] = mk_seg(g.H, (uint32_t)np, 0, 0);
+            aR.seg[0] = mk_seg(g.G, (uint32_t)np, 0, 0);      aR.seg[1] = mk_seg(g.H + np, (uint32_t)np, 0, 0);
+        } else {
+            aL.seg[0] = mk_seg(d_Gf.as<p3_st>() + np, (uint32_t)np, (uint32_t)half, 1); aL.seg[1] = mk_seg(d_Hf.as<p3_st>(), (uint32_t)np, (uint32_t)half, 1);
+            aR.seg[0] = mk_seg(d_Gf.as<p3_st>(), (uint32_t)np, (uint32_t)half, 1);      aR.seg[1] = mk_seg(d_Hf.as<p3_st>() + np, (uint32_t)np, (uint32_t)half, 1);
+        }
+        run_msm(e, aL, C); run_msm(e, aR, C);
+        {
+            finalize_args f = {}; f.windows = d_win.as<p3_st>(); f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
+            f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
+            LAUNCH(k_finalize, dim3((2 * C + 31) / 32), dim3(32), s, f);
+        }
+        rt_d2h(hLR.data(), d_LR.p, hLR.size(), s);
+        rt_sync(s);
+        parallel_for(C, e.host_threads, [&](size_t c) {
+            transcript &t = ts[c]; uint8_t *o = h_proofs + plen * c + 224 + 64 * round;
+            memcpy(o, &hLR[32 * c], 32); memcpy(o + 32, &hLR[32 * (C + c)], 32);
+            transcript_append(t, "L", o, 32); transcript_append(t, "R", o + 32, 32);
+            ts_challenge_scalar(t, "u", u[c]);
+        });
+        uinv = u; sc_batch_invert(uinv);
+        const int lgnp = ilog2_sz(np);
+        for (int c = 0; c < C; c++) {
+            sc u2, ui2, sH, yp;
+            sc_mul(u2, u[c], u[c]); sc_mul(ui2, uinv[c], uinv[c]);
+            st_to_sc(yp, h_yinvpow2[32 * c + lgnp]); sc_mul(sH, ui2, yp);            // u^-2 y^-np
+            sc_to_st(h_u2[c], u2); sc_to_st(h_uinv2[c], ui2);
+            sc_naf(&h_nafs[512 * c], u2, FOLD_W); sc_naf(&h_nafs[512 * c + 256], sH, FOLD_W);
+            sc_mul(uprod[c], uprod[c], u[c]); sc_mul(uinvprod[c], uinvprod[c], uinv[c]);
+        }
+        rt_h2d(d_u2.p, h_u2.data(), sizeof(sc_st) * C, s); rt_h2d(d_uinv2.p, h_uinv2.data(), sizeof(sc_st) * C, s);
+        LAUNCH(k_ipp_fold_scalars, dim3((unsigned)((np + 255) / 256), C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_u2.as<sc_st>(), d_uinv2.as<sc_st>(), N, (uint32_t)np);
+        if (np >= 2) {
+            rt_h2d(d_nafs.p, h_nafs.data(), h_nafs.size(), s);
+            fold_args fa = {}; fa.Gn = round == 0 ? g.G : nullptr; fa.Hn = round == 0 ? g.H : nullptr;
+            fa.Gf = d_Gf.as<p3_st>(); fa.Hf = d_Hf.as<p3_st>(); fa.nafs = d_nafs.as<int8_t>(); fa.np = (uint32_t)np; fa.stride = (uint32_t)half;
+            rt_prof_begin(PROF_FOLD, s);
+            LAUNCH_COOP(k_ipp_fold_points, dim3((unsigned)((np + 127) / 128), C, 2), dim3(128), s, fa);
+            rt_prof_end(PROF_FOLD, s);
+        }
+    }
+    // ---- final a, b: a = a^ prod u_k, b = b^ prod u_k^-1
+    std::vector<sc_st> h_ab(2 * (size_t)C);
+    for (int c = 0; c < C; c++) { rt_d2h(&h_ab[2 * c], d_a.as<sc_st>() + (size_t)c * N, sizeof(sc_st), s); rt_d2h(&h_ab[2 * c + 1], d_b.as<sc_st>() + (size_t)c * N, sizeof(sc_st), s); }
+    rt_sync(s);
+    for (int c = 0; c < C; c++) {
+        sc a, b; st_to_sc(a, h_ab[2 * c]); st_to_sc(b, h_ab[2 * c + 1]);
+        sc_mul(a, a, uprod[c]); sc_mul(b, b, uinvprod[c]);
+        uint8_t *o = h_proofs + plen * c + 224 + 64 * lgN;
+        sc_tobytes(o, a); sc_tobytes(o + 32, b);
+    }
+}
+
+// =============================================================================================================================
+// range_proof_vec::create_rangeproof (range_proof_vec/mod.rs:16-102).  d_values / d_blind / d_commits are device pointers.
+// returns 0 ok, 2 ValueOutOfRangeError, -1 InvalidBitsize, -2 bad arguments, -98 NaN input (reference panics),
+// -99 non power-of-two chunking (reference panics "Should not get here")
+// =============================================================================================================================
+static int engine_range_prove(rofl_engine &e, const float *d_values, const uint8_t *d_blind, size_t D, int range, size_t n_partition,
+                              int n_bits, int frac, const uint8_t seed[32], uint8_t *h_proofs, size_t *proof_len, size_t *n_proofs, uint8_t *d_commits) {
+    if (!fp_ok(n_bits, frac) || D == 0 || range < 1 || range > n_bits || n_partition == 0) return -2;
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    const size_t Dp = next_pow2_sz(D);
+    const size_t C = std::min(Dp, n_partition), m = Dp / C;                         // :54-55
+    const bool bitsize_ok = (range == 8 || range == 16 || range == 32 || range == 64);
+    const bool chunk_ok = !(m & (m - 1)) && m * C == Dp;
+    dev_buf d_V(32 * Dp, s), d_vals(8 * Dp, s), d_bl(sizeof(sc_st) * Dp, s), d_flags(sizeof(int), s);
+    rt_memset(d_flags.p, 0, sizeof(int), s);
+    commit_args ca = {}; ca.values = d_values; ca.blind = d_blind; ca.D = D; ca.Dp = Dp; ca.n_bits = n_bits; ca.frac = frac;
+    ca.shift_bits = range; ca.mx = clip_max_f(range, n_bits, frac); ca.mn = -ca.mx; ca.tabB = e.tabB; ca.tabH = e.tabH;
+    ca.V = d_V.as<uint8_t>(); ca.C = d_commits; ca.vals = d_vals.as<uint64_t>(); ca.blind_sc = d_bl.as<sc_st>(); ca.flags = d_flags.as<int>();
+    rt_prof_begin(PROF_COMMIT, s);
+    LAUNCH(k_commit, dim3((unsigned)((Dp + 127) / 128)), dim3(128), s, ca);
+    rt_prof_end(PROF_COMMIT, s);
+    int flags = 0; rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_sync(s);
+    if (flags & 2) return 2;                                                         // :26-29
+    if (flags & 1) return -98;
+    if (!bitsize_ok) return -1;
+    if (!chunk_ok) return -99;
+    gens_entry &g = engine_gens(e, range, (int)m);
+    std::vector<uint8_t> keys(32 * C);
+    for (size_t c = 0; c < C; c++) derive_key(&keys[32 * c], seed, DOM_RANGE_PROVE, c);
+    prove_chunks(e, "RangeProof", range, (int)m, (int)C, g, d_vals.as<uint64_t>(), d_bl.as<sc_st>(), d_V.as<uint8_t>(), keys, h_proofs);
+    *proof_len = 32 * (9 + 2 * (size_t)ilog2_sz((size_t)range * m)); *n_proofs = C;
+    return 0;
+}
+
+// =============================================================================================================================
+// RangeProof::verify_multiple for C chunks: d_Vp3 / h_V32 hold C*m (shifted) commitments.
+// verdict[c] = 1 accept / 0 VerificationError.  returns 0 or a negative error (-1 FormatError).
+// =============================================================================================================================
+static int verify_chunks(rofl_engine &e, const char *label, int n, int m, int C, const gens_entry &g, const p3_st *d_Vp3, const uint8_t *h_V32,
+                         const uint8_t *h_proofs, size_t plen, const std::vector<uint8_t> &keys, std::vector<int> &verdict) {
+    cudaStream_t s = e.stream;
+    verdict.assign(C, 0);
+    // RangeProof::from_bytes / InnerProductProof::from_bytes
+    if (plen % 32 || plen < 7 * 32) return -1;
+    size_t ne = plen / 32 - 7;
+    if (ne < 2 || (ne - 2) % 2) return -1;
+    const size_t lg = (ne - 2) / 2; if (lg >= 32) return -1;
+    for (int c = 0; c < C; c++) {
+        const uint8_t *p = h_proofs + plen * c; sc t;
+        for (size_t off : {(size_t)128, (size_t)160, (size_t)192, 224 + 64 * lg, 224 + 64 * lg + 32}) { sc_frombytes(t, p + off); if (!sc_is_canonical(t)) return -1; }
+    }
+    const size_t N = (size_t)n * m;
+    if ((m & (m - 1)) || N != ((size_t)1 << lg)) return 0;                      // verification_scalars: n != 1 << lg_n -> VerificationError (all chunks false)
+    const int lgN = (int)lg, nsmall = 6 + 2 * lgN;
+    const uint32_t T = (uint32_t)(2 * N + m + nsmall);
+    const int chs = 5 + 2 * lgN;
+    std::vector<sc_st> h_chal((size_t)C * chs), h_small((size_t)C * nsmall), h_yinvpow2(32 * (size_t)C), h_zpow2(32 * (size_t)C);
+    std::vector<uint8_t> h_smallpts(32 * (size_t)C * nsmall);
+    std::vector<int> host_ok(C, 1);
+    std::vector<sc> y(C), yinv(C), z(C), x(C), w(C), cc(C);
+    std::vector<std::vector<sc>> u(C, std::vector<sc>(lgN));
+    std::vector<sc> allu; allu.reserve((size_t)C * (lgN + 1));
+    parallel_for(C, e.host_threads, [&](size_t c) {
+        const uint8_t *p = h_proofs + plen * c, *ipp = p + 224;
+        transcript t; transcript_init(t, label);
+        transcript_append(t, "dom-sep", (const uint8_t *)"rangeproof v1", 13);
+        transcript_append_u64(t, "n", (uint64_t)n); transcript_append_u64(t, "m", (uint64_t)m);
+        for (int j = 0; j < m; j++) transcript_append(t, "V", h_V32 + 32 * (c * m + j), 32);
+        int ok = 1;
+        ok &= !is_zero32(p) && !is_zero32(p + 32) && !is_zero32(p + 64) && !is_zero32(p + 96);          // validate_and_append_point
+        transcript_append(t, "A", p, 32); transcript_append(t, "S", p + 32, 32);
+        ts_challenge_scalar(t, "y", y[c]); ts_challenge_scalar(t, "z", z[c]);
+        transcript_append(t, "T_1", p + 64, 32); transcript_append(t, "T_2", p + 96, 32);
+        ts_challenge_scalar(t, "x", x[c]);
+        transcript_append(t, "t_x", p + 128, 32); transcript_append(t, "t_x_blinding", p + 160, 32); transcript_append(t, "e_blinding", p + 192, 32);
+        ts_challenge_scalar(t, "w", w[c]);
+        uint32_t kw[8]; key_words(kw, &keys[32 * c]); nonce_scalar(cc[c], kw, 0);                     // batching scalar c <- rng
+        transcript_append(t, "dom-sep", (const uint8_t *)"ipp v1", 6); transcript_append_u64(t, "n", (uint64_t)N);
+        for (int k = 0; k < lgN; k++) {
+            ok &= !is_zero32(ipp + 64 * k) && !is_zero32(ipp + 64 * k + 32);
+            transcript_append(t, "L", ipp + 64 * k, 32); transcript_append(t, "R", ipp + 64 * k + 32, 32);
+            ts_challenge_scalar(t, "u", u[c][k]);
+        }
+        host_ok[c] = ok;
+        // small points: A S T1 T2 L.. R.. H B
+        uint8_t *sp = &h_smallpts[32 * c * nsmall];
+        memcpy(sp, p, 128);
+        for (int k = 0; k < lgN; k++) { memcpy(sp + 32 * (4 + k), ipp + 64 * k, 32); memcpy(sp + 32 * (4 + lgN + k), ipp + 64 * k + 32, 32); }
+        memcpy(sp + 32 * (4 + 2 * lgN), e.H32, 32); memcpy(sp + 32 * (5 + 2 * lgN), e.B32, 32);
+    });
+    for (int c = 0; c < C; c++) { allu.push_back(y[c]); for (int k = 0; k < lgN; k++) allu.push_back(u[c][k]); }
+    for (auto &v : allu) if (sc_iszero(v)) sc_from_u64(v, 1);                    // (probability 2^-252; keeps the batch inversion defined)
+    sc_batch_invert(allu);
+    parallel_for(C, e.host_threads, [&](size_t c) {
+        const uint8_t *p = h_proofs + plen * c, *ipp = p + 224;
+        const sc *inv = &allu[c * (lgN + 1)];
+        yinv[c] = inv[0];
+        sc t_x, t_xb, e_bl, a, b, zz, tmp, tmp2;
+        sc_frombytes(t_x, p + 128); sc_frombytes(t_xb, p + 160); sc_frombytes(e_bl, p + 192);
+        sc_frombytes(a, ipp + 64 * lgN); sc_frombytes(b, ipp + 64 * lgN + 32);
+        sc_mul(zz, z[c], z[c]);
+        sc_st *ch = &h_chal[c * chs];
+        sc_to_st(ch[0], z[c]); sc_to_st(ch[1], zz); sc_to_st(ch[2], a); sc_to_st(ch[3], b);
+        sc_mul(tmp, cc[c], zz); sc_to_st(ch[4], tmp);
+        sc_st *sm = &h_small[c * nsmall];
+        sc one, cx; sc_from_u64(one, 1); sc_mul(cx, cc[c], x[c]);
+        sc_to_st(sm[0], one); sc_to_st(sm[1], x[c]); sc_to_st(sm[2], cx); sc_mul(tmp, cx, x[c]); sc_to_st(sm[3], tmp);
+        for (int k = 0; k < lgN; k++) {
+            sc_to_st(ch[5 + k], u[c][k]); sc_to_st(ch[5 + lgN + k], inv[1 + k]);
+            sc_mul(tmp, u[c][k], u[c][k]); sc_to_st(sm[4 + k], tmp);
+            sc_mul(tmp, inv[1 + k], inv[1 + k]); sc_to_st(sm[4 + lgN + k], tmp);
+        }
+        sc_mul(tmp, cc[c], t_xb); sc_add(tmp, tmp, e_bl); sc_neg(tmp, tmp); sc_to_st(sm[4 + 2 * lgN], tmp);      // H: -e_bl - c t_x_bl
+        // delta = (z - zz) sum_{i<N} y^i - z^3 (2^n - 1) sum_{j<m} z^j ; sums of powers via prod (1 + s^(2^b))
+        sc_pow2_table(&h_yinvpow2[32 * c], yinv[c]); sc_pow2_table(&h_zpow2[32 * c], z[c]);
+        sc sum_y, sum_z, pw, delta, s2; sc_from_u64(sum_y, 1); sc_from_u64(sum_z, 1);
+        pw = y[c]; for (int bb = 0; bb < lgN; bb++) { sc_add(tmp, one, pw); sc_mul(sum_y, sum_y, tmp); sc_mul(pw, pw, pw); }
+        pw = z[c]; for (int bb = 0; bb < ilog2_sz(m); bb++) { sc_add(tmp, one, pw); sc_mul(sum_z, sum_z, tmp); sc_mul(pw, pw, pw); }
+        sc_from_u64(s2, n == 64 ? ~0ULL : ((1ULL << n) - 1));
+        sc_sub(delta, z[c], zz); sc_mul(delta, delta, sum_y);
+        sc_mul(tmp, zz, z[c]); sc_mul(tmp, tmp, s2); sc_mul(tmp, tmp, sum_z); sc_sub(delta, delta, tmp);
+        sc_mul(tmp, a, b); sc_sub(tmp, t_x, tmp); sc_mul(tmp, w[c], tmp);                                        // w (t_x - a b)
+        sc_sub(tmp2, delta, t_x); sc_mul(tmp2, cc[c], tmp2); sc_add(tmp, tmp, tmp2); sc_to_st(sm[5 + 2 * lgN], tmp);   // B
+    });
+    dev_buf d_chal(sizeof(sc_st) * h_chal.size(), s), d_yinvpow2(sizeof(sc_st) * 32 * C, s), d_zpow2(sizeof(sc_st) * 32 * C, s);
+    dev_buf d_scal(sizeof(sc_st) * (size_t)C * T, s), d_sp32(h_smallpts.size(), s), d_sp(sizeof(p3_st) * (size_t)C * nsmall, s), d_bad(sizeof(int) * C, s);
+    dev_buf d_win(sizeof(p3_st) * MSM_WINDOWS * (size_t)C, s), d_id(sizeof(int) * C, s);
+    rt_h2d(d_chal.p, h_chal.data(), sizeof(sc_st) * h_chal.size(), s);
+    rt_h2d(d_yinvpow2.p, h_yinvpow2.data(), sizeof(sc_st) * 32 * C, s); rt_h2d(d_zpow2.p, h_zpow2.data(), sizeof(sc_st) * 32 * C, s);
+    rt_h2d(d_sp32.p, h_smallpts.data(), h_smallpts.size(), s);
+    rt_memset(d_bad.p, 0, sizeof(int) * C, s);
+    for (int c = 0; c < C; c++) rt_h2d(d_scal.as<sc_st>() + (size_t)c * T + 2 * N + m, &h_small[(size_t)c * nsmall], sizeof(sc_st) * nsmall, s);
+    const int nbV = (int)std::min<size_t>(256, (N + 255) / 256);
+    LAUNCH(k_verify_scalars, dim3(nbV, C), dim3(256), s, d_scal.as<sc_st>(), T, d_chal.as<sc_st>(), chs, d_yinvpow2.as<sc_st>(), d_zpow2.as<sc_st>(), n, m, lgN);
+    LAUNCH(k_decompress, dim3((unsigned)(((size_t)C * nsmall + 127) / 128)), dim3(128), s, d_sp.as<p3_st>(), (uint8_t *)nullptr, d_sp32.as<uint8_t>(), (size_t)C * nsmall, (size_t)C * nsmall, (const p3_st *)nullptr, d_bad.as<int>(), (size_t)nsmall);
+    msm_args a = {}; a.scalars = d_scal.as<sc_st>(); a.T = T; a.scalar_stride = T; a.nseg = 4; a.out = d_win.as<p3_st>();
+    a.seg[0] = mk_seg(g.G, (uint32_t)N, 0, 0); a.seg[1] = mk_seg(g.H, (uint32_t)N, 0, 0);
+    a.seg[2] = mk_seg(d_Vp3, (uint32_t)m, (uint32_t)m, 1); a.seg[3] = mk_seg(d_sp.p, (uint32_t)nsmall, (uint32_t)nsmall, 1);
+    run_msm(e, a, C);
+    finalize_args f = {}; f.windows = d_win.as<p3_st>(); f.tabB = e.tabB; f.tabH = e.tabH; f.is_id = d_id.as<int>(); f.count = C;
+    LAUNCH(k_finalize, dim3((C + 31) / 32), dim3(32), s, f);
+    std::vector<int> h_id(C), h_bad(C);
+    rt_d2h(h_id.data(), d_id.p, sizeof(int) * C, s); rt_d2h(h_bad.data(), d_bad.p, sizeof(int) * C, s);
+    rt_sync(s);
+    for (int c = 0; c < C; c++) verdict[c] = (host_ok[c] && !h_bad[c] && h_id[c]) ? 1 : 0;
+    return 0;
+}
+
+// range_proof_vec::verify_rangeproof (range_proof_vec/mod.rs:149-191).  d_commits: D compressed points (device).
+// returns 1 true, 0 false, -1 FormatError, -2 InvalidBitsize / bad args, -3 InvalidGeneratorsLength, -4 undecodable commitment
+static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t plen, size_t n_proofs, const uint8_t *d_commits, size_t D,
+                               int range, const uint8_t seed[32]) {
+    if (D == 0 || n_proofs == 0 || range < 1 || range > 64) return -2;
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    const size_t Dp = next_pow2_sz(D), m = Dp / n_proofs;                     // :168
+    if (m == 0) return -3;
+    // RangeProof::from_bytes happens when the caller deserialises (params.rs:444-458): format errors come first
+    if (plen % 32 || plen < 7 * 32) return -1;
+    { size_t ne = plen / 32 - 7; if (ne < 2 || (ne - 2) % 2 || (ne - 2) / 2 >= 32) return -1; }
+    if (!(range == 8 || range == 16 || range == 32 || range == 64)) {
+        // scalars must still be canonical for from_bytes to succeed; check then report InvalidBitsize
+        size_t lg = (plen / 32 - 9) / 2;
+        for (size_t c = 0; c < n_proofs; c++) { const uint8_t *p = h_proofs + plen * c; sc t; for (size_t off : {(size_t)128, (size_t)160, (size_t)192, 224 + 64 * lg, 224 + 64 * lg + 32}) { sc_frombytes(t, p + off); if (!sc_is_canonical(t)) return -1; } }
+        return -2;
+    }
+    const size_t C = std::min(n_proofs, (Dp + m - 1) / m);                        // zip(proofs, chunks)
+    dev_buf d_off(sizeof(p3_st), s), d_offs(sizeof(sc_st), s), d_Vp3(sizeof(p3_st) * Dp, s), d_V32(32 * Dp, s), d_bad(sizeof(int), s);
+    { sc o; sc_from_u64(o, 1ULL << (range - 1)); sc_st os; sc_to_st(os, o); rt_h2d(d_offs.p, &os, sizeof(os), s);
+      finalize_args f = {}; f.sBa = d_offs.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH; f.out_p3 = d_off.as<p3_st>(); f.count = 1;
+      LAUNCH(k_finalize, dim3(1), dim3(32), s, f); }
+    rt_memset(d_bad.p, 0, sizeof(int), s);
+    LAUNCH(k_decompress, dim3((unsigned)((Dp + 127) / 128)), dim3(128), s, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), d_commits, D, Dp, d_off.as<p3_st>(), d_bad.as<int>(), Dp);
+    std::vector<uint8_t> hV(32 * Dp); int bad = 0;
+    rt_d2h(hV.data(), d_V32.p, hV.size(), s); rt_d2h(&bad, d_bad.p, sizeof(int), s);
+    rt_sync(s);
+    if (bad) return -4;
+    gens_entry &g = engine_gens(e, range, (int)m);
+    std::vector<uint8_t> keys(32 * C);
+    for (size_t c = 0; c < C; c++) derive_key(&keys[32 * c], seed, DOM_RANGE_VERIFY, c);
+    std::vector<int> verdict;
+    int rc = verify_chunks(e, "RangeProof", range, (int)m, (int)C, g, d_Vp3.as<p3_st>(), hV.data(), h_proofs, plen, keys, verdict);
+    if (rc < 0) return rc;
+    int res = 1; for (int v : verdict) res &= v;                                   // :183-190
+    return res;
+}
+
+// =============================================================================================================================
+// l2_range_proof_vec::create_rangeproof_l2 (l2_range_proof_vec/mod.rs:15-140): one m=1 proof on sum x_i^2 with blinding sum r_i.
+// h_values is a HOST copy of the values: the reference cross-checks the scalar sum against a sequential f32 fold (:44-58)
+// whose rounding depends on the summation order, so that O(D) fold runs on the host exactly as written.
+// returns 0 ok, 2 ValueOutOfRange, 3 OverflowError, 4 NormOutOfRange, -1 InvalidBitsize, -2 bad args
+// =============================================================================================================================
+static int engine_l2_prove(rofl_engine &e, const float *h_values, const float *d_values, const uint8_t *d_blind, size_t D, int range,
+                           int n_bits, int frac, const uint8_t seed[32], uint8_t *h_proof, size_t *proof_len, uint8_t *h_commit) {
+    if (!fp_ok(n_bits, frac) || D == 0 || range < 1) return -2;
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    const float mx = clip_max_f(range, n_bits, frac), mn = -mx;
+    for (size_t i = 0; i < D; i++) if (mn > h_values[i] || h_values[i] > mx) return 2;
+    const int nb = (int)std::min<size_t>(256, (D + 255) / 256);
+    dev_buf d_part(sizeof(sc_st) * 2 * nb, s), d_sum(sizeof(sc_st) * 2, s), d_flags(sizeof(int), s);
+    rt_memset(d_flags.p, 0, sizeof(int), s);
+    LAUNCH_COOP(k_l2_sums, dim3(nb), dim3(256), s, d_part.as<sc_st>(), d_values, d_blind, D, n_bits, frac, d_flags.as<int>());
+    LAUNCH_COOP(k_sc_sum, dim3(1), dim3(256), s, d_sum.as<sc_st>(), d_part.as<sc_st>(), nb, 2);
+    sc_st hs[2]; int flags = 0;
+    rt_d2h(hs, d_sum.p, sizeof(hs), s); rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_sync(s);
+    if (flags & 1) return -98;
+    sc val, bsum; st_to_sc(val, hs[0]); st_to_sc(bsum, hs[1]);
+    // :44-58 sequential f32 cross-check
+    const float shift = (float)(1 << frac); float val_float = 0.0f;
+    for (size_t i = 0; i < D; i++) {
+        sc sx; f32_to_scalar(sx, h_values[i], n_bits, frac);
+        float xq = scalar_to_f32(sx, n_bits, frac), term = xq * xq * shift;
+        val_float = (i == 0) ? term : val_float + term;
+    }
+    const float vf = scalar_to_f32(val, n_bits, frac);
+    if (fabsf(vf - val_float) > 1.1920929e-7f) return 3;
+    if (vf > l2_clip_max_f(range, n_bits, frac)) return 4;
+    if (!(range == 8 || range == 16 || range == 32 || range == 64)) return -1;
+    uint64_t v = (((uint64_t)val.v[1] << 32) | val.v[0]) & fix_max(n_bits);      // :69-73 read_from_bytes
+    // V = v B + bsum H
+    dev_buf d_v(8, s), d_bl(sizeof(sc_st), s), d_vs(sizeof(sc_st), s), d_V(32, s);
+    sc vs; sc_from_u64(vs, v); sc_st t; sc_to_st(t, vs); rt_h2d(d_vs.p, &t, sizeof(t), s);
+    sc_to_st(t, bsum); rt_h2d(d_bl.p, &t, sizeof(t), s); rt_h2d(d_v.p, &v, 8, s);
+    { finalize_args f = {}; f.sBa = d_vs.as<sc_st>(); f.sHa = d_bl.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH; f.out32 = d_V.as<uint8_t>(); f.count = 1;
+      LAUNCH(k_finalize, dim3(1), dim3(32), s, f); }
+    gens_entry &g = engine_gens(e, range, 1);                                     // BulletproofGens::new(64, 1) restricted to n = range (:162)
+    std::vector<uint8_t> keys(32); derive_key(keys.data(), seed, DOM_L2_PROVE, 0);
+    prove_chunks(e, "L2RangeProof", range, 1, 1, g, d_v.as<uint64_t>(), d_bl.as<sc_st>(), d_V.as<uint8_t>(), keys, h_proof);
+    rt_d2h(h_commit, d_V.p, 32, s); rt_sync(s);
+    *proof_len = 32 * (9 + 2 * (size_t)ilog2_sz((size_t)range));
+    return 0;
+}
+// verify_rangeproof_l2 (:185-228)
+static int engine_l2_verify(rofl_engine &e, const uint8_t *h_proof, size_t plen, const uint8_t *h_commit, int range, const uint8_t seed[32]) {
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    if (plen % 32 || plen < 7 * 32) return -1;
+    { size_t ne = plen / 32 - 7; if (ne < 2 || (ne - 2) % 2 || (ne - 2) / 2 >= 32) return -1; }
+    dev_buf d_c(32, s), d_Vp3(sizeof(p3_st), s), d_V32(32, s), d_bad(sizeof(int), s);
+    rt_h2d(d_c.p, h_commit, 32, s); rt_memset(d_bad.p, 0, sizeof(int), s);
+    LAUNCH(k_decompress, dim3(1), dim3(128), s, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), d_c.as<uint8_t>(), (size_t)1, (size_t)1, (const p3_st *)nullptr, d_bad.as<int>(), (size_t)1);
+    uint8_t hV[32]; int bad = 0; rt_d2h(hV, d_V32.p, 32, s); rt_d2h(&bad, d_bad.p, sizeof(int), s); rt_sync(s);
+    if (bad) return -4;
+    if (!(range == 8 || range == 16 || range == 32 || range == 64)) {
+        size_t lg = (plen / 32 - 9) / 2; const uint8_t *p = h_proof; sc t;
+        for (size_t off : {(size_t)128, (size_t)160, (size_t)192, 224 + 64 * lg, 224 + 64 * lg + 32}) { sc_frombytes(t, p + off); if (!sc_is_canonical(t)) return -1; }
+        return -2;
+    }
+    gens_entry &g = engine_gens(e, range, 1);
+    std::vector<uint8_t> keys(32); derive_key(keys.data(), seed, DOM_L2_VERIFY, 0);
+    std::vector<int> verdict;
+    int rc = verify_chunks(e, "L2RangeProof", range, 1, 1, g, d_Vp3.as<p3_st>(), hV, h_proof, plen, keys, verdict);
+    if (rc < 0) return rc;
+    return verdict.empty() ? 0 : verdict[0];
+}
+
+// =============================================================================================================================
+// square_proof_vec::create_l2rangeproof_vec_existing / verify_l2rangeproof_vec (square_proof_vec/mod.rs:19-75,130-160); device pointers
+// =============================================================================================================================
+static int engine_square_prove(rofl_engine &e, const float *d_values, const uint8_t *d_value_com, const uint8_t *d_r1, const uint8_t *d_r2, size_t D,
+                               int n_bits, int frac, const uint8_t seed[32], uint8_t *d_proofs, uint8_t *d_commits) {
+    if (!fp_ok(n_bits, frac)) return -2;
+    if (D == 0) return 0;
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    dev_buf d_flags(sizeof(int), s); rt_memset(d_flags.p, 0, sizeof(int), s);
+    square_args a = {}; a.values = d_values; a.value_com = d_value_com; a.r1 = d_r1; a.r2 = d_r2; a.D = D; a.n_bits = n_bits; a.frac = frac;
+    uint8_t key[32]; derive_key(key, seed, DOM_SQUARE, 0); key_words(a.key, key);
+    a.tabB = e.tabB; a.tabH = e.tabH; a.proofs = d_proofs; a.commits = d_commits; a.flags = d_flags.as<int>();
+    rt_prof_begin(PROF_SQUARE, s);
+    LAUNCH(k_square_prove, dim3((unsigned)((D + 127) / 128)), dim3(128), s, a);
+    rt_prof_end(PROF_SQUARE, s);
+    int flags = 0; rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_sync(s);
+    if (flags & 4) return -4;
+    if (flags & 1) return -98;
+    return 0;
+}
+static int engine_square_verify(rofl_engine &e, const uint8_t *d_proofs, const uint8_t *d_commits, size_t D) {
+    if (D == 0) return 1;
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    dev_buf d_res(2 * sizeof(int), s); int init[2] = {1, 0}; rt_h2d(d_res.p, init, sizeof(init), s);
+    rt_prof_begin(PROF_SQUARE, s);
+    LAUNCH(k_square_verify, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_proofs, d_commits, D, e.tabB, e.tabH, d_res.as<int>());
+    rt_prof_end(PROF_SQUARE, s);
+    int res[2]; rt_d2h(res, d_res.p, sizeof(res), s); rt_sync(s);
+    if (res[1]) return -1;
+    return res[0] ? 1 : 0;
+}
+
+// =============================================================================================================================
+// commitments (pedersen_ops.rs:9-25; el_gamal.rs:57-69), aggregation (params.rs:81-124), discrete log (bsgs32.rs, pedersen_ops.rs:47-53)
+// =============================================================================================================================
+static int engine_commit(rofl_engine &e, const float *d_values, const uint8_t *d_blind, size_t D, int n_bits, int frac, uint8_t *d_L, uint8_t *d_R) {
+    if (!fp_ok(n_bits, frac)) return -2;
+    if (D == 0) return 0;
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    dev_buf d_flags(sizeof(int), s); rt_memset(d_flags.p, 0, sizeof(int), s);
+    commit_args ca = {}; ca.values = d_values; ca.blind = d_blind; ca.D = D; ca.Dp = D; ca.n_bits = n_bits; ca.frac = frac;
+    ca.tabB = e.tabB; ca.tabH = e.tabH; ca.C = d_L; ca.R = d_blind ? d_R : nullptr; ca.flags = d_flags.as<int>();
+    rt_prof_begin(PROF_COMMIT, s);
+    LAUNCH(k_commit, dim3((unsigned)((D + 127) / 128)), dim3(128), s, ca);
+    rt_prof_end(PROF_COMMIT, s);
+    int flags = 0; rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_sync(s);
+    return (flags & 1) ? -98 : 0;
+}
+static int engine_aggregate(rofl_engine &e, const uint8_t *d_pts, size_t n_clients, size_t D, int init_base, uint8_t *d_out) {
+    if (D == 0) return 0;
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    dev_buf d_bad(sizeof(int), s); rt_memset(d_bad.p, 0, sizeof(int), s);
+    LAUNCH(k_aggregate, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_out, d_pts, n_clients, D, init_base, d_bad.as<int>());
+    int bad = 0; rt_d2h(&bad, d_bad.p, sizeof(int), s); rt_sync(s);
+    return bad ? -4 : 0;
+}
+static bsgs_entry &engine_bsgs(rofl_engine &e, uint64_t table_size, int bsgs_bits) {
+    auto key = std::make_pair(table_size, bsgs_bits);
+    auto it = e.bsgs.find(key);
+    if (it != e.bsgs.end()) return it->second;
+    cudaStream_t s = e.stream;
+    bsgs_entry b; b.cap = 1; while (b.cap < 4 * (table_size + 1)) b.cap <<= 1;
+    b.keys = (unsigned long long *)rt_malloc(8 * (size_t)b.cap, s); b.vals = (uint32_t *)rt_malloc(4 * (size_t)b.cap, s);
+    rt_memset(b.keys, 0xff, 8 * (size_t)b.cap, s); rt_memset(b.vals, 0, 4 * (size_t)b.cap, s);
+    dev_buf d_cnt(sizeof(int), s); rt_memset(d_cnt.p, 0, sizeof(int), s);
+    LAUNCH(k_bsgs_build, dim3((unsigned)((table_size + 1 + 127) / 128)), dim3(128), s, b.keys, b.vals, b.cap, (uint32_t)table_size, e.tabB, d_cnt.as<int>());
+    int cnt = 0; rt_d2h(&cnt, d_cnt.p, sizeof(int), s); rt_sync(s);
+    b.size = (uint64_t)cnt - 1;                                                   // get_size (bsgs32.rs:44-46)
+    return e.bsgs[key] = b;
+}
+// returns 0, -4 undecodable point, -5 where the reference panics (no discrete log within range for either sign, bsgs32.rs:69-70)
+static int engine_dlog(rofl_engine &e, const uint8_t *d_pts, size_t D, uint64_t table_size, int bsgs_bits, int n_bits, int frac, uint8_t *d_out_sc, float *d_out_f32) {
+    if (table_size == 0 || table_size > (1ull << 28) || bsgs_bits < 1 || bsgs_bits > 32) return -2;
+    if (D == 0) return 0;
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    bsgs_entry &b = engine_bsgs(e, table_size, bsgs_bits);
+    uint64_t max_it = b.size ? (1ULL << bsgs_bits) / b.size : 0;                  // bsgs32.rs:60-62
+    dev_buf d_flags(sizeof(int), s); rt_memset(d_flags.p, 0, sizeof(int), s);
+    LAUNCH(k_bsgs_solve, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_out_sc, d_out_f32, d_pts, D, b.keys, b.vals, b.cap, (uint32_t)table_size, b.size, max_it,
+           bsgs_bits, n_bits, frac, e.tabB, d_flags.as<int>());
+    int flags = 0; rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_sync(s);
+    if (flags & 4) return -4;
+    if (flags & 8) return -5;
+    return 0;
+}

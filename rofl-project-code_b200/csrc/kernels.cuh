@@ -1,0 +1,754 @@
+// sm_100a kernels of the rofl_crypto prove / verify hot path.
+//
+// Everything in this file is written against plain CUDA C++ (threadIdx/blockIdx, __shared__, __syncthreads,
+// shared-memory atomics) so that tests/hostsim/cuda_emul.h can run the very same kernel bodies on CPU threads in
+// this GPU-less container; on the device they are compiled by nvcc for sm_100a only.  No CPU path ships in the
+// product library.
+//
+// HBM layout (all arrays 16-byte aligned, one record per point/scalar so gathers touch whole sectors):
+//   niels_st  128 B : affine (y+x, y-x, 2dxy) radix-2^25.5 limbs, 30 words + 2 pad   -- fixed generators, tables
+//   p3_st     160 B : extended (X,Y,Z,T), 40 words                                    -- folded generators, partial sums
+//   sc        32 B  : canonical scalar, 8 words
+#pragma once
+#include "devfn.cuh"
+
+#include "rt.cuh"
+#ifndef ROFL_EMUL
+#define KERNEL extern "C" __global__
+#define LB(t, b) __launch_bounds__(t, b)
+#define DEV __device__ __forceinline__
+// host-side launcher defined next to each kernel (the kernels are split over several translation units, see Makefile)
+#define KLAUNCH(k, coop, PARAMS, ARGS) void launch_##k(dim3 g_, dim3 b_, cudaStream_t s_, KL_UNPACK PARAMS) { k<<<g_, b_, 0, s_>>> ARGS; rt_check(cudaGetLastError(), #k); rt_count_launch(#k); }
+#else
+#define KERNEL static
+#define LB(t, b)
+#define DEV inline
+#define KLAUNCH(k, coop, PARAMS, ARGS) void launch_##k(dim3 g_, dim3 b_, cudaStream_t s_, KL_UNPACK PARAMS) { (void)s_; emu_launch(g_, b_, coop, [&] { k ARGS; }); }
+#endif
+#define KL_UNPACK(...) __VA_ARGS__
+// kernel groups: a translation unit defines KG_<GROUP> (or KG_ALL) to get the kernel bodies of that group
+#if defined(KG_ALL)
+#define KG_TABLES 1
+#define KG_COMMIT 1
+#define KG_SCALAR 1
+#define KG_MSM 1
+#define KG_FOLD 1
+#define KG_SQUARE 1
+#define KG_BSGS 1
+#endif
+
+// a point operand that is either a fixed generator (niels) or a variable point (p3)
+HD void acc_add_niels(ge_p3 &acc, const niels_st *p, bool neg) { ge_niels n; ld_niels(n, p); if (neg) ge_msub(acc, acc, n); else ge_madd(acc, acc, n); }
+HD void acc_add_p3(ge_p3 &acc, const p3_st *p, bool neg) { ge_p3 q; ld_p3(q, p); if (neg) ge_sub(acc, acc, q); else ge_add(acc, acc, q); }
+
+// ===================================================================================================================
+// K0: tables
+// ===================================================================================================================
+// fixed-base table of the point with compressed encoding `pt`: entry (w,k) = (k+1) 256^w P  (FB_WINDOWS x FB_ENTRIES)
+#ifdef KG_TABLES
+KERNEL void k_fb_table_build(niels_st *tab, const uint8_t *pt) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= FB_WINDOWS * FB_ENTRIES) return;
+    uint8_t b[32]; for (int i = 0; i < 32; i++) b[i] = pt[i];
+    ge_p3 p; ge_decompress(p, b);
+    ge_niels n; fb_table_entry(n, p, idx / FB_ENTRIES, idx % FB_ENTRIES);
+    st_niels(tab + idx, n);
+}
+KLAUNCH(k_fb_table_build, false, (niels_st *tab, const uint8_t *pt), (tab, pt))
+#endif
+// K3: BulletproofGens (range_proof_vec/mod.rs:126,201 rebuild these per chunk per call; here once per (n, capacity)).
+// one thread per (party, G|H) chain; writes niels records party-major: G[(j*n + i)]
+#ifdef KG_TABLES
+KERNEL void k_gens_build(niels_st *G, niels_st *H, int n, int party_begin, int party_end) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = party_begin + (idx >> 1);
+    if (j >= party_end) return;
+    int which = (idx & 1) ? 'H' : 'G';
+    niels_st *out = ((idx & 1) ? H : G) + (size_t)j * n;
+    gen_chain c; gen_chain_init(c, which, (uint32_t)j);
+    for (int i = 0; i < n; i++) {
+        ge_p3 p; gen_chain_next(c, p);
+        fe zinv; fe_invert(zinv, p.Z);
+        ge_niels q; ge_p3_to_niels(q, p, zinv);
+        st_niels(out + i, q);
+    }
+}
+KLAUNCH(k_gens_build, false, (niels_st *G, niels_st *H, int n, int party_begin, int party_end), (G, H, n, party_begin, party_end))
+#endif
+
+// ===================================================================================================================
+// K1 + K2: f32 -> fixed point -> commitments
+// ===================================================================================================================
+// flags bits: 1 = NaN, 2 = value out of [mn, mx]
+struct commit_args {
+    const float *values;        // D
+    const uint8_t *blind;       // D x 32 or null (zero blinding)
+    size_t D, Dp;               // Dp = padded length (>= D); padding = value 0, blinding 0
+    int n_bits, frac;
+    int shift_bits;             // > 0: range-proof mode, commit to raw + 2^(shift_bits-1) (range_proof_vec/mod.rs:35-43)
+    float mn, mx;               // range check bounds (range-proof mode)
+    const niels_st *tabB, *tabH;
+    uint8_t *V;                 // Dp x 32 compressed commitments to the (shifted) value   (may be null)
+    uint8_t *C;                 // D x 32 compressed un-shifted commitments v*B + r*H        (may be null)
+    uint8_t *R;                 // D x 32 compressed r*B  (ElGamal right halves, el_gamal.rs:57-69)  (may be null)
+    uint64_t *vals;             // Dp shifted values as u64 (may be null)
+    sc_st *blind_sc;            // Dp blindings reduced mod l (may be null)
+    int *flags;
+};
+#ifdef KG_COMMIT
+KERNEL void LB(128, 1) k_commit(commit_args a) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.Dp) return;
+    sc gamma; sc_0(gamma);
+    uint64_t raw = 0; bool neg = false; int fl = 0;
+    if (i < a.D) {
+        float x = a.values[i];
+        if (f32_to_fix(&raw, x, a.n_bits, a.frac)) fl |= 1;
+        neg = x < 0.0f;
+        if (a.shift_bits > 0 && (a.mn > x || x > a.mx)) fl |= 2;
+        if (a.blind) { uint8_t b[32]; ld_bytes32(b, a.blind + 32 * i); sc_from_bytes_mod_order(gamma, b); }
+    }
+    if (fl) atomicOr(a.flags, fl);
+    if (a.blind_sc) st_sc(a.blind_sc + i, gamma);
+    // gamma * H
+    ge_p3 bh; ge_p3_0(bh);
+    if (a.blind) fb_mul_acc(bh, a.tabH, gamma, 32);
+    if (a.shift_bits > 0) {
+        // shifted value: low n_bits of (f32_to_scalar(x) + 2^(shift-1)) mod l
+        uint64_t sh = 0;
+        if (i < a.D) {
+            uint64_t off = 1ULL << (a.shift_bits - 1);
+            if (!neg) sh = (raw + off) & fix_max(a.n_bits);
+            else if (raw <= off) sh = (off - raw) & fix_max(a.n_bits);
+            else { sc s, o; sc_from_u64(s, raw); sc_neg(s, s); sc_from_u64(o, off); sc_add(s, s, o); sh = (((uint64_t)s.v[1] << 32) | s.v[0]) & fix_max(a.n_bits); }
+        }
+        if (a.vals) a.vals[i] = sh;
+        if (a.V) {
+            ge_p3 v = bh; sc s; sc_from_u64(s, sh); fb_mul_acc(v, a.tabB, s, 32);
+            uint8_t out[32]; ge_compress(out, v); st_bytes32(a.V + 32 * i, out);
+        }
+    }
+    if (i < a.D && a.C) {
+        ge_p3 v; ge_p3_0(v); sc s; sc_from_u64(s, raw); fb_mul_acc(v, a.tabB, s, 32);
+        if (neg) ge_neg(v, v);
+        ge_add(v, v, bh);
+        uint8_t out[32]; ge_compress(out, v); st_bytes32(a.C + 32 * i, out);
+    }
+    if (i < a.D && a.R) {
+        ge_p3 v; ge_p3_0(v); fb_mul_acc(v, a.tabB, gamma, 32);
+        uint8_t out[32]; ge_compress(out, v); st_bytes32(a.R + 32 * i, out);
+    }
+}
+KLAUNCH(k_commit, false, (commit_args a), (a))
+#endif
+
+// ===================================================================================================================
+// block-level reductions through shared memory (no warp shuffles: keeps the bodies runnable under cuda_emul.h)
+// ===================================================================================================================
+// sum of one scalar per thread; result valid in thread 0.  `buf` = blockDim.x records of shared memory.
+DEV void block_sum_sc(sc &v, sc_st *buf, int tid, int nthreads) {
+    st_sc(buf + tid, v);
+    __syncthreads();
+    for (int s = nthreads >> 1; s > 0; s >>= 1) {
+        if (tid < s) { sc a, b; ld_sc(a, buf + tid); ld_sc(b, buf + tid + s); sc_add(a, a, b); st_sc(buf + tid, a); }
+        __syncthreads();
+    }
+    ld_sc(v, buf);
+    __syncthreads();
+}
+// sum of one point per thread; result valid in thread 0
+DEV void block_sum_p3(ge_p3 &v, p3_st *buf, int tid, int nthreads) {
+    st_p3(buf + tid, v);
+    __syncthreads();
+    for (int s = nthreads >> 1; s > 0; s >>= 1) {
+        if (tid < s) { ge_p3 a, b; ld_p3(a, buf + tid); ld_p3(b, buf + tid + s); ge_add(a, a, b); st_p3(buf + tid, a); }
+        __syncthreads();
+    }
+    ld_p3(v, buf);
+    __syncthreads();
+}
+
+// ===================================================================================================================
+// K11 + K4/K5 helpers: nonces in the draw order of RangeProof::prove_multiple_with_rng
+//   chunk c uses ChaCha20 key keys[c]; party j draws a_blinding (2n+2)j, s_blinding +1, s_L[i] +2+i, s_R[i] +2+n+i;
+//   after all parties: t1_blinding m(2n+2)+2j, t2_blinding +1.
+// ===================================================================================================================
+// sLR[c][0..N) = s_L, sLR[c][N..2N) = s_R  (one array so that S = <s_L,G> + <s_R,H> is a single 2N-term MSM per chunk)
+#ifdef KG_SCALAR
+KERNEL void LB(256, 2) k_nonces(sc_st *sLR, const uint32_t *keys, int n, int m, size_t total) {
+    size_t gp = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= total) return;
+    size_t N = (size_t)n * m;
+    size_t c = gp / N, k = gp % N, j = k / n, i = k % n;
+    const uint32_t *key = keys + 8 * c;
+    uint32_t kk[8]; for (int t = 0; t < 8; t++) kk[t] = key[t];
+    sc s;
+    nonce_scalar(s, kk, (uint64_t)j * (2 * n + 2) + 2 + i); st_sc(sLR + c * 2 * N + k, s);
+    nonce_scalar(s, kk, (uint64_t)j * (2 * n + 2) + 2 + n + i); st_sc(sLR + c * 2 * N + N + k, s);
+}
+KLAUNCH(k_nonces, false, (sc_st *sLR, const uint32_t *keys, int n, int m, size_t total), (sLR, keys, n, m, total))
+#endif
+// per-chunk sums over parties.  out[q*C + c] (C = gridDim.x): q=0 sum a_bl, 1 sum s_bl, 2 sum t1_bl, 3 sum t2_bl, 4 sum z^(j+2) gamma_j
+// phase 0 computes q=0,1 ; phase 1 computes q=2,3,4 (needs z)
+#ifdef KG_SCALAR
+KERNEL void LB(256, 1) k_party_sums(sc_st *out, const uint32_t *keys, const sc_st *blind, const sc_st *z, int n, int m, int phase) {
+    __shared__ sc_st buf[256];
+    int c = blockIdx.x, tid = threadIdx.x;
+    uint32_t kk[8]; for (int t = 0; t < 8; t++) kk[t] = keys[8 * c + t];
+    sc s0, s1, s2; sc_0(s0); sc_0(s1); sc_0(s2);
+    sc zc, zz; sc_0(zc); sc_0(zz);
+    if (phase == 1) { ld_sc(zc, z + c); sc_mul(zz, zc, zc); }
+    for (int j = tid; j < m; j += blockDim.x) {
+        sc t;
+        if (phase == 0) {
+            nonce_scalar(t, kk, (uint64_t)j * (2 * n + 2)); sc_add(s0, s0, t);
+            nonce_scalar(t, kk, (uint64_t)j * (2 * n + 2) + 1); sc_add(s1, s1, t);
+        } else {
+            uint64_t base = (uint64_t)m * (2 * n + 2);
+            nonce_scalar(t, kk, base + 2 * (uint64_t)j); sc_add(s0, s0, t);
+            nonce_scalar(t, kk, base + 2 * (uint64_t)j + 1); sc_add(s1, s1, t);
+            sc zj, g; sc_pow_u64(zj, zc, (uint64_t)j); sc_mul(zj, zj, zz);
+            ld_sc(g, blind + (size_t)c * m + j); sc_mul(g, g, zj); sc_add(s2, s2, g);
+        }
+    }
+    block_sum_sc(s0, buf, tid, blockDim.x); block_sum_sc(s1, buf, tid, blockDim.x);
+    if (phase == 1) block_sum_sc(s2, buf, tid, blockDim.x);
+    if (tid == 0) {
+        int C = gridDim.x;
+        if (phase == 0) { st_sc(out + 0 * C + c, s0); st_sc(out + 1 * C + c, s1); }
+        else { st_sc(out + 2 * C + c, s0); st_sc(out + 3 * C + c, s1); st_sc(out + 4 * C + c, s2); }
+    }
+}
+KLAUNCH(k_party_sums, true, (sc_st *out, const uint32_t *keys, const sc_st *blind, const sc_st *z, int n, int m, int phase), (out, keys, blind, z, n, m, phase))
+#endif
+
+// ===================================================================================================================
+// K4: A = a_bl*H + sum_k (bit_k ? G_k : -H_k)     (bulletproofs Party::assign_position, aggregated over parties)
+//   grid (blocks_per_chunk, C); partial[c*gridDim.x + blockIdx.x]
+// ===================================================================================================================
+#ifdef KG_MSM
+KERNEL void LB(128, 2) k_bits_sum(p3_st *partial, const uint64_t *vals, const niels_st *G, const niels_st *H, int n, int m) {
+    __shared__ p3_st buf[128];
+    int c = blockIdx.y, tid = threadIdx.x;
+    size_t N = (size_t)n * m;
+    ge_p3 acc; ge_p3_0(acc);
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + tid; k < N; k += (size_t)gridDim.x * blockDim.x) {
+        size_t j = k / n; int i = (int)(k % n);
+        bool bit = (vals[(size_t)c * m + j] >> i) & 1;
+        if (bit) acc_add_niels(acc, G + k, false); else acc_add_niels(acc, H + k, true);
+    }
+    block_sum_p3(acc, buf, tid, blockDim.x);
+    if (tid == 0) st_p3(partial + (size_t)c * gridDim.x + blockIdx.x, acc);
+}
+KLAUNCH(k_bits_sum, true, (p3_st *partial, const uint64_t *vals, const niels_st *G, const niels_st *H, int n, int m), (partial, vals, G, H, n, m))
+#endif
+
+// ===================================================================================================================
+// K4/K6/K7: batched Pippenger multiscalar multiplication, radix 2^8 signed digits, one block per (window, msm).
+//   digit_w(x) = byte_w(x + 0x7f7f..7f) - 127  in [-127, 128]   (unique signed-digit recoding, no carries to track)
+//   bucket |d| is owned by thread |d|-1; per tile the terms are counting-sorted by bucket in shared memory so each
+//   thread walks only its own list; bucket sums are combined by a suffix scan + tree sum in shared memory.
+// ===================================================================================================================
+#define MSM_WINDOWS 32
+#define MSM_BUCKETS 128
+#define MSM_TILE 8192
+struct msm_seg { const void *base; uint32_t count; uint32_t stride; int kind; };     // kind 0 = niels_st, 1 = p3_st; stride = records per msm (0: shared)
+struct msm_args {
+    const sc_st *scalars; uint32_t T; uint32_t scalar_stride;    // scalars[msm*scalar_stride + t]
+    msm_seg seg[4]; int nseg;
+    p3_st *out;                                                  // out[msm*MSM_WINDOWS + w]
+};
+HD int msm_digit(const sc &x, int w) {
+    // byte w of x + K, K = 0x7f repeated; x < 2^253 so no overflow out of 256 bits
+    uint64_t c = 0; uint32_t word = 0;
+    for (int i = 0; i <= (w >> 2); i++) { c += (uint64_t)x.v[i] + 0x7f7f7f7fu; word = (uint32_t)c; c >>= 32; }
+    return (int)((word >> (8 * (w & 3))) & 0xff) - 127;
+}
+HD void msm_add_term(ge_p3 &acc, const msm_args &a, uint32_t msm, uint32_t t, bool neg) {
+    uint32_t start = 0;
+    for (int s = 0; s < a.nseg; s++) {
+        const msm_seg &g = a.seg[s];
+        if (t < start + g.count) {
+            size_t rec = (size_t)msm * g.stride + (t - start);
+            if (g.kind == 0) acc_add_niels(acc, (const niels_st *)g.base + rec, neg);
+            else acc_add_p3(acc, (const p3_st *)g.base + rec, neg);
+            return;
+        }
+        start += g.count;
+    }
+}
+#ifdef KG_MSM
+KERNEL void LB(128, 2) k_msm(msm_args a) {
+    __shared__ uint16_t sorted[MSM_TILE];
+    __shared__ int cnt[MSM_BUCKETS + 1], off[MSM_BUCKETS + 2], cur[MSM_BUCKETS + 1];
+    __shared__ p3_st bk[MSM_BUCKETS];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const uint32_t msm = blockIdx.y;
+    const sc_st *scal = a.scalars + (size_t)msm * a.scalar_stride;
+    ge_p3 acc; ge_p3_0(acc);
+    for (uint32_t tile = 0; tile < a.T; tile += MSM_TILE) {
+        uint32_t nt = a.T - tile < MSM_TILE ? a.T - tile : MSM_TILE;
+        cnt[tid + 1] = 0; if (tid == 0) cnt[0] = 0;
+        __syncthreads();
+        for (uint32_t t = tid; t < nt; t += MSM_BUCKETS) {
+            sc x; ld_sc(x, scal + tile + t);
+            int d = msm_digit(x, w);
+            if (d != 0) atomicAdd(&cnt[d > 0 ? d : -d], 1);
+        }
+        __syncthreads();
+        if (tid == 0) { int o = 0; for (int b = 1; b <= MSM_BUCKETS; b++) { off[b] = o; cur[b] = o; o += cnt[b]; } off[MSM_BUCKETS + 1] = o; }
+        __syncthreads();
+        for (uint32_t t = tid; t < nt; t += MSM_BUCKETS) {
+            sc x; ld_sc(x, scal + tile + t);
+            int d = msm_digit(x, w);
+            if (d != 0) { int p = atomicAdd(&cur[d > 0 ? d : -d], 1); sorted[p] = (uint16_t)(t | (d < 0 ? 0x8000u : 0u)); }
+        }
+        __syncthreads();
+        int b = tid + 1;
+        for (int e = off[b]; e < off[b + 1]; e++) {
+            uint32_t ent = sorted[e];
+            msm_add_term(acc, a, msm, tile + (ent & 0x7fffu), (ent >> 15) != 0);
+        }
+        __syncthreads();
+    }
+    // sum_b b*acc_b: suffix sums then total
+    st_p3(bk + tid, acc);
+    __syncthreads();
+    for (int s = 1; s < MSM_BUCKETS; s <<= 1) {
+        ge_p3 x, y; bool act = tid + s < MSM_BUCKETS;
+        if (act) { ld_p3(x, bk + tid); ld_p3(y, bk + tid + s); ge_add(x, x, y); }
+        __syncthreads();
+        if (act) st_p3(bk + tid, x);
+        __syncthreads();
+    }
+    for (int s = MSM_BUCKETS >> 1; s > 0; s >>= 1) {
+        if (tid < s) { ge_p3 x, y; ld_p3(x, bk + tid); ld_p3(y, bk + tid + s); ge_add(x, x, y); st_p3(bk + tid, x); }
+        __syncthreads();
+    }
+    if (tid == 0) { ge_p3 r; ld_p3(r, bk); st_p3(a.out + (size_t)msm * MSM_WINDOWS + w, r); }
+}
+KLAUNCH(k_msm, true, (msm_args a), (a))
+#endif
+
+// combine: R = sum_w 256^w W_w (+ sum of `npartial` extra points) (+ sB*B + sH*H), one thread per output.
+//   sB = sBa[idx] (* sBb[idx] if sBb), same for sH; any pointer may be null.
+//   out32: compressed result (nullable); out_p3: extended result (nullable); is_id: 1 if the result is the identity (nullable)
+struct finalize_args {
+    const p3_st *windows;          // [count][MSM_WINDOWS] or null
+    const p3_st *partial; int npartial;     // [count][npartial] or null
+    const sc_st *sBa, *sBb, *sHa, *sHb;
+    const niels_st *tabB, *tabH;
+    uint8_t *out32; p3_st *out_p3; int *is_id;
+    int count;
+};
+#ifdef KG_MSM
+KERNEL void LB(32, 1) k_finalize(finalize_args a) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.count) return;
+    ge_p3 r; ge_p3_0(r);
+    if (a.windows) {
+        ld_p3(r, a.windows + (size_t)idx * MSM_WINDOWS + MSM_WINDOWS - 1);
+        for (int w = MSM_WINDOWS - 2; w >= 0; w--) {
+            ge_p2 q; ge_p1p1 t;
+            ge_dbl_p1p1(t, r.X, r.Y, r.Z); ge_dbl_fix(t); ge_p1p1_to_p2(q, t);
+            for (int k = 0; k < 6; k++) { ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); ge_p1p1_to_p2(q, t); }
+            ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); ge_p1p1_to_p3(r, t);
+            acc_add_p3(r, a.windows + (size_t)idx * MSM_WINDOWS + w, false);
+        }
+    }
+    for (int k = 0; k < a.npartial; k++) acc_add_p3(r, a.partial + (size_t)idx * a.npartial + k, false);
+    if (a.sBa) { sc s; ld_sc(s, a.sBa + idx); if (a.sBb) { sc t; ld_sc(t, a.sBb + idx); sc_mul(s, s, t); } fb_mul_acc(r, a.tabB, s, 32); }
+    if (a.sHa) { sc s; ld_sc(s, a.sHa + idx); if (a.sHb) { sc t; ld_sc(t, a.sHb + idx); sc_mul(s, s, t); } fb_mul_acc(r, a.tabH, s, 32); }
+    if (a.out32) { uint8_t o[32]; ge_compress(o, r); st_bytes32(a.out32 + 32 * (size_t)idx, o); }
+    if (a.out_p3) st_p3(a.out_p3 + idx, r);
+    if (a.is_id) a.is_id[idx] = ge_is_identity(r) ? 1 : 0;
+}
+KLAUNCH(k_finalize, false, (finalize_args a), (a))
+#endif
+
+// ===================================================================================================================
+// K5: polynomial vectors of the range proof, per position k = j*n + i of chunk c:
+//   l0 = aL - z, l1 = sL, r0 = y^k (aL - 1 + z) + z^(j+2) 2^i, r1 = y^k sR;  partial sums t0 = <l0,r0>, t2 = <l1,r1>,
+//   t1' = <l0+l1, r0+r1>.   ypow2[c*32+b] = y^(2^b), zpow2 likewise.  r1 overwrites sR.
+//   partial[(c*gridDim.x + blockIdx.x)*3 + q]
+// ===================================================================================================================
+HD void sc_pow_tab(sc &r, const sc_st *pow2, uint64_t e) {
+    sc_from_u64(r, 1);
+    for (int b = 0; e; b++, e >>= 1) if (e & 1) { sc t; ld_sc(t, pow2 + b); sc_mul(r, r, t); }
+}
+#ifdef KG_SCALAR
+KERNEL void LB(256, 1) k_poly(sc_st *l0, sc_st *r0, sc_st *sLR, sc_st *partial, const uint64_t *vals,
+                             const sc_st *ypow2, const sc_st *zpow2, int n, int m) {
+    __shared__ sc_st buf[256];
+    int c = blockIdx.y, tid = threadIdx.x;
+    size_t N = (size_t)n * m;
+    sc z, zz, one; ld_sc(z, zpow2 + 32 * c); ld_sc(zz, zpow2 + 32 * c + 1); sc_from_u64(one, 1);
+    sc t0, t1, t2; sc_0(t0); sc_0(t1); sc_0(t2);
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + tid; k < N; k += (size_t)gridDim.x * blockDim.x) {
+        size_t j = k / n; int i = (int)(k % n); size_t gp = (size_t)c * N + k;
+        sc ey, ozz, aL, a, b, rr0, rr1, ll0, ll1, e2;
+        sc_pow_tab(ey, ypow2 + 32 * c, k);
+        sc_pow_tab(ozz, zpow2 + 32 * c, j); sc_mul(ozz, ozz, zz);
+        sc_from_u64(aL, (vals[(size_t)c * m + j] >> i) & 1);
+        sc_sub(ll0, aL, z);
+        sc_sub(a, aL, one); sc_add(a, a, z); sc_mul(rr0, ey, a);
+        sc_from_u64(e2, 1ULL << i); sc_mul(b, ozz, e2); sc_add(rr0, rr0, b);
+        sc_st *sLc = sLR + (size_t)c * 2 * N, *sRc = sLc + N;
+        ld_sc(rr1, sRc + k); sc_mul(rr1, ey, rr1);
+        ld_sc(ll1, sLc + k);
+        st_sc(l0 + gp, ll0); st_sc(r0 + gp, rr0); st_sc(sRc + k, rr1);
+        sc_mul(a, ll0, rr0); sc_add(t0, t0, a);
+        sc_mul(a, ll1, rr1); sc_add(t2, t2, a);
+        sc_add(a, ll0, ll1); sc_add(b, rr0, rr1); sc_mul(a, a, b); sc_add(t1, t1, a);
+    }
+    block_sum_sc(t0, buf, tid, blockDim.x); block_sum_sc(t1, buf, tid, blockDim.x); block_sum_sc(t2, buf, tid, blockDim.x);
+    if (tid == 0) { sc_st *o = partial + ((size_t)c * gridDim.x + blockIdx.x) * 3; st_sc(o, t0); st_sc(o + 1, t1); st_sc(o + 2, t2); }
+}
+KLAUNCH(k_poly, true, (sc_st *l0, sc_st *r0, sc_st *sLR, sc_st *partial, const uint64_t *vals, const sc_st *ypow2, const sc_st *zpow2, int n, int m), (l0, r0, sLR, partial, vals, ypow2, zpow2, n, m))
+#endif
+// out[s*C + c] = sum_{b < cnt} in[(c*cnt + b)*q + s]   (second stage of the block partial sums; C = gridDim.x)
+#ifdef KG_SCALAR
+KERNEL void LB(256, 1) k_sc_sum(sc_st *out, const sc_st *in, int cnt, int q) {
+    __shared__ sc_st buf[256];
+    int c = blockIdx.x, tid = threadIdx.x;
+    for (int s = 0; s < q; s++) {
+        sc acc; sc_0(acc);
+        for (int b = tid; b < cnt; b += blockDim.x) { sc t; ld_sc(t, in + ((size_t)c * cnt + b) * q + s); sc_add(acc, acc, t); }
+        block_sum_sc(acc, buf, tid, blockDim.x);
+        if (tid == 0) st_sc(out + (size_t)s * gridDim.x + c, acc);
+    }
+}
+KLAUNCH(k_sc_sum, true, (sc_st *out, const sc_st *in, int cnt, int q), (out, in, cnt, q))
+#endif
+// l = l0 + x sL (into l0), r = r0 + x r1 (into r0), yinv[k] = y^-k     
+#ifdef KG_SCALAR
+KERNEL void LB(256, 2) k_lr(sc_st *l0, sc_st *r0, const sc_st *sLR, sc_st *yinv, const sc_st *x, const sc_st *yinvpow2, size_t N, size_t total) {
+    size_t gp = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= total) return;
+    size_t c = gp / N, k = gp % N;
+    sc xc, a, b; ld_sc(xc, x + c);
+    ld_sc(a, sLR + c * 2 * N + k); sc_mul(a, a, xc); ld_sc(b, l0 + gp); sc_add(a, a, b); st_sc(l0 + gp, a);
+    ld_sc(a, sLR + c * 2 * N + N + k); sc_mul(a, a, xc); ld_sc(b, r0 + gp); sc_add(a, a, b); st_sc(r0 + gp, a);
+    sc_pow_tab(a, yinvpow2 + 32 * c, k); st_sc(yinv + gp, a);
+}
+KLAUNCH(k_lr, false, (sc_st *l0, sc_st *r0, const sc_st *sLR, sc_st *yinv, const sc_st *x, const sc_st *yinvpow2, size_t N, size_t total), (l0, r0, sLR, yinv, x, yinvpow2, N, total))
+#endif
+
+// ===================================================================================================================
+// K6: inner-product argument, one round for every chunk in lock step, in the "lazy factor" form:
+//   with fG = prod u_k^-1, fH = prod u_k the true vectors are a = a^ / fG, b = b^ / fH, G = fG G", H_i = y^-i fH H"_i,
+//   so  <a_L,b_R> = <a^_L, b^_R>,  L = <a^_L, G"_R> + <b^_R y^-i, H"_L> + c_L w B   and the folds need ONE scalar each:
+//   a^ <- a^_L + u^-2 a^_R,  b^ <- b^_L + u^2 b^_R,  G" <- G"_L + u^2 G"_R,  H" <- H"_L + (u^-2 y^-n') H"_R.
+//   Every L_k, R_k is the same group element the reference computes, so the compressed proof bytes are identical.
+// ===================================================================================================================
+// grid (blocks, C): msmL[c*2n' + ..], msmR[...], partial[(c*gridDim.x+blk)*2 + {cL,cR}]
+#ifdef KG_SCALAR
+KERNEL void LB(256, 1) k_ipp_scalars(const sc_st *a, const sc_st *b, const sc_st *yinv, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np) {
+    __shared__ sc_st buf[256];
+    int c = blockIdx.y, tid = threadIdx.x;
+    const sc_st *ac = a + (size_t)c * N, *bc = b + (size_t)c * N, *yc = yinv + (size_t)c * N;
+    sc cL, cR; sc_0(cL); sc_0(cR);
+    for (uint32_t i = blockIdx.x * blockDim.x + tid; i < np; i += gridDim.x * blockDim.x) {
+        sc alo, ahi, blo, bhi, ylo, yhi, t;
+        ld_sc(alo, ac + i); ld_sc(ahi, ac + np + i); ld_sc(blo, bc + i); ld_sc(bhi, bc + np + i); ld_sc(ylo, yc + i); ld_sc(yhi, yc + np + i);
+        sc_mul(t, alo, bhi); sc_add(cL, cL, t);
+        sc_mul(t, ahi, blo); sc_add(cR, cR, t);
+        st_sc(msmL + (size_t)c * 2 * np + i, alo);
+        sc_mul(t, bhi, ylo); st_sc(msmL + (size_t)c * 2 * np + np + i, t);
+        st_sc(msmR + (size_t)c * 2 * np + i, ahi);
+        sc_mul(t, blo, yhi); st_sc(msmR + (size_t)c * 2 * np + np + i, t);
+    }
+    block_sum_sc(cL, buf, tid, blockDim.x); block_sum_sc(cR, buf, tid, blockDim.x);
+    if (tid == 0) { sc_st *o = partial + ((size_t)c * gridDim.x + blockIdx.x) * 2; st_sc(o, cL); st_sc(o + 1, cR); }
+}
+KLAUNCH(k_ipp_scalars, true, (const sc_st *a, const sc_st *b, const sc_st *yinv, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np), (a, b, yinv, msmL, msmR, partial, N, np))
+#endif
+// a^[i] += uinv2[c] a^[np+i],  b^[i] += u2[c] b^[np+i]
+#ifdef KG_SCALAR
+KERNEL void LB(256, 2) k_ipp_fold_scalars(sc_st *a, sc_st *b, const sc_st *u2, const sc_st *uinv2, size_t N, uint32_t np) {
+    int c = blockIdx.y;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    sc_st *ac = a + (size_t)c * N, *bc = b + (size_t)c * N;
+    sc s, lo, hi;
+    ld_sc(s, uinv2 + c); ld_sc(lo, ac + i); ld_sc(hi, ac + np + i); sc_mul(hi, hi, s); sc_add(lo, lo, hi); st_sc(ac + i, lo);
+    ld_sc(s, u2 + c); ld_sc(lo, bc + i); ld_sc(hi, bc + np + i); sc_mul(hi, hi, s); sc_add(lo, lo, hi); st_sc(bc + i, lo);
+}
+KLAUNCH(k_ipp_fold_scalars, false, (sc_st *a, sc_st *b, const sc_st *u2, const sc_st *uinv2, size_t N, uint32_t np), (a, b, u2, uinv2, N, np))
+#endif
+// generator fold: out[c][i] = P[i] + s_c * P[np + i], s_c given as width-FOLD_W NAF nafs[(c*2 + which)*256 ..]
+//   grid (blocks, C, 2): z = 0 folds G (scalar u^2), z = 1 folds H (scalar u^-2 y^-np).
+//   first round: in = shared niels generators (in_stride 0); later rounds: in == out (p3, in place, stride = out_stride)
+#define FOLD_W 5
+struct fold_args {
+    const niels_st *Gn, *Hn;       // first round sources (or null)
+    p3_st *Gf, *Hf;                // folded generators [C][stride]
+    const int8_t *nafs;
+    uint32_t np, stride;
+};
+#ifdef KG_FOLD
+KERNEL void LB(128, 3) k_ipp_fold_points(fold_args a) {
+    __shared__ int8_t naf[256];
+    int c = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
+    for (int t = tid; t < 256; t += blockDim.x) naf[t] = a.nafs[((size_t)c * 2 + which) * 256 + t];
+    __syncthreads();
+    uint32_t i = blockIdx.x * blockDim.x + tid;
+    if (i >= a.np) return;
+    ge_p3 lo, hi, r;
+    p3_st *dst = (which ? a.Hf : a.Gf) + (size_t)c * a.stride;
+    if (a.Gn) {
+        const niels_st *src = which ? a.Hn : a.Gn;
+        ge_niels nl, nh; ld_niels(nl, src + i); ld_niels(nh, src + a.np + i);
+        ge_niels_to_p3(lo, nl); ge_niels_to_p3(hi, nh);
+    } else { ld_p3(lo, dst + i); ld_p3(hi, dst + a.np + i); }
+    ge_fold(r, naf, lo, hi, FOLD_W);
+    st_p3(dst + i, r);
+}
+KLAUNCH(k_ipp_fold_points, true, (fold_args a), (a))
+#endif
+
+// ===================================================================================================================
+// K7: verifier side (RangeProof::verify_multiple)
+// ===================================================================================================================
+// decompress `count` encodings; optionally add a fixed point (offset, as p3) -- verify_rangeproof shifts every
+// commitment by 2^(n-1) B (range_proof_vec/mod.rs:155-160) and pads with the identity (:163-165).
+//   in: count_in encodings; out p3 [count_out] (entries >= count_in are the identity); out32: compressed shifted points
+//   bad[i / bad_group] is set to 1 if encoding i fails to decode
+#ifdef KG_COMMIT
+KERNEL void LB(128, 2) k_decompress(p3_st *out, uint8_t *out32, const uint8_t *in, size_t count_in, size_t count_out, const p3_st *offset, int *bad, size_t bad_group) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count_out) return;
+    ge_p3 p; ge_p3_0(p);
+    if (i < count_in) {
+        uint8_t b[32]; ld_bytes32(b, in + 32 * i);
+        if (!ge_decompress(p, b)) { atomicOr(bad + i / bad_group, 1); ge_p3_0(p); }
+        if (offset) { ge_p3 o; ld_p3(o, offset); ge_add(p, p, o); }
+    }
+    st_p3(out + i, p);
+    if (out32) { uint8_t o[32]; ge_compress(o, p); st_bytes32(out32 + 32 * i, o); }
+}
+KLAUNCH(k_decompress, false, (p3_st *out, uint8_t *out32, const uint8_t *in, size_t count_in, size_t count_out, const p3_st *offset, int *bad, size_t bad_group), (out, out32, in, count_in, count_out, offset, bad, bad_group))
+#endif
+// per-chunk challenge block prepared by the host (all canonical scalars):
+//   [0] z  [1] z^2  [2] a  [3] b  [4] c*z^2  [5..5+lgN) u_k  [5+lgN..5+2lgN) u_k^-1 ; ypow2inv[c*32+b] = y^-(2^b), zpow2[c*32+b] = z^(2^b)
+// output scalars[c][0..N) = g_k = -z - a s_k ; [N..2N) = h_k = z + y^-k (z^2 z^j 2^i - b s_k^-1) ; [2N..2N+m) = c z^2 z^j
+#ifdef KG_SCALAR
+KERNEL void LB(256, 1) k_verify_scalars(sc_st *scalars, uint32_t scalar_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int n, int m, int lgN) {
+    int c = blockIdx.y;
+    size_t N = (size_t)n * m;
+    const sc_st *ch = chal + (size_t)c * chal_stride;
+    sc z, zz, a, b; ld_sc(z, ch); ld_sc(zz, ch + 1); ld_sc(a, ch + 2); ld_sc(b, ch + 3);
+    sc_st *out = scalars + (size_t)c * scalar_stride;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
+        size_t j = k / n; int i = (int)(k % n);
+        sc s, sinv; sc_from_u64(s, 1); sc_from_u64(sinv, 1);
+        for (int t = 0; t < lgN; t++) {
+            sc u, ui; ld_sc(u, ch + 5 + t); ld_sc(ui, ch + 5 + lgN + t);
+            bool bit = (k >> (lgN - 1 - t)) & 1;
+            sc_mul(s, s, bit ? u : ui); sc_mul(sinv, sinv, bit ? ui : u);
+        }
+        sc g, h, t1, t2;
+        sc_mul(g, a, s); sc_add(g, g, z); sc_neg(g, g);
+        sc_pow_tab(t1, zpow2 + 32 * c, j); sc_mul(t1, t1, zz); sc_from_u64(t2, 1ULL << i); sc_mul(t1, t1, t2);
+        sc_mul(t2, b, sinv); sc_sub(t1, t1, t2);
+        sc_pow_tab(t2, yinvpow2 + 32 * c, k); sc_mul(t1, t1, t2); sc_add(h, z, t1);
+        st_sc(out + k, g); st_sc(out + N + k, h);
+        if (i == 0) { sc czz; ld_sc(czz, ch + 4); sc_pow_tab(t1, zpow2 + 32 * c, j); sc_mul(t1, t1, czz); st_sc(out + 2 * N + j, t1); }
+    }
+}
+KLAUNCH(k_verify_scalars, false, (sc_st *scalars, uint32_t scalar_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int n, int m, int lgN), (scalars, scalar_stride, chal, chal_stride, yinvpow2, zpow2, n, m, lgN))
+#endif
+
+// ===================================================================================================================
+// K8: per-element square proofs (square_proof_vec/mod.rs)
+// ===================================================================================================================
+struct square_args {
+    const float *values; const uint8_t *value_com, *r1, *r2; size_t D; int n_bits, frac;
+    uint32_t key[8];
+    const niels_st *tabB, *tabH;
+    uint8_t *proofs, *commits;     // D x 160, D x 64
+    int *flags;                    // bit 1 NaN, bit 4 bad point
+};
+#ifdef KG_SQUARE
+KERNEL void LB(128, 1) k_square_prove(square_args a) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.D) return;
+    uint8_t cl[32], r1[32], r2[32], proof[160], com[64];
+    ld_bytes32(cl, a.value_com + 32 * i); ld_bytes32(r1, a.r1 + 32 * i); ld_bytes32(r2, a.r2 + 32 * i);
+    int rc = square_prove_one(proof, com, a.values[i], cl, r1, r2, a.key, (uint64_t)i, a.n_bits, a.frac, a.tabB, a.tabH);
+    if (rc) { atomicOr(a.flags, rc == -1 ? 1 : 4); return; }
+    for (int k = 0; k < 5; k++) st_bytes32(a.proofs + 160 * i + 32 * k, proof + 32 * k);
+    st_bytes32(a.commits + 64 * i, com); st_bytes32(a.commits + 64 * i + 32, com + 32);
+}
+KLAUNCH(k_square_prove, false, (square_args a), (a))
+#endif
+// result[0] &= all valid ; result[1] |= format error
+#ifdef KG_SQUARE
+KERNEL void LB(128, 1) k_square_verify(const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    uint8_t proof[160], com[64];
+    for (int k = 0; k < 5; k++) ld_bytes32(proof + 32 * k, proofs + 160 * i + 32 * k);
+    ld_bytes32(com, commits + 64 * i); ld_bytes32(com + 32, commits + 64 * i + 32);
+    int rc = square_verify_one(proof, com, tabB, tabH);
+    if (rc < 0) atomicOr(result + 1, 1);
+    else if (rc == 0) atomicAnd(result, 0);
+}
+KLAUNCH(k_square_verify, false, (const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result), (proofs, commits, D, tabB, tabH, result))
+#endif
+
+// ===================================================================================================================
+// K9: homomorphic aggregation over clients (params.rs:81-124, pedersen_ops.rs:56-69); pts[client][D] compressed
+// ===================================================================================================================
+#ifdef KG_COMMIT
+KERNEL void LB(128, 2) k_aggregate(uint8_t *out, const uint8_t *pts, size_t n_clients, size_t D, int init_base, int *bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    ge_p3 acc; if (init_base) ge_base(acc); else ge_p3_0(acc);
+    for (size_t c = 0; c < n_clients; c++) {
+        uint8_t b[32]; ld_bytes32(b, pts + 32 * (c * D + i));
+        ge_p3 p; if (!ge_decompress(p, b)) { atomicOr(bad, 1); continue; }
+        ge_add(acc, acc, p);
+    }
+    uint8_t o[32]; ge_compress(o, acc); st_bytes32(out + 32 * i, o);
+}
+KLAUNCH(k_aggregate, false, (uint8_t *out, const uint8_t *pts, size_t n_clients, size_t D, int init_base, int *bad), (out, pts, n_clients, D, init_base, bad))
+#endif
+
+// ===================================================================================================================
+// K10: baby-step giant-step discrete log (bsgs32.rs:20-73).  The table maps the first 8 bytes of compress(x B) (an
+//   injective key with overwhelming probability; the full encoding is stored for an exact compare) to x, in an
+//   open-addressing hash table of `cap` (power of two) slots that lives in HBM / L2.
+// ===================================================================================================================
+// Table = two arrays of `cap` (power of two) slots: keys[] (u64, 0xff..ff = empty) and vals[] (u32, x+1).
+#define BSGS_EMPTY 0xffffffffffffffffULL
+HD unsigned long long bsgs_key(const ge_p3 &p) {
+    uint8_t o[32]; ge_compress(o, p);
+    unsigned long long k = 0; for (int i = 0; i < 8; i++) k |= (unsigned long long)o[i] << (8 * i);
+    return k == BSGS_EMPTY ? BSGS_EMPTY - 1 : k;
+}
+HD uint32_t bsgs_hash(unsigned long long k, uint32_t cap) { return (uint32_t)((k * 0x9E3779B97F4A7C15ULL) >> 24) & (cap - 1); }
+// entry x in [0, m]: key(compress(x B)) -> x+1.  Later entries overwrite earlier ones on equal keys (HashMap::insert,
+// bsgs32.rs:26-33): atomicMax makes that independent of thread order.  distinct counts the occupied slots (table.len()).
+#ifdef KG_BSGS
+KERNEL void LB(128, 2) k_bsgs_build(unsigned long long *keys, uint32_t *vals, uint32_t cap, uint32_t m, const niels_st *tabB, int *distinct) {
+    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x > m) return;
+    ge_p3 p; ge_p3_0(p); sc s; sc_from_u64(s, x); fb_mul_acc(p, tabB, s, 32);
+    unsigned long long k = bsgs_key(p);
+    uint32_t pos = bsgs_hash(k, cap);
+    for (uint32_t probe = 0; probe < cap; probe++) {
+        unsigned long long prev = atomicCAS(&keys[pos], BSGS_EMPTY, k);
+        if (prev == BSGS_EMPTY) atomicAdd(distinct, 1);
+        if (prev == BSGS_EMPTY || prev == k) { atomicMax(&vals[pos], x + 1); return; }
+        pos = (pos + 1) & (cap - 1);
+    }
+}
+KLAUNCH(k_bsgs_build, false, (unsigned long long *keys, uint32_t *vals, uint32_t cap, uint32_t m, const niels_st *tabB, int *distinct), (keys, vals, cap, m, tabB, distinct))
+#endif
+// exact lookup: a key hit is confirmed by recomputing x B and comparing group elements
+HD bool bsgs_lookup(uint32_t &val, const unsigned long long *keys, const uint32_t *vals, uint32_t cap, const ge_p3 &p, const niels_st *tabB) {
+    unsigned long long k = bsgs_key(p);
+    uint32_t pos = bsgs_hash(k, cap);
+    for (uint32_t probe = 0; probe < cap; probe++) {
+        unsigned long long cur = keys[pos];
+        if (cur == BSGS_EMPTY) return false;
+        if (cur == k) {
+            uint32_t x = vals[pos] - 1;
+            ge_p3 q; ge_p3_0(q); sc s; sc_from_u64(s, x); fb_mul_acc(q, tabB, s, 32);
+            if (ge_eq(q, p)) { val = x; return true; }
+        }
+        pos = (pos + 1) & (cap - 1);
+    }
+    return false;
+}
+// solve_discrete_log_with_neg (bsgs32.rs:48-73): up to max_it giant steps for M, then for -M.
+//   size = distinct - 1 (get_size), mG = (m & vmask) B, result (it*size + val) & vmask; miss on both signs -> flag 8
+#ifdef KG_BSGS
+KERNEL void LB(128, 2) k_bsgs_solve(uint8_t *out_sc, float *out_f32, const uint8_t *pts, size_t D, const unsigned long long *keys, const uint32_t *vals, uint32_t cap,
+                                   uint32_t m, uint64_t size, uint64_t max_it, int bsgs_bits, int n_bits, int frac, const niels_st *tabB, int *flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    uint8_t b[32]; ld_bytes32(b, pts + 32 * i);
+    ge_p3 M; if (!ge_decompress(M, b)) { atomicOr(flags, 4); return; }
+    uint64_t vmask = (1ULL << bsgs_bits) - 1;
+    ge_p3 mG; ge_p3_0(mG); { sc s; sc_from_u64(s, (uint64_t)m & vmask); fb_mul_acc(mG, tabB, s, 32); }
+    int found = 0; uint64_t val = 0;
+    for (int sign = 0; sign < 2 && !found; sign++) {
+        ge_p3 cur; if (sign) ge_neg(cur, M); else cur = M;
+        for (uint64_t it = 0; it < max_it && !found; it++) {
+            uint32_t v;
+            if (bsgs_lookup(v, keys, vals, cap, cur, tabB)) { found = 1 + sign; val = (it * size + (v & vmask)) & vmask; }
+            else ge_sub(cur, cur, mG);
+        }
+    }
+    sc r; sc_0(r);
+    if (!found) { atomicOr(flags, 8); for (int k = 0; k < 8; k++) r.v[k] = 0xffffffffu; }
+    else { sc_from_u64(r, val); if (found == 2) sc_neg(r, r); }
+    if (out_sc) { uint8_t o[32]; sc_tobytes(o, r); st_bytes32(out_sc + 32 * i, o); }
+    if (out_f32) out_f32[i] = found ? scalar_to_f32(r, n_bits, frac) : 0.0f;
+}
+KLAUNCH(k_bsgs_solve, false, (uint8_t *out_sc, float *out_f32, const uint8_t *pts, size_t D, const unsigned long long *keys, const uint32_t *vals, uint32_t cap, uint32_t m, uint64_t size, uint64_t max_it, int bsgs_bits, int n_bits, int frac, const niels_st *tabB, int *flags), (out_sc, out_f32, pts, D, keys, vals, cap, m, size, max_it, bsgs_bits, n_bits, frac, tabB, flags))
+#endif
+
+// K1: conversions exposed on their own (conversion32.rs:11-38, range_proof_vec/mod.rs:104-111)
+#ifdef KG_COMMIT
+KERNEL void k_f32_to_scalar(uint8_t *out, const float *v, size_t D, int n_bits, int frac, int *flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    sc s; if (f32_to_scalar(s, v[i], n_bits, frac)) { atomicOr(flags, 1); sc_0(s); }
+    uint8_t o[32]; sc_tobytes(o, s); st_bytes32(out + 32 * i, o);
+}
+KLAUNCH(k_f32_to_scalar, false, (uint8_t *out, const float *v, size_t D, int n_bits, int frac, int *flags), (out, v, D, n_bits, frac, flags))
+#endif
+#ifdef KG_COMMIT
+KERNEL void k_scalar_to_f32(float *out, const uint8_t *in, size_t D, int n_bits, int frac) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    uint8_t b[32]; ld_bytes32(b, in + 32 * i); sc s; sc_from_bytes_mod_order(s, b);
+    out[i] = scalar_to_f32(s, n_bits, frac);
+}
+KLAUNCH(k_scalar_to_f32, false, (float *out, const uint8_t *in, size_t D, int n_bits, int frac), (out, in, D, n_bits, frac))
+#endif
+// sum of squares of f32_to_scalar(x) mod l and sum of blindings (l2_range_proof_vec/mod.rs:37-42,75-79): block partials
+#ifdef KG_COMMIT
+KERNEL void LB(256, 1) k_l2_sums(sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, int *flags) {
+    __shared__ sc_st buf[256];
+    int tid = threadIdx.x;
+    sc sq, bs; sc_0(sq); sc_0(bs);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < D; i += (size_t)gridDim.x * blockDim.x) {
+        sc s, t; if (f32_to_scalar(s, v[i], n_bits, frac)) { atomicOr(flags, 1); continue; }
+        sc_mul(t, s, s); sc_add(sq, sq, t);
+        uint8_t b[32]; ld_bytes32(b, blind + 32 * i); sc_from_bytes_mod_order(t, b); sc_add(bs, bs, t);
+    }
+    block_sum_sc(sq, buf, tid, blockDim.x); block_sum_sc(bs, buf, tid, blockDim.x);
+    if (tid == 0) { st_sc(partial + 2 * blockIdx.x, sq); st_sc(partial + 2 * blockIdx.x + 1, bs); }
+}
+KLAUNCH(k_l2_sums, true, (sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, int *flags), (partial, v, blind, D, n_bits, frac, flags))
+#endif
+
+// ---- launcher declarations (definitions live in the translation unit of each kernel group) ----------------------------
+void launch_k_fb_table_build(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *tab, const uint8_t *pt);
+void launch_k_gens_build(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *G, niels_st *H, int n, int party_begin, int party_end);
+void launch_k_commit(dim3 g_, dim3 b_, cudaStream_t s_, commit_args a);
+void launch_k_nonces(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *sLR, const uint32_t *keys, int n, int m, size_t total);
+void launch_k_party_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *out, const uint32_t *keys, const sc_st *blind, const sc_st *z, int n, int m, int phase);
+void launch_k_bits_sum(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *partial, const uint64_t *vals, const niels_st *G, const niels_st *H, int n, int m);
+void launch_k_msm(dim3 g_, dim3 b_, cudaStream_t s_, msm_args a);
+void launch_k_finalize(dim3 g_, dim3 b_, cudaStream_t s_, finalize_args a);
+void launch_k_poly(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *l0, sc_st *r0, sc_st *sLR, sc_st *partial, const uint64_t *vals, const sc_st *ypow2, const sc_st *zpow2, int n, int m);
+void launch_k_sc_sum(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *out, const sc_st *in, int cnt, int q);
+void launch_k_lr(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *l0, sc_st *r0, const sc_st *sLR, sc_st *yinv, const sc_st *x, const sc_st *yinvpow2, size_t N, size_t total);
+void launch_k_ipp_scalars(dim3 g_, dim3 b_, cudaStream_t s_, const sc_st *a, const sc_st *b, const sc_st *yinv, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np);
+void launch_k_ipp_fold_scalars(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *a, sc_st *b, const sc_st *u2, const sc_st *uinv2, size_t N, uint32_t np);
+void launch_k_ipp_fold_points(dim3 g_, dim3 b_, cudaStream_t s_, fold_args a);
+void launch_k_decompress(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *out, uint8_t *out32, const uint8_t *in, size_t count_in, size_t count_out, const p3_st *offset, int *bad, size_t bad_group);
+void launch_k_verify_scalars(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *scalars, uint32_t scalar_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int n, int m, int lgN);
+void launch_k_square_prove(dim3 g_, dim3 b_, cudaStream_t s_, square_args a);
+void launch_k_square_verify(dim3 g_, dim3 b_, cudaStream_t s_, const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result);
+void launch_k_aggregate(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const uint8_t *pts, size_t n_clients, size_t D, int init_base, int *bad);
+void launch_k_bsgs_build(dim3 g_, dim3 b_, cudaStream_t s_, unsigned long long *keys, uint32_t *vals, uint32_t cap, uint32_t m, const niels_st *tabB, int *distinct);
+void launch_k_bsgs_solve(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out_sc, float *out_f32, const uint8_t *pts, size_t D, const unsigned long long *keys, const uint32_t *vals, uint32_t cap, uint32_t m, uint64_t size, uint64_t max_it, int bsgs_bits, int n_bits, int frac, const niels_st *tabB, int *flags);
+void launch_k_f32_to_scalar(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const float *v, size_t D, int n_bits, int frac, int *flags);
+void launch_k_scalar_to_f32(dim3 g_, dim3 b_, cudaStream_t s_, float *out, const uint8_t *in, size_t D, int n_bits, int frac);
+void launch_k_l2_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, int *flags);

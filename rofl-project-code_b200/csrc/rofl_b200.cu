@@ -1,0 +1,66 @@
+// librofl_b200.so: the product library (CUDA, sm_100a only).  Context lifetime, CUDA-event profiling hooks, and the
+// C ABI of include/rofl_b200.h (capi.cuh).  There is no CPU path in this translation unit.
+#include "capi.cuh"
+#include <atomic>
+#include <cstring>
+
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+struct prof_pair { cudaEvent_t a, b; };
+static std::vector<prof_pair> g_prof_events[PROF_SLOTS];
+static cudaEvent_t g_prof_open[PROF_SLOTS];
+static double g_prof_ms[PROF_SLOTS];
+static long g_prof_launch[PROF_SLOTS];
+static std::atomic<long> g_launches{0};
+
+void rt_count_launch(const char *) { g_launches++; }
+void rt_prof_begin(int slot, cudaStream_t s) {
+    if (!g_prof_on.load()) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t a; cudaEventCreate(&a); cudaEventRecord(a, s); g_prof_open[slot] = a;
+}
+void rt_prof_end(int slot, cudaStream_t s) {
+    if (!g_prof_on.load()) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t b; cudaEventCreate(&b); cudaEventRecord(b, s);
+    g_prof_events[slot].push_back({g_prof_open[slot], b}); g_prof_launch[slot]++;
+}
+static void prof_collect() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int sl = 0; sl < PROF_SLOTS; sl++) {
+        for (auto &p : g_prof_events[sl]) { cudaEventSynchronize(p.b); float ms = 0; cudaEventElapsedTime(&ms, p.a, p.b); g_prof_ms[sl] += ms; cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+        g_prof_events[sl].clear();
+    }
+}
+extern "C" void rofl_prof_enable(int on) { g_prof_on = on; }
+extern "C" void rofl_prof_reset(void) { prof_collect(); for (int i = 0; i < PROF_SLOTS; i++) { g_prof_ms[i] = 0; g_prof_launch[i] = 0; } g_launches = 0; }
+extern "C" double rofl_prof_ms(int slot) { prof_collect(); return (slot >= 0 && slot < PROF_SLOTS) ? g_prof_ms[slot] : 0.0; }
+extern "C" long rofl_prof_launches(int slot) { if (slot < 0) return g_launches.load(); return slot < PROF_SLOTS ? g_prof_launch[slot] : 0; }
+extern "C" void *rofl_ctx_stream(rofl_ctx *c) { return c ? (void *)c->e.stream : nullptr; }
+
+extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
+    if (!out) return ROFL_ERR_ARGS;
+    *out = nullptr;
+    try {
+        int ndev = 0;
+        rt_check(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount");
+        if (device < 0 || device >= ndev) throw std::runtime_error("rofl_b200 needs a CUDA device (no CPU fallback): device index out of range");
+        rt_check(cudaSetDevice(device), "cudaSetDevice");
+        cudaDeviceProp prop; rt_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+        if (prop.major < 10) throw std::runtime_error("rofl_b200 is built for sm_100a only");
+        rofl_ctx *c = new rofl_ctx();
+        c->e.device = device;
+        rt_check(cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        // keep freed scratch in the pool between calls
+        cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
+        unsigned hc = std::thread::hardware_concurrency(); c->e.host_threads = hc ? (int)std::min(hc, 32u) : 8;
+        engine_init(c->e);
+        *out = c;
+        return ROFL_OK;
+    } catch (const std::exception &ex) { g_last_error = ex.what(); return ROFL_ERR_CUDA; }
+}
+extern "C" void rofl_ctx_destroy(rofl_ctx *c) {
+    if (!c) return;
+    try { cudaSetDevice(c->e.device); engine_destroy(c->e); cudaStreamDestroy(c->e.stream); } catch (...) {}
+    delete c;
+}

@@ -1,0 +1,117 @@
+// Integers mod l = 2^252 + 27742317777372353535851937790883648493 (ristretto255 group order) on 8 x u32 limbs.
+// curve25519-dalek-ng `Scalar` semantics (32-byte little-endian canonical form at every API edge).
+// Multiplication is two Montgomery REDC passes (R = 2^256) so values stay canonical between calls;
+// the oracle uses a different method (2^252 = -c folding on 64-bit limbs), so the two cross-check.
+// All __host__ __device__ (see fe25519.cuh).
+#pragma once
+#include "fe25519.cuh"
+#include "constants25.cuh"
+
+struct sc { uint32_t v[8]; };
+
+#if defined(__CUDA_ARCH__)
+#define SC_CONST static __device__ __constant__ const
+#else
+#define SC_CONST static const
+#endif
+SC_CONST uint32_t SC_L_[8] = SC_L;
+SC_CONST uint32_t SC_R2_[8] = SC_MONT_R2;
+#define SC_NINV SC_MONT_NINV
+
+HD void sc_0(sc &r) { for (int i = 0; i < 8; i++) r.v[i] = 0; }
+HD void sc_from_u64(sc &r, uint64_t x) { sc_0(r); r.v[0] = (uint32_t)x; r.v[1] = (uint32_t)(x >> 32); }
+HD bool sc_iszero(const sc &a) { uint32_t r = 0; for (int i = 0; i < 8; i++) r |= a.v[i]; return r == 0; }
+HD bool sc_eq(const sc &a, const sc &b) { uint32_t r = 0; for (int i = 0; i < 8; i++) r |= a.v[i] ^ b.v[i]; return r == 0; }
+HD void sc_frombytes(sc &r, const uint8_t *s) {
+    for (int i = 0; i < 8; i++) r.v[i] = (uint32_t)s[4 * i] | ((uint32_t)s[4 * i + 1] << 8) | ((uint32_t)s[4 * i + 2] << 16) | ((uint32_t)s[4 * i + 3] << 24);
+}
+HD void sc_tobytes(uint8_t *s, const sc &a) {
+    for (int i = 0; i < 8; i++) { s[4 * i] = (uint8_t)a.v[i]; s[4 * i + 1] = (uint8_t)(a.v[i] >> 8); s[4 * i + 2] = (uint8_t)(a.v[i] >> 16); s[4 * i + 3] = (uint8_t)(a.v[i] >> 24); }
+}
+// a >= l ?
+HD bool sc_geq_l(const uint32_t a[8]) {
+    for (int i = 7; i >= 0; i--) { if (a[i] > SC_L_[i]) return true; if (a[i] < SC_L_[i]) return false; }
+    return true;
+}
+HD bool sc_is_canonical(const sc &a) { return !sc_geq_l(a.v); }
+// r = a - l if a >= l  (a < 2l)
+HD void sc_cond_sub_l(uint32_t a[8], uint32_t extra_hi = 0) {
+    uint32_t t[8]; uint64_t br = 0;
+    for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a[i] - SC_L_[i] - br; t[i] = (uint32_t)d; br = (d >> 32) & 1; }
+    bool ge = (extra_hi != 0) || (br == 0);
+    for (int i = 0; i < 8; i++) a[i] = ge ? t[i] : a[i];
+}
+HD void sc_add(sc &r, const sc &a, const sc &b) {
+    uint64_t c = 0; uint32_t t[8];
+    for (int i = 0; i < 8; i++) { c += (uint64_t)a.v[i] + b.v[i]; t[i] = (uint32_t)c; c >>= 32; }
+    sc_cond_sub_l(t);                              // a + b < 2l < 2^254: no carry out
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+}
+HD void sc_sub(sc &r, const sc &a, const sc &b) {
+    uint64_t br = 0; uint32_t t[8];
+    for (int i = 0; i < 8; i++) { uint64_t d = (uint64_t)a.v[i] - b.v[i] - br; t[i] = (uint32_t)d; br = (d >> 32) & 1; }
+    uint64_t c = 0; uint32_t m = br ? 0xffffffffu : 0;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)t[i] + (SC_L_[i] & m); r.v[i] = (uint32_t)c; c >>= 32; }
+}
+HD void sc_neg(sc &r, const sc &a) { sc z; sc_0(z); sc_sub(r, z, a); }
+// Montgomery product a*b/2^256 mod l (CIOS); needs a*b < l*2^256; result < l
+HDNI void sc_montmul(uint32_t r[8], const uint32_t a[8], const uint32_t b[8]) {
+    uint32_t t[10];
+    for (int i = 0; i < 10; i++) t[i] = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 8; j++) { c += (uint64_t)a[i] * b[j] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
+        c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
+        uint32_t m = t[0] * SC_NINV;
+        c = (uint64_t)m * SC_L_[0] + t[0]; c >>= 32;
+        for (int j = 1; j < 8; j++) { c += (uint64_t)m * SC_L_[j] + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
+        c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32);
+    }
+    sc_cond_sub_l(t, t[8]);
+    for (int i = 0; i < 8; i++) r[i] = t[i];
+}
+HD void sc_mul(sc &r, const sc &a, const sc &b) {
+    uint32_t t[8];
+    sc_montmul(t, a.v, b.v);          // a b / R
+    sc_montmul(r.v, t, SC_R2_);       // a b
+}
+HD void sc_muladd(sc &r, const sc &a, const sc &b, const sc &c) { sc t; sc_mul(t, a, b); sc_add(r, t, c); }
+HD void sc_sq(sc &r, const sc &a) { sc_mul(r, a, a); }
+// reduce a 512-bit little-endian value (16 words): lo + hi*R == mont(lo, R mod l ... ) -- done as
+// mont(lo, R2)*1 path: x mod l = mont(mont(lo,R2),1)?  Simpler: lo mod l + mont(hi, R2) (= hi*R mod l)
+HD void sc_from_wide_words(sc &r, const uint32_t w[16]) {
+    uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t lo_m[8], lo[8], hi[8];
+    sc_montmul(lo_m, w, SC_R2_);      // lo * R   (lo < 2^256, R2 < l  => product < l*2^256)
+    sc_montmul(lo, lo_m, one);        // lo mod l
+    sc_montmul(hi, w + 8, SC_R2_);    // hi * R mod l
+    sc a, b; for (int i = 0; i < 8; i++) { a.v[i] = lo[i]; b.v[i] = hi[i]; }
+    sc_add(r, a, b);
+}
+HD void sc_from_bytes_wide(sc &r, const uint8_t *s) {
+    uint32_t w[16];
+    for (int i = 0; i < 16; i++) w[i] = (uint32_t)s[4 * i] | ((uint32_t)s[4 * i + 1] << 8) | ((uint32_t)s[4 * i + 2] << 16) | ((uint32_t)s[4 * i + 3] << 24);
+    sc_from_wide_words(r, w);
+}
+// reduce an arbitrary 256-bit value
+HD void sc_from_bytes_mod_order(sc &r, const uint8_t *s) {
+    uint32_t w[16]; for (int i = 0; i < 16; i++) w[i] = 0;
+    for (int i = 0; i < 8; i++) w[i] = (uint32_t)s[4 * i] | ((uint32_t)s[4 * i + 1] << 8) | ((uint32_t)s[4 * i + 2] << 16) | ((uint32_t)s[4 * i + 3] << 24);
+    sc_from_wide_words(r, w);
+}
+// a^(l-2)
+HD void sc_invert(sc &r, const sc &a) {
+    uint32_t e[8]; for (int i = 0; i < 8; i++) e[i] = SC_L_[i];
+    e[0] -= 2;
+    sc acc; sc_from_u64(acc, 1);
+    for (int i = 252; i >= 0; i--) {
+        sc_mul(acc, acc, acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) sc_mul(acc, acc, a);
+    }
+    r = acc;
+}
+HD void sc_pow_u64(sc &r, const sc &a, uint64_t e) {
+    sc acc, base = a; sc_from_u64(acc, 1);
+    while (e) { if (e & 1) sc_mul(acc, acc, base); sc_mul(base, base, base); e >>= 1; }
+    r = acc;
+}

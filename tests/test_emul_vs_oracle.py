@@ -1,0 +1,103 @@
+"""Product kernels + host engine + C ABI executed under the CUDA-on-CPU emulation (tests/hostsim/libemul.so, a test
+tool) and compared byte for byte with the oracle.  This is the CPU-side rehearsal of tests/test_gpu_parity.py: same
+calls, same seeds, tiny sizes.  CPU only."""
+import ctypes as C
+import importlib.util
+import os
+import subprocess
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def api():
+    d = os.path.join(HERE, "hostsim")
+    subprocess.check_call(["make", "-C", d, "-s", "libemul.so"], env={**os.environ, "CXX": "g++"})
+    spec = importlib.util.spec_from_file_location("rofl_ffi", os.path.join(ROOT, "rofl-project-code_b200", "_ffi.py"))
+    ffi = importlib.util.module_from_spec(spec); spec.loader.exec_module(ffi)
+    a = ffi.Api(C.CDLL(os.path.join(d, "libemul.so")))
+    yield a
+    a.close()
+
+
+def test_commit_and_conversion(api, oracle):
+    rng = np.random.default_rng(0)
+    v = np.concatenate([rng.uniform(-300, 300, 20), [0.0, -0.0, 0.25, -1.5, 600.0, -600.0]]).astype(np.float32)
+    bl = oracle.rnd_scalar_vec(b"\x31" * 32, v.size)
+    for nb, fr in [(16, 7), (32, 7), (8, 7)]:
+        assert (api.f32_to_scalar_vec(v, nb, fr) == oracle.f32_to_scalar_vec(v, nb, fr)).all()
+        L, R = api.commit(v, bl, nb, fr, want_R=True)
+        assert (L == oracle.commit_f32(v, bl, nb, fr)).all()
+        assert (R == oracle.elgamal_R(bl)).all()
+        assert (api.commit(v, None, nb, fr) == oracle.commit_f32(v, None, nb, fr)).all()
+    assert (api.rnd_scalar_vec(b"\x31" * 32, 9) == oracle.rnd_scalar_vec(b"\x31" * 32, 9)).all()
+    s = oracle.f32_to_scalar_vec(v, 16, 7)
+    assert (api.scalar_to_f32_vec(s, 16, 7) == oracle.scalar_to_f32_vec(s, 16, 7)).all()
+
+
+@pytest.mark.parametrize("D,rngbits,P,nb", [(5, 8, 2, 16), (3, 16, 4, 16), (8, 8, 1, 16), (1, 8, 4, 16)])
+def test_range_prove_bytes_and_verify(api, oracle, D, rngbits, P, nb):
+    rng = np.random.default_rng(D * 100 + rngbits)
+    mn, mx = oracle.clip_bounds(rngbits, nb, 7)
+    v = rng.uniform(mn, mx, D).astype(np.float32)
+    bl = oracle.rnd_scalar_vec(b"\x32" * 32, D)
+    seed = bytes([7] * 32)
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, rngbits, P, nb, 7, seed)
+    rc, p, c = api.range_prove(v, bl, rngbits, P, nb, 7, seed)
+    assert rc == rc_o == 0
+    assert (c == c_o).all()
+    assert p.shape == p_o.shape and (p == p_o).all()
+    assert api.range_verify(p, c, rngbits, seed) == 1 and oracle.range_verify(p, c, rngbits, seed) == 1
+    bad = c.copy(); bad[0] = np.frombuffer(oracle.basepoint(), np.uint8)
+    assert api.range_verify(p, bad, rngbits, seed) == 0
+    badp = p.copy(); badp[0, 40] ^= 1
+    assert api.range_verify(badp, c, rngbits, seed) == oracle.range_verify(badp, c, rngbits, seed)
+    badp = p.copy(); badp[0, 128:160] = 0xff
+    assert api.range_verify(badp, c, rngbits, seed) == -1
+
+
+def test_range_prove_errors(api, oracle):
+    z = np.zeros((8, 32), np.uint8)
+    assert api.range_prove(np.full(8, 1.5, np.float32), z, 8, 4, 16, 7)[0] == 2
+    assert api.range_prove(np.zeros(8, np.float32), z, 8, 3, 16, 7)[0] == -99
+    assert api.range_prove(np.zeros(8, np.float32), z, 12, 4, 16, 7)[0] == -1
+
+
+def test_l2_and_square(api, oracle):
+    rng = np.random.default_rng(5)
+    D = 6
+    v = (rng.integers(-24, 25, D) / 128).astype(np.float32)
+    r1 = oracle.rnd_scalar_vec(b"\x33" * 32, D); r2 = oracle.rnd_scalar_vec(b"\x34" * 32, D)
+    seed = bytes([9] * 32)
+    rc_o, pf_o, cm_o = oracle.l2_prove(v, r2, 32, 32, 7, seed)
+    rc, pf, cm = api.l2_prove(v, r2, 32, 32, 7, seed)
+    assert rc == rc_o == 0 and (pf == pf_o).all() and (cm == cm_o).all()
+    assert api.l2_verify(pf, cm, 32, seed) == 1
+    assert api.l2_verify(pf, oracle.basepoint(), 32, seed) == 0
+    assert api.l2_prove(np.array([8.0], np.float32), np.zeros((1, 32), np.uint8), 16, 32, 7)[0] == 4
+    cl = oracle.commit_f32(v, r1, 32, 7)
+    rc_o, sp_o, sc_o = oracle.square_prove(v, cl, r1, r2, 32, 7, seed)
+    rc, sp, sc = api.square_prove(v, cl, r1, r2, 32, 7, seed)
+    assert rc == rc_o == 0 and (sp == sp_o).all() and (sc == sc_o).all()
+    assert api.square_verify(sp, sc) == 1
+    bad = sc.copy(); bad[1, 32:] = sc[2, 32:]
+    assert api.square_verify(sp, bad) == 0
+    bad = sp.copy(); bad[0, 64:96] = 0xff
+    assert api.square_verify(bad, sc) == -1
+
+
+def test_aggregate_and_dlog(api, oracle):
+    x = np.array([[0.25, 1.25, -1.5], [-0.75, 1.25, -2.0], [0.5, 1.25, -3.0]], np.float32)
+    cs = np.stack([oracle.commit_f32(r, None, 16, 7) for r in x])
+    agg = api.aggregate(cs, 0)
+    assert (agg == oracle.aggregate(cs, 0)).all()
+    assert (api.aggregate(cs, 1) == oracle.aggregate(cs, 1)).all()
+    rc, s, f = api.dlog(agg, 1 << 9, 16, 16, 7)        # small table: giant steps
+    rc_o, s_o = oracle.dlog(agg, 1 << 9, 16)
+    assert rc == rc_o == 0 and (s == s_o).all()
+    assert (f == np.array([0.0, 3.75, -6.5], np.float32)).all()
+    far = oracle.commit_f32(np.array([400.0], np.float32), None, 16, 7)
+    assert api.dlog(far, 1 << 4, 8, 8, 7)[0] == -5 and oracle.dlog(far, 1 << 4, 8)[0] == -5
