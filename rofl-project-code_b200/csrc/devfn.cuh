@@ -101,7 +101,7 @@ HDNI void fb_mul_acc(ge_p3 &r, const niels_st *tab, const sc &k, int nwin) {
         int di = d[i];
         if (di != 0) {
             ge_niels n; ld_niels(n, tab + i * FB_ENTRIES + (di > 0 ? di : -di) - 1);
-            if (di > 0) ge_madd(r, r, n); else ge_msub(r, r, n);
+            ge_madd_signed(r, r, n, di < 0);
         }
     }
 }
@@ -166,8 +166,8 @@ HDNI void ge_double_scalarmult_r16(ge_p3 &r, const sc &a, const ge_tab8 &tp, con
             ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); ge_p1p1_to_p3(r, t);
         }
         int d = ea[i];
-        if (d > 0) ge_add_cached(r, r, tp.t[d - 1]); else if (d < 0) ge_sub_cached(r, r, tp.t[-d - 1]);
-        if (b) { d = eb[i]; if (d > 0) ge_add_cached(r, r, tq->t[d - 1]); else if (d < 0) ge_sub_cached(r, r, tq->t[-d - 1]); }
+        if (d != 0) ge_add_cached_signed(r, r, tp.t[(d > 0 ? d : -d) - 1], d < 0);
+        if (b) { d = eb[i]; if (d != 0) ge_add_cached_signed(r, r, tq->t[(d > 0 ? d : -d) - 1], d < 0); }
     }
 }
 

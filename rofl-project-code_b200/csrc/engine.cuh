@@ -17,7 +17,8 @@
 enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE = 4, DOM_L2_VERIFY = 5, DOM_CRP = 6, DOM_RND_VEC = 7 };
 enum { PROF_FOLD = 0, PROF_MSM = 1, PROF_COMMIT = 2, PROF_SQUARE = 3, PROF_SLOTS = 8 };
 
-struct gens_entry { int n = 0; int cap = 0; niels_st *G = nullptr, *H = nullptr; };
+struct gens_entry { int n = 0; int cap = 0; niels_st *G = nullptr, *H = nullptr;
+                    int rt_cap = 0; niels_st *RTG = nullptr, *RTH = nullptr; };     // radix-256 tables (RT path), 512 KB per generator
 struct bsgs_entry { unsigned long long *keys = nullptr; uint32_t *vals = nullptr; uint32_t cap = 0; uint64_t size = 0; };
 struct rofl_engine {
     int device = 0;
@@ -28,6 +29,11 @@ struct rofl_engine {
     std::map<std::pair<uint64_t, int>, bsgs_entry> bsgs;
     std::mutex mu;
     int host_threads = 8;
+    int groups = 1;                       // chunk groups proved / verified concurrently on separate streams (hides per-round latency)
+    std::vector<cudaStream_t> gstreams;   // gstreams[0] == stream
+    int use_rt = 1;                       // 0: never build generator tables (generic Pippenger / fold path only)
+    int rt_unfold = 3;                    // IPP rounds computed over the original generators before the catch-up fold
+    double rt_mem_frac = 0.45;            // tables may take this fraction of the free device memory
 };
 
 // ---- small host helpers ---------------------------------------------------------------------------------------------------
@@ -76,6 +82,7 @@ static inline void engine_init(rofl_engine &e) {
     ge_p3 B, H; ge_base(B); ge_compress(e.B32, B);
     uint8_t h[64]; sha3_512(h, e.B32, 32); ge_from_uniform_bytes(H, h); ge_compress(e.H32, H);     // PedersenGens::default / el_gamal.rs:31-40
     cudaStream_t s = e.stream;
+    if (e.gstreams.empty()) e.gstreams.push_back(e.stream);
     e.tabB = (niels_st *)rt_malloc(sizeof(niels_st) * FB_WINDOWS * FB_ENTRIES, s);
     e.tabH = (niels_st *)rt_malloc(sizeof(niels_st) * FB_WINDOWS * FB_ENTRIES, s);
     dev_buf pts(64, s);
@@ -89,7 +96,7 @@ static inline void engine_destroy(rofl_engine &e) {
     cudaStream_t s = e.stream;
     rt_sync(s);
     rt_free(e.tabB, s); rt_free(e.tabH, s);
-    for (auto &g : e.gens) { rt_free(g.second.G, s); rt_free(g.second.H, s); }
+    for (auto &g : e.gens) { rt_free(g.second.G, s); rt_free(g.second.H, s); rt_free(g.second.RTG, s); rt_free(g.second.RTH, s); }
     for (auto &b : e.bsgs) { rt_free(b.second.keys, s); rt_free(b.second.vals, s); }
     e.gens.clear(); e.bsgs.clear();
     rt_sync(s);
@@ -112,11 +119,46 @@ static inline gens_entry &engine_gens(rofl_engine &e, int n, int m) {
     return g;
 }
 
+// radix-256 tables for the first m parties of the n-bit generators; returns false when they do not fit in memory
+static inline bool engine_rt(rofl_engine &e, gens_entry &g, int n, int m, rt_tables &out) {
+    if (!e.use_rt) return false;
+    if (g.rt_cap >= m) { out.G = g.RTG; out.H = g.RTH; return true; }
+    cudaStream_t s = e.stream;
+    const size_t cnt = (size_t)n * m, bytes = cnt * RT_W * RT_E * sizeof(niels_st);
+    size_t have = rt_free_mem() + (g.RTG ? 2 * (size_t)n * g.rt_cap * RT_W * RT_E * sizeof(niels_st) : 0);
+    if ((double)(2 * bytes + 2 * cnt * RT_W * sizeof(p3_st)) > e.rt_mem_frac * (double)have) return false;
+    rt_sync(s); rt_free(g.RTG, s); rt_free(g.RTH, s); g.RTG = g.RTH = nullptr; g.rt_cap = 0;
+    niels_st *RTG = (niels_st *)rt_malloc(bytes, s), *RTH = (niels_st *)rt_malloc(bytes, s);
+    {
+        dev_buf P(cnt * RT_W * sizeof(p3_st), s);
+        for (int which = 0; which < 2; which++) {
+            LAUNCH(k_rt_shifts, dim3((unsigned)((cnt + 127) / 128)), dim3(128), s, P.as<p3_st>(), which ? g.H : g.G, (uint32_t)cnt);
+            LAUNCH(k_rt_rows, dim3((unsigned)((cnt * RT_W * 8 + 127) / 128)), dim3(128), s, which ? RTH : RTG, P.as<p3_st>(), cnt * RT_W);
+        }
+        rt_sync(s);
+    }
+    g.RTG = RTG; g.RTH = RTH; g.rt_cap = m; out.G = RTG; out.H = RTH;
+    return true;
+}
+// blocks per msm for the direct table MSM: whole waves of 148 SMs x 4 resident blocks, >= 4 terms per thread when possible
+static inline int rt_blocks(size_t T, int C) {
+    const double slots = 148.0 * 4.0;
+    double waves = std::max(1.0, std::floor((double)T * C / (128.0 * 8.0) / slots + 0.5));
+    size_t nb = (size_t)std::ceil(slots * waves / C);
+    nb = std::min(nb, (T + 127) / 128);
+    return (int)std::max<size_t>(1, nb);
+}
+static inline void run_rt_msm(rofl_engine &e, cudaStream_t s, rt_msm_args a, int nb, uint32_t n_msm) {
+    void *tk = rt_prof_begin(PROF_MSM, s);
+    LAUNCH_COOP(k_rt_msm, dim3(nb, n_msm), dim3(128), s, a);
+    rt_prof_end(PROF_MSM, tk, s);
+}
+
 // ---- MSM front end ----------------------------------------------------------------------------------------------------------
-static inline void run_msm(rofl_engine &e, const msm_args &a, uint32_t n_msm) {
-    rt_prof_begin(PROF_MSM, e.stream);
-    LAUNCH_COOP(k_msm, dim3(MSM_WINDOWS, n_msm), dim3(MSM_BUCKETS), e.stream, a);
-    rt_prof_end(PROF_MSM, e.stream);
+static inline void run_msm(rofl_engine &e, cudaStream_t s, const msm_args &a, uint32_t n_msm) {
+    void *tk = rt_prof_begin(PROF_MSM, s);
+    LAUNCH_COOP(k_msm, dim3(MSM_WINDOWS, n_msm), dim3(MSM_BUCKETS), s, a);
+    rt_prof_end(PROF_MSM, tk, s);
 }
 static inline msm_seg mk_seg(const void *base, uint32_t count, uint32_t stride, int kind) { msm_seg s; s.base = base; s.count = count; s.stride = stride; s.kind = kind; return s; }
 
@@ -125,9 +167,8 @@ static inline msm_seg mk_seg(const void *base, uint32_t count, uint32_t stride, 
 // h_proofs (host).  d_vals: C*m shifted values, d_blind: C*m blindings (reduced), d_V32: C*m compressed commitments.
 // label = transcript label ("RangeProof" / "L2RangeProof"); keys = C ChaCha20 keys (host).
 // =============================================================================================================================
-static void prove_chunks(rofl_engine &e, const char *label, int n, int m, int C, const gens_entry &g, const uint64_t *d_vals,
+static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int n, int m, int C, const gens_entry &g, const rt_tables *rt, const uint64_t *d_vals,
                          const sc_st *d_blind, const uint8_t *d_V32, const std::vector<uint8_t> &keys, uint8_t *h_proofs) {
-    cudaStream_t s = e.stream;
     const size_t N = (size_t)n * m, NT = N * C;
     const int lgN = ilog2_sz(N);
     const size_t plen = 32 * (9 + 2 * (size_t)lgN);
@@ -146,10 +187,18 @@ static void prove_chunks(rofl_engine &e, const char *label, int n, int m, int C,
         LAUNCH(k_finalize, dim3((C + 31) / 32), dim3(32), s, f);
     }
     // ---- S = (sum s_bl) H + <s_L, G> + <s_R, H>
-    {
+    if (rt) {
+        const int nbS = rt_blocks(2 * N, C);
+        dev_buf d_partS(sizeof(p3_st) * (size_t)C * nbS, s);
+        rt_msm_args a = {}; a.scalars = d_sLR.as<sc_st>(); a.T = (uint32_t)(2 * N); a.scalar_stride = (uint32_t)(2 * N); a.nG = (uint32_t)N; a.mode = 0; a.rt = *rt; a.partial = d_partS.as<p3_st>();
+        run_rt_msm(e, s, a, nbS, C);
+        finalize_args f = {}; f.partial = d_partS.as<p3_st>(); f.npartial = nbS; f.sHa = d_sums.as<sc_st>() + C; f.tabB = e.tabB; f.tabH = e.tabH;
+        f.out32 = d_AS.as<uint8_t>() + 32 * (size_t)C; f.count = C;
+        LAUNCH(k_finalize, dim3((C + 31) / 32), dim3(32), s, f);
+    } else {
         msm_args a = {}; a.scalars = d_sLR.as<sc_st>(); a.T = (uint32_t)(2 * N); a.scalar_stride = (uint32_t)(2 * N);
         a.seg[0] = mk_seg(g.G, (uint32_t)N, 0, 0); a.seg[1] = mk_seg(g.H, (uint32_t)N, 0, 0); a.nseg = 2; a.out = d_win.as<p3_st>();
-        run_msm(e, a, C);
+        run_msm(e, s, a, C);
         finalize_args f = {}; f.windows = d_win.as<p3_st>(); f.sHa = d_sums.as<sc_st>() + C; f.tabB = e.tabB; f.tabH = e.tabH;
         f.out32 = d_AS.as<uint8_t>() + 32 * (size_t)C; f.count = C;
         LAUNCH(k_finalize, dim3((C + 31) / 32), dim3(32), s, f);
@@ -235,23 +284,48 @@ static void prove_chunks(rofl_engine &e, const char *label, int n, int m, int C,
     std::vector<uint8_t> hLR(64 * (size_t)C);
     std::vector<sc> u(C), uinv(C);
     std::vector<sc_st> h_u2(C), h_uinv2(C); std::vector<int8_t> h_nafs(512 * (size_t)C);
+    // RT path: the first r_unf rounds take L/R as table MSMs over the ORIGINAL generators (no generator folding), then one
+    // catch-up fold builds G"/H" of length N >> r_unf directly from the tables
+    const int r_unf = rt ? std::min(e.rt_unfold, lgN) : 0;
+    const int nbU = rt ? rt_blocks(N, 2 * C) : 1;
+    const uint32_t cstride = 1u << (r_unf > 0 ? r_unf : 0);
+    std::vector<sc> cG((size_t)C * cstride), cH((size_t)C * cstride);
+    std::vector<sc_st> h_cGH(2 * (size_t)C * cstride);
+    for (int c = 0; c < C; c++) { sc_from_u64(cG[(size_t)c * cstride], 1); sc_from_u64(cH[(size_t)c * cstride], 1); }
+    dev_buf d_cGH(sizeof(sc_st) * 2 * (size_t)C * cstride, s), d_partU(sizeof(p3_st) * 2 * (size_t)C * nbU, s), d_digs(sizeof(int16_t) * 2 * (size_t)C * cstride * 32, s);
     int round = 0;
     for (size_t np = N / 2; np >= 1; np /= 2, round++) {
         const int nbI = (int)std::min<size_t>(256, (np + 255) / 256);
-        LAUNCH_COOP(k_ipp_scalars, dim3(nbI, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), msmL, msmR, d_part.as<sc_st>(), N, (uint32_t)np);
-        LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_part.as<sc_st>(), nbI, 2);
-        msm_args aL = {}, aR = {};
-        aL.scalars = msmL; aL.T = (uint32_t)(2 * np); aL.scalar_stride = (uint32_t)(2 * np); aL.nseg = 2; aL.out = d_win.as<p3_st>();
-        aR = aL; aR.scalars = msmR; aR.out = d_win.as<p3_st>() + (size_t)C * MSM_WINDOWS;
-        if (round == 0) {
-            aL.seg[0] = mk_seg(g.G + np, (uint32_t)np, 0, 0); aL.seg[1] = mk_seg(g.H, (uint32_t)np, 0, 0);
-            aR.seg[0] = mk_seg(g.G, (uint32_t)np, 0, 0);      aR.seg[1] = mk_seg(g.H + np, (uint32_t)np, 0, 0);
+        const bool unfolded = round < r_unf;
+        if (unfolded) {
+            const uint32_t nblk = 1u << round;
+            for (int c = 0; c < C; c++) for (uint32_t t = 0; t < nblk; t++) { sc_to_st(h_cGH[(size_t)c * cstride + t], cG[(size_t)c * cstride + t]); sc_to_st(h_cGH[((size_t)C + c) * cstride + t], cH[(size_t)c * cstride + t]); }
+            rt_h2d(d_cGH.p, h_cGH.data(), sizeof(sc_st) * h_cGH.size(), s);
+            const int nbQ = (int)std::min<size_t>(256, (N / 2 + 255) / 256);
+            dev_buf d_partQ(sizeof(sc_st) * 2 * (size_t)C * nbQ, s);
+            LAUNCH_COOP(k_ipp_scalars_unf, dim3(nbQ, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), d_cGH.as<sc_st>(), d_cGH.as<sc_st>() + (size_t)C * cstride, cstride,
+                        msmL, msmR, d_partQ.as<sc_st>(), N, (uint32_t)np, nblk);
+            LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_partQ.as<sc_st>(), nbQ, 2);
+            rt_msm_args aL = {}; aL.scalars = msmL; aL.T = (uint32_t)N; aL.scalar_stride = (uint32_t)N; aL.nG = (uint32_t)(N / 2); aL.np = (uint32_t)np; aL.mode = 1; aL.rt = *rt; aL.partial = d_partU.as<p3_st>();
+            rt_msm_args aR = aL; aR.scalars = msmR; aR.mode = 2; aR.partial = d_partU.as<p3_st>() + (size_t)C * nbU;
+            run_rt_msm(e, s, aL, nbU, C); run_rt_msm(e, s, aR, nbU, C);
+            finalize_args f = {}; f.partial = d_partU.as<p3_st>(); f.npartial = nbU; f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
+            f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
+            LAUNCH(k_finalize, dim3((2 * C + 31) / 32), dim3(32), s, f);
         } else {
-            aL.seg[0] = mk_seg(d_Gf.as<p3_st>() + np, (uint32_t)np, (uint32_t)half, 1); aL.seg[1] = mk_seg(d_Hf.as<p3_st>(), (uint32_t)np, (uint32_t)half, 1);
-            aR.seg[0] = mk_seg(d_Gf.as<p3_st>(), (uint32_t)np, (uint32_t)half, 1);      aR.seg[1] = mk_seg(d_Hf.as<p3_st>() + np, (uint32_t)np, (uint32_t)half, 1);
-        }
-        run_msm(e, aL, C); run_msm(e, aR, C);
-        {
+            LAUNCH_COOP(k_ipp_scalars, dim3(nbI, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), msmL, msmR, d_part.as<sc_st>(), N, (uint32_t)np);
+            LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_part.as<sc_st>(), nbI, 2);
+            msm_args aL = {}, aR = {};
+            aL.scalars = msmL; aL.T = (uint32_t)(2 * np); aL.scalar_stride = (uint32_t)(2 * np); aL.nseg = 2; aL.out = d_win.as<p3_st>();
+            aR = aL; aR.scalars = msmR; aR.out = d_win.as<p3_st>() + (size_t)C * MSM_WINDOWS;
+            if (round == 0) {
+                aL.seg[0] = mk_seg(g.G + np, (uint32_t)np, 0, 0); aL.seg[1] = mk_seg(g.H, (uint32_t)np, 0, 0);
+                aR.seg[0] = mk_seg(g.G, (uint32_t)np, 0, 0);      aR.seg[1] = mk_seg(g.H + np, (uint32_t)np, 0, 0);
+            } else {
+                aL.seg[0] = mk_seg(d_Gf.as<p3_st>() + np, (uint32_t)np, (uint32_t)half, 1); aL.seg[1] = mk_seg(d_Hf.as<p3_st>(), (uint32_t)np, (uint32_t)half, 1);
+                aR.seg[0] = mk_seg(d_Gf.as<p3_st>(), (uint32_t)np, (uint32_t)half, 1);      aR.seg[1] = mk_seg(d_Hf.as<p3_st>() + np, (uint32_t)np, (uint32_t)half, 1);
+            }
+            run_msm(e, s, aL, C); run_msm(e, s, aR, C);
             finalize_args f = {}; f.windows = d_win.as<p3_st>(); f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
             f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
             LAUNCH(k_finalize, dim3((2 * C + 31) / 32), dim3(32), s, f);
@@ -271,18 +345,35 @@ static void prove_chunks(rofl_engine &e, const char *label, int n, int m, int C,
             sc_mul(u2, u[c], u[c]); sc_mul(ui2, uinv[c], uinv[c]);
             st_to_sc(yp, h_yinvpow2[32 * c + lgnp]); sc_mul(sH, ui2, yp);            // u^-2 y^-np
             sc_to_st(h_u2[c], u2); sc_to_st(h_uinv2[c], ui2);
-            sc_naf(&h_nafs[512 * c], u2, FOLD_W); sc_naf(&h_nafs[512 * c + 256], sH, FOLD_W);
+            if (unfolded) {       // coefficient tables of the next level: c'[2t] = c[t], c'[2t+1] = c[t] * s
+                const uint32_t nblk = 1u << round; sc *g0 = &cG[(size_t)c * cstride], *h0 = &cH[(size_t)c * cstride];
+                for (uint32_t t = nblk; t-- > 0;) { sc gt = g0[t], ht = h0[t]; g0[2 * t] = gt; sc_mul(g0[2 * t + 1], gt, u2); h0[2 * t] = ht; sc_mul(h0[2 * t + 1], ht, sH); }
+            } else { sc_naf(&h_nafs[512 * c], u2, FOLD_W); sc_naf(&h_nafs[512 * c + 256], sH, FOLD_W); }
             sc_mul(uprod[c], uprod[c], u[c]); sc_mul(uinvprod[c], uinvprod[c], uinv[c]);
         }
         rt_h2d(d_u2.p, h_u2.data(), sizeof(sc_st) * C, s); rt_h2d(d_uinv2.p, h_uinv2.data(), sizeof(sc_st) * C, s);
         LAUNCH(k_ipp_fold_scalars, dim3((unsigned)((np + 255) / 256), C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_u2.as<sc_st>(), d_uinv2.as<sc_st>(), N, (uint32_t)np);
-        if (np >= 2) {
+        if (unfolded) {
+            if (round + 1 == r_unf && np >= 2) {          // catch-up: G", H" of length np straight from the tables
+                const uint32_t nblk = 1u << r_unf;
+                std::vector<int16_t> h_digs(2 * (size_t)C * nblk * 32);
+                for (int c = 0; c < C; c++) for (uint32_t t = 0; t < nblk; t++) {
+                    rt_digits(&h_digs[(((size_t)c * 2 + 0) * nblk + t) * 32], cG[(size_t)c * cstride + t]);
+                    rt_digits(&h_digs[(((size_t)c * 2 + 1) * nblk + t) * 32], cH[(size_t)c * cstride + t]);
+                }
+                rt_h2d(d_digs.p, h_digs.data(), sizeof(int16_t) * h_digs.size(), s);
+                catchup_args ca = {}; ca.rt = *rt; ca.Gf = d_Gf.as<p3_st>(); ca.Hf = d_Hf.as<p3_st>(); ca.digits = d_digs.as<int16_t>(); ca.nr = (uint32_t)np; ca.nblk = nblk; ca.stride = (uint32_t)half;
+                void *tk = rt_prof_begin(PROF_FOLD, s);
+                LAUNCH_COOP(k_rt_catchup, dim3((unsigned)((np + 127) / 128), C, 2), dim3(128), s, ca);
+                rt_prof_end(PROF_FOLD, tk, s);
+            }
+        } else if (np >= 2) {
             rt_h2d(d_nafs.p, h_nafs.data(), h_nafs.size(), s);
             fold_args fa = {}; fa.Gn = round == 0 ? g.G : nullptr; fa.Hn = round == 0 ? g.H : nullptr;
             fa.Gf = d_Gf.as<p3_st>(); fa.Hf = d_Hf.as<p3_st>(); fa.nafs = d_nafs.as<int8_t>(); fa.np = (uint32_t)np; fa.stride = (uint32_t)half;
-            rt_prof_begin(PROF_FOLD, s);
+            void *tk = rt_prof_begin(PROF_FOLD, s);
             LAUNCH_COOP(k_ipp_fold_points, dim3((unsigned)((np + 127) / 128), C, 2), dim3(128), s, fa);
-            rt_prof_end(PROF_FOLD, s);
+            rt_prof_end(PROF_FOLD, tk, s);
         }
     }
     // ---- final a, b: a = a^ prod u_k, b = b^ prod u_k^-1
@@ -295,6 +386,19 @@ static void prove_chunks(rofl_engine &e, const char *label, int n, int m, int C,
         uint8_t *o = h_proofs + plen * c + 224 + 64 * lgN;
         sc_tobytes(o, a); sc_tobytes(o + 32, b);
     }
+}
+
+
+// run f(group, c0, c1, stream) for `groups` contiguous chunk ranges concurrently (one host thread + one stream per group)
+template <class F> static void for_chunk_groups(rofl_engine &e, size_t C, F f) {
+    size_t G = std::max<size_t>(1, std::min<size_t>({(size_t)e.groups, e.gstreams.size(), C}));
+    if (G == 1) { f(0, (size_t)0, C, e.stream); return; }
+    std::vector<std::thread> th; std::vector<std::string> errs(G);
+    for (size_t gi = 0; gi < G; gi++) th.emplace_back([&, gi] {
+        try { f(gi, C * gi / G, C * (gi + 1) / G, e.gstreams[gi]); } catch (const std::exception &ex) { errs[gi] = ex.what(); }
+    });
+    for (auto &t : th) t.join();
+    for (auto &m : errs) if (!m.empty()) throw std::runtime_error(m);
 }
 
 // =============================================================================================================================
@@ -316,19 +420,24 @@ static int engine_range_prove(rofl_engine &e, const float *d_values, const uint8
     commit_args ca = {}; ca.values = d_values; ca.blind = d_blind; ca.D = D; ca.Dp = Dp; ca.n_bits = n_bits; ca.frac = frac;
     ca.shift_bits = range; ca.mx = clip_max_f(range, n_bits, frac); ca.mn = -ca.mx; ca.tabB = e.tabB; ca.tabH = e.tabH;
     ca.V = d_V.as<uint8_t>(); ca.C = d_commits; ca.vals = d_vals.as<uint64_t>(); ca.blind_sc = d_bl.as<sc_st>(); ca.flags = d_flags.as<int>();
-    rt_prof_begin(PROF_COMMIT, s);
+    void *tk = rt_prof_begin(PROF_COMMIT, s);
     LAUNCH(k_commit, dim3((unsigned)((Dp + 127) / 128)), dim3(128), s, ca);
-    rt_prof_end(PROF_COMMIT, s);
+    rt_prof_end(PROF_COMMIT, tk, s);
     int flags = 0; rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_sync(s);
     if (flags & 2) return 2;                                                         // :26-29
     if (flags & 1) return -98;
     if (!bitsize_ok) return -1;
     if (!chunk_ok) return -99;
     gens_entry &g = engine_gens(e, range, (int)m);
+    rt_tables rt; const bool have_rt = engine_rt(e, g, range, (int)m, rt);
     std::vector<uint8_t> keys(32 * C);
     for (size_t c = 0; c < C; c++) derive_key(&keys[32 * c], seed, DOM_RANGE_PROVE, c);
-    prove_chunks(e, "RangeProof", range, (int)m, (int)C, g, d_vals.as<uint64_t>(), d_bl.as<sc_st>(), d_V.as<uint8_t>(), keys, h_proofs);
-    *proof_len = 32 * (9 + 2 * (size_t)ilog2_sz((size_t)range * m)); *n_proofs = C;
+    const size_t plen = 32 * (9 + 2 * (size_t)ilog2_sz((size_t)range * m));
+    for_chunk_groups(e, C, [&](size_t, size_t c0, size_t c1, cudaStream_t gs) {
+        std::vector<uint8_t> k(keys.begin() + 32 * c0, keys.begin() + 32 * c1);
+        prove_chunks(e, gs, "RangeProof", range, (int)m, (int)(c1 - c0), g, have_rt ? &rt : nullptr, d_vals.as<uint64_t>() + c0 * m, d_bl.as<sc_st>() + c0 * m, d_V.as<uint8_t>() + 32 * c0 * m, k, h_proofs + plen * c0);
+    });
+    *proof_len = plen; *n_proofs = C;
     return 0;
 }
 
@@ -336,9 +445,8 @@ static int engine_range_prove(rofl_engine &e, const float *d_values, const uint8
 // RangeProof::verify_multiple for C chunks: d_Vp3 / h_V32 hold C*m (shifted) commitments.
 // verdict[c] = 1 accept / 0 VerificationError.  returns 0 or a negative error (-1 FormatError).
 // =============================================================================================================================
-static int verify_chunks(rofl_engine &e, const char *label, int n, int m, int C, const gens_entry &g, const p3_st *d_Vp3, const uint8_t *h_V32,
+static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int n, int m, int C, const gens_entry &g, const rt_tables *rt, const p3_st *d_Vp3, const uint8_t *h_V32,
                          const uint8_t *h_proofs, size_t plen, const std::vector<uint8_t> &keys, std::vector<int> &verdict) {
-    cudaStream_t s = e.stream;
     verdict.assign(C, 0);
     // RangeProof::from_bytes / InnerProductProof::from_bytes
     if (plen % 32 || plen < 7 * 32) return -1;
@@ -433,11 +541,22 @@ static int verify_chunks(rofl_engine &e, const char *label, int n, int m, int C,
     const int nbV = (int)std::min<size_t>(256, (N + 255) / 256);
     LAUNCH(k_verify_scalars, dim3(nbV, C), dim3(256), s, d_scal.as<sc_st>(), T, d_chal.as<sc_st>(), chs, d_yinvpow2.as<sc_st>(), d_zpow2.as<sc_st>(), n, m, lgN);
     LAUNCH(k_decompress, dim3((unsigned)(((size_t)C * nsmall + 127) / 128)), dim3(128), s, d_sp.as<p3_st>(), (uint8_t *)nullptr, d_sp32.as<uint8_t>(), (size_t)C * nsmall, (size_t)C * nsmall, (const p3_st *)nullptr, d_bad.as<int>(), (size_t)nsmall);
-    msm_args a = {}; a.scalars = d_scal.as<sc_st>(); a.T = T; a.scalar_stride = T; a.nseg = 4; a.out = d_win.as<p3_st>();
-    a.seg[0] = mk_seg(g.G, (uint32_t)N, 0, 0); a.seg[1] = mk_seg(g.H, (uint32_t)N, 0, 0);
-    a.seg[2] = mk_seg(d_Vp3, (uint32_t)m, (uint32_t)m, 1); a.seg[3] = mk_seg(d_sp.p, (uint32_t)nsmall, (uint32_t)nsmall, 1);
-    run_msm(e, a, C);
     finalize_args f = {}; f.windows = d_win.as<p3_st>(); f.tabB = e.tabB; f.tabH = e.tabH; f.is_id = d_id.as<int>(); f.count = C;
+    const int nbV2 = rt ? rt_blocks(2 * N, C) : 1;
+    dev_buf d_partV(sizeof(p3_st) * (size_t)C * nbV2, s);
+    msm_args a = {}; a.scalar_stride = T; a.out = d_win.as<p3_st>();
+    if (rt) {       // fixed generators through the radix-256 tables, only V and the proof points through the bucket MSM
+        rt_msm_args ra = {}; ra.scalars = d_scal.as<sc_st>(); ra.T = (uint32_t)(2 * N); ra.scalar_stride = T; ra.nG = (uint32_t)N; ra.mode = 0; ra.rt = *rt; ra.partial = d_partV.as<p3_st>();
+        run_rt_msm(e, s, ra, nbV2, C);
+        a.scalars = d_scal.as<sc_st>() + 2 * N; a.T = (uint32_t)(m + nsmall); a.nseg = 2;
+        a.seg[0] = mk_seg(d_Vp3, (uint32_t)m, (uint32_t)m, 1); a.seg[1] = mk_seg(d_sp.p, (uint32_t)nsmall, (uint32_t)nsmall, 1);
+        f.partial = d_partV.as<p3_st>(); f.npartial = nbV2;
+    } else {
+        a.scalars = d_scal.as<sc_st>(); a.T = T; a.nseg = 4;
+        a.seg[0] = mk_seg(g.G, (uint32_t)N, 0, 0); a.seg[1] = mk_seg(g.H, (uint32_t)N, 0, 0);
+        a.seg[2] = mk_seg(d_Vp3, (uint32_t)m, (uint32_t)m, 1); a.seg[3] = mk_seg(d_sp.p, (uint32_t)nsmall, (uint32_t)nsmall, 1);
+    }
+    run_msm(e, s, a, C);
     LAUNCH(k_finalize, dim3((C + 31) / 32), dim3(32), s, f);
     std::vector<int> h_id(C), h_bad(C);
     rt_d2h(h_id.data(), d_id.p, sizeof(int) * C, s); rt_d2h(h_bad.data(), d_bad.p, sizeof(int) * C, s);
@@ -476,12 +595,18 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
     rt_sync(s);
     if (bad) return -4;
     gens_entry &g = engine_gens(e, range, (int)m);
+    rt_tables rt; const bool have_rt = engine_rt(e, g, range, (int)m, rt);
     std::vector<uint8_t> keys(32 * C);
     for (size_t c = 0; c < C; c++) derive_key(&keys[32 * c], seed, DOM_RANGE_VERIFY, c);
-    std::vector<int> verdict;
-    int rc = verify_chunks(e, "RangeProof", range, (int)m, (int)C, g, d_Vp3.as<p3_st>(), hV.data(), h_proofs, plen, keys, verdict);
-    if (rc < 0) return rc;
-    int res = 1; for (int v : verdict) res &= v;                                   // :183-190
+    std::vector<int> rcs(e.groups + 1, 1);
+    for_chunk_groups(e, C, [&](size_t gi, size_t c0, size_t c1, cudaStream_t gs) {
+        std::vector<uint8_t> k(keys.begin() + 32 * c0, keys.begin() + 32 * c1); std::vector<int> verdict;
+        int rc = verify_chunks(e, gs, "RangeProof", range, (int)m, (int)(c1 - c0), g, have_rt ? &rt : nullptr, d_Vp3.as<p3_st>() + c0 * m, hV.data() + 32 * c0 * m, h_proofs + plen * c0, plen, k, verdict);
+        int res = 1; for (int v : verdict) res &= v;                               // :183-190
+        rcs[gi] = rc < 0 ? rc : res;
+    });
+    int res = 1;
+    for (int r : rcs) { if (r < 0) return r; res &= r; }
     return res;
 }
 
@@ -527,7 +652,7 @@ static int engine_l2_prove(rofl_engine &e, const float *h_values, const float *d
       LAUNCH(k_finalize, dim3(1), dim3(32), s, f); }
     gens_entry &g = engine_gens(e, range, 1);                                     // BulletproofGens::new(64, 1) restricted to n = range (:162)
     std::vector<uint8_t> keys(32); derive_key(keys.data(), seed, DOM_L2_PROVE, 0);
-    prove_chunks(e, "L2RangeProof", range, 1, 1, g, d_v.as<uint64_t>(), d_bl.as<sc_st>(), d_V.as<uint8_t>(), keys, h_proof);
+    prove_chunks(e, s, "L2RangeProof", range, 1, 1, g, nullptr, d_v.as<uint64_t>(), d_bl.as<sc_st>(), d_V.as<uint8_t>(), keys, h_proof);
     rt_d2h(h_commit, d_V.p, 32, s); rt_sync(s);
     *proof_len = 32 * (9 + 2 * (size_t)ilog2_sz((size_t)range));
     return 0;
@@ -551,7 +676,7 @@ static int engine_l2_verify(rofl_engine &e, const uint8_t *h_proof, size_t plen,
     gens_entry &g = engine_gens(e, range, 1);
     std::vector<uint8_t> keys(32); derive_key(keys.data(), seed, DOM_L2_VERIFY, 0);
     std::vector<int> verdict;
-    int rc = verify_chunks(e, "L2RangeProof", range, 1, 1, g, d_Vp3.as<p3_st>(), hV, h_proof, plen, keys, verdict);
+    int rc = verify_chunks(e, s, "L2RangeProof", range, 1, 1, g, nullptr, d_Vp3.as<p3_st>(), hV, h_proof, plen, keys, verdict);
     if (rc < 0) return rc;
     return verdict.empty() ? 0 : verdict[0];
 }
@@ -569,9 +694,9 @@ static int engine_square_prove(rofl_engine &e, const float *d_values, const uint
     square_args a = {}; a.values = d_values; a.value_com = d_value_com; a.r1 = d_r1; a.r2 = d_r2; a.D = D; a.n_bits = n_bits; a.frac = frac;
     uint8_t key[32]; derive_key(key, seed, DOM_SQUARE, 0); key_words(a.key, key);
     a.tabB = e.tabB; a.tabH = e.tabH; a.proofs = d_proofs; a.commits = d_commits; a.flags = d_flags.as<int>();
-    rt_prof_begin(PROF_SQUARE, s);
+    void *tk = rt_prof_begin(PROF_SQUARE, s);
     LAUNCH(k_square_prove, dim3((unsigned)((D + 127) / 128)), dim3(128), s, a);
-    rt_prof_end(PROF_SQUARE, s);
+    rt_prof_end(PROF_SQUARE, tk, s);
     int flags = 0; rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_sync(s);
     if (flags & 4) return -4;
     if (flags & 1) return -98;
@@ -582,9 +707,9 @@ static int engine_square_verify(rofl_engine &e, const uint8_t *d_proofs, const u
     std::lock_guard<std::mutex> lk(e.mu);
     cudaStream_t s = e.stream;
     dev_buf d_res(2 * sizeof(int), s); int init[2] = {1, 0}; rt_h2d(d_res.p, init, sizeof(init), s);
-    rt_prof_begin(PROF_SQUARE, s);
+    void *tk = rt_prof_begin(PROF_SQUARE, s);
     LAUNCH(k_square_verify, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_proofs, d_commits, D, e.tabB, e.tabH, d_res.as<int>());
-    rt_prof_end(PROF_SQUARE, s);
+    rt_prof_end(PROF_SQUARE, tk, s);
     int res[2]; rt_d2h(res, d_res.p, sizeof(res), s); rt_sync(s);
     if (res[1]) return -1;
     return res[0] ? 1 : 0;
@@ -601,9 +726,9 @@ static int engine_commit(rofl_engine &e, const float *d_values, const uint8_t *d
     dev_buf d_flags(sizeof(int), s); rt_memset(d_flags.p, 0, sizeof(int), s);
     commit_args ca = {}; ca.values = d_values; ca.blind = d_blind; ca.D = D; ca.Dp = D; ca.n_bits = n_bits; ca.frac = frac;
     ca.tabB = e.tabB; ca.tabH = e.tabH; ca.C = d_L; ca.R = d_blind ? d_R : nullptr; ca.flags = d_flags.as<int>();
-    rt_prof_begin(PROF_COMMIT, s);
+    void *tk = rt_prof_begin(PROF_COMMIT, s);
     LAUNCH(k_commit, dim3((unsigned)((D + 127) / 128)), dim3(128), s, ca);
-    rt_prof_end(PROF_COMMIT, s);
+    rt_prof_end(PROF_COMMIT, tk, s);
     int flags = 0; rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_sync(s);
     return (flags & 1) ? -98 : 0;
 }

@@ -84,11 +84,11 @@ HD void ge_msub_p1p1(ge_p1p1 &r, const ge_p3 &p, const ge_niels &q) {
 }
 HD void ge_madd(ge_p3 &r, const ge_p3 &p, const ge_niels &q) { ge_p1p1 t; ge_madd_p1p1(t, p, q); ge_p1p1_to_p3(r, t); }
 HD void ge_msub(ge_p3 &r, const ge_p3 &p, const ge_niels &q) { ge_p1p1 t; ge_msub_p1p1(t, p, q); ge_p1p1_to_p3(r, t); }
-// add / subtract niels by sign flag (branch-free operand swap)
+// add / subtract by sign flag with a branch-free operand swap: lanes of a warp with different signs run ONE addition
 HD void ge_madd_signed(ge_p3 &r, const ge_p3 &p, const ge_niels &q, bool neg) {
-    ge_niels n; n.yplusx = q.yplusx; n.yminusx = q.yminusx; fe_neg(n.xy2d, q.xy2d);
-    fe_cmov(n.yplusx, q.yminusx, neg); fe_cmov(n.yminusx, q.yplusx, neg);
-    if (!neg) n.xy2d = q.xy2d; else fe_carry(n.xy2d, n.xy2d);
+    ge_niels n; n.yplusx = q.yplusx; n.yminusx = q.yminusx; n.xy2d = q.xy2d;
+    fe nx; fe_neg(nx, q.xy2d); fe_carry(nx, nx);
+    fe_cmov(n.yplusx, q.yminusx, neg); fe_cmov(n.yminusx, q.yplusx, neg); fe_cmov(n.xy2d, nx, neg);
     ge_madd(r, p, n);
 }
 
@@ -122,6 +122,12 @@ HD void ge_add_cached(ge_p3 &r, const ge_p3 &p, const ge_cached &q) { ge_p1p1 t;
 HD void ge_sub_cached(ge_p3 &r, const ge_p3 &p, const ge_cached &q) { ge_p1p1 t; ge_sub_p1p1(t, p, q); ge_p1p1_to_p3(r, t); }
 HD void ge_add(ge_p3 &r, const ge_p3 &p, const ge_p3 &q) { ge_cached c; ge_p3_to_cached(c, q); ge_add_cached(r, p, c); }
 HD void ge_sub(ge_p3 &r, const ge_p3 &p, const ge_p3 &q) { ge_cached c; ge_p3_to_cached(c, q); ge_sub_cached(r, p, c); }
+HD void ge_add_cached_signed(ge_p3 &r, const ge_p3 &p, const ge_cached &q, bool neg) {
+    ge_cached n; n.YplusX = q.YplusX; n.YminusX = q.YminusX; n.Z = q.Z; n.T2d = q.T2d;
+    fe nt; fe_neg(nt, q.T2d); fe_carry(nt, nt);
+    fe_cmov(n.YplusX, q.YminusX, neg); fe_cmov(n.YminusX, q.YplusX, neg); fe_cmov(n.T2d, nt, neg);
+    ge_add_cached(r, p, n);
+}
 HD void ge_neg(ge_p3 &r, const ge_p3 &p) { fe_neg(r.X, p.X); fe_carry(r.X, r.X); r.Y = p.Y; r.Z = p.Z; fe_neg(r.T, p.T); fe_carry(r.T, r.T); }
 
 // ristretto equality (X1 Y2 == Y1 X2  or  Y1 Y2 == X1 X2)

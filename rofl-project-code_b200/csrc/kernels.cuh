@@ -38,8 +38,20 @@
 #endif
 
 // a point operand that is either a fixed generator (niels) or a variable point (p3)
-HD void acc_add_niels(ge_p3 &acc, const niels_st *p, bool neg) { ge_niels n; ld_niels(n, p); if (neg) ge_msub(acc, acc, n); else ge_madd(acc, acc, n); }
-HD void acc_add_p3(ge_p3 &acc, const p3_st *p, bool neg) { ge_p3 q; ld_p3(q, p); if (neg) ge_sub(acc, acc, q); else ge_add(acc, acc, q); }
+// the sign is applied to the operand (swap y+x / y-x, negate 2dxy resp. X and T) so that lanes of a warp with different
+// signs execute ONE addition instead of diverging into add and sub paths
+HD void acc_add_niels(ge_p3 &acc, const niels_st *p, bool neg) {
+    ge_niels n, m; ld_niels(n, p);
+    m.yplusx = n.yplusx; m.yminusx = n.yminusx; m.xy2d = n.xy2d;
+    fe nx; fe_neg(nx, n.xy2d); fe_carry(nx, nx);
+    fe_cmov(m.yplusx, n.yminusx, neg); fe_cmov(m.yminusx, n.yplusx, neg); fe_cmov(m.xy2d, nx, neg);
+    ge_madd(acc, acc, m);
+}
+HD void acc_add_p3(ge_p3 &acc, const p3_st *p, bool neg) {
+    ge_p3 q, nq; ld_p3(q, p); ge_neg(nq, q);
+    fe_cmov(q.X, nq.X, neg); fe_cmov(q.T, nq.T, neg);
+    ge_add(acc, acc, q);
+}
 
 // ===================================================================================================================
 // K0: tables
@@ -241,7 +253,7 @@ KERNEL void LB(128, 2) k_bits_sum(p3_st *partial, const uint64_t *vals, const ni
     for (size_t k = (size_t)blockIdx.x * blockDim.x + tid; k < N; k += (size_t)gridDim.x * blockDim.x) {
         size_t j = k / n; int i = (int)(k % n);
         bool bit = (vals[(size_t)c * m + j] >> i) & 1;
-        if (bit) acc_add_niels(acc, G + k, false); else acc_add_niels(acc, H + k, true);
+        acc_add_niels(acc, (bit ? G : H) + k, !bit);
     }
     block_sum_p3(acc, buf, tid, blockDim.x);
     if (tid == 0) st_p3(partial + (size_t)c * gridDim.x + blockIdx.x, acc);
@@ -284,7 +296,7 @@ HD void msm_add_term(ge_p3 &acc, const msm_args &a, uint32_t msm, uint32_t t, bo
     }
 }
 #ifdef KG_MSM
-KERNEL void LB(128, 2) k_msm(msm_args a) {
+KERNEL void LB(128, 4) k_msm(msm_args a) {
     __shared__ uint16_t sorted[MSM_TILE];
     __shared__ int cnt[MSM_BUCKETS + 1], off[MSM_BUCKETS + 2], cur[MSM_BUCKETS + 1];
     __shared__ p3_st bk[MSM_BUCKETS];
@@ -493,7 +505,7 @@ struct fold_args {
     uint32_t np, stride;
 };
 #ifdef KG_FOLD
-KERNEL void LB(128, 3) k_ipp_fold_points(fold_args a) {
+KERNEL void LB(128, 4) k_ipp_fold_points(fold_args a) {
     __shared__ int8_t naf[256];
     int c = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
     for (int t = tid; t < 256; t += blockDim.x) naf[t] = a.nafs[((size_t)c * 2 + which) * 256 + t];
@@ -758,3 +770,148 @@ void launch_k_bsgs_solve(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out_sc, flo
 void launch_k_f32_to_scalar(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const float *v, size_t D, int n_bits, int frac, int *flags);
 void launch_k_scalar_to_f32(dim3 g_, dim3 b_, cudaStream_t s_, float *out, const uint8_t *in, size_t D, int n_bits, int frac);
 void launch_k_l2_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, int *flags);
+
+// ===================================================================================================================
+// RT path: per-generator radix-256 tables in HBM (512 KB per generator: 32 windows x 128 affine-Niels multiples).
+//   Fixed generators never need doublings, buckets or sorting: s*G_j = sum_w +-RT[j][w][|d_w|-1]  (<= 32 mixed adds).
+//   Used for S, the verifier's G/H part, the first IPP rounds in "unfolded" form and the catch-up fold (engine.cuh).
+//   Layout: RT[(j*32 + w)*128 + k] = (k+1) * 256^w * Gen_j ;  j < n*m for G, then the same for H in a second array.
+// ===================================================================================================================
+#define RT_W 32
+#define RT_E 128
+struct rt_tables { const niels_st *G, *H; };
+#ifdef KG_TABLES
+// step 1: P[j*32 + w] = 256^w * Gen_j  (one thread per generator, 8 doublings per window)
+KERNEL void LB(128, 2) k_rt_shifts(p3_st *P, const niels_st *gens, uint32_t count) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    ge_niels g; ld_niels(g, gens + j);
+    ge_p3 p; ge_niels_to_p3(p, g);
+    for (int w = 0; w < RT_W; w++) {
+        st_p3(P + (size_t)j * RT_W + w, p);
+        for (int k = 0; k < 8; k++) ge_p3_dbl(p, p);
+    }
+}
+KLAUNCH(k_rt_shifts, false, (p3_st *P, const niels_st *gens, uint32_t count), (P, gens, count))
+// step 2: one thread per (row = j*32+w, group of 16 multiples): entries 16g+1 .. 16g+16 of row, converted to affine with
+// one shared inversion (Montgomery's trick over the 16 Z's)
+KERNEL void LB(128, 2) k_rt_rows(niels_st *RT, const p3_st *P, size_t rows) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * 8) return;
+    size_t row = idx >> 3; int grp = (int)(idx & 7);
+    ge_p3 base; ld_p3(base, P + row);
+    ge_cached cb; ge_p3_to_cached(cb, base);
+    // start = (16 grp + 1) * base
+    ge_p3 cur; ge_p3_0(cur);
+    { uint32_t k = 16 * grp + 1; for (int b = 7; b >= 0; b--) { ge_p3_dbl(cur, cur); if ((k >> b) & 1) ge_add_cached(cur, cur, cb); } }
+    ge_p3 pts[16]; fe pre[16], acc; fe_1(acc);
+    for (int e = 0; e < 16; e++) { pts[e] = cur; pre[e] = acc; fe_mul(acc, acc, cur.Z); if (e < 15) ge_add_cached(cur, cur, cb); }
+    fe inv; fe_invert(inv, acc);
+    for (int e = 15; e >= 0; e--) {
+        fe zinv; fe_mul(zinv, inv, pre[e]); fe_mul(inv, inv, pts[e].Z);
+        ge_niels n; ge_p3_to_niels(n, pts[e], zinv);
+        st_niels(RT + row * RT_E + 16 * grp + e, n);
+    }
+}
+KLAUNCH(k_rt_rows, false, (niels_st *RT, const p3_st *P, size_t rows), (RT, P, rows))
+#endif
+
+// radix-256 signed digits of a scalar: d_w = byte_w(x + 0x7f..7f) - 127 for all 32 windows at once
+HD void rt_digits(int16_t d[32], const sc &x) {
+    uint64_t c = 0; uint32_t wds[8];
+    for (int i = 0; i < 8; i++) { c += (uint64_t)x.v[i] + 0x7f7f7f7fu; wds[i] = (uint32_t)c; c >>= 32; }
+    for (int w = 0; w < 32; w++) d[w] = (int16_t)((int)((wds[w >> 2] >> (8 * (w & 3))) & 0xff) - 127);
+}
+HD void rt_mul_acc(ge_p3 &acc, const niels_st *row0, const sc &x) {          // acc += x * Gen ; row0 = RT + j*32*128
+    int16_t d[32]; rt_digits(d, x);
+    for (int w = 0; w < RT_W; w++) {
+        int dw = d[w];
+        if (dw != 0) acc_add_niels(acc, row0 + (size_t)w * RT_E + (dw > 0 ? dw : -dw) - 1, dw < 0);
+    }
+}
+// direct table MSM: out partial[msm*gridDim.x + blockIdx.x] = sum over this block's terms of s_t * Gen_{map(t)}.
+//   terms t < T per msm; scalars[msm*scalar_stride + t]; generator of term t:
+//     mode 0: t < nG -> G[t], else H[t - nG]                                         (S, verifier: all generators in order)
+//     mode 1/2 (unfolded IPP round, np = half block): the G part uses the hi (mode 1, "L") or lo (mode 2, "R") half of every
+//       2np block, the H part the opposite half:  q < nG: j = (q/np)*2np + (hiG ? np : 0) + q%np
+struct rt_msm_args { const sc_st *scalars; uint32_t T, scalar_stride, nG, np; int mode; rt_tables rt; p3_st *partial; };
+#ifdef KG_MSM
+KERNEL void LB(128, 4) k_rt_msm(rt_msm_args a) {
+    __shared__ p3_st buf[128];
+    const int tid = threadIdx.x; const uint32_t msm = blockIdx.y;
+    const sc_st *scal = a.scalars + (size_t)msm * a.scalar_stride;
+    ge_p3 acc; ge_p3_0(acc);
+    for (uint32_t t = blockIdx.x * blockDim.x + tid; t < a.T; t += gridDim.x * blockDim.x) {
+        sc x; ld_sc(x, scal + t);
+        if (sc_iszero(x)) continue;
+        bool isG = t < a.nG; uint32_t q = isG ? t : t - a.nG, j = q;
+        if (a.mode) { bool hi = (a.mode == 1) == isG; j = (q / a.np) * 2 * a.np + (hi ? a.np : 0) + q % a.np; }
+        rt_mul_acc(acc, (isG ? a.rt.G : a.rt.H) + (size_t)j * RT_W * RT_E, x);
+    }
+    block_sum_p3(acc, buf, tid, blockDim.x);
+    if (tid == 0) st_p3(a.partial + (size_t)msm * gridDim.x + blockIdx.x, acc);
+}
+KLAUNCH(k_rt_msm, true, (rt_msm_args a), (a))
+#endif
+void launch_k_rt_shifts(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *P, const niels_st *gens, uint32_t count);
+void launch_k_rt_rows(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *RT, const p3_st *P, size_t rows);
+void launch_k_rt_msm(dim3 g_, dim3 b_, cudaStream_t s_, rt_msm_args a);
+
+// unfolded IPP round k (np = N >> (k+1), 2^k blocks of 2np original generators each; coefficient tables cG/cH[c*cstride + t]):
+//   L: G-term (t,i) -> a^[i] cG[t] on G[t*2np + np + i];  H-term -> b^[np+i] y^-i cH[t] on H[t*2np + i]
+//   R: G-term -> a^[np+i] cG[t] on G[t*2np + i];           H-term -> b^[i] y^-(np+i) cH[t] on H[t*2np + np + i]
+//   msmL / msmR: [c][N] scalars laid out for k_rt_msm modes 1 / 2 (N/2 G-terms then N/2 H-terms, term q = t*np + i)
+#ifdef KG_SCALAR
+KERNEL void LB(256, 1) k_ipp_scalars_unf(const sc_st *a, const sc_st *b, const sc_st *yinv, const sc_st *cG, const sc_st *cH, uint32_t cstride,
+                                         sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np, uint32_t nblk) {
+    __shared__ sc_st buf[256];
+    int c = blockIdx.y, tid = threadIdx.x;
+    const sc_st *ac = a + (size_t)c * N, *bc = b + (size_t)c * N, *yc = yinv + (size_t)c * N;
+    sc_st *L = msmL + (size_t)c * N, *R = msmR + (size_t)c * N;
+    const uint32_t half = (uint32_t)(N / 2);
+    sc cL, cR; sc_0(cL); sc_0(cR);
+    for (uint32_t q = blockIdx.x * blockDim.x + tid; q < half; q += gridDim.x * blockDim.x) {
+        uint32_t t = q / np, i = q % np;
+        sc alo, ahi, blo, bhi, ylo, yhi, g, h, x;
+        ld_sc(alo, ac + i); ld_sc(ahi, ac + np + i); ld_sc(blo, bc + i); ld_sc(bhi, bc + np + i); ld_sc(ylo, yc + i); ld_sc(yhi, yc + np + i);
+        ld_sc(g, cG + (size_t)c * cstride + t); ld_sc(h, cH + (size_t)c * cstride + t);
+        if (t == 0) { sc_mul(x, alo, bhi); sc_add(cL, cL, x); sc_mul(x, ahi, blo); sc_add(cR, cR, x); }
+        sc_mul(x, alo, g); st_sc(L + q, x);
+        sc_mul(x, bhi, ylo); sc_mul(x, x, h); st_sc(L + half + q, x);
+        sc_mul(x, ahi, g); st_sc(R + q, x);
+        sc_mul(x, blo, yhi); sc_mul(x, x, h); st_sc(R + half + q, x);
+    }
+    (void)nblk;
+    block_sum_sc(cL, buf, tid, blockDim.x); block_sum_sc(cR, buf, tid, blockDim.x);
+    if (tid == 0) { sc_st *o = partial + ((size_t)c * gridDim.x + blockIdx.x) * 2; st_sc(o, cL); st_sc(o + 1, cR); }
+}
+KLAUNCH(k_ipp_scalars_unf, true, (const sc_st *a, const sc_st *b, const sc_st *yinv, const sc_st *cG, const sc_st *cH, uint32_t cstride, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np, uint32_t nblk),
+        (a, b, yinv, cG, cH, cstride, msmL, msmR, partial, N, np, nblk))
+#endif
+// catch-up fold after r unfolded rounds: out[c][i] = sum_{t < nblk} coef[t] * Gen[t*nr + i], i < nr = N >> r, through the RT tables.
+//   digits[((c*2 + which)*nblk + t)*32 + w] = radix-256 signed digits of the coefficient (host-computed, uniform per chunk)
+//   grid (blocks, C, 2): z = 0 -> G, 1 -> H
+struct catchup_args { rt_tables rt; p3_st *Gf, *Hf; const int16_t *digits; uint32_t nr, nblk, stride; };
+#ifdef KG_FOLD
+KERNEL void LB(128, 4) k_rt_catchup(catchup_args a) {
+    __shared__ int16_t dg[64 * 32];
+    int c = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
+    for (uint32_t t = tid; t < a.nblk * 32; t += blockDim.x) dg[t] = a.digits[((size_t)c * 2 + which) * a.nblk * 32 + t];
+    __syncthreads();
+    uint32_t i = blockIdx.x * blockDim.x + tid;
+    if (i >= a.nr) return;
+    const niels_st *RT = which ? a.rt.H : a.rt.G;
+    ge_p3 acc; ge_p3_0(acc);
+    for (uint32_t t = 0; t < a.nblk; t++) {
+        const niels_st *row0 = RT + ((size_t)t * a.nr + i) * RT_W * RT_E;
+        for (int w = 0; w < RT_W; w++) {
+            int d = dg[t * 32 + w];
+            if (d != 0) acc_add_niels(acc, row0 + (size_t)w * RT_E + (d > 0 ? d : -d) - 1, d < 0);
+        }
+    }
+    st_p3((which ? a.Hf : a.Gf) + (size_t)c * a.stride + i, acc);
+}
+KLAUNCH(k_rt_catchup, true, (catchup_args a), (a))
+#endif
+void launch_k_ipp_scalars_unf(dim3 g_, dim3 b_, cudaStream_t s_, const sc_st *a, const sc_st *b, const sc_st *yinv, const sc_st *cG, const sc_st *cH, uint32_t cstride, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np, uint32_t nblk);
+void launch_k_rt_catchup(dim3 g_, dim3 b_, cudaStream_t s_, catchup_args a);

@@ -8,22 +8,20 @@ static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
 struct prof_pair { cudaEvent_t a, b; };
 static std::vector<prof_pair> g_prof_events[PROF_SLOTS];
-static cudaEvent_t g_prof_open[PROF_SLOTS];
 static double g_prof_ms[PROF_SLOTS];
 static long g_prof_launch[PROF_SLOTS];
 static std::atomic<long> g_launches{0};
 
 void rt_count_launch(const char *) { g_launches++; }
-void rt_prof_begin(int slot, cudaStream_t s) {
-    if (!g_prof_on.load()) return;
-    std::lock_guard<std::mutex> lk(g_prof_mu);
-    cudaEvent_t a; cudaEventCreate(&a); cudaEventRecord(a, s); g_prof_open[slot] = a;
+void *rt_prof_begin(int, cudaStream_t s) {
+    if (!g_prof_on.load()) return nullptr;
+    cudaEvent_t a; cudaEventCreate(&a); cudaEventRecord(a, s); return (void *)a;
 }
-void rt_prof_end(int slot, cudaStream_t s) {
-    if (!g_prof_on.load()) return;
-    std::lock_guard<std::mutex> lk(g_prof_mu);
+void rt_prof_end(int slot, void *token, cudaStream_t s) {
+    if (!token) return;
     cudaEvent_t b; cudaEventCreate(&b); cudaEventRecord(b, s);
-    g_prof_events[slot].push_back({g_prof_open[slot], b}); g_prof_launch[slot]++;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_events[slot].push_back({(cudaEvent_t)token, b}); g_prof_launch[slot]++;
 }
 static void prof_collect() {
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -54,6 +52,11 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
         // keep freed scratch in the pool between calls
         cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
         unsigned hc = std::thread::hardware_concurrency(); c->e.host_threads = hc ? (int)std::min(hc, 32u) : 8;
+        c->e.gstreams.push_back(c->e.stream);
+        for (int i = 1; i < 4; i++) { cudaStream_t st; rt_check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate"); c->e.gstreams.push_back(st); }
+        if (const char *gv = getenv("ROFL_GROUPS")) c->e.groups = std::max(1, std::min(4, atoi(gv)));
+        if (const char *gv = getenv("ROFL_RT")) c->e.use_rt = atoi(gv);                                   // 0 disables the generator tables
+        if (const char *gv = getenv("ROFL_UNFOLD")) c->e.rt_unfold = std::max(0, std::min(6, atoi(gv)));   // unfolded IPP rounds (RT path)
         engine_init(c->e);
         *out = c;
         return ROFL_OK;
@@ -61,6 +64,6 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
 }
 extern "C" void rofl_ctx_destroy(rofl_ctx *c) {
     if (!c) return;
-    try { cudaSetDevice(c->e.device); engine_destroy(c->e); cudaStreamDestroy(c->e.stream); } catch (...) {}
+    try { cudaSetDevice(c->e.device); engine_destroy(c->e); for (auto st : c->e.gstreams) cudaStreamDestroy(st); } catch (...) {}
     delete c;
 }

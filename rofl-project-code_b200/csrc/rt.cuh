@@ -14,9 +14,10 @@ inline void rt_d2h(void *h, const void *d, size_t n, cudaStream_t) { memcpy(h, d
 inline void rt_d2d(void *d, const void *s, size_t n, cudaStream_t) { memcpy(d, s, n); }
 inline void rt_memset(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); }
 inline void rt_sync(cudaStream_t) {}
+inline size_t rt_free_mem() { return (size_t)8 << 30; }
 struct rt_event { };
-inline void rt_prof_begin(int, cudaStream_t) {}
-inline void rt_prof_end(int, cudaStream_t) {}
+inline void *rt_prof_begin(int, cudaStream_t) { return nullptr; }
+inline void rt_prof_end(int, void *, cudaStream_t) {}
 #else
 #include <cuda_runtime.h>
 inline void rt_check(cudaError_t e, const char *what) {
@@ -30,8 +31,9 @@ inline void rt_d2h(void *h, const void *d, size_t n, cudaStream_t s) { rt_check(
 inline void rt_d2d(void *d, const void *s_, size_t n, cudaStream_t s) { rt_check(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s), "d2d"); }
 inline void rt_memset(void *d, int v, size_t n, cudaStream_t s) { rt_check(cudaMemsetAsync(d, v, n, s), "memset"); }
 inline void rt_sync(cudaStream_t s) { rt_check(cudaStreamSynchronize(s), "sync"); }
-void rt_prof_begin(int slot, cudaStream_t s);
-void rt_prof_end(int slot, cudaStream_t s);
+inline size_t rt_free_mem() { size_t f = 0, t = 0; cudaMemGetInfo(&f, &t); return f; }
+void *rt_prof_begin(int slot, cudaStream_t s);
+void rt_prof_end(int slot, void *token, cudaStream_t s);
 #endif
 
 #define LAUNCH(k, grid, block, stream, ...) launch_##k(grid, block, stream, __VA_ARGS__)

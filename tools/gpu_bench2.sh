@@ -1,0 +1,11 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+for g in 1 2 4; do ROFL_GROUPS=$g timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_g$g.json 2> gpurun_out/bench_g$g.err; python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_g$g.json"))
+print("groups=$g value=%.0f prove_ms=%.1f verify_ms=%.1f fold_ms=%.1f msm_ms=%.1f e2e=%.0f launches=%d" % (d["value"], d["prove_ms"], d["verify_ms"], d["roofline"]["kernel_ms_per_step"], d["roofline"]["msm_ms_per_step"], d["e2e"]["value"], d["gpu_launches"]))
+PY
+done
