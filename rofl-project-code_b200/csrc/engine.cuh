@@ -63,6 +63,8 @@ template <class F> static void parallel_for(size_t n, int threads, F f) {
     for (size_t t = 0; t < nt; t++) th.emplace_back([=] { for (size_t i = t; i < n; i += nt) f(i); });
     for (auto &x : th) x.join();
 }
+// light per-chunk host work (a few Keccak-f per chunk): thread start-up would cost more than the work
+template <class F> static void serial_for(size_t n, F f) { for (size_t i = 0; i < n; i++) f(i); }
 // Montgomery's trick: v[i] <- v[i]^-1 (all non-zero)
 static inline void sc_batch_invert(std::vector<sc> &v) {
     size_t n = v.size(); if (!n) return;
@@ -254,7 +256,7 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     // ---- x, shares, w
     std::vector<sc> x(C), w(C);
     std::vector<sc_st> h_x(C), h_w2(2 * (size_t)C);
-    parallel_for(C, e.host_threads, [&](size_t c) {
+    serial_for(C, [&](size_t c) {
         transcript &t = ts[c]; uint8_t *o = h_proofs + plen * c;
         memcpy(o + 64, &hT[32 * c], 32); memcpy(o + 96, &hT[32 * (C + c)], 32);
         transcript_append(t, "T_1", o + 64, 32); transcript_append(t, "T_2", o + 96, 32);
@@ -293,6 +295,8 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     std::vector<sc_st> h_cGH(2 * (size_t)C * cstride);
     for (int c = 0; c < C; c++) { sc_from_u64(cG[(size_t)c * cstride], 1); sc_from_u64(cH[(size_t)c * cstride], 1); }
     dev_buf d_cGH(sizeof(sc_st) * 2 * (size_t)C * cstride, s), d_partU(sizeof(p3_st) * 2 * (size_t)C * nbU, s), d_digs(sizeof(int16_t) * 2 * (size_t)C * cstride * 32, s);
+    const int nbQ = (int)std::min<size_t>(256, (N / 2 + 255) / 256);
+    dev_buf d_partQ(sizeof(sc_st) * 2 * (size_t)C * nbQ, s);
     int round = 0;
     for (size_t np = N / 2; np >= 1; np /= 2, round++) {
         const int nbI = (int)std::min<size_t>(256, (np + 255) / 256);
@@ -301,8 +305,6 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             const uint32_t nblk = 1u << round;
             for (int c = 0; c < C; c++) for (uint32_t t = 0; t < nblk; t++) { sc_to_st(h_cGH[(size_t)c * cstride + t], cG[(size_t)c * cstride + t]); sc_to_st(h_cGH[((size_t)C + c) * cstride + t], cH[(size_t)c * cstride + t]); }
             rt_h2d(d_cGH.p, h_cGH.data(), sizeof(sc_st) * h_cGH.size(), s);
-            const int nbQ = (int)std::min<size_t>(256, (N / 2 + 255) / 256);
-            dev_buf d_partQ(sizeof(sc_st) * 2 * (size_t)C * nbQ, s);
             LAUNCH_COOP(k_ipp_scalars_unf, dim3(nbQ, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), d_cGH.as<sc_st>(), d_cGH.as<sc_st>() + (size_t)C * cstride, cstride,
                         msmL, msmR, d_partQ.as<sc_st>(), N, (uint32_t)np, nblk);
             LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_partQ.as<sc_st>(), nbQ, 2);
@@ -332,7 +334,7 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         }
         rt_d2h(hLR.data(), d_LR.p, hLR.size(), s);
         rt_sync(s);
-        parallel_for(C, e.host_threads, [&](size_t c) {
+        serial_for(C, [&](size_t c) {
             transcript &t = ts[c]; uint8_t *o = h_proofs + plen * c + 224 + 64 * round;
             memcpy(o, &hLR[32 * c], 32); memcpy(o + 32, &hLR[32 * (C + c)], 32);
             transcript_append(t, "L", o, 32); transcript_append(t, "R", o + 32, 32);
