@@ -52,6 +52,9 @@ int rofl_ctx_create(rofl_ctx **out, int device);
 void rofl_ctx_destroy(rofl_ctx *ctx);
 const char *rofl_last_error(void);
 void rofl_set_host_threads(rofl_ctx *ctx, int n);          /* host threads used for the per-chunk Merlin transcripts */
+/* tuning knobs (results never depend on them): "use_rt" 0/1 generator tables, "rt_unfold" unfolded IPP rounds, "groups" chunk
+ * groups on separate streams, "tail_np" largest half-size handled by the fused tail kernel (0 = off).  returns 0, -2 unknown name */
+int rofl_set_option(rofl_ctx *ctx, const char *name, long value);
 
 /* ---- sizes ---------------------------------------------------------------------------------------------------- */
 size_t rofl_next_pow2(size_t v);                           /* range_proof_vec/mod.rs:237-246                          */

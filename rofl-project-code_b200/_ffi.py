@@ -13,6 +13,7 @@ _SIGS = {
     "rofl_ctx_destroy": (None, [c_vp]),
     "rofl_last_error": (C.c_char_p, []),
     "rofl_set_host_threads": (None, [c_vp, C.c_int]),
+    "rofl_set_option": (C.c_int, [c_vp, C.c_char_p, C.c_long]),
     "rofl_next_pow2": (c_sz, [c_sz]),
     "rofl_range_proof_len": (c_sz, [c_sz]),
     "rofl_range_proof_shape": (None, [c_sz, C.c_int, c_sz, C.POINTER(c_sz), C.POINTER(c_sz)]),
@@ -98,6 +99,14 @@ class Api:
     def close(self):
         if self.h:
             self.lib.rofl_ctx_destroy(self.h); self.h = None
+
+    def set_option(self, name, value):
+        rc = self.lib.rofl_set_option(self.h, name.encode(), int(value))
+        if rc != 0:
+            raise self._err(rc)
+
+    def set_use_rt(self, on):
+        self.set_option("use_rt", 1 if on else 0)
 
     def _err(self, rc):
         return RoflError(rc, (self.lib.rofl_last_error() or b"").decode())

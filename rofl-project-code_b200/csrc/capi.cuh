@@ -11,6 +11,17 @@ static thread_local std::string g_last_error;
 
 extern "C" const char *rofl_last_error(void) { return g_last_error.c_str(); }
 extern "C" void rofl_set_host_threads(rofl_ctx *c, int n) { if (c && n > 0) c->e.host_threads = n; }
+extern "C" int rofl_set_option(rofl_ctx *c, const char *name, long value) {
+    if (!c || !name) return ROFL_ERR_ARGS;
+    std::lock_guard<std::mutex> lk(c->e.mu);
+    std::string n(name);
+    if (n == "use_rt") c->e.use_rt = value != 0;
+    else if (n == "rt_unfold") c->e.rt_unfold = (int)std::max<long>(0, std::min<long>(8, value));
+    else if (n == "groups") c->e.groups = (int)std::max<long>(1, std::min<long>((long)c->e.gstreams.size(), value));
+    else if (n == "tail_np") c->e.tail_np = (int)std::max<long>(0, std::min<long>(64, value));
+    else return ROFL_ERR_ARGS;
+    return ROFL_OK;
+}
 extern "C" size_t rofl_next_pow2(size_t v) { return next_pow2_sz(v); }
 extern "C" size_t rofl_range_proof_len(size_t N) { return 32 * (9 + 2 * (size_t)ilog2_sz(N)); }
 extern "C" void rofl_range_proof_shape(size_t D, int range, size_t n_partition, size_t *n_proofs, size_t *proof_len) {

@@ -33,6 +33,7 @@ struct rofl_engine {
     std::vector<cudaStream_t> gstreams;   // gstreams[0] == stream
     int use_rt = 1;                       // 0: never build generator tables (generic Pippenger / fold path only)
     int rt_unfold = 3;                    // IPP rounds computed over the original generators before the catch-up fold
+    int tail_np = 32;                     // IPP rounds with half-size <= tail_np run in the fused on-device tail kernel (0 = off)
     double rt_mem_frac = 0.45;            // tables may take this fraction of the free device memory
 };
 
@@ -157,12 +158,40 @@ static inline void run_rt_msm(rofl_engine &e, cudaStream_t s, rt_msm_args a, int
 }
 
 // ---- MSM front end ----------------------------------------------------------------------------------------------------------
-static inline void run_msm(rofl_engine &e, cudaStream_t s, const msm_args &a, uint32_t n_msm) {
+// window width and term slicing for an MSM of T terms run as n_msm independent instances (kernels.cuh, k_msm)
+struct msm_plan { int c, nw; uint32_t slices, slice_len; size_t out_count(size_t n_msm) const { return n_msm * slices * (size_t)nw; } };
+static inline int msm_pick_c(size_t T) {
+    int best = 8; double bc = 1e300;
+    for (int c = 3; c <= 8; c++) { const double B = (double)(1 << (c - 1)), cost = (double)msm_nw(c) * ((double)T + B * c); if (cost < bc) { bc = cost; best = c; } }
+    return best;
+}
+static inline msm_plan msm_plan_for(size_t T, size_t n_msm) {
+    msm_plan p; p.c = msm_pick_c(T); p.slices = 1; p.slice_len = (uint32_t)T;
+    if (const char *fc = getenv("ROFL_MSM_C")) {       // test hook: force the window width / slicing
+        p.c = std::max(3, std::min(8, atoi(fc)));
+        if (const char *fs = getenv("ROFL_MSM_SLICES")) { p.slices = (uint32_t)std::max<size_t>(1, std::min<size_t>(atoi(fs), T)); p.slice_len = (uint32_t)((T + p.slices - 1) / p.slices); p.slices = (uint32_t)((T + p.slice_len - 1) / p.slice_len); }
+        p.nw = msm_nw(p.c); return p;
+    }
+    const size_t wpb = MSM_THREADS >> (p.c - 1), blocks = n_msm * ((msm_nw(p.c) + wpb - 1) / wpb), slots = 148 * 4;
+    if (blocks < slots && T >= 4096) {
+        p.slices = (uint32_t)std::min<size_t>((slots + blocks - 1) / blocks, T / 2048);
+        p.slice_len = (uint32_t)((T + p.slices - 1) / p.slices); p.slices = (uint32_t)((T + p.slice_len - 1) / p.slice_len);
+        p.c = msm_pick_c(p.slice_len);
+    }
+    p.nw = msm_nw(p.c);
+    return p;
+}
+// a: v[], split, nseg, T, scalar_stride, out filled by the caller
+static inline void run_msm(rofl_engine &e, cudaStream_t s, msm_args a, const msm_plan &p, uint32_t n_msm) {
+    a.c = p.c; a.nw = p.nw; a.slices = p.slices; a.slice_len = p.slice_len; msm_recode_const(a.K, p.c);
+    const int wpb = MSM_THREADS >> (p.c - 1);
     void *tk = rt_prof_begin(PROF_MSM, s);
-    LAUNCH_COOP(k_msm, dim3(MSM_WINDOWS, n_msm), dim3(MSM_BUCKETS), s, a);
+    LAUNCH_COOP(k_msm, dim3((p.nw + wpb - 1) / wpb, n_msm, p.slices), dim3(MSM_THREADS), s, a);
     rt_prof_end(PROF_MSM, tk, s);
 }
 static inline msm_seg mk_seg(const void *base, uint32_t count, uint32_t stride, int kind) { msm_seg s; s.base = base; s.count = count; s.stride = stride; s.kind = kind; return s; }
+static inline void run_finalize(cudaStream_t s, const finalize_args &f) { LAUNCH_COOP(k_finalize, dim3(f.count), dim3(FIN_THREADS), s, f); }
+static inline void fin_windows(finalize_args &f, const p3_st *win, const msm_plan &p) { f.windows = win; f.c = p.c; f.nw = p.nw; f.slices = p.slices; }
 
 // =============================================================================================================================
 // RangeProof::prove_multiple for C chunks in lock step.  All pointers are device pointers except
@@ -181,12 +210,12 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     LAUNCH_COOP(k_party_sums, dim3(C), dim3(256), s, d_sums.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, (const sc_st *)nullptr, n, m, 0);
     // ---- A
     const int nbA = (int)std::min<size_t>(64, (N + 511) / 512);
-    dev_buf d_partA(sizeof(p3_st) * (size_t)C * nbA, s), d_AS(64 * (size_t)C, s), d_win(sizeof(p3_st) * MSM_WINDOWS * 2 * (size_t)C, s);
+    dev_buf d_partA(sizeof(p3_st) * (size_t)C * nbA, s), d_AS(64 * (size_t)C, s);
     LAUNCH_COOP(k_bits_sum, dim3(nbA, C), dim3(128), s, d_partA.as<p3_st>(), d_vals, g.G, g.H, n, m);
     {
         finalize_args f = {}; f.partial = d_partA.as<p3_st>(); f.npartial = nbA; f.sHa = d_sums.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
         f.out32 = d_AS.as<uint8_t>(); f.count = C;
-        LAUNCH(k_finalize, dim3((C + 31) / 32), dim3(32), s, f);
+        run_finalize(s, f);
     }
     // ---- S = (sum s_bl) H + <s_L, G> + <s_R, H>
     if (rt) {
@@ -196,14 +225,16 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         run_rt_msm(e, s, a, nbS, C);
         finalize_args f = {}; f.partial = d_partS.as<p3_st>(); f.npartial = nbS; f.sHa = d_sums.as<sc_st>() + C; f.tabB = e.tabB; f.tabH = e.tabH;
         f.out32 = d_AS.as<uint8_t>() + 32 * (size_t)C; f.count = C;
-        LAUNCH(k_finalize, dim3((C + 31) / 32), dim3(32), s, f);
+        run_finalize(s, f);
     } else {
-        msm_args a = {}; a.scalars = d_sLR.as<sc_st>(); a.T = (uint32_t)(2 * N); a.scalar_stride = (uint32_t)(2 * N);
-        a.seg[0] = mk_seg(g.G, (uint32_t)N, 0, 0); a.seg[1] = mk_seg(g.H, (uint32_t)N, 0, 0); a.nseg = 2; a.out = d_win.as<p3_st>();
-        run_msm(e, s, a, C);
-        finalize_args f = {}; f.windows = d_win.as<p3_st>(); f.sHa = d_sums.as<sc_st>() + C; f.tabB = e.tabB; f.tabH = e.tabH;
+        const msm_plan pl = msm_plan_for(2 * N, C);
+        dev_buf d_winS(sizeof(p3_st) * pl.out_count(C), s);
+        msm_args a = {}; a.v[0].scalars = d_sLR.as<sc_st>(); a.split = (uint32_t)C; a.T = (uint32_t)(2 * N); a.scalar_stride = (uint32_t)(2 * N);
+        a.v[0].seg[0] = mk_seg(g.G, (uint32_t)N, 0, 0); a.v[0].seg[1] = mk_seg(g.H, (uint32_t)N, 0, 0); a.nseg = 2; a.out = d_winS.as<p3_st>();
+        run_msm(e, s, a, pl, C);
+        finalize_args f = {}; fin_windows(f, d_winS.as<p3_st>(), pl); f.sHa = d_sums.as<sc_st>() + C; f.tabB = e.tabB; f.tabH = e.tabH;
         f.out32 = d_AS.as<uint8_t>() + 32 * (size_t)C; f.count = C;
-        LAUNCH(k_finalize, dim3((C + 31) / 32), dim3(32), s, f);
+        run_finalize(s, f);
     }
     std::vector<uint8_t> hV(32 * (size_t)C * m), hAS(64 * (size_t)C);
     rt_d2h(hV.data(), d_V32, hV.size(), s); rt_d2h(hAS.data(), d_AS.p, hAS.size(), s);
@@ -248,7 +279,7 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     {
         finalize_args f = {}; f.sBa = d_t12.as<sc_st>(); f.sHa = d_sums.as<sc_st>() + 2 * C; f.tabB = e.tabB; f.tabH = e.tabH;
         f.out32 = d_T12.as<uint8_t>(); f.count = 2 * C;
-        LAUNCH(k_finalize, dim3((2 * C + 31) / 32), dim3(32), s, f);
+        run_finalize(s, f);
     }
     std::vector<uint8_t> hT(64 * (size_t)C);
     rt_d2h(hT.data(), d_T12.p, hT.size(), s);
@@ -313,24 +344,26 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             run_rt_msm(e, s, aL, nbU, C); run_rt_msm(e, s, aR, nbU, C);
             finalize_args f = {}; f.partial = d_partU.as<p3_st>(); f.npartial = nbU; f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
             f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
-            LAUNCH(k_finalize, dim3((2 * C + 31) / 32), dim3(32), s, f);
+            run_finalize(s, f);
         } else {
             LAUNCH_COOP(k_ipp_scalars, dim3(nbI, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), msmL, msmR, d_part.as<sc_st>(), N, (uint32_t)np);
             LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_part.as<sc_st>(), nbI, 2);
-            msm_args aL = {}, aR = {};
-            aL.scalars = msmL; aL.T = (uint32_t)(2 * np); aL.scalar_stride = (uint32_t)(2 * np); aL.nseg = 2; aL.out = d_win.as<p3_st>();
-            aR = aL; aR.scalars = msmR; aR.out = d_win.as<p3_st>() + (size_t)C * MSM_WINDOWS;
+            // L and R of every chunk in one launch: msm = lr*C + c
+            const msm_plan pl = msm_plan_for(2 * np, 2 * (size_t)C);
+            dev_buf d_win(sizeof(p3_st) * pl.out_count(2 * (size_t)C), s);
+            msm_args a = {}; a.v[0].scalars = msmL; a.v[1].scalars = msmR; a.split = (uint32_t)C;
+            a.T = (uint32_t)(2 * np); a.scalar_stride = (uint32_t)(2 * np); a.nseg = 2; a.out = d_win.as<p3_st>();
             if (round == 0) {
-                aL.seg[0] = mk_seg(g.G + np, (uint32_t)np, 0, 0); aL.seg[1] = mk_seg(g.H, (uint32_t)np, 0, 0);
-                aR.seg[0] = mk_seg(g.G, (uint32_t)np, 0, 0);      aR.seg[1] = mk_seg(g.H + np, (uint32_t)np, 0, 0);
+                a.v[0].seg[0] = mk_seg(g.G + np, (uint32_t)np, 0, 0); a.v[0].seg[1] = mk_seg(g.H, (uint32_t)np, 0, 0);
+                a.v[1].seg[0] = mk_seg(g.G, (uint32_t)np, 0, 0);      a.v[1].seg[1] = mk_seg(g.H + np, (uint32_t)np, 0, 0);
             } else {
-                aL.seg[0] = mk_seg(d_Gf.as<p3_st>() + np, (uint32_t)np, (uint32_t)half, 1); aL.seg[1] = mk_seg(d_Hf.as<p3_st>(), (uint32_t)np, (uint32_t)half, 1);
-                aR.seg[0] = mk_seg(d_Gf.as<p3_st>(), (uint32_t)np, (uint32_t)half, 1);      aR.seg[1] = mk_seg(d_Hf.as<p3_st>() + np, (uint32_t)np, (uint32_t)half, 1);
+                a.v[0].seg[0] = mk_seg(d_Gf.as<p3_st>() + np, (uint32_t)np, (uint32_t)half, 1); a.v[0].seg[1] = mk_seg(d_Hf.as<p3_st>(), (uint32_t)np, (uint32_t)half, 1);
+                a.v[1].seg[0] = mk_seg(d_Gf.as<p3_st>(), (uint32_t)np, (uint32_t)half, 1);      a.v[1].seg[1] = mk_seg(d_Hf.as<p3_st>() + np, (uint32_t)np, (uint32_t)half, 1);
             }
-            run_msm(e, s, aL, C); run_msm(e, s, aR, C);
-            finalize_args f = {}; f.windows = d_win.as<p3_st>(); f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
+            run_msm(e, s, a, pl, 2 * (uint32_t)C);
+            finalize_args f = {}; fin_windows(f, d_win.as<p3_st>(), pl); f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
             f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
-            LAUNCH(k_finalize, dim3((2 * C + 31) / 32), dim3(32), s, f);
+            run_finalize(s, f);
         }
         rt_d2h(hLR.data(), d_LR.p, hLR.size(), s);
         rt_sync(s);
@@ -462,12 +495,13 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     const size_t N = (size_t)n * m;
     if ((m & (m - 1)) || N != ((size_t)1 << lg)) return 0;                      // verification_scalars: n != 1 << lg_n -> VerificationError (all chunks false)
     const int lgN = (int)lg, nsmall = 6 + 2 * lgN;
-    const uint32_t T = (uint32_t)(2 * N + m + nsmall);
+    // all C chunks are checked with ONE equation: sum_c rho_c * (chunk c's mega-check) == identity (kernels.cuh, k_verify_scalars)
     const int chs = 5 + 2 * lgN;
+    const uint32_t vstride = (uint32_t)(m + nsmall);
     std::vector<sc_st> h_chal((size_t)C * chs), h_small((size_t)C * nsmall), h_yinvpow2(32 * (size_t)C), h_zpow2(32 * (size_t)C);
     std::vector<uint8_t> h_smallpts(32 * (size_t)C * nsmall);
     std::vector<int> host_ok(C, 1);
-    std::vector<sc> y(C), yinv(C), z(C), x(C), w(C), cc(C);
+    std::vector<sc> y(C), yinv(C), z(C), x(C), w(C), cc(C), rho(C);
     std::vector<std::vector<sc>> u(C, std::vector<sc>(lgN));
     std::vector<sc> allu; allu.reserve((size_t)C * (lgN + 1));
     parallel_for(C, e.host_threads, [&](size_t c) {
@@ -485,6 +519,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         transcript_append(t, "t_x", p + 128, 32); transcript_append(t, "t_x_blinding", p + 160, 32); transcript_append(t, "e_blinding", p + 192, 32);
         ts_challenge_scalar(t, "w", w[c]);
         uint32_t kw[8]; key_words(kw, &keys[32 * c]); nonce_scalar(cc[c], kw, 0);                     // batching scalar c <- rng
+        nonce_scalar(rho[c], kw, 1);                                                                   // cross-chunk weight
         transcript_append(t, "dom-sep", (const uint8_t *)"ipp v1", 6); transcript_append_u64(t, "n", (uint64_t)N);
         for (int k = 0; k < lgN; k++) {
             ok &= !is_zero32(ipp + 64 * k) && !is_zero32(ipp + 64 * k + 32);
@@ -504,66 +539,85 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     parallel_for(C, e.host_threads, [&](size_t c) {
         const uint8_t *p = h_proofs + plen * c, *ipp = p + 224;
         const sc *inv = &allu[c * (lgN + 1)];
+        const sc &r = rho[c];
         yinv[c] = inv[0];
         sc t_x, t_xb, e_bl, a, b, zz, tmp, tmp2;
         sc_frombytes(t_x, p + 128); sc_frombytes(t_xb, p + 160); sc_frombytes(e_bl, p + 192);
         sc_frombytes(a, ipp + 64 * lgN); sc_frombytes(b, ipp + 64 * lgN + 32);
         sc_mul(zz, z[c], z[c]);
         sc_st *ch = &h_chal[c * chs];
-        sc_to_st(ch[0], z[c]); sc_to_st(ch[1], zz); sc_to_st(ch[2], a); sc_to_st(ch[3], b);
-        sc_mul(tmp, cc[c], zz); sc_to_st(ch[4], tmp);
+        sc_mul(tmp, r, z[c]); sc_to_st(ch[0], tmp); sc_mul(tmp, r, zz); sc_to_st(ch[1], tmp);
+        sc_mul(tmp, r, a); sc_to_st(ch[2], tmp); sc_mul(tmp, r, b); sc_to_st(ch[3], tmp); sc_to_st(ch[4], cc[c]);
         sc_st *sm = &h_small[c * nsmall];
-        sc one, cx; sc_from_u64(one, 1); sc_mul(cx, cc[c], x[c]);
-        sc_to_st(sm[0], one); sc_to_st(sm[1], x[c]); sc_to_st(sm[2], cx); sc_mul(tmp, cx, x[c]); sc_to_st(sm[3], tmp);
+        sc cx; sc_mul(cx, cc[c], x[c]);
+        auto put = [&](int i, const sc &v) { sc t; sc_mul(t, v, r); sc_to_st(sm[i], t); };                  // every small scalar carries rho_c
+        sc_to_st(sm[0], r); put(1, x[c]); put(2, cx); sc_mul(tmp, cx, x[c]); put(3, tmp);
         for (int k = 0; k < lgN; k++) {
             sc_to_st(ch[5 + k], u[c][k]); sc_to_st(ch[5 + lgN + k], inv[1 + k]);
-            sc_mul(tmp, u[c][k], u[c][k]); sc_to_st(sm[4 + k], tmp);
-            sc_mul(tmp, inv[1 + k], inv[1 + k]); sc_to_st(sm[4 + lgN + k], tmp);
+            sc_mul(tmp, u[c][k], u[c][k]); put(4 + k, tmp);
+            sc_mul(tmp, inv[1 + k], inv[1 + k]); put(4 + lgN + k, tmp);
         }
-        sc_mul(tmp, cc[c], t_xb); sc_add(tmp, tmp, e_bl); sc_neg(tmp, tmp); sc_to_st(sm[4 + 2 * lgN], tmp);      // H: -e_bl - c t_x_bl
+        sc_mul(tmp, cc[c], t_xb); sc_add(tmp, tmp, e_bl); sc_neg(tmp, tmp); put(4 + 2 * lgN, tmp);      // H: -e_bl - c t_x_bl
         // delta = (z - zz) sum_{i<N} y^i - z^3 (2^n - 1) sum_{j<m} z^j ; sums of powers via prod (1 + s^(2^b))
         sc_pow2_table(&h_yinvpow2[32 * c], yinv[c]); sc_pow2_table(&h_zpow2[32 * c], z[c]);
-        sc sum_y, sum_z, pw, delta, s2; sc_from_u64(sum_y, 1); sc_from_u64(sum_z, 1);
+        sc one, sum_y, sum_z, pw, delta, s2; sc_from_u64(one, 1); sc_from_u64(sum_y, 1); sc_from_u64(sum_z, 1);
         pw = y[c]; for (int bb = 0; bb < lgN; bb++) { sc_add(tmp, one, pw); sc_mul(sum_y, sum_y, tmp); sc_mul(pw, pw, pw); }
         pw = z[c]; for (int bb = 0; bb < ilog2_sz(m); bb++) { sc_add(tmp, one, pw); sc_mul(sum_z, sum_z, tmp); sc_mul(pw, pw, pw); }
         sc_from_u64(s2, n == 64 ? ~0ULL : ((1ULL << n) - 1));
         sc_sub(delta, z[c], zz); sc_mul(delta, delta, sum_y);
         sc_mul(tmp, zz, z[c]); sc_mul(tmp, tmp, s2); sc_mul(tmp, tmp, sum_z); sc_sub(delta, delta, tmp);
         sc_mul(tmp, a, b); sc_sub(tmp, t_x, tmp); sc_mul(tmp, w[c], tmp);                                        // w (t_x - a b)
-        sc_sub(tmp2, delta, t_x); sc_mul(tmp2, cc[c], tmp2); sc_add(tmp, tmp, tmp2); sc_to_st(sm[5 + 2 * lgN], tmp);   // B
+        sc_sub(tmp2, delta, t_x); sc_mul(tmp2, cc[c], tmp2); sc_add(tmp, tmp, tmp2); put(5 + 2 * lgN, tmp);      // B
     });
+    const vtab_layout vt = vtab_make(lgN, ilog2_sz(m));
     dev_buf d_chal(sizeof(sc_st) * h_chal.size(), s), d_yinvpow2(sizeof(sc_st) * 32 * C, s), d_zpow2(sizeof(sc_st) * 32 * C, s);
-    dev_buf d_scal(sizeof(sc_st) * (size_t)C * T, s), d_sp32(h_smallpts.size(), s), d_sp(sizeof(p3_st) * (size_t)C * nsmall, s), d_bad(sizeof(int) * C, s);
-    dev_buf d_win(sizeof(p3_st) * MSM_WINDOWS * (size_t)C, s), d_id(sizeof(int) * C, s);
+    dev_buf d_tab(sizeof(sc_st) * (size_t)C * vt.total, s), d_gh(sizeof(sc_st) * 2 * N, s), d_var(sizeof(sc_st) * (size_t)C * vstride, s);
+    dev_buf d_sp32(h_smallpts.size(), s), d_sp(sizeof(p3_st) * (size_t)C * nsmall, s), d_bad(sizeof(int) * C, s), d_id(sizeof(int), s), d_fix(sizeof(p3_st), s);
     rt_h2d(d_chal.p, h_chal.data(), sizeof(sc_st) * h_chal.size(), s);
     rt_h2d(d_yinvpow2.p, h_yinvpow2.data(), sizeof(sc_st) * 32 * C, s); rt_h2d(d_zpow2.p, h_zpow2.data(), sizeof(sc_st) * 32 * C, s);
     rt_h2d(d_sp32.p, h_smallpts.data(), h_smallpts.size(), s);
     rt_memset(d_bad.p, 0, sizeof(int) * C, s);
-    for (int c = 0; c < C; c++) rt_h2d(d_scal.as<sc_st>() + (size_t)c * T + 2 * N + m, &h_small[(size_t)c * nsmall], sizeof(sc_st) * nsmall, s);
-    const int nbV = (int)std::min<size_t>(256, (N + 255) / 256);
-    LAUNCH(k_verify_scalars, dim3(nbV, C), dim3(256), s, d_scal.as<sc_st>(), T, d_chal.as<sc_st>(), chs, d_yinvpow2.as<sc_st>(), d_zpow2.as<sc_st>(), n, m, lgN);
+    for (int c = 0; c < C; c++) rt_h2d(d_var.as<sc_st>() + (size_t)c * vstride + m, &h_small[(size_t)c * nsmall], sizeof(sc_st) * nsmall, s);
+    LAUNCH(k_verify_tables, dim3((vt.total + m + 255) / 256, C), dim3(256), s, d_tab.as<sc_st>(), vt, d_var.as<sc_st>(), vstride, d_chal.as<sc_st>(), chs, d_yinvpow2.as<sc_st>(), d_zpow2.as<sc_st>(), m);
+    LAUNCH(k_verify_scalars, dim3((unsigned)((N + 255) / 256)), dim3(256), s, d_gh.as<sc_st>(), d_tab.as<sc_st>(), vt, d_chal.as<sc_st>(), chs, n, C);
     LAUNCH(k_decompress, dim3((unsigned)(((size_t)C * nsmall + 127) / 128)), dim3(128), s, d_sp.as<p3_st>(), (uint8_t *)nullptr, d_sp32.as<uint8_t>(), (size_t)C * nsmall, (size_t)C * nsmall, (const p3_st *)nullptr, d_bad.as<int>(), (size_t)nsmall);
-    finalize_args f = {}; f.windows = d_win.as<p3_st>(); f.tabB = e.tabB; f.tabH = e.tabH; f.is_id = d_id.as<int>(); f.count = C;
-    const int nbV2 = rt ? rt_blocks(2 * N, C) : 1;
-    dev_buf d_partV(sizeof(p3_st) * (size_t)C * nbV2, s);
-    msm_args a = {}; a.scalar_stride = T; a.out = d_win.as<p3_st>();
-    if (rt) {       // fixed generators through the radix-256 tables, only V and the proof points through the bucket MSM
-        rt_msm_args ra = {}; ra.scalars = d_scal.as<sc_st>(); ra.T = (uint32_t)(2 * N); ra.scalar_stride = T; ra.nG = (uint32_t)N; ra.mode = 0; ra.rt = *rt; ra.partial = d_partV.as<p3_st>();
-        run_rt_msm(e, s, ra, nbV2, C);
-        a.scalars = d_scal.as<sc_st>() + 2 * N; a.T = (uint32_t)(m + nsmall); a.nseg = 2;
-        a.seg[0] = mk_seg(d_Vp3, (uint32_t)m, (uint32_t)m, 1); a.seg[1] = mk_seg(d_sp.p, (uint32_t)nsmall, (uint32_t)nsmall, 1);
-        f.partial = d_partV.as<p3_st>(); f.npartial = nbV2;
-    } else {
-        a.scalars = d_scal.as<sc_st>(); a.T = T; a.nseg = 4;
-        a.seg[0] = mk_seg(g.G, (uint32_t)N, 0, 0); a.seg[1] = mk_seg(g.H, (uint32_t)N, 0, 0);
-        a.seg[2] = mk_seg(d_Vp3, (uint32_t)m, (uint32_t)m, 1); a.seg[3] = mk_seg(d_sp.p, (uint32_t)nsmall, (uint32_t)nsmall, 1);
+    // fixed generators: one 2N-term MSM (radix-256 tables when they exist, bucket MSM otherwise) -> d_fix
+    {
+        finalize_args f = {}; f.tabB = e.tabB; f.tabH = e.tabH; f.out_p3 = d_fix.as<p3_st>(); f.count = 1;
+        if (rt) {
+            const int nbV = rt_blocks(2 * N, 1);
+            dev_buf d_partV(sizeof(p3_st) * (size_t)nbV, s);
+            rt_msm_args ra = {}; ra.scalars = d_gh.as<sc_st>(); ra.T = (uint32_t)(2 * N); ra.scalar_stride = (uint32_t)(2 * N); ra.nG = (uint32_t)N; ra.mode = 0; ra.rt = *rt; ra.partial = d_partV.as<p3_st>();
+            run_rt_msm(e, s, ra, nbV, 1);
+            f.partial = d_partV.as<p3_st>(); f.npartial = nbV;
+            run_finalize(s, f);
+        } else {
+            const msm_plan pl = msm_plan_for(2 * N, 1);
+            dev_buf d_winF(sizeof(p3_st) * pl.out_count(1), s);
+            msm_args a = {}; a.v[0].scalars = d_gh.as<sc_st>(); a.split = 1; a.T = (uint32_t)(2 * N); a.scalar_stride = (uint32_t)(2 * N); a.nseg = 2; a.out = d_winF.as<p3_st>();
+            a.v[0].seg[0] = mk_seg(g.G, (uint32_t)N, 0, 0); a.v[0].seg[1] = mk_seg(g.H, (uint32_t)N, 0, 0);
+            run_msm(e, s, a, pl, 1);
+            fin_windows(f, d_winF.as<p3_st>(), pl);
+            run_finalize(s, f);
+        }
     }
-    run_msm(e, s, a, C);
-    LAUNCH(k_finalize, dim3((C + 31) / 32), dim3(32), s, f);
-    std::vector<int> h_id(C), h_bad(C);
-    rt_d2h(h_id.data(), d_id.p, sizeof(int) * C, s); rt_d2h(h_bad.data(), d_bad.p, sizeof(int) * C, s);
+    // commitments and proof points: one MSM per chunk, the per-chunk window sums are added up like slices
+    {
+        msm_plan pl = msm_plan_for(vstride, C); pl.slices = 1; pl.slice_len = vstride;
+        dev_buf d_winV(sizeof(p3_st) * pl.out_count(C), s);
+        msm_args a = {}; a.v[0].scalars = d_var.as<sc_st>(); a.split = (uint32_t)C; a.T = vstride; a.scalar_stride = vstride; a.nseg = 2; a.out = d_winV.as<p3_st>();
+        a.v[0].seg[0] = mk_seg(d_Vp3, (uint32_t)m, (uint32_t)m, 1); a.v[0].seg[1] = mk_seg(d_sp.p, (uint32_t)nsmall, (uint32_t)nsmall, 1);
+        run_msm(e, s, a, pl, C);
+        finalize_args f = {}; f.windows = d_winV.as<p3_st>(); f.c = pl.c; f.nw = pl.nw; f.slices = (uint32_t)C;
+        f.partial = d_fix.as<p3_st>(); f.npartial = 1; f.tabB = e.tabB; f.tabH = e.tabH; f.is_id = d_id.as<int>(); f.count = 1;
+        run_finalize(s, f);
+    }
+    std::vector<int> h_bad(C); int h_id = 0;
+    rt_d2h(&h_id, d_id.p, sizeof(int), s); rt_d2h(h_bad.data(), d_bad.p, sizeof(int) * C, s);
     rt_sync(s);
-    for (int c = 0; c < C; c++) verdict[c] = (host_ok[c] && !h_bad[c] && h_id[c]) ? 1 : 0;
+    int all_ok = h_id;
+    for (int c = 0; c < C; c++) all_ok &= (host_ok[c] && !h_bad[c]) ? 1 : 0;
+    for (int c = 0; c < C; c++) verdict[c] = all_ok;
     return 0;
 }
 
@@ -589,7 +643,7 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
     dev_buf d_off(sizeof(p3_st), s), d_offs(sizeof(sc_st), s), d_Vp3(sizeof(p3_st) * Dp, s), d_V32(32 * Dp, s), d_bad(sizeof(int), s);
     { sc o; sc_from_u64(o, 1ULL << (range - 1)); sc_st os; sc_to_st(os, o); rt_h2d(d_offs.p, &os, sizeof(os), s);
       finalize_args f = {}; f.sBa = d_offs.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH; f.out_p3 = d_off.as<p3_st>(); f.count = 1;
-      LAUNCH(k_finalize, dim3(1), dim3(32), s, f); }
+      run_finalize(s, f); }
     rt_memset(d_bad.p, 0, sizeof(int), s);
     LAUNCH(k_decompress, dim3((unsigned)((Dp + 127) / 128)), dim3(128), s, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), d_commits, D, Dp, d_off.as<p3_st>(), d_bad.as<int>(), Dp);
     std::vector<uint8_t> hV(32 * Dp); int bad = 0;
@@ -651,7 +705,7 @@ static int engine_l2_prove(rofl_engine &e, const float *h_values, const float *d
     sc vs; sc_from_u64(vs, v); sc_st t; sc_to_st(t, vs); rt_h2d(d_vs.p, &t, sizeof(t), s);
     sc_to_st(t, bsum); rt_h2d(d_bl.p, &t, sizeof(t), s); rt_h2d(d_v.p, &v, 8, s);
     { finalize_args f = {}; f.sBa = d_vs.as<sc_st>(); f.sHa = d_bl.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH; f.out32 = d_V.as<uint8_t>(); f.count = 1;
-      LAUNCH(k_finalize, dim3(1), dim3(32), s, f); }
+      run_finalize(s, f); }
     gens_entry &g = engine_gens(e, range, 1);                                     // BulletproofGens::new(64, 1) restricted to n = range (:162)
     std::vector<uint8_t> keys(32); derive_key(keys.data(), seed, DOM_L2_PROVE, 0);
     prove_chunks(e, s, "L2RangeProof", range, 1, 1, g, nullptr, d_v.as<uint64_t>(), d_bl.as<sc_st>(), d_V.as<uint8_t>(), keys, h_proof);

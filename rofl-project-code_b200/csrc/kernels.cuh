@@ -262,32 +262,48 @@ KLAUNCH(k_bits_sum, true, (p3_st *partial, const uint64_t *vals, const niels_st 
 #endif
 
 // ===================================================================================================================
-// K4/K6/K7: batched Pippenger multiscalar multiplication, radix 2^8 signed digits, one block per (window, msm).
-//   digit_w(x) = byte_w(x + 0x7f7f..7f) - 127  in [-127, 128]   (unique signed-digit recoding, no carries to track)
-//   bucket |d| is owned by thread |d|-1; per tile the terms are counting-sorted by bucket in shared memory so each
-//   thread walks only its own list; bucket sums are combined by a suffix scan + tree sum in shared memory.
+// K4/K6/K7: batched Pippenger multiscalar multiplication with a run-time window width c in [3, 8].
+//   digit_w(x) = field_w(x + K) - (B-1),  K = sum_w (B-1) 2^(cw),  B = 2^(c-1):  signed digits in [-(B-1), B] without
+//   carries to track.  One block of 128 threads owns 128/B consecutive windows of one (msm, slice): thread (wl, b) owns
+//   bucket b+1 of window wl.  Per tile the scalars are read once, the terms are counting-sorted by (window, bucket) in
+//   shared memory, each thread walks its own list, then the buckets of every window are combined by a suffix scan + tree
+//   sum in shared memory.  Small MSMs pick small c (few buckets to reduce), large ones c = 8; a long MSM can be cut into
+//   `slices` term ranges whose window sums k_finalize adds up.
 // ===================================================================================================================
-#define MSM_WINDOWS 32
-#define MSM_BUCKETS 128
-#define MSM_TILE 8192
+#define MSM_THREADS 128
+#define MSM_SORT 8192
+#define MSM_MAXW 85
 struct msm_seg { const void *base; uint32_t count; uint32_t stride; int kind; };     // kind 0 = niels_st, 1 = p3_st; stride = records per msm (0: shared)
+struct msm_var { const sc_st *scalars; msm_seg seg[4]; };                            // scalars[idx*scalar_stride + t]
 struct msm_args {
-    const sc_st *scalars; uint32_t T; uint32_t scalar_stride;    // scalars[msm*scalar_stride + t]
-    msm_seg seg[4]; int nseg;
-    p3_st *out;                                                  // out[msm*MSM_WINDOWS + w]
+    msm_var v[2]; uint32_t split;            // msm < split: v[0] with idx = msm; else v[1] with idx = msm - split   (L / R in one launch)
+    int nseg; uint32_t T, scalar_stride;
+    int c, nw; uint32_t K[9];                // window bits, window count = ceil(254/c), recoding constant
+    uint32_t slices, slice_len;              // slice s covers terms [s*slice_len, min(T, (s+1)*slice_len))
+    p3_st *out;                              // out[(msm*slices + slice)*nw + w]
 };
-HD int msm_digit(const sc &x, int w) {
-    // byte w of x + K, K = 0x7f repeated; x < 2^253 so no overflow out of 256 bits
-    uint64_t c = 0; uint32_t word = 0;
-    for (int i = 0; i <= (w >> 2); i++) { c += (uint64_t)x.v[i] + 0x7f7f7f7fu; word = (uint32_t)c; c >>= 32; }
-    return (int)((word >> (8 * (w & 3))) & 0xff) - 127;
+HD int msm_nw(int c) { return (254 + c - 1) / c; }
+HD void msm_recode_const(uint32_t K[9], int c) {
+    for (int i = 0; i < 9; i++) K[i] = 0;
+    const uint32_t bm1 = (1u << (c - 1)) - 1; const int nw = msm_nw(c);
+    for (int w = 0; w < nw; w++) { int bit = c * w; uint64_t v = (uint64_t)bm1 << (bit & 31); K[bit >> 5] |= (uint32_t)v; if ((bit >> 5) + 1 < 9) K[(bit >> 5) + 1] |= (uint32_t)(v >> 32); }
 }
-HD void msm_add_term(ge_p3 &acc, const msm_args &a, uint32_t msm, uint32_t t, bool neg) {
+HD void msm_recode(uint32_t xk[9], const sc &x, const uint32_t K[9]) {
+    uint64_t cy = 0;
+    for (int i = 0; i < 8; i++) { cy += (uint64_t)x.v[i] + K[i]; xk[i] = (uint32_t)cy; cy >>= 32; }
+    xk[8] = (uint32_t)cy + K[8];
+}
+HD int msm_digit(const uint32_t xk[9], int w, int c) {
+    int bit = c * w, i = bit >> 5, sh = bit & 31;
+    uint64_t v = (uint64_t)xk[i] | ((uint64_t)(i + 1 < 9 ? xk[i + 1] : 0) << 32);
+    return (int)((v >> sh) & ((1u << c) - 1)) - ((1 << (c - 1)) - 1);
+}
+HD void msm_add_term(ge_p3 &acc, const msm_var &v, int nseg, uint32_t idx, uint32_t t, bool neg) {
     uint32_t start = 0;
-    for (int s = 0; s < a.nseg; s++) {
-        const msm_seg &g = a.seg[s];
+    for (int s = 0; s < nseg; s++) {
+        const msm_seg &g = v.seg[s];
         if (t < start + g.count) {
-            size_t rec = (size_t)msm * g.stride + (t - start);
+            size_t rec = (size_t)idx * g.stride + (t - start);
             if (g.kind == 0) acc_add_niels(acc, (const niels_st *)g.base + rec, neg);
             else acc_add_p3(acc, (const p3_st *)g.base + rec, neg);
             return;
@@ -296,92 +312,122 @@ HD void msm_add_term(ge_p3 &acc, const msm_args &a, uint32_t msm, uint32_t t, bo
     }
 }
 #ifdef KG_MSM
-KERNEL void LB(128, 4) k_msm(msm_args a) {
-    __shared__ uint16_t sorted[MSM_TILE];
-    __shared__ int cnt[MSM_BUCKETS + 1], off[MSM_BUCKETS + 2], cur[MSM_BUCKETS + 1];
-    __shared__ p3_st bk[MSM_BUCKETS];
-    const int w = blockIdx.x, tid = threadIdx.x;
-    const uint32_t msm = blockIdx.y;
-    const sc_st *scal = a.scalars + (size_t)msm * a.scalar_stride;
+KERNEL void LB(MSM_THREADS, 4) k_msm(msm_args a) {
+    __shared__ uint16_t sorted[MSM_SORT];
+    __shared__ int cnt[MSM_THREADS], off[MSM_THREADS + 1], cur[MSM_THREADS];
+    __shared__ p3_st bk[MSM_THREADS];
+    const int tid = threadIdx.x, c = a.c, B = 1 << (c - 1), wpb = MSM_THREADS / B;
+    const int w0 = blockIdx.x * wpb, wl_mine = tid / B, b_mine = tid & (B - 1);
+    const uint32_t msm = blockIdx.y, slice = blockIdx.z;
+    const msm_var &v = msm < a.split ? a.v[0] : a.v[1];
+    const uint32_t idx = msm < a.split ? msm : msm - a.split;
+    const sc_st *scal = v.scalars + (size_t)idx * a.scalar_stride;
+    const uint32_t t_begin = slice * a.slice_len, t_end = t_begin + a.slice_len < a.T ? t_begin + a.slice_len : a.T;
+    const uint32_t tile_len = MSM_SORT / wpb;
+    int nwl = a.nw - w0; if (nwl > wpb) nwl = wpb;                   // windows of this block that exist
     ge_p3 acc; ge_p3_0(acc);
-    for (uint32_t tile = 0; tile < a.T; tile += MSM_TILE) {
-        uint32_t nt = a.T - tile < MSM_TILE ? a.T - tile : MSM_TILE;
-        cnt[tid + 1] = 0; if (tid == 0) cnt[0] = 0;
+    for (uint32_t tile = t_begin; tile < t_end; tile += tile_len) {
+        const uint32_t nt = t_end - tile < tile_len ? t_end - tile : tile_len;
+        cnt[tid] = 0;
         __syncthreads();
-        for (uint32_t t = tid; t < nt; t += MSM_BUCKETS) {
+        for (uint32_t t = tid; t < nt; t += MSM_THREADS) {
             sc x; ld_sc(x, scal + tile + t);
-            int d = msm_digit(x, w);
-            if (d != 0) atomicAdd(&cnt[d > 0 ? d : -d], 1);
+            uint32_t xk[9]; msm_recode(xk, x, a.K);
+            for (int wl = 0; wl < nwl; wl++) { int d = msm_digit(xk, w0 + wl, c); if (d != 0) atomicAdd(&cnt[wl * B + (d > 0 ? d : -d) - 1], 1); }
         }
         __syncthreads();
-        if (tid == 0) { int o = 0; for (int b = 1; b <= MSM_BUCKETS; b++) { off[b] = o; cur[b] = o; o += cnt[b]; } off[MSM_BUCKETS + 1] = o; }
+        if (tid == 0) { int o = 0; for (int b = 0; b < MSM_THREADS; b++) { off[b] = o; cur[b] = o; o += cnt[b]; } off[MSM_THREADS] = o; }
         __syncthreads();
-        for (uint32_t t = tid; t < nt; t += MSM_BUCKETS) {
+        for (uint32_t t = tid; t < nt; t += MSM_THREADS) {
             sc x; ld_sc(x, scal + tile + t);
-            int d = msm_digit(x, w);
-            if (d != 0) { int p = atomicAdd(&cur[d > 0 ? d : -d], 1); sorted[p] = (uint16_t)(t | (d < 0 ? 0x8000u : 0u)); }
+            uint32_t xk[9]; msm_recode(xk, x, a.K);
+            for (int wl = 0; wl < nwl; wl++) {
+                int d = msm_digit(xk, w0 + wl, c);
+                if (d != 0) { int p = atomicAdd(&cur[wl * B + (d > 0 ? d : -d) - 1], 1); sorted[p] = (uint16_t)(t | (d < 0 ? 0x8000u : 0u)); }
+            }
         }
         __syncthreads();
-        int b = tid + 1;
-        for (int e = off[b]; e < off[b + 1]; e++) {
+        for (int e = off[tid]; e < off[tid + 1]; e++) {
             uint32_t ent = sorted[e];
-            msm_add_term(acc, a, msm, tile + (ent & 0x7fffu), (ent >> 15) != 0);
+            msm_add_term(acc, v, a.nseg, idx, tile + (ent & 0x7fffu), (ent >> 15) != 0);
         }
         __syncthreads();
     }
-    // sum_b b*acc_b: suffix sums then total
+    // per window: sum_b (b+1) * bucket_b  =  sum of the suffix sums
     st_p3(bk + tid, acc);
     __syncthreads();
-    for (int s = 1; s < MSM_BUCKETS; s <<= 1) {
-        ge_p3 x, y; bool act = tid + s < MSM_BUCKETS;
+    for (int s = 1; s < B; s <<= 1) {
+        ge_p3 x, y; const bool act = b_mine + s < B;
         if (act) { ld_p3(x, bk + tid); ld_p3(y, bk + tid + s); ge_add(x, x, y); }
         __syncthreads();
         if (act) st_p3(bk + tid, x);
         __syncthreads();
     }
-    for (int s = MSM_BUCKETS >> 1; s > 0; s >>= 1) {
-        if (tid < s) { ge_p3 x, y; ld_p3(x, bk + tid); ld_p3(y, bk + tid + s); ge_add(x, x, y); st_p3(bk + tid, x); }
+    for (int s = B >> 1; s > 0; s >>= 1) {
+        if (b_mine < s) { ge_p3 x, y; ld_p3(x, bk + tid); ld_p3(y, bk + tid + s); ge_add(x, x, y); st_p3(bk + tid, x); }
         __syncthreads();
     }
-    if (tid == 0) { ge_p3 r; ld_p3(r, bk); st_p3(a.out + (size_t)msm * MSM_WINDOWS + w, r); }
+    if (b_mine == 0 && wl_mine < nwl) { ge_p3 r; ld_p3(r, bk + tid); st_p3(a.out + ((size_t)msm * a.slices + slice) * a.nw + w0 + wl_mine, r); }
 }
 KLAUNCH(k_msm, true, (msm_args a), (a))
 #endif
 
-// combine: R = sum_w 256^w W_w (+ sum of `npartial` extra points) (+ sB*B + sH*H), one thread per output.
-//   sB = sBa[idx] (* sBb[idx] if sBb), same for sH; any pointer may be null.
+// combine, one block per output idx:
+//   R = sum_w 2^(cw) (sum_s W[idx][s][w])  +  sum of `npartial` extra points  +  sB*B + sH*H
+//   sB = sBa[idx] (* sBb[idx] if sBb), same for sH; any pointer may be null.  The window sums, the extra points and the two
+//   fixed-base products are computed by different threads, then thread 0 runs the doubling chain and compresses.
 //   out32: compressed result (nullable); out_p3: extended result (nullable); is_id: 1 if the result is the identity (nullable)
+#define FIN_THREADS 128
 struct finalize_args {
-    const p3_st *windows;          // [count][MSM_WINDOWS] or null
-    const p3_st *partial; int npartial;     // [count][npartial] or null
+    const p3_st *windows; int c, nw; uint32_t slices;      // [count][slices][nw] or null
+    const p3_st *partial; int npartial;                    // [count][npartial] or null
     const sc_st *sBa, *sBb, *sHa, *sHb;
     const niels_st *tabB, *tabH;
     uint8_t *out32; p3_st *out_p3; int *is_id;
     int count;
 };
 #ifdef KG_MSM
-KERNEL void LB(32, 1) k_finalize(finalize_args a) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.count) return;
-    ge_p3 r; ge_p3_0(r);
-    if (a.windows) {
-        ld_p3(r, a.windows + (size_t)idx * MSM_WINDOWS + MSM_WINDOWS - 1);
-        for (int w = MSM_WINDOWS - 2; w >= 0; w--) {
-            ge_p2 q; ge_p1p1 t;
-            ge_dbl_p1p1(t, r.X, r.Y, r.Z); ge_dbl_fix(t); ge_p1p1_to_p2(q, t);
-            for (int k = 0; k < 6; k++) { ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); ge_p1p1_to_p2(q, t); }
-            ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); ge_p1p1_to_p3(r, t);
-            acc_add_p3(r, a.windows + (size_t)idx * MSM_WINDOWS + w, false);
-        }
+KERNEL void LB(FIN_THREADS, 1) k_finalize(finalize_args a) {
+    __shared__ p3_st sw[MSM_MAXW + 3];
+    __shared__ p3_st ex[32];
+    const int idx = blockIdx.x, tid = threadIdx.x;
+    if (a.windows && tid < a.nw) {
+        const p3_st *src = a.windows + (size_t)idx * a.slices * a.nw + tid;
+        ge_p3 r; ld_p3(r, src);
+        for (uint32_t s = 1; s < a.slices; s++) acc_add_p3(r, src + (size_t)s * a.nw, false);
+        st_p3(sw + tid, r);
     }
-    for (int k = 0; k < a.npartial; k++) acc_add_p3(r, a.partial + (size_t)idx * a.npartial + k, false);
-    if (a.sBa) { sc s; ld_sc(s, a.sBa + idx); if (a.sBb) { sc t; ld_sc(t, a.sBb + idx); sc_mul(s, s, t); } fb_mul_acc(r, a.tabB, s, 32); }
-    if (a.sHa) { sc s; ld_sc(s, a.sHa + idx); if (a.sHb) { sc t; ld_sc(t, a.sHb + idx); sc_mul(s, s, t); } fb_mul_acc(r, a.tabH, s, 32); }
+    if (tid >= 96) {
+        const int j = tid - 96;
+        ge_p3 r; ge_p3_0(r);
+        if (j == 0) { if (a.sBa) { sc s; ld_sc(s, a.sBa + idx); if (a.sBb) { sc t; ld_sc(t, a.sBb + idx); sc_mul(s, s, t); } fb_mul_acc(r, a.tabB, s, 32); } }
+        else if (j == 1) { if (a.sHa) { sc s; ld_sc(s, a.sHa + idx); if (a.sHb) { sc t; ld_sc(t, a.sHb + idx); sc_mul(s, s, t); } fb_mul_acc(r, a.tabH, s, 32); } }
+        else for (int k = j - 2; k < a.npartial; k += 30) acc_add_p3(r, a.partial + (size_t)idx * a.npartial + k, false);
+        st_p3(ex + j, r);
+    }
+    __syncthreads();
+    for (int s = 16; s > 0; s >>= 1) {
+        if (tid >= 96 && tid - 96 < s) { ge_p3 x, y; ld_p3(x, ex + tid - 96); ld_p3(y, ex + tid - 96 + s); ge_add(x, x, y); st_p3(ex + tid - 96, x); }
+        __syncthreads();
+    }
+    if (tid != 0) return;
+    ge_p3 r; ld_p3(r, ex);
+    if (a.windows) {
+        ge_p3 h; ld_p3(h, sw + a.nw - 1);
+        for (int w = a.nw - 2; w >= 0; w--) {
+            ge_p2 q; ge_p1p1 t;
+            ge_dbl_p1p1(t, h.X, h.Y, h.Z); ge_dbl_fix(t);
+            for (int k = 1; k < a.c; k++) { ge_p1p1_to_p2(q, t); ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); }
+            ge_p1p1_to_p3(h, t);
+            acc_add_p3(h, sw + w, false);
+        }
+        ge_add(r, r, h);
+    }
     if (a.out32) { uint8_t o[32]; ge_compress(o, r); st_bytes32(a.out32 + 32 * (size_t)idx, o); }
     if (a.out_p3) st_p3(a.out_p3 + idx, r);
     if (a.is_id) a.is_id[idx] = ge_is_identity(r) ? 1 : 0;
 }
-KLAUNCH(k_finalize, false, (finalize_args a), (a))
+KLAUNCH(k_finalize, true, (finalize_args a), (a))
 #endif
 
 // ===================================================================================================================
@@ -547,34 +593,74 @@ KERNEL void LB(128, 2) k_decompress(p3_st *out, uint8_t *out32, const uint8_t *i
 }
 KLAUNCH(k_decompress, false, (p3_st *out, uint8_t *out32, const uint8_t *in, size_t count_in, size_t count_out, const p3_st *offset, int *bad, size_t bad_group), (out, out32, in, count_in, count_out, offset, bad, bad_group))
 #endif
+// Batched verification: all C chunks of a call share the generators, so the verifier takes one random weight rho_c per chunk
+// and checks  sum_c rho_c * (chunk c's verification equation) == 0  with ONE 2N-term generator MSM (soundness error 2^-252;
+// the reference ANDs the per-chunk verdicts, range_proof_vec/mod.rs:183-190).
 // per-chunk challenge block prepared by the host (all canonical scalars):
-//   [0] z  [1] z^2  [2] a  [3] b  [4] c*z^2  [5..5+lgN) u_k  [5+lgN..5+2lgN) u_k^-1 ; ypow2inv[c*32+b] = y^-(2^b), zpow2[c*32+b] = z^(2^b)
-// output scalars[c][0..N) = g_k = -z - a s_k ; [N..2N) = h_k = z + y^-k (z^2 z^j 2^i - b s_k^-1) ; [2N..2N+m) = c z^2 z^j
+//   [0] rho z  [1] rho z^2  [2] rho a  [3] rho b  [4] c (the reference's own batching scalar)  [5..5+lgN) u_k  [5+lgN..5+2lgN) u_k^-1
+// k_verify_tables builds per-chunk split tables (k = khi 2^L + klo, j = jhi 2^Lm + jlo) so that every per-position factor is
+// one product of two table entries instead of a lgN-step square-and-multiply:
+//   tab[c] = S_lo[2^L] | S_hi[2^H] | Y_lo[2^L] | Y_hi[2^H] | Z_lo[2^Lm] | Z_hi[2^Hm]
+//   s_k = S_lo[klo] S_hi[khi] (= prod_p bit_p(k) ? u_(lgN-1-p) : u^-1_(lgN-1-p)),  y^-k = Y_lo Y_hi,  rho z^2 z^j = Z_lo Z_hi
+// and the per-chunk commitment scalars var[c*var_stride + j] = c * rho z^2 z^j.
+struct vtab_layout { int lgN, L, H, lgm, Lm, Hm; uint32_t oSlo, oShi, oYlo, oYhi, oZlo, oZhi, total; };
+HD vtab_layout vtab_make(int lgN, int lgm) {
+    vtab_layout t; t.lgN = lgN; t.L = lgN / 2; t.H = lgN - t.L; t.lgm = lgm; t.Lm = lgm / 2; t.Hm = lgm - t.Lm;
+    t.oSlo = 0; t.oShi = t.oSlo + (1u << t.L); t.oYlo = t.oShi + (1u << t.H); t.oYhi = t.oYlo + (1u << t.L);
+    t.oZlo = t.oYhi + (1u << t.H); t.oZhi = t.oZlo + (1u << t.Lm); t.total = t.oZhi + (1u << t.Hm);
+    return t;
+}
 #ifdef KG_SCALAR
-KERNEL void LB(256, 1) k_verify_scalars(sc_st *scalars, uint32_t scalar_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int n, int m, int lgN) {
-    int c = blockIdx.y;
-    size_t N = (size_t)n * m;
+KERNEL void LB(256, 1) k_verify_tables(sc_st *tab, vtab_layout t, sc_st *var, uint32_t var_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int m) {
+    const int c = blockIdx.y;
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     const sc_st *ch = chal + (size_t)c * chal_stride;
-    sc z, zz, a, b; ld_sc(z, ch); ld_sc(zz, ch + 1); ld_sc(a, ch + 2); ld_sc(b, ch + 3);
-    sc_st *out = scalars + (size_t)c * scalar_stride;
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
-        size_t j = k / n; int i = (int)(k % n);
-        sc s, sinv; sc_from_u64(s, 1); sc_from_u64(sinv, 1);
-        for (int t = 0; t < lgN; t++) {
-            sc u, ui; ld_sc(u, ch + 5 + t); ld_sc(ui, ch + 5 + lgN + t);
-            bool bit = (k >> (lgN - 1 - t)) & 1;
-            sc_mul(s, s, bit ? u : ui); sc_mul(sinv, sinv, bit ? ui : u);
-        }
-        sc g, h, t1, t2;
-        sc_mul(g, a, s); sc_add(g, g, z); sc_neg(g, g);
-        sc_pow_tab(t1, zpow2 + 32 * c, j); sc_mul(t1, t1, zz); sc_from_u64(t2, 1ULL << i); sc_mul(t1, t1, t2);
-        sc_mul(t2, b, sinv); sc_sub(t1, t1, t2);
-        sc_pow_tab(t2, yinvpow2 + 32 * c, k); sc_mul(t1, t1, t2); sc_add(h, z, t1);
-        st_sc(out + k, g); st_sc(out + N + k, h);
-        if (i == 0) { sc czz; ld_sc(czz, ch + 4); sc_pow_tab(t1, zpow2 + 32 * c, j); sc_mul(t1, t1, czz); st_sc(out + 2 * N + j, t1); }
+    sc_st *out = tab + (size_t)c * t.total;
+    if (e < t.oYlo) {                                   // S_lo / S_hi
+        const bool hi = e >= t.oShi; const uint32_t v = hi ? e - t.oShi : e; const int p0 = hi ? t.L : 0, nb = hi ? t.H : t.L;
+        sc s; sc_from_u64(s, 1);
+        for (int q = 0; q < nb; q++) { const int tt = t.lgN - 1 - (p0 + q); sc f; ld_sc(f, ((v >> q) & 1) ? ch + 5 + tt : ch + 5 + t.lgN + tt); sc_mul(s, s, f); }
+        st_sc(out + e, s);
+    } else if (e < t.oZlo) {                            // Y_lo[j] = y^-j, Y_hi[j] = y^-(j 2^L)
+        const bool hi = e >= t.oYhi; const uint64_t v = hi ? (uint64_t)(e - t.oYhi) << t.L : e - t.oYlo;
+        sc s; sc_pow_tab(s, yinvpow2 + 32 * c, v); st_sc(out + e, s);
+    } else if (e < t.total) {                           // Z_lo[j] = rho z^2 z^j, Z_hi[j] = z^(j 2^Lm)
+        const bool hi = e >= t.oZhi; const uint64_t v = hi ? (uint64_t)(e - t.oZhi) << t.Lm : e - t.oZlo;
+        sc s; sc_pow_tab(s, zpow2 + 32 * c, v);
+        if (!hi) { sc r; ld_sc(r, ch + 1); sc_mul(s, s, r); }
+        st_sc(out + e, s);
+    } else if (e < t.total + (uint32_t)m) {             // commitment scalars
+        const uint32_t j = e - t.total;
+        sc s, r, cc; sc_pow_tab(s, zpow2 + 32 * c, j); ld_sc(r, ch + 1); ld_sc(cc, ch + 4); sc_mul(s, s, r); sc_mul(s, s, cc);
+        st_sc(var + (size_t)c * var_stride + j, s);
     }
 }
-KLAUNCH(k_verify_scalars, false, (sc_st *scalars, uint32_t scalar_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int n, int m, int lgN), (scalars, scalar_stride, chal, chal_stride, yinvpow2, zpow2, n, m, lgN))
+KLAUNCH(k_verify_tables, false, (sc_st *tab, vtab_layout t, sc_st *var, uint32_t var_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int m),
+        (tab, t, var, var_stride, chal, chal_stride, yinvpow2, zpow2, m))
+// gh[k] = sum_c rho_c g_(c,k) = sum_c -(rho z + rho a s_k);  gh[N + k] = sum_c rho z + y^-k (rho z^2 z^j 2^i - rho b s_k^-1),  k = j n + i
+KERNEL void LB(256, 1) k_verify_scalars(sc_st *gh, const sc_st *tab, vtab_layout t, const sc_st *chal, int chal_stride, int n, int C) {
+    const size_t N = (size_t)1 << t.lgN;
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const uint32_t mL = (1u << t.L) - 1, mH = (1u << t.H) - 1, mLm = (1u << t.Lm) - 1;
+    const uint32_t klo = (uint32_t)k & mL, khi = (uint32_t)(k >> t.L);
+    const size_t j = k / n; const int i = (int)(k % n);
+    sc e2; sc_from_u64(e2, 1ULL << i);
+    sc g, h; sc_0(g); sc_0(h);
+    for (int c = 0; c < C; c++) {
+        const sc_st *tb = tab + (size_t)c * t.total, *ch = chal + (size_t)c * chal_stride;
+        sc a, b, s, sinv, yk, zj, rz, ra, rb, t1;
+        ld_sc(a, tb + t.oSlo + klo); ld_sc(b, tb + t.oShi + khi); sc_mul(s, a, b);
+        ld_sc(a, tb + t.oSlo + (~klo & mL)); ld_sc(b, tb + t.oShi + (~khi & mH)); sc_mul(sinv, a, b);
+        ld_sc(a, tb + t.oYlo + klo); ld_sc(b, tb + t.oYhi + khi); sc_mul(yk, a, b);
+        ld_sc(a, tb + t.oZlo + ((uint32_t)j & mLm)); ld_sc(b, tb + t.oZhi + (uint32_t)(j >> t.Lm)); sc_mul(zj, a, b);
+        ld_sc(rz, ch); ld_sc(ra, ch + 2); ld_sc(rb, ch + 3);
+        sc_mul(t1, ra, s); sc_add(t1, t1, rz); sc_sub(g, g, t1);
+        sc_mul(zj, zj, e2); sc_mul(t1, rb, sinv); sc_sub(zj, zj, t1); sc_mul(zj, zj, yk); sc_add(h, h, zj); sc_add(h, h, rz);
+    }
+    st_sc(gh + k, g); st_sc(gh + N + k, h);
+}
+KLAUNCH(k_verify_scalars, false, (sc_st *gh, const sc_st *tab, vtab_layout t, const sc_st *chal, int chal_stride, int n, int C), (gh, tab, t, chal, chal_stride, n, C))
 #endif
 
 // ===================================================================================================================
@@ -761,7 +847,8 @@ void launch_k_ipp_scalars(dim3 g_, dim3 b_, cudaStream_t s_, const sc_st *a, con
 void launch_k_ipp_fold_scalars(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *a, sc_st *b, const sc_st *u2, const sc_st *uinv2, size_t N, uint32_t np);
 void launch_k_ipp_fold_points(dim3 g_, dim3 b_, cudaStream_t s_, fold_args a);
 void launch_k_decompress(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *out, uint8_t *out32, const uint8_t *in, size_t count_in, size_t count_out, const p3_st *offset, int *bad, size_t bad_group);
-void launch_k_verify_scalars(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *scalars, uint32_t scalar_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int n, int m, int lgN);
+void launch_k_verify_tables(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *tab, vtab_layout t, sc_st *var, uint32_t var_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int m);
+void launch_k_verify_scalars(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *gh, const sc_st *tab, vtab_layout t, const sc_st *chal, int chal_stride, int n, int C);
 void launch_k_square_prove(dim3 g_, dim3 b_, cudaStream_t s_, square_args a);
 void launch_k_square_verify(dim3 g_, dim3 b_, cudaStream_t s_, const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result);
 void launch_k_aggregate(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const uint8_t *pts, size_t n_clients, size_t D, int init_base, int *bad);

@@ -102,3 +102,26 @@ def test_aggregate_and_dlog(api, oracle):
     assert (f == np.array([0.0, 3.75, -6.5], np.float32)).all()
     far = oracle.commit_f32(np.array([400.0], np.float32), None, 16, 7)
     assert api.dlog(far, 1 << 4, 8, 8, 7)[0] == -5 and oracle.dlog(far, 1 << 4, 8)[0] == -5
+
+
+@pytest.mark.parametrize("c,slices,rt", [(3, 1, 1), (4, 3, 0), (5, 1, 0), (6, 2, 1), (7, 1, 0), (8, 2, 0)])
+def test_msm_window_widths(api, oracle, monkeypatch, c, slices, rt):
+    """Every window width / slicing of the bucket MSM (k_msm) gives the oracle's bytes; rt=0 also exercises the path without
+    generator tables (generic MSM for S and the verifier, folded IPP from round 0)."""
+    monkeypatch.setenv("ROFL_MSM_C", str(c)); monkeypatch.setenv("ROFL_MSM_SLICES", str(slices))
+    api.set_use_rt(rt)
+    try:
+        rng = np.random.default_rng(c)
+        D, rngbits, P, nb = 6, 8, 2, 16
+        mn, mx = oracle.clip_bounds(rngbits, nb, 7)
+        v = rng.uniform(mn, mx, D).astype(np.float32)
+        bl = oracle.rnd_scalar_vec(b"\x35" * 32, D)
+        seed = bytes([c] * 32)
+        rc_o, p_o, c_o = oracle.range_prove(v, bl, rngbits, P, nb, 7, seed)
+        rc, p, cm = api.range_prove(v, bl, rngbits, P, nb, 7, seed)
+        assert rc == rc_o == 0 and (cm == c_o).all() and (p == p_o).all()
+        assert api.range_verify(p, cm, rngbits, seed) == 1
+        badp = p.copy(); badp[1, 230] ^= 4
+        assert api.range_verify(badp, cm, rngbits, seed) == 0
+    finally:
+        api.set_use_rt(1)
