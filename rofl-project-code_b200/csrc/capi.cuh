@@ -43,6 +43,17 @@ extern "C" void rofl_rnd_scalar_vec(const uint8_t seed[32], size_t D, uint8_t *o
 // host <-> device staging helpers
 struct staged_in { dev_buf b; staged_in(const void *h, size_t n, cudaStream_t s) : b(n ? n : 16, s) { if (h && n) rt_h2d(b.p, h, n, s); } };
 
+// device field-arithmetic self test (a32, b32: n raw 256-bit little-endian values; out: n x 6 x 32 canonical encodings)
+extern "C" int rofl_field_selftest(rofl_ctx *c, const uint8_t *a32, const uint8_t *b32, size_t n, uint8_t *out) {
+    API_TRY
+    if (!n) return 0;
+    std::lock_guard<std::mutex> lk(c->e.mu); cudaStream_t s = c->e.stream;
+    staged_in da(a32, 32 * n, s), db(b32, 32 * n, s); dev_buf o(192 * n, s);
+    LAUNCH(k_field_selftest, dim3((unsigned)((n + 127) / 128)), dim3(128), s, o.as<uint8_t>(), da.b.as<uint8_t>(), db.b.as<uint8_t>(), n);
+    rt_d2h(out, o.p, 192 * n, s); rt_sync(s);
+    return 0;
+    API_CATCH
+}
 extern "C" int rofl_f32_to_scalar_vec(rofl_ctx *c, const float *v, size_t D, int n_bits, int frac, uint8_t *out) {
     API_TRY
     if (!fp_ok(n_bits, frac)) return ROFL_ERR_ARGS;

@@ -7,41 +7,24 @@
 #include <math.h>
 
 // ---- HBM record formats (16-byte aligned, one record per point / scalar) ------------------------------------------
-struct __align__(16) niels_st { uint32_t w[32]; };
-struct __align__(16) p3_st { uint32_t w[40]; };
+struct __align__(16) niels_st { uint32_t w[24]; };     //  96 B: y+x | y-x | 2dxy
+struct __align__(16) p3_st { uint32_t w[32]; };        // 128 B: X | Y | Z | T
 struct __align__(16) sc_st { uint32_t w[8]; };
 
-HD void ld_niels(ge_niels &n, const niels_st *p) {
-    const uint4 *q = (const uint4 *)p; uint32_t w[32];
-#pragma unroll
-    for (int i = 0; i < 8; i++) { uint4 v = q[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
-#pragma unroll
-    for (int i = 0; i < 10; i++) { n.yplusx.v[i] = w[i]; n.yminusx.v[i] = w[10 + i]; n.xy2d.v[i] = w[20 + i]; }
+HD void ld_fe2(fe &a, fe &b, const uint4 *q) {          // two field elements = four 16-byte loads
+    uint4 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
+    a.v[0] = v0.x; a.v[1] = v0.y; a.v[2] = v0.z; a.v[3] = v0.w; a.v[4] = v1.x; a.v[5] = v1.y; a.v[6] = v1.z; a.v[7] = v1.w;
+    b.v[0] = v2.x; b.v[1] = v2.y; b.v[2] = v2.z; b.v[3] = v2.w; b.v[4] = v3.x; b.v[5] = v3.y; b.v[6] = v3.z; b.v[7] = v3.w;
 }
-HD void st_niels(niels_st *p, const ge_niels &n) {
-    uint32_t w[32];
-#pragma unroll
-    for (int i = 0; i < 10; i++) { w[i] = n.yplusx.v[i]; w[10 + i] = n.yminusx.v[i]; w[20 + i] = n.xy2d.v[i]; }
-    w[30] = 0; w[31] = 0;
-    uint4 *q = (uint4 *)p;
-#pragma unroll
-    for (int i = 0; i < 8; i++) q[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+HD void ld_fe1(fe &a, const uint4 *q) {
+    uint4 v0 = q[0], v1 = q[1];
+    a.v[0] = v0.x; a.v[1] = v0.y; a.v[2] = v0.z; a.v[3] = v0.w; a.v[4] = v1.x; a.v[5] = v1.y; a.v[6] = v1.z; a.v[7] = v1.w;
 }
-HD void ld_p3(ge_p3 &r, const p3_st *p) {
-    const uint4 *q = (const uint4 *)p; uint32_t w[40];
-#pragma unroll
-    for (int i = 0; i < 10; i++) { uint4 v = q[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
-#pragma unroll
-    for (int i = 0; i < 10; i++) { r.X.v[i] = w[i]; r.Y.v[i] = w[10 + i]; r.Z.v[i] = w[20 + i]; r.T.v[i] = w[30 + i]; }
-}
-HD void st_p3(p3_st *p, const ge_p3 &r) {
-    uint32_t w[40];
-#pragma unroll
-    for (int i = 0; i < 10; i++) { w[i] = r.X.v[i]; w[10 + i] = r.Y.v[i]; w[20 + i] = r.Z.v[i]; w[30 + i] = r.T.v[i]; }
-    uint4 *q = (uint4 *)p;
-#pragma unroll
-    for (int i = 0; i < 10; i++) q[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-}
+HD void st_fe1(uint4 *q, const fe &a) { q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]); q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]); }
+HD void ld_niels(ge_niels &n, const niels_st *p) { const uint4 *q = (const uint4 *)p; ld_fe2(n.yplusx, n.yminusx, q); ld_fe1(n.xy2d, q + 4); }
+HD void st_niels(niels_st *p, const ge_niels &n) { uint4 *q = (uint4 *)p; st_fe1(q, n.yplusx); st_fe1(q + 2, n.yminusx); st_fe1(q + 4, n.xy2d); }
+HD void ld_p3(ge_p3 &r, const p3_st *p) { const uint4 *q = (const uint4 *)p; ld_fe2(r.X, r.Y, q); ld_fe2(r.Z, r.T, q + 4); }
+HD void st_p3(p3_st *p, const ge_p3 &r) { uint4 *q = (uint4 *)p; st_fe1(q, r.X); st_fe1(q + 2, r.Y); st_fe1(q + 4, r.Z); st_fe1(q + 6, r.T); }
 HD void ld_sc(sc &s, const sc_st *p) { const uint4 *q = (const uint4 *)p; uint4 a = q[0], b = q[1]; s.v[0] = a.x; s.v[1] = a.y; s.v[2] = a.z; s.v[3] = a.w; s.v[4] = b.x; s.v[5] = b.y; s.v[6] = b.z; s.v[7] = b.w; }
 HD void st_sc(sc_st *p, const sc &s) { uint4 *q = (uint4 *)p; q[0] = make_uint4(s.v[0], s.v[1], s.v[2], s.v[3]); q[1] = make_uint4(s.v[4], s.v[5], s.v[6], s.v[7]); }
 HD void ld_bytes32(uint8_t b[32], const uint8_t *p) { const uint4 *q = (const uint4 *)p; uint4 a = q[0], c = q[1]; uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w}; for (int i = 0; i < 32; i++) b[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3))); }

@@ -1,17 +1,16 @@
-// GF(2^255-19) for sm_100a: radix 2^25.5, 10 x u32 limbs (26,25,26,25,... bits), products accumulated
-// in 64-bit registers so every partial product is one IMAD.WIDE.U32 on the FMA pipe.
+// GF(2^255-19) for sm_100a: 8 saturated 32-bit limbs.  Every element is ANY 256-bit integer (a "loose" representative
+// mod p; 2^256 = 38 mod p), so there are no limb-scale rules: every function accepts and returns loose values.
 //
-// This is the arithmetic the reference reaches through curve25519-dalek-ng `FieldElement`
-// (rofl_crypto/Cargo.toml:13; third-party).  Written from the field definition; all functions are
-// __host__ __device__ so tests/hostsim can run the identical code on the CPU against the oracle.
+// Device code is column-wise (Comba) multiplication in inline PTX: each of the 15 product columns is an independent
+// 96-bit accumulator (lo, hi, ex) fed by `mad.lo.cc / madc.hi.cc / addc`, which ptxas fuses into ONE
+// `IMAD.WIDE.U32 Rd, Pc, Ra, Rb, Rd` (64-bit accumulate with carry-out predicate) plus half an `IADD3.X` per product
+// (tools/microbench2.cu measures that pair at the IMAD.WIDE issue rate).  A multiplication is 64 + 8 IMAD.WIDE.U32 and a
+// squaring 36 + 8, against 100 / 55 for the radix-2^25.5 representation this replaces; the IMAD.WIDE pipe
+// (32 lanes/clk/SM) is the roofline of the whole prove / verify path.
 //
-// Limb-size discipline (unsigned limbs, "scale" = multiple of the reduced bound 2^26 / 2^25):
-//   * fe_mul / fe_sq / fe_carry outputs are REDUCED: even limbs < 2^26, odd limbs < 2^25 + 2^19   (scale 1)
-//   * fe_add adds scales; fe_sub(a,b) = a + 2p - b needs scale(b) <= 1 (+slack) and gives scale(a)+2;
-//     fe_sub4(a,b) = a + 4p - b needs scale(b) <= 3 and gives scale(a)+4
-//   * fe_mul(f,g) needs scale(f)*scale(g) <= 28 and scale(g) <= 3 (19*g_i must fit u32);
-//     fe_sq(f) needs scale(f) <= 3 (38*f_i must fit u32)
-// Define FE_CHECK_BOUNDS (host builds only) to assert these preconditions at run time.
+// This is the arithmetic the reference reaches through curve25519-dalek-ng `FieldElement` (rofl_crypto/Cargo.toml:13;
+// third-party).  Written from the field definition; all functions are __host__ __device__ with a portable C path for the
+// host so tests/hostsim can run the same point / protocol code on the CPU against the oracle.
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -23,13 +22,7 @@
 #define HD inline
 #define HDNI static inline
 #endif
-
-#if defined(FE_CHECK_BOUNDS) && !defined(__CUDA_ARCH__)
-#include <assert.h>
-#define FE_ASSERT(c) assert(c)
-#else
 #define FE_ASSERT(c) ((void)0)
-#endif
 
 #if !defined(__CUDACC__)
 // host-only builds (tests/hostsim): the few CUDA vector types the storage helpers use
@@ -38,182 +31,207 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 #define __align__(n) alignas(n)
 #endif
 
-struct fe { uint32_t v[10]; };
+#define FE_LIMBS 8
+struct fe { uint32_t v[8]; };
 
-#define FE_M26 0x3ffffffu
-#define FE_M25 0x1ffffffu
-
-HD void fe_0(fe &h) { for (int i = 0; i < 10; i++) h.v[i] = 0; }
+HD void fe_0(fe &h) { for (int i = 0; i < 8; i++) h.v[i] = 0; }
 HD void fe_1(fe &h) { fe_0(h); h.v[0] = 1; }
-HD void fe_add(fe &h, const fe &f, const fe &g) { for (int i = 0; i < 10; i++) h.v[i] = f.v[i] + g.v[i]; }
-// 2p limbs: 2*(2^26-19), 2*(2^25-1), 2*(2^26-1), ...
+HD void fe_carry(fe &h, const fe &f) { h = f; }          // kept for source compatibility: loose values need no carry pass
+
+// h = f + g: 256-bit add; a carry out of bit 256 is worth 38
+HD void fe_add(fe &h, const fe &f, const fe &g) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7, c;
+    asm("add.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, %18;\n\taddc.cc.u32 %2, %11, %19;\n\taddc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\taddc.cc.u32 %5, %14, %22;\n\taddc.cc.u32 %6, %15, %23;\n\taddc.cc.u32 %7, %16, %24;\n\taddc.u32 %8, 0, 0;"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7), "=r"(c)
+        : "r"(f.v[0]), "r"(f.v[1]), "r"(f.v[2]), "r"(f.v[3]), "r"(f.v[4]), "r"(f.v[5]), "r"(f.v[6]), "r"(f.v[7]),
+          "r"(g.v[0]), "r"(g.v[1]), "r"(g.v[2]), "r"(g.v[3]), "r"(g.v[4]), "r"(g.v[5]), "r"(g.v[6]), "r"(g.v[7]));
+    c *= 38;
+    asm("add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\taddc.cc.u32 %5, %5, 0;\n\taddc.cc.u32 %6, %6, 0;\n\taddc.cc.u32 %7, %7, 0;\n\taddc.u32 %8, 0, 0;"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(c));
+    r0 += 38 * c;                                        // second wrap only when the sum was >= 2^256 - 38: r0 < 38, no carry
+    h.v[0] = r0; h.v[1] = r1; h.v[2] = r2; h.v[3] = r3; h.v[4] = r4; h.v[5] = r5; h.v[6] = r6; h.v[7] = r7;
+#else
+    uint64_t c = 0; uint32_t r[8];
+    for (int i = 0; i < 8; i++) { c += (uint64_t)f.v[i] + g.v[i]; r[i] = (uint32_t)c; c >>= 32; }
+    c *= 38;
+    for (int i = 0; i < 8; i++) { c += r[i]; r[i] = (uint32_t)c; c >>= 32; }
+    r[0] += 38 * (uint32_t)c;
+    for (int i = 0; i < 8; i++) h.v[i] = r[i];
+#endif
+}
+// h = f - g: 256-bit subtract; a borrow out of bit 256 is worth -38
 HD void fe_sub(fe &h, const fe &f, const fe &g) {
-    FE_ASSERT(g.v[0] <= 0x7ffffdau);
-    h.v[0] = f.v[0] + 0x7ffffdau - g.v[0];
-    for (int i = 1; i < 10; i++) {
-        uint32_t b = (i & 1) ? 0x3fffffeu : 0x7fffffeu;
-        FE_ASSERT(g.v[i] <= b);
-        h.v[i] = f.v[i] + b - g.v[i];
-    }
+#if defined(__CUDA_ARCH__)
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7, b;
+    asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, %18;\n\tsubc.cc.u32 %2, %11, %19;\n\tsubc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\tsubc.cc.u32 %5, %14, %22;\n\tsubc.cc.u32 %6, %15, %23;\n\tsubc.cc.u32 %7, %16, %24;\n\tsubc.u32 %8, 0, 0;"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7), "=r"(b)
+        : "r"(f.v[0]), "r"(f.v[1]), "r"(f.v[2]), "r"(f.v[3]), "r"(f.v[4]), "r"(f.v[5]), "r"(f.v[6]), "r"(f.v[7]),
+          "r"(g.v[0]), "r"(g.v[1]), "r"(g.v[2]), "r"(g.v[3]), "r"(g.v[4]), "r"(g.v[5]), "r"(g.v[6]), "r"(g.v[7]));
+    b = (b & 1) * 38;                                    // b = 0xffffffff on borrow
+    asm("sub.cc.u32 %0, %0, %8;\n\tsubc.cc.u32 %1, %1, 0;\n\tsubc.cc.u32 %2, %2, 0;\n\tsubc.cc.u32 %3, %3, 0;\n\t"
+        "subc.cc.u32 %4, %4, 0;\n\tsubc.cc.u32 %5, %5, 0;\n\tsubc.cc.u32 %6, %6, 0;\n\tsubc.cc.u32 %7, %7, 0;\n\tsubc.u32 %8, 0, 0;"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(b));
+    r0 -= 38 * (b & 1);                                  // second wrap only when the difference was < 38 - 2^256 ...: r0 >= 2^32 - 38, no borrow
+    h.v[0] = r0; h.v[1] = r1; h.v[2] = r2; h.v[3] = r3; h.v[4] = r4; h.v[5] = r5; h.v[6] = r6; h.v[7] = r7;
+#else
+    int64_t c = 0; uint32_t r[8];
+    for (int i = 0; i < 8; i++) { c += (int64_t)f.v[i] - (int64_t)g.v[i]; r[i] = (uint32_t)c; c >>= 32; }
+    c *= 38;                                             // c = 0 or -1
+    for (int i = 0; i < 8; i++) { c += r[i]; r[i] = (uint32_t)c; c >>= 32; }
+    r[0] -= 38 * (uint32_t)(-c);
+    for (int i = 0; i < 8; i++) h.v[i] = r[i];
+#endif
 }
-// a + 4p - b
-HD void fe_sub4(fe &h, const fe &f, const fe &g) {
-    FE_ASSERT(g.v[0] <= 0xfffffb4u);
-    h.v[0] = f.v[0] + 0xfffffb4u - g.v[0];
-    for (int i = 1; i < 10; i++) {
-        uint32_t b = (i & 1) ? 0x7fffffcu : 0xffffffcu;
-        FE_ASSERT(g.v[i] <= b);
-        h.v[i] = f.v[i] + b - g.v[i];
-    }
-}
+HD void fe_sub4(fe &h, const fe &f, const fe &g) { fe_sub(h, f, g); }
 HD void fe_neg(fe &h, const fe &f) { fe z; fe_0(z); fe_sub(h, z, f); }
 
-// carry chain on ten 64-bit columns -> reduced limbs
-HD void fe_reduce64(fe &h, uint64_t t[10]) {
-    uint64_t c;
-    c = t[0] >> 26; t[1] += c; h.v[0] = (uint32_t)t[0] & FE_M26;
-    c = t[1] >> 25; t[2] += c; h.v[1] = (uint32_t)t[1] & FE_M25;
-    c = t[2] >> 26; t[3] += c; h.v[2] = (uint32_t)t[2] & FE_M26;
-    c = t[3] >> 25; t[4] += c; h.v[3] = (uint32_t)t[3] & FE_M25;
-    c = t[4] >> 26; t[5] += c; h.v[4] = (uint32_t)t[4] & FE_M26;
-    c = t[5] >> 25; t[6] += c; h.v[5] = (uint32_t)t[5] & FE_M25;
-    c = t[6] >> 26; t[7] += c; h.v[6] = (uint32_t)t[6] & FE_M26;
-    c = t[7] >> 25; t[8] += c; h.v[7] = (uint32_t)t[7] & FE_M25;
-    c = t[8] >> 26; t[9] += c; h.v[8] = (uint32_t)t[8] & FE_M26;
-    c = t[9] >> 25;            h.v[9] = (uint32_t)t[9] & FE_M25;
-    // c < 2^39; wrap 19*c into limb 0 and carry once more into limb 1
-    uint64_t w = (uint64_t)h.v[0] + c * 19;
-    h.v[0] = (uint32_t)w & FE_M26;
-    h.v[1] += (uint32_t)(w >> 26);
+// ---- reduction of a 512-bit product t[0..15] to a loose 256-bit value: lo + 38 hi, then fold the 6-bit overflow twice ----
+#if defined(__CUDA_ARCH__)
+// d = a*b + c (64-bit, cannot overflow for b = 38): one IMAD.WIDE.U32
+__device__ __forceinline__ uint64_t fe_mad_wide(uint32_t a, uint32_t b, uint32_t c) {
+    uint64_t d; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"((uint64_t)c)); return d;
 }
-HD void fe_carry(fe &h, const fe &f) {
-    uint64_t t[10];
-    for (int i = 0; i < 10; i++) t[i] = f.v[i];
-    fe_reduce64(h, t);
+__device__ __forceinline__ void fe_reduce512(fe &h, const uint32_t t[16]) {
+    uint64_t d0 = fe_mad_wide(t[8], 38, t[0]), d1 = fe_mad_wide(t[9], 38, t[1]), d2 = fe_mad_wide(t[10], 38, t[2]), d3 = fe_mad_wide(t[11], 38, t[3]);
+    uint64_t d4 = fe_mad_wide(t[12], 38, t[4]), d5 = fe_mad_wide(t[13], 38, t[5]), d6 = fe_mad_wide(t[14], 38, t[6]), d7 = fe_mad_wide(t[15], 38, t[7]);
+    uint32_t r0 = (uint32_t)d0, r1, r2, r3, r4, r5, r6, r7, top;
+    asm("add.cc.u32 %0, %8, %9;\n\taddc.cc.u32 %1, %10, %11;\n\taddc.cc.u32 %2, %12, %13;\n\taddc.cc.u32 %3, %14, %15;\n\t"
+        "addc.cc.u32 %4, %16, %17;\n\taddc.cc.u32 %5, %18, %19;\n\taddc.cc.u32 %6, %20, %21;\n\taddc.u32 %7, %22, 0;"
+        : "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7), "=r"(top)
+        : "r"((uint32_t)d1), "r"((uint32_t)(d0 >> 32)), "r"((uint32_t)d2), "r"((uint32_t)(d1 >> 32)), "r"((uint32_t)d3), "r"((uint32_t)(d2 >> 32)),
+          "r"((uint32_t)d4), "r"((uint32_t)(d3 >> 32)), "r"((uint32_t)d5), "r"((uint32_t)(d4 >> 32)), "r"((uint32_t)d6), "r"((uint32_t)(d5 >> 32)),
+          "r"((uint32_t)d7), "r"((uint32_t)(d6 >> 32)), "r"((uint32_t)(d7 >> 32)));
+    uint32_t c = top * 38;                               // top <= 38
+    asm("add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\taddc.cc.u32 %5, %5, 0;\n\taddc.cc.u32 %6, %6, 0;\n\taddc.cc.u32 %7, %7, 0;\n\taddc.u32 %8, 0, 0;"
+        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(c));
+    r0 += 38 * c;
+    h.v[0] = r0; h.v[1] = r1; h.v[2] = r2; h.v[3] = r3; h.v[4] = r4; h.v[5] = r5; h.v[6] = r6; h.v[7] = r7;
 }
-
-#define M64(a, b) ((uint64_t)(a) * (uint64_t)(b))
+// column accumulator: (lo, hi, ex) += a*b
+#define FE_MAC(lo, hi, ex, a, b) asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;" : "+r"(lo), "+r"(hi), "+r"(ex) : "r"(a), "r"(b))
+#define FE_MUL0(lo, hi, a, b) do { uint64_t p_; asm("mul.wide.u32 %0, %1, %2;" : "=l"(p_) : "r"(a), "r"(b)); lo = (uint32_t)p_; hi = (uint32_t)(p_ >> 32); } while (0)
+// fold 15 column accumulators into 16 words: word k = lo_k + hi_(k-1) + ex_(k-2) + carries
+__device__ __forceinline__ void fe_columns_to_words(uint32_t t[16], const uint32_t lo[15], const uint32_t hi[15], const uint32_t ex[15]) {
+    t[0] = lo[0];
+    asm("add.cc.u32 %0, %15, %30;\n\taddc.cc.u32 %1, %16, %31;\n\taddc.cc.u32 %2, %17, %32;\n\taddc.cc.u32 %3, %18, %33;\n\taddc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\taddc.cc.u32 %6, %21, %36;\n\taddc.cc.u32 %7, %22, %37;\n\taddc.cc.u32 %8, %23, %38;\n\taddc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\taddc.cc.u32 %11, %26, %41;\n\taddc.cc.u32 %12, %27, %42;\n\taddc.cc.u32 %13, %28, %43;\n\taddc.u32 %14, %29, 0;"
+        : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+        : "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]), "r"(lo[8]), "r"(lo[9]), "r"(lo[10]), "r"(lo[11]), "r"(lo[12]), "r"(lo[13]), "r"(lo[14]), "r"(hi[14]),
+          "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]), "r"(hi[8]), "r"(hi[9]), "r"(hi[10]), "r"(hi[11]), "r"(hi[12]), "r"(hi[13]));
+    asm("add.cc.u32 %0, %0, %14;\n\taddc.cc.u32 %1, %1, %15;\n\taddc.cc.u32 %2, %2, %16;\n\taddc.cc.u32 %3, %3, %17;\n\taddc.cc.u32 %4, %4, %18;\n\t"
+        "addc.cc.u32 %5, %5, %19;\n\taddc.cc.u32 %6, %6, %20;\n\taddc.cc.u32 %7, %7, %21;\n\taddc.cc.u32 %8, %8, %22;\n\taddc.cc.u32 %9, %9, %23;\n\t"
+        "addc.cc.u32 %10, %10, %24;\n\taddc.cc.u32 %11, %11, %25;\n\taddc.cc.u32 %12, %12, %26;\n\taddc.u32 %13, %13, %27;"
+        : "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+        : "r"(ex[0]), "r"(ex[1]), "r"(ex[2]), "r"(ex[3]), "r"(ex[4]), "r"(ex[5]), "r"(ex[6]), "r"(ex[7]), "r"(ex[8]), "r"(ex[9]), "r"(ex[10]), "r"(ex[11]), "r"(ex[12]), "r"(ex[13]));
+}
+#endif
+// portable reduction (host)
+HD void fe_reduce512_c(fe &h, const uint32_t t[16]) {
+    uint64_t c = 0; uint32_t r[8];
+    for (int i = 0; i < 8; i++) { c += (uint64_t)t[i] + 38ull * t[8 + i]; r[i] = (uint32_t)c; c >>= 32; }
+    c *= 38;
+    for (int i = 0; i < 8; i++) { c += r[i]; r[i] = (uint32_t)c; c >>= 32; }
+    r[0] += 38 * (uint32_t)c;
+    for (int i = 0; i < 8; i++) h.v[i] = r[i];
+}
 
 HD void fe_mul(fe &h, const fe &f, const fe &g) {
-    const uint32_t f0 = f.v[0], f1 = f.v[1], f2 = f.v[2], f3 = f.v[3], f4 = f.v[4], f5 = f.v[5], f6 = f.v[6], f7 = f.v[7], f8 = f.v[8], f9 = f.v[9];
-    const uint32_t g0 = g.v[0], g1 = g.v[1], g2 = g.v[2], g3 = g.v[3], g4 = g.v[4], g5 = g.v[5], g6 = g.v[6], g7 = g.v[7], g8 = g.v[8], g9 = g.v[9];
-#if defined(FE_CHECK_BOUNDS) && !defined(__CUDA_ARCH__)
-    for (int i = 0; i < 10; i++) { FE_ASSERT((uint64_t)g.v[i] * 19 < (1ull << 32)); FE_ASSERT(f.v[i] < (1u << 31)); }
-    { uint32_t mf = 0, mg = 0; for (int i = 0; i < 10; i++) { uint32_t a = f.v[i] >> ((i & 1) ? 25 : 26), b = g.v[i] >> ((i & 1) ? 25 : 26); if (a > mf) mf = a; if (b > mg) mg = b; }
-      FE_ASSERT((uint64_t)(mf + 1) * (mg + 1) <= 30); }
+#if defined(__CUDA_ARCH__)
+    uint32_t lo[15], hi[15], ex[15];
+#pragma unroll
+    for (int k = 0; k < 15; k++) {
+        const int i0 = k < 8 ? 0 : k - 7, i1 = k < 8 ? k : 7;
+        FE_MUL0(lo[k], hi[k], f.v[i0], g.v[k - i0]); ex[k] = 0;
+#pragma unroll
+        for (int i = i0 + 1; i <= i1; i++) FE_MAC(lo[k], hi[k], ex[k], f.v[i], g.v[k - i]);
+    }
+    uint32_t t[16]; fe_columns_to_words(t, lo, hi, ex);
+    fe_reduce512(h, t);
+#else
+    uint32_t t[16]; for (int i = 0; i < 16; i++) t[i] = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 8; j++) { c += (uint64_t)f.v[i] * g.v[j] + t[i + j]; t[i + j] = (uint32_t)c; c >>= 32; }
+        t[i + 8] = (uint32_t)c;
+    }
+    fe_reduce512_c(h, t);
 #endif
-    const uint32_t g1_19 = 19 * g1, g2_19 = 19 * g2, g3_19 = 19 * g3, g4_19 = 19 * g4, g5_19 = 19 * g5, g6_19 = 19 * g6, g7_19 = 19 * g7, g8_19 = 19 * g8, g9_19 = 19 * g9;
-    const uint32_t f1_2 = 2 * f1, f3_2 = 2 * f3, f5_2 = 2 * f5, f7_2 = 2 * f7, f9_2 = 2 * f9;
-    uint64_t t[10];
-    t[0] = M64(f0, g0) + M64(f1_2, g9_19) + M64(f2, g8_19) + M64(f3_2, g7_19) + M64(f4, g6_19) + M64(f5_2, g5_19) + M64(f6, g4_19) + M64(f7_2, g3_19) + M64(f8, g2_19) + M64(f9_2, g1_19);
-    t[1] = M64(f0, g1) + M64(f1, g0) + M64(f2, g9_19) + M64(f3, g8_19) + M64(f4, g7_19) + M64(f5, g6_19) + M64(f6, g5_19) + M64(f7, g4_19) + M64(f8, g3_19) + M64(f9, g2_19);
-    t[2] = M64(f0, g2) + M64(f1_2, g1) + M64(f2, g0) + M64(f3_2, g9_19) + M64(f4, g8_19) + M64(f5_2, g7_19) + M64(f6, g6_19) + M64(f7_2, g5_19) + M64(f8, g4_19) + M64(f9_2, g3_19);
-    t[3] = M64(f0, g3) + M64(f1, g2) + M64(f2, g1) + M64(f3, g0) + M64(f4, g9_19) + M64(f5, g8_19) + M64(f6, g7_19) + M64(f7, g6_19) + M64(f8, g5_19) + M64(f9, g4_19);
-    t[4] = M64(f0, g4) + M64(f1_2, g3) + M64(f2, g2) + M64(f3_2, g1) + M64(f4, g0) + M64(f5_2, g9_19) + M64(f6, g8_19) + M64(f7_2, g7_19) + M64(f8, g6_19) + M64(f9_2, g5_19);
-    t[5] = M64(f0, g5) + M64(f1, g4) + M64(f2, g3) + M64(f3, g2) + M64(f4, g1) + M64(f5, g0) + M64(f6, g9_19) + M64(f7, g8_19) + M64(f8, g7_19) + M64(f9, g6_19);
-    t[6] = M64(f0, g6) + M64(f1_2, g5) + M64(f2, g4) + M64(f3_2, g3) + M64(f4, g2) + M64(f5_2, g1) + M64(f6, g0) + M64(f7_2, g9_19) + M64(f8, g8_19) + M64(f9_2, g7_19);
-    t[7] = M64(f0, g7) + M64(f1, g6) + M64(f2, g5) + M64(f3, g4) + M64(f4, g3) + M64(f5, g2) + M64(f6, g1) + M64(f7, g0) + M64(f8, g9_19) + M64(f9, g8_19);
-    t[8] = M64(f0, g8) + M64(f1_2, g7) + M64(f2, g6) + M64(f3_2, g5) + M64(f4, g4) + M64(f5_2, g3) + M64(f6, g2) + M64(f7_2, g1) + M64(f8, g0) + M64(f9_2, g9_19);
-    t[9] = M64(f0, g9) + M64(f1, g8) + M64(f2, g7) + M64(f3, g6) + M64(f4, g5) + M64(f5, g4) + M64(f6, g3) + M64(f7, g2) + M64(f8, g1) + M64(f9, g0);
-    fe_reduce64(h, t);
 }
 
 HD void fe_sq(fe &h, const fe &f) {
-    const uint32_t f0 = f.v[0], f1 = f.v[1], f2 = f.v[2], f3 = f.v[3], f4 = f.v[4], f5 = f.v[5], f6 = f.v[6], f7 = f.v[7], f8 = f.v[8], f9 = f.v[9];
-#if defined(FE_CHECK_BOUNDS) && !defined(__CUDA_ARCH__)
-    for (int i = 0; i < 10; i++) FE_ASSERT(f.v[i] < (3u << ((i & 1) ? 25 : 26)) + (1u << 20));      // scale <= 3
-    FE_ASSERT((uint64_t)f5 * 38 < (1ull << 32) && (uint64_t)f7 * 38 < (1ull << 32) && (uint64_t)f9 * 38 < (1ull << 32));
-    FE_ASSERT((uint64_t)f6 * 19 < (1ull << 32) && (uint64_t)f8 * 19 < (1ull << 32));
+#if defined(__CUDA_ARCH__)
+    // off-diagonal products once, doubled by a 1-bit shift of the whole 512-bit value, then the diagonal squares
+    uint32_t lo[15], hi[15], ex[15];
+    lo[0] = hi[0] = ex[0] = 0; lo[14] = hi[14] = ex[14] = 0;
+#pragma unroll
+    for (int k = 1; k < 14; k++) {
+        const int i0 = k < 8 ? 0 : k - 7;            // pairs i < j = k - i  <=>  i0 <= i < k/2 (+1 if k odd)
+        const int i1 = (k - 1) / 2;
+        FE_MUL0(lo[k], hi[k], f.v[i0], f.v[k - i0]); ex[k] = 0;
+#pragma unroll
+        for (int i = i0 + 1; i <= i1; i++) FE_MAC(lo[k], hi[k], ex[k], f.v[i], f.v[k - i]);
+    }
+    uint32_t t[16]; fe_columns_to_words(t, lo, hi, ex);
+#pragma unroll
+    for (int i = 15; i > 0; i--) t[i] = (t[i] << 1) | (t[i - 1] >> 31);
+    t[0] <<= 1;
+    uint32_t dl[8], dh[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) FE_MUL0(dl[i], dh[i], f.v[i], f.v[i]);
+    asm("add.cc.u32 %0, %0, %16;\n\taddc.cc.u32 %1, %1, %17;\n\taddc.cc.u32 %2, %2, %18;\n\taddc.cc.u32 %3, %3, %19;\n\taddc.cc.u32 %4, %4, %20;\n\t"
+        "addc.cc.u32 %5, %5, %21;\n\taddc.cc.u32 %6, %6, %22;\n\taddc.cc.u32 %7, %7, %23;\n\taddc.cc.u32 %8, %8, %24;\n\taddc.cc.u32 %9, %9, %25;\n\t"
+        "addc.cc.u32 %10, %10, %26;\n\taddc.cc.u32 %11, %11, %27;\n\taddc.cc.u32 %12, %12, %28;\n\taddc.cc.u32 %13, %13, %29;\n\taddc.cc.u32 %14, %14, %30;\n\taddc.u32 %15, %15, %31;"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+        : "r"(dl[0]), "r"(dh[0]), "r"(dl[1]), "r"(dh[1]), "r"(dl[2]), "r"(dh[2]), "r"(dl[3]), "r"(dh[3]), "r"(dl[4]), "r"(dh[4]), "r"(dl[5]), "r"(dh[5]), "r"(dl[6]), "r"(dh[6]), "r"(dl[7]), "r"(dh[7]));
+    fe_reduce512(h, t);
+#else
+    fe_mul(h, f, f);
 #endif
-    const uint32_t f0_2 = 2 * f0, f1_2 = 2 * f1, f2_2 = 2 * f2, f3_2 = 2 * f3, f4_2 = 2 * f4, f5_2 = 2 * f5, f6_2 = 2 * f6, f7_2 = 2 * f7;
-    const uint32_t f5_38 = 38 * f5, f6_19 = 19 * f6, f7_38 = 38 * f7, f8_19 = 19 * f8, f9_38 = 38 * f9;
-    uint64_t t[10];
-    t[0] = M64(f0, f0) + M64(f1_2, f9_38) + M64(f2_2, f8_19) + M64(f3_2, f7_38) + M64(f4_2, f6_19) + M64(f5, f5_38);
-    t[1] = M64(f0_2, f1) + M64(f2, f9_38) + M64(f3_2, f8_19) + M64(f4, f7_38) + M64(f5_2, f6_19);
-    t[2] = M64(f0_2, f2) + M64(f1_2, f1) + M64(f3_2, f9_38) + M64(f4_2, f8_19) + M64(f5_2, f7_38) + M64(f6, f6_19);
-    t[3] = M64(f0_2, f3) + M64(f1_2, f2) + M64(f4, f9_38) + M64(f5_2, f8_19) + M64(f6, f7_38);
-    t[4] = M64(f0_2, f4) + M64(f1_2, f3_2) + M64(f2, f2) + M64(f5_2, f9_38) + M64(f6_2, f8_19) + M64(f7, f7_38);
-    t[5] = M64(f0_2, f5) + M64(f1_2, f4) + M64(f2_2, f3) + M64(f6, f9_38) + M64(f7_2, f8_19);
-    t[6] = M64(f0_2, f6) + M64(f1_2, f5_2) + M64(f2_2, f4) + M64(f3_2, f3) + M64(f7_2, f9_38) + M64(f8, f8_19);
-    t[7] = M64(f0_2, f7) + M64(f1_2, f6) + M64(f2_2, f5) + M64(f3_2, f4) + M64(f8, f9_38);
-    t[8] = M64(f0_2, f8) + M64(f1_2, f7_2) + M64(f2_2, f6) + M64(f3_2, f5_2) + M64(f4, f4) + M64(f9, f9_38);
-    t[9] = M64(f0_2, f9) + M64(f1_2, f8) + M64(f2_2, f7) + M64(f3_2, f6) + M64(f4_2, f5);
-    fe_reduce64(h, t);
 }
 HD void fe_sqn(fe &h, const fe &f, int n) { fe_sq(h, f); for (int i = 1; i < n; i++) fe_sq(h, h); }
-// small-constant multiply (c*scale must stay in range); result reduced
+// multiply by a small constant (c < 2^26)
 HD void fe_mul_small(fe &h, const fe &f, uint32_t c) {
-    uint64_t t[10];
-    for (int i = 0; i < 10; i++) t[i] = M64(f.v[i], c);
-    fe_reduce64(h, t);
+    uint32_t t[16]; uint64_t cy = 0;
+    for (int i = 0; i < 8; i++) { cy += (uint64_t)f.v[i] * c; t[i] = (uint32_t)cy; cy >>= 32; }
+    t[8] = (uint32_t)cy; for (int i = 9; i < 16; i++) t[i] = 0;
+    fe_reduce512_c(h, t);
 }
 
 // little-endian bytes, bit 255 ignored (dalek FieldElement::from_bytes)
 HD void fe_frombytes(fe &h, const uint8_t *s) {
-    uint32_t w[8];
-    for (int i = 0; i < 8; i++) w[i] = (uint32_t)s[4 * i] | ((uint32_t)s[4 * i + 1] << 8) | ((uint32_t)s[4 * i + 2] << 16) | ((uint32_t)s[4 * i + 3] << 24);
-    // limb offsets (bits): 0,26,51,77,102,128,153,179,204,230
-    h.v[0] = w[0] & FE_M26;
-    h.v[1] = ((w[0] >> 26) | (w[1] << 6)) & FE_M25;
-    h.v[2] = ((w[1] >> 19) | (w[2] << 13)) & FE_M26;
-    h.v[3] = ((w[2] >> 13) | (w[3] << 19)) & FE_M25;
-    h.v[4] = (w[3] >> 6) & FE_M26;
-    h.v[5] = w[4] & FE_M25;
-    h.v[6] = ((w[4] >> 25) | (w[5] << 7)) & FE_M26;
-    h.v[7] = ((w[5] >> 19) | (w[6] << 13)) & FE_M25;
-    h.v[8] = ((w[6] >> 12) | (w[7] << 20)) & FE_M26;
-    h.v[9] = (w[7] >> 6) & FE_M25;
+    for (int i = 0; i < 8; i++) h.v[i] = (uint32_t)s[4 * i] | ((uint32_t)s[4 * i + 1] << 8) | ((uint32_t)s[4 * i + 2] << 16) | ((uint32_t)s[4 * i + 3] << 24);
+    h.v[7] &= 0x7fffffffu;
 }
-// from 8 little-endian 32-bit words
-HD void fe_fromwords(fe &h, const uint32_t w[8]) {
-    h.v[0] = w[0] & FE_M26;
-    h.v[1] = ((w[0] >> 26) | (w[1] << 6)) & FE_M25;
-    h.v[2] = ((w[1] >> 19) | (w[2] << 13)) & FE_M26;
-    h.v[3] = ((w[2] >> 13) | (w[3] << 19)) & FE_M25;
-    h.v[4] = (w[3] >> 6) & FE_M26;
-    h.v[5] = w[4] & FE_M25;
-    h.v[6] = ((w[4] >> 25) | (w[5] << 7)) & FE_M26;
-    h.v[7] = ((w[5] >> 19) | (w[6] << 13)) & FE_M25;
-    h.v[8] = ((w[6] >> 12) | (w[7] << 20)) & FE_M26;
-    h.v[9] = (w[7] >> 6) & FE_M25;
-}
-// canonical value as 8 little-endian words
+HD void fe_fromwords(fe &h, const uint32_t w[8]) { for (int i = 0; i < 8; i++) h.v[i] = w[i]; h.v[7] &= 0x7fffffffu; }
+// canonical value (< p) as 8 little-endian words
 HD void fe_towords(uint32_t w[8], const fe &f) {
-    fe t; fe_carry(t, f); fe_carry(t, t);          // limbs now tight: even < 2^26, odd < 2^25 (+1 on limb 1)
-    // q = 1 iff t >= p : propagate t + 19 through the limbs
-    uint32_t q = (t.v[0] + 19) >> 26;
-    q = (t.v[1] + q) >> 25; q = (t.v[2] + q) >> 26; q = (t.v[3] + q) >> 25; q = (t.v[4] + q) >> 26;
-    q = (t.v[5] + q) >> 25; q = (t.v[6] + q) >> 26; q = (t.v[7] + q) >> 25; q = (t.v[8] + q) >> 26; q = (t.v[9] + q) >> 25;
-    t.v[0] += 19 * q;
-    uint32_t c;
-    c = t.v[0] >> 26; t.v[0] &= FE_M26; t.v[1] += c;
-    c = t.v[1] >> 25; t.v[1] &= FE_M25; t.v[2] += c;
-    c = t.v[2] >> 26; t.v[2] &= FE_M26; t.v[3] += c;
-    c = t.v[3] >> 25; t.v[3] &= FE_M25; t.v[4] += c;
-    c = t.v[4] >> 26; t.v[4] &= FE_M26; t.v[5] += c;
-    c = t.v[5] >> 25; t.v[5] &= FE_M25; t.v[6] += c;
-    c = t.v[6] >> 26; t.v[6] &= FE_M26; t.v[7] += c;
-    c = t.v[7] >> 25; t.v[7] &= FE_M25; t.v[8] += c;
-    c = t.v[8] >> 26; t.v[8] &= FE_M26; t.v[9] += c;
-    t.v[9] &= FE_M25;
-    w[0] = t.v[0] | (t.v[1] << 26);
-    w[1] = (t.v[1] >> 6) | (t.v[2] << 19);
-    w[2] = (t.v[2] >> 13) | (t.v[3] << 13);
-    w[3] = (t.v[3] >> 19) | (t.v[4] << 6);
-    w[4] = t.v[5] | (t.v[6] << 25);
-    w[5] = (t.v[6] >> 7) | (t.v[7] << 19);
-    w[6] = (t.v[7] >> 13) | (t.v[8] << 12);
-    w[7] = (t.v[8] >> 20) | (t.v[9] << 6);
+    // fold bit 255 (worth 19) twice: value < 2^255 + 19 -> < 2^255 after the second fold unless the value is in [p, 2^255)
+    uint32_t r[8]; for (int i = 0; i < 8; i++) r[i] = f.v[i];
+    for (int pass = 0; pass < 2; pass++) {
+        uint64_t c = 19ull * (r[7] >> 31); r[7] &= 0x7fffffffu;
+        for (int i = 0; i < 8; i++) { c += r[i]; r[i] = (uint32_t)c; c >>= 32; }
+    }
+    // now r < 2^255; subtract p iff r >= p  <=>  r + 19 >= 2^255
+    uint32_t q[8]; uint64_t c = 19;
+    for (int i = 0; i < 8; i++) { c += r[i]; q[i] = (uint32_t)c; c >>= 32; }
+    const bool ge = (q[7] >> 31) != 0;
+    q[7] &= 0x7fffffffu;
+    for (int i = 0; i < 8; i++) w[i] = ge ? q[i] : r[i];
 }
 HD void fe_tobytes(uint8_t *s, const fe &f) {
     uint32_t w[8]; fe_towords(w, f);
     for (int i = 0; i < 8; i++) { s[4 * i] = (uint8_t)w[i]; s[4 * i + 1] = (uint8_t)(w[i] >> 8); s[4 * i + 2] = (uint8_t)(w[i] >> 16); s[4 * i + 3] = (uint8_t)(w[i] >> 24); }
 }
 HD bool fe_iszero(const fe &f) { uint32_t w[8]; fe_towords(w, f); uint32_t r = 0; for (int i = 0; i < 8; i++) r |= w[i]; return r == 0; }
-HD bool fe_eq(const fe &f, const fe &g) { fe c, t; fe_carry(c, g); fe_sub(t, f, c); return fe_iszero(t); }
+HD bool fe_eq(const fe &f, const fe &g) { fe t; fe_sub(t, f, g); return fe_iszero(t); }
 HD bool fe_isneg(const fe &f) { uint32_t w[8]; fe_towords(w, f); return w[0] & 1; }
-HD void fe_cmov(fe &h, const fe &g, bool b) { for (int i = 0; i < 10; i++) h.v[i] = b ? g.v[i] : h.v[i]; }
-// input must be reduced
+HD void fe_cmov(fe &h, const fe &g, bool b) { for (int i = 0; i < 8; i++) h.v[i] = b ? g.v[i] : h.v[i]; }
 HD void fe_abs(fe &h, const fe &f) { fe n; fe_neg(n, f); bool neg = fe_isneg(f); h = f; fe_cmov(h, n, neg); }
 
 // z^(2^252-3)

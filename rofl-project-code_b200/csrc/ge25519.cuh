@@ -11,7 +11,7 @@
 #pragma once
 #include "fe25519.cuh"
 #include "sc25519.cuh"
-#include "constants25.cuh"
+#include "constants32.cuh"
 
 struct ge_p3 { fe X, Y, Z, T; };
 struct ge_p2 { fe X, Y, Z; };

@@ -6,8 +6,8 @@
 // product library.
 //
 // HBM layout (all arrays 16-byte aligned, one record per point/scalar so gathers touch whole sectors):
-//   niels_st  128 B : affine (y+x, y-x, 2dxy) radix-2^25.5 limbs, 30 words + 2 pad   -- fixed generators, tables
-//   p3_st     160 B : extended (X,Y,Z,T), 40 words                                    -- folded generators, partial sums
+//   niels_st   96 B : affine (y+x, y-x, 2dxy), 3 x 8 saturated 32-bit limbs            -- fixed generators, tables
+//   p3_st     128 B : extended (X,Y,Z,T), 4 x 8 limbs                                 -- folded generators, partial sums
 //   sc        32 B  : canonical scalar, 8 words
 #pragma once
 #include "devfn.cuh"
@@ -158,6 +158,27 @@ KERNEL void LB(128, 1) k_commit(commit_args a) {
     }
 }
 KLAUNCH(k_commit, false, (commit_args a), (a))
+#endif
+
+// field self-test (tests/test_gpu_parity.py): raw 256-bit inputs (NOT masked: loose representatives incl. values >= p) ->
+// canonical encodings of a*b, a^2, a+b, a-b, (a+b)*(a-b), 1/a computed by the device code paths
+#ifdef KG_COMMIT
+KERNEL void LB(128, 1) k_field_selftest(uint8_t *out, const uint8_t *a32, const uint8_t *b32, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe a, b, r, s, t;
+    for (int k = 0; k < 8; k++) { const uint8_t *pa = a32 + 32 * i + 4 * k, *pb = b32 + 32 * i + 4 * k;
+        a.v[k] = (uint32_t)pa[0] | ((uint32_t)pa[1] << 8) | ((uint32_t)pa[2] << 16) | ((uint32_t)pa[3] << 24);
+        b.v[k] = (uint32_t)pb[0] | ((uint32_t)pb[1] << 8) | ((uint32_t)pb[2] << 16) | ((uint32_t)pb[3] << 24); }
+    uint8_t *o = out + 192 * i;
+    fe_mul(r, a, b); fe_tobytes(o, r);
+    fe_sq(r, a); fe_tobytes(o + 32, r);
+    fe_add(s, a, b); fe_tobytes(o + 64, s);
+    fe_sub(t, a, b); fe_tobytes(o + 96, t);
+    fe_mul(r, s, t); fe_tobytes(o + 128, r);
+    fe_invert(r, a); fe_tobytes(o + 160, r);
+}
+KLAUNCH(k_field_selftest, false, (uint8_t *out, const uint8_t *a32, const uint8_t *b32, size_t n), (out, a32, b32, n))
 #endif
 
 // ===================================================================================================================
@@ -835,6 +856,7 @@ KLAUNCH(k_l2_sums, true, (sc_st *partial, const float *v, const uint8_t *blind, 
 void launch_k_fb_table_build(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *tab, const uint8_t *pt);
 void launch_k_gens_build(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *G, niels_st *H, int n, int party_begin, int party_end);
 void launch_k_commit(dim3 g_, dim3 b_, cudaStream_t s_, commit_args a);
+void launch_k_field_selftest(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const uint8_t *a32, const uint8_t *b32, size_t n);
 void launch_k_nonces(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *sLR, const uint32_t *keys, int n, int m, size_t total);
 void launch_k_party_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *out, const uint32_t *keys, const sc_st *blind, const sc_st *z, int n, int m, int phase);
 void launch_k_bits_sum(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *partial, const uint64_t *vals, const niels_st *G, const niels_st *H, int n, int m);

@@ -5,7 +5,7 @@
 // All __host__ __device__ (see fe25519.cuh).
 #pragma once
 #include "fe25519.cuh"
-#include "constants25.cuh"
+#include "constants32.cuh"
 
 struct sc { uint32_t v[8]; };
 

@@ -26,6 +26,24 @@ def test_library_is_cuda_and_loaded(api):
     assert api.lib.rofl_ctx_stream(api.h) is not None
 
 
+def test_field_arithmetic_device_paths(api):
+    """The inline-PTX field arithmetic (fe25519.cuh: Comba columns with carry predicates) against Python integers, on random
+    and extreme 256-bit LOOSE representatives (values >= p, all ones, 2^256-38+-1, p, p+-1 ...)."""
+    P = 2**255 - 19
+    rng = np.random.default_rng(11)
+    edge = [0, 1, 2, 18, 19, 20, 37, 38, 39, P - 1, P, P + 1, 2 * P, 2 * P + 1, 2**255 - 1, 2**255, 2**255 + 18, 2**255 + 19, 2**256 - 39, 2**256 - 38,
+            2**256 - 37, 2**256 - 1, 2**256 - 2, 2**224 - 1, 2**32 - 1, 2**32, (2**256 - 1) // 3, 0xFFFFFFFF00000000FFFFFFFF00000000FFFFFFFF00000000FFFFFFFF00000000]
+    vals_a = [x for x in edge for _ in edge] + [int.from_bytes(rng.bytes(32), "little") for _ in range(4000)]
+    vals_b = [y for _ in edge for y in edge] + [int.from_bytes(rng.bytes(32), "little") for _ in range(4000)]
+    a = np.frombuffer(b"".join(x.to_bytes(32, "little") for x in vals_a), np.uint8).reshape(-1, 32)
+    b = np.frombuffer(b"".join(x.to_bytes(32, "little") for x in vals_b), np.uint8).reshape(-1, 32)
+    out = api.field_selftest(a, b)
+    for i, (x, y) in enumerate(zip(vals_a, vals_b)):
+        exp = [x * y % P, x * x % P, (x + y) % P, (x - y) % P, (x + y) * (x - y) % P, pow(x, P - 2, P)]
+        got = [int.from_bytes(out[i, k].tobytes(), "little") for k in range(6)]
+        assert got == exp, (i, hex(x), hex(y), [hex(g) for g in got], [hex(e) for e in exp])
+
+
 def test_commit_conversion_parity(api, oracle):
     rng = np.random.default_rng(0)
     v = np.concatenate([rng.uniform(-300, 300, 2000), [0.0, -0.0, 0.25, -1.5, 600.0, -600.0, 0.5 / 128, 1.5 / 128]]).astype(np.float32)
