@@ -18,7 +18,7 @@ extern "C" int rofl_set_option(rofl_ctx *c, const char *name, long value) {
     if (n == "use_rt") c->e.use_rt = value != 0;
     else if (n == "rt_unfold") c->e.rt_unfold = (int)std::max<long>(0, std::min<long>(8, value));
     else if (n == "groups") c->e.groups = (int)std::max<long>(1, std::min<long>((long)c->e.gstreams.size(), value));
-    else if (n == "tail_np") c->e.tail_np = (int)std::max<long>(0, std::min<long>(64, value));
+    else if (n == "tail_np") c->e.tail_np = (int)std::max<long>(0, std::min<long>(TAIL_MAX_F / 2, value));
     else return ROFL_ERR_ARGS;
     return ROFL_OK;
 }

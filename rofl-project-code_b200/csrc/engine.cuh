@@ -15,7 +15,7 @@
 #include <algorithm>
 
 enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE = 4, DOM_L2_VERIFY = 5, DOM_CRP = 6, DOM_RND_VEC = 7 };
-enum { PROF_FOLD = 0, PROF_MSM = 1, PROF_COMMIT = 2, PROF_SQUARE = 3, PROF_SLOTS = 8 };
+enum { PROF_FOLD = 0, PROF_MSM = 1, PROF_COMMIT = 2, PROF_SQUARE = 3, PROF_RTMSM = 4, PROF_TAIL = 5, PROF_SLOTS = 8 };
 
 struct gens_entry { int n = 0; int cap = 0; niels_st *G = nullptr, *H = nullptr;
                     int rt_cap = 0; niels_st *RTG = nullptr, *RTH = nullptr; };     // radix-256 tables (RT path), 512 KB per generator
@@ -152,9 +152,9 @@ static inline int rt_blocks(size_t T, int C) {
     return (int)std::max<size_t>(1, nb);
 }
 static inline void run_rt_msm(rofl_engine &e, cudaStream_t s, rt_msm_args a, int nb, uint32_t n_msm) {
-    void *tk = rt_prof_begin(PROF_MSM, s);
+    void *tk = rt_prof_begin(PROF_RTMSM, s);
     LAUNCH_COOP(k_rt_msm, dim3(nb, n_msm), dim3(128), s, a);
-    rt_prof_end(PROF_MSM, tk, s);
+    rt_prof_end(PROF_RTMSM, tk, s);
 }
 
 // ---- MSM front end ----------------------------------------------------------------------------------------------------------
@@ -319,7 +319,10 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     std::vector<sc_st> h_u2(C), h_uinv2(C); std::vector<int8_t> h_nafs(512 * (size_t)C);
     // RT path: the first r_unf rounds take L/R as table MSMs over the ORIGINAL generators (no generator folding), then one
     // catch-up fold builds G"/H" of length N >> r_unf directly from the tables
-    const int r_unf = rt ? std::min(e.rt_unfold, lgN) : 0;
+    // rounds with half-size <= tail_np run in the fused on-device tail kernel; `pre` rounds come before it
+    const size_t tail_np = (size_t)std::min(e.tail_np, TAIL_MAX_F / 2);
+    int pre = 0; while (pre < lgN && ((N / 2) >> pre) > tail_np) pre++;
+    const int r_unf = rt ? std::min({e.rt_unfold, lgN, pre}) : 0;
     const int nbU = rt ? rt_blocks(N, 2 * C) : 1;
     const uint32_t cstride = 1u << (r_unf > 0 ? r_unf : 0);
     std::vector<sc> cG((size_t)C * cstride), cH((size_t)C * cstride);
@@ -329,7 +332,28 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     const int nbQ = (int)std::min<size_t>(256, (N / 2 + 255) / 256);
     dev_buf d_partQ(sizeof(sc_st) * 2 * (size_t)C * nbQ, s);
     int round = 0;
+    bool tail_done = false;
     for (size_t np = N / 2; np >= 1; np /= 2, round++) {
+        if (round == pre) {          // np <= tail_np: every remaining round in one launch (kernels.cuh, k_ipp_tail)
+            const int rounds_left = lgN - round; const uint32_t ostride = 64 * (uint32_t)rounds_left + 64;
+            std::vector<sc_st> h_up(2 * (size_t)C);
+            for (int c = 0; c < C; c++) { sc_to_st(h_up[c], uprod[c]); sc_to_st(h_up[C + c], uinvprod[c]); }
+            dev_buf d_ts(sizeof(transcript) * (size_t)C, s), d_up(sizeof(sc_st) * 2 * (size_t)C, s), d_tail((size_t)ostride * C, s);
+            rt_h2d(d_ts.p, ts.data(), sizeof(transcript) * (size_t)C, s); rt_h2d(d_up.p, h_up.data(), sizeof(sc_st) * 2 * (size_t)C, s);
+            tail_args ta = {}; ta.Gn = round == 0 ? g.G : nullptr; ta.Hn = round == 0 ? g.H : nullptr;
+            ta.Gf = d_Gf.as<p3_st>(); ta.Hf = d_Hf.as<p3_st>(); ta.stride = (uint32_t)half;
+            ta.a = d_a.as<sc_st>(); ta.b = d_b.as<sc_st>(); ta.yinv = d_yinv.as<sc_st>(); ta.N = N;
+            ta.ts = d_ts.as<transcript>(); ta.w = d_w2.as<sc_st>(); ta.uprod = d_up.as<sc_st>(); ta.uinvprod = d_up.as<sc_st>() + C; ta.tabB = e.tabB;
+            ta.out = d_tail.as<uint8_t>(); ta.out_stride = ostride; ta.F = (uint32_t)(2 * np);
+            void *tk = rt_prof_begin(PROF_TAIL, s);
+            LAUNCH_COOP(k_ipp_tail, dim3(C), dim3(TAIL_THREADS), s, ta);
+            rt_prof_end(PROF_TAIL, tk, s);
+            std::vector<uint8_t> h_tail((size_t)ostride * C);
+            rt_d2h(h_tail.data(), d_tail.p, h_tail.size(), s); rt_sync(s);
+            for (int c = 0; c < C; c++) memcpy(h_proofs + plen * c + 224 + 64 * (size_t)round, &h_tail[(size_t)ostride * c], ostride);
+            tail_done = true;
+            break;
+        }
         const int nbI = (int)std::min<size_t>(256, (np + 255) / 256);
         const bool unfolded = round < r_unf;
         if (unfolded) {
@@ -411,6 +435,7 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             rt_prof_end(PROF_FOLD, tk, s);
         }
     }
+    if (tail_done) return;
     // ---- final a, b: a = a^ prod u_k, b = b^ prod u_k^-1
     std::vector<sc_st> h_ab(2 * (size_t)C);
     for (int c = 0; c < C; c++) { rt_d2h(&h_ab[2 * c], d_a.as<sc_st>() + (size_t)c * N, sizeof(sc_st), s); rt_d2h(&h_ab[2 * c + 1], d_b.as<sc_st>() + (size_t)c * N, sizeof(sc_st), s); }

@@ -46,6 +46,8 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
         rt_check(cudaSetDevice(device), "cudaSetDevice");
         cudaDeviceProp prop; rt_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
         if (prop.major < 10) throw std::runtime_error("rofl_b200 is built for sm_100a only");
+        // the point formulas call fe_mul / fe_sq as real functions: give every thread room for the deepest call chain
+        { size_t cur = 0; cudaDeviceGetLimit(&cur, cudaLimitStackSize); if (cur < 8192) rt_check(cudaDeviceSetLimit(cudaLimitStackSize, 8192), "cudaDeviceSetLimit(stack)"); }
         rofl_ctx *c = new rofl_ctx();
         c->e.device = device;
         rt_check(cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -57,6 +59,7 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
         if (const char *gv = getenv("ROFL_GROUPS")) c->e.groups = std::max(1, std::min(4, atoi(gv)));
         if (const char *gv = getenv("ROFL_RT")) c->e.use_rt = atoi(gv);                                   // 0 disables the generator tables
         if (const char *gv = getenv("ROFL_UNFOLD")) c->e.rt_unfold = std::max(0, std::min(6, atoi(gv)));   // unfolded IPP rounds (RT path)
+        if (const char *gv = getenv("ROFL_TAIL")) c->e.tail_np = std::max(0, std::min(TAIL_MAX_F / 2, atoi(gv)));    // 0 disables the fused IPP tail
         engine_init(c->e);
         *out = c;
         return ROFL_OK;

@@ -110,6 +110,28 @@ HD void sc_invert(sc &r, const sc &a) {
     }
     r = acc;
 }
+// a^-1 by the binary extended Euclid (variable time: only used on public Fiat-Shamir challenges); a canonical, non-zero.
+// ~750 shift / add / subtract steps on 8-word integers instead of the ~380 modular multiplications of sc_invert.
+HD void sc_raw_shr1(uint32_t a[8]) { for (int i = 0; i < 7; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31); a[7] >>= 1; }
+HD void sc_raw_add_l(uint32_t a[8]) { uint64_t c = 0; for (int i = 0; i < 8; i++) { c += (uint64_t)a[i] + SC_L_[i]; a[i] = (uint32_t)c; c >>= 32; } }
+HD bool sc_raw_sub(uint32_t a[8], const uint32_t b[8]) { int64_t bw = 0; for (int i = 0; i < 8; i++) { bw += (int64_t)a[i] - (int64_t)b[i]; a[i] = (uint32_t)bw; bw >>= 32; } return bw != 0; }
+HD bool sc_raw_is_one(const uint32_t a[8]) { uint32_t r = a[0] ^ 1; for (int i = 1; i < 8; i++) r |= a[i]; return r == 0; }
+HD void sc_invert_vartime(sc &r, const sc &a) {
+    if (sc_iszero(a)) { sc_0(r); return; }
+    uint32_t u[8], v[8], x1[8], x2[8];
+    for (int i = 0; i < 8; i++) { u[i] = a.v[i]; v[i] = SC_L_[i]; x1[i] = 0; x2[i] = 0; }
+    x1[0] = 1;
+    for (;;) {
+        if (sc_raw_is_one(u)) { for (int i = 0; i < 8; i++) r.v[i] = x1[i]; return; }
+        if (sc_raw_is_one(v)) { for (int i = 0; i < 8; i++) r.v[i] = x2[i]; return; }
+        while (!(u[0] & 1)) { sc_raw_shr1(u); if (x1[0] & 1) sc_raw_add_l(x1); sc_raw_shr1(x1); }       // x1 + l < 2^254
+        while (!(v[0] & 1)) { sc_raw_shr1(v); if (x2[0] & 1) sc_raw_add_l(x2); sc_raw_shr1(x2); }
+        bool ge = true;                                    // u >= v ?
+        for (int i = 7; i >= 0; i--) { if (u[i] != v[i]) { ge = u[i] > v[i]; break; } }
+        if (ge) { sc_raw_sub(u, v); if (sc_raw_sub(x1, x2)) sc_raw_add_l(x1); }
+        else { sc_raw_sub(v, u); if (sc_raw_sub(x2, x1)) sc_raw_add_l(x2); }
+    }
+}
 HD void sc_pow_u64(sc &r, const sc &a, uint64_t e) {
     sc acc, base = a; sc_from_u64(acc, 1);
     while (e) { if (e & 1) sc_mul(acc, acc, base); sc_mul(base, base, base); e >>= 1; }

@@ -22,6 +22,7 @@ EXPORT void hs_sc_add(uint8_t *o, const uint8_t *a, const uint8_t *b) { sc x, y,
 EXPORT void hs_sc_sub(uint8_t *o, const uint8_t *a, const uint8_t *b) { sc x, y, r; sc_frombytes(x, a); sc_frombytes(y, b); sc_sub(r, x, y); sc_tobytes(o, r); }
 EXPORT void hs_sc_wide(uint8_t *o, const uint8_t *a) { sc r; sc_from_bytes_wide(r, a); sc_tobytes(o, r); }
 EXPORT void hs_sc_invert(uint8_t *o, const uint8_t *a) { sc x, r; sc_frombytes(x, a); sc_invert(r, x); sc_tobytes(o, r); }
+EXPORT void hs_sc_invert_vartime(uint8_t *o, const uint8_t *a) { sc x, r; sc_frombytes(x, a); sc_invert_vartime(r, x); sc_tobytes(o, r); }
 EXPORT int hs_decompress_compress(uint8_t *o, const uint8_t *a) { ge_p3 p; bool ok = ge_decompress(p, a); if (ok) ge_compress(o, p); return ok; }
 EXPORT void hs_from_uniform(uint8_t *o, const uint8_t *a) { ge_p3 p; ge_from_uniform_bytes(p, a); ge_compress(o, p); }
 EXPORT int hs_point_add(uint8_t *o, const uint8_t *a, const uint8_t *b, int sub) {

@@ -125,3 +125,23 @@ def test_msm_window_widths(api, oracle, monkeypatch, c, slices, rt):
         assert api.range_verify(badp, cm, rngbits, seed) == 0
     finally:
         api.set_use_rt(1)
+
+
+@pytest.mark.parametrize("tail_np,rt,unfold", [(0, 1, 3), (0, 0, 3), (4, 1, 3), (4, 0, 3), (2, 1, 1), (1, 1, 2), (32, 1, 3), (8, 0, 0)])
+def test_ipp_tail_kernel_handover(api, oracle, tail_np, rt, unfold):
+    """The fused on-device tail (k_ipp_tail: transcript, challenge inversion and folds on the device, frozen generators)
+    takes over from the host-driven rounds at any round: from round 0, after the table catch-up, after ordinary folds."""
+    api.set_option("tail_np", tail_np); api.set_use_rt(rt); api.set_option("rt_unfold", unfold)
+    try:
+        rng = np.random.default_rng(tail_np * 7 + rt)
+        D, rngbits, P, nb = 7, 8, 2, 16            # 2 chunks x (m = 4, n = 8): N = 32, 5 rounds
+        mn, mx = oracle.clip_bounds(rngbits, nb, 7)
+        v = rng.uniform(mn, mx, D).astype(np.float32)
+        bl = oracle.rnd_scalar_vec(b"\x36" * 32, D)
+        seed = bytes([tail_np + 1] * 32)
+        rc_o, p_o, c_o = oracle.range_prove(v, bl, rngbits, P, nb, 7, seed)
+        rc, p, cm = api.range_prove(v, bl, rngbits, P, nb, 7, seed)
+        assert rc == rc_o == 0 and (cm == c_o).all() and (p == p_o).all()
+        assert api.range_verify(p, cm, rngbits, seed) == 1
+    finally:
+        api.set_option("tail_np", 32); api.set_use_rt(1); api.set_option("rt_unfold", 3)

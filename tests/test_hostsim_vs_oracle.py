@@ -61,6 +61,10 @@ def test_scalars(hs, oracle):
         assert call(hs, "hs_sc_wide", 32, w)[1] == oracle.sc_reduce_wide(w)
     for a in vals[1:20]:
         assert call(hs, "hs_sc_invert", 32, a)[1] == oracle.sc_invert(a)
+    for a in vals[1:6] + vals[6:] + [(2**k).to_bytes(32, "little") for k in (1, 31, 32, 64, 251)]:      # binary-Euclid inverse (Fiat-Shamir challenges)
+        ai = int.from_bytes(a, "little")
+        assert int.from_bytes(call(hs, "hs_sc_invert_vartime", 32, a)[1], "little") == pow(ai, L - 2, L)
+    assert call(hs, "hs_sc_invert_vartime", 32, bytes(32))[1] == bytes(32)
 
 
 def test_ristretto(hs, oracle):
