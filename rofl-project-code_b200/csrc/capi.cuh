@@ -16,8 +16,13 @@ extern "C" int rofl_set_option(rofl_ctx *c, const char *name, long value) {
     std::lock_guard<std::mutex> lk(c->e.mu);
     std::string n(name);
     if (n == "use_rt") c->e.use_rt = value != 0;
-    else if (n == "rt_unfold") c->e.rt_unfold = (int)std::max<long>(0, std::min<long>(8, value));
+    else if (n == "rt_unfold") c->e.rt_unfold = (int)std::max<long>(0, std::min<long>(6, value));
     else if (n == "groups") c->e.groups = (int)std::max<long>(1, std::min<long>((long)c->e.gstreams.size(), value));
+    else if (n == "rt_bits") {                                                                       // drops the cached tables: they are rebuilt at the new radix on next use
+        c->e.rt_bits = (int)std::max<long>(8, std::min<long>(10, value));
+        rt_sync(c->e.stream);
+        for (auto &g : c->e.gens) { rt_free(g.second.RTG, c->e.stream); rt_free(g.second.RTH, c->e.stream); g.second.RTG = g.second.RTH = nullptr; g.second.rt_cap = 0; }
+    }
     else if (n == "tail_np") c->e.tail_np = (int)std::max<long>(0, std::min<long>(TAIL_MAX_F / 2, value));
     else return ROFL_ERR_ARGS;
     return ROFL_OK;

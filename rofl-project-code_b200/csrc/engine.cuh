@@ -18,7 +18,7 @@ enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE =
 enum { PROF_FOLD = 0, PROF_MSM = 1, PROF_COMMIT = 2, PROF_SQUARE = 3, PROF_RTMSM = 4, PROF_TAIL = 5, PROF_SLOTS = 8 };
 
 struct gens_entry { int n = 0; int cap = 0; niels_st *G = nullptr, *H = nullptr;
-                    int rt_cap = 0; niels_st *RTG = nullptr, *RTH = nullptr; };     // radix-256 tables (RT path), 512 KB per generator
+                    int rt_cap = 0, rt_c = 8; niels_st *RTG = nullptr, *RTH = nullptr; };     // radix-2^rt_c tables (RT path)
 struct bsgs_entry { unsigned long long *keys = nullptr; uint32_t *vals = nullptr; uint32_t cap = 0; uint64_t size = 0; };
 struct rofl_engine {
     int device = 0;
@@ -32,8 +32,9 @@ struct rofl_engine {
     int groups = 1;                       // chunk groups proved / verified concurrently on separate streams (hides per-round latency)
     std::vector<cudaStream_t> gstreams;   // gstreams[0] == stream
     int use_rt = 1;                       // 0: never build generator tables (generic Pippenger / fold path only)
-    int rt_unfold = 3;                    // IPP rounds computed over the original generators before the catch-up fold
+    int rt_unfold = 4;                    // IPP rounds computed over the original generators before the catch-up fold
     int tail_np = 32;                     // IPP rounds with half-size <= tail_np run in the fused on-device tail kernel (0 = off)
+    int rt_bits = 10;                     // widest generator-table radix to try (8..10)
     double rt_mem_frac = 0.45;            // tables may take this fraction of the free device memory
 };
 
@@ -71,7 +72,7 @@ static inline void sc_batch_invert(std::vector<sc> &v) {
     size_t n = v.size(); if (!n) return;
     std::vector<sc> pre(n); sc acc; sc_from_u64(acc, 1);
     for (size_t i = 0; i < n; i++) { pre[i] = acc; sc_mul(acc, acc, v[i]); }
-    sc inv; sc_invert(inv, acc);
+    sc inv; sc_invert_vartime(inv, acc);           // public Fiat-Shamir challenges only
     for (size_t i = n; i-- > 0;) { sc t; sc_mul(t, inv, pre[i]); sc_mul(inv, inv, v[i]); v[i] = t; }
 }
 static inline void ts_challenge_scalar(transcript &t, const char *label, sc &out) { uint8_t b[64]; transcript_challenge(t, label, b, 64); sc_from_bytes_wide(out, b); }
@@ -122,25 +123,35 @@ static inline gens_entry &engine_gens(rofl_engine &e, int n, int m) {
     return g;
 }
 
-// radix-256 tables for the first m parties of the n-bit generators; returns false when they do not fit in memory
+// radix-2^c generator tables for the first m parties of the n-bit generators (c = 10, 9 or 8: the widest that fits the memory
+// budget; wider = fewer additions per term); returns false when not even c = 8 fits
 static inline bool engine_rt(rofl_engine &e, gens_entry &g, int n, int m, rt_tables &out) {
     if (!e.use_rt) return false;
-    if (g.rt_cap >= m) { out.G = g.RTG; out.H = g.RTH; return true; }
+    auto fill = [&](rt_tables &t, int c) { t.c = c; t.nw = msm_nw(c); t.B = 1 << (c - 1); msm_recode_const(t.K, c); };
+    if (g.rt_cap >= m) { out.G = g.RTG; out.H = g.RTH; fill(out, g.rt_c); return true; }
     cudaStream_t s = e.stream;
-    const size_t cnt = (size_t)n * m, bytes = cnt * RT_W * RT_E * sizeof(niels_st);
-    size_t have = rt_free_mem() + (g.RTG ? 2 * (size_t)n * g.rt_cap * RT_W * RT_E * sizeof(niels_st) : 0);
-    if ((double)(2 * bytes + 2 * cnt * RT_W * sizeof(p3_st)) > e.rt_mem_frac * (double)have) return false;
-    rt_sync(s); rt_free(g.RTG, s); rt_free(g.RTH, s); g.RTG = g.RTH = nullptr; g.rt_cap = 0;
+    const size_t cnt = (size_t)n * m;
+    rt_sync(s); rt_free(g.RTG, s); rt_free(g.RTH, s); g.RTG = g.RTH = nullptr; g.rt_cap = 0; rt_sync(s);
+    const size_t have = rt_free_mem();
+    int c = std::max(8, std::min(10, e.rt_bits));
+    for (; c >= 8; c--) {
+        const size_t nw = msm_nw(c), B = (size_t)1 << (c - 1);
+        if ((double)(2 * cnt * nw * B * sizeof(niels_st) + cnt * nw * sizeof(p3_st)) <= e.rt_mem_frac * (double)have) break;
+    }
+    if (c < 8) return false;
+    rt_tables t; fill(t, c);
+    const size_t bytes = cnt * rt_row_entries(t) * sizeof(niels_st);
     niels_st *RTG = (niels_st *)rt_malloc(bytes, s), *RTH = (niels_st *)rt_malloc(bytes, s);
     {
-        dev_buf P(cnt * RT_W * sizeof(p3_st), s);
+        dev_buf P(cnt * t.nw * sizeof(p3_st), s);
+        const size_t rows = cnt * t.nw, thr = rows * (t.B / 16);
         for (int which = 0; which < 2; which++) {
-            LAUNCH(k_rt_shifts, dim3((unsigned)((cnt + 127) / 128)), dim3(128), s, P.as<p3_st>(), which ? g.H : g.G, (uint32_t)cnt);
-            LAUNCH(k_rt_rows, dim3((unsigned)((cnt * RT_W * 8 + 127) / 128)), dim3(128), s, which ? RTH : RTG, P.as<p3_st>(), cnt * RT_W);
+            LAUNCH(k_rt_shifts, dim3((unsigned)((cnt + 127) / 128)), dim3(128), s, P.as<p3_st>(), which ? g.H : g.G, (uint32_t)cnt, t.c, t.nw);
+            LAUNCH(k_rt_rows, dim3((unsigned)((thr + 127) / 128)), dim3(128), s, which ? RTH : RTG, P.as<p3_st>(), rows, t.B);
         }
         rt_sync(s);
     }
-    g.RTG = RTG; g.RTH = RTH; g.rt_cap = m; out.G = RTG; out.H = RTH;
+    g.RTG = RTG; g.RTH = RTH; g.rt_cap = m; g.rt_c = c; t.G = RTG; t.H = RTH; out = t;
     return true;
 }
 // blocks per msm for the direct table MSM: whole waves of 148 SMs x 4 resident blocks, >= 4 terms per thread when possible
@@ -261,7 +272,15 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     // ---- polynomials
     const int nbP = (int)std::min<size_t>(256, (N + 255) / 256);
     dev_buf d_a(sizeof(sc_st) * NT, s), d_b(sizeof(sc_st) * NT, s), d_part(sizeof(sc_st) * 3 * (size_t)C * nbP, s), d_tsum(sizeof(sc_st) * 3 * C, s);
-    LAUNCH_COOP(k_poly, dim3(nbP, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_part.as<sc_st>(), d_vals, d_ypow2.as<sc_st>(), d_zpow2.as<sc_st>(), n, m);
+    // split power tables for y^k, y^-k (k < N) and z^j (j < m)
+    const int lgm = ilog2_sz((size_t)m);
+    pow_tab ytab = {nullptr, lgN / 2, lgN - lgN / 2}, yitab = ytab, ztab = {nullptr, lgm / 2, lgm - lgm / 2};
+    dev_buf d_ptab(sizeof(sc_st) * (size_t)C * (2 * pow_tab_size(ytab) + pow_tab_size(ztab)), s);
+    ytab.tab = d_ptab.as<sc_st>(); yitab.tab = ytab.tab + (size_t)C * pow_tab_size(ytab); ztab.tab = yitab.tab + (size_t)C * pow_tab_size(yitab);
+    LAUNCH(k_pow_tables, dim3((pow_tab_size(ytab) + 255) / 256, C), dim3(256), s, (sc_st *)ytab.tab, d_ypow2.as<sc_st>(), ytab.L, ytab.H);
+    LAUNCH(k_pow_tables, dim3((pow_tab_size(yitab) + 255) / 256, C), dim3(256), s, (sc_st *)yitab.tab, d_yinvpow2.as<sc_st>(), yitab.L, yitab.H);
+    LAUNCH(k_pow_tables, dim3((pow_tab_size(ztab) + 255) / 256, C), dim3(256), s, (sc_st *)ztab.tab, d_zpow2.as<sc_st>(), ztab.L, ztab.H);
+    LAUNCH_COOP(k_poly, dim3(nbP, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_part.as<sc_st>(), d_vals, ytab, ztab, d_zpow2.as<sc_st>(), n, m);
     LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_tsum.as<sc_st>(), d_part.as<sc_st>(), nbP, 3);
     LAUNCH_COOP(k_party_sums, dim3(C), dim3(256), s, d_sums.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, d_z.as<sc_st>(), n, m, 1);
     std::vector<sc_st> h_tsum(3 * (size_t)C), h_sums(5 * (size_t)C);
@@ -306,7 +325,7 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     });
     dev_buf d_x(sizeof(sc_st) * C, s), d_w2(sizeof(sc_st) * 2 * C, s), d_yinv(sizeof(sc_st) * NT, s);
     rt_h2d(d_x.p, h_x.data(), sizeof(sc_st) * C, s); rt_h2d(d_w2.p, h_w2.data(), sizeof(sc_st) * 2 * C, s);
-    LAUNCH(k_lr, dim3((unsigned)((NT + 255) / 256)), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_yinv.as<sc_st>(), d_x.as<sc_st>(), d_yinvpow2.as<sc_st>(), N, NT);
+    LAUNCH(k_lr, dim3((unsigned)((NT + 255) / 256)), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_yinv.as<sc_st>(), d_x.as<sc_st>(), yitab, N, NT);
     // ---- inner product argument
     const size_t half = N / 2 ? N / 2 : 1;
     dev_buf d_Gf(sizeof(p3_st) * half * C, s), d_Hf(sizeof(p3_st) * half * C, s);
@@ -328,7 +347,7 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     std::vector<sc> cG((size_t)C * cstride), cH((size_t)C * cstride);
     std::vector<sc_st> h_cGH(2 * (size_t)C * cstride);
     for (int c = 0; c < C; c++) { sc_from_u64(cG[(size_t)c * cstride], 1); sc_from_u64(cH[(size_t)c * cstride], 1); }
-    dev_buf d_cGH(sizeof(sc_st) * 2 * (size_t)C * cstride, s), d_partU(sizeof(p3_st) * 2 * (size_t)C * nbU, s), d_digs(sizeof(int16_t) * 2 * (size_t)C * cstride * 32, s);
+    dev_buf d_cGH(sizeof(sc_st) * 2 * (size_t)C * cstride, s), d_partU(sizeof(p3_st) * 2 * (size_t)C * nbU, s), d_digs(sizeof(int16_t) * 2 * (size_t)C * cstride * RT_MAXW, s);
     const int nbQ = (int)std::min<size_t>(256, (N / 2 + 255) / 256);
     dev_buf d_partQ(sizeof(sc_st) * 2 * (size_t)C * nbQ, s);
     int round = 0;
@@ -344,6 +363,7 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             ta.Gf = d_Gf.as<p3_st>(); ta.Hf = d_Hf.as<p3_st>(); ta.stride = (uint32_t)half;
             ta.a = d_a.as<sc_st>(); ta.b = d_b.as<sc_st>(); ta.yinv = d_yinv.as<sc_st>(); ta.N = N;
             ta.ts = d_ts.as<transcript>(); ta.w = d_w2.as<sc_st>(); ta.uprod = d_up.as<sc_st>(); ta.uinvprod = d_up.as<sc_st>() + C; ta.tabB = e.tabB;
+            dev_buf d_tscr(sizeof(p3_st) * 2 * TAIL_Q * TAIL_MAX_F * (size_t)C, s); ta.scratch = d_tscr.as<p3_st>();
             ta.out = d_tail.as<uint8_t>(); ta.out_stride = ostride; ta.F = (uint32_t)(2 * np);
             void *tk = rt_prof_begin(PROF_TAIL, s);
             LAUNCH_COOP(k_ipp_tail, dim3(C), dim3(TAIL_THREADS), s, ta);
@@ -415,10 +435,10 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         if (unfolded) {
             if (round + 1 == r_unf && np >= 2) {          // catch-up: G", H" of length np straight from the tables
                 const uint32_t nblk = 1u << r_unf;
-                std::vector<int16_t> h_digs(2 * (size_t)C * nblk * 32);
+                std::vector<int16_t> h_digs(2 * (size_t)C * nblk * RT_MAXW);
                 for (int c = 0; c < C; c++) for (uint32_t t = 0; t < nblk; t++) {
-                    rt_digits(&h_digs[(((size_t)c * 2 + 0) * nblk + t) * 32], cG[(size_t)c * cstride + t]);
-                    rt_digits(&h_digs[(((size_t)c * 2 + 1) * nblk + t) * 32], cH[(size_t)c * cstride + t]);
+                    rt_digits(&h_digs[(((size_t)c * 2 + 0) * nblk + t) * RT_MAXW], cG[(size_t)c * cstride + t], *rt);
+                    rt_digits(&h_digs[(((size_t)c * 2 + 1) * nblk + t) * RT_MAXW], cH[(size_t)c * cstride + t], *rt);
                 }
                 rt_h2d(d_digs.p, h_digs.data(), sizeof(int16_t) * h_digs.size(), s);
                 catchup_args ca = {}; ca.rt = *rt; ca.Gf = d_Gf.as<p3_st>(); ca.Hf = d_Hf.as<p3_st>(); ca.digits = d_digs.as<int16_t>(); ca.nr = (uint32_t)np; ca.nblk = nblk; ca.stride = (uint32_t)half;
@@ -602,8 +622,8 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     rt_h2d(d_yinvpow2.p, h_yinvpow2.data(), sizeof(sc_st) * 32 * C, s); rt_h2d(d_zpow2.p, h_zpow2.data(), sizeof(sc_st) * 32 * C, s);
     rt_h2d(d_sp32.p, h_smallpts.data(), h_smallpts.size(), s);
     rt_memset(d_bad.p, 0, sizeof(int) * C, s);
-    for (int c = 0; c < C; c++) rt_h2d(d_var.as<sc_st>() + (size_t)c * vstride + m, &h_small[(size_t)c * nsmall], sizeof(sc_st) * nsmall, s);
-    LAUNCH(k_verify_tables, dim3((vt.total + m + 255) / 256, C), dim3(256), s, d_tab.as<sc_st>(), vt, d_var.as<sc_st>(), vstride, d_chal.as<sc_st>(), chs, d_yinvpow2.as<sc_st>(), d_zpow2.as<sc_st>(), m);
+    rt_h2d(d_var.as<sc_st>() + (size_t)C * m, h_small.data(), sizeof(sc_st) * h_small.size(), s);
+    LAUNCH(k_verify_tables, dim3((vt.total + m + 255) / 256, C), dim3(256), s, d_tab.as<sc_st>(), vt, d_var.as<sc_st>(), (uint32_t)m, d_chal.as<sc_st>(), chs, d_yinvpow2.as<sc_st>(), d_zpow2.as<sc_st>(), m);
     LAUNCH(k_verify_scalars, dim3((unsigned)((N + 255) / 256)), dim3(256), s, d_gh.as<sc_st>(), d_tab.as<sc_st>(), vt, d_chal.as<sc_st>(), chs, n, C);
     LAUNCH(k_decompress, dim3((unsigned)(((size_t)C * nsmall + 127) / 128)), dim3(128), s, d_sp.as<p3_st>(), (uint8_t *)nullptr, d_sp32.as<uint8_t>(), (size_t)C * nsmall, (size_t)C * nsmall, (const p3_st *)nullptr, d_bad.as<int>(), (size_t)nsmall);
     // fixed generators: one 2N-term MSM (radix-256 tables when they exist, bucket MSM otherwise) -> d_fix
@@ -626,14 +646,15 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             run_finalize(s, f);
         }
     }
-    // commitments and proof points: one MSM per chunk, the per-chunk window sums are added up like slices
+    // commitments and proof points of ALL chunks: one sliced MSM over C*m + C*nsmall terms (scalars laid out the same way)
     {
-        msm_plan pl = msm_plan_for(vstride, C); pl.slices = 1; pl.slice_len = vstride;
-        dev_buf d_winV(sizeof(p3_st) * pl.out_count(C), s);
-        msm_args a = {}; a.v[0].scalars = d_var.as<sc_st>(); a.split = (uint32_t)C; a.T = vstride; a.scalar_stride = vstride; a.nseg = 2; a.out = d_winV.as<p3_st>();
-        a.v[0].seg[0] = mk_seg(d_Vp3, (uint32_t)m, (uint32_t)m, 1); a.v[0].seg[1] = mk_seg(d_sp.p, (uint32_t)nsmall, (uint32_t)nsmall, 1);
-        run_msm(e, s, a, pl, C);
-        finalize_args f = {}; f.windows = d_winV.as<p3_st>(); f.c = pl.c; f.nw = pl.nw; f.slices = (uint32_t)C;
+        const uint32_t TV = (uint32_t)((size_t)C * m + (size_t)C * nsmall);
+        const msm_plan pl = msm_plan_for(TV, 1);
+        dev_buf d_winV(sizeof(p3_st) * pl.out_count(1), s);
+        msm_args a = {}; a.v[0].scalars = d_var.as<sc_st>(); a.split = 1; a.T = TV; a.scalar_stride = TV; a.nseg = 2; a.out = d_winV.as<p3_st>();
+        a.v[0].seg[0] = mk_seg(d_Vp3, (uint32_t)((size_t)C * m), 0, 1); a.v[0].seg[1] = mk_seg(d_sp.p, (uint32_t)((size_t)C * nsmall), 0, 1);
+        run_msm(e, s, a, pl, 1);
+        finalize_args f = {}; fin_windows(f, d_winV.as<p3_st>(), pl);
         f.partial = d_fix.as<p3_st>(); f.npartial = 1; f.tabB = e.tabB; f.tabH = e.tabH; f.is_id = d_id.as<int>(); f.count = 1;
         run_finalize(s, f);
     }

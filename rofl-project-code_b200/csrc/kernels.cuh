@@ -319,18 +319,18 @@ HD int msm_digit(const uint32_t xk[9], int w, int c) {
     uint64_t v = (uint64_t)xk[i] | ((uint64_t)(i + 1 < 9 ? xk[i + 1] : 0) << 32);
     return (int)((v >> sh) & ((1u << c) - 1)) - ((1 << (c - 1)) - 1);
 }
+// locate the record of term t first, THEN add: lanes whose terms sit in different segments of the same kind must run ONE
+// addition together (an add inside the segment loop made them take turns and halved the SIMT efficiency)
 HD void msm_add_term(ge_p3 &acc, const msm_var &v, int nseg, uint32_t idx, uint32_t t, bool neg) {
-    uint32_t start = 0;
+    uint32_t start = 0; const void *base = nullptr; size_t rec = 0; int kind = -1;
     for (int s = 0; s < nseg; s++) {
         const msm_seg &g = v.seg[s];
-        if (t < start + g.count) {
-            size_t rec = (size_t)idx * g.stride + (t - start);
-            if (g.kind == 0) acc_add_niels(acc, (const niels_st *)g.base + rec, neg);
-            else acc_add_p3(acc, (const p3_st *)g.base + rec, neg);
-            return;
-        }
+        const bool here = kind < 0 && t < start + g.count;
+        if (here) { base = g.base; rec = (size_t)idx * g.stride + (t - start); kind = g.kind; }
         start += g.count;
     }
+    if (kind == 0) acc_add_niels(acc, (const niels_st *)base + rec, neg);
+    else if (kind == 1) acc_add_p3(acc, (const p3_st *)base + rec, neg);
 }
 #ifdef KG_MSM
 KERNEL void LB(MSM_THREADS, 4) k_msm(msm_args a) {
@@ -457,13 +457,30 @@ KLAUNCH(k_finalize, true, (finalize_args a), (a))
 //   t1' = <l0+l1, r0+r1>.   ypow2[c*32+b] = y^(2^b), zpow2 likewise.  r1 overwrites sR.
 //   partial[(c*gridDim.x + blockIdx.x)*3 + q]
 // ===================================================================================================================
+// split power tables: b^e = lo[e & (2^L - 1)] * hi[e >> L] -- one multiplication per position instead of a square-and-multiply.
+//   tab[c*(2^L + 2^H) + ..] = lo[2^L] | hi[2^H] for base b_c given as pow2[c*32 + i] = b_c^(2^i)
+struct pow_tab { const sc_st *tab; int L, H; };
+HD uint32_t pow_tab_size(const pow_tab &t) { return (1u << t.L) + (1u << t.H); }
 HD void sc_pow_tab(sc &r, const sc_st *pow2, uint64_t e) {
     sc_from_u64(r, 1);
     for (int b = 0; e; b++, e >>= 1) if (e & 1) { sc t; ld_sc(t, pow2 + b); sc_mul(r, r, t); }
 }
+HD void pow_tab_get(sc &r, const pow_tab &t, int c, uint64_t e) {
+    const sc_st *b = t.tab + (size_t)c * pow_tab_size(t);
+    sc lo, hi; ld_sc(lo, b + (e & ((1u << t.L) - 1))); ld_sc(hi, b + (1u << t.L) + (e >> t.L)); sc_mul(r, lo, hi);
+}
+#ifdef KG_SCALAR
+KERNEL void LB(256, 1) k_pow_tables(sc_st *tab, const sc_st *pow2, int L, int H) {
+    const int c = blockIdx.y; const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x, nlo = 1u << L, n = nlo + (1u << H);
+    if (e >= n) return;
+    sc r; sc_pow_tab(r, pow2 + 32 * c, e < nlo ? (uint64_t)e : (uint64_t)(e - nlo) << L);
+    st_sc(tab + (size_t)c * n + e, r);
+}
+KLAUNCH(k_pow_tables, false, (sc_st *tab, const sc_st *pow2, int L, int H), (tab, pow2, L, H))
+#endif
 #ifdef KG_SCALAR
 KERNEL void LB(256, 1) k_poly(sc_st *l0, sc_st *r0, sc_st *sLR, sc_st *partial, const uint64_t *vals,
-                             const sc_st *ypow2, const sc_st *zpow2, int n, int m) {
+                             pow_tab ytab, pow_tab ztab, const sc_st *zpow2, int n, int m) {
     __shared__ sc_st buf[256];
     int c = blockIdx.y, tid = threadIdx.x;
     size_t N = (size_t)n * m;
@@ -472,8 +489,8 @@ KERNEL void LB(256, 1) k_poly(sc_st *l0, sc_st *r0, sc_st *sLR, sc_st *partial, 
     for (size_t k = (size_t)blockIdx.x * blockDim.x + tid; k < N; k += (size_t)gridDim.x * blockDim.x) {
         size_t j = k / n; int i = (int)(k % n); size_t gp = (size_t)c * N + k;
         sc ey, ozz, aL, a, b, rr0, rr1, ll0, ll1, e2;
-        sc_pow_tab(ey, ypow2 + 32 * c, k);
-        sc_pow_tab(ozz, zpow2 + 32 * c, j); sc_mul(ozz, ozz, zz);
+        pow_tab_get(ey, ytab, c, k);
+        pow_tab_get(ozz, ztab, c, j); sc_mul(ozz, ozz, zz);
         sc_from_u64(aL, (vals[(size_t)c * m + j] >> i) & 1);
         sc_sub(ll0, aL, z);
         sc_sub(a, aL, one); sc_add(a, a, z); sc_mul(rr0, ey, a);
@@ -489,7 +506,7 @@ KERNEL void LB(256, 1) k_poly(sc_st *l0, sc_st *r0, sc_st *sLR, sc_st *partial, 
     block_sum_sc(t0, buf, tid, blockDim.x); block_sum_sc(t1, buf, tid, blockDim.x); block_sum_sc(t2, buf, tid, blockDim.x);
     if (tid == 0) { sc_st *o = partial + ((size_t)c * gridDim.x + blockIdx.x) * 3; st_sc(o, t0); st_sc(o + 1, t1); st_sc(o + 2, t2); }
 }
-KLAUNCH(k_poly, true, (sc_st *l0, sc_st *r0, sc_st *sLR, sc_st *partial, const uint64_t *vals, const sc_st *ypow2, const sc_st *zpow2, int n, int m), (l0, r0, sLR, partial, vals, ypow2, zpow2, n, m))
+KLAUNCH(k_poly, true, (sc_st *l0, sc_st *r0, sc_st *sLR, sc_st *partial, const uint64_t *vals, pow_tab ytab, pow_tab ztab, const sc_st *zpow2, int n, int m), (l0, r0, sLR, partial, vals, ytab, ztab, zpow2, n, m))
 #endif
 // out[s*C + c] = sum_{b < cnt} in[(c*cnt + b)*q + s]   (second stage of the block partial sums; C = gridDim.x)
 #ifdef KG_SCALAR
@@ -507,16 +524,16 @@ KLAUNCH(k_sc_sum, true, (sc_st *out, const sc_st *in, int cnt, int q), (out, in,
 #endif
 // l = l0 + x sL (into l0), r = r0 + x r1 (into r0), yinv[k] = y^-k     
 #ifdef KG_SCALAR
-KERNEL void LB(256, 2) k_lr(sc_st *l0, sc_st *r0, const sc_st *sLR, sc_st *yinv, const sc_st *x, const sc_st *yinvpow2, size_t N, size_t total) {
+KERNEL void LB(256, 2) k_lr(sc_st *l0, sc_st *r0, const sc_st *sLR, sc_st *yinv, const sc_st *x, pow_tab yitab, size_t N, size_t total) {
     size_t gp = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gp >= total) return;
     size_t c = gp / N, k = gp % N;
     sc xc, a, b; ld_sc(xc, x + c);
     ld_sc(a, sLR + c * 2 * N + k); sc_mul(a, a, xc); ld_sc(b, l0 + gp); sc_add(a, a, b); st_sc(l0 + gp, a);
     ld_sc(a, sLR + c * 2 * N + N + k); sc_mul(a, a, xc); ld_sc(b, r0 + gp); sc_add(a, a, b); st_sc(r0 + gp, a);
-    sc_pow_tab(a, yinvpow2 + 32 * c, k); st_sc(yinv + gp, a);
+    pow_tab_get(a, yitab, (int)c, k); st_sc(yinv + gp, a);
 }
-KLAUNCH(k_lr, false, (sc_st *l0, sc_st *r0, const sc_st *sLR, sc_st *yinv, const sc_st *x, const sc_st *yinvpow2, size_t N, size_t total), (l0, r0, sLR, yinv, x, yinvpow2, N, total))
+KLAUNCH(k_lr, false, (sc_st *l0, sc_st *r0, const sc_st *sLR, sc_st *yinv, const sc_st *x, pow_tab yitab, size_t N, size_t total), (l0, r0, sLR, yinv, x, yitab, N, total))
 #endif
 
 // ===================================================================================================================
@@ -602,7 +619,8 @@ KLAUNCH(k_ipp_fold_points, true, (fold_args a), (a))
 //   out[c]: rounds x (L | R) compressed, then a | b (the proof's last two scalars)
 // ===================================================================================================================
 #define TAIL_MAX_F 64
-#define TAIL_THREADS (2 * TAIL_MAX_F + 32)
+#define TAIL_Q 4                                              // threads per frozen point: each owns one 64-bit quarter of the scalar
+#define TAIL_THREADS (2 * TAIL_MAX_F * TAIL_Q + 32)
 struct tail_args {
     const niels_st *Gn, *Hn;                 // non-null: the tail starts at round 0 on the shared generators
     const p3_st *Gf, *Hf; uint32_t stride;   // folded generators [C][stride] (first F entries live)
@@ -610,27 +628,47 @@ struct tail_args {
     const transcript *ts;                    // [C] transcript states after the previous challenge
     const sc_st *w, *uprod, *uinvprod;       // [C] w; products of the earlier u_k and u_k^-1
     const niels_st *tabB;
+    p3_st *scratch;                          // [C][2 * TAIL_Q * TAIL_MAX_F] partial products (L half | R half)
     uint8_t *out; uint32_t out_stride;
     uint32_t F;
 };
+// r = sum_{i<16} e[i] 16^i * P  (one 64-bit quarter of a signed radix-16 scalar), table = 1P..8P
+HD void ge_scalarmult_r16_quarter(ge_p3 &r, const int8_t *e, const ge_tab8 &tp) {
+    ge_p3_0(r);
+    for (int i = 15; i >= 0; i--) {
+        if (i != 15) {
+            ge_p2 q; ge_p1p1 t;
+            ge_dbl_p1p1(t, r.X, r.Y, r.Z); ge_dbl_fix(t); ge_p1p1_to_p2(q, t);
+            ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); ge_p1p1_to_p2(q, t);
+            ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); ge_p1p1_to_p2(q, t);
+            ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); ge_p1p1_to_p3(r, t);
+        }
+        const int d = e[i];
+        if (d != 0) ge_add_cached_signed(r, r, tp.t[(d > 0 ? d : -d) - 1], d < 0);
+    }
+}
 #ifdef KG_FOLD
 KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
     __shared__ sc_st sa[TAIL_MAX_F], sb[TAIL_MAX_F], sy[TAIL_MAX_F], scg[TAIL_MAX_F], sch[TAIL_MAX_F], red[64], sfac[3];
-    __shared__ p3_st pts[2 * TAIL_MAX_F], ptB[2];
+    __shared__ p3_st ptB[2];
     const int c = blockIdx.x, tid = threadIdx.x;
-    const uint32_t F = a.F;
-    const bool pt_thread = (uint32_t)tid < 2 * F, isH = (uint32_t)tid >= F;
-    const uint32_t j = isH ? tid - F : tid;
+    const uint32_t F = a.F, NP = 2 * F;                                // NP frozen points: G" then H"
+    const bool pt_thread = (uint32_t)tid < TAIL_Q * NP;
+    const uint32_t q = (uint32_t)tid / NP, p = (uint32_t)tid % NP;     // quarter (uniform per warp when NP >= 32), point
+    const bool isH = p >= F; const uint32_t j = isH ? p - F : p;
     const int tB = TAIL_THREADS - 32;                                  // lanes 0 / 1 of the last warp: the c_L w B and c_R w B terms
+    p3_st *pts = a.scratch + (size_t)c * 2 * TAIL_Q * TAIL_MAX_F;      // L products [0, TAIL_Q F), R products [TAIL_Q F, 2 TAIL_Q F)
+    const uint32_t half = TAIL_Q * F;
     for (uint32_t i = tid; i < F; i += TAIL_THREADS) {
         sa[i] = a.a[(size_t)c * a.N + i]; sb[i] = a.b[(size_t)c * a.N + i]; sy[i] = a.yinv[(size_t)c * a.N + i];
     }
     if (tid == 0) { sc one; sc_from_u64(one, 1); st_sc(scg, one); st_sc(sch, one); }
     ge_tab8 tb;
-    if (pt_thread) {
+    if (pt_thread) {                                                   // table of 2^(64 q) * P_p
         ge_p3 P;
         if (a.Gn) { ge_niels n; ld_niels(n, (isH ? a.Hn : a.Gn) + j); ge_niels_to_p3(P, n); }
         else ld_p3(P, (isH ? a.Hf : a.Gf) + (size_t)c * a.stride + j);
+        for (uint32_t k = 0; k < 64 * q; k++) ge_p3_dbl(P, P);
         ge_tab8_build(tb, P);
     }
     transcript t; sc up, uip, wc;
@@ -657,19 +695,21 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
             sc s, x; bool toL;
             if (!isH) { toL = h == 1; ld_sc(s, toL ? sa + i : sa + np + i); ld_sc(x, scg + tt); sc_mul(s, s, x); }
             else { toL = h == 0; ld_sc(s, toL ? sb + np + i : sb + i); ld_sc(x, toL ? sy + i : sy + np + i); sc_mul(s, s, x); ld_sc(x, sch + tt); sc_mul(s, s, x); }
-            ge_p3 r; ge_double_scalarmult_r16(r, s, tb, nullptr, nullptr);
-            st_p3(pts + (toL ? 0 : F) + (isH ? F / 2 : 0) + tt * np + i, r);
+            int8_t e[64]; sc_radix16(e, s);
+            ge_p3 r; ge_scalarmult_r16_quarter(r, e + 16 * q, tb);
+            st_p3(pts + (toL ? 0 : half) + q * F + (isH ? F / 2 : 0) + tt * np + i, r);
         } else if (tid == tB || tid == tB + 1) {
             sc s; ld_sc(s, red + 32 * (tid - tB)); sc_mul(s, s, wc);
             ge_p3 r; ge_p3_0(r); fb_mul_acc(r, a.tabB, s, 32);
             st_p3(ptB + (tid - tB), r);
         }
         __syncthreads();
-        for (uint32_t s2 = F >> 1; s2 > 0; s2 >>= 1) {
-            if (pt_thread && ((uint32_t)tid & (F - 1)) < s2) { ge_p3 x, y; ld_p3(x, pts + tid); ld_p3(y, pts + tid + s2); ge_add(x, x, y); st_p3(pts + tid, x); }
+        // both sums at once: entries [0, half) -> L, [half, 2 half) -> R
+        for (uint32_t s2 = half >> 1; s2 > 0; s2 >>= 1) {
+            if ((uint32_t)tid < 2 * half && ((uint32_t)tid % half) < s2) { ge_p3 x, y; ld_p3(x, pts + tid); ld_p3(y, pts + tid + s2); ge_add(x, x, y); st_p3(pts + tid, x); }
             __syncthreads();
         }
-        if (tid == 0 || (uint32_t)tid == F) {
+        if (tid == 0 || (uint32_t)tid == half) {
             const int lr = tid ? 1 : 0;
             ge_p3 x, y; ld_p3(x, pts + tid); ld_p3(y, ptB + lr); ge_add(x, x, y);
             uint8_t enc[32]; ge_compress(enc, x);
@@ -677,7 +717,6 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
         }
         __syncthreads();
         if (tid == 0) {
-            __threadfence();
             uint8_t lrb[64]; for (int k = 0; k < 64; k++) lrb[k] = out[64 * round + k];
             transcript_append(t, "L", lrb, 32); transcript_append(t, "R", lrb + 32, 32);
             uint8_t ub[64]; transcript_challenge(t, "u", ub, 64);
@@ -774,7 +813,7 @@ KERNEL void LB(256, 1) k_verify_tables(sc_st *tab, vtab_layout t, sc_st *var, ui
     } else if (e < t.total + (uint32_t)m) {             // commitment scalars
         const uint32_t j = e - t.total;
         sc s, r, cc; sc_pow_tab(s, zpow2 + 32 * c, j); ld_sc(r, ch + 1); ld_sc(cc, ch + 4); sc_mul(s, s, r); sc_mul(s, s, cc);
-        st_sc(var + (size_t)c * var_stride + j, s);
+        st_sc(var + (size_t)c * var_stride + j, s);          // var_stride = m: the commitment scalars of all chunks are contiguous
     }
 }
 KLAUNCH(k_verify_tables, false, (sc_st *tab, vtab_layout t, sc_st *var, uint32_t var_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int m),
@@ -983,9 +1022,10 @@ void launch_k_party_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *out, const ui
 void launch_k_bits_sum(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *partial, const uint64_t *vals, const niels_st *G, const niels_st *H, int n, int m);
 void launch_k_msm(dim3 g_, dim3 b_, cudaStream_t s_, msm_args a);
 void launch_k_finalize(dim3 g_, dim3 b_, cudaStream_t s_, finalize_args a);
-void launch_k_poly(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *l0, sc_st *r0, sc_st *sLR, sc_st *partial, const uint64_t *vals, const sc_st *ypow2, const sc_st *zpow2, int n, int m);
+void launch_k_pow_tables(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *tab, const sc_st *pow2, int L, int H);
+void launch_k_poly(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *l0, sc_st *r0, sc_st *sLR, sc_st *partial, const uint64_t *vals, pow_tab ytab, pow_tab ztab, const sc_st *zpow2, int n, int m);
 void launch_k_sc_sum(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *out, const sc_st *in, int cnt, int q);
-void launch_k_lr(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *l0, sc_st *r0, const sc_st *sLR, sc_st *yinv, const sc_st *x, const sc_st *yinvpow2, size_t N, size_t total);
+void launch_k_lr(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *l0, sc_st *r0, const sc_st *sLR, sc_st *yinv, const sc_st *x, pow_tab yitab, size_t N, size_t total);
 void launch_k_ipp_scalars(dim3 g_, dim3 b_, cudaStream_t s_, const sc_st *a, const sc_st *b, const sc_st *yinv, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np);
 void launch_k_ipp_fold_scalars(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *a, sc_st *b, const sc_st *u2, const sc_st *uinv2, size_t N, uint32_t np);
 void launch_k_ipp_fold_points(dim3 g_, dim3 b_, cudaStream_t s_, fold_args a);
@@ -1006,58 +1046,59 @@ void launch_k_l2_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const f
 // RT path: per-generator radix-256 tables in HBM (512 KB per generator: 32 windows x 128 affine-Niels multiples).
 //   Fixed generators never need doublings, buckets or sorting: s*G_j = sum_w +-RT[j][w][|d_w|-1]  (<= 32 mixed adds).
 //   Used for S, the verifier's G/H part, the first IPP rounds in "unfolded" form and the catch-up fold (engine.cuh).
-//   Layout: RT[(j*32 + w)*128 + k] = (k+1) * 256^w * Gen_j ;  j < n*m for G, then the same for H in a second array.
+//   Layout: RT[(j*nw + w)*B + k] = (k+1) * 2^(cw) * Gen_j ;  j < n*m for G, then the same for H in a second array.
 // ===================================================================================================================
-#define RT_W 32
-#define RT_E 128
-struct rt_tables { const niels_st *G, *H; };
+// run-time radix 2^c (c = 8, 9 or 10): nw = ceil(254/c) windows of B = 2^(c-1) multiples; same signed recoding as k_msm
+#define RT_MAXW 32
+struct rt_tables { const niels_st *G, *H; int c, nw, B; uint32_t K[9]; };
+HD size_t rt_row_entries(const rt_tables &t) { return (size_t)t.nw * t.B; }      // niels records per generator
 #ifdef KG_TABLES
-// step 1: P[j*32 + w] = 256^w * Gen_j  (one thread per generator, 8 doublings per window)
-KERNEL void LB(128, 2) k_rt_shifts(p3_st *P, const niels_st *gens, uint32_t count) {
+// step 1: P[j*nw + w] = 2^(cw) * Gen_j  (one thread per generator, c doublings per window)
+KERNEL void LB(128, 2) k_rt_shifts(p3_st *P, const niels_st *gens, uint32_t count, int c, int nw) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
     ge_niels g; ld_niels(g, gens + j);
     ge_p3 p; ge_niels_to_p3(p, g);
-    for (int w = 0; w < RT_W; w++) {
-        st_p3(P + (size_t)j * RT_W + w, p);
-        for (int k = 0; k < 8; k++) ge_p3_dbl(p, p);
+    for (int w = 0; w < nw; w++) {
+        st_p3(P + (size_t)j * nw + w, p);
+        for (int k = 0; k < c; k++) ge_p3_dbl(p, p);
     }
 }
-KLAUNCH(k_rt_shifts, false, (p3_st *P, const niels_st *gens, uint32_t count), (P, gens, count))
-// step 2: one thread per (row = j*32+w, group of 16 multiples): entries 16g+1 .. 16g+16 of row, converted to affine with
+KLAUNCH(k_rt_shifts, false, (p3_st *P, const niels_st *gens, uint32_t count, int c, int nw), (P, gens, count, c, nw))
+// step 2: one thread per (row = j*nw+w, group of 16 multiples): entries 16g+1 .. 16g+16 of row, converted to affine with
 // one shared inversion (Montgomery's trick over the 16 Z's)
-KERNEL void LB(128, 2) k_rt_rows(niels_st *RT, const p3_st *P, size_t rows) {
+KERNEL void LB(128, 2) k_rt_rows(niels_st *RT, const p3_st *P, size_t rows, int B) {
+    const int gpr = B / 16;                               // groups per row
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * 8) return;
-    size_t row = idx >> 3; int grp = (int)(idx & 7);
+    if (idx >= rows * gpr) return;
+    size_t row = idx / gpr; int grp = (int)(idx % gpr);
     ge_p3 base; ld_p3(base, P + row);
     ge_cached cb; ge_p3_to_cached(cb, base);
     // start = (16 grp + 1) * base
     ge_p3 cur; ge_p3_0(cur);
-    { uint32_t k = 16 * grp + 1; for (int b = 7; b >= 0; b--) { ge_p3_dbl(cur, cur); if ((k >> b) & 1) ge_add_cached(cur, cur, cb); } }
+    { uint32_t k = 16 * grp + 1; for (int b = 9; b >= 0; b--) { ge_p3_dbl(cur, cur); if ((k >> b) & 1) ge_add_cached(cur, cur, cb); } }
     ge_p3 pts[16]; fe pre[16], acc; fe_1(acc);
     for (int e = 0; e < 16; e++) { pts[e] = cur; pre[e] = acc; fe_mul(acc, acc, cur.Z); if (e < 15) ge_add_cached(cur, cur, cb); }
     fe inv; fe_invert(inv, acc);
     for (int e = 15; e >= 0; e--) {
         fe zinv; fe_mul(zinv, inv, pre[e]); fe_mul(inv, inv, pts[e].Z);
         ge_niels n; ge_p3_to_niels(n, pts[e], zinv);
-        st_niels(RT + row * RT_E + 16 * grp + e, n);
+        st_niels(RT + row * B + 16 * grp + e, n);
     }
 }
-KLAUNCH(k_rt_rows, false, (niels_st *RT, const p3_st *P, size_t rows), (RT, P, rows))
+KLAUNCH(k_rt_rows, false, (niels_st *RT, const p3_st *P, size_t rows, int B), (RT, P, rows, B))
 #endif
 
-// radix-256 signed digits of a scalar: d_w = byte_w(x + 0x7f..7f) - 127 for all 32 windows at once
-HD void rt_digits(int16_t d[32], const sc &x) {
-    uint64_t c = 0; uint32_t wds[8];
-    for (int i = 0; i < 8; i++) { c += (uint64_t)x.v[i] + 0x7f7f7f7fu; wds[i] = (uint32_t)c; c >>= 32; }
-    for (int w = 0; w < 32; w++) d[w] = (int16_t)((int)((wds[w >> 2] >> (8 * (w & 3))) & 0xff) - 127);
+// signed digits of a scalar for all nw windows at once (same recoding as k_msm: digit_w = field_w(x + K) - (B-1))
+HD void rt_digits(int16_t d[RT_MAXW], const sc &x, const rt_tables &t) {
+    uint32_t xk[9]; msm_recode(xk, x, t.K);
+    for (int w = 0; w < t.nw; w++) d[w] = (int16_t)msm_digit(xk, w, t.c);
 }
-HD void rt_mul_acc(ge_p3 &acc, const niels_st *row0, const sc &x) {          // acc += x * Gen ; row0 = RT + j*32*128
-    int16_t d[32]; rt_digits(d, x);
-    for (int w = 0; w < RT_W; w++) {
-        int dw = d[w];
-        if (dw != 0) acc_add_niels(acc, row0 + (size_t)w * RT_E + (dw > 0 ? dw : -dw) - 1, dw < 0);
+HD void rt_mul_acc(ge_p3 &acc, const niels_st *row0, const sc &x, const rt_tables &t) {          // acc += x * Gen ; row0 = RT + j*nw*B
+    uint32_t xk[9]; msm_recode(xk, x, t.K);
+    for (int w = 0; w < t.nw; w++) {
+        const int dw = msm_digit(xk, w, t.c);
+        if (dw != 0) acc_add_niels(acc, row0 + (size_t)w * t.B + (dw > 0 ? dw : -dw) - 1, dw < 0);
     }
 }
 // direct table MSM: out partial[msm*gridDim.x + blockIdx.x] = sum over this block's terms of s_t * Gen_{map(t)}.
@@ -1071,21 +1112,22 @@ KERNEL void LB(128, 4) k_rt_msm(rt_msm_args a) {
     __shared__ p3_st buf[128];
     const int tid = threadIdx.x; const uint32_t msm = blockIdx.y;
     const sc_st *scal = a.scalars + (size_t)msm * a.scalar_stride;
+    const size_t rowsz = rt_row_entries(a.rt);
     ge_p3 acc; ge_p3_0(acc);
     for (uint32_t t = blockIdx.x * blockDim.x + tid; t < a.T; t += gridDim.x * blockDim.x) {
         sc x; ld_sc(x, scal + t);
         if (sc_iszero(x)) continue;
         bool isG = t < a.nG; uint32_t q = isG ? t : t - a.nG, j = q;
         if (a.mode) { bool hi = (a.mode == 1) == isG; j = (q / a.np) * 2 * a.np + (hi ? a.np : 0) + q % a.np; }
-        rt_mul_acc(acc, (isG ? a.rt.G : a.rt.H) + (size_t)j * RT_W * RT_E, x);
+        rt_mul_acc(acc, (isG ? a.rt.G : a.rt.H) + (size_t)j * rowsz, x, a.rt);
     }
     block_sum_p3(acc, buf, tid, blockDim.x);
     if (tid == 0) st_p3(a.partial + (size_t)msm * gridDim.x + blockIdx.x, acc);
 }
 KLAUNCH(k_rt_msm, true, (rt_msm_args a), (a))
 #endif
-void launch_k_rt_shifts(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *P, const niels_st *gens, uint32_t count);
-void launch_k_rt_rows(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *RT, const p3_st *P, size_t rows);
+void launch_k_rt_shifts(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *P, const niels_st *gens, uint32_t count, int c, int nw);
+void launch_k_rt_rows(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *RT, const p3_st *P, size_t rows, int B);
 void launch_k_rt_msm(dim3 g_, dim3 b_, cudaStream_t s_, rt_msm_args a);
 
 // unfolded IPP round k (np = N >> (k+1), 2^k blocks of 2np original generators each; coefficient tables cG/cH[c*cstride + t]):
@@ -1122,22 +1164,23 @@ KLAUNCH(k_ipp_scalars_unf, true, (const sc_st *a, const sc_st *b, const sc_st *y
 // catch-up fold after r unfolded rounds: out[c][i] = sum_{t < nblk} coef[t] * Gen[t*nr + i], i < nr = N >> r, through the RT tables.
 //   digits[((c*2 + which)*nblk + t)*32 + w] = radix-256 signed digits of the coefficient (host-computed, uniform per chunk)
 //   grid (blocks, C, 2): z = 0 -> G, 1 -> H
-struct catchup_args { rt_tables rt; p3_st *Gf, *Hf; const int16_t *digits; uint32_t nr, nblk, stride; };
+struct catchup_args { rt_tables rt; p3_st *Gf, *Hf; const int16_t *digits; uint32_t nr, nblk, stride; };      // digits[((c*2+which)*nblk + t)*RT_MAXW + w]
 #ifdef KG_FOLD
 KERNEL void LB(128, 4) k_rt_catchup(catchup_args a) {
-    __shared__ int16_t dg[64 * 32];
+    __shared__ int16_t dg[64 * RT_MAXW];
     int c = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
-    for (uint32_t t = tid; t < a.nblk * 32; t += blockDim.x) dg[t] = a.digits[((size_t)c * 2 + which) * a.nblk * 32 + t];
+    for (uint32_t t = tid; t < a.nblk * RT_MAXW; t += blockDim.x) dg[t] = a.digits[((size_t)c * 2 + which) * a.nblk * RT_MAXW + t];
     __syncthreads();
     uint32_t i = blockIdx.x * blockDim.x + tid;
     if (i >= a.nr) return;
     const niels_st *RT = which ? a.rt.H : a.rt.G;
+    const size_t rowsz = rt_row_entries(a.rt);
     ge_p3 acc; ge_p3_0(acc);
     for (uint32_t t = 0; t < a.nblk; t++) {
-        const niels_st *row0 = RT + ((size_t)t * a.nr + i) * RT_W * RT_E;
-        for (int w = 0; w < RT_W; w++) {
-            int d = dg[t * 32 + w];
-            if (d != 0) acc_add_niels(acc, row0 + (size_t)w * RT_E + (d > 0 ? d : -d) - 1, d < 0);
+        const niels_st *row0 = RT + ((size_t)t * a.nr + i) * rowsz;
+        for (int w = 0; w < a.rt.nw; w++) {
+            int d = dg[t * RT_MAXW + w];
+            if (d != 0) acc_add_niels(acc, row0 + (size_t)w * a.rt.B + (d > 0 ? d : -d) - 1, d < 0);
         }
     }
     st_p3((which ? a.Hf : a.Gf) + (size_t)c * a.stride + i, acc);

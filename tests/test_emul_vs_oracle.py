@@ -145,3 +145,23 @@ def test_ipp_tail_kernel_handover(api, oracle, tail_np, rt, unfold):
         assert api.range_verify(p, cm, rngbits, seed) == 1
     finally:
         api.set_option("tail_np", 32); api.set_use_rt(1); api.set_option("rt_unfold", 3)
+
+
+@pytest.mark.parametrize("bits", [9, 10])
+def test_generator_table_radix(api, oracle, bits):
+    """Radix-2^9 / 2^10 generator tables (fewer additions per term than radix 2^8) give the same bytes."""
+    api.set_option("rt_bits", bits); api.set_option("tail_np", 2)
+    try:
+        rng = np.random.default_rng(bits)
+        D, rngbits, P, nb = 2, 8, 1, 8             # one chunk, m = 2, n = 8: 16 + 16 generators, fresh (n, fp) so the tables are rebuilt
+        mn, mx = oracle.clip_bounds(rngbits, nb, 3)
+        v = rng.uniform(mn, mx, D).astype(np.float32)
+        bl = oracle.rnd_scalar_vec(b"\x37" * 32, D)
+        seed = bytes([bits] * 32)
+        rc_o, p_o, c_o = oracle.range_prove(v, bl, rngbits, P, nb, 3, seed)
+        api.set_use_rt(0); api.set_use_rt(1)
+        rc, p, cm = api.range_prove(v, bl, rngbits, P, nb, 3, seed)
+        assert rc == rc_o == 0 and (cm == c_o).all() and (p == p_o).all()
+        assert api.range_verify(p, cm, rngbits, seed) == 1
+    finally:
+        api.set_option("rt_bits", 8); api.set_option("tail_np", 32)
