@@ -128,6 +128,30 @@ extern "C" int rofl_range_verify(rofl_ctx *c, const uint8_t *proofs, size_t plen
     return engine_range_verify(c->e, proofs, plen, np, dc.b.as<uint8_t>(), D, range, seed);
     API_CATCH
 }
+// chunk-sharded variants (multi-GPU: chunk c of an update goes to GPU c mod G)
+extern "C" int rofl_range_prove_shard(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D_shard, size_t chunk_len, size_t chunk_begin, size_t n_chunks, int range,
+                                      int n_bits, int frac, const uint8_t seed[32], uint8_t *proofs, size_t *plen, uint8_t *commits) {
+    API_TRY
+    cudaStream_t s = c->e.stream;
+    staged_in dv(v, 4 * D_shard, s), db(blind, 32 * D_shard, s); dev_buf dC(32 * (D_shard ? D_shard : 1), s);
+    shard_spec sh = {chunk_len, chunk_begin, n_chunks};
+    size_t a = 0, b = 0;
+    int rc = engine_range_prove(c->e, dv.b.as<float>(), db.b.as<uint8_t>(), D_shard, range, 0, n_bits, frac, seed, proofs, &a, &b, dC.as<uint8_t>(), &sh);
+    if (plen) *plen = a;
+    if (rc) return rc;
+    if (D_shard) rt_d2h(commits, dC.p, 32 * D_shard, s);
+    rt_sync(s);
+    return 0;
+    API_CATCH
+}
+extern "C" int rofl_range_verify_shard(rofl_ctx *c, const uint8_t *proofs, size_t plen, size_t n_chunks, const uint8_t *commits, size_t D_shard, size_t chunk_len, size_t chunk_begin,
+                                       int range, const uint8_t seed[32]) {
+    API_TRY
+    staged_in dc(commits, 32 * D_shard, c->e.stream);
+    shard_spec sh = {chunk_len, chunk_begin, n_chunks};
+    return engine_range_verify(c->e, proofs, plen, n_chunks, dc.b.as<uint8_t>(), D_shard, range, seed, &sh);
+    API_CATCH
+}
 extern "C" int rofl_l2_prove(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D, int range, int n_bits, int frac, const uint8_t seed[32],
                              uint8_t *proof, size_t *plen, uint8_t *commit) {
     API_TRY

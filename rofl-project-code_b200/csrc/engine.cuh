@@ -163,6 +163,7 @@ static inline int rt_blocks(size_t T, int C) {
     return (int)std::max<size_t>(1, nb);
 }
 static inline void run_rt_msm(rofl_engine &e, cudaStream_t s, rt_msm_args a, int nb, uint32_t n_msm) {
+    rt_prof_work(PROF_RTMSM, (double)a.T * n_msm * a.rt.nw);          // mixed additions (upper bound: zero digits skip theirs)
     void *tk = rt_prof_begin(PROF_RTMSM, s);
     LAUNCH_COOP(k_rt_msm, dim3(nb, n_msm), dim3(128), s, a);
     rt_prof_end(PROF_RTMSM, tk, s);
@@ -486,13 +487,20 @@ template <class F> static void for_chunk_groups(rofl_engine &e, size_t C, F f) {
 // returns 0 ok, 2 ValueOutOfRangeError, -1 InvalidBitsize, -2 bad arguments, -98 NaN input (reference panics),
 // -99 non power-of-two chunking (reference panics "Should not get here")
 // =============================================================================================================================
+// A shard = chunks [chunk_begin, chunk_begin + n_chunks) of a larger update (chunk length m): the caller passes only that
+// slice of the values / blindings (D = its real elements, the rest of the m * n_chunks positions is the reference's zero
+// padding) and gets exactly the proofs the whole-update call would produce for those chunks (same per-chunk nonce streams).
+struct shard_spec { size_t m, chunk_begin, n_chunks; };
 static int engine_range_prove(rofl_engine &e, const float *d_values, const uint8_t *d_blind, size_t D, int range, size_t n_partition,
-                              int n_bits, int frac, const uint8_t seed[32], uint8_t *h_proofs, size_t *proof_len, size_t *n_proofs, uint8_t *d_commits) {
-    if (!fp_ok(n_bits, frac) || D == 0 || range < 1 || range > n_bits || n_partition == 0) return -2;
+                              int n_bits, int frac, const uint8_t seed[32], uint8_t *h_proofs, size_t *proof_len, size_t *n_proofs, uint8_t *d_commits,
+                              const shard_spec *shard = nullptr) {
+    if (!fp_ok(n_bits, frac) || range < 1 || range > n_bits) return -2;
+    if (shard ? (shard->m == 0 || shard->n_chunks == 0 || D > shard->m * shard->n_chunks) : (D == 0 || n_partition == 0)) return -2;
     std::lock_guard<std::mutex> lk(e.mu);
     cudaStream_t s = e.stream;
-    const size_t Dp = next_pow2_sz(D);
-    const size_t C = std::min(Dp, n_partition), m = Dp / C;                         // :54-55
+    const size_t Dp = shard ? shard->m * shard->n_chunks : next_pow2_sz(D);
+    const size_t C = shard ? shard->n_chunks : std::min(Dp, n_partition), m = Dp / C;                         // :54-55
+    const size_t c_off = shard ? shard->chunk_begin : 0;
     const bool bitsize_ok = (range == 8 || range == 16 || range == 32 || range == 64);
     const bool chunk_ok = !(m & (m - 1)) && m * C == Dp;
     dev_buf d_V(32 * Dp, s), d_vals(8 * Dp, s), d_bl(sizeof(sc_st) * Dp, s), d_flags(sizeof(int), s);
@@ -511,7 +519,7 @@ static int engine_range_prove(rofl_engine &e, const float *d_values, const uint8
     gens_entry &g = engine_gens(e, range, (int)m);
     rt_tables rt; const bool have_rt = engine_rt(e, g, range, (int)m, rt);
     std::vector<uint8_t> keys(32 * C);
-    for (size_t c = 0; c < C; c++) derive_key(&keys[32 * c], seed, DOM_RANGE_PROVE, c);
+    for (size_t c = 0; c < C; c++) derive_key(&keys[32 * c], seed, DOM_RANGE_PROVE, c_off + c);
     const size_t plen = 32 * (9 + 2 * (size_t)ilog2_sz((size_t)range * m));
     for_chunk_groups(e, C, [&](size_t, size_t c0, size_t c1, cudaStream_t gs) {
         std::vector<uint8_t> k(keys.begin() + 32 * c0, keys.begin() + 32 * c1);
@@ -670,11 +678,13 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
 // range_proof_vec::verify_rangeproof (range_proof_vec/mod.rs:149-191).  d_commits: D compressed points (device).
 // returns 1 true, 0 false, -1 FormatError, -2 InvalidBitsize / bad args, -3 InvalidGeneratorsLength, -4 undecodable commitment
 static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t plen, size_t n_proofs, const uint8_t *d_commits, size_t D,
-                               int range, const uint8_t seed[32]) {
-    if (D == 0 || n_proofs == 0 || range < 1 || range > 64) return -2;
+                               int range, const uint8_t seed[32], const shard_spec *shard = nullptr) {
+    if (n_proofs == 0 || range < 1 || range > 64) return -2;
+    if (shard ? (shard->m == 0 || shard->n_chunks != n_proofs || D > shard->m * shard->n_chunks) : D == 0) return -2;
     std::lock_guard<std::mutex> lk(e.mu);
     cudaStream_t s = e.stream;
-    const size_t Dp = next_pow2_sz(D), m = Dp / n_proofs;                     // :168
+    const size_t Dp = shard ? shard->m * shard->n_chunks : next_pow2_sz(D), m = Dp / n_proofs;                     // :168
+    const size_t c_off = shard ? shard->chunk_begin : 0;
     if (m == 0) return -3;
     // RangeProof::from_bytes happens when the caller deserialises (params.rs:444-458): format errors come first
     if (plen % 32 || plen < 7 * 32) return -1;
@@ -699,7 +709,7 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
     gens_entry &g = engine_gens(e, range, (int)m);
     rt_tables rt; const bool have_rt = engine_rt(e, g, range, (int)m, rt);
     std::vector<uint8_t> keys(32 * C);
-    for (size_t c = 0; c < C; c++) derive_key(&keys[32 * c], seed, DOM_RANGE_VERIFY, c);
+    for (size_t c = 0; c < C; c++) derive_key(&keys[32 * c], seed, DOM_RANGE_VERIFY, c_off + c);
     std::vector<int> rcs(e.groups + 1, 1);
     for_chunk_groups(e, C, [&](size_t gi, size_t c0, size_t c1, cudaStream_t gs) {
         std::vector<uint8_t> k(keys.begin() + 32 * c0, keys.begin() + 32 * c1); std::vector<int> verdict;

@@ -10,6 +10,7 @@ struct prof_pair { cudaEvent_t a, b; };
 static std::vector<prof_pair> g_prof_events[PROF_SLOTS];
 static double g_prof_ms[PROF_SLOTS];
 static long g_prof_launch[PROF_SLOTS];
+static double g_prof_work[PROF_SLOTS];
 static std::atomic<long> g_launches{0};
 
 void rt_count_launch(const char *) { g_launches++; }
@@ -23,6 +24,7 @@ void rt_prof_end(int slot, void *token, cudaStream_t s) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_events[slot].push_back({(cudaEvent_t)token, b}); g_prof_launch[slot]++;
 }
+void rt_prof_work(int slot, double units) { if (!g_prof_on.load()) return; std::lock_guard<std::mutex> lk(g_prof_mu); g_prof_work[slot] += units; }
 static void prof_collect() {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     for (int sl = 0; sl < PROF_SLOTS; sl++) {
@@ -31,9 +33,38 @@ static void prof_collect() {
     }
 }
 extern "C" void rofl_prof_enable(int on) { g_prof_on = on; }
-extern "C" void rofl_prof_reset(void) { prof_collect(); for (int i = 0; i < PROF_SLOTS; i++) { g_prof_ms[i] = 0; g_prof_launch[i] = 0; } g_launches = 0; }
+extern "C" void rofl_prof_reset(void) { prof_collect(); for (int i = 0; i < PROF_SLOTS; i++) { g_prof_ms[i] = 0; g_prof_launch[i] = 0; g_prof_work[i] = 0; } g_launches = 0; }
+extern "C" double rofl_prof_work(int slot) { std::lock_guard<std::mutex> lk(g_prof_mu); return (slot >= 0 && slot < PROF_SLOTS) ? g_prof_work[slot] : 0.0; }
 extern "C" double rofl_prof_ms(int slot) { prof_collect(); return (slot >= 0 && slot < PROF_SLOTS) ? g_prof_ms[slot] : 0.0; }
 extern "C" long rofl_prof_launches(int slot) { if (slot < 0) return g_launches.load(); return slot < PROF_SLOTS ? g_prof_launch[slot] : 0; }
+// IMAD.WIDE.U32 issue-rate probe (the roofline denominator of this path): 8 accumulator chains per thread whose multiplicands change every
+// iteration (nothing for ptxas to hoist), all SMs, best of 5.  Returns multiply-adds per second.
+__global__ void k_probe_imad_wide(uint64_t *out, uint32_t y, int iters) {
+    uint64_t c[8]; for (int k = 0; k < 8; k++) c[k] = threadIdx.x * 8 + k + y;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] = (uint64_t)(uint32_t)c[(k + 1) & 7] * (uint32_t)c[(k + 2) & 7] + c[k];
+    }
+    uint64_t r = 0; for (int k = 0; k < 8; k++) r ^= c[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+extern "C" double rofl_probe_imad_wide(rofl_ctx *c) {
+    if (!c) return 0.0;
+    try {
+        std::lock_guard<std::mutex> lk(c->e.mu); cudaStream_t s = c->e.stream;
+        cudaDeviceProp prop; rt_check(cudaGetDeviceProperties(&prop, c->e.device), "props");
+        const int tpb = 256, blocks = prop.multiProcessorCount * 32, iters = 4096;
+        dev_buf buf(sizeof(uint64_t) * (size_t)tpb * blocks, s);
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        float best = 1e30f;
+        for (int r = 0; r < 6; r++) {
+            cudaEventRecord(a, s); k_probe_imad_wide<<<blocks, tpb, 0, s>>>(buf.as<uint64_t>(), 12345u + r, iters); cudaEventRecord(b, s);
+            rt_check(cudaEventSynchronize(b), "probe"); float ms = 0; cudaEventElapsedTime(&ms, a, b); if (r && ms < best) best = ms;
+        }
+        cudaEventDestroy(a); cudaEventDestroy(b);
+        return (double)tpb * blocks * iters * 8 / (best * 1e-3);
+    } catch (const std::exception &ex) { g_last_error = ex.what(); return 0.0; }
+}
 extern "C" void *rofl_ctx_stream(rofl_ctx *c) { return c ? (void *)c->e.stream : nullptr; }
 
 extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {

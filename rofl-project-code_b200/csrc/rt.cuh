@@ -18,6 +18,7 @@ inline size_t rt_free_mem() { return (size_t)8 << 30; }
 struct rt_event { };
 inline void *rt_prof_begin(int, cudaStream_t) { return nullptr; }
 inline void rt_prof_end(int, void *, cudaStream_t) {}
+inline void rt_prof_work(int, double) {}
 #else
 #include <cuda_runtime.h>
 inline void rt_check(cudaError_t e, const char *what) {
@@ -34,6 +35,7 @@ inline void rt_sync(cudaStream_t s) { rt_check(cudaStreamSynchronize(s), "sync")
 inline size_t rt_free_mem() { size_t f = 0, t = 0; cudaMemGetInfo(&f, &t); return f; }
 void *rt_prof_begin(int slot, cudaStream_t s);
 void rt_prof_end(int slot, void *token, cudaStream_t s);
+void rt_prof_work(int slot, double units);        // algorithmic work of the launches in that slot (e.g. point additions)
 #endif
 
 #define LAUNCH(k, grid, block, stream, ...) launch_##k(grid, block, stream, __VA_ARGS__)
