@@ -27,9 +27,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(workload="cifar_lenet5 update: commit + L-inf range proofs, prove and verify", D=62006, range_bits=16, n_partition=64, n_bits=16, frac=7)
 METRIC = "range-proved commitment elements/s (prove & verify)"
-IMAD_PER_FIELD_MUL = 100                       # 10x10 limb schoolbook
-# generator fold (dominant kernel): per output one NAF-5 ladder = 256 doublings (4S+3M) + ~43+8 additions (8M) + conversions
-FIELD_MULS_PER_FOLD_OUTPUT = 256 * 7 + 51 * 8 + 9
+IMAD_PER_FIELD_MUL = 72                        # 8 x 8 limb schoolbook (64) + the 2^256 = 38 fold (8): the algorithmic cost of one field multiplication
 
 
 def synth(D, rng_bits, n_bits, frac, seed):
@@ -171,18 +169,16 @@ def main():
 
     for it in range(args.warmup):
         step_resident(it); step_e2e(it)
-    # ---- timed: resident
-    lib.rofl_prof_enable(1); lib.rofl_prof_reset()
+    imad_peak = lib.rofl_probe_imad_wide(api.h) if rank == 0 else 0.0       # roofline denominator, measured on this GPU before the timed region
+    # ---- timed: resident (no per-kernel events inside the timed region)
+    lib.rofl_prof_enable(0); lib.rofl_prof_reset()
     sampler = ClockSampler(local); sampler.start()
     barrier()
     t_p = t_v = 0.0
     for it in range(args.steps):
         a, b, proofs = step_resident(100 + it); t_p += a; t_v += b
     barrier()
-    fold_ms, fold_launches = lib.rofl_prof_ms(0), lib.rofl_prof_launches(0)
-    msm_ms = lib.rofl_prof_ms(1)
     launches = lib.rofl_prof_launches(-1)
-    lib.rofl_prof_enable(0)
     # ---- timed: end to end through the host-buffer API
     barrier()
     e_p = e_v = 0.0
@@ -190,6 +186,15 @@ def main():
         a, b = step_e2e(200 + it); e_p += a; e_v += b
     barrier()
     clocks = sampler.stop()
+    # ---- per-kernel breakdown: the same K resident steps again with CUDA events around every launch of the main kernel families
+    # (separate pass: creating / recording the events costs host time that must not leak into `value`)
+    lib.rofl_prof_enable(1); lib.rofl_prof_reset()
+    for it in range(args.steps):
+        step_resident(300 + it)
+    torch.cuda.synchronize()
+    prof = dict(fold_ms=lib.rofl_prof_ms(0), msm_ms=lib.rofl_prof_ms(1), commit_ms=lib.rofl_prof_ms(2), rt_ms=lib.rofl_prof_ms(4), tail_ms=lib.rofl_prof_ms(5),
+                rt_launches=lib.rofl_prof_launches(4), rt_madds=lib.rofl_prof_work(4))
+    lib.rofl_prof_enable(0)
     if world > 1:      # proof pieces are the only thing that crosses NVLink: gather them (outside the timed kernels)
         pt = torch.from_numpy(proofs).cuda(); out = [torch.empty_like(pt) for _ in range(world)]; dist.all_gather(out, pt)
         tt = torch.tensor([t_p, t_v, e_p, e_v], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t_p, t_v, e_p, e_v = tt.tolist()
@@ -201,28 +206,30 @@ def main():
     ms_step = (t_p + t_v) / K
     value = world * D / (ms_step / 1e3)
     e2e_val = world * D / ((e_p + e_v) / K / 1e3)
-    # roofline of the dominant kernel (generator fold, integer pipe): algorithmic IMADs / measured kernel time
-    Dp = 1 << (D - 1).bit_length(); N_total = Dp * rb
-    fold_outputs_per_step = 2 * (N_total - 2 * P)              # G and H, sum over rounds of N/2^k except the last round
-    peak = None
-    peaks_path = os.path.join(ROOT, "profiles", "int_peaks.json")
-    try:
-        mb = subprocess.run([os.path.join(ROOT, "tools", "microbench")], capture_output=True, text=True, timeout=120)
-        peak_info = json.loads(mb.stdout.strip().splitlines()[-1])
-        peak = max(val for k, val in peak_info.items() if k.startswith("imad_wide_gops")) / 1e3          # T IMAD.WIDE/s, measured now on this GPU
-    except Exception:
-        if os.path.exists(peaks_path):
-            peak = json.load(open(peaks_path)).get("imad_wide_tops")
-    achieved = fold_outputs_per_step * K * FIELD_MULS_PER_FOLD_OUTPUT * IMAD_PER_FIELD_MUL / (fold_ms / 1e3) / 1e12 if fold_ms > 0 else None
-    hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    fold_bytes = fold_outputs_per_step * K * (2 * 160 + 160)
-    roofline = dict(bound="int-imad (the path is integer-pipe bound, not hbm/tensor; see DESIGN.md)", kernel="k_ipp_fold_points", achieved=achieved, peak=peak, unit="T IMAD.WIDE.U32/s",
-                    frac=(achieved / peak) if (achieved and peak) else None, traffic=None, kernel_ms_per_step=fold_ms / K, kernel_share_of_step=fold_ms / K / ms_step,
-                    msm_ms_per_step=msm_ms / K, peak_source="tools/microbench run inside this bench (independent mad.wide.u32 chains, all SMs)",
-                    hbm=dict(achieved_gbs=fold_bytes / (fold_ms / 1e3) / 1e9 if fold_ms > 0 else None, peak_gbs=hbm_peak, peak_source="MEASURED_PEAKS.json (of measured)"))
+    # ---- roofline of the dominant kernel: k_rt_msm (direct table MSM: S, the unfolded IPP rounds, the verifier's generator part).
+    # The path is bound by the IMAD.WIDE.U32 pipe (32 lanes/clk/SM), not by HBM or the tensor cores.
+    #   achieved = algorithmic multiply-adds / measured kernel time;  algorithmic = mixed additions x 7 field multiplications x 72
+    #   IMAD.WIDE.U32 (8x8 schoolbook + 8 for the 2^256 = 38 fold);  peak = IMAD.WIDE issue rate measured now by rofl_probe_imad_wide
+    madds = prof["rt_madds"]; rt_ms = prof["rt_ms"]
+    achieved = madds * 7 * IMAD_PER_FIELD_MUL / (rt_ms / 1e3) / 1e12 if rt_ms > 0 else None
+    peak = imad_peak / 1e12 if imad_peak else None
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_rt_msm_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    launches_rt = max(1, prof["rt_launches"])
+    roofline = dict(bound="int-imad-wide (integer multiply pipe; not hbm / tensor: see DESIGN.md section 5)", kernel="k_rt_msm", achieved=achieved, peak=peak, unit="T IMAD.WIDE.U32/s",
+                    frac=(achieved / peak) if (achieved and peak) else None, traffic=traffic,
+                    algorithmic=dict(mixed_additions_per_launch=madds / launches_rt, field_muls_per_addition=7, imad_wide_per_field_mul=IMAD_PER_FIELD_MUL, launches_per_step=launches_rt / K),
+                    kernel_ms_per_launch=rt_ms / launches_rt, kernel_ms_per_step=rt_ms / K, kernel_share_of_step=rt_ms / K / ms_step,
+                    peak_source="rofl_probe_imad_wide: best of two mad.wide.u32 patterns (rotating multiplicands; carry-chained as in the field multiply), all SMs, best of 5, run before the timed region",
+                    hbm=dict(achieved_gbs=madds * 96 / (rt_ms / 1e3) / 1e9 if rt_ms > 0 else None, peak_gbs=hbm_peak, note="table gathers: 96 B per mixed addition; MEASURED_PEAKS.json copy bandwidth" if peaks else "fallback 6650 GB/s"),
+                    other_kernels_ms_per_step=dict(bucket_msm=prof["msm_ms"] / K, generator_fold=prof["fold_ms"] / K, ipp_tail=prof["tail_ms"] / K, commit=prof["commit_ms"] / K))
     line = dict(metric=METRIC, value=value, unit="elements/s", n_gpus=world, steps=K, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype="u32 (radix-2^25.5 GF(2^255-19) limbs, 64-bit accumulators; scalars mod l)", data="synthetic",
-                config=dict(w, l2_flush="256 MiB write between timed iterations", parallelism=f"client x{world}"),
+                vs_baseline=None, dtype="u32 (8 saturated 32-bit limbs of GF(2^255-19), IMAD.WIDE.U32 with 64-bit accumulate; scalars mod l)", data="synthetic",
+                config=dict(w, l2_flush="256 MiB write between timed iterations", parallelism=f"client x{world}", generators="warm (cached tables)"),
                 prove_eps=world * D / (t_p / K / 1e3), verify_eps=world * D / (t_v / K / 1e3), prove_ms=t_p / K, verify_ms=t_v / K,
                 e2e=dict(value=e2e_val, unit="elements/s", h2d_bytes_per_step=int(v_h.numel() * 4 + bl_h.numel() + D * 32), d2h_bytes_per_step=int(D * 32 + n_proofs * plen),
                          prove_ms=e_p / K, verify_ms=e_v / K),

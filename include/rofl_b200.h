@@ -92,6 +92,14 @@ int rofl_range_verify_dev(rofl_ctx *, const uint8_t *proofs /*host*/, size_t pro
 
 /* ---- l2_range_proof_vec::{create_rangeproof_l2, verify_rangeproof_l2} (l2_range_proof_vec/mod.rs:15-140,185-228;
  *      bindings32.rs:441,507).  out_proof: rofl_range_proof_len(range) bytes; out_commit32: 32 bytes (not shifted). */
+/* chunk-sharded range proofs for multi-GPU (one update, chunk c -> GPU c mod G; range_proof_vec/mod.rs:54-78 makes the chunks
+ * independent proofs).  The caller passes the slice of chunks [chunk_begin, chunk_begin + n_chunks) of chunk length chunk_len
+ * (= next_pow2(D) / min(next_pow2(D), n_partition)); D_shard = real elements in the slice (the rest is the reference's zero padding).
+ * The proofs / commitments are byte-identical to the corresponding rows of the whole-update call. */
+int rofl_range_prove_shard(rofl_ctx *, const float *v, const uint8_t *blind32, size_t D_shard, size_t chunk_len, size_t chunk_begin, size_t n_chunks, int range,
+                           int n_bits, int frac, const uint8_t seed[32], uint8_t *out_proofs, size_t *out_proof_len, uint8_t *out_commits32);
+int rofl_range_verify_shard(rofl_ctx *, const uint8_t *proofs, size_t proof_len, size_t n_chunks, const uint8_t *commits32, size_t D_shard, size_t chunk_len, size_t chunk_begin,
+                            int range, const uint8_t seed[32]);
 int rofl_l2_prove(rofl_ctx *, const float *v, const uint8_t *blind32, size_t D, int range, int n_bits, int frac, const uint8_t seed[32],
                   uint8_t *out_proof, size_t *out_proof_len, uint8_t *out_commit32);
 int rofl_l2_verify(rofl_ctx *, const uint8_t *proof, size_t proof_len, const uint8_t commit32[32], int range, const uint8_t seed[32]);
@@ -123,6 +131,8 @@ void rofl_prof_enable(int on);
 void rofl_prof_reset(void);
 double rofl_prof_ms(int slot);            /* summed device time of that kernel family, milliseconds */
 long rofl_prof_launches(int slot);        /* launches of that family; slot -1 = all kernels launched by the library */
+double rofl_prof_work(int slot);          /* algorithmic work of that family since the last reset (slot 4, table MSM: mixed point additions) */
+double rofl_probe_imad_wide(rofl_ctx *);  /* measured IMAD.WIDE.U32 issue rate of this GPU, multiply-adds per second (roofline denominator) */
 void *rofl_ctx_stream(rofl_ctx *);        /* the cudaStream_t the context launches on */
 #ifdef __cplusplus
 }

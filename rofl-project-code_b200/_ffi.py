@@ -28,6 +28,8 @@ _SIGS = {
     "rofl_commit_dev": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p]),
     "rofl_range_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, C.POINTER(c_sz), C.POINTER(c_sz), c_u8p]),
     "rofl_range_prove_dev": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, C.POINTER(c_sz), C.POINTER(c_sz), c_u8p]),
+    "rofl_range_prove_shard": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, c_sz, c_sz, c_sz, C.c_int, C.c_int, C.c_int, c_u8p, c_u8p, C.POINTER(c_sz), c_u8p]),
+    "rofl_range_verify_shard": (C.c_int, [c_vp, c_u8p, c_sz, c_sz, c_u8p, c_sz, c_sz, c_sz, C.c_int, c_u8p]),
     "rofl_range_verify": (C.c_int, [c_vp, c_u8p, c_sz, c_sz, c_u8p, c_sz, C.c_int, c_u8p]),
     "rofl_range_verify_dev": (C.c_int, [c_vp, c_u8p, c_sz, c_sz, c_u8p, c_sz, C.c_int, c_u8p]),
     "rofl_l2_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, C.c_int, C.c_int, c_u8p, c_u8p, C.POINTER(c_sz), c_u8p]),
@@ -43,6 +45,8 @@ _SIGS = {
     "rofl_prof_enable": (None, [C.c_int]),
     "rofl_prof_reset": (None, []),
     "rofl_prof_ms": (C.c_double, [C.c_int]),
+    "rofl_prof_work": (C.c_double, [C.c_int]),
+    "rofl_probe_imad_wide": (C.c_double, [c_vp]),
     "rofl_prof_launches": (C.c_long, [C.c_int]),
     "rofl_ctx_stream": (c_vp, [c_vp]),
 }
@@ -169,6 +173,19 @@ class Api:
     def range_verify(self, proofs, commits, rng, seed=SEED0):
         p = _u8(proofs); p = p.reshape(p.shape[0], -1); c = _u8(commits).reshape(-1, 32)
         rc = self.lib.rofl_range_verify(self.h, _ptr(p), p.shape[1], p.shape[0], _ptr(c), c.shape[0], rng, _ptr(_u8(seed, 32)))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc
+    def range_prove_shard(self, v, blind, chunk_len, chunk_begin, n_chunks, rng, n_bits, frac, seed=SEED0):
+        """Chunks [chunk_begin, chunk_begin + n_chunks) of a larger update; v / blind hold the real elements of that slice."""
+        v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
+        plen = self.range_proof_len(rng * chunk_len)
+        proofs = np.zeros((n_chunks, plen), np.uint8); commits = np.zeros((D, 32), np.uint8); a = c_sz()
+        rc = self.lib.rofl_range_prove_shard(self.h, _ptr(v), _ptr(b), D, chunk_len, chunk_begin, n_chunks, rng, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proofs), C.byref(a), _ptr(commits))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc, proofs, commits
+    def range_verify_shard(self, proofs, commits, chunk_len, chunk_begin, rng, seed=SEED0):
+        p = _u8(proofs); p = p.reshape(p.shape[0], -1); c = _u8(commits).reshape(-1, 32)
+        rc = self.lib.rofl_range_verify_shard(self.h, _ptr(p), p.shape[1], p.shape[0], _ptr(c), c.shape[0], chunk_len, chunk_begin, rng, _ptr(_u8(seed, 32)))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
     def range_verify_dev(self, proofs, commits_ptr, D, rng, seed=SEED0):

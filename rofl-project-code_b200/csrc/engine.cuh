@@ -29,13 +29,27 @@ struct rofl_engine {
     std::map<std::pair<uint64_t, int>, bsgs_entry> bsgs;
     std::mutex mu;
     int host_threads = 8;
-    int groups = 1;                       // chunk groups proved / verified concurrently on separate streams (hides per-round latency)
+    int groups = 2;                       // chunk groups proved / verified concurrently on separate streams (hides per-round latency)
     std::vector<cudaStream_t> gstreams;   // gstreams[0] == stream
     int use_rt = 1;                       // 0: never build generator tables (generic Pippenger / fold path only)
     int rt_unfold = 4;                    // IPP rounds computed over the original generators before the catch-up fold
     int tail_np = 32;                     // IPP rounds with half-size <= tail_np run in the fused on-device tail kernel (0 = off)
+    std::mutex pin_mu; std::vector<std::pair<void *, size_t>> pins;      // pool of pinned host blocks for the per-round exchanges
     int rt_bits = 10;                     // widest generator-table radix to try (8..10)
     double rt_mem_frac = 0.45;            // tables may take this fraction of the free device memory
+};
+
+// pinned host scratch with scope lifetime, recycled through the engine's pool (cudaHostAlloc is far too slow to call per proof)
+struct pinned_buf {
+    rofl_engine &e; void *p = nullptr; size_t n = 0;
+    pinned_buf(rofl_engine &eng, size_t bytes) : e(eng) {
+        { std::lock_guard<std::mutex> lk(e.pin_mu);
+          for (size_t i = 0; i < e.pins.size(); i++) if (e.pins[i].second >= bytes) { p = e.pins[i].first; n = e.pins[i].second; e.pins.erase(e.pins.begin() + i); break; } }
+        if (!p) { n = std::max<size_t>(bytes, 1 << 16); p = rt_host_alloc(n); }
+    }
+    ~pinned_buf() { std::lock_guard<std::mutex> lk(e.pin_mu); e.pins.emplace_back(p, n); }
+    pinned_buf(const pinned_buf &) = delete; pinned_buf &operator=(const pinned_buf &) = delete;
+    template <class T> T *as() const { return (T *)p; }
 };
 
 // ---- small host helpers ---------------------------------------------------------------------------------------------------
@@ -102,6 +116,8 @@ static inline void engine_destroy(rofl_engine &e) {
     rt_free(e.tabB, s); rt_free(e.tabH, s);
     for (auto &g : e.gens) { rt_free(g.second.G, s); rt_free(g.second.H, s); rt_free(g.second.RTG, s); rt_free(g.second.RTH, s); }
     for (auto &b : e.bsgs) { rt_free(b.second.keys, s); rt_free(b.second.vals, s); }
+    for (auto &pp : e.pins) rt_host_free(pp.first);
+    e.pins.clear();
     e.gens.clear(); e.bsgs.clear();
     rt_sync(s);
 }
@@ -334,7 +350,7 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     dev_buf d_cLR(sizeof(sc_st) * 2 * C, s), d_LR(64 * (size_t)C, s), d_u2(sizeof(sc_st) * C, s), d_uinv2(sizeof(sc_st) * C, s), d_nafs(512 * (size_t)C, s);
     std::vector<sc> uprod(C), uinvprod(C);
     for (int c = 0; c < C; c++) { sc_from_u64(uprod[c], 1); sc_from_u64(uinvprod[c], 1); }
-    std::vector<uint8_t> hLR(64 * (size_t)C);
+    pinned_buf pinLR(e, 64 * (size_t)C); uint8_t *hLR = pinLR.as<uint8_t>();
     std::vector<sc> u(C), uinv(C);
     std::vector<sc_st> h_u2(C), h_uinv2(C); std::vector<int8_t> h_nafs(512 * (size_t)C);
     // RT path: the first r_unf rounds take L/R as table MSMs over the ORIGINAL generators (no generator folding), then one
@@ -410,7 +426,7 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
             run_finalize(s, f);
         }
-        rt_d2h(hLR.data(), d_LR.p, hLR.size(), s);
+        rt_d2h(hLR, d_LR.p, 64 * (size_t)C, s);
         rt_sync(s);
         serial_for(C, [&](size_t c) {
             transcript &t = ts[c]; uint8_t *o = h_proofs + plen * c + 224 + 64 * round;
@@ -710,8 +726,9 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
     rt_tables rt; const bool have_rt = engine_rt(e, g, range, (int)m, rt);
     std::vector<uint8_t> keys(32 * C);
     for (size_t c = 0; c < C; c++) derive_key(&keys[32 * c], seed, DOM_RANGE_VERIFY, c_off + c);
-    std::vector<int> rcs(e.groups + 1, 1);
-    for_chunk_groups(e, C, [&](size_t gi, size_t c0, size_t c1, cudaStream_t gs) {
+    // one group: every chunk goes into the same batched check (kernels.cuh, k_verify_scalars), splitting would repeat the generator MSM
+    std::vector<int> rcs(2, 1);
+    [&](auto f) { f((size_t)0, (size_t)0, C, e.stream); }([&](size_t gi, size_t c0, size_t c1, cudaStream_t gs) {
         std::vector<uint8_t> k(keys.begin() + 32 * c0, keys.begin() + 32 * c1); std::vector<int> verdict;
         int rc = verify_chunks(e, gs, "RangeProof", range, (int)m, (int)(c1 - c0), g, have_rt ? &rt : nullptr, d_Vp3.as<p3_st>() + c0 * m, hV.data() + 32 * c0 * m, h_proofs + plen * c0, plen, k, verdict);
         int res = 1; for (int v : verdict) res &= v;                               // :183-190

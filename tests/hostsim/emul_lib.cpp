@@ -15,5 +15,7 @@ extern "C" void rofl_prof_enable(int) {}
 extern "C" void rofl_prof_reset(void) {}
 extern "C" double rofl_prof_ms(int) { return 0; }
 extern "C" long rofl_prof_launches(int) { return 0; }
+extern "C" double rofl_prof_work(int) { return 0; }
+extern "C" double rofl_probe_imad_wide(rofl_ctx *) { return 0; }
 extern "C" void *rofl_ctx_stream(rofl_ctx *) { return nullptr; }
 #pragma GCC visibility pop
