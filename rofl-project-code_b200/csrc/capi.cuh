@@ -171,6 +171,17 @@ extern "C" int rofl_square_prove_dev(rofl_ctx *c, const float *v, const uint8_t 
                                      const uint8_t seed[32], uint8_t *proofs, uint8_t *commits) {
     API_TRY return engine_square_prove(c->e, v, vc, r1, r2, D, n_bits, frac, seed, proofs, commits); API_CATCH
 }
+extern "C" int rofl_crp_prove(rofl_ctx *c, const float *v, const uint8_t *value_com32, const uint8_t *blind, size_t D, int n_bits, int frac, const uint8_t seed[32],
+                              uint8_t *proof128, uint8_t *pairs64) {
+    API_TRY
+    cudaStream_t s = c->e.stream;
+    staged_in dv(v, 4 * D, s), db(blind, 32 * D, s), dc(value_com32, value_com32 ? 32 * D : 0, s);
+    return engine_crp_prove(c->e, dv.b.as<float>(), value_com32 ? dc.b.as<uint8_t>() : nullptr, db.b.as<uint8_t>(), D, n_bits, frac, seed, proof128, pairs64);
+    API_CATCH
+}
+extern "C" int rofl_crp_verify(rofl_ctx *c, const uint8_t *proof128, const uint8_t *pairs64, size_t D) {
+    API_TRY return engine_crp_verify(c->e, proof128, pairs64, D); API_CATCH
+}
 extern "C" int rofl_square_prove(rofl_ctx *c, const float *v, const uint8_t *vc, const uint8_t *r1, const uint8_t *r2, size_t D, int n_bits, int frac,
                                  const uint8_t seed[32], uint8_t *proofs, uint8_t *commits) {
     API_TRY

@@ -845,6 +845,126 @@ static int engine_square_verify(rofl_engine &e, const uint8_t *d_proofs, const u
 }
 
 // =============================================================================================================================
+// compressed_rand_proof::CompressedRandProof::{helper_prove, helper_prove_existing, helper_verify} (compressed_rand_proof/mod.rs:134-158)
+//   d_values / d_blind / d_value_com (nullable: L_i = commit(m_i, r_i)) are device pointers; h_proof (128 B) and h_pairs (D x 64) host.
+//   returns 0 ok, -4 undecodable existing commitment, -6 more than 900 000 pairs (the reference's label table ends there and it panics), -98 NaN
+// =============================================================================================================================
+#define CRP_MAX_D 900000
+static inline void crp_challenge(sc &c, const uint8_t *h_pairs, size_t D, const uint8_t cprime[64]) {
+    transcript t; transcript_init(t, "CompressedRandProof");
+    const uint8_t ds[19] = {'r', 'a', 'n', 'd', 'o', 'm', 'n', 'e', 's', 's', ' ', 'p', 'r', 'o', 'o', 'f', ' ', 'v', '1'};
+    transcript_append(t, "dom-sep", ds, 19);                                                         // rand_proof/transcript.rs:20-22
+    for (size_t i = 0; i < D; i++) {                                                                 // dealer.rs:27-29; labels: generate_unique_u8_triplets.py:9-13
+        const uint8_t lab[3] = {(uint8_t)(3 * i), (uint8_t)(3 * i + 1), (uint8_t)(3 * i + 2)};
+        transcript_append_l(t, lab, 3, h_pairs + 64 * i, 64);
+    }
+    transcript_append(t, "C_prime_eg", cprime, 64);                                                  // dealer.rs:53-54
+    ts_challenge_scalar(t, "c", c);
+}
+static inline pow_tab crp_pow_table(rofl_engine &e, cudaStream_t s, const sc &c, size_t D, dev_buf &store) {
+    const int bits = std::max(2, ilog2_sz(D + 2));
+    pow_tab ct = {nullptr, bits / 2, bits - bits / 2};
+    std::vector<sc_st> h_pow2(32); sc_pow2_table(h_pow2.data(), c);
+    sc_st *base = store.as<sc_st>();                               // [32 pow2 | table]
+    rt_h2d(base, h_pow2.data(), sizeof(sc_st) * 32, s);
+    ct.tab = base + 32;
+    LAUNCH(k_pow_tables, dim3((pow_tab_size(ct) + 255) / 256, 1), dim3(256), s, base + 32, base, ct.L, ct.H);
+    return ct;
+}
+static int engine_crp_prove(rofl_engine &e, const float *d_values, const uint8_t *d_value_com, const uint8_t *d_blind, size_t D, int n_bits, int frac,
+                            const uint8_t seed[32], uint8_t *h_proof, uint8_t *h_pairs) {
+    if (!fp_ok(n_bits, frac)) return -2;
+    if (D > CRP_MAX_D) return -6;
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    const size_t Dn = D ? D : 1;
+    dev_buf d_L(32 * Dn, s), d_R(32 * Dn, s), d_pairs(64 * Dn, s), d_flags(sizeof(int), s), d_bad(sizeof(int), s);
+    rt_memset(d_flags.p, 0, sizeof(int), s); rt_memset(d_bad.p, 0, sizeof(int), s);
+    if (D) {
+        commit_args ca = {}; ca.values = d_values; ca.blind = d_blind; ca.D = D; ca.Dp = D; ca.n_bits = n_bits; ca.frac = frac;
+        ca.tabB = e.tabB; ca.tabH = e.tabH; ca.C = d_value_com ? nullptr : d_L.as<uint8_t>(); ca.R = d_R.as<uint8_t>(); ca.flags = d_flags.as<int>();   // R_i = r_i B (el_gamal.rs:57-69)
+        LAUNCH(k_commit, dim3((unsigned)((D + 127) / 128)), dim3(128), s, ca);
+        if (d_value_com) {          // prove_existing: the caller's commitments must at least decode (the reference holds RistrettoPoints)
+            dev_buf d_tmp(sizeof(p3_st) * D, s);
+            LAUNCH(k_decompress, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_tmp.as<p3_st>(), (uint8_t *)nullptr, d_value_com, D, D, (const p3_st *)nullptr, d_bad.as<int>(), D);
+        }
+        LAUNCH(k_pairs_join, dim3((unsigned)((D + 255) / 256)), dim3(256), s, d_pairs.as<uint8_t>(), d_value_com ? d_value_com : d_L.as<uint8_t>(), d_R.as<uint8_t>(), D);
+        rt_d2h(h_pairs, d_pairs.p, 64 * D, s);
+    }
+    // C' = (m' B + r' H, r' B), nonces in the draw order of Party::new (party.rs:26-29)
+    uint8_t key[32]; derive_key(key, seed, DOM_CRP, 0); uint32_t kw[8]; key_words(kw, key);
+    sc mp, rp, zero; nonce_scalar(mp, kw, 0); nonce_scalar(rp, kw, 1); sc_0(zero);
+    sc_st h_sB[2], h_sH[2]; sc_to_st(h_sB[0], mp); sc_to_st(h_sH[0], rp); sc_to_st(h_sB[1], rp); sc_to_st(h_sH[1], zero);
+    dev_buf d_s(sizeof(sc_st) * 4, s), d_cp(64, s);
+    rt_h2d(d_s.p, h_sB, sizeof(h_sB), s); rt_h2d(d_s.as<sc_st>() + 2, h_sH, sizeof(h_sH), s);
+    { finalize_args f = {}; f.sBa = d_s.as<sc_st>(); f.sHa = d_s.as<sc_st>() + 2; f.tabB = e.tabB; f.tabH = e.tabH; f.out32 = d_cp.as<uint8_t>(); f.count = 2; run_finalize(s, f); }
+    int flags = 0, bad = 0;
+    rt_d2h(h_proof, d_cp.p, 64, s); rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_d2h(&bad, d_bad.p, sizeof(int), s);
+    rt_sync(s);
+    if (flags & 1) return -98;
+    if (bad) return -4;
+    sc c; crp_challenge(c, h_pairs, D, h_proof);
+    sc zm = mp, zr = rp;
+    if (D) {
+        dev_buf d_ct(sizeof(sc_st) * (32 + ((size_t)2 << ((ilog2_sz(D + 2) + 1) / 2 + 1))), s);
+        pow_tab ct = crp_pow_table(e, s, c, D, d_ct);
+        const int nb = (int)std::min<size_t>(256, (D + 255) / 256);
+        dev_buf d_part(sizeof(sc_st) * 2 * nb, s), d_sum(sizeof(sc_st) * 2, s);
+        LAUNCH_COOP(k_crp_sums, dim3(nb), dim3(256), s, d_part.as<sc_st>(), d_values, d_blind, D, n_bits, frac, ct, d_flags.as<int>());
+        LAUNCH_COOP(k_sc_sum, dim3(1), dim3(256), s, d_sum.as<sc_st>(), d_part.as<sc_st>(), nb, 2);
+        sc_st hs[2]; rt_d2h(hs, d_sum.p, sizeof(hs), s); rt_sync(s);
+        sc a, b; st_to_sc(a, hs[0]); st_to_sc(b, hs[1]); sc_add(zm, zm, a); sc_add(zr, zr, b);     // party.rs:93-97
+    }
+    sc_tobytes(h_proof + 64, zm); sc_tobytes(h_proof + 96, zr);
+    return 0;
+}
+// returns 1 valid, 0 invalid, -1 FormatError (from_bytes: mod.rs:118-134, el_gamal.rs:113-123), -6 too many pairs
+static int engine_crp_verify(rofl_engine &e, const uint8_t *h_proof, const uint8_t *h_pairs, size_t D) {
+    if (D > CRP_MAX_D) return -6;
+    sc zm, zr; sc_frombytes(zm, h_proof + 64); sc_frombytes(zr, h_proof + 96);
+    if (!sc_is_canonical(zm) || !sc_is_canonical(zr)) return -1;
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    const size_t Dn = D ? D : 1;
+    dev_buf d_pairs(64 * Dn, s), d_LR32(64 * Dn, s), d_LR(sizeof(p3_st) * 2 * Dn, s), d_cp32(64, s), d_cp(sizeof(p3_st) * 2, s), d_bad(sizeof(int) * 2, s);
+    rt_memset(d_bad.p, 0, sizeof(int) * 2, s);
+    rt_h2d(d_cp32.p, h_proof, 64, s);
+    LAUNCH(k_decompress, dim3(1), dim3(128), s, d_cp.as<p3_st>(), (uint8_t *)nullptr, d_cp32.as<uint8_t>(), (size_t)2, (size_t)2, (const p3_st *)nullptr, d_bad.as<int>(), (size_t)2);
+    if (D) {
+        rt_h2d(d_pairs.p, h_pairs, 64 * D, s);
+        LAUNCH(k_pairs_split, dim3((unsigned)((D + 255) / 256)), dim3(256), s, d_LR32.as<uint8_t>(), d_LR32.as<uint8_t>() + 32 * D, d_pairs.as<uint8_t>(), D);
+        LAUNCH(k_decompress, dim3((unsigned)((2 * D + 127) / 128)), dim3(128), s, d_LR.as<p3_st>(), (uint8_t *)nullptr, d_LR32.as<uint8_t>(), 2 * D, 2 * D, (const p3_st *)nullptr, d_bad.as<int>() + 1, 2 * D);
+    }
+    sc c; crp_challenge(c, h_pairs, D, h_proof);                   // overlaps the decompression
+    // sum_i c^(i+1) L_i and sum_i c^(i+1) R_i: two MSMs that share their scalars
+    sc nzm, nzr, zero; sc_neg(nzm, zm); sc_neg(nzr, zr); sc_0(zero);
+    sc_st h_s[4]; sc_to_st(h_s[0], nzm); sc_to_st(h_s[1], nzr); sc_to_st(h_s[2], nzr); sc_to_st(h_s[3], zero);      // sB = [-z_m, -z_r], sH = [-z_r, 0]
+    dev_buf d_s(sizeof(sc_st) * 4, s), d_id(sizeof(int) * 2, s);
+    rt_h2d(d_s.p, h_s, sizeof(h_s), s);
+    finalize_args f = {}; f.partial = d_cp.as<p3_st>(); f.npartial = 1; f.sBa = d_s.as<sc_st>(); f.sHa = d_s.as<sc_st>() + 2; f.tabB = e.tabB; f.tabH = e.tabH;
+    f.is_id = d_id.as<int>(); f.count = 2;
+    if (D) {
+        dev_buf d_ct(sizeof(sc_st) * (32 + ((size_t)2 << ((ilog2_sz(D + 2) + 1) / 2 + 1))), s), d_pw(sizeof(sc_st) * D, s);
+        pow_tab ct = crp_pow_table(e, s, c, D, d_ct);
+        LAUNCH(k_crp_pows, dim3((unsigned)((D + 255) / 256)), dim3(256), s, d_pw.as<sc_st>(), D, ct);
+        const msm_plan pl = msm_plan_for(D, 2);
+        dev_buf d_win(sizeof(p3_st) * pl.out_count(2), s);
+        msm_args a = {}; a.v[0].scalars = d_pw.as<sc_st>(); a.v[1].scalars = d_pw.as<sc_st>(); a.split = 1; a.T = (uint32_t)D; a.scalar_stride = 0; a.nseg = 1; a.out = d_win.as<p3_st>();
+        a.v[0].seg[0] = mk_seg(d_LR.as<p3_st>(), (uint32_t)D, 0, 1); a.v[1].seg[0] = mk_seg(d_LR.as<p3_st>() + D, (uint32_t)D, 0, 1);
+        run_msm(e, s, a, pl, 2);
+        fin_windows(f, d_win.as<p3_st>(), pl);
+        run_finalize(s, f);
+        int id[2], bad[2]; rt_d2h(id, d_id.p, sizeof(id), s); rt_d2h(bad, d_bad.p, sizeof(bad), s); rt_sync(s);
+        if (bad[0] || bad[1]) return -1;
+        return (id[0] && id[1]) ? 1 : 0;
+    }
+    run_finalize(s, f);
+    int id[2], bad[2]; rt_d2h(id, d_id.p, sizeof(id), s); rt_d2h(bad, d_bad.p, sizeof(bad), s); rt_sync(s);
+    if (bad[0]) return -1;
+    return (id[0] && id[1]) ? 1 : 0;
+}
+
+// =============================================================================================================================
 // commitments (pedersen_ops.rs:9-25; el_gamal.rs:57-69), aggregation (params.rs:81-124), discrete log (bsgs32.rs, pedersen_ops.rs:47-53)
 // =============================================================================================================================
 static int engine_commit(rofl_engine &e, const float *d_values, const uint8_t *d_blind, size_t D, int n_bits, int frac, uint8_t *d_L, uint8_t *d_R) {

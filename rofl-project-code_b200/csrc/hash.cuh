@@ -104,6 +104,13 @@ HD void transcript_append(transcript &t, const char *label, const uint8_t *msg, 
     strobe_meta_ad(t, len, 4, true);
     strobe_ad(t, msg, n, false);
 }
+// label given as raw bytes (the compressed rand proof labels its pairs with 3 arbitrary bytes, zeros included)
+HD void transcript_append_l(transcript &t, const uint8_t *label, size_t ll, const uint8_t *msg, size_t n) {
+    uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+    strobe_meta_ad(t, label, ll, false);
+    strobe_meta_ad(t, len, 4, true);
+    strobe_ad(t, msg, n, false);
+}
 HD void transcript_init(transcript &t, const char *label) {
     const uint8_t proto[11] = {'M', 'e', 'r', 'l', 'i', 'n', ' ', 'v', '1', '.', '0'};
     strobe_init(t, proto, 11);

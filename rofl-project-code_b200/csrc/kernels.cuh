@@ -1012,6 +1012,48 @@ KERNEL void LB(256, 1) k_l2_sums(sc_st *partial, const float *v, const uint8_t *
 KLAUNCH(k_l2_sums, true, (sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, int *flags), (partial, v, blind, D, n_bits, frac, flags))
 #endif
 
+// ===================================================================================================================
+// K9: compressed randomness proof (compressed_rand_proof/mod.rs:43-102, party.rs:90-100): one sigma proof over all D ElGamal pairs
+//   z_m = m' + sum_i m_i c^(i+1),  z_r = r' + sum_i r_i c^(i+1);  verify: commit(z_m, z_r) == C' + sum_i c^(i+1) (L_i, R_i)
+// ===================================================================================================================
+#ifdef KG_COMMIT
+// block partial sums of m_i c^(i+1) and r_i c^(i+1); ctab = split power table of c (chunk 0)
+KERNEL void LB(256, 1) k_crp_sums(sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, pow_tab ctab, int *flags) {
+    __shared__ sc_st buf[256];
+    int tid = threadIdx.x;
+    sc sm, sr; sc_0(sm); sc_0(sr);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < D; i += (size_t)gridDim.x * blockDim.x) {
+        sc m, r, pw, t; if (f32_to_scalar(m, v[i], n_bits, frac)) { atomicOr(flags, 1); continue; }
+        uint8_t b[32]; ld_bytes32(b, blind + 32 * i); sc_from_bytes_mod_order(r, b);
+        pow_tab_get(pw, ctab, 0, i + 1);
+        sc_mul(t, m, pw); sc_add(sm, sm, t); sc_mul(t, r, pw); sc_add(sr, sr, t);
+    }
+    block_sum_sc(sm, buf, tid, blockDim.x); block_sum_sc(sr, buf, tid, blockDim.x);
+    if (tid == 0) { st_sc(partial + 2 * blockIdx.x, sm); st_sc(partial + 2 * blockIdx.x + 1, sr); }
+}
+KLAUNCH(k_crp_sums, true, (sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, pow_tab ctab, int *flags), (partial, v, blind, D, n_bits, frac, ctab, flags))
+// out[i] = c^(i+1)
+KERNEL void LB(256, 2) k_crp_pows(sc_st *out, size_t D, pow_tab ctab) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    sc pw; pow_tab_get(pw, ctab, 0, i + 1); st_sc(out + i, pw);
+}
+KLAUNCH(k_crp_pows, false, (sc_st *out, size_t D, pow_tab ctab), (out, D, ctab))
+// pairs[i] = L[i] | R[i]  (64-byte wire form of an ElGamalPair, el_gamal.rs:105-111) and the reverse
+KERNEL void LB(256, 2) k_pairs_join(uint8_t *pairs, const uint8_t *L, const uint8_t *R, size_t D) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    uint8_t b[32]; ld_bytes32(b, L + 32 * i); st_bytes32(pairs + 64 * i, b); ld_bytes32(b, R + 32 * i); st_bytes32(pairs + 64 * i + 32, b);
+}
+KLAUNCH(k_pairs_join, false, (uint8_t *pairs, const uint8_t *L, const uint8_t *R, size_t D), (pairs, L, R, D))
+KERNEL void LB(256, 2) k_pairs_split(uint8_t *L, uint8_t *R, const uint8_t *pairs, size_t D) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    uint8_t b[32]; ld_bytes32(b, pairs + 64 * i); st_bytes32(L + 32 * i, b); ld_bytes32(b, pairs + 64 * i + 32); st_bytes32(R + 32 * i, b);
+}
+KLAUNCH(k_pairs_split, false, (uint8_t *L, uint8_t *R, const uint8_t *pairs, size_t D), (L, R, pairs, D))
+#endif
+
 // ---- launcher declarations (definitions live in the translation unit of each kernel group) ----------------------------
 void launch_k_fb_table_build(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *tab, const uint8_t *pt);
 void launch_k_gens_build(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *G, niels_st *H, int n, int party_begin, int party_end);
@@ -1041,6 +1083,10 @@ void launch_k_bsgs_solve(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out_sc, flo
 void launch_k_f32_to_scalar(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const float *v, size_t D, int n_bits, int frac, int *flags);
 void launch_k_scalar_to_f32(dim3 g_, dim3 b_, cudaStream_t s_, float *out, const uint8_t *in, size_t D, int n_bits, int frac);
 void launch_k_l2_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, int *flags);
+void launch_k_crp_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, pow_tab ctab, int *flags);
+void launch_k_crp_pows(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *out, size_t D, pow_tab ctab);
+void launch_k_pairs_join(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *pairs, const uint8_t *L, const uint8_t *R, size_t D);
+void launch_k_pairs_split(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *L, uint8_t *R, const uint8_t *pairs, size_t D);
 
 // ===================================================================================================================
 // RT path: per-generator radix-256 tables in HBM (512 KB per generator: 32 windows x 128 affine-Niels multiples).
