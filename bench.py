@@ -188,10 +188,12 @@ def main():
     clocks = sampler.stop()
     # ---- per-kernel breakdown: the same K resident steps again with CUDA events around every launch of the main kernel families
     # (separate pass: creating / recording the events costs host time that must not leak into `value`)
+    api.set_option("groups", 1)             # one chunk group: every kernel is timed ALONE on the GPU (two groups overlap kernels of different rounds)
     lib.rofl_prof_enable(1); lib.rofl_prof_reset()
     for it in range(args.steps):
         step_resident(300 + it)
     torch.cuda.synchronize()
+    api.set_option("groups", 2)
     prof = dict(fold_ms=lib.rofl_prof_ms(0), msm_ms=lib.rofl_prof_ms(1), commit_ms=lib.rofl_prof_ms(2), rt_ms=lib.rofl_prof_ms(4), tail_ms=lib.rofl_prof_ms(5),
                 rt_launches=lib.rofl_prof_launches(4), rt_madds=lib.rofl_prof_work(4))
     lib.rofl_prof_enable(0)

@@ -106,6 +106,15 @@ int rofl_l2_verify(rofl_ctx *, const uint8_t *proof, size_t proof_len, const uin
 
 /* ---- square_proof_vec::{create_l2rangeproof_vec_existing, verify_l2rangeproof_vec} (square_proof_vec/mod.rs:19-75,130-160).
  *      value_com32: D commitments c_l; r1/r2: D blindings each; out_proofs: D*160; out_commits: D*64 (c_l | c_sq). */
+/* compressed_rand_proof::CompressedRandProof::{helper_prove, helper_prove_existing, helper_verify} (compressed_rand_proof/mod.rs:134-158):
+ * ONE sigma proof that all D ElGamal pairs (L_i, R_i) = (m_i B + r_i H, r_i B) are well formed; also the call that materialises the
+ * R halves (party.rs:23-24,55-56).  value_com32 = the existing L_i (prove_existing) or NULL (L_i = commit(m_i, r_i)).
+ * proof128 = C'_L | C'_R | z_m | z_r (mod.rs:108-114), pairs64 = D x (L | R) (el_gamal.rs:105-111).
+ * prove: 0 ok, ROFL_ERR_POINT, -6 more than 900 000 pairs (the reference's label table ends there: it panics), ROFL_ERR_NAN.
+ * verify: 1 valid, 0 invalid, ROFL_ERR_FORMAT, -6. */
+int rofl_crp_prove(rofl_ctx *, const float *v, const uint8_t *value_com32, const uint8_t *blind32, size_t D, int n_bits, int frac, const uint8_t seed[32],
+                   uint8_t *out_proof128, uint8_t *out_pairs64);
+int rofl_crp_verify(rofl_ctx *, const uint8_t *proof128, const uint8_t *pairs64, size_t D);
 int rofl_square_prove(rofl_ctx *, const float *v, const uint8_t *value_com32, const uint8_t *r1_32, const uint8_t *r2_32, size_t D, int n_bits, int frac,
                       const uint8_t seed[32], uint8_t *out_proofs160, uint8_t *out_commits64);
 int rofl_square_prove_dev(rofl_ctx *, const float *v, const uint8_t *value_com32, const uint8_t *r1_32, const uint8_t *r2_32, size_t D, int n_bits, int frac,

@@ -155,6 +155,15 @@ def square_prove(values, value_com, r1, r2, n_bits=32, frac=7, seed=SEED0):
 def square_verify(proofs, commits):
     p = _u8(proofs).reshape(-1, 160); c = _u8(commits).reshape(-1, 64)
     return lib().orc_square_verify(_p(p), _p(c), C.c_size_t(p.shape[0]))
+def crp_prove(values, value_com, blind, n_bits=16, frac=7, seed=SEED0):
+    """CompressedRandProof::helper_prove (value_com None) / helper_prove_existing -> (rc, proof[128], pairs[D, 64])"""
+    v = _f32(values); D = v.size
+    proof = np.zeros(128, np.uint8); pairs = np.zeros((D, 64), np.uint8)
+    rc = lib().orc_crp_prove(_p(proof), _p(pairs), _p(v), None if value_com is None else _p(_u8(value_com, 32 * D)), _p(_u8(blind, 32 * D)), C.c_size_t(D), n_bits, frac, _p(_u8(seed, 32)))
+    return rc, proof, pairs
+def crp_verify(proof, pairs):
+    p = _u8(pairs).reshape(-1, 64)
+    return lib().orc_crp_verify(_p(_u8(proof, 128)), _p(p), C.c_size_t(p.shape[0]))
 def aggregate(pts, init=0):
     a = _u8(pts); assert a.ndim == 3 and a.shape[2] == 32
     o = np.zeros((a.shape[1], 32), np.uint8); rc = lib().orc_aggregate(_p(o), _p(a), C.c_size_t(a.shape[0]), C.c_size_t(a.shape[1]), init); assert rc == 0; return o

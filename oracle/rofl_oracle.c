@@ -318,6 +318,75 @@ EXPORT int orc_square_prove(uint8_t *proofs_out, uint8_t *commits_out, const flo
     }
     return rc;
 }
+/* CompressedRandProof (compressed_rand_proof/mod.rs:43-102, party.rs:17-100, dealer.rs:20-94, constants.rs:5-7):
+ * ONE sigma proof that every ElGamal pair (L_i, R_i) = (m_i B + r_i H, r_i B) of an update is well formed.
+ *   pairs_out: D*64 (L|R).  value_com = existing L_i (prove_existing, party.rs:17-45) or NULL (Party::new :50-79: L_i = commit(m_i, r_i)).
+ *   proof_out: 128 = C'_L | C'_R | z_m | z_r.   Transcript labels of the pairs: [3i, 3i+1, 3i+2] mod 256 (generate_unique_u8_triplets.py:9-13);
+ *   the label table has 900 000 rows, a longer update indexes past its end (panic) -> -6.  returns 0, -4 bad point, -2 bad args */
+#define CRP_MAX_D 900000
+static void crp_transcript(transcript *t, const uint8_t *pairs, size_t D, const uint8_t cprime[64], sc *c) {
+    transcript_init(t, "CompressedRandProof");                                                     /* mod.rs:137,144,153 */
+    transcript_append(t, "dom-sep", (const uint8_t *)"randomness proof v1", 19);                   /* rand_proof/transcript.rs:20-22 */
+    for (size_t i = 0; i < D; i++) {
+        uint8_t lab[3] = {(uint8_t)(3 * i), (uint8_t)(3 * i + 1), (uint8_t)(3 * i + 2)};
+        transcript_append_l(t, lab, 3, pairs + 64 * i, 64);                                        /* dealer.rs:27-29 */
+    }
+    transcript_append(t, "C_prime_eg", cprime, 64);                                                /* dealer.rs:53-54 */
+    ts_challenge(t, "c", c);
+}
+EXPORT int orc_crp_prove(uint8_t proof_out[128], uint8_t *pairs_out, const float *values, const uint8_t *value_com, const uint8_t *rv, size_t D,
+                         int n_bits, int frac, const uint8_t seed[32]) {
+    if (!fp_ok(n_bits, frac)) return -2;
+    if (D > CRP_MAX_D) return -6;
+    init_pc();
+    sc *m = malloc(sizeof(sc) * (D ? D : 1)), *r = malloc(sizeof(sc) * (D ? D : 1)); int rc = 0;
+    ge Bp; ge_base(&Bp);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < D; i++) {
+        ge Lp, Rp;
+        if (f32_to_scalar(&m[i], values[i], n_bits, frac)) { rc = -98; continue; }
+        sc_from_bytes_mod_order(&r[i], rv + 32 * i);
+        if (value_com) { if (!ge_decompress(&Lp, value_com + 32 * i)) { rc = -4; continue; } }
+        else pc_commit(&Lp, &PC, &m[i], &r[i]);
+        ge_scalarmult(&Rp, &r[i], &Bp);                                                            /* el_gamal.rs:57-69 */
+        ge_compress(pairs_out + 64 * i, &Lp); ge_compress(pairs_out + 64 * i + 32, &Rp);
+    }
+    if (!rc) {
+        uint8_t key[32]; orc_derive_key(key, seed, DOM_CRP, 0);
+        sc mp, rp, c, zm, zr, pw, t; ge Cl, Cr;
+        rng_scalar_at(key, 0, &mp); rng_scalar_at(key, 1, &rp);                                    /* party.rs:26-29 */
+        pc_commit(&Cl, &PC, &mp, &rp); ge_scalarmult(&Cr, &rp, &Bp);
+        ge_compress(proof_out, &Cl); ge_compress(proof_out + 32, &Cr);
+        transcript tr; crp_transcript(&tr, pairs_out, D, proof_out, &c);
+        zm = mp; zr = rp; pw = c;                                                                  /* party.rs:90-100: sum m_i c^(i+1) */
+        for (size_t i = 0; i < D; i++) { sc_mul(&t, &m[i], &pw); sc_add(&zm, &zm, &t); sc_mul(&t, &r[i], &pw); sc_add(&zr, &zr, &t); sc_mul(&pw, &pw, &c); }
+        sc_tobytes(proof_out + 64, &zm); sc_tobytes(proof_out + 96, &zr);
+    }
+    free(m); free(r);
+    return rc;
+}
+/* CompressedRandProof::verify (mod.rs:76-102) after from_bytes (:118-134): 1 valid, 0 invalid, -1 FormatError, -6 too long */
+EXPORT int orc_crp_verify(const uint8_t proof[128], const uint8_t *pairs, size_t D) {
+    if (D > CRP_MAX_D) return -6;
+    init_pc();
+    ge Cl, Cr, Bp; sc zm, zr, c; ge_base(&Bp);
+    if (!ge_decompress(&Cl, proof) || !ge_decompress(&Cr, proof + 32) || !sc_from_canonical_bytes(&zm, proof + 64) || !sc_from_canonical_bytes(&zr, proof + 96)) return -1;
+    ge *Lp = malloc(sizeof(ge) * (D ? D : 1)), *Rp = malloc(sizeof(ge) * (D ? D : 1)); sc *pw = malloc(sizeof(sc) * (D ? D : 1)); int bad = 0;
+    for (size_t i = 0; i < D; i++) if (!ge_decompress(&Lp[i], pairs + 64 * i) || !ge_decompress(&Rp[i], pairs + 64 * i + 32)) bad = 1;
+    int res = -1;
+    if (!bad) {
+        transcript tr; crp_transcript(&tr, pairs, D, proof, &c);
+        sc p = c; for (size_t i = 0; i < D; i++) { pw[i] = p; sc_mul(&p, &p, &c); }
+        ge SL, SR, lhsL, lhsR, T;
+        ge_msm(&SL, pw, Lp, D); ge_msm(&SR, pw, Rp, D);
+        ge_add(&SL, &SL, &Cl); ge_add(&SR, &SR, &Cr);                                              /* C' + sum c^(i+1) C_i */
+        pc_commit(&lhsL, &PC, &zm, &zr); ge_scalarmult(&lhsR, &zr, &Bp);                            /* eg_gens.commit(z_m, z_r) */
+        (void)T;
+        res = (ge_eq(&lhsL, &SL) && ge_eq(&lhsR, &SR)) ? 1 : 0;
+    }
+    free(Lp); free(Rp); free(pw);
+    return res;
+}
 /* verify_l2rangeproof_vec (square_proof_vec/mod.rs:130-160) -> SquareProof::verify (square_proof/mod.rs:77-112).
  * returns 1 true, 0 false, -1 FormatError (from_bytes :127-146, pedersen.rs:30-45) */
 EXPORT int orc_square_verify(const uint8_t *proofs, const uint8_t *commits, size_t D) {

@@ -34,6 +34,8 @@ _SIGS = {
     "rofl_range_verify_dev": (C.c_int, [c_vp, c_u8p, c_sz, c_sz, c_u8p, c_sz, C.c_int, c_u8p]),
     "rofl_l2_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, C.c_int, C.c_int, c_u8p, c_u8p, C.POINTER(c_sz), c_u8p]),
     "rofl_l2_verify": (C.c_int, [c_vp, c_u8p, c_sz, c_u8p, C.c_int, c_u8p]),
+    "rofl_crp_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p]),
+    "rofl_crp_verify": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz]),
     "rofl_square_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_u8p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p]),
     "rofl_square_prove_dev": (C.c_int, [c_vp, c_f32p, c_u8p, c_u8p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p]),
     "rofl_square_verify": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz]),
@@ -112,6 +114,20 @@ class Api:
         if rc != 0:
             raise self._err(rc)
         return out
+
+    # ---- compressed randomness proof: (rc, proof[128], pairs[D, 64]) / 1|0|<0
+    def crp_prove(self, v, value_com, blind, n_bits, frac, seed=SEED0):
+        v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
+        proof = np.zeros(128, np.uint8); pairs = np.zeros((max(D, 1), 64), np.uint8)
+        vc = None if value_com is None else _u8(value_com, 32 * D)
+        rc = self.lib.rofl_crp_prove(self.h, _ptr(v), _ptr(vc), _ptr(b), D, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proof), _ptr(pairs))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc, proof, pairs[:D]
+    def crp_verify(self, proof, pairs):
+        p = _u8(pairs).reshape(-1, 64)
+        rc = self.lib.rofl_crp_verify(self.h, _ptr(_u8(proof, 128)), _ptr(p), p.shape[0])
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc
 
     def set_option(self, name, value):
         rc = self.lib.rofl_set_option(self.h, name.encode(), int(value))

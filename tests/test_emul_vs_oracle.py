@@ -165,3 +165,27 @@ def test_generator_table_radix(api, oracle, bits):
         assert api.range_verify(p, cm, rngbits, seed) == 1
     finally:
         api.set_option("rt_bits", 8); api.set_option("tail_np", 32)
+
+
+def test_compressed_rand_proof(api, oracle):
+    """compressed_rand_proof (one sigma proof over all ElGamal pairs): bytes, R halves, existing-commitment mode, tamper and format rejection."""
+    rng = np.random.default_rng(21)
+    for D in (1, 9, 300):                      # 300 > 256: the 3-byte pair labels wrap around (generate_unique_u8_triplets.py:9-13)
+        v = rng.uniform(-3, 3, D).astype(np.float32)
+        bl = oracle.rnd_scalar_vec(b"\x61" * 32, D)
+        seed = bytes([D % 251] * 32)
+        rc_o, pf_o, pairs_o = oracle.crp_prove(v, None, bl, 16, 7, seed)
+        rc, pf, pairs = api.crp_prove(v, None, bl, 16, 7, seed)
+        assert rc == rc_o == 0 and (pf == pf_o).all() and (pairs == pairs_o).all()
+        assert (pairs[:, 32:] == oracle.elgamal_R(bl)).all()
+        assert api.crp_verify(pf, pairs) == 1 and oracle.crp_verify(pf, pairs) == 1
+        rc2, pf2, pairs2 = api.crp_prove(v, pairs[:, :32].copy(), bl, 16, 7, seed)            # prove_existing
+        assert rc2 == 0 and (pf2 == pf).all() and (pairs2 == pairs).all()
+        if D > 1:
+            bad = pairs.copy(); bad[D // 2, 32:] = pairs[0, 32:]
+            assert api.crp_verify(pf, bad) == 0 and oracle.crp_verify(pf, bad) == 0
+    badp = pf.copy(); badp[64:96] = 0xff
+    assert api.crp_verify(badp, pairs) == -1 and oracle.crp_verify(badp, pairs) == -1
+    badc = pairs.copy(); badc[1, :32] = 0xff
+    assert api.crp_verify(pf, badc) == -1 and oracle.crp_verify(pf, badc) == -1
+    assert api.crp_prove(v, badc[:, :32].copy(), bl, 16, 7, seed)[0] == -4

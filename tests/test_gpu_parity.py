@@ -193,3 +193,26 @@ def test_full_size_round_trip_cifar_lenet5(api, oracle):
     # determinism: same seed -> same bytes
     rc, p2, c2 = api.range_prove(v, bl, 16, 64, 16, 7, b"\x51" * 32)
     assert (p2 == p).all() and (c2 == c).all()
+
+
+def test_compressed_rand_proof_parity_and_full_size(api, oracle):
+    """compressed_rand_proof: byte parity with the oracle at a size it finishes quickly, then configs[2]'s 50 000 pairs on the
+    GPU alone (prove -> verify, tamper rejection) -- the verifier is one 2 x 50 000-term MSM sharing its challenge-power scalars."""
+    rng = np.random.default_rng(31)
+    D = 700
+    v = rng.uniform(-3, 3, D).astype(np.float32); bl = oracle.rnd_scalar_vec(b"\x62" * 32, D); seed = bytes([4] * 32)
+    rc_o, pf_o, pairs_o = oracle.crp_prove(v, None, bl, 16, 7, seed)
+    rc, pf, pairs = api.crp_prove(v, None, bl, 16, 7, seed)
+    assert rc == rc_o == 0 and (pf == pf_o).all() and (pairs == pairs_o).all()
+    assert api.crp_verify(pf, pairs) == 1 and oracle.crp_verify(pf, pairs) == 1
+    D = 50000
+    v = (rng.integers(-24, 25, D) / 128).astype(np.float32); bl = api.rnd_scalar_vec(b"\x63" * 32, D)
+    L_ = api.commit(v, bl, 32, 7)
+    rc, pf, pairs = api.crp_prove(v, L_, bl, 32, 7, seed)                 # prove_existing, as the service does (params.rs:729-735)
+    assert rc == 0 and (pairs[:, :32] == L_).all()
+    assert api.crp_verify(pf, pairs) == 1
+    bad = pairs.copy(); bad[D - 1, 32:] = pairs[0, 32:]
+    assert api.crp_verify(pf, bad) == 0
+    badp = pf.copy(); badp[97] ^= 1
+    assert api.crp_verify(badp, pairs) in (0, -1)
+    assert api.crp_prove(np.zeros(900001, np.float32), None, np.zeros((900001, 32), np.uint8), 16, 7, seed)[0] == -6

@@ -107,6 +107,13 @@ def main():
     prot["l2"] = {"values": [float(x) for x in vals], "r1_seed": "33" * 32, "r2_seed": "34" * 32, "seed": "09" * 32, "range_bits": 32, "n_bits": 32, "frac": 7,
                   "proof": np.asarray(pf).tobytes().hex(), "commit": bytes(cm).hex() if not isinstance(cm, np.ndarray) else cm.tobytes().hex(),
                   "square_proofs": np.asarray(sp).tobytes().hex(), "square_commits": np.asarray(sc).tobytes().hex()}
+    # compressed randomness proof (one sigma proof over all ElGamal pairs)
+    D = 10
+    r3 = np.random.default_rng(77)
+    vals = r3.uniform(-3, 3, D).astype(np.float32); blind = oracle.rnd_scalar_vec(b"\x64" * 32, D)
+    rc, pf, pairs = oracle.crp_prove(vals, None, blind, 16, 7, bytes([6]) * 32); assert rc == 0 and oracle.crp_verify(pf, pairs) == 1
+    prot["crp"] = {"values": [float(x) for x in vals], "blind_seed": "64" * 32, "seed": "06" * 32, "n_bits": 16, "frac": 7,
+                   "proof": np.asarray(pf).tobytes().hex(), "pairs": np.asarray(pairs).tobytes().hex()}
     # aggregate + discrete log
     x = np.array([[0.25, 1.25, -1.5, 100.5], [-0.75, 1.25, -2.0, 27.25], [0.5, 1.25, -3.0, 0.0078125]], np.float32)
     cs = np.stack([oracle.commit_f32(r, None, 16, 7) for r in x])
