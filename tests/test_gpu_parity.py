@@ -216,3 +216,100 @@ def test_compressed_rand_proof_parity_and_full_size(api, oracle):
     badp = pf.copy(); badp[97] ^= 1
     assert api.crp_verify(badp, pairs) in (0, -1)
     assert api.crp_prove(np.zeros(900001, np.float32), None, np.zeros((900001, 32), np.uint8), 16, 7, seed)[0] == -6
+
+
+@pytest.mark.parametrize("P", [64, 4])
+def test_config0_mnist_5k_full_size_byte_parity(api, oracle, P):
+    """BASELINE.json configs[0] at its real size (5 000 params, 8-bit, 1 client; P = 64 as in mnist_e2e.yml and P = 4 as in the reference's
+    own bench): the oracle proves it in seconds, so the comparison is byte for byte on all proofs and commitments."""
+    rng = np.random.default_rng(3)
+    D = 5000
+    mn, mx = oracle.clip_bounds(8, 16, 7)
+    v = rng.uniform(mn, mx, D).astype(np.float32)
+    bl = oracle.rnd_scalar_vec(b"\x53" * 32, D)
+    seed = b"\x54" * 32
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, 8, P, 16, 7, seed)
+    rc, p, c = api.range_prove(v, bl, 8, P, 16, 7, seed)
+    assert rc == rc_o == 0 and (c == c_o).all() and p.shape == p_o.shape and (p == p_o).all()
+    assert api.range_verify(p, c, 8, seed) == 1 and oracle.range_verify(p, c, 8, seed) == 1
+
+
+def test_config2_resnet18_intrinsic_50k_l2_pipeline(api, oracle):
+    """BASELINE.json configs[2]: 50 000 params, L2 bound = per-element square proofs + ONE 32-bit range proof on the sum of squares, plus the
+    8-bit L-inf range proofs.  Sum proof: byte parity with the oracle (it is O(D) scalar work there).  Square proofs: byte parity on a
+    prefix, then full-size verification, homomorphic consistency (sum of the square commitments == the L2 commitment) and tamper rejection."""
+    rng = np.random.default_rng(4)
+    D = 50000
+    v = (rng.integers(-24, 25, D) / 128).astype(np.float32)               # SURVEY 8d: keeps the reference's f32 cross-check exact
+    r1 = api.rnd_scalar_vec(b"\x55" * 32, D); r2 = api.rnd_scalar_vec(b"\x56" * 32, D); seed = b"\x57" * 32
+    rc, pf, cm = api.l2_prove(v, r2, 32, 32, 7, seed)
+    rc_o, pf_o, cm_o = oracle.l2_prove(v, r2, 32, 32, 7, seed)
+    assert rc == rc_o == 0 and (pf == pf_o).all() and (np.asarray(cm) == np.asarray(cm_o)).all()
+    assert api.l2_verify(pf, cm, 32, seed) == 1 and oracle.l2_verify(pf, cm, 32, seed) == 1
+    cl = api.commit(v, r1, 32, 7)
+    rc, sp, sc = api.square_prove(v, cl, r1, r2, 32, 7, seed)
+    assert rc == 0 and api.square_verify(sp, sc) == 1
+    k = 300
+    rc_o, sp_o, sc_o = oracle.square_prove(v[:k], cl[:k], r1[:k], r2[:k], 32, 7, seed)
+    assert rc_o == 0 and (sp[:k] == sp_o).all() and (sc[:k] == sc_o).all()
+    # sum_i c_sq,i == commitment of the sum proof (same value sum x_i^2, same blinding sum r2_i): the link the server relies on (params.rs:81-124)
+    agg = api.aggregate(sc[:, 32:].reshape(D, 1, 32).copy(), 0)            # D "clients" x 1 point: sums all square commitments
+    assert (agg[0] == np.asarray(cm)).all()
+    bad = sp.copy(); bad[D - 7, 64] ^= 1
+    assert api.square_verify(bad, sc) in (0, -1)
+    mn, mx = oracle.clip_bounds(8, 32, 7)
+    assert mn <= v.min() and v.max() <= mx
+    rc, p, c = api.range_prove(v, r1, 8, 64, 32, 7, seed)
+    assert rc == 0 and api.range_verify(p, c, 8, seed) == 1 and (c == cl).all()
+
+
+def test_config3_resnet18_full_one_gpu_share_of_eight(api, oracle):
+    """BASELINE.json configs[3]: 11 689 512 params, 8-bit, 64 chunks of 2^18 values sharded over 8 GPUs.  This is the work of ONE of the
+    eight ranks (8 chunks = 2^21 values, 2^24 bit positions, no generator tables at this size: bucket MSMs and folds), through the
+    shard entry points; a spot chunk of the commitments is compared with the oracle and a tampered shard is rejected."""
+    from importlib import import_module
+    D, P = 11689512, 64
+    m = (1 << 24) // P
+    rank, world = 5, 8
+    c0, n_chunks = rank * (P // world), P // world
+    e0, e1 = c0 * m, min(D, (c0 + n_chunks) * m)
+    rng = np.random.default_rng(6)
+    v = rng.uniform(-0.99, 0.99, e1 - e0).astype(np.float32)
+    bl = api.rnd_scalar_vec(b"\x58" * 32, e1 - e0)
+    seed = b"\x59" * 32
+    rc, p, c = api.range_prove_shard(v, bl, m, c0, n_chunks, 8, 16, 7, seed)
+    assert rc == 0 and p.shape == (n_chunks, 32 * (9 + 2 * 21)) and c.shape == (e1 - e0, 32)
+    assert api.range_verify_shard(p, c, m, c0, 8, seed) == 1
+    assert (c[:1000] == oracle.commit_f32(v[:1000], bl[:1000], 16, 7)).all()
+    bad = c.copy(); bad[123456] = c[123457]
+    assert api.range_verify_shard(p, bad, m, c0, 8, seed) == 0
+
+
+def test_config4_server_batch_verify_aggregate_decrypt(api, oracle):
+    """BASELINE.json configs[4] (server side) with 6 of the 48 clients: verify every client's proofs, aggregate the ElGamal halves with
+    cancelling blindings, decrypt with the 2^16 table; the decrypted aggregate must equal the exact sum of the quantised inputs."""
+    rng = np.random.default_rng(7)
+    n_clients, D = 6, 50000
+    vs = [(rng.integers(-24, 25, D) / 128).astype(np.float32) for _ in range(n_clients)]
+    bls = [np.frombuffer(api.rnd_scalar_vec(bytes([0x70 + k]) * 32, D).tobytes(), np.uint8).reshape(D, 32).copy() for k in range(n_clients - 1)]
+    # last client's blindings cancel the others (pedersen_ops.rs:110-122): r_last = -sum r_k mod l
+    Lmod = L
+    tot = np.zeros(D, dtype=object)
+    for b in bls:
+        tot = (tot + np.array([int.from_bytes(row.tobytes(), "little") for row in b], dtype=object)) % Lmod
+    last = np.frombuffer(b"".join(int((Lmod - t) % Lmod).to_bytes(32, "little") for t in tot), np.uint8).reshape(D, 32).copy()
+    bls.append(last)
+    Ls, Rs = [], []
+    for k in range(n_clients):
+        seed = bytes([0x80 + k]) * 32
+        rc, p, c = api.range_prove(vs[k], bls[k], 8, 64, 32, 7, seed)
+        assert rc == 0 and api.range_verify(p, c, 8, seed) == 1
+        rc, pf, pairs = api.crp_prove(vs[k], c, bls[k], 32, 7, seed)
+        assert rc == 0 and api.crp_verify(pf, pairs) == 1
+        Ls.append(pairs[:, :32].copy()); Rs.append(pairs[:, 32:].copy())
+    aggL = api.aggregate(np.stack(Ls), 1); aggR = api.aggregate(np.stack(Rs), 1)            # accumulators start at (B, B) (el_gamal.rs:83-88)
+    B = np.frombuffer(oracle.basepoint(), np.uint8)
+    assert (aggR == B).all()                                                                   # blindings cancelled: right halves are the unity element
+    rc, s, f = api.dlog(api.aggregate(np.stack(Ls), 0), 1 << 16, 16, 32, 7)
+    assert rc == 0
+    assert (f == np.sum(np.stack(vs), axis=0, dtype=np.float64).astype(np.float32)).all()
