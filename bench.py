@@ -77,6 +77,7 @@ class ClockSampler:
 def cpu_reference_run(steps, warmup, sample_chunks=None):
     """CPU restatement of the reference on a bounded sample: `cores` chunks of the real chunk size (1024 values, 16 bit)."""
     import oracle
+    oracle.set_num_threads(os.cpu_count() or 1)          # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses all host threads it can
     cores = oracle.num_threads()
     w = WORKLOAD
     Dp = 1 << (w["D"] - 1).bit_length()

@@ -6,13 +6,15 @@
 
 struct rofl_ctx { rofl_engine e; };
 static thread_local std::string g_last_error;
-#define API_TRY try {
+// every entry point may be called from any host thread: bind that thread to the context's GPU first
+#define API_TRY try { if (c) rt_set_device(c->e.device);
 #define API_CATCH } catch (const std::exception &ex) { g_last_error = ex.what(); return ROFL_ERR_CUDA; }
 
 extern "C" const char *rofl_last_error(void) { return g_last_error.c_str(); }
 extern "C" void rofl_set_host_threads(rofl_ctx *c, int n) { if (c && n > 0) c->e.host_threads = n; }
 extern "C" int rofl_set_option(rofl_ctx *c, const char *name, long value) {
     if (!c || !name) return ROFL_ERR_ARGS;
+    try { rt_set_device(c->e.device); } catch (...) { return ROFL_ERR_CUDA; }
     std::lock_guard<std::mutex> lk(c->e.mu);
     std::string n(name);
     if (n == "use_rt") c->e.use_rt = value != 0;
@@ -23,6 +25,7 @@ extern "C" int rofl_set_option(rofl_ctx *c, const char *name, long value) {
         rt_sync(c->e.stream);
         for (auto &g : c->e.gens) { rt_free(g.second.RTG, c->e.stream); rt_free(g.second.RTH, c->e.stream); g.second.RTG = g.second.RTH = nullptr; g.second.rt_cap = 0; }
     }
+    else if (n == "frozen") c->e.use_frz = value != 0;
     else if (n == "tail_np") c->e.tail_np = (int)std::max<long>(0, std::min<long>(TAIL_MAX_F / 2, value));
     else return ROFL_ERR_ARGS;
     return ROFL_OK;

@@ -15,7 +15,7 @@
 #include <algorithm>
 
 enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE = 4, DOM_L2_VERIFY = 5, DOM_CRP = 6, DOM_RND_VEC = 7 };
-enum { PROF_FOLD = 0, PROF_MSM = 1, PROF_COMMIT = 2, PROF_SQUARE = 3, PROF_RTMSM = 4, PROF_TAIL = 5, PROF_SLOTS = 8 };
+enum { PROF_FOLD = 0, PROF_MSM = 1, PROF_COMMIT = 2, PROF_SQUARE = 3, PROF_RTMSM = 4, PROF_TAIL = 5, PROF_FRZ = 6, PROF_SLOTS = 8 };
 
 struct gens_entry { int n = 0; int cap = 0; niels_st *G = nullptr, *H = nullptr;
                     int rt_cap = 0, rt_c = 8; niels_st *RTG = nullptr, *RTH = nullptr; };     // radix-2^rt_c tables (RT path)
@@ -35,6 +35,7 @@ struct rofl_engine {
     int rt_unfold = 4;                    // IPP rounds computed over the original generators before the catch-up fold
     int tail_np = 32;                     // IPP rounds with half-size <= tail_np run in the fused on-device tail kernel (0 = off)
     std::mutex pin_mu; std::vector<std::pair<void *, size_t>> pins;      // pool of pinned host blocks for the per-round exchanges
+    int use_frz = 1;                      // middle IPP rounds over frozen generators with on-the-fly Straus tables (kernels.cuh K6c)
     int rt_bits = 10;                     // widest generator-table radix to try (8..10)
     double rt_mem_frac = 0.45;            // tables may take this fraction of the free device memory
 };
@@ -367,9 +368,45 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     dev_buf d_cGH(sizeof(sc_st) * 2 * (size_t)C * cstride, s), d_partU(sizeof(p3_st) * 2 * (size_t)C * nbU, s), d_digs(sizeof(int16_t) * 2 * (size_t)C * cstride * RT_MAXW, s);
     const int nbQ = (int)std::min<size_t>(256, (N / 2 + 255) / 256);
     dev_buf d_partQ(sizeof(sc_st) * 2 * (size_t)C * nbQ, s);
+    // frozen level (kernels.cuh K6c): rounds ra .. pre-1 run over the generators as they are at round ra (FA of G" and of H" per chunk)
+    int ra = -1; size_t FA = 0; uint32_t cAstride = 1;
+    if (e.use_frz) {
+        int r = std::max(r_unf, 1);
+        while (r < pre && 2 * ((N / 2) >> r) > FRZ_MAX_F) r++;
+        const size_t fa = r < lgN ? 2 * ((N / 2) >> r) : 0;
+        const double need = (double)C * 2 * fa * FRZ_Q * (FRZ_E + 1) * sizeof(p3_st);
+        if (pre - r >= 2 && fa >= 4 && need < 0.25 * (double)rt_free_mem()) { ra = r; FA = fa; cAstride = (uint32_t)(FA / ((N / 2) >> (pre - 1))); }
+    }
+    std::vector<sc> cAG((size_t)C * cAstride), cAH((size_t)C * cAstride);
+    std::vector<sc_st> h_cA(2 * (size_t)C * cAstride);
+    for (int c = 0; c < C; c++) { sc_from_u64(cAG[(size_t)c * cAstride], 1); sc_from_u64(cAH[(size_t)c * cAstride], 1); }
+    dev_buf d_cA(sizeof(sc_st) * 2 * (size_t)C * cAstride, s), d_frzT(ra >= 0 ? sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q * FRZ_E : 16, s), d_frzV(sizeof(p3_st) * 2 * (size_t)C * 8, s);
     int round = 0;
     bool tail_done = false;
     for (size_t np = N / 2; np >= 1; np /= 2, round++) {
+        if (round == ra) {           // enter the frozen level: Straus tables of the current G", H"
+            dev_buf d_bases(sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q, s);
+            void *tk = rt_prof_begin(PROF_FRZ, s);
+            LAUNCH(k_frz_bases, dim3((unsigned)((2 * FA + 127) / 128), C), dim3(128), s, d_bases.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), (uint32_t)FA, (uint32_t)half);
+            const size_t cnt = (size_t)C * 2 * FA * FRZ_Q;
+            LAUNCH(k_frz_tables, dim3((unsigned)((cnt + 127) / 128)), dim3(128), s, d_frzT.as<p3_st>(), d_bases.as<p3_st>(), cnt);
+            rt_prof_end(PROF_FRZ, tk, s);
+        }
+        const bool frozen = ra >= 0 && round >= ra;
+        if (round == pre && frozen) {       // leave the frozen level: the 2*np generators the tail starts from, straight from the tables
+            const uint32_t nblk = (uint32_t)(FA / (2 * np));
+            std::vector<int8_t> h_dg(2 * (size_t)C * nblk * 64);
+            for (int c = 0; c < C; c++) for (uint32_t t = 0; t < nblk; t++) {
+                sc_radix16(&h_dg[(((size_t)c * 2 + 0) * nblk + t) * 64], cAG[(size_t)c * cAstride + t]);
+                sc_radix16(&h_dg[(((size_t)c * 2 + 1) * nblk + t) * 64], cAH[(size_t)c * cAstride + t]);
+            }
+            dev_buf d_dg(h_dg.size(), s); rt_h2d(d_dg.p, h_dg.data(), h_dg.size(), s);
+            frz_exit_args xa = {}; xa.T = d_frzT.as<p3_st>(); xa.digs = d_dg.as<int8_t>(); xa.Gf = d_Gf.as<p3_st>(); xa.Hf = d_Hf.as<p3_st>();
+            xa.F = (uint32_t)FA; xa.Fo = (uint32_t)(2 * np); xa.nblk = nblk; xa.stride = (uint32_t)half;
+            void *tk = rt_prof_begin(PROF_FRZ, s);
+            LAUNCH_COOP(k_frz_exit, dim3((unsigned)(2 * np), C, 2), dim3(128), s, xa);
+            rt_prof_end(PROF_FRZ, tk, s);
+        }
         if (round == pre) {          // np <= tail_np: every remaining round in one launch (kernels.cuh, k_ipp_tail)
             const int rounds_left = lgN - round; const uint32_t ostride = 64 * (uint32_t)rounds_left + 64;
             std::vector<sc_st> h_up(2 * (size_t)C);
@@ -393,12 +430,26 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         }
         const int nbI = (int)std::min<size_t>(256, (np + 255) / 256);
         const bool unfolded = round < r_unf;
-        if (unfolded) {
+        if (frozen) {
+            const uint32_t nblk = (uint32_t)(FA / (2 * np)); const int nbQA = (int)std::min<size_t>(256, (FA / 2 + 255) / 256);
+            for (int c = 0; c < C; c++) for (uint32_t t = 0; t < nblk; t++) { sc_to_st(h_cA[(size_t)c * cAstride + t], cAG[(size_t)c * cAstride + t]); sc_to_st(h_cA[((size_t)C + c) * cAstride + t], cAH[(size_t)c * cAstride + t]); }
+            rt_h2d(d_cA.p, h_cA.data(), sizeof(sc_st) * h_cA.size(), s);
+            LAUNCH_COOP(k_ipp_scalars_unf, dim3(nbQA, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), d_cA.as<sc_st>(), d_cA.as<sc_st>() + (size_t)C * cAstride, cAstride,
+                        msmL, msmR, d_partQ.as<sc_st>(), N, (uint32_t)np, (uint32_t)FA);
+            LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_partQ.as<sc_st>(), nbQA, 2);
+            frz_reduce_args ra_ = {}; ra_.T = d_frzT.as<p3_st>(); ra_.msmL = msmL; ra_.msmR = msmR; ra_.V = d_frzV.as<p3_st>(); ra_.F = (uint32_t)FA; ra_.np = (uint32_t)np; ra_.C = (uint32_t)C;
+            void *tk = rt_prof_begin(PROF_FRZ, s);
+            LAUNCH_COOP(k_frz_reduce, dim3(8, 2 * C), dim3(128), s, ra_);
+            rt_prof_end(PROF_FRZ, tk, s);
+            finalize_args f = {}; f.windows = d_frzV.as<p3_st>(); f.c = 4; f.nw = 8; f.slices = 1; f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
+            f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
+            run_finalize(s, f);
+        } else if (unfolded) {
             const uint32_t nblk = 1u << round;
             for (int c = 0; c < C; c++) for (uint32_t t = 0; t < nblk; t++) { sc_to_st(h_cGH[(size_t)c * cstride + t], cG[(size_t)c * cstride + t]); sc_to_st(h_cGH[((size_t)C + c) * cstride + t], cH[(size_t)c * cstride + t]); }
             rt_h2d(d_cGH.p, h_cGH.data(), sizeof(sc_st) * h_cGH.size(), s);
             LAUNCH_COOP(k_ipp_scalars_unf, dim3(nbQ, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), d_cGH.as<sc_st>(), d_cGH.as<sc_st>() + (size_t)C * cstride, cstride,
-                        msmL, msmR, d_partQ.as<sc_st>(), N, (uint32_t)np, nblk);
+                        msmL, msmR, d_partQ.as<sc_st>(), N, (uint32_t)np, (uint32_t)N);
             LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_partQ.as<sc_st>(), nbQ, 2);
             rt_msm_args aL = {}; aL.scalars = msmL; aL.T = (uint32_t)N; aL.scalar_stride = (uint32_t)N; aL.nG = (uint32_t)(N / 2); aL.np = (uint32_t)np; aL.mode = 1; aL.rt = *rt; aL.partial = d_partU.as<p3_st>();
             rt_msm_args aR = aL; aR.scalars = msmR; aR.mode = 2; aR.partial = d_partU.as<p3_st>() + (size_t)C * nbU;
@@ -441,7 +492,10 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             sc_mul(u2, u[c], u[c]); sc_mul(ui2, uinv[c], uinv[c]);
             st_to_sc(yp, h_yinvpow2[32 * c + lgnp]); sc_mul(sH, ui2, yp);            // u^-2 y^-np
             sc_to_st(h_u2[c], u2); sc_to_st(h_uinv2[c], ui2);
-            if (unfolded) {       // coefficient tables of the next level: c'[2t] = c[t], c'[2t+1] = c[t] * s
+            if (frozen) {
+                const uint32_t nblk = (uint32_t)(FA / (2 * np)); sc *g0 = &cAG[(size_t)c * cAstride], *h0 = &cAH[(size_t)c * cAstride];
+                if (2 * nblk <= cAstride) for (uint32_t t = nblk; t-- > 0;) { sc gt = g0[t], ht = h0[t]; g0[2 * t] = gt; sc_mul(g0[2 * t + 1], gt, u2); h0[2 * t] = ht; sc_mul(h0[2 * t + 1], ht, sH); }
+            } else if (unfolded) {       // coefficient tables of the next level: c'[2t] = c[t], c'[2t+1] = c[t] * s
                 const uint32_t nblk = 1u << round; sc *g0 = &cG[(size_t)c * cstride], *h0 = &cH[(size_t)c * cstride];
                 for (uint32_t t = nblk; t-- > 0;) { sc gt = g0[t], ht = h0[t]; g0[2 * t] = gt; sc_mul(g0[2 * t + 1], gt, u2); h0[2 * t] = ht; sc_mul(h0[2 * t + 1], ht, sH); }
             } else { sc_naf(&h_nafs[512 * c], u2, FOLD_W); sc_naf(&h_nafs[512 * c + 256], sH, FOLD_W); }
@@ -449,7 +503,9 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         }
         rt_h2d(d_u2.p, h_u2.data(), sizeof(sc_st) * C, s); rt_h2d(d_uinv2.p, h_uinv2.data(), sizeof(sc_st) * C, s);
         LAUNCH(k_ipp_fold_scalars, dim3((unsigned)((np + 255) / 256), C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_u2.as<sc_st>(), d_uinv2.as<sc_st>(), N, (uint32_t)np);
-        if (unfolded) {
+        if (frozen) {
+            // nothing to fold: the generators stay frozen, only the coefficient tables grew
+        } else if (unfolded) {
             if (round + 1 == r_unf && np >= 2) {          // catch-up: G", H" of length np straight from the tables
                 const uint32_t nblk = 1u << r_unf;
                 std::vector<int16_t> h_digs(2 * (size_t)C * nblk * RT_MAXW);
@@ -492,7 +548,7 @@ template <class F> static void for_chunk_groups(rofl_engine &e, size_t C, F f) {
     if (G == 1) { f(0, (size_t)0, C, e.stream); return; }
     std::vector<std::thread> th; std::vector<std::string> errs(G);
     for (size_t gi = 0; gi < G; gi++) th.emplace_back([&, gi] {
-        try { f(gi, C * gi / G, C * (gi + 1) / G, e.gstreams[gi]); } catch (const std::exception &ex) { errs[gi] = ex.what(); }
+        try { rt_set_device(e.device); f(gi, C * gi / G, C * (gi + 1) / G, e.gstreams[gi]); } catch (const std::exception &ex) { errs[gi] = ex.what(); }
     });
     for (auto &t : th) t.join();
     for (auto &m : errs) if (!m.empty()) throw std::runtime_error(m);

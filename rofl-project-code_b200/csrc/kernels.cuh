@@ -1182,12 +1182,14 @@ void launch_k_rt_msm(dim3 g_, dim3 b_, cudaStream_t s_, rt_msm_args a);
 //   msmL / msmR: [c][N] scalars laid out for k_rt_msm modes 1 / 2 (N/2 G-terms then N/2 H-terms, term q = t*np + i)
 #ifdef KG_SCALAR
 KERNEL void LB(256, 1) k_ipp_scalars_unf(const sc_st *a, const sc_st *b, const sc_st *yinv, const sc_st *cG, const sc_st *cH, uint32_t cstride,
-                                         sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np, uint32_t nblk) {
+                                         sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np, uint32_t live) {
+    // N = stride of a / b / yinv per chunk; live = number of base points the round is expressed over (N for the original generators,
+    // F for a frozen level): msmL / msmR are [c][live]
     __shared__ sc_st buf[256];
     int c = blockIdx.y, tid = threadIdx.x;
     const sc_st *ac = a + (size_t)c * N, *bc = b + (size_t)c * N, *yc = yinv + (size_t)c * N;
-    sc_st *L = msmL + (size_t)c * N, *R = msmR + (size_t)c * N;
-    const uint32_t half = (uint32_t)(N / 2);
+    sc_st *L = msmL + (size_t)c * live, *R = msmR + (size_t)c * live;
+    const uint32_t half = live / 2;
     sc cL, cR; sc_0(cL); sc_0(cR);
     for (uint32_t q = blockIdx.x * blockDim.x + tid; q < half; q += gridDim.x * blockDim.x) {
         uint32_t t = q / np, i = q % np;
@@ -1200,12 +1202,11 @@ KERNEL void LB(256, 1) k_ipp_scalars_unf(const sc_st *a, const sc_st *b, const s
         sc_mul(x, ahi, g); st_sc(R + q, x);
         sc_mul(x, blo, yhi); sc_mul(x, x, h); st_sc(R + half + q, x);
     }
-    (void)nblk;
     block_sum_sc(cL, buf, tid, blockDim.x); block_sum_sc(cR, buf, tid, blockDim.x);
     if (tid == 0) { sc_st *o = partial + ((size_t)c * gridDim.x + blockIdx.x) * 2; st_sc(o, cL); st_sc(o + 1, cR); }
 }
-KLAUNCH(k_ipp_scalars_unf, true, (const sc_st *a, const sc_st *b, const sc_st *yinv, const sc_st *cG, const sc_st *cH, uint32_t cstride, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np, uint32_t nblk),
-        (a, b, yinv, cG, cH, cstride, msmL, msmR, partial, N, np, nblk))
+KLAUNCH(k_ipp_scalars_unf, true, (const sc_st *a, const sc_st *b, const sc_st *yinv, const sc_st *cG, const sc_st *cH, uint32_t cstride, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np, uint32_t live),
+        (a, b, yinv, cG, cH, cstride, msmL, msmR, partial, N, np, live))
 #endif
 // catch-up fold after r unfolded rounds: out[c][i] = sum_{t < nblk} coef[t] * Gen[t*nr + i], i < nr = N >> r, through the RT tables.
 //   digits[((c*2 + which)*nblk + t)*32 + w] = radix-256 signed digits of the coefficient (host-computed, uniform per chunk)
@@ -1233,5 +1234,104 @@ KERNEL void LB(128, 4) k_rt_catchup(catchup_args a) {
 }
 KLAUNCH(k_rt_catchup, true, (catchup_args a), (a))
 #endif
-void launch_k_ipp_scalars_unf(dim3 g_, dim3 b_, cudaStream_t s_, const sc_st *a, const sc_st *b, const sc_st *yinv, const sc_st *cG, const sc_st *cH, uint32_t cstride, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np, uint32_t nblk);
+void launch_k_ipp_scalars_unf(dim3 g_, dim3 b_, cudaStream_t s_, const sc_st *a, const sc_st *b, const sc_st *yinv, const sc_st *cG, const sc_st *cH, uint32_t cstride, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np, uint32_t live);
 void launch_k_rt_catchup(dim3 g_, dim3 b_, cudaStream_t s_, catchup_args a);
+
+// ===================================================================================================================
+// K6c: FROZEN LEVEL.  After the catch-up the folded generators of a chunk (F = N/16 of G" and of H") stay frozen for the
+// middle rounds: like the first rounds over the original generators, every later L / R is a sum over ALL frozen points with
+// coefficient tables, but the points are new per proof, so their tables are small Straus tables built on the fly:
+//   T[p][q][k] = (k+1) * 2^(32 q) * P_p,  q < 8 octants, k < 8  (signed radix-16 digits; 64 cached records = 8 KB per point)
+//   s * P_p = sum_{pos<8} 16^pos * sum_{q<8} e[8q+pos] * 2^(32q) P_p       (e = signed radix-16 digits of s)
+// so a round is 64 additions per point and its doubling chain has only 28 doublings (k_finalize with c = 4, nw = 8) instead
+// of a 253-step fold ladder per point plus a 252-doubling chain per output.
+// ===================================================================================================================
+#define FRZ_Q 8
+#define FRZ_E 8
+#define FRZ_MAX_F 1024
+HD void st_cached(p3_st *p, const ge_cached &c) { uint4 *q = (uint4 *)p; st_fe1(q, c.YplusX); st_fe1(q + 2, c.YminusX); st_fe1(q + 4, c.Z); st_fe1(q + 6, c.T2d); }
+HD void ld_cached(ge_cached &c, const p3_st *p) { const uint4 *q = (const uint4 *)p; ld_fe2(c.YplusX, c.YminusX, q); ld_fe2(c.Z, c.T2d, q + 4); }
+HD void acc_add_cached(ge_p3 &acc, const p3_st *p, bool neg) { ge_cached c; ld_cached(c, p); ge_add_cached_signed(acc, acc, c, neg); }
+struct frz_reduce_args { const p3_st *T; const sc_st *msmL, *msmR; p3_st *V; uint32_t F, np, C; };
+struct frz_exit_args { const p3_st *T; const int8_t *digs; p3_st *Gf, *Hf; uint32_t F, Fo, nblk, stride; };
+#ifdef KG_FOLD
+// bases[(c*2F + p)*8 + q] = 2^(32 q) * P_p ; P = G"[c][0..F) then H"[c][0..F).  grid (blocks, C)
+KERNEL void LB(128, 4) k_frz_bases(p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride) {
+    const int c = blockIdx.y; const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= 2 * F) return;
+    ge_p3 P; ld_p3(P, (p < F ? Gf + (size_t)c * stride + p : Hf + (size_t)c * stride + (p - F)));
+    p3_st *o = bases + ((size_t)c * 2 * F + p) * FRZ_Q;
+    for (int q = 0; q < FRZ_Q; q++) {
+        st_p3(o + q, P);
+        if (q + 1 < FRZ_Q) for (int k = 0; k < 32; k++) ge_p3_dbl(P, P);
+    }
+}
+KLAUNCH(k_frz_bases, false, (p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride), (bases, Gf, Hf, F, stride))
+// T[idx*8 + k] = (k+1) * bases[idx]   (cached form), one thread per (point, octant)
+KERNEL void LB(128, 4) k_frz_tables(p3_st *T, const p3_st *bases, size_t count) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    ge_p3 base, cur; ld_p3(base, bases + idx); cur = base;
+    ge_cached cb; ge_p3_to_cached(cb, base);
+    st_cached(T + idx * FRZ_E, cb);
+    for (int k = 1; k < FRZ_E; k++) { ge_add_cached(cur, cur, cb); ge_cached ck; ge_p3_to_cached(ck, cur); st_cached(T + idx * FRZ_E + k, ck); }
+}
+KLAUNCH(k_frz_tables, false, (p3_st *T, const p3_st *bases, size_t count), (T, bases, count))
+// one round: V[(lr*C + c)*8 + pos] = sum over the F terms of side lr (F/2 G-terms then F/2 H-terms, scalars as k_ipp_scalars_unf lays them
+// out) and the 8 octants of the table entry selected by digit e[8q + pos].  grid (8, 2C), 128 threads
+KERNEL void LB(128, 4) k_frz_reduce(frz_reduce_args a) {
+    __shared__ p3_st buf[128];
+    const int pos = blockIdx.x, tid = threadIdx.x; const uint32_t lr = blockIdx.y / a.C, c = blockIdx.y % a.C;
+    const sc_st *scal = (lr ? a.msmR : a.msmL) + (size_t)c * a.F;
+    const uint32_t half = a.F / 2;
+    ge_p3 acc; ge_p3_0(acc);
+    for (uint32_t k = tid; k < a.F; k += 128) {
+        sc x; ld_sc(x, scal + k);
+        if (sc_iszero(x)) continue;
+        const bool isG = k < half; const uint32_t qk = isG ? k : k - half;
+        const bool hi = (lr == 0) == isG;
+        const uint32_t j = (qk / a.np) * 2 * a.np + (hi ? a.np : 0) + qk % a.np, p = isG ? j : a.F + j;
+        int8_t e[64]; sc_radix16(e, x);
+        const p3_st *row = a.T + ((size_t)c * 2 * a.F + p) * FRZ_Q * FRZ_E;
+        for (int q = 0; q < FRZ_Q; q++) {
+            const int d = e[8 * q + pos];
+            if (d != 0) acc_add_cached(acc, row + q * FRZ_E + (d > 0 ? d : -d) - 1, d < 0);
+        }
+    }
+    block_sum_p3(acc, buf, tid, 128);
+    if (tid == 0) st_p3(a.V + ((size_t)lr * a.C + c) * 8 + pos, acc);
+}
+KLAUNCH(k_frz_reduce, true, (frz_reduce_args a), (a))
+// leave the level: out[c][i] = sum_{t < nblk} coef[t] * P[t*Fo + i], i < Fo (the folded generators the next stage starts from), through the
+// tables.  digs[((c*2 + which)*nblk + t)*64 + ..] = signed radix-16 digits of the coefficient (host).  grid (Fo, C, 2), 128 threads:
+// thread (pos = tid % 8, g = tid / 8) sums the (t, q) pairs g, g+16, .. of its digit position; 16-way tree per position; thread 0 runs the
+// 28-doubling chain.
+KERNEL void LB(128, 4) k_frz_exit(frz_exit_args a) {
+    __shared__ p3_st buf[128];
+    const uint32_t i = blockIdx.x, c = blockIdx.y, which = blockIdx.z; const int tid = threadIdx.x, pos = tid & 7, g = tid >> 3;
+    const int8_t *dg = a.digs + ((size_t)c * 2 + which) * a.nblk * 64;
+    ge_p3 acc; ge_p3_0(acc);
+    for (uint32_t pr = g; pr < a.nblk * FRZ_Q; pr += 16) {
+        const uint32_t t = pr / FRZ_Q, q = pr % FRZ_Q;
+        const int d = dg[t * 64 + 8 * q + pos];
+        const uint32_t p = which * a.F + t * a.Fo + i;
+        if (d != 0) acc_add_cached(acc, a.T + (((size_t)c * 2 * a.F + p) * FRZ_Q + q) * FRZ_E + (d > 0 ? d : -d) - 1, d < 0);
+    }
+    st_p3(buf + tid, acc);
+    __syncthreads();
+    for (int s2 = 64; s2 >= 8; s2 >>= 1) {
+        if (tid < s2) { ge_p3 x, y; ld_p3(x, buf + tid); ld_p3(y, buf + tid + s2); ge_add(x, x, y); st_p3(buf + tid, x); }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        ge_p3 h; ld_p3(h, buf + 7);
+        for (int w = 6; w >= 0; w--) { for (int k = 0; k < 4; k++) ge_p3_dbl(h, h); acc_add_p3(h, buf + w, false); }
+        st_p3((which ? a.Hf : a.Gf) + (size_t)c * a.stride + i, h);
+    }
+}
+KLAUNCH(k_frz_exit, true, (frz_exit_args a), (a))
+#endif
+void launch_k_frz_bases(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride);
+void launch_k_frz_tables(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *T, const p3_st *bases, size_t count);
+void launch_k_frz_reduce(dim3 g_, dim3 b_, cudaStream_t s_, frz_reduce_args a);
+void launch_k_frz_exit(dim3 g_, dim3 b_, cudaStream_t s_, frz_exit_args a);

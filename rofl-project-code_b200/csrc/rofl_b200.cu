@@ -63,6 +63,7 @@ __global__ void k_probe_imad_wide_cc(uint32_t *out, uint32_t y, int iters) {
 extern "C" double rofl_probe_imad_wide(rofl_ctx *c) {
     if (!c) return 0.0;
     try {
+        rt_set_device(c->e.device);
         std::lock_guard<std::mutex> lk(c->e.mu); cudaStream_t s = c->e.stream;
         cudaDeviceProp prop; rt_check(cudaGetDeviceProperties(&prop, c->e.device), "props");
         const int tpb = 256, blocks = prop.multiProcessorCount * 32, iters = 4096;
@@ -106,6 +107,7 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
         if (const char *gv = getenv("ROFL_RT")) c->e.use_rt = atoi(gv);                                   // 0 disables the generator tables
         if (const char *gv = getenv("ROFL_UNFOLD")) c->e.rt_unfold = std::max(0, std::min(6, atoi(gv)));   // unfolded IPP rounds (RT path)
         if (const char *gv = getenv("ROFL_RT_BITS")) c->e.rt_bits = std::max(8, std::min(10, atoi(gv)));              // generator-table radix
+        if (const char *gv = getenv("ROFL_FRZ")) c->e.use_frz = atoi(gv) != 0;                                            // frozen-level middle rounds
         if (const char *gv = getenv("ROFL_TAIL")) c->e.tail_np = std::max(0, std::min(TAIL_MAX_F / 2, atoi(gv)));    // 0 disables the fused IPP tail
         engine_init(c->e);
         *out = c;

@@ -16,6 +16,7 @@ inline void rt_memset(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n);
 inline void rt_sync(cudaStream_t) {}
 inline size_t rt_free_mem() { return (size_t)8 << 30; }
 inline void *rt_host_alloc(size_t n) { return malloc(n ? n : 1); }
+inline void rt_set_device(int) {}
 inline void rt_host_free(void *p) { free(p); }
 struct rt_event { };
 inline void *rt_prof_begin(int, cudaStream_t) { return nullptr; }
@@ -35,6 +36,7 @@ inline void rt_d2d(void *d, const void *s_, size_t n, cudaStream_t s) { rt_check
 inline void rt_memset(void *d, int v, size_t n, cudaStream_t s) { rt_check(cudaMemsetAsync(d, v, n, s), "memset"); }
 inline void rt_sync(cudaStream_t s) { rt_check(cudaStreamSynchronize(s), "sync"); }
 inline size_t rt_free_mem() { size_t f = 0, t = 0; cudaMemGetInfo(&f, &t); return f; }
+inline void rt_set_device(int d) { rt_check(cudaSetDevice(d), "cudaSetDevice"); }     // the current device is per host thread
 inline void *rt_host_alloc(size_t n) { void *p = nullptr; rt_check(cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault), "cudaHostAlloc"); return p; }     // pinned: async copies really are async
 inline void rt_host_free(void *p) { if (p) cudaFreeHost(p); }
 void *rt_prof_begin(int slot, cudaStream_t s);

@@ -189,3 +189,25 @@ def test_compressed_rand_proof(api, oracle):
     badc = pairs.copy(); badc[1, :32] = 0xff
     assert api.crp_verify(pf, badc) == -1 and oracle.crp_verify(pf, badc) == -1
     assert api.crp_prove(v, badc[:, :32].copy(), bl, 16, 7, seed)[0] == -4
+
+
+@pytest.mark.parametrize("tail_np,rt,unfold", [(2, 1, 1), (2, 0, 0), (1, 1, 2), (0, 1, 1), (0, 0, 0), (4, 1, 1)])
+def test_ipp_frozen_level(api, oracle, tail_np, rt, unfold):
+    """Middle rounds over FROZEN generators with on-the-fly Straus tables (k_frz_*): entered after the table catch-up or after ordinary
+    folds, left through k_frz_exit into the tail kernel, or run to the last round when the tail is off -- always the oracle's bytes."""
+    api.set_option("tail_np", tail_np); api.set_use_rt(rt); api.set_option("rt_unfold", unfold); api.set_option("frozen", 1)
+    try:
+        rng = np.random.default_rng(tail_np * 11 + rt)
+        D, rngbits, P, nb = 14, 8, 2, 16            # 2 chunks x (m = 8, n = 8): N = 64, 6 rounds
+        mn, mx = oracle.clip_bounds(rngbits, nb, 7)
+        v = rng.uniform(mn, mx, D).astype(np.float32)
+        bl = oracle.rnd_scalar_vec(b"\x38" * 32, D)
+        seed = bytes([tail_np + 40] * 32)
+        rc_o, p_o, c_o = oracle.range_prove(v, bl, rngbits, P, nb, 7, seed)
+        rc, p, cm = api.range_prove(v, bl, rngbits, P, nb, 7, seed)
+        assert rc == rc_o == 0 and (cm == c_o).all() and (p == p_o).all()
+        api.set_option("frozen", 0)
+        rc, p2, _ = api.range_prove(v, bl, rngbits, P, nb, 7, seed)
+        assert (p2 == p).all()
+    finally:
+        api.set_option("tail_np", 32); api.set_use_rt(1); api.set_option("rt_unfold", 3)
