@@ -46,7 +46,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.p.stdout], daemon=True); self.t.start()
         except Exception:
             self.p = None
@@ -168,24 +168,31 @@ def main():
         assert rc == 0 and ok == 1
         return e0.elapsed_time(e1), e1.elapsed_time(e2)
 
+    sampler = ClockSampler(local); sampler.start()      # started BEFORE the warm-up: nvidia-smi's own start-up (NVML init) stalls the driver for a moment
     for it in range(args.warmup):
         step_resident(it); step_e2e(it)
+    sampler.lines.clear()                               # keep only the samples taken during the timed regions
     imad_peak = lib.rofl_probe_imad_wide(api.h) if rank == 0 else 0.0       # roofline denominator, measured on this GPU before the timed region
     # ---- timed: resident (no per-kernel events inside the timed region)
     lib.rofl_prof_enable(0); lib.rofl_prof_reset()
-    sampler = ClockSampler(local); sampler.start()
     barrier()
     t_p = t_v = 0.0
+    per_step = []
     for it in range(args.steps):
-        a, b, proofs = step_resident(100 + it); t_p += a; t_v += b
+        a, b, proofs = step_resident(100 + it); t_p += a; t_v += b; per_step.append((round(a, 2), round(b, 2)))
     barrier()
+    if rank == 0:
+        print("resident per-step (prove_ms, verify_ms):", per_step, file=sys.stderr)
     launches = lib.rofl_prof_launches(-1)
     # ---- timed: end to end through the host-buffer API
     barrier()
     e_p = e_v = 0.0
+    per_step = []
     for it in range(args.steps):
-        a, b = step_e2e(200 + it); e_p += a; e_v += b
+        a, b = step_e2e(200 + it); e_p += a; e_v += b; per_step.append((round(a, 2), round(b, 2)))
     barrier()
+    if rank == 0:
+        print("e2e per-step (prove_ms, verify_ms):", per_step, file=sys.stderr)
     clocks = sampler.stop()
     # ---- per-kernel breakdown: the same K resident steps again with CUDA events around every launch of the main kernel families
     # (separate pass: creating / recording the events costs host time that must not leak into `value`)

@@ -13,6 +13,8 @@
 #include <mutex>
 #include <thread>
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 
 enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE = 4, DOM_L2_VERIFY = 5, DOM_CRP = 6, DOM_RND_VEC = 7 };
 enum { PROF_FOLD = 0, PROF_MSM = 1, PROF_COMMIT = 2, PROF_SQUARE = 3, PROF_RTMSM = 4, PROF_TAIL = 5, PROF_FRZ = 6, PROF_SLOTS = 8 };
@@ -35,6 +37,7 @@ struct rofl_engine {
     int rt_unfold = 4;                    // IPP rounds computed over the original generators before the catch-up fold
     int tail_np = 32;                     // IPP rounds with half-size <= tail_np run in the fused on-device tail kernel (0 = off)
     std::mutex pin_mu; std::vector<std::pair<void *, size_t>> pins;      // pool of pinned host blocks for the per-round exchanges
+    std::mutex big_mu; std::vector<std::pair<void *, size_t>> bigs;      // persistent device blocks for the large per-proof tables (no pool churn)
     int use_frz = 1;                      // middle IPP rounds over frozen generators with on-the-fly Straus tables (kernels.cuh K6c)
     int rt_bits = 10;                     // widest generator-table radix to try (8..10)
     double rt_mem_frac = 0.45;            // tables may take this fraction of the free device memory
@@ -51,6 +54,30 @@ struct pinned_buf {
     ~pinned_buf() { std::lock_guard<std::mutex> lk(e.pin_mu); e.pins.emplace_back(p, n); }
     pinned_buf(const pinned_buf &) = delete; pinned_buf &operator=(const pinned_buf &) = delete;
     template <class T> T *as() const { return (T *)p; }
+};
+
+// large device scratch that survives between calls: taken from / returned to the engine's list (allocated once, never trimmed)
+struct big_buf {
+    rofl_engine &e; void *p = nullptr; size_t n = 0;
+    big_buf(rofl_engine &eng, size_t bytes, cudaStream_t s) : e(eng) {
+        if (!bytes) return;
+        { std::lock_guard<std::mutex> lk(e.big_mu);
+          size_t best = e.bigs.size();
+          for (size_t i = 0; i < e.bigs.size(); i++) if (e.bigs[i].second >= bytes && (best == e.bigs.size() || e.bigs[i].second < e.bigs[best].second)) best = i;
+          if (best < e.bigs.size()) { p = e.bigs[best].first; n = e.bigs[best].second; e.bigs.erase(e.bigs.begin() + best); } }
+        if (!p) { n = bytes; p = rt_malloc(n, s); }
+    }
+    ~big_buf() { if (p) { std::lock_guard<std::mutex> lk(e.big_mu); e.bigs.emplace_back(p, n); } }
+    big_buf(const big_buf &) = delete; big_buf &operator=(const big_buf &) = delete;
+    template <class T> T *as() const { return (T *)p; }
+};
+
+// ROFL_TRACE=1: wall-clock phase marks of prove_chunks on stderr (stream synchronised at every mark; debugging aid only)
+struct phase_trace {
+    bool on; cudaStream_t s; std::chrono::steady_clock::time_point t0; std::string out;
+    phase_trace(cudaStream_t st) : on(getenv("ROFL_TRACE") != nullptr), s(st) { if (on) { rt_sync(s); t0 = std::chrono::steady_clock::now(); } }
+    void mark(const char *what) { if (!on) return; rt_sync(s); auto t = std::chrono::steady_clock::now(); char b[96]; snprintf(b, sizeof b, " %s=%.2f", what, std::chrono::duration<double, std::milli>(t - t0).count()); out += b; t0 = t; }
+    ~phase_trace() { if (on) fprintf(stderr, "[rofl trace]%s\n", out.c_str()); }
 };
 
 // ---- small host helpers ---------------------------------------------------------------------------------------------------
@@ -119,6 +146,8 @@ static inline void engine_destroy(rofl_engine &e) {
     for (auto &b : e.bsgs) { rt_free(b.second.keys, s); rt_free(b.second.vals, s); }
     for (auto &pp : e.pins) rt_host_free(pp.first);
     e.pins.clear();
+    for (auto &bb : e.bigs) rt_free(bb.first, s);
+    e.bigs.clear();
     e.gens.clear(); e.bsgs.clear();
     rt_sync(s);
 }
@@ -232,6 +261,7 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     const size_t N = (size_t)n * m, NT = N * C;
     const int lgN = ilog2_sz(N);
     const size_t plen = 32 * (9 + 2 * (size_t)lgN);
+    phase_trace tr(s);
     // ---- device scratch
     dev_buf d_keys(32 * (size_t)C, s), d_sLR(sizeof(sc_st) * 2 * NT, s), d_sums(sizeof(sc_st) * 5 * C, s);
     { std::vector<uint32_t> kw(8 * (size_t)C); for (int c = 0; c < C; c++) key_words(&kw[8 * c], &keys[32 * c]); rt_h2d(d_keys.p, kw.data(), 32 * (size_t)C, s); }
@@ -344,8 +374,10 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     dev_buf d_x(sizeof(sc_st) * C, s), d_w2(sizeof(sc_st) * 2 * C, s), d_yinv(sizeof(sc_st) * NT, s);
     rt_h2d(d_x.p, h_x.data(), sizeof(sc_st) * C, s); rt_h2d(d_w2.p, h_w2.data(), sizeof(sc_st) * 2 * C, s);
     LAUNCH(k_lr, dim3((unsigned)((NT + 255) / 256)), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_yinv.as<sc_st>(), d_x.as<sc_st>(), yitab, N, NT);
+    tr.mark("pre_ipp");
     // ---- inner product argument
-    const size_t half = N / 2 ? N / 2 : 1;
+    // folded generators [C][half]; a tail that starts at round 0 keeps all N original generators there instead
+    const size_t half = (N / 2 <= (size_t)std::min(e.tail_np, TAIL_MAX_F / 2)) ? N : (N / 2 ? N / 2 : 1);
     dev_buf d_Gf(sizeof(p3_st) * half * C, s), d_Hf(sizeof(p3_st) * half * C, s);
     sc_st *msmL = d_sLR.as<sc_st>(), *msmR = d_sLR.as<sc_st>() + NT;         // s_L / s_R are dead after k_lr: reuse as MSM scalar buffers
     dev_buf d_cLR(sizeof(sc_st) * 2 * C, s), d_LR(64 * (size_t)C, s), d_u2(sizeof(sc_st) * C, s), d_uinv2(sizeof(sc_st) * C, s), d_nafs(512 * (size_t)C, s);
@@ -380,12 +412,14 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     std::vector<sc> cAG((size_t)C * cAstride), cAH((size_t)C * cAstride);
     std::vector<sc_st> h_cA(2 * (size_t)C * cAstride);
     for (int c = 0; c < C; c++) { sc_from_u64(cAG[(size_t)c * cAstride], 1); sc_from_u64(cAH[(size_t)c * cAstride], 1); }
-    dev_buf d_cA(sizeof(sc_st) * 2 * (size_t)C * cAstride, s), d_frzT(ra >= 0 ? sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q * FRZ_E : 16, s), d_frzV(sizeof(p3_st) * 2 * (size_t)C * 8, s);
+    dev_buf d_cA(sizeof(sc_st) * 2 * (size_t)C * cAstride, s), d_frzV(sizeof(p3_st) * 2 * (size_t)C * 8, s);
+    big_buf d_frzT(e, ra >= 0 ? sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q * FRZ_E : 0, s);
     int round = 0;
     bool tail_done = false;
     for (size_t np = N / 2; np >= 1; np /= 2, round++) {
+        if (round == r_unf) tr.mark("unfolded");
         if (round == ra) {           // enter the frozen level: Straus tables of the current G", H"
-            dev_buf d_bases(sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q, s);
+            big_buf d_bases(e, sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q, s);
             void *tk = rt_prof_begin(PROF_FRZ, s);
             LAUNCH(k_frz_bases, dim3((unsigned)((2 * FA + 127) / 128), C), dim3(128), s, d_bases.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), (uint32_t)FA, (uint32_t)half);
             const size_t cnt = (size_t)C * 2 * FA * FRZ_Q;
@@ -393,6 +427,7 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             rt_prof_end(PROF_FRZ, tk, s);
         }
         const bool frozen = ra >= 0 && round >= ra;
+        if (round == pre) tr.mark("middle");
         if (round == pre && frozen) {       // leave the frozen level: the 2*np generators the tail starts from, straight from the tables
             const uint32_t nblk = (uint32_t)(FA / (2 * np));
             std::vector<int8_t> h_dg(2 * (size_t)C * nblk * 64);
@@ -407,25 +442,31 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             LAUNCH_COOP(k_frz_exit, dim3((unsigned)(2 * np), C, 2), dim3(128), s, xa);
             rt_prof_end(PROF_FRZ, tk, s);
         }
+        if (round == pre) tr.mark("exit");
         if (round == pre) {          // np <= tail_np: every remaining round in one launch (kernels.cuh, k_ipp_tail)
             const int rounds_left = lgN - round; const uint32_t ostride = 64 * (uint32_t)rounds_left + 64;
             std::vector<sc_st> h_up(2 * (size_t)C);
             for (int c = 0; c < C; c++) { sc_to_st(h_up[c], uprod[c]); sc_to_st(h_up[C + c], uinvprod[c]); }
             dev_buf d_ts(sizeof(transcript) * (size_t)C, s), d_up(sizeof(sc_st) * 2 * (size_t)C, s), d_tail((size_t)ostride * C, s);
             rt_h2d(d_ts.p, ts.data(), sizeof(transcript) * (size_t)C, s); rt_h2d(d_up.p, h_up.data(), sizeof(sc_st) * 2 * (size_t)C, s);
-            tail_args ta = {}; ta.Gn = round == 0 ? g.G : nullptr; ta.Hn = round == 0 ? g.H : nullptr;
-            ta.Gf = d_Gf.as<p3_st>(); ta.Hf = d_Hf.as<p3_st>(); ta.stride = (uint32_t)half;
+            // freeze the 2*np generators the tail works on: Straus tables (kernels.cuh K6c), built once for all its rounds
+            const uint32_t Ft = (uint32_t)(2 * np);
+            if (round == 0) LAUNCH(k_niels_to_p3, dim3((Ft + 127) / 128, C), dim3(128), s, d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), g.G, g.H, Ft, (uint32_t)half);
+            dev_buf d_tb(sizeof(p3_st) * (size_t)C * 2 * Ft * FRZ_Q, s), d_tT(sizeof(p3_st) * (size_t)C * 2 * Ft * FRZ_Q * FRZ_E, s);
+            void *tk = rt_prof_begin(PROF_TAIL, s);
+            LAUNCH(k_frz_bases, dim3((2 * Ft + 127) / 128, C), dim3(128), s, d_tb.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), Ft, (uint32_t)half);
+            LAUNCH(k_frz_tables, dim3((unsigned)(((size_t)C * 2 * Ft * FRZ_Q + 127) / 128)), dim3(128), s, d_tT.as<p3_st>(), d_tb.as<p3_st>(), (size_t)C * 2 * Ft * FRZ_Q);
+            tail_args ta = {}; ta.T = d_tT.as<p3_st>();
             ta.a = d_a.as<sc_st>(); ta.b = d_b.as<sc_st>(); ta.yinv = d_yinv.as<sc_st>(); ta.N = N;
             ta.ts = d_ts.as<transcript>(); ta.w = d_w2.as<sc_st>(); ta.uprod = d_up.as<sc_st>(); ta.uinvprod = d_up.as<sc_st>() + C; ta.tabB = e.tabB;
-            dev_buf d_tscr(sizeof(p3_st) * 2 * TAIL_Q * TAIL_MAX_F * (size_t)C, s); ta.scratch = d_tscr.as<p3_st>();
-            ta.out = d_tail.as<uint8_t>(); ta.out_stride = ostride; ta.F = (uint32_t)(2 * np);
-            void *tk = rt_prof_begin(PROF_TAIL, s);
+            dev_buf d_tscr(sizeof(p3_st) * 512 * (size_t)C, s); ta.scratch = d_tscr.as<p3_st>();
+            ta.out = d_tail.as<uint8_t>(); ta.out_stride = ostride; ta.F = Ft;
             LAUNCH_COOP(k_ipp_tail, dim3(C), dim3(TAIL_THREADS), s, ta);
             rt_prof_end(PROF_TAIL, tk, s);
             std::vector<uint8_t> h_tail((size_t)ostride * C);
             rt_d2h(h_tail.data(), d_tail.p, h_tail.size(), s); rt_sync(s);
             for (int c = 0; c < C; c++) memcpy(h_proofs + plen * c + 224 + 64 * (size_t)round, &h_tail[(size_t)ostride * c], ostride);
-            tail_done = true;
+            tail_done = true; tr.mark("tail");
             break;
         }
         const int nbI = (int)std::min<size_t>(256, (np + 255) / 256);

@@ -609,148 +609,6 @@ KERNEL void LB(128, 4) k_ipp_fold_points(fold_args a) {
 KLAUNCH(k_ipp_fold_points, true, (fold_args a), (a))
 #endif
 
-// ===================================================================================================================
-// K6b: the last rounds of the inner-product argument (half-size np <= TAIL_MAX_F/2) in ONE launch, one block per chunk,
-// nothing leaves the SM between rounds: the Merlin transcript, the challenge inversion and the scalar folds run on the
-// device.  The generators are never folded again: they stay FROZEN at their F = 2 np0 entry values and every later
-// L / R is a sum over all F frozen points with coefficient tables cg / ch (the same identity as the unfolded first
-// rounds).  Every frozen point feeds exactly one of L or R per round, so thread p owns point p (radix-16 table built
-// once) and does one 253-bit variable-base multiplication per round; the 2F products are tree-summed in shared memory.
-//   out[c]: rounds x (L | R) compressed, then a | b (the proof's last two scalars)
-// ===================================================================================================================
-#define TAIL_MAX_F 64
-#define TAIL_Q 4                                              // threads per frozen point: each owns one 64-bit quarter of the scalar
-#define TAIL_THREADS (2 * TAIL_MAX_F * TAIL_Q + 32)
-struct tail_args {
-    const niels_st *Gn, *Hn;                 // non-null: the tail starts at round 0 on the shared generators
-    const p3_st *Gf, *Hf; uint32_t stride;   // folded generators [C][stride] (first F entries live)
-    const sc_st *a, *b, *yinv; size_t N;     // [C][N] lazy-factor vectors a^, b^ and y^-i (first F entries live)
-    const transcript *ts;                    // [C] transcript states after the previous challenge
-    const sc_st *w, *uprod, *uinvprod;       // [C] w; products of the earlier u_k and u_k^-1
-    const niels_st *tabB;
-    p3_st *scratch;                          // [C][2 * TAIL_Q * TAIL_MAX_F] partial products (L half | R half)
-    uint8_t *out; uint32_t out_stride;
-    uint32_t F;
-};
-// r = sum_{i<16} e[i] 16^i * P  (one 64-bit quarter of a signed radix-16 scalar), table = 1P..8P
-HD void ge_scalarmult_r16_quarter(ge_p3 &r, const int8_t *e, const ge_tab8 &tp) {
-    ge_p3_0(r);
-    for (int i = 15; i >= 0; i--) {
-        if (i != 15) {
-            ge_p2 q; ge_p1p1 t;
-            ge_dbl_p1p1(t, r.X, r.Y, r.Z); ge_dbl_fix(t); ge_p1p1_to_p2(q, t);
-            ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); ge_p1p1_to_p2(q, t);
-            ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); ge_p1p1_to_p2(q, t);
-            ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); ge_p1p1_to_p3(r, t);
-        }
-        const int d = e[i];
-        if (d != 0) ge_add_cached_signed(r, r, tp.t[(d > 0 ? d : -d) - 1], d < 0);
-    }
-}
-#ifdef KG_FOLD
-KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
-    __shared__ sc_st sa[TAIL_MAX_F], sb[TAIL_MAX_F], sy[TAIL_MAX_F], scg[TAIL_MAX_F], sch[TAIL_MAX_F], red[64], sfac[3];
-    __shared__ p3_st ptB[2];
-    const int c = blockIdx.x, tid = threadIdx.x;
-    const uint32_t F = a.F, NP = 2 * F;                                // NP frozen points: G" then H"
-    const bool pt_thread = (uint32_t)tid < TAIL_Q * NP;
-    const uint32_t q = (uint32_t)tid / NP, p = (uint32_t)tid % NP;     // quarter (uniform per warp when NP >= 32), point
-    const bool isH = p >= F; const uint32_t j = isH ? p - F : p;
-    const int tB = TAIL_THREADS - 32;                                  // lanes 0 / 1 of the last warp: the c_L w B and c_R w B terms
-    p3_st *pts = a.scratch + (size_t)c * 2 * TAIL_Q * TAIL_MAX_F;      // L products [0, TAIL_Q F), R products [TAIL_Q F, 2 TAIL_Q F)
-    const uint32_t half = TAIL_Q * F;
-    for (uint32_t i = tid; i < F; i += TAIL_THREADS) {
-        sa[i] = a.a[(size_t)c * a.N + i]; sb[i] = a.b[(size_t)c * a.N + i]; sy[i] = a.yinv[(size_t)c * a.N + i];
-    }
-    if (tid == 0) { sc one; sc_from_u64(one, 1); st_sc(scg, one); st_sc(sch, one); }
-    ge_tab8 tb;
-    if (pt_thread) {                                                   // table of 2^(64 q) * P_p
-        ge_p3 P;
-        if (a.Gn) { ge_niels n; ld_niels(n, (isH ? a.Hn : a.Gn) + j); ge_niels_to_p3(P, n); }
-        else ld_p3(P, (isH ? a.Hf : a.Gf) + (size_t)c * a.stride + j);
-        for (uint32_t k = 0; k < 64 * q; k++) ge_p3_dbl(P, P);
-        ge_tab8_build(tb, P);
-    }
-    transcript t; sc up, uip, wc;
-    if (tid == 0) { t = a.ts[c]; ld_sc(up, a.uprod + c); ld_sc(uip, a.uinvprod + c); }
-    if (tid >= tB) ld_sc(wc, a.w + c);
-    uint8_t *out = a.out + (size_t)c * a.out_stride;
-    __syncthreads();
-    int round = 0;
-    for (uint32_t np = F >> 1; np >= 1; np >>= 1, round++) {
-        // c_L = <a^_lo, b^_hi>, c_R = <a^_hi, b^_lo>
-        if (tid < 64) {
-            sc v; sc_0(v);
-            const uint32_t i = tid & 31;
-            if (i < np) { sc x, y; ld_sc(x, tid < 32 ? sa + i : sa + np + i); ld_sc(y, tid < 32 ? sb + np + i : sb + i); sc_mul(v, x, y); }
-            st_sc(red + tid, v);
-        }
-        __syncthreads();
-        for (int s2 = 16; s2 > 0; s2 >>= 1) {
-            if (tid < 64 && (tid & 31) < s2) { sc x, y; ld_sc(x, red + tid); ld_sc(y, red + tid + s2); sc_add(x, x, y); st_sc(red + tid, x); }
-            __syncthreads();
-        }
-        if (pt_thread) {
-            const uint32_t tt = j / (2 * np), h = (j / np) & 1, i = j % np;
-            sc s, x; bool toL;
-            if (!isH) { toL = h == 1; ld_sc(s, toL ? sa + i : sa + np + i); ld_sc(x, scg + tt); sc_mul(s, s, x); }
-            else { toL = h == 0; ld_sc(s, toL ? sb + np + i : sb + i); ld_sc(x, toL ? sy + i : sy + np + i); sc_mul(s, s, x); ld_sc(x, sch + tt); sc_mul(s, s, x); }
-            int8_t e[64]; sc_radix16(e, s);
-            ge_p3 r; ge_scalarmult_r16_quarter(r, e + 16 * q, tb);
-            st_p3(pts + (toL ? 0 : half) + q * F + (isH ? F / 2 : 0) + tt * np + i, r);
-        } else if (tid == tB || tid == tB + 1) {
-            sc s; ld_sc(s, red + 32 * (tid - tB)); sc_mul(s, s, wc);
-            ge_p3 r; ge_p3_0(r); fb_mul_acc(r, a.tabB, s, 32);
-            st_p3(ptB + (tid - tB), r);
-        }
-        __syncthreads();
-        // both sums at once: entries [0, half) -> L, [half, 2 half) -> R
-        for (uint32_t s2 = half >> 1; s2 > 0; s2 >>= 1) {
-            if ((uint32_t)tid < 2 * half && ((uint32_t)tid % half) < s2) { ge_p3 x, y; ld_p3(x, pts + tid); ld_p3(y, pts + tid + s2); ge_add(x, x, y); st_p3(pts + tid, x); }
-            __syncthreads();
-        }
-        if (tid == 0 || (uint32_t)tid == half) {
-            const int lr = tid ? 1 : 0;
-            ge_p3 x, y; ld_p3(x, pts + tid); ld_p3(y, ptB + lr); ge_add(x, x, y);
-            uint8_t enc[32]; ge_compress(enc, x);
-            for (int k = 0; k < 32; k++) out[64 * round + 32 * lr + k] = enc[k];
-        }
-        __syncthreads();
-        if (tid == 0) {
-            uint8_t lrb[64]; for (int k = 0; k < 64; k++) lrb[k] = out[64 * round + k];
-            transcript_append(t, "L", lrb, 32); transcript_append(t, "R", lrb + 32, 32);
-            uint8_t ub[64]; transcript_challenge(t, "u", ub, 64);
-            sc u, ui, u2, ui2, sH, ynp;
-            sc_from_bytes_wide(u, ub); sc_invert_vartime(ui, u);
-            sc_mul(u2, u, u); sc_mul(ui2, ui, ui); ld_sc(ynp, sy + np); sc_mul(sH, ui2, ynp);          // u^-2 y^-np
-            sc_mul(up, up, u); sc_mul(uip, uip, ui);
-            st_sc(sfac, u2); st_sc(sfac + 1, ui2); st_sc(sfac + 2, sH);
-        }
-        __syncthreads();
-        // fold a^ / b^ and extend the coefficient tables: c'[2t] = c[t], c'[2t+1] = c[t] * s
-        sc cgv, chv; const uint32_t nblk = F / (2 * np);
-        if ((uint32_t)tid < nblk) { ld_sc(cgv, scg + tid); ld_sc(chv, sch + tid); }
-        if ((uint32_t)tid < np) {
-            sc f, lo, hi;
-            ld_sc(f, sfac + 1); ld_sc(lo, sa + tid); ld_sc(hi, sa + np + tid); sc_mul(hi, hi, f); sc_add(lo, lo, hi); st_sc(sa + tid, lo);
-            ld_sc(f, sfac); ld_sc(lo, sb + tid); ld_sc(hi, sb + np + tid); sc_mul(hi, hi, f); sc_add(lo, lo, hi); st_sc(sb + tid, lo);
-        }
-        __syncthreads();
-        if ((uint32_t)tid < nblk) {
-            sc f, x;
-            ld_sc(f, sfac); sc_mul(x, cgv, f); st_sc(scg + 2 * tid, cgv); st_sc(scg + 2 * tid + 1, x);
-            ld_sc(f, sfac + 2); sc_mul(x, chv, f); st_sc(sch + 2 * tid, chv); st_sc(sch + 2 * tid + 1, x);
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {            // a = a^ prod u_k, b = b^ prod u_k^-1
-        sc x, y; ld_sc(x, sa); ld_sc(y, sb); sc_mul(x, x, up); sc_mul(y, y, uip);
-        uint8_t e[32]; sc_tobytes(e, x); for (int k = 0; k < 32; k++) out[64 * round + k] = e[k];
-        sc_tobytes(e, y); for (int k = 0; k < 32; k++) out[64 * round + 32 + k] = e[k];
-    }
-}
-KLAUNCH(k_ipp_tail, true, (tail_args a), (a))
-#endif
 
 // ===================================================================================================================
 // K7: verifier side (RangeProof::verify_multiple)
@@ -1071,7 +929,6 @@ void launch_k_lr(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *l0, sc_st *r0, const 
 void launch_k_ipp_scalars(dim3 g_, dim3 b_, cudaStream_t s_, const sc_st *a, const sc_st *b, const sc_st *yinv, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np);
 void launch_k_ipp_fold_scalars(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *a, sc_st *b, const sc_st *u2, const sc_st *uinv2, size_t N, uint32_t np);
 void launch_k_ipp_fold_points(dim3 g_, dim3 b_, cudaStream_t s_, fold_args a);
-void launch_k_ipp_tail(dim3 g_, dim3 b_, cudaStream_t s_, tail_args a);
 void launch_k_decompress(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *out, uint8_t *out32, const uint8_t *in, size_t count_in, size_t count_out, const p3_st *offset, int *bad, size_t bad_group);
 void launch_k_verify_tables(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *tab, vtab_layout t, sc_st *var, uint32_t var_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int m);
 void launch_k_verify_scalars(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *gh, const sc_st *tab, vtab_layout t, const sc_st *chal, int chal_stride, int n, int C);
@@ -1335,3 +1192,149 @@ void launch_k_frz_bases(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *bases, const p
 void launch_k_frz_tables(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *T, const p3_st *bases, size_t count);
 void launch_k_frz_reduce(dim3 g_, dim3 b_, cudaStream_t s_, frz_reduce_args a);
 void launch_k_frz_exit(dim3 g_, dim3 b_, cudaStream_t s_, frz_exit_args a);
+
+// ===================================================================================================================
+// K6b: the last rounds of the inner-product argument (half-size np <= TAIL_MAX_F/2) in ONE launch, one block per chunk,
+// nothing leaves the SM between rounds: the Merlin transcript, the challenge inversion and the scalar folds run on the
+// device.  The generators are frozen at their F = 2 np0 entry values (their Straus tables T are built by k_frz_bases /
+// k_frz_tables right before the launch) and every round is the frozen-level round of K6c inside the block:
+//   128 threads recode the scalars of the 2F points into signed radix-16 digits (shared memory);
+//   512 threads (side, digit position, group) add up table entries: 16 sums of 8F entries each, 32-way tree per sum;
+//   2 threads run the 28-doubling chains of L and R, add c_L w B / c_R w B (computed meanwhile by a spare warp) and compress;
+//   thread 0 appends L, R to the transcript, draws u, inverts it (binary Euclid) and publishes u^2, u^-2, u^-2 y^-np.
+//   out[c]: rounds x (L | R) compressed, then a | b (the proof's last two scalars)
+// ===================================================================================================================
+#define TAIL_MAX_F 64
+#define TAIL_THREADS (512 + 32)
+struct tail_args {
+    const p3_st *T;                          // [C][2F][FRZ_Q][FRZ_E] Straus tables of G"[0..F) then H"[0..F)
+    const sc_st *a, *b, *yinv; size_t N;     // [C][N] lazy-factor vectors a^, b^ and y^-i (first F entries live)
+    const transcript *ts;                    // [C] transcript states after the previous challenge
+    const sc_st *w, *uprod, *uinvprod;       // [C] w; products of the earlier u_k and u_k^-1
+    const niels_st *tabB;
+    p3_st *scratch;                          // [C][512] partial sums
+    uint8_t *out; uint32_t out_stride;
+    uint32_t F;
+};
+#ifdef KG_FOLD
+KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
+    __shared__ sc_st sa[TAIL_MAX_F], sb[TAIL_MAX_F], sy[TAIL_MAX_F], scg[TAIL_MAX_F], sch[TAIL_MAX_F], red[64], sfac[3];
+    __shared__ p3_st ptB[2];
+    __shared__ int8_t dig[2 * TAIL_MAX_F][64];
+    __shared__ uint8_t side_of[2 * TAIL_MAX_F];                         // 0: the point feeds L this round, 1: R
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const uint32_t F = a.F, NP = 2 * F;
+    const int tB = 512;                                                // lanes 0 / 1 of the last warp: the c_L w B and c_R w B terms
+    p3_st *pts = a.scratch + (size_t)c * 512;
+    const p3_st *T = a.T + (size_t)c * NP * FRZ_Q * FRZ_E;
+    for (uint32_t i = tid; i < F; i += TAIL_THREADS) {
+        sa[i] = a.a[(size_t)c * a.N + i]; sb[i] = a.b[(size_t)c * a.N + i]; sy[i] = a.yinv[(size_t)c * a.N + i];
+    }
+    if (tid == 0) { sc one; sc_from_u64(one, 1); st_sc(scg, one); st_sc(sch, one); }
+    transcript t; sc up, uip, wc;
+    if (tid == 0) { t = a.ts[c]; ld_sc(up, a.uprod + c); ld_sc(uip, a.uinvprod + c); }
+    if (tid >= tB) ld_sc(wc, a.w + c);
+    uint8_t *out = a.out + (size_t)c * a.out_stride;
+    // accumulation role: side (L / R), digit position, group
+    const uint32_t a_side = (uint32_t)tid >> 8, a_pos = ((uint32_t)tid >> 5) & 7, a_g = (uint32_t)tid & 31;
+    __syncthreads();
+    int round = 0;
+    for (uint32_t np = F >> 1; np >= 1; np >>= 1, round++) {
+        // c_L = <a^_lo, b^_hi>, c_R = <a^_hi, b^_lo>
+        if (tid < 64) {
+            sc v; sc_0(v);
+            const uint32_t i = tid & 31;
+            if (i < np) { sc x, y; ld_sc(x, tid < 32 ? sa + i : sa + np + i); ld_sc(y, tid < 32 ? sb + np + i : sb + i); sc_mul(v, x, y); }
+            st_sc(red + tid, v);
+        }
+        // digits of the scalar of every frozen point (points 0..F-1 = G", F..2F-1 = H")
+        if ((uint32_t)tid >= 64 && (uint32_t)tid < 64 + NP) {
+            const uint32_t p = tid - 64; const bool isH = p >= F; const uint32_t j = isH ? p - F : p;
+            const uint32_t tt = j / (2 * np), h = (j / np) & 1, i = j % np;
+            sc s, x; bool toL;
+            if (!isH) { toL = h == 1; ld_sc(s, toL ? sa + i : sa + np + i); ld_sc(x, scg + tt); sc_mul(s, s, x); }
+            else { toL = h == 0; ld_sc(s, toL ? sb + np + i : sb + i); ld_sc(x, toL ? sy + i : sy + np + i); sc_mul(s, s, x); ld_sc(x, sch + tt); sc_mul(s, s, x); }
+            int8_t e[64]; sc_radix16(e, s);
+            for (int k = 0; k < 64; k++) dig[p][k] = e[k];
+            side_of[p] = toL ? 0 : 1;
+        }
+        __syncthreads();
+        for (int s2 = 16; s2 > 0; s2 >>= 1) {
+            if (tid < 64 && (tid & 31) < s2) { sc x, y; ld_sc(x, red + tid); ld_sc(y, red + tid + s2); sc_add(x, x, y); st_sc(red + tid, x); }
+            __syncthreads();
+        }
+        if (tid < 512) {
+            // pairs (point, octant) of my side, strided over the 32 groups of my (side, position)
+            ge_p3 acc; ge_p3_0(acc);
+            for (uint32_t pr = a_g; pr < NP * FRZ_Q; pr += 32) {
+                const uint32_t p = pr / FRZ_Q, q = pr % FRZ_Q;
+                if (side_of[p] != a_side) continue;
+                const int d = dig[p][8 * q + a_pos];
+                if (d != 0) acc_add_cached(acc, T + ((size_t)p * FRZ_Q + q) * FRZ_E + (d > 0 ? d : -d) - 1, d < 0);
+            }
+            st_p3(pts + tid, acc);
+        } else if (tid == tB || tid == tB + 1) {
+            sc s; ld_sc(s, red + 32 * (tid - tB)); sc_mul(s, s, wc);
+            ge_p3 r; ge_p3_0(r); fb_mul_acc(r, a.tabB, s, 32);
+            st_p3(ptB + (tid - tB), r);
+        }
+        __syncthreads();
+        for (uint32_t s2 = 16; s2 > 0; s2 >>= 1) {          // 32-way tree inside every (side, position) group
+            if (tid < 512 && a_g < s2) { ge_p3 x, y; ld_p3(x, pts + tid); ld_p3(y, pts + tid + s2); ge_add(x, x, y); st_p3(pts + tid, x); }
+            __syncthreads();
+        }
+        if (tid == 0 || tid == 256) {                        // 16^pos chain of my side, + c w B, compress
+            const int lr = tid ? 1 : 0;
+            ge_p3 h; ld_p3(h, pts + tid + 7 * 32);
+            for (int w = 6; w >= 0; w--) { for (int k = 0; k < 4; k++) ge_p3_dbl(h, h); acc_add_p3(h, pts + tid + w * 32, false); }
+            ge_p3 y; ld_p3(y, ptB + lr); ge_add(h, h, y);
+            uint8_t enc[32]; ge_compress(enc, h);
+            for (int k = 0; k < 32; k++) out[64 * round + 32 * lr + k] = enc[k];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint8_t lrb[64]; for (int k = 0; k < 64; k++) lrb[k] = out[64 * round + k];
+            transcript_append(t, "L", lrb, 32); transcript_append(t, "R", lrb + 32, 32);
+            uint8_t ub[64]; transcript_challenge(t, "u", ub, 64);
+            sc u, ui, u2, ui2, sH, ynp;
+            sc_from_bytes_wide(u, ub); sc_invert_vartime(ui, u);
+            sc_mul(u2, u, u); sc_mul(ui2, ui, ui); ld_sc(ynp, sy + np); sc_mul(sH, ui2, ynp);          // u^-2 y^-np
+            sc_mul(up, up, u); sc_mul(uip, uip, ui);
+            st_sc(sfac, u2); st_sc(sfac + 1, ui2); st_sc(sfac + 2, sH);
+        }
+        __syncthreads();
+        // fold a^ / b^ and extend the coefficient tables: c'[2t] = c[t], c'[2t+1] = c[t] * s
+        sc cgv, chv; const uint32_t nblk = F / (2 * np);
+        if ((uint32_t)tid < nblk) { ld_sc(cgv, scg + tid); ld_sc(chv, sch + tid); }
+        if ((uint32_t)tid < np) {
+            sc f, lo, hi;
+            ld_sc(f, sfac + 1); ld_sc(lo, sa + tid); ld_sc(hi, sa + np + tid); sc_mul(hi, hi, f); sc_add(lo, lo, hi); st_sc(sa + tid, lo);
+            ld_sc(f, sfac); ld_sc(lo, sb + tid); ld_sc(hi, sb + np + tid); sc_mul(hi, hi, f); sc_add(lo, lo, hi); st_sc(sb + tid, lo);
+        }
+        __syncthreads();
+        if ((uint32_t)tid < nblk) {
+            sc f, x;
+            ld_sc(f, sfac); sc_mul(x, cgv, f); st_sc(scg + 2 * tid, cgv); st_sc(scg + 2 * tid + 1, x);
+            ld_sc(f, sfac + 2); sc_mul(x, chv, f); st_sc(sch + 2 * tid, chv); st_sc(sch + 2 * tid + 1, x);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {            // a = a^ prod u_k, b = b^ prod u_k^-1
+        sc x, y; ld_sc(x, sa); ld_sc(y, sb); sc_mul(x, x, up); sc_mul(y, y, uip);
+        uint8_t e[32]; sc_tobytes(e, x); for (int k = 0; k < 32; k++) out[64 * round + k] = e[k];
+        sc_tobytes(e, y); for (int k = 0; k < 32; k++) out[64 * round + 32 + k] = e[k];
+    }
+}
+KLAUNCH(k_ipp_tail, true, (tail_args a), (a))
+// the shared niels generators as extended points (a tail that starts at round 0 freezes the original generators)
+KERNEL void LB(128, 4) k_niels_to_p3(p3_st *Gf, p3_st *Hf, const niels_st *G, const niels_st *H, uint32_t F, uint32_t stride) {
+    const int c = blockIdx.y; const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F) return;
+    ge_niels n; ge_p3 p;
+    ld_niels(n, G + i); ge_niels_to_p3(p, n); st_p3(Gf + (size_t)c * stride + i, p);
+    ld_niels(n, H + i); ge_niels_to_p3(p, n); st_p3(Hf + (size_t)c * stride + i, p);
+}
+KLAUNCH(k_niels_to_p3, false, (p3_st *Gf, p3_st *Hf, const niels_st *G, const niels_st *H, uint32_t F, uint32_t stride), (Gf, Hf, G, H, F, stride))
+#endif
+void launch_k_ipp_tail(dim3 g_, dim3 b_, cudaStream_t s_, tail_args a);
+void launch_k_niels_to_p3(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *Gf, p3_st *Hf, const niels_st *G, const niels_st *H, uint32_t F, uint32_t stride);
