@@ -37,7 +37,6 @@ struct rofl_engine {
     int rt_unfold = 4;                    // IPP rounds computed over the original generators before the catch-up fold
     int tail_np = 32;                     // IPP rounds with half-size <= tail_np run in the fused on-device tail kernel (0 = off)
     std::mutex pin_mu; std::vector<std::pair<void *, size_t>> pins;      // pool of pinned host blocks for the per-round exchanges
-    std::mutex big_mu; std::vector<std::pair<void *, size_t>> bigs;      // persistent device blocks for the large per-proof tables (no pool churn)
     int use_frz = 1;                      // middle IPP rounds over frozen generators with on-the-fly Straus tables (kernels.cuh K6c)
     int rt_bits = 10;                     // widest generator-table radix to try (8..10)
     double rt_mem_frac = 0.45;            // tables may take this fraction of the free device memory
@@ -53,22 +52,6 @@ struct pinned_buf {
     }
     ~pinned_buf() { std::lock_guard<std::mutex> lk(e.pin_mu); e.pins.emplace_back(p, n); }
     pinned_buf(const pinned_buf &) = delete; pinned_buf &operator=(const pinned_buf &) = delete;
-    template <class T> T *as() const { return (T *)p; }
-};
-
-// large device scratch that survives between calls: taken from / returned to the engine's list (allocated once, never trimmed)
-struct big_buf {
-    rofl_engine &e; void *p = nullptr; size_t n = 0;
-    big_buf(rofl_engine &eng, size_t bytes, cudaStream_t s) : e(eng) {
-        if (!bytes) return;
-        { std::lock_guard<std::mutex> lk(e.big_mu);
-          size_t best = e.bigs.size();
-          for (size_t i = 0; i < e.bigs.size(); i++) if (e.bigs[i].second >= bytes && (best == e.bigs.size() || e.bigs[i].second < e.bigs[best].second)) best = i;
-          if (best < e.bigs.size()) { p = e.bigs[best].first; n = e.bigs[best].second; e.bigs.erase(e.bigs.begin() + best); } }
-        if (!p) { n = bytes; p = rt_malloc(n, s); }
-    }
-    ~big_buf() { if (p) { std::lock_guard<std::mutex> lk(e.big_mu); e.bigs.emplace_back(p, n); } }
-    big_buf(const big_buf &) = delete; big_buf &operator=(const big_buf &) = delete;
     template <class T> T *as() const { return (T *)p; }
 };
 
@@ -146,8 +129,6 @@ static inline void engine_destroy(rofl_engine &e) {
     for (auto &b : e.bsgs) { rt_free(b.second.keys, s); rt_free(b.second.vals, s); }
     for (auto &pp : e.pins) rt_host_free(pp.first);
     e.pins.clear();
-    for (auto &bb : e.bigs) rt_free(bb.first, s);
-    e.bigs.clear();
     e.gens.clear(); e.bsgs.clear();
     rt_sync(s);
 }
@@ -413,13 +394,13 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     std::vector<sc_st> h_cA(2 * (size_t)C * cAstride);
     for (int c = 0; c < C; c++) { sc_from_u64(cAG[(size_t)c * cAstride], 1); sc_from_u64(cAH[(size_t)c * cAstride], 1); }
     dev_buf d_cA(sizeof(sc_st) * 2 * (size_t)C * cAstride, s), d_frzV(sizeof(p3_st) * 2 * (size_t)C * 8, s);
-    big_buf d_frzT(e, ra >= 0 ? sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q * FRZ_E : 0, s);
+    dev_buf d_frzT(ra >= 0 ? sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q * FRZ_E : 16, s);
     int round = 0;
     bool tail_done = false;
     for (size_t np = N / 2; np >= 1; np /= 2, round++) {
         if (round == r_unf) tr.mark("unfolded");
         if (round == ra) {           // enter the frozen level: Straus tables of the current G", H"
-            big_buf d_bases(e, sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q, s);
+            dev_buf d_bases(sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q, s);      // returned stream-ordered: the kernels below may still be running
             void *tk = rt_prof_begin(PROF_FRZ, s);
             LAUNCH(k_frz_bases, dim3((unsigned)((2 * FA + 127) / 128), C), dim3(128), s, d_bases.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), (uint32_t)FA, (uint32_t)half);
             const size_t cnt = (size_t)C * 2 * FA * FRZ_Q;

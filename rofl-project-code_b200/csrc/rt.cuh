@@ -4,6 +4,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <mutex>
 #ifdef ROFL_EMUL
 #include "cuda_emul.h"
 inline void rt_check(int, const char *) {}
@@ -28,13 +29,62 @@ inline void rt_check(cudaError_t e, const char *what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 void rt_count_launch(const char *name);
-inline void *rt_malloc(size_t n, cudaStream_t s) { void *p = nullptr; rt_check(cudaMallocAsync(&p, n ? n : 16, s), "cudaMallocAsync"); return p; }
-inline void rt_free(void *p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
+// Scratch allocation.  Small blocks come from the CUDA stream-ordered pool.  Blocks of RT_BIG_BYTES and more (the per-proof vectors and
+// tables, hundreds of MB per call) are kept in a process-wide free list instead: the pool occasionally has to grow when two streams
+// allocate and free large blocks alternately, which costs tens of milliseconds in the middle of a proof.  A block returned on one stream
+// and taken on another is ordered through the event recorded at return time.
+#define RT_BIG_BYTES ((size_t)2 << 20)
+struct rt_big_block { void *p; size_t n; int dev; cudaStream_t s; cudaEvent_t ev; };
+struct rt_big_cache {
+    std::mutex mu; std::vector<rt_big_block> free_list; std::vector<rt_big_block> live;
+    void *take(size_t n, cudaStream_t s) {
+        int dev = 0; cudaGetDevice(&dev);
+        rt_big_block b{}; bool found = false;
+        { std::lock_guard<std::mutex> lk(mu);
+          // prefer a block this very stream returned (no cross-stream wait: waiting on another group's stream can cost tens of ms)
+          size_t best = free_list.size();
+          for (int pass = 0; pass < 2 && best == free_list.size(); pass++)
+              for (size_t i = 0; i < free_list.size(); i++)
+                  if (free_list[i].dev == dev && (pass == 1 || free_list[i].s == s) && free_list[i].n >= n && free_list[i].n <= 2 * n &&
+                      (best == free_list.size() || free_list[i].n < free_list[best].n)) best = i;
+          if (best < free_list.size()) { b = free_list[best]; free_list.erase(free_list.begin() + best); found = true; } }
+        if (found) { if (b.s != s) rt_check(cudaStreamWaitEvent(s, b.ev, 0), "cudaStreamWaitEvent"); }
+        else { b.n = n; b.dev = dev; rt_check(cudaMalloc(&b.p, n), "cudaMalloc"); rt_check(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming), "cudaEventCreate"); }
+        b.s = s;
+        std::lock_guard<std::mutex> lk(mu); live.push_back(b);
+        return b.p;
+    }
+    bool give(void *p, cudaStream_t s) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t i = 0; i < live.size(); i++) if (live[i].p == p) {
+            rt_big_block b = live[i]; live.erase(live.begin() + i);
+            b.s = s; cudaEventRecord(b.ev, s); free_list.push_back(b); return true;
+        }
+        return false;
+    }
+};
+inline rt_big_cache &rt_bigs() { static rt_big_cache c; return c; }
+inline void *rt_malloc(size_t n, cudaStream_t s) {
+    if (n >= RT_BIG_BYTES) return rt_bigs().take(n, s);
+    void *p = nullptr; rt_check(cudaMallocAsync(&p, n ? n : 16, s), "cudaMallocAsync"); return p;
+}
+inline void rt_free(void *p, cudaStream_t s) { if (p && !rt_bigs().give(p, s)) cudaFreeAsync(p, s); }
 inline void rt_h2d(void *d, const void *h, size_t n, cudaStream_t s) { rt_check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "h2d"); }
 inline void rt_d2h(void *h, const void *d, size_t n, cudaStream_t s) { rt_check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "d2h"); }
 inline void rt_d2d(void *d, const void *s_, size_t n, cudaStream_t s) { rt_check(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s), "d2d"); }
 inline void rt_memset(void *d, int v, size_t n, cudaStream_t s) { rt_check(cudaMemsetAsync(d, v, n, s), "memset"); }
-inline void rt_sync(cudaStream_t s) { rt_check(cudaStreamSynchronize(s), "sync"); }
+// Stream wait by polling: a proof has ~20 host round trips (Fiat-Shamir challenges), each only tens of microseconds of GPU work apart, so
+// the wake-up latency of a blocking cudaStreamSynchronize (and the scheduler's mood on a busy host) would add up; spin instead.
+inline void rt_sync(cudaStream_t s) {
+    for (;;) {
+        cudaError_t e = cudaStreamQuery(s);
+        if (e == cudaSuccess) return;
+        if (e != cudaErrorNotReady) rt_check(e, "sync");
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
 inline size_t rt_free_mem() { size_t f = 0, t = 0; cudaMemGetInfo(&f, &t); return f; }
 inline void rt_set_device(int d) { rt_check(cudaSetDevice(d), "cudaSetDevice"); }     // the current device is per host thread
 inline void *rt_host_alloc(size_t n) { void *p = nullptr; rt_check(cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault), "cudaHostAlloc"); return p; }     // pinned: async copies really are async
