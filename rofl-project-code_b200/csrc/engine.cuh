@@ -419,8 +419,10 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             dev_buf d_dg(h_dg.size(), s); rt_h2d(d_dg.p, h_dg.data(), h_dg.size(), s);
             frz_exit_args xa = {}; xa.T = d_frzT.as<p3_st>(); xa.digs = d_dg.as<int8_t>(); xa.Gf = d_Gf.as<p3_st>(); xa.Hf = d_Hf.as<p3_st>();
             xa.F = (uint32_t)FA; xa.Fo = (uint32_t)(2 * np); xa.nblk = nblk; xa.stride = (uint32_t)half;
+            dev_buf d_xV(sizeof(p3_st) * (size_t)C * 2 * xa.Fo * 8, s); xa.V = d_xV.as<p3_st>();
             void *tk = rt_prof_begin(PROF_FRZ, s);
             LAUNCH_COOP(k_frz_exit, dim3((unsigned)(2 * np), C, 2), dim3(128), s, xa);
+            LAUNCH(k_frz_exit_chain, dim3((unsigned)(((size_t)C * 2 * xa.Fo + 127) / 128)), dim3(128), s, xa, (uint32_t)C);
             rt_prof_end(PROF_FRZ, tk, s);
         }
         if (round == pre) tr.mark("exit");
@@ -726,7 +728,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     rt_memset(d_bad.p, 0, sizeof(int) * C, s);
     rt_h2d(d_var.as<sc_st>() + (size_t)C * m, h_small.data(), sizeof(sc_st) * h_small.size(), s);
     LAUNCH(k_verify_tables, dim3((vt.total + m + 255) / 256, C), dim3(256), s, d_tab.as<sc_st>(), vt, d_var.as<sc_st>(), (uint32_t)m, d_chal.as<sc_st>(), chs, d_yinvpow2.as<sc_st>(), d_zpow2.as<sc_st>(), m);
-    LAUNCH(k_verify_scalars, dim3((unsigned)((N + 255) / 256)), dim3(256), s, d_gh.as<sc_st>(), d_tab.as<sc_st>(), vt, d_chal.as<sc_st>(), chs, n, C);
+    LAUNCH_COOP(k_verify_scalars, dim3((unsigned)((N + 63) / 64)), dim3(256), s, d_gh.as<sc_st>(), d_tab.as<sc_st>(), vt, d_chal.as<sc_st>(), chs, n, C);
     LAUNCH(k_decompress, dim3((unsigned)(((size_t)C * nsmall + 127) / 128)), dim3(128), s, d_sp.as<p3_st>(), (uint8_t *)nullptr, d_sp32.as<uint8_t>(), (size_t)C * nsmall, (size_t)C * nsmall, (const p3_st *)nullptr, d_bad.as<int>(), (size_t)nsmall);
     // fixed generators: one 2N-term MSM (radix-256 tables when they exist, bucket MSM otherwise) -> d_fix
     {

@@ -677,29 +677,39 @@ KERNEL void LB(256, 1) k_verify_tables(sc_st *tab, vtab_layout t, sc_st *var, ui
 KLAUNCH(k_verify_tables, false, (sc_st *tab, vtab_layout t, sc_st *var, uint32_t var_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int m),
         (tab, t, var, var_stride, chal, chal_stride, yinvpow2, zpow2, m))
 // gh[k] = sum_c rho_c g_(c,k) = sum_c -(rho z + rho a s_k);  gh[N + k] = sum_c rho z + y^-k (rho z^2 z^j 2^i - rho b s_k^-1),  k = j n + i
+// block = 64 positions x 4 chunk lanes (lane cs takes chunks cs, cs+4, ..), partial sums joined through shared memory: 4x the blocks of a
+// thread-per-position layout (N = 16 384 positions would fill only 64 blocks)
 KERNEL void LB(256, 1) k_verify_scalars(sc_st *gh, const sc_st *tab, vtab_layout t, const sc_st *chal, int chal_stride, int n, int C) {
+    __shared__ sc_st part[2][4][64];
     const size_t N = (size_t)1 << t.lgN;
-    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= N) return;
-    const uint32_t mL = (1u << t.L) - 1, mH = (1u << t.H) - 1, mLm = (1u << t.Lm) - 1;
-    const uint32_t klo = (uint32_t)k & mL, khi = (uint32_t)(k >> t.L);
-    const size_t j = k / n; const int i = (int)(k % n);
-    sc e2; sc_from_u64(e2, 1ULL << i);
+    const int pl = threadIdx.x & 63, cs = threadIdx.x >> 6;
+    const size_t k = (size_t)blockIdx.x * 64 + pl;
     sc g, h; sc_0(g); sc_0(h);
-    for (int c = 0; c < C; c++) {
-        const sc_st *tb = tab + (size_t)c * t.total, *ch = chal + (size_t)c * chal_stride;
-        sc a, b, s, sinv, yk, zj, rz, ra, rb, t1;
-        ld_sc(a, tb + t.oSlo + klo); ld_sc(b, tb + t.oShi + khi); sc_mul(s, a, b);
-        ld_sc(a, tb + t.oSlo + (~klo & mL)); ld_sc(b, tb + t.oShi + (~khi & mH)); sc_mul(sinv, a, b);
-        ld_sc(a, tb + t.oYlo + klo); ld_sc(b, tb + t.oYhi + khi); sc_mul(yk, a, b);
-        ld_sc(a, tb + t.oZlo + ((uint32_t)j & mLm)); ld_sc(b, tb + t.oZhi + (uint32_t)(j >> t.Lm)); sc_mul(zj, a, b);
-        ld_sc(rz, ch); ld_sc(ra, ch + 2); ld_sc(rb, ch + 3);
-        sc_mul(t1, ra, s); sc_add(t1, t1, rz); sc_sub(g, g, t1);
-        sc_mul(zj, zj, e2); sc_mul(t1, rb, sinv); sc_sub(zj, zj, t1); sc_mul(zj, zj, yk); sc_add(h, h, zj); sc_add(h, h, rz);
+    if (k < N) {
+        const uint32_t mL = (1u << t.L) - 1, mH = (1u << t.H) - 1, mLm = (1u << t.Lm) - 1;
+        const uint32_t klo = (uint32_t)k & mL, khi = (uint32_t)(k >> t.L);
+        const size_t j = k / n; const int i = (int)(k % n);
+        sc e2; sc_from_u64(e2, 1ULL << i);
+        for (int c = cs; c < C; c += 4) {
+            const sc_st *tb = tab + (size_t)c * t.total, *ch = chal + (size_t)c * chal_stride;
+            sc a, b, s, sinv, yk, zj, rz, ra, rb, t1;
+            ld_sc(a, tb + t.oSlo + klo); ld_sc(b, tb + t.oShi + khi); sc_mul(s, a, b);
+            ld_sc(a, tb + t.oSlo + (~klo & mL)); ld_sc(b, tb + t.oShi + (~khi & mH)); sc_mul(sinv, a, b);
+            ld_sc(a, tb + t.oYlo + klo); ld_sc(b, tb + t.oYhi + khi); sc_mul(yk, a, b);
+            ld_sc(a, tb + t.oZlo + ((uint32_t)j & mLm)); ld_sc(b, tb + t.oZhi + (uint32_t)(j >> t.Lm)); sc_mul(zj, a, b);
+            ld_sc(rz, ch); ld_sc(ra, ch + 2); ld_sc(rb, ch + 3);
+            sc_mul(t1, ra, s); sc_add(t1, t1, rz); sc_sub(g, g, t1);
+            sc_mul(zj, zj, e2); sc_mul(t1, rb, sinv); sc_sub(zj, zj, t1); sc_mul(zj, zj, yk); sc_add(h, h, zj); sc_add(h, h, rz);
+        }
     }
-    st_sc(gh + k, g); st_sc(gh + N + k, h);
+    st_sc(&part[0][cs][pl], g); st_sc(&part[1][cs][pl], h);
+    __syncthreads();
+    if (cs == 0 && k < N) {
+        for (int q = 1; q < 4; q++) { sc x; ld_sc(x, &part[0][q][pl]); sc_add(g, g, x); ld_sc(x, &part[1][q][pl]); sc_add(h, h, x); }
+        st_sc(gh + k, g); st_sc(gh + N + k, h);
+    }
 }
-KLAUNCH(k_verify_scalars, false, (sc_st *gh, const sc_st *tab, vtab_layout t, const sc_st *chal, int chal_stride, int n, int C), (gh, tab, t, chal, chal_stride, n, C))
+KLAUNCH(k_verify_scalars, true, (sc_st *gh, const sc_st *tab, vtab_layout t, const sc_st *chal, int chal_stride, int n, int C), (gh, tab, t, chal, chal_stride, n, C))
 #endif
 
 // ===================================================================================================================
@@ -1110,7 +1120,7 @@ HD void st_cached(p3_st *p, const ge_cached &c) { uint4 *q = (uint4 *)p; st_fe1(
 HD void ld_cached(ge_cached &c, const p3_st *p) { const uint4 *q = (const uint4 *)p; ld_fe2(c.YplusX, c.YminusX, q); ld_fe2(c.Z, c.T2d, q + 4); }
 HD void acc_add_cached(ge_p3 &acc, const p3_st *p, bool neg) { ge_cached c; ld_cached(c, p); ge_add_cached_signed(acc, acc, c, neg); }
 struct frz_reduce_args { const p3_st *T; const sc_st *msmL, *msmR; p3_st *V; uint32_t F, np, C; };
-struct frz_exit_args { const p3_st *T; const int8_t *digs; p3_st *Gf, *Hf; uint32_t F, Fo, nblk, stride; };
+struct frz_exit_args { const p3_st *T; const int8_t *digs; p3_st *Gf, *Hf, *V; uint32_t F, Fo, nblk, stride; };
 #ifdef KG_FOLD
 // bases[(c*2F + p)*8 + q] = 2^(32 q) * P_p ; P = G"[c][0..F) then H"[c][0..F).  grid (blocks, C)
 KERNEL void LB(128, 4) k_frz_bases(p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride) {
@@ -1180,18 +1190,27 @@ KERNEL void LB(128, 4) k_frz_exit(frz_exit_args a) {
         if (tid < s2) { ge_p3 x, y; ld_p3(x, buf + tid); ld_p3(y, buf + tid + s2); ge_add(x, x, y); st_p3(buf + tid, x); }
         __syncthreads();
     }
-    if (tid == 0) {
-        ge_p3 h; ld_p3(h, buf + 7);
-        for (int w = 6; w >= 0; w--) { for (int k = 0; k < 4; k++) ge_p3_dbl(h, h); acc_add_p3(h, buf + w, false); }
-        st_p3((which ? a.Hf : a.Gf) + (size_t)c * a.stride + i, h);
-    }
+    if (tid < 8) { ge_p3 x; ld_p3(x, buf + tid); st_p3(a.V + ((((size_t)c * 2 + which) * a.Fo + i) * 8 + tid), x); }      // the 8 position sums; chains: k_frz_exit_chain
 }
 KLAUNCH(k_frz_exit, true, (frz_exit_args a), (a))
+// out = sum_pos 16^pos V[pos]: one thread per output so that all 28-doubling chains run side by side (inside k_frz_exit they would keep one
+// lane of every block busy for 2/3 of its life)
+KERNEL void LB(128, 1) k_frz_exit_chain(frz_exit_args a, uint32_t C) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= C * 2 * a.Fo) return;
+    const uint32_t i = idx % a.Fo, which = (idx / a.Fo) & 1, c = idx / (2 * a.Fo);
+    const p3_st *v = a.V + (size_t)idx * 8;
+    ge_p3 h; ld_p3(h, v + 7);
+    for (int w = 6; w >= 0; w--) { for (int k = 0; k < 4; k++) ge_p3_dbl(h, h); acc_add_p3(h, v + w, false); }
+    st_p3((which ? a.Hf : a.Gf) + (size_t)c * a.stride + i, h);
+}
+KLAUNCH(k_frz_exit_chain, false, (frz_exit_args a, uint32_t C), (a, C))
 #endif
 void launch_k_frz_bases(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride);
 void launch_k_frz_tables(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *T, const p3_st *bases, size_t count);
 void launch_k_frz_reduce(dim3 g_, dim3 b_, cudaStream_t s_, frz_reduce_args a);
 void launch_k_frz_exit(dim3 g_, dim3 b_, cudaStream_t s_, frz_exit_args a);
+void launch_k_frz_exit_chain(dim3 g_, dim3 b_, cudaStream_t s_, frz_exit_args a, uint32_t C);
 
 // ===================================================================================================================
 // K6b: the last rounds of the inner-product argument (half-size np <= TAIL_MAX_F/2) in ONE launch, one block per chunk,

@@ -99,7 +99,7 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
         c->e.device = device;
         rt_check(cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking), "cudaStreamCreate");
         // keep freed scratch in the pool between calls
-        cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
+        // (scratch comes from rt.cuh's own block cache, not from the CUDA stream-ordered pool: see rt_malloc)
         unsigned hc = std::thread::hardware_concurrency(); c->e.host_threads = hc ? (int)std::min(hc, 32u) : 8;
         c->e.gstreams.push_back(c->e.stream);
         for (int i = 1; i < 4; i++) { cudaStream_t st; rt_check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate"); c->e.gstreams.push_back(st); }

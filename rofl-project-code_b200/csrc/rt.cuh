@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <cstdlib>
 #ifdef ROFL_EMUL
 #include "cuda_emul.h"
 inline void rt_check(int, const char *) {}
@@ -29,15 +30,17 @@ inline void rt_check(cudaError_t e, const char *what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 void rt_count_launch(const char *name);
-// Scratch allocation.  Small blocks come from the CUDA stream-ordered pool.  Blocks of RT_BIG_BYTES and more (the per-proof vectors and
-// tables, hundreds of MB per call) are kept in a process-wide free list instead: the pool occasionally has to grow when two streams
-// allocate and free large blocks alternately, which costs tens of milliseconds in the middle of a proof.  A block returned on one stream
-// and taken on another is ordered through the event recorded at return time.
-#define RT_BIG_BYTES ((size_t)2 << 20)
+// Scratch allocation: a process-wide cache of device blocks (cudaMalloc once, reused forever).  The CUDA stream-ordered pool was the
+// first choice, but with two chunk groups allocating and freeing on two streams it made one stream wait for the other's long kernels
+// (cross-stream reuse), and forbidding that reuse made the pool grow with real allocations in the middle of a proof.
+// Here a block is preferably handed back to the stream that returned it (no waiting at all); only when none fits is a block of another
+// stream taken, ordered through the event recorded when it was returned.  Sizes are rounded up to 256 B; a block may serve requests down
+// to half its size.
 struct rt_big_block { void *p; size_t n; int dev; cudaStream_t s; cudaEvent_t ev; };
 struct rt_big_cache {
     std::mutex mu; std::vector<rt_big_block> free_list; std::vector<rt_big_block> live;
     void *take(size_t n, cudaStream_t s) {
+        n = (n + 255) / 256 * 256; if (!n) n = 256;
         int dev = 0; cudaGetDevice(&dev);
         rt_big_block b{}; bool found = false;
         { std::lock_guard<std::mutex> lk(mu);
@@ -64,18 +67,17 @@ struct rt_big_cache {
     }
 };
 inline rt_big_cache &rt_bigs() { static rt_big_cache c; return c; }
-inline void *rt_malloc(size_t n, cudaStream_t s) {
-    if (n >= RT_BIG_BYTES) return rt_bigs().take(n, s);
-    void *p = nullptr; rt_check(cudaMallocAsync(&p, n ? n : 16, s), "cudaMallocAsync"); return p;
-}
+inline void *rt_malloc(size_t n, cudaStream_t s) { return rt_bigs().take(n, s); }
 inline void rt_free(void *p, cudaStream_t s) { if (p && !rt_bigs().give(p, s)) cudaFreeAsync(p, s); }
 inline void rt_h2d(void *d, const void *h, size_t n, cudaStream_t s) { rt_check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "h2d"); }
 inline void rt_d2h(void *h, const void *d, size_t n, cudaStream_t s) { rt_check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "d2h"); }
 inline void rt_d2d(void *d, const void *s_, size_t n, cudaStream_t s) { rt_check(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s), "d2d"); }
 inline void rt_memset(void *d, int v, size_t n, cudaStream_t s) { rt_check(cudaMemsetAsync(d, v, n, s), "memset"); }
-// Stream wait by polling: a proof has ~20 host round trips (Fiat-Shamir challenges), each only tens of microseconds of GPU work apart, so
-// the wake-up latency of a blocking cudaStreamSynchronize (and the scheduler's mood on a busy host) would add up; spin instead.
+// Stream wait.  ROFL_SYNC=spin polls cudaStreamQuery instead (a proof has ~20 host round trips; measured on B200: no gain over the
+// blocking call, so blocking stays the default)
 inline void rt_sync(cudaStream_t s) {
+    static const int spin = [] { const char *m = getenv("ROFL_SYNC"); return m && m[0] == 's' ? 1 : 0; }();
+    if (!spin) { rt_check(cudaStreamSynchronize(s), "sync"); return; }
     for (;;) {
         cudaError_t e = cudaStreamQuery(s);
         if (e == cudaSuccess) return;
