@@ -170,6 +170,86 @@ extern "C" int rofl_l2_prove(rofl_ctx *c, const float *v, const uint8_t *blind, 
 extern "C" int rofl_l2_verify(rofl_ctx *c, const uint8_t *proof, size_t plen, const uint8_t commit[32], int range, const uint8_t seed[32]) {
     API_TRY return engine_l2_verify(c->e, proof, plen, commit, range, seed); API_CATCH
 }
+// ---- the two optimised encodings end to end (rofl_service/src/flserver/params.rs): client `encrypt`, server `verify` on the wire fields ----------
+// EncParamsRangeCompressed::encrypt (params.rs:699-743): range proofs + compressed rand proof.  enc_values = D x 64 (L | R).
+extern "C" int rofl_enc_range_compressed_encrypt(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D, int prove_range, size_t n_partition, int n_bits, int frac,
+                                                 const uint8_t seed[32], uint8_t *enc_values64, uint8_t *rand_proof128, uint8_t *range_proofs, size_t *plen, size_t *n_proofs) {
+    API_TRY
+    if (!D) return ROFL_ERR_ARGS;
+    cudaStream_t s = c->e.stream;
+    std::vector<float> clipped(D); rofl_clip_f32_to_range_vec(v, D, prove_range, n_bits, frac, clipped.data());                 // :709
+    staged_in dv(clipped.data(), 4 * D, s), db(blind, 32 * D, s); dev_buf dC(32 * D, s);
+    size_t a = 0, b = 0;
+    int rc = engine_range_prove(c->e, dv.b.as<float>(), db.b.as<uint8_t>(), D, prove_range, n_partition, n_bits, frac, seed, range_proofs, &a, &b, dC.as<uint8_t>());
+    if (plen) *plen = a; if (n_proofs) *n_proofs = b;
+    if (rc) return rc;
+    return engine_crp_prove(c->e, dv.b.as<float>(), dC.as<uint8_t>(), db.b.as<uint8_t>(), D, n_bits, frac, seed, rand_proof128, enc_values64);      // helper_prove_existing
+    API_CATCH
+}
+// EncModelParams::verify, EncRangeCompressed arm (params.rs:236-256): rand proof over ALL pairs, range proofs over the first
+// round(D * check_percentage) Pedersen halves.  1 accept, 0 reject (any Err of the parts is a reject there too), < 0 bad arguments
+extern "C" int rofl_enc_range_compressed_verify(rofl_ctx *c, const uint8_t *enc_values64, size_t D, const uint8_t *rand_proof128, const uint8_t *range_proofs, size_t plen,
+                                                size_t n_proofs, int prove_range, float check_percentage, const uint8_t seed[32]) {
+    API_TRY
+    if (!D || !n_proofs) return ROFL_ERR_ARGS;
+    int ok = engine_crp_verify(c->e, rand_proof128, enc_values64, D);
+    if (ok < 0 && ok != ROFL_ERR_FORMAT && ok != -6) return ok;
+    if (ok != 1) return 0;
+    const size_t num = (size_t)llroundf((float)D * check_percentage);                                                                   // :243-244
+    if (num == 0 || num > D) return 0;
+    cudaStream_t s = c->e.stream;
+    staged_in dp(enc_values64, 64 * D, s); dev_buf dL(32 * D, s), dR(32 * D, s);
+    LAUNCH(k_pairs_split, dim3((unsigned)((D + 255) / 256)), dim3(256), s, dL.as<uint8_t>(), dR.as<uint8_t>(), dp.b.as<uint8_t>(), D);
+    int rr = engine_range_verify(c->e, range_proofs, plen, n_proofs, dL.as<uint8_t>(), num, prove_range, seed);
+    return rr == 1 ? 1 : 0;
+    API_CATCH
+}
+// EncParamsL2Compressed::encrypt (params.rs:797-845): range proofs, the sum-of-squares proof, the compressed rand proof (existing commitments),
+// the per-element square proofs; enc_values = D x 96 (L | R | c_sq), square_proofs = D x 160.
+extern "C" int rofl_enc_l2_compressed_encrypt(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D, int prove_range, size_t n_partition, int l2_range, int n_bits, int frac,
+                                              const uint8_t seed[32], uint8_t *enc_values96, uint8_t *square_proofs160, uint8_t *rand_proof128, uint8_t *range_proofs, size_t *plen,
+                                              size_t *n_proofs, uint8_t *square_range_proof, size_t *sq_plen) {
+    API_TRY
+    if (!D) return ROFL_ERR_ARGS;
+    cudaStream_t s = c->e.stream;
+    std::vector<float> clipped(D); rofl_clip_f32_to_range_vec(v, D, prove_range, n_bits, frac, clipped.data());                 // :806
+    std::vector<uint8_t> rnd(32 * D); { uint8_t k2[32]; derive_key(k2, seed, DOM_RND_VEC, 1); rofl_rnd_scalar_vec(k2, D, rnd.data()); }   // rand_scalars (:805)
+    staged_in dv(clipped.data(), 4 * D, s), db(blind, 32 * D, s), dr(rnd.data(), 32 * D, s); dev_buf dC(32 * D, s), dPairs(64 * D, s), dSp(160 * D, s), dSc(64 * D, s), dEnc(96 * D, s);
+    size_t a = 0, b = 0, q = 0;
+    int rc = engine_range_prove(c->e, dv.b.as<float>(), db.b.as<uint8_t>(), D, prove_range, n_partition, n_bits, frac, seed, range_proofs, &a, &b, dC.as<uint8_t>());
+    if (plen) *plen = a; if (n_proofs) *n_proofs = b;
+    if (rc) return rc;
+    uint8_t sum_commit[32];
+    rc = engine_l2_prove(c->e, clipped.data(), dv.b.as<float>(), dr.b.as<uint8_t>(), D, l2_range, n_bits, frac, seed, square_range_proof, &q, sum_commit);      // :815-821
+    if (sq_plen) *sq_plen = q;
+    if (rc) return rc;
+    std::vector<uint8_t> pairs(64 * D);
+    rc = engine_crp_prove(c->e, dv.b.as<float>(), dC.as<uint8_t>(), db.b.as<uint8_t>(), D, n_bits, frac, seed, rand_proof128, pairs.data());                    // :822-825
+    if (rc) return rc;
+    rc = engine_square_prove(c->e, dv.b.as<float>(), dC.as<uint8_t>(), db.b.as<uint8_t>(), dr.b.as<uint8_t>(), D, n_bits, frac, seed, dSp.as<uint8_t>(), dSc.as<uint8_t>());   // :826-831
+    if (rc) return rc;
+    rt_h2d(dPairs.p, pairs.data(), 64 * D, s);
+    LAUNCH(k_join96, dim3((unsigned)((D + 255) / 256)), dim3(256), s, dEnc.as<uint8_t>(), dPairs.as<uint8_t>(), dSc.as<uint8_t>(), D);                           // merge (:774-784)
+    rt_d2h(enc_values96, dEnc.p, 96 * D, s); rt_d2h(square_proofs160, dSp.p, 160 * D, s); rt_sync(s);
+    return 0;
+    API_CATCH
+}
+// EncModelParams::verify, EncL2Compressed arm (params.rs:257-290): square proofs on (c.L, c_sq), range proofs on c.L, the sum proof on sum c_sq.
+// (The compressed rand proof is NOT checked by that arm of the reference; rofl_crp_verify is available separately.)
+extern "C" int rofl_enc_l2_compressed_verify(rofl_ctx *c, const uint8_t *enc_values96, size_t D, const uint8_t *square_proofs160, const uint8_t *range_proofs, size_t plen,
+                                             size_t n_proofs, const uint8_t *square_range_proof, size_t sq_plen, int prove_range, int l2_range, const uint8_t seed[32]) {
+    API_TRY
+    if (!D || !n_proofs) return ROFL_ERR_ARGS;
+    cudaStream_t s = c->e.stream;
+    staged_in de(enc_values96, 96 * D, s), dsp(square_proofs160, 160 * D, s); dev_buf dL(32 * D, s), dSc(64 * D, s), dCsq(32 * D, s);
+    LAUNCH(k_split96, dim3((unsigned)((D + 255) / 256)), dim3(256), s, dL.as<uint8_t>(), dSc.as<uint8_t>(), dCsq.as<uint8_t>(), de.b.as<uint8_t>(), D);
+    if (engine_square_verify(c->e, dsp.b.as<uint8_t>(), dSc.as<uint8_t>(), D) != 1) return 0;
+    if (engine_range_verify(c->e, range_proofs, plen, n_proofs, dL.as<uint8_t>(), D, prove_range, seed) != 1) return 0;
+    uint8_t sum[32];
+    if (engine_points_sum(c->e, dCsq.as<uint8_t>(), D, sum) != 0) return 0;
+    return engine_l2_verify(c->e, square_range_proof, sq_plen, sum, l2_range, seed) == 1 ? 1 : 0;
+    API_CATCH
+}
 extern "C" int rofl_square_prove_dev(rofl_ctx *c, const float *v, const uint8_t *vc, const uint8_t *r1, const uint8_t *r2, size_t D, int n_bits, int frac,
                                      const uint8_t seed[32], uint8_t *proofs, uint8_t *commits) {
     API_TRY return engine_square_prove(c->e, v, vc, r1, r2, D, n_bits, frac, seed, proofs, commits); API_CATCH

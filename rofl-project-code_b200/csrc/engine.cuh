@@ -1044,6 +1044,20 @@ static int engine_crp_verify(rofl_engine &e, const uint8_t *h_proof, const uint8
     return (id[0] && id[1]) ? 1 : 0;
 }
 
+// sum of D compressed points -> compressed (device in, host out); -4 if one does not decode
+static int engine_points_sum(rofl_engine &e, const uint8_t *d_pts, size_t D, uint8_t *h_out32) {
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    const int nb = (int)std::max<size_t>(1, std::min<size_t>(296, (D + 127) / 128));
+    dev_buf d_part(sizeof(p3_st) * nb, s), d_bad(sizeof(int), s), d_out(32, s);
+    rt_memset(d_bad.p, 0, sizeof(int), s);
+    LAUNCH_COOP(k_points_sum, dim3(nb), dim3(128), s, d_part.as<p3_st>(), d_pts, D, d_bad.as<int>());
+    finalize_args f = {}; f.partial = d_part.as<p3_st>(); f.npartial = nb; f.tabB = e.tabB; f.tabH = e.tabH; f.out32 = d_out.as<uint8_t>(); f.count = 1;
+    run_finalize(s, f);
+    int bad = 0; rt_d2h(h_out32, d_out.p, 32, s); rt_d2h(&bad, d_bad.p, sizeof(int), s); rt_sync(s);
+    return bad ? -4 : 0;
+}
+
 // =============================================================================================================================
 // commitments (pedersen_ops.rs:9-25; el_gamal.rs:57-69), aggregation (params.rs:81-124), discrete log (bsgs32.rs, pedersen_ops.rs:47-53)
 // =============================================================================================================================

@@ -922,6 +922,45 @@ KERNEL void LB(256, 2) k_pairs_split(uint8_t *L, uint8_t *R, const uint8_t *pair
 KLAUNCH(k_pairs_split, false, (uint8_t *L, uint8_t *R, const uint8_t *pairs, size_t D), (L, R, pairs, D))
 #endif
 
+// ===================================================================================================================
+// K12: wire records of the optimised encodings (params.rs:408-458,554-605) and the sum of a point vector
+// ===================================================================================================================
+#ifdef KG_COMMIT
+// SquareRandProofCommitments, 96 bytes = c.L | c.R | c_sq (square_rand_proof/pedersen.rs:21-30)
+KERNEL void LB(256, 2) k_join96(uint8_t *out96, const uint8_t *pairs64, const uint8_t *sq64, size_t D) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    uint8_t b[32];
+    ld_bytes32(b, pairs64 + 64 * i); st_bytes32(out96 + 96 * i, b);
+    ld_bytes32(b, pairs64 + 64 * i + 32); st_bytes32(out96 + 96 * i + 32, b);
+    ld_bytes32(b, sq64 + 64 * i + 32); st_bytes32(out96 + 96 * i + 64, b);          // c_sq of SquareProofCommitments (c_l | c_sq)
+}
+KLAUNCH(k_join96, false, (uint8_t *out96, const uint8_t *pairs64, const uint8_t *sq64, size_t D), (out96, pairs64, sq64, D))
+// -> L[D x 32] (the Pedersen halves the range proofs are about), sq64[D x 64] = c_l | c_sq (SquareProofCommitments), csq[D x 32]
+KERNEL void LB(256, 2) k_split96(uint8_t *L, uint8_t *sq64, uint8_t *csq, const uint8_t *in96, size_t D) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    uint8_t b[32];
+    ld_bytes32(b, in96 + 96 * i); st_bytes32(L + 32 * i, b); st_bytes32(sq64 + 64 * i, b);
+    ld_bytes32(b, in96 + 96 * i + 64); st_bytes32(sq64 + 64 * i + 32, b); st_bytes32(csq + 32 * i, b);
+}
+KLAUNCH(k_split96, false, (uint8_t *L, uint8_t *sq64, uint8_t *csq, const uint8_t *in96, size_t D), (L, sq64, csq, in96, D))
+// partial[blockIdx.x] = sum of this block's share of D compressed points (params.rs:267: enc_values.iter().map(|x| x.c_sq).sum())
+KERNEL void LB(128, 2) k_points_sum(p3_st *partial, const uint8_t *pts32, size_t D, int *bad) {
+    __shared__ p3_st buf[128];
+    const int tid = threadIdx.x;
+    ge_p3 acc; ge_p3_0(acc);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < D; i += (size_t)gridDim.x * blockDim.x) {
+        uint8_t b[32]; ld_bytes32(b, pts32 + 32 * i);
+        ge_p3 p; if (!ge_decompress(p, b)) { atomicOr(bad, 1); continue; }
+        ge_add(acc, acc, p);
+    }
+    block_sum_p3(acc, buf, tid, blockDim.x);
+    if (tid == 0) st_p3(partial + blockIdx.x, acc);
+}
+KLAUNCH(k_points_sum, true, (p3_st *partial, const uint8_t *pts32, size_t D, int *bad), (partial, pts32, D, bad))
+#endif
+
 // ---- launcher declarations (definitions live in the translation unit of each kernel group) ----------------------------
 void launch_k_fb_table_build(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *tab, const uint8_t *pt);
 void launch_k_gens_build(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *G, niels_st *H, int n, int party_begin, int party_end);
@@ -950,6 +989,9 @@ void launch_k_bsgs_solve(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out_sc, flo
 void launch_k_f32_to_scalar(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const float *v, size_t D, int n_bits, int frac, int *flags);
 void launch_k_scalar_to_f32(dim3 g_, dim3 b_, cudaStream_t s_, float *out, const uint8_t *in, size_t D, int n_bits, int frac);
 void launch_k_l2_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, int *flags);
+void launch_k_join96(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out96, const uint8_t *pairs64, const uint8_t *sq64, size_t D);
+void launch_k_split96(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *L, uint8_t *sq64, uint8_t *csq, const uint8_t *in96, size_t D);
+void launch_k_points_sum(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *partial, const uint8_t *pts32, size_t D, int *bad);
 void launch_k_crp_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, pow_tab ctab, int *flags);
 void launch_k_crp_pows(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *out, size_t D, pow_tab ctab);
 void launch_k_pairs_join(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *pairs, const uint8_t *L, const uint8_t *R, size_t D);

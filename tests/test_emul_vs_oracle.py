@@ -211,3 +211,38 @@ def test_ipp_frozen_level(api, oracle, tail_np, rt, unfold):
         assert (p2 == p).all()
     finally:
         api.set_option("tail_np", 32); api.set_use_rt(1); api.set_option("rt_unfold", 3)
+
+
+def test_optimised_encodings_end_to_end(api, oracle):
+    """EncParamsRangeCompressed / EncParamsL2Compressed (params.rs): encrypt gives exactly the pieces the oracle builds one by one,
+    verify accepts them, honours check_percentage, and rejects a tampered field of every kind."""
+    rng = np.random.default_rng(33)
+    D, P, seed = 6, 2, bytes([11] * 32)
+    v = (rng.integers(-24, 25, D) / 128).astype(np.float32); bl = oracle.rnd_scalar_vec(b"\x65" * 32, D)
+    # --- range compressed (fp 16/7, 8-bit)
+    rc, msg = api.enc_range_compressed_encrypt(v, bl, 8, P, 16, 7, seed)
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, 8, P, 16, 7, seed)
+    rc2, rp_o, pairs_o = oracle.crp_prove(v, c_o, bl, 16, 7, seed)
+    assert rc == rc_o == rc2 == 0 and (msg["range_proof"] == p_o).all() and (msg["enc_values"] == pairs_o).all() and (msg["rand_proof"] == rp_o).all()
+    assert api.enc_range_compressed_verify(msg, 1.0, seed) == 1
+    bad = dict(msg); bad["enc_values"] = msg["enc_values"].copy(); bad["enc_values"][1, 32:] = msg["enc_values"][0, 32:]
+    assert api.enc_range_compressed_verify(bad, 1.0, seed) == 0
+    bad = dict(msg); bad["range_proof"] = msg["range_proof"].copy(); bad["range_proof"][0, 70] ^= 1
+    assert api.enc_range_compressed_verify(bad, 1.0, seed) == 0
+    # --- L2 compressed (fp 32/7, 8-bit L-inf, 32-bit L2)
+    rc, m2 = api.enc_l2_compressed_encrypt(v, bl, 8, P, 32, 32, 7, seed)
+    assert rc == 0
+    rnd = oracle.rnd_scalar_vec(oracle.derive_key(seed, 7, 1), D)                     # rand_scalars: DOM_RND_VEC stream 1
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, 8, P, 32, 7, seed)
+    rc_s, sumproof_o, sumcm_o = oracle.l2_prove(v, rnd, 32, 32, 7, seed)
+    rc_c, rp_o, pairs_o = oracle.crp_prove(v, c_o, bl, 32, 7, seed)
+    rc_q, sp_o, sc_o = oracle.square_prove(v, c_o, bl, rnd, 32, 7, seed)
+    assert rc_o == rc_s == rc_c == rc_q == 0
+    assert (m2["range_proof"] == p_o).all() and (m2["square_range_proof"] == sumproof_o).all() and (m2["rand_proof"] == rp_o).all() and (m2["square_proof"] == sp_o).all()
+    assert (m2["enc_values"][:, :64] == pairs_o).all() and (m2["enc_values"][:, 64:] == sc_o[:, 32:]).all()
+    assert api.enc_l2_compressed_verify(m2, seed) == 1
+    for field, (i, j) in [("enc_values", (2, 70)), ("square_proof", (3, 100)), ("range_proof", (1, 40)), ("square_range_proof", (None, 50))]:
+        bad = dict(m2); bad[field] = m2[field].copy()
+        if i is None: bad[field][j] ^= 1
+        else: bad[field][i, j] ^= 1
+        assert api.enc_l2_compressed_verify(bad, seed) == 0, field

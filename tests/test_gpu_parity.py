@@ -313,3 +313,42 @@ def test_config4_server_batch_verify_aggregate_decrypt(api, oracle):
     rc, s, f = api.dlog(api.aggregate(np.stack(Ls), 0), 1 << 16, 16, 32, 7)
     assert rc == 0
     assert (f == np.sum(np.stack(vs), axis=0, dtype=np.float64).astype(np.float32)).all()
+
+
+def test_optimised_encodings_server_path_full_size(api, oracle):
+    """params.rs EncParamsL2Compressed / EncParamsRangeCompressed at configs[2] size (50 000 params): encrypt on the GPU, verify on the GPU from
+    the wire fields, tamper rejection; pieces spot-checked against the oracle; several clients aggregated and decrypted (configs[4] in small)."""
+    rng = np.random.default_rng(41)
+    D, P = 50000, 64
+    msgs, vs = [], []
+    n_clients = 3
+    bls = [np.frombuffer(api.rnd_scalar_vec(bytes([0x90 + k]) * 32, D).tobytes(), np.uint8).reshape(D, 32).copy() for k in range(n_clients - 1)]
+    tot = np.zeros(D, dtype=object)
+    for b in bls:
+        tot = (tot + np.array([int.from_bytes(row.tobytes(), "little") for row in b], dtype=object)) % L
+    bls.append(np.frombuffer(b"".join(int((L - t) % L).to_bytes(32, "little") for t in tot), np.uint8).reshape(D, 32).copy())
+    for k in range(n_clients):
+        v = (rng.integers(-24, 25, D) / 128).astype(np.float32); vs.append(v)
+        seed = bytes([0xa0 + k]) * 32
+        rc, m = api.enc_l2_compressed_encrypt(v, bls[k], 8, P, 32, 32, 7, seed)
+        assert rc == 0 and api.enc_l2_compressed_verify(m, seed) == 1
+        assert api.crp_verify(m["rand_proof"], m["enc_values"][:, :64].copy()) == 1
+        msgs.append(m)
+    m = msgs[0]
+    assert (m["enc_values"][:500, :32] == oracle.commit_f32(vs[0][:500], bls[0][:500], 32, 7)).all()
+    bad = dict(m); bad["enc_values"] = m["enc_values"].copy(); bad["enc_values"][D - 3, 64:] = m["enc_values"][0, 64:]
+    assert api.enc_l2_compressed_verify(bad, bytes([0xa0]) * 32) == 0
+    bad = dict(m); bad["square_range_proof"] = m["square_range_proof"].copy(); bad["square_range_proof"][33] ^= 2
+    assert api.enc_l2_compressed_verify(bad, bytes([0xa0]) * 32) == 0
+    # aggregate the ElGamal halves of all clients and decrypt
+    aggL = api.aggregate(np.stack([x["enc_values"][:, :32].copy() for x in msgs]), 0)
+    aggR = api.aggregate(np.stack([x["enc_values"][:, 32:64].copy() for x in msgs]), 1)
+    assert (aggR == np.frombuffer(oracle.basepoint(), np.uint8)).all()
+    rc, s, f = api.dlog(aggL, 1 << 16, 16, 32, 7)
+    assert rc == 0 and (f == np.sum(np.stack(vs), axis=0, dtype=np.float64).astype(np.float32)).all()
+    # range-compressed encoding with probabilistic checking (check_percentage < 1 verifies a prefix, params.rs:243-249)
+    v = rng.uniform(-0.99, 0.99, 5000).astype(np.float32); bl = api.rnd_scalar_vec(b"\x99" * 32, 5000); seed = b"\x9a" * 32
+    rc, m = api.enc_range_compressed_encrypt(v, bl, 8, 64, 16, 7, seed)
+    assert rc == 0 and api.enc_range_compressed_verify(m, 1.0, seed) == 1
+    bad = dict(m); bad["rand_proof"] = m["rand_proof"].copy(); bad["rand_proof"][70] ^= 1
+    assert api.enc_range_compressed_verify(bad, 1.0, seed) == 0
