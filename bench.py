@@ -121,6 +121,7 @@ def main():
                     e2e=dict(value=r["value"], unit="elements/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
         print(json.dumps(line)); return
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's own version / debug lines off stdout: stdout carries the one JSON line
     import torch
     import torch.distributed as dist
     import __graft_entry__ as g
