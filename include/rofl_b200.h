@@ -115,6 +115,18 @@ int rofl_l2_verify(rofl_ctx *, const uint8_t *proof, size_t proof_len, const uin
 int rofl_crp_prove(rofl_ctx *, const float *v, const uint8_t *value_com32, const uint8_t *blind32, size_t D, int n_bits, int frac, const uint8_t seed[32],
                    uint8_t *out_proof128, uint8_t *out_pairs64);
 int rofl_crp_verify(rofl_ctx *, const uint8_t *proof128, const uint8_t *pairs64, size_t D);
+/* The un-optimised encodings' per-element proofs (enc types 2 and 3, params.rs:468-511,608-646):
+ *   rand_proof_vec::{create_randproof_vec, create_randproof_vec_existing, verify_randproof_vec}  (rand_proof_vec/mod.rs:14-118): RandProof = 128 B
+ *       (C'_L | C'_R | z_m | z_r, rand_proof/mod.rs:87-97) over 64-byte ElGamal pairs;
+ *   square_rand_proof_vec::{create_l2rangeproof_vec, create_l2rangeproof_vec_existing, verify_l2rangeproof_vec} (square_rand_proof_vec/mod.rs:18-160):
+ *       SquareRandProof = 192 B over SquareRandProofCommitments = 96 B (c.L | c.R | c_sq).
+ * value_com32 = existing Pedersen commitments (the *_existing variants) or NULL.  prove: 0 ok, ROFL_ERR_POINT, ROFL_ERR_NAN; verify: 1 / 0 / ROFL_ERR_FORMAT. */
+int rofl_rand_prove(rofl_ctx *, const float *v, const uint8_t *value_com32, const uint8_t *blind32, size_t D, int n_bits, int frac, const uint8_t seed[32],
+                    uint8_t *out_proofs128, uint8_t *out_pairs64);
+int rofl_rand_verify(rofl_ctx *, const uint8_t *proofs128, const uint8_t *pairs64, size_t D);
+int rofl_square_rand_prove(rofl_ctx *, const float *v, const uint8_t *value_com32, const uint8_t *r1_32, const uint8_t *r2_32, size_t D, int n_bits, int frac,
+                           const uint8_t seed[32], uint8_t *out_proofs192, uint8_t *out_commits96);
+int rofl_square_rand_verify(rofl_ctx *, const uint8_t *proofs192, const uint8_t *commits96, size_t D);
 /* The two optimised encodings of rofl_service end to end, on the wire fields of flservice.proto (the protobuf framing stays on the Rust side):
  *   EncParamsRangeCompressed::{encrypt, verify}  (params.rs:699-743, 236-256)   enc_values = D x 64 (L | R), rand_proof 128 B, range_proof[]
  *   EncParamsL2Compressed::{encrypt, verify}     (params.rs:797-845, 257-290)   enc_values = D x 96 (L | R | c_sq), square_proof D x 160,

@@ -155,6 +155,22 @@ def square_prove(values, value_com, r1, r2, n_bits=32, frac=7, seed=SEED0):
 def square_verify(proofs, commits):
     p = _u8(proofs).reshape(-1, 160); c = _u8(commits).reshape(-1, 64)
     return lib().orc_square_verify(_p(p), _p(c), C.c_size_t(p.shape[0]))
+def rand_prove(values, value_com, blind, n_bits=16, frac=7, seed=SEED0):
+    """rand_proof_vec::create_randproof_vec (value_com None) / _existing -> (rc, proofs[D, 128], pairs[D, 64])"""
+    v = _f32(values); D = v.size; proofs = np.zeros((D, 128), np.uint8); pairs = np.zeros((D, 64), np.uint8)
+    rc = lib().orc_rand_prove(_p(proofs), _p(pairs), _p(v), None if value_com is None else _p(_u8(value_com, 32 * D)), _p(_u8(blind, 32 * D)), C.c_size_t(D), n_bits, frac, _p(_u8(seed, 32)))
+    return rc, proofs, pairs
+def rand_verify(proofs, pairs):
+    p = _u8(proofs).reshape(-1, 128); c = _u8(pairs).reshape(-1, 64)
+    return lib().orc_rand_verify(_p(p), _p(c), C.c_size_t(p.shape[0]))
+def square_rand_prove(values, value_com, r1, r2, n_bits=32, frac=7, seed=SEED0):
+    """square_rand_proof_vec::create_l2rangeproof_vec(_existing) -> (rc, proofs[D, 192], commits[D, 96])"""
+    v = _f32(values); D = v.size; proofs = np.zeros((D, 192), np.uint8); commits = np.zeros((D, 96), np.uint8)
+    rc = lib().orc_square_rand_prove(_p(proofs), _p(commits), _p(v), None if value_com is None else _p(_u8(value_com, 32 * D)), _p(_u8(r1, 32 * D)), _p(_u8(r2, 32 * D)), C.c_size_t(D), n_bits, frac, _p(_u8(seed, 32)))
+    return rc, proofs, commits
+def square_rand_verify(proofs, commits):
+    p = _u8(proofs).reshape(-1, 192); c = _u8(commits).reshape(-1, 96)
+    return lib().orc_square_rand_verify(_p(p), _p(c), C.c_size_t(p.shape[0]))
 def crp_prove(values, value_com, blind, n_bits=16, frac=7, seed=SEED0):
     """CompressedRandProof::helper_prove (value_com None) / helper_prove_existing -> (rc, proof[128], pairs[D, 64])"""
     v = _f32(values); D = v.size

@@ -21,7 +21,7 @@
 
 #define EXPORT __attribute__((visibility("default")))
 
-enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE = 4, DOM_L2_VERIFY = 5, DOM_CRP = 6, DOM_RND_VEC = 7 };
+enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE = 4, DOM_L2_VERIFY = 5, DOM_CRP = 6, DOM_RND_VEC = 7, DOM_RANDPROOF = 8, DOM_SQUARE_RAND = 9 };
 
 /* key = SHA3-256(seed || u32le(domain) || u64le(index)) */
 EXPORT void orc_derive_key(uint8_t out[32], const uint8_t seed[32], uint32_t domain, uint64_t index) {
@@ -317,6 +317,101 @@ EXPORT int orc_square_prove(uint8_t *proofs_out, uint8_t *commits_out, const flo
         sc_tobytes(o + 64, &zm); sc_tobytes(o + 96, &zr1); sc_tobytes(o + 128, &zr2);
     }
     return rc;
+}
+/* RandProof per element (rand_proof/{mod,party,dealer}.rs, rand_proof_vec/mod.rs:14-118).  pairs_out D*64 (L|R), proofs_out D*128 (C'_L|C'_R|z_m|z_r).
+ * value_com NULL: Party::new (L = commit(m, r)); else PartyExisting.  0 ok, -4 bad point */
+static void rp_challenge(sc *c, const uint8_t pair[64], const uint8_t cp[64]) {
+    transcript t; transcript_init(&t, "RandProof");
+    transcript_append(&t, "dom-sep", (const uint8_t *)"randomness proof v1", 19);
+    transcript_append(&t, "C", pair, 64); transcript_append(&t, "C_prime", cp, 64);               /* dealer.rs:20-21,42 */
+    ts_challenge(&t, "c", c);
+}
+EXPORT int orc_rand_prove(uint8_t *proofs_out, uint8_t *pairs_out, const float *values, const uint8_t *value_com, const uint8_t *rv, size_t D, int n_bits, int frac, const uint8_t seed[32]) {
+    if (!fp_ok(n_bits, frac)) return -2;
+    init_pc(); uint8_t key[32]; orc_derive_key(key, seed, DOM_RANDPROOF, 0); int rc = 0; ge Bp; ge_base(&Bp);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < D; i++) {
+        sc m, r, mp, rp, c, zm, zr; ge L, R, Lp, Rp;
+        if (f32_to_scalar(&m, values[i], n_bits, frac)) { rc = -98; continue; }
+        sc_from_bytes_mod_order(&r, rv + 32 * i);
+        if (value_com) { if (!ge_decompress(&L, value_com + 32 * i)) { rc = -4; continue; } } else pc_commit(&L, &PC, &m, &r);
+        ge_scalarmult(&R, &r, &Bp);
+        rng_scalar_at(key, 2 * i, &mp); rng_scalar_at(key, 2 * i + 1, &rp);                        /* party.rs:23-24 */
+        pc_commit(&Lp, &PC, &mp, &rp); ge_scalarmult(&Rp, &rp, &Bp);
+        uint8_t *o = proofs_out + 128 * i, *po = pairs_out + 64 * i;
+        ge_compress(po, &L); ge_compress(po + 32, &R); ge_compress(o, &Lp); ge_compress(o + 32, &Rp);
+        rp_challenge(&c, po, o);
+        sc_muladd(&zm, &m, &c, &mp); sc_muladd(&zr, &r, &c, &rp);                                  /* party.rs:76-80 */
+        sc_tobytes(o + 64, &zm); sc_tobytes(o + 96, &zr);
+    }
+    return rc;
+}
+EXPORT int orc_rand_verify(const uint8_t *proofs, const uint8_t *pairs, size_t D) {              /* rand_proof/mod.rs:64-85, rand_proof_vec/mod.rs:91-118 */
+    init_pc(); int res = 1, err = 0; ge Bp; ge_base(&Bp);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < D; i++) {
+        const uint8_t *o = proofs + 128 * i, *po = pairs + 64 * i;
+        ge L, R, Lp, Rp, lhs, rhs, T; sc zm, zr, c;
+        if (!ge_decompress(&L, po) || !ge_decompress(&R, po + 32) || !ge_decompress(&Lp, o) || !ge_decompress(&Rp, o + 32) ||
+            !sc_from_canonical_bytes(&zm, o + 64) || !sc_from_canonical_bytes(&zr, o + 96)) { err = -1; continue; }
+        rp_challenge(&c, po, o);
+        int ok = 1;
+        pc_commit(&lhs, &PC, &zm, &zr); ge_scalarmult(&T, &c, &L); ge_add(&rhs, &Lp, &T); ok &= ge_eq(&lhs, &rhs);
+        ge_scalarmult(&lhs, &zr, &Bp); ge_scalarmult(&T, &c, &R); ge_add(&rhs, &Rp, &T); ok &= ge_eq(&lhs, &rhs);
+        if (!ok) res = 0;
+    }
+    return err ? err : res;
+}
+/* SquareRandProof per element (square_rand_proof/{mod,party,dealer,constants}.rs, square_rand_proof_vec/mod.rs:18-160).
+ * commits_out D*96 (c.L|c.R|c_sq), proofs_out D*192 (C'.L|C'.R|C'_sq|z_m|z_r1|z_r2) */
+static void srp_challenge(sc *c, const uint8_t com[96], const uint8_t cp[96]) {
+    transcript t; transcript_init(&t, "SquareRandProof");
+    transcript_append(&t, "dom-sep", (const uint8_t *)"randomness proof v1", 19);
+    transcript_append(&t, "C_eg", com, 64); transcript_append(&t, "C_ped", com + 64, 32);         /* dealer.rs:23-25 */
+    transcript_append(&t, "C_prime_eg", cp, 64); transcript_append(&t, "C_prime_ped", cp + 64, 32);
+    ts_challenge(&t, "c", c);
+}
+EXPORT int orc_square_rand_prove(uint8_t *proofs_out, uint8_t *commits_out, const float *values, const uint8_t *value_com, const uint8_t *r1v, const uint8_t *r2v, size_t D,
+                                 int n_bits, int frac, const uint8_t seed[32]) {
+    if (!fp_ok(n_bits, frac)) return -2;
+    init_pc(); uint8_t key[32]; orc_derive_key(key, seed, DOM_SQUARE_RAND, 0); int rc = 0; ge Bp; ge_base(&Bp);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < D; i++) {
+        sc m, r1, r2, msq, mp, r1p, r2p, c, zm, zr1, zr2, tmp; ge L, R, Csq, Lp, Rp, Csqp, T;
+        if (f32_to_scalar(&m, values[i], n_bits, frac)) { rc = -98; continue; }
+        sc_from_bytes_mod_order(&r1, r1v + 32 * i); sc_from_bytes_mod_order(&r2, r2v + 32 * i);
+        if (value_com) { if (!ge_decompress(&L, value_com + 32 * i)) { rc = -4; continue; } } else pc_commit(&L, &PC, &m, &r1);
+        ge_scalarmult(&R, &r1, &Bp);
+        sc_mul(&msq, &m, &m); pc_commit(&Csq, &PC, &msq, &r2);                                      /* party.rs:31-32 */
+        rng_scalar_at(key, 3 * i, &mp); rng_scalar_at(key, 3 * i + 1, &r1p); rng_scalar_at(key, 3 * i + 2, &r2p);
+        pc_commit(&Lp, &PC, &mp, &r1p); ge_scalarmult(&Rp, &r1p, &Bp);
+        ge_scalarmult(&Csqp, &mp, &L); ge_scalarmult(&T, &r2p, &PC.B_blinding); ge_add(&Csqp, &Csqp, &T);
+        uint8_t *o = proofs_out + 192 * i, *co = commits_out + 96 * i;
+        ge_compress(co, &L); ge_compress(co + 32, &R); ge_compress(co + 64, &Csq); ge_compress(o, &Lp); ge_compress(o + 32, &Rp); ge_compress(o + 64, &Csqp);
+        srp_challenge(&c, co, o);
+        sc_muladd(&zm, &m, &c, &mp); sc_muladd(&zr1, &r1, &c, &r1p);
+        sc_mul(&tmp, &m, &r1); sc_sub(&tmp, &r2, &tmp); sc_muladd(&zr2, &tmp, &c, &r2p);
+        sc_tobytes(o + 96, &zm); sc_tobytes(o + 128, &zr1); sc_tobytes(o + 160, &zr2);
+    }
+    return rc;
+}
+EXPORT int orc_square_rand_verify(const uint8_t *proofs, const uint8_t *commits, size_t D) {     /* square_rand_proof/mod.rs:76-112 */
+    init_pc(); int res = 1, err = 0; ge Bp; ge_base(&Bp);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < D; i++) {
+        const uint8_t *o = proofs + 192 * i, *co = commits + 96 * i;
+        ge L, R, Csq, Lp, Rp, Csqp, lhs, rhs, T; sc zm, zr1, zr2, c;
+        if (!ge_decompress(&L, co) || !ge_decompress(&R, co + 32) || !ge_decompress(&Csq, co + 64) || !ge_decompress(&Lp, o) || !ge_decompress(&Rp, o + 32) || !ge_decompress(&Csqp, o + 64) ||
+            !sc_from_canonical_bytes(&zm, o + 96) || !sc_from_canonical_bytes(&zr1, o + 128) || !sc_from_canonical_bytes(&zr2, o + 160)) { err = -1; continue; }
+        srp_challenge(&c, co, o);
+        int ok = 1;
+        pc_commit(&lhs, &PC, &zm, &zr1); ge_scalarmult(&T, &c, &L); ge_add(&rhs, &Lp, &T); ok &= ge_eq(&lhs, &rhs);
+        ge_scalarmult(&lhs, &zr1, &Bp); ge_scalarmult(&T, &c, &R); ge_add(&rhs, &Rp, &T); ok &= ge_eq(&lhs, &rhs);
+        ge_scalarmult(&lhs, &zm, &L); ge_scalarmult(&T, &zr2, &PC.B_blinding); ge_add(&lhs, &lhs, &T);
+        ge_scalarmult(&T, &c, &Csq); ge_add(&rhs, &Csqp, &T); ok &= ge_eq(&lhs, &rhs);
+        if (!ok) res = 0;
+    }
+    return err ? err : res;
 }
 /* CompressedRandProof (compressed_rand_proof/mod.rs:43-102, party.rs:17-100, dealer.rs:20-94, constants.rs:5-7):
  * ONE sigma proof that every ElGamal pair (L_i, R_i) = (m_i B + r_i H, r_i B) of an update is well formed.

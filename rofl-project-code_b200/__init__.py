@@ -42,4 +42,4 @@ def context(device=None):
     return _ctx[device]
 
 
-from . import fp, conversion32, pedersen_ops, range_proof_vec, l2_range_proof_vec, square_proof_vec, compressed_rand_proof, bsgs32, sharding, params  # noqa: E402,F401
+from . import fp, conversion32, pedersen_ops, range_proof_vec, l2_range_proof_vec, square_proof_vec, compressed_rand_proof, rand_proof_vec, square_rand_proof_vec, bsgs32, sharding, params  # noqa: E402,F401

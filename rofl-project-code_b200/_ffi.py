@@ -38,6 +38,10 @@ _SIGS = {
     "rofl_enc_range_compressed_verify": (C.c_int, [c_vp, c_u8p, c_sz, c_u8p, c_u8p, c_sz, c_sz, C.c_int, C.c_float, c_u8p]),
     "rofl_enc_l2_compressed_encrypt": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, c_sz, C.c_int, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, C.POINTER(c_sz), C.POINTER(c_sz), c_u8p, C.POINTER(c_sz)]),
     "rofl_enc_l2_compressed_verify": (C.c_int, [c_vp, c_u8p, c_sz, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_sz, C.c_int, C.c_int, c_u8p]),
+    "rofl_rand_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p]),
+    "rofl_rand_verify": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz]),
+    "rofl_square_rand_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_u8p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p]),
+    "rofl_square_rand_verify": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz]),
     "rofl_crp_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p]),
     "rofl_crp_verify": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz]),
     "rofl_square_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_u8p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p]),
@@ -119,6 +123,29 @@ class Api:
             raise self._err(rc)
         return out
 
+    # ---- per-element proofs of the un-optimised encodings
+    def rand_prove(self, v, value_com, blind, n_bits, frac, seed=SEED0):
+        v = _f32(v); D = v.size; b = _u8(blind, 32 * D); vc = None if value_com is None else _u8(value_com, 32 * D)
+        proofs = np.zeros((D, 128), np.uint8); pairs = np.zeros((D, 64), np.uint8)
+        rc = self.lib.rofl_rand_prove(self.h, _ptr(v), _ptr(vc), _ptr(b), D, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proofs), _ptr(pairs))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc, proofs, pairs
+    def rand_verify(self, proofs, pairs):
+        p = _u8(proofs).reshape(-1, 128); c = _u8(pairs).reshape(-1, 64)
+        rc = self.lib.rofl_rand_verify(self.h, _ptr(p), _ptr(c), p.shape[0])
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc
+    def square_rand_prove(self, v, value_com, r1, r2, n_bits, frac, seed=SEED0):
+        v = _f32(v); D = v.size; vc = None if value_com is None else _u8(value_com, 32 * D)
+        proofs = np.zeros((D, 192), np.uint8); commits = np.zeros((D, 96), np.uint8)
+        rc = self.lib.rofl_square_rand_prove(self.h, _ptr(v), _ptr(vc), _ptr(_u8(r1, 32 * D)), _ptr(_u8(r2, 32 * D)), D, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proofs), _ptr(commits))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc, proofs, commits
+    def square_rand_verify(self, proofs, commits):
+        p = _u8(proofs).reshape(-1, 192); c = _u8(commits).reshape(-1, 96)
+        rc = self.lib.rofl_square_rand_verify(self.h, _ptr(p), _ptr(c), p.shape[0])
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc
     # ---- compressed randomness proof: (rc, proof[128], pairs[D, 64]) / 1|0|<0
     def crp_prove(self, v, value_com, blind, n_bits, frac, seed=SEED0):
         v = _f32(v); D = v.size; b = _u8(blind, 32 * D)

@@ -170,6 +170,34 @@ extern "C" int rofl_l2_prove(rofl_ctx *c, const float *v, const uint8_t *blind, 
 extern "C" int rofl_l2_verify(rofl_ctx *c, const uint8_t *proof, size_t plen, const uint8_t commit[32], int range, const uint8_t seed[32]) {
     API_TRY return engine_l2_verify(c->e, proof, plen, commit, range, seed); API_CATCH
 }
+// rand_proof_vec (RandProof, 128 B per element over 64-byte ElGamal pairs) and square_rand_proof_vec (SquareRandProof, 192 B over 96-byte commitments)
+static int sigma_prove_host(rofl_ctx *c, int kind, const float *v, const uint8_t *vc, const uint8_t *r1, const uint8_t *r2, size_t D, int n_bits, int frac, const uint8_t seed[32],
+                            uint8_t *proofs, uint8_t *commits) {
+    if (!D) return 0;
+    const size_t pw = kind == 1 ? 128 : 192, cw = kind == 1 ? 64 : 96;
+    cudaStream_t s = c->e.stream;
+    staged_in dv(v, 4 * D, s), dvc(vc, vc ? 32 * D : 0, s), d1(r1, 32 * D, s), d2(r2, r2 ? 32 * D : 0, s); dev_buf dp(pw * D, s), dc(cw * D, s);
+    int rc = engine_sigma_prove(c->e, kind, dv.b.as<float>(), vc ? dvc.b.as<uint8_t>() : nullptr, d1.b.as<uint8_t>(), r2 ? d2.b.as<uint8_t>() : nullptr, D, n_bits, frac, seed, dp.as<uint8_t>(), dc.as<uint8_t>());
+    if (rc) return rc;
+    rt_d2h(proofs, dp.p, pw * D, s); rt_d2h(commits, dc.p, cw * D, s); rt_sync(s);
+    return 0;
+}
+static int sigma_verify_host(rofl_ctx *c, int kind, const uint8_t *proofs, const uint8_t *commits, size_t D) {
+    if (!D) return 1;
+    const size_t pw = kind == 1 ? 128 : 192, cw = kind == 1 ? 64 : 96;
+    staged_in dp(proofs, pw * D, c->e.stream), dc(commits, cw * D, c->e.stream);
+    return engine_sigma_verify(c->e, kind, dp.b.as<uint8_t>(), dc.b.as<uint8_t>(), D);
+}
+extern "C" int rofl_rand_prove(rofl_ctx *c, const float *v, const uint8_t *value_com32, const uint8_t *blind32, size_t D, int n_bits, int frac, const uint8_t seed[32],
+                               uint8_t *proofs128, uint8_t *pairs64) {
+    API_TRY return sigma_prove_host(c, 1, v, value_com32, blind32, nullptr, D, n_bits, frac, seed, proofs128, pairs64); API_CATCH
+}
+extern "C" int rofl_rand_verify(rofl_ctx *c, const uint8_t *proofs128, const uint8_t *pairs64, size_t D) { API_TRY return sigma_verify_host(c, 1, proofs128, pairs64, D); API_CATCH }
+extern "C" int rofl_square_rand_prove(rofl_ctx *c, const float *v, const uint8_t *value_com32, const uint8_t *r1_32, const uint8_t *r2_32, size_t D, int n_bits, int frac,
+                                      const uint8_t seed[32], uint8_t *proofs192, uint8_t *commits96) {
+    API_TRY return sigma_prove_host(c, 2, v, value_com32, r1_32, r2_32, D, n_bits, frac, seed, proofs192, commits96); API_CATCH
+}
+extern "C" int rofl_square_rand_verify(rofl_ctx *c, const uint8_t *proofs192, const uint8_t *commits96, size_t D) { API_TRY return sigma_verify_host(c, 2, proofs192, commits96, D); API_CATCH }
 // ---- the two optimised encodings end to end (rofl_service/src/flserver/params.rs): client `encrypt`, server `verify` on the wire fields ----------
 // EncParamsRangeCompressed::encrypt (params.rs:699-743): range proofs + compressed rand proof.  enc_values = D x 64 (L | R).
 extern "C" int rofl_enc_range_compressed_encrypt(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D, int prove_range, size_t n_partition, int n_bits, int frac,

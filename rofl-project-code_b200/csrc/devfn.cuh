@@ -224,3 +224,99 @@ HD int square_verify_one(const uint8_t *proof160, const uint8_t *commit64, const
     bool v2 = ge_eq(lhs, Csqp);
     return (v1 && v2) ? 1 : 0;
 }
+
+// ---- per-element ElGamal randomness proof (rand_proof/{mod,party,dealer}.rs; rand_proof_vec/mod.rs:14-118) -- enc type 2 -----------------
+//   pair = (L, R) = (m B + r H, r B) (L may be an existing commitment: PartyExisting), C' = commit(m', r'), c = H(pair, C'),
+//   z_m = m' + m c, z_r = r' + r c;  proof = C'_L | C'_R | z_m | z_r (128 B).  Nonces: blocks 2i, 2i+1 of the key stream.
+HDNI void rp_transcript_challenge(sc &c, const uint8_t pair[64], const uint8_t cprime[64]) {
+    transcript t; transcript_init(t, "RandProof");                                           // rand_proof_vec/mod.rs:32,73,104
+    const uint8_t ds[19] = {'r', 'a', 'n', 'd', 'o', 'm', 'n', 'e', 's', 's', ' ', 'p', 'r', 'o', 'o', 'f', ' ', 'v', '1'};
+    transcript_append(t, "dom-sep", ds, 19);
+    transcript_append(t, "C", pair, 64); transcript_append(t, "C_prime", cprime, 64);       // dealer.rs:20-21,42
+    uint8_t buf[64]; transcript_challenge(t, "c", buf, 64);
+    sc_from_bytes_wide(c, buf);
+}
+// value_com32 null: L = commit(m, r) (Party::new), else the existing commitment.  returns 0, -1 NaN, -4 existing commitment does not decode
+HD int rand_prove_one(uint8_t *proof128, uint8_t *pair64, float v, const uint8_t *value_com32, const uint8_t *rb, const uint32_t key[8], uint64_t idx,
+                      int n_bits, int frac, const niels_st *tabB, const niels_st *tabH) {
+    sc m, r, mp, rp, c, zm, zr; ge_p3 P;
+    if (f32_to_scalar(m, v, n_bits, frac)) return -1;
+    sc_from_bytes_mod_order(r, rb);
+    if (value_com32) { if (!ge_decompress(P, value_com32)) return -4; for (int i = 0; i < 32; i++) pair64[i] = value_com32[i]; }
+    else { ge_p3_0(P); fb_mul_acc(P, tabB, m, 32); fb_mul_acc(P, tabH, r, 32); ge_compress(pair64, P); }
+    ge_p3_0(P); fb_mul_acc(P, tabB, r, 32); ge_compress(pair64 + 32, P);                     // R = r B (el_gamal.rs:57-69)
+    nonce_scalar(mp, key, 2 * idx); nonce_scalar(rp, key, 2 * idx + 1);                      // party.rs:23-24
+    ge_p3_0(P); fb_mul_acc(P, tabB, mp, 32); fb_mul_acc(P, tabH, rp, 32); ge_compress(proof128, P);
+    ge_p3_0(P); fb_mul_acc(P, tabB, rp, 32); ge_compress(proof128 + 32, P);
+    rp_transcript_challenge(c, pair64, proof128);
+    sc_muladd(zm, m, c, mp); sc_muladd(zr, r, c, rp);                                       // party.rs:76-80
+    sc_tobytes(proof128 + 64, zm); sc_tobytes(proof128 + 96, zr);
+    return 0;
+}
+// 1 valid, 0 invalid, -1 FormatError (rand_proof/mod.rs:64-85,99-118)
+HD int rand_verify_one(const uint8_t *proof128, const uint8_t *pair64, const niels_st *tabB, const niels_st *tabH) {
+    ge_p3 L, R, Lp, Rp, lhs, rhs, T; sc zm, zr, c;
+    bool ok = ge_decompress(L, pair64) & ge_decompress(R, pair64 + 32) & ge_decompress(Lp, proof128) & ge_decompress(Rp, proof128 + 32);
+    sc_frombytes(zm, proof128 + 64); sc_frombytes(zr, proof128 + 96);
+    ok = ok && sc_is_canonical(zm) && sc_is_canonical(zr);
+    if (!ok) return -1;
+    rp_transcript_challenge(c, pair64, proof128);
+    ge_tab8 tl, tr; ge_tab8_build(tl, L); ge_tab8_build(tr, R);
+    ge_p3_0(lhs); fb_mul_acc(lhs, tabB, zm, 32); fb_mul_acc(lhs, tabH, zr, 32);             // z_m B + z_r H == C'_L + c L
+    ge_double_scalarmult_r16(T, c, tl, nullptr, nullptr); ge_add(rhs, Lp, T);
+    const bool v1 = ge_eq(lhs, rhs);
+    ge_p3_0(lhs); fb_mul_acc(lhs, tabB, zr, 32);                                             // z_r B == C'_R + c R
+    ge_double_scalarmult_r16(T, c, tr, nullptr, nullptr); ge_add(rhs, Rp, T);
+    return (v1 && ge_eq(lhs, rhs)) ? 1 : 0;
+}
+
+// ---- per-element square + randomness proof (square_rand_proof/*; square_rand_proof_vec/mod.rs:18-160) -- enc type 3 ------------------------
+//   commitments = c.L | c.R | c_sq (96 B), proof = C'.L | C'.R | C'_sq | z_m | z_r1 | z_r2 (192 B).  Nonces: blocks 3i, 3i+1, 3i+2.
+HDNI void srp_transcript_challenge(sc &c, const uint8_t com[96], const uint8_t cp[96]) {
+    transcript t; transcript_init(t, "SquareRandProof");                                     // square_rand_proof_vec/mod.rs:51,105,142
+    const uint8_t ds[19] = {'r', 'a', 'n', 'd', 'o', 'm', 'n', 'e', 's', 's', ' ', 'p', 'r', 'o', 'o', 'f', ' ', 'v', '1'};
+    transcript_append(t, "dom-sep", ds, 19);
+    transcript_append(t, "C_eg", com, 64); transcript_append(t, "C_ped", com + 64, 32);     // dealer.rs:23-25
+    transcript_append(t, "C_prime_eg", cp, 64); transcript_append(t, "C_prime_ped", cp + 64, 32);
+    uint8_t buf[64]; transcript_challenge(t, "c", buf, 64);
+    sc_from_bytes_wide(c, buf);
+}
+HD int square_rand_prove_one(uint8_t *proof192, uint8_t *com96, float v, const uint8_t *value_com32, const uint8_t *r1b, const uint8_t *r2b, const uint32_t key[8], uint64_t idx,
+                             int n_bits, int frac, const niels_st *tabB, const niels_st *tabH) {
+    sc m, r1, r2, msq, mp, r1p, r2p, c, zm, zr1, zr2, tmp; ge_p3 Cl, P;
+    if (f32_to_scalar(m, v, n_bits, frac)) return -1;
+    sc_from_bytes_mod_order(r1, r1b); sc_from_bytes_mod_order(r2, r2b);
+    if (value_com32) { if (!ge_decompress(Cl, value_com32)) return -4; for (int i = 0; i < 32; i++) com96[i] = value_com32[i]; }
+    else { ge_p3_0(Cl); fb_mul_acc(Cl, tabB, m, 32); fb_mul_acc(Cl, tabH, r1, 32); ge_compress(com96, Cl); }
+    ge_p3_0(P); fb_mul_acc(P, tabB, r1, 32); ge_compress(com96 + 32, P);                     // c.R = r1 B
+    sc_mul(msq, m, m); ge_p3_0(P); fb_mul_acc(P, tabB, msq, 32); fb_mul_acc(P, tabH, r2, 32); ge_compress(com96 + 64, P);      // c_sq (party.rs:31-32)
+    nonce_scalar(mp, key, 3 * idx); nonce_scalar(r1p, key, 3 * idx + 1); nonce_scalar(r2p, key, 3 * idx + 2);
+    ge_p3_0(P); fb_mul_acc(P, tabB, mp, 32); fb_mul_acc(P, tabH, r1p, 32); ge_compress(proof192, P);      // C'.L
+    ge_p3_0(P); fb_mul_acc(P, tabB, r1p, 32); ge_compress(proof192 + 32, P);                              // C'.R
+    ge_tab8 tb; ge_tab8_build(tb, Cl);
+    ge_double_scalarmult_r16(P, mp, tb, nullptr, nullptr); fb_mul_acc(P, tabH, r2p, 32); ge_compress(proof192 + 64, P);       // C'_sq = m' c.L + r2' H
+    srp_transcript_challenge(c, com96, proof192);
+    sc_muladd(zm, m, c, mp); sc_muladd(zr1, r1, c, r1p);
+    sc_mul(tmp, m, r1); sc_sub(tmp, r2, tmp); sc_muladd(zr2, tmp, c, r2p);
+    sc_tobytes(proof192 + 96, zm); sc_tobytes(proof192 + 128, zr1); sc_tobytes(proof192 + 160, zr2);
+    return 0;
+}
+HD int square_rand_verify_one(const uint8_t *proof192, const uint8_t *com96, const niels_st *tabB, const niels_st *tabH) {
+    ge_p3 L, R, Csq, Lp, Rp, Csqp, lhs, rhs, T; sc zm, zr1, zr2, c, nc;
+    bool ok = ge_decompress(L, com96) & ge_decompress(R, com96 + 32) & ge_decompress(Csq, com96 + 64) & ge_decompress(Lp, proof192) & ge_decompress(Rp, proof192 + 32) & ge_decompress(Csqp, proof192 + 64);
+    sc_frombytes(zm, proof192 + 96); sc_frombytes(zr1, proof192 + 128); sc_frombytes(zr2, proof192 + 160);
+    ok = ok && sc_is_canonical(zm) && sc_is_canonical(zr1) && sc_is_canonical(zr2);
+    if (!ok) return -1;
+    srp_transcript_challenge(c, com96, proof192);
+    ge_tab8 tl, tr, ts; ge_tab8_build(tl, L); ge_tab8_build(tr, R); ge_tab8_build(ts, Csq);
+    ge_p3_0(lhs); fb_mul_acc(lhs, tabB, zm, 32); fb_mul_acc(lhs, tabH, zr1, 32);            // mod.rs:94-99
+    ge_double_scalarmult_r16(T, c, tl, nullptr, nullptr); ge_add(rhs, Lp, T);
+    bool v = ge_eq(lhs, rhs);
+    ge_p3_0(lhs); fb_mul_acc(lhs, tabB, zr1, 32);
+    ge_double_scalarmult_r16(T, c, tr, nullptr, nullptr); ge_add(rhs, Rp, T);
+    v = v && ge_eq(lhs, rhs);
+    sc_neg(nc, c);                                                                            // z_m c.L + z_r2 H == C'_sq + c c_sq (mod.rs:101-109)
+    ge_double_scalarmult_r16(lhs, zm, tl, &nc, &ts); fb_mul_acc(lhs, tabH, zr2, 32);
+    v = v && ge_eq(lhs, Csqp);
+    return v ? 1 : 0;
+}

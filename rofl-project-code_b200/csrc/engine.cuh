@@ -16,7 +16,7 @@
 #include <chrono>
 #include <cstdio>
 
-enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE = 4, DOM_L2_VERIFY = 5, DOM_CRP = 6, DOM_RND_VEC = 7 };
+enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE = 4, DOM_L2_VERIFY = 5, DOM_CRP = 6, DOM_RND_VEC = 7, DOM_RANDPROOF = 8, DOM_SQUARE_RAND = 9 };
 enum { PROF_FOLD = 0, PROF_MSM = 1, PROF_COMMIT = 2, PROF_SQUARE = 3, PROF_RTMSM = 4, PROF_TAIL = 5, PROF_FRZ = 6, PROF_SLOTS = 8 };
 
 struct gens_entry { int n = 0; int cap = 0; niels_st *G = nullptr, *H = nullptr;
@@ -1042,6 +1042,38 @@ static int engine_crp_verify(rofl_engine &e, const uint8_t *h_proof, const uint8
     int id[2], bad[2]; rt_d2h(id, d_id.p, sizeof(id), s); rt_d2h(bad, d_bad.p, sizeof(bad), s); rt_sync(s);
     if (bad[0]) return -1;
     return (id[0] && id[1]) ? 1 : 0;
+}
+
+// rand_proof_vec::{create_randproof_vec(_existing), verify_randproof_vec} (kind 1) and square_rand_proof_vec::{create_l2rangeproof_vec(_existing),
+// verify_l2rangeproof_vec} (kind 2); device pointers; d_value_com nullable (commit inside).  prove: 0, -4 bad point, -98 NaN; verify: 1 / 0 / -1 FormatError
+static int engine_sigma_prove(rofl_engine &e, int kind, const float *d_values, const uint8_t *d_value_com, const uint8_t *d_r1, const uint8_t *d_r2, size_t D,
+                              int n_bits, int frac, const uint8_t seed[32], uint8_t *d_proofs, uint8_t *d_commits) {
+    if (!fp_ok(n_bits, frac) || (kind != 1 && kind != 2)) return -2;
+    if (D == 0) return 0;
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    dev_buf d_flags(sizeof(int), s); rt_memset(d_flags.p, 0, sizeof(int), s);
+    sigma_args a = {}; a.kind = kind; a.values = d_values; a.value_com = d_value_com; a.r1 = d_r1; a.r2 = d_r2; a.D = D; a.n_bits = n_bits; a.frac = frac;
+    uint8_t key[32]; derive_key(key, seed, kind == 1 ? DOM_RANDPROOF : DOM_SQUARE_RAND, 0); key_words(a.key, key);
+    a.tabB = e.tabB; a.tabH = e.tabH; a.proofs = d_proofs; a.commits = d_commits; a.flags = d_flags.as<int>();
+    void *tk = rt_prof_begin(PROF_SQUARE, s);
+    LAUNCH(k_sigma_prove, dim3((unsigned)((D + 127) / 128)), dim3(128), s, a);
+    rt_prof_end(PROF_SQUARE, tk, s);
+    int flags = 0; rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_sync(s);
+    if (flags & 4) return -4;
+    if (flags & 1) return -98;
+    return 0;
+}
+static int engine_sigma_verify(rofl_engine &e, int kind, const uint8_t *d_proofs, const uint8_t *d_commits, size_t D) {
+    if (kind != 1 && kind != 2) return -2;
+    if (D == 0) return 1;
+    std::lock_guard<std::mutex> lk(e.mu);
+    cudaStream_t s = e.stream;
+    dev_buf d_res(2 * sizeof(int), s); int init[2] = {1, 0}; rt_h2d(d_res.p, init, sizeof(init), s);
+    LAUNCH(k_sigma_verify, dim3((unsigned)((D + 127) / 128)), dim3(128), s, kind, d_proofs, d_commits, D, e.tabB, e.tabH, d_res.as<int>());
+    int res[2]; rt_d2h(res, d_res.p, sizeof(res), s); rt_sync(s);
+    if (res[1]) return -1;
+    return res[0] ? 1 : 0;
 }
 
 // sum of D compressed points -> compressed (device in, host out); -4 if one does not decode

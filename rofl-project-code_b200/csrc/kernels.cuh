@@ -750,6 +750,43 @@ KERNEL void LB(128, 1) k_square_verify(const uint8_t *proofs, const uint8_t *com
 KLAUNCH(k_square_verify, false, (const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result), (proofs, commits, D, tabB, tabH, result))
 #endif
 
+// the un-optimised encodings' per-element proofs (enc types 2 and 3): same shape as K8, one thread per element.
+//   kind 1 = RandProof (pair 64 B, proof 128 B), kind 2 = SquareRandProof (commitments 96 B, proof 192 B)
+struct sigma_args {
+    int kind; const float *values; const uint8_t *value_com, *r1, *r2; size_t D; int n_bits, frac;
+    uint32_t key[8]; const niels_st *tabB, *tabH;
+    uint8_t *proofs, *commits; int *flags;
+};
+#ifdef KG_SQUARE
+KERNEL void LB(128, 1) k_sigma_prove(sigma_args a) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.D) return;
+    uint8_t vc[32], r1[32], r2[32], proof[192], com[96];
+    if (a.value_com) ld_bytes32(vc, a.value_com + 32 * i);
+    ld_bytes32(r1, a.r1 + 32 * i);
+    const int pw = a.kind == 1 ? 4 : 6, cw = a.kind == 1 ? 2 : 3;
+    int rc;
+    if (a.kind == 1) rc = rand_prove_one(proof, com, a.values[i], a.value_com ? vc : nullptr, r1, a.key, (uint64_t)i, a.n_bits, a.frac, a.tabB, a.tabH);
+    else { ld_bytes32(r2, a.r2 + 32 * i); rc = square_rand_prove_one(proof, com, a.values[i], a.value_com ? vc : nullptr, r1, r2, a.key, (uint64_t)i, a.n_bits, a.frac, a.tabB, a.tabH); }
+    if (rc) { atomicOr(a.flags, rc == -1 ? 1 : 4); return; }
+    for (int k = 0; k < pw; k++) st_bytes32(a.proofs + 32 * (pw * i + k), proof + 32 * k);
+    for (int k = 0; k < cw; k++) st_bytes32(a.commits + 32 * (cw * i + k), com + 32 * k);
+}
+KLAUNCH(k_sigma_prove, false, (sigma_args a), (a))
+KERNEL void LB(128, 1) k_sigma_verify(int kind, const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    uint8_t proof[192], com[96];
+    const int pw = kind == 1 ? 4 : 6, cw = kind == 1 ? 2 : 3;
+    for (int k = 0; k < pw; k++) ld_bytes32(proof + 32 * k, proofs + 32 * (pw * i + k));
+    for (int k = 0; k < cw; k++) ld_bytes32(com + 32 * k, commits + 32 * (cw * i + k));
+    const int rc = kind == 1 ? rand_verify_one(proof, com, tabB, tabH) : square_rand_verify_one(proof, com, tabB, tabH);
+    if (rc < 0) atomicOr(result + 1, 1);
+    else if (rc == 0) atomicAnd(result, 0);
+}
+KLAUNCH(k_sigma_verify, false, (int kind, const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result), (kind, proofs, commits, D, tabB, tabH, result))
+#endif
+
 // ===================================================================================================================
 // K9: homomorphic aggregation over clients (params.rs:81-124, pedersen_ops.rs:56-69); pts[client][D] compressed
 // ===================================================================================================================
@@ -982,6 +1019,8 @@ void launch_k_decompress(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *out, uint8_t 
 void launch_k_verify_tables(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *tab, vtab_layout t, sc_st *var, uint32_t var_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int m);
 void launch_k_verify_scalars(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *gh, const sc_st *tab, vtab_layout t, const sc_st *chal, int chal_stride, int n, int C);
 void launch_k_square_prove(dim3 g_, dim3 b_, cudaStream_t s_, square_args a);
+void launch_k_sigma_prove(dim3 g_, dim3 b_, cudaStream_t s_, sigma_args a);
+void launch_k_sigma_verify(dim3 g_, dim3 b_, cudaStream_t s_, int kind, const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result);
 void launch_k_square_verify(dim3 g_, dim3 b_, cudaStream_t s_, const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result);
 void launch_k_aggregate(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const uint8_t *pts, size_t n_clients, size_t D, int init_base, int *bad);
 void launch_k_bsgs_build(dim3 g_, dim3 b_, cudaStream_t s_, unsigned long long *keys, uint32_t *vals, uint32_t cap, uint32_t m, const niels_st *tabB, int *distinct);

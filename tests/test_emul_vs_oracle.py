@@ -246,3 +246,34 @@ def test_optimised_encodings_end_to_end(api, oracle):
         if i is None: bad[field][j] ^= 1
         else: bad[field][i, j] ^= 1
         assert api.enc_l2_compressed_verify(bad, seed) == 0, field
+
+
+def test_rand_and_square_rand_proofs(api, oracle):
+    """RandProof (enc type 2) and SquareRandProof (enc type 3): bytes, existing-commitment mode, tamper and format rejection."""
+    rng = np.random.default_rng(55)
+    D = 7
+    v = (rng.integers(-200, 200, D) / 128).astype(np.float32)
+    r1 = oracle.rnd_scalar_vec(b"\x66" * 32, D); r2 = oracle.rnd_scalar_vec(b"\x67" * 32, D); seed = bytes([13] * 32)
+    rc_o, pf_o, pr_o = oracle.rand_prove(v, None, r1, 16, 7, seed)
+    rc, pf, pr = api.rand_prove(v, None, r1, 16, 7, seed)
+    assert rc == rc_o == 0 and (pf == pf_o).all() and (pr == pr_o).all()
+    assert (pr[:, :32] == oracle.commit_f32(v, r1, 16, 7)).all() and (pr[:, 32:] == oracle.elgamal_R(r1)).all()
+    assert api.rand_verify(pf, pr) == 1 and oracle.rand_verify(pf, pr) == 1
+    rc, pf2, pr2 = api.rand_prove(v, pr[:, :32].copy(), r1, 16, 7, seed)
+    assert rc == 0 and (pf2 == pf).all() and (pr2 == pr).all()
+    bad = pr.copy(); bad[2, 32:] = pr[3, 32:]
+    assert api.rand_verify(pf, bad) == 0 and oracle.rand_verify(pf, bad) == 0
+    badp = pf.copy(); badp[1, 64:96] = 0xff
+    assert api.rand_verify(badp, pr) == -1 and oracle.rand_verify(badp, pr) == -1
+    rc_o, sp_o, sc_o = oracle.square_rand_prove(v, None, r1, r2, 32, 7, seed)
+    rc, sp, sc = api.square_rand_prove(v, None, r1, r2, 32, 7, seed)
+    assert rc == rc_o == 0 and (sp == sp_o).all() and (sc == sc_o).all()
+    assert api.square_rand_verify(sp, sc) == 1 and oracle.square_rand_verify(sp, sc) == 1
+    rc, sp2, sc2 = api.square_rand_prove(v, sc[:, :32].copy(), r1, r2, 32, 7, seed)
+    assert rc == 0 and (sp2 == sp).all() and (sc2 == sc).all()
+    bad = sc.copy(); bad[4, 64:] = sc[5, 64:]
+    assert api.square_rand_verify(sp, bad) == 0 and oracle.square_rand_verify(sp, bad) == 0
+    bad = sc.copy(); bad[0, 32:64] = sc[1, 32:64]
+    assert api.square_rand_verify(sp, bad) == 0 and oracle.square_rand_verify(sp, bad) == 0
+    badp = sp.copy(); badp[6, 160:] = 0xff
+    assert api.square_rand_verify(badp, sc) == -1 and oracle.square_rand_verify(badp, sc) == -1

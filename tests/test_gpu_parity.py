@@ -218,6 +218,41 @@ def test_compressed_rand_proof_parity_and_full_size(api, oracle):
     assert api.crp_prove(np.zeros(900001, np.float32), None, np.zeros((900001, 32), np.uint8), 16, 7, seed)[0] == -6
 
 
+def test_rand_and_square_rand_proof_parity_and_full_size(api, oracle):
+    """Per-element proofs of the un-optimised encodings (enc types 2 and 3): byte parity at 3 000 elements, then configs[0]'s 5 000 x 4
+    on the GPU alone with existing commitments (as params.rs creates them), tamper and format rejection."""
+    rng = np.random.default_rng(41)
+    D = 3000
+    v = (rng.integers(-300, 300, D) / 128).astype(np.float32); seed = bytes([6] * 32)
+    r1 = oracle.rnd_scalar_vec(b"\x68" * 32, D); r2 = oracle.rnd_scalar_vec(b"\x69" * 32, D)
+    rc_o, pf_o, pr_o = oracle.rand_prove(v, None, r1, 16, 7, seed)
+    rc, pf, pr = api.rand_prove(v, None, r1, 16, 7, seed)
+    assert rc == rc_o == 0 and (pf == pf_o).all() and (pr == pr_o).all()
+    assert api.rand_verify(pf, pr) == 1 and oracle.rand_verify(pf, pr) == 1
+    rc_o, sp_o, sc_o = oracle.square_rand_prove(v, None, r1, r2, 32, 7, seed)
+    rc, sp, sc = api.square_rand_prove(v, None, r1, r2, 32, 7, seed)
+    assert rc == rc_o == 0 and (sp == sp_o).all() and (sc == sc_o).all()
+    assert api.square_rand_verify(sp, sc) == 1 and oracle.square_rand_verify(sp, sc) == 1
+    D = 20000
+    v = (rng.integers(-100, 100, D) / 128).astype(np.float32)
+    r1 = api.rnd_scalar_vec(b"\x6a" * 32, D); r2 = api.rnd_scalar_vec(b"\x6b" * 32, D)
+    L_ = api.commit(v, r1, 32, 7)
+    rc, pf, pr = api.rand_prove(v, L_, r1, 32, 7, seed)
+    assert rc == 0 and (pr[:, :32] == L_).all() and api.rand_verify(pf, pr) == 1
+    bad = pr.copy(); bad[D - 1, 32:] = pr[0, 32:]
+    assert api.rand_verify(pf, bad) == 0
+    badp = pf.copy(); badp[D // 2, 64:96] = 0xff
+    assert api.rand_verify(badp, pr) == -1
+    rc, sp, sc = api.square_rand_prove(v, L_, r1, r2, 32, 7, seed)
+    assert rc == 0 and (sc[:, :32] == L_).all() and api.square_rand_verify(sp, sc) == 1
+    sq = api.commit(((v.astype(np.float64) * 128) ** 2).astype(np.float32), r2, 32, 0)                 # c_sq commits to m^2 under r2
+    assert (sc[:, 64:] == sq).all()
+    bad = sc.copy(); bad[7, 64:] = sc[8, 64:]
+    assert api.square_rand_verify(sp, bad) == 0
+    badp = sp.copy(); badp[3, :32] = 0xff
+    assert api.square_rand_verify(badp, sc) == -1
+
+
 @pytest.mark.parametrize("P", [64, 4])
 def test_config0_mnist_5k_full_size_byte_parity(api, oracle, P):
     """BASELINE.json configs[0] at its real size (5 000 params, 8-bit, 1 client; P = 64 as in mnist_e2e.yml and P = 4 as in the reference's
