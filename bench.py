@@ -48,6 +48,9 @@ class ClockSampler:
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.p.stdout], daemon=True); self.t.start()
+            t0 = time.time()                     # nvidia-smi's start-up (NVML attach to every GPU of the box) stalls CUDA calls of running
+            while not self.lines and time.time() - t0 < 15 and self.p.poll() is None:      # processes: let it finish before any timing
+                time.sleep(0.05)
         except Exception:
             self.p = None
 

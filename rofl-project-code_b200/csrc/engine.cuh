@@ -181,13 +181,17 @@ static inline bool engine_rt(rofl_engine &e, gens_entry &g, int n, int m, rt_tab
     g.RTG = RTG; g.RTH = RTH; g.rt_cap = m; g.rt_c = c; t.G = RTG; t.H = RTH; out = t;
     return true;
 }
-// blocks per msm for the direct table MSM: whole waves of 148 SMs x 4 resident blocks, >= 4 terms per thread when possible
+// blocks per msm for the direct table MSM: every block of a wave runs ceil(T / (nb*128)) terms per thread, so pick the nb whose
+// waves (148 SMs x 4 resident blocks) x terms-per-thread product is smallest (+ a block-sum epilogue worth ~half a term)
 static inline int rt_blocks(size_t T, int C) {
-    const double slots = 148.0 * 4.0;
-    double waves = std::max(1.0, std::floor((double)T * C / (128.0 * 8.0) / slots + 0.5));
-    size_t nb = (size_t)std::ceil(slots * waves / C);
-    nb = std::min(nb, (T + 127) / 128);
-    return (int)std::max<size_t>(1, nb);
+    const size_t slots = 148 * 4, max_nb = std::max<size_t>(1, std::min((T + 127) / 128, slots * 4 / (size_t)C));
+    size_t best = 1; double best_cost = 1e300;
+    for (size_t nb = 1; nb <= max_nb; nb++) {
+        const double waves = (double)((nb * C + slots - 1) / slots), per = (double)((T + nb * 128 - 1) / (nb * 128));
+        const double cost = waves * (per + 0.5);
+        if (cost < best_cost * 0.999) { best_cost = cost; best = nb; }
+    }
+    return (int)best;
 }
 static inline void run_rt_msm(rofl_engine &e, cudaStream_t s, rt_msm_args a, int nb, uint32_t n_msm) {
     rt_prof_work(PROF_RTMSM, (double)a.T * n_msm * a.rt.nw);          // mixed additions (upper bound: zero digits skip theirs)

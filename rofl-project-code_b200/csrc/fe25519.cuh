@@ -27,6 +27,9 @@
 // friendlier to the instruction cache) but that build is NOT bit-exact on sm_100a with CUDA 12.9: tools/ge_selftest.cu shows a
 // doubling + addition + compress sequence going wrong only in that configuration (no memcheck / racecheck findings), so it
 // stays off until the cause is understood.  The GPU parity tests would catch the same failure in any other build.
+#ifndef FE_MUL_ROWS
+#define FE_MUL_ROWS 1
+#endif
 #ifndef FE_INLINE_MUL
 #define FE_INLINE_MUL 1
 #endif
@@ -144,6 +147,119 @@ __device__ __forceinline__ void fe_columns_to_words(uint32_t t[16], const uint32
         : "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
         : "r"(ex[0]), "r"(ex[1]), "r"(ex[2]), "r"(ex[3]), "r"(ex[4]), "r"(ex[5]), "r"(ex[6]), "r"(ex[7]), "r"(ex[8]), "r"(ex[9]), "r"(ex[10]), "r"(ex[11]), "r"(ex[12]), "r"(ex[13]));
 }
+// h = f*g, row-wise: products of equal parity of (i + j) accumulate into 64-bit aligned register pairs along a carry chain
+// (IMAD.WIDE.U32 with carry-in and carry-out), so no per-product carry word is needed; E holds the pairs at even word
+// positions, O those at odd positions, T = E + O.  Chain ends: the running sum after row i is < 2^(32(i+9)), so a chain that
+// ends at word i+8 cannot carry out and one that ends at word i+7 carries into a still-untouched word.
+__device__ __forceinline__ void fe_mul_rows(uint32_t t[16], const fe &f, const fe &g) {
+    uint32_t e[16], o[17];
+    for (int k = 0; k < 16; k++) e[k] = 0;
+    for (int k = 0; k < 17; k++) o[k] = 0;
+    FE_MUL0(e[0], e[1], f.v[0], g.v[0]);
+    FE_MUL0(e[2], e[3], f.v[0], g.v[2]);
+    FE_MUL0(e[4], e[5], f.v[0], g.v[4]);
+    FE_MUL0(e[6], e[7], f.v[0], g.v[6]);
+    FE_MUL0(o[1], o[2], f.v[0], g.v[1]);
+    FE_MUL0(o[3], o[4], f.v[0], g.v[3]);
+    FE_MUL0(o[5], o[6], f.v[0], g.v[5]);
+    FE_MUL0(o[7], o[8], f.v[0], g.v[7]);
+    asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\tmadc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\tmadc.lo.cc.u32 %4, %8, %11, %4;\n\tmadc.hi.cc.u32 %5, %8, %11, %5;\n\tmadc.lo.cc.u32 %6, %8, %12, %6;\n\tmadc.hi.u32 %7, %8, %12, %7;"
+        : "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9])
+        : "r"(f.v[1]), "r"(g.v[1]), "r"(g.v[3]), "r"(g.v[5]), "r"(g.v[7]));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\tmadc.hi.cc.u32 %1, %9, %10, %1;\n\tmadc.lo.cc.u32 %2, %9, %11, %2;\n\tmadc.hi.cc.u32 %3, %9, %11, %3;\n\tmadc.lo.cc.u32 %4, %9, %12, %4;\n\tmadc.hi.cc.u32 %5, %9, %12, %5;\n\tmadc.lo.cc.u32 %6, %9, %13, %6;\n\tmadc.hi.cc.u32 %7, %9, %13, %7;\n\taddc.u32 %8, 0, 0;"
+        : "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(o[8]), "+r"(o[9])
+        : "r"(f.v[1]), "r"(g.v[0]), "r"(g.v[2]), "r"(g.v[4]), "r"(g.v[6]));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\tmadc.hi.cc.u32 %1, %9, %10, %1;\n\tmadc.lo.cc.u32 %2, %9, %11, %2;\n\tmadc.hi.cc.u32 %3, %9, %11, %3;\n\tmadc.lo.cc.u32 %4, %9, %12, %4;\n\tmadc.hi.cc.u32 %5, %9, %12, %5;\n\tmadc.lo.cc.u32 %6, %9, %13, %6;\n\tmadc.hi.cc.u32 %7, %9, %13, %7;\n\taddc.u32 %8, 0, 0;"
+        : "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9]), "+r"(e[10])
+        : "r"(f.v[2]), "r"(g.v[0]), "r"(g.v[2]), "r"(g.v[4]), "r"(g.v[6]));
+    asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\tmadc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\tmadc.lo.cc.u32 %4, %8, %11, %4;\n\tmadc.hi.cc.u32 %5, %8, %11, %5;\n\tmadc.lo.cc.u32 %6, %8, %12, %6;\n\tmadc.hi.u32 %7, %8, %12, %7;"
+        : "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(o[8]), "+r"(o[9]), "+r"(o[10])
+        : "r"(f.v[2]), "r"(g.v[1]), "r"(g.v[3]), "r"(g.v[5]), "r"(g.v[7]));
+    asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\tmadc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\tmadc.lo.cc.u32 %4, %8, %11, %4;\n\tmadc.hi.cc.u32 %5, %8, %11, %5;\n\tmadc.lo.cc.u32 %6, %8, %12, %6;\n\tmadc.hi.u32 %7, %8, %12, %7;"
+        : "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9]), "+r"(e[10]), "+r"(e[11])
+        : "r"(f.v[3]), "r"(g.v[1]), "r"(g.v[3]), "r"(g.v[5]), "r"(g.v[7]));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\tmadc.hi.cc.u32 %1, %9, %10, %1;\n\tmadc.lo.cc.u32 %2, %9, %11, %2;\n\tmadc.hi.cc.u32 %3, %9, %11, %3;\n\tmadc.lo.cc.u32 %4, %9, %12, %4;\n\tmadc.hi.cc.u32 %5, %9, %12, %5;\n\tmadc.lo.cc.u32 %6, %9, %13, %6;\n\tmadc.hi.cc.u32 %7, %9, %13, %7;\n\taddc.u32 %8, 0, 0;"
+        : "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(o[8]), "+r"(o[9]), "+r"(o[10]), "+r"(o[11])
+        : "r"(f.v[3]), "r"(g.v[0]), "r"(g.v[2]), "r"(g.v[4]), "r"(g.v[6]));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\tmadc.hi.cc.u32 %1, %9, %10, %1;\n\tmadc.lo.cc.u32 %2, %9, %11, %2;\n\tmadc.hi.cc.u32 %3, %9, %11, %3;\n\tmadc.lo.cc.u32 %4, %9, %12, %4;\n\tmadc.hi.cc.u32 %5, %9, %12, %5;\n\tmadc.lo.cc.u32 %6, %9, %13, %6;\n\tmadc.hi.cc.u32 %7, %9, %13, %7;\n\taddc.u32 %8, 0, 0;"
+        : "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9]), "+r"(e[10]), "+r"(e[11]), "+r"(e[12])
+        : "r"(f.v[4]), "r"(g.v[0]), "r"(g.v[2]), "r"(g.v[4]), "r"(g.v[6]));
+    asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\tmadc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\tmadc.lo.cc.u32 %4, %8, %11, %4;\n\tmadc.hi.cc.u32 %5, %8, %11, %5;\n\tmadc.lo.cc.u32 %6, %8, %12, %6;\n\tmadc.hi.u32 %7, %8, %12, %7;"
+        : "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(o[8]), "+r"(o[9]), "+r"(o[10]), "+r"(o[11]), "+r"(o[12])
+        : "r"(f.v[4]), "r"(g.v[1]), "r"(g.v[3]), "r"(g.v[5]), "r"(g.v[7]));
+    asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\tmadc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\tmadc.lo.cc.u32 %4, %8, %11, %4;\n\tmadc.hi.cc.u32 %5, %8, %11, %5;\n\tmadc.lo.cc.u32 %6, %8, %12, %6;\n\tmadc.hi.u32 %7, %8, %12, %7;"
+        : "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9]), "+r"(e[10]), "+r"(e[11]), "+r"(e[12]), "+r"(e[13])
+        : "r"(f.v[5]), "r"(g.v[1]), "r"(g.v[3]), "r"(g.v[5]), "r"(g.v[7]));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\tmadc.hi.cc.u32 %1, %9, %10, %1;\n\tmadc.lo.cc.u32 %2, %9, %11, %2;\n\tmadc.hi.cc.u32 %3, %9, %11, %3;\n\tmadc.lo.cc.u32 %4, %9, %12, %4;\n\tmadc.hi.cc.u32 %5, %9, %12, %5;\n\tmadc.lo.cc.u32 %6, %9, %13, %6;\n\tmadc.hi.cc.u32 %7, %9, %13, %7;\n\taddc.u32 %8, 0, 0;"
+        : "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(o[8]), "+r"(o[9]), "+r"(o[10]), "+r"(o[11]), "+r"(o[12]), "+r"(o[13])
+        : "r"(f.v[5]), "r"(g.v[0]), "r"(g.v[2]), "r"(g.v[4]), "r"(g.v[6]));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\tmadc.hi.cc.u32 %1, %9, %10, %1;\n\tmadc.lo.cc.u32 %2, %9, %11, %2;\n\tmadc.hi.cc.u32 %3, %9, %11, %3;\n\tmadc.lo.cc.u32 %4, %9, %12, %4;\n\tmadc.hi.cc.u32 %5, %9, %12, %5;\n\tmadc.lo.cc.u32 %6, %9, %13, %6;\n\tmadc.hi.cc.u32 %7, %9, %13, %7;\n\taddc.u32 %8, 0, 0;"
+        : "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9]), "+r"(e[10]), "+r"(e[11]), "+r"(e[12]), "+r"(e[13]), "+r"(e[14])
+        : "r"(f.v[6]), "r"(g.v[0]), "r"(g.v[2]), "r"(g.v[4]), "r"(g.v[6]));
+    asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\tmadc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\tmadc.lo.cc.u32 %4, %8, %11, %4;\n\tmadc.hi.cc.u32 %5, %8, %11, %5;\n\tmadc.lo.cc.u32 %6, %8, %12, %6;\n\tmadc.hi.u32 %7, %8, %12, %7;"
+        : "+r"(o[7]), "+r"(o[8]), "+r"(o[9]), "+r"(o[10]), "+r"(o[11]), "+r"(o[12]), "+r"(o[13]), "+r"(o[14])
+        : "r"(f.v[6]), "r"(g.v[1]), "r"(g.v[3]), "r"(g.v[5]), "r"(g.v[7]));
+    asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\tmadc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\tmadc.lo.cc.u32 %4, %8, %11, %4;\n\tmadc.hi.cc.u32 %5, %8, %11, %5;\n\tmadc.lo.cc.u32 %6, %8, %12, %6;\n\tmadc.hi.u32 %7, %8, %12, %7;"
+        : "+r"(e[8]), "+r"(e[9]), "+r"(e[10]), "+r"(e[11]), "+r"(e[12]), "+r"(e[13]), "+r"(e[14]), "+r"(e[15])
+        : "r"(f.v[7]), "r"(g.v[1]), "r"(g.v[3]), "r"(g.v[5]), "r"(g.v[7]));
+    asm("mad.lo.cc.u32 %0, %9, %10, %0;\n\tmadc.hi.cc.u32 %1, %9, %10, %1;\n\tmadc.lo.cc.u32 %2, %9, %11, %2;\n\tmadc.hi.cc.u32 %3, %9, %11, %3;\n\tmadc.lo.cc.u32 %4, %9, %12, %4;\n\tmadc.hi.cc.u32 %5, %9, %12, %5;\n\tmadc.lo.cc.u32 %6, %9, %13, %6;\n\tmadc.hi.cc.u32 %7, %9, %13, %7;\n\taddc.u32 %8, 0, 0;"
+        : "+r"(o[7]), "+r"(o[8]), "+r"(o[9]), "+r"(o[10]), "+r"(o[11]), "+r"(o[12]), "+r"(o[13]), "+r"(o[14]), "+r"(o[15])
+        : "r"(f.v[7]), "r"(g.v[0]), "r"(g.v[2]), "r"(g.v[4]), "r"(g.v[6]));
+    t[0] = e[0];
+    asm("add.cc.u32 %0, %15, %30;\n\taddc.cc.u32 %1, %16, %31;\n\taddc.cc.u32 %2, %17, %32;\n\taddc.cc.u32 %3, %18, %33;\n\taddc.cc.u32 %4, %19, %34;\n\taddc.cc.u32 %5, %20, %35;\n\taddc.cc.u32 %6, %21, %36;\n\taddc.cc.u32 %7, %22, %37;\n\taddc.cc.u32 %8, %23, %38;\n\taddc.cc.u32 %9, %24, %39;\n\taddc.cc.u32 %10, %25, %40;\n\taddc.cc.u32 %11, %26, %41;\n\taddc.cc.u32 %12, %27, %42;\n\taddc.cc.u32 %13, %28, %43;\n\taddc.u32 %14, %29, %44;"
+        : "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(t[8]), "=&r"(t[9]), "=&r"(t[10]), "=&r"(t[11]), "=&r"(t[12]), "=&r"(t[13]), "=&r"(t[14]), "=&r"(t[15])
+        : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]), "r"(e[9]), "r"(e[10]), "r"(e[11]), "r"(e[12]), "r"(e[13]), "r"(e[14]), "r"(e[15]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]));
+}
+// off-diagonal products f_i f_j (i < j) of a square, row-wise as in fe_mul_rows: t = sum_{i<j} f_i f_j 2^(32(i+j))
+__device__ __forceinline__ void fe_sq_rows(uint32_t t[16], const fe &f) {
+    uint32_t e[16], o[17];
+    for (int k = 0; k < 16; k++) e[k] = 0;
+    for (int k = 0; k < 17; k++) o[k] = 0;
+    FE_MUL0(e[2], e[3], f.v[0], f.v[2]);
+    FE_MUL0(e[4], e[5], f.v[0], f.v[4]);
+    FE_MUL0(e[6], e[7], f.v[0], f.v[6]);
+    FE_MUL0(o[1], o[2], f.v[0], f.v[1]);
+    FE_MUL0(o[3], o[4], f.v[0], f.v[3]);
+    FE_MUL0(o[5], o[6], f.v[0], f.v[5]);
+    FE_MUL0(o[7], o[8], f.v[0], f.v[7]);
+    asm("mad.lo.cc.u32 %0, %6, %7, %0;\n\tmadc.hi.cc.u32 %1, %6, %7, %1;\n\tmadc.lo.cc.u32 %2, %6, %8, %2;\n\tmadc.hi.cc.u32 %3, %6, %8, %3;\n\tmadc.lo.cc.u32 %4, %6, %9, %4;\n\tmadc.hi.u32 %5, %6, %9, %5;"
+        : "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9])
+        : "r"(f.v[1]), "r"(f.v[3]), "r"(f.v[5]), "r"(f.v[7]));
+    asm("mad.lo.cc.u32 %0, %7, %8, %0;\n\tmadc.hi.cc.u32 %1, %7, %8, %1;\n\tmadc.lo.cc.u32 %2, %7, %9, %2;\n\tmadc.hi.cc.u32 %3, %7, %9, %3;\n\tmadc.lo.cc.u32 %4, %7, %10, %4;\n\tmadc.hi.cc.u32 %5, %7, %10, %5;\n\taddc.u32 %6, 0, 0;"
+        : "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(o[8]), "+r"(o[9])
+        : "r"(f.v[1]), "r"(f.v[2]), "r"(f.v[4]), "r"(f.v[6]));
+    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\tmadc.hi.cc.u32 %1, %5, %6, %1;\n\tmadc.lo.cc.u32 %2, %5, %7, %2;\n\tmadc.hi.cc.u32 %3, %5, %7, %3;\n\taddc.u32 %4, 0, 0;"
+        : "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9]), "+r"(e[10])
+        : "r"(f.v[2]), "r"(f.v[4]), "r"(f.v[6]));
+    asm("mad.lo.cc.u32 %0, %6, %7, %0;\n\tmadc.hi.cc.u32 %1, %6, %7, %1;\n\tmadc.lo.cc.u32 %2, %6, %8, %2;\n\tmadc.hi.cc.u32 %3, %6, %8, %3;\n\tmadc.lo.cc.u32 %4, %6, %9, %4;\n\tmadc.hi.u32 %5, %6, %9, %5;"
+        : "+r"(o[5]), "+r"(o[6]), "+r"(o[7]), "+r"(o[8]), "+r"(o[9]), "+r"(o[10])
+        : "r"(f.v[2]), "r"(f.v[3]), "r"(f.v[5]), "r"(f.v[7]));
+    asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\tmadc.hi.cc.u32 %1, %4, %5, %1;\n\tmadc.lo.cc.u32 %2, %4, %6, %2;\n\tmadc.hi.u32 %3, %4, %6, %3;"
+        : "+r"(e[8]), "+r"(e[9]), "+r"(e[10]), "+r"(e[11])
+        : "r"(f.v[3]), "r"(f.v[5]), "r"(f.v[7]));
+    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\tmadc.hi.cc.u32 %1, %5, %6, %1;\n\tmadc.lo.cc.u32 %2, %5, %7, %2;\n\tmadc.hi.cc.u32 %3, %5, %7, %3;\n\taddc.u32 %4, 0, 0;"
+        : "+r"(o[7]), "+r"(o[8]), "+r"(o[9]), "+r"(o[10]), "+r"(o[11])
+        : "r"(f.v[3]), "r"(f.v[4]), "r"(f.v[6]));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, 0, 0;"
+        : "+r"(e[10]), "+r"(e[11]), "+r"(e[12])
+        : "r"(f.v[4]), "r"(f.v[6]));
+    asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\tmadc.hi.cc.u32 %1, %4, %5, %1;\n\tmadc.lo.cc.u32 %2, %4, %6, %2;\n\tmadc.hi.u32 %3, %4, %6, %3;"
+        : "+r"(o[9]), "+r"(o[10]), "+r"(o[11]), "+r"(o[12])
+        : "r"(f.v[4]), "r"(f.v[5]), "r"(f.v[7]));
+    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+        : "+r"(e[12]), "+r"(e[13])
+        : "r"(f.v[5]), "r"(f.v[7]));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, 0, 0;"
+        : "+r"(o[11]), "+r"(o[12]), "+r"(o[13])
+        : "r"(f.v[5]), "r"(f.v[6]));
+    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+        : "+r"(o[13]), "+r"(o[14])
+        : "r"(f.v[6]), "r"(f.v[7]));
+    t[0] = 0;
+    asm("add.cc.u32 %0, %15, %30;\n\taddc.cc.u32 %1, %16, %31;\n\taddc.cc.u32 %2, %17, %32;\n\taddc.cc.u32 %3, %18, %33;\n\taddc.cc.u32 %4, %19, %34;\n\taddc.cc.u32 %5, %20, %35;\n\taddc.cc.u32 %6, %21, %36;\n\taddc.cc.u32 %7, %22, %37;\n\taddc.cc.u32 %8, %23, %38;\n\taddc.cc.u32 %9, %24, %39;\n\taddc.cc.u32 %10, %25, %40;\n\taddc.cc.u32 %11, %26, %41;\n\taddc.cc.u32 %12, %27, %42;\n\taddc.cc.u32 %13, %28, %43;\n\taddc.u32 %14, %29, %44;"
+        : "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(t[8]), "=&r"(t[9]), "=&r"(t[10]), "=&r"(t[11]), "=&r"(t[12]), "=&r"(t[13]), "=&r"(t[14]), "=&r"(t[15])
+        : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]), "r"(e[9]), "r"(e[10]), "r"(e[11]), "r"(e[12]), "r"(e[13]), "r"(e[14]), "r"(e[15]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]));
+}
 #endif
 // portable reduction (host)
 HD void fe_reduce512_c(fe &h, const uint32_t t[16]) {
@@ -157,6 +273,9 @@ HD void fe_reduce512_c(fe &h, const uint32_t t[16]) {
 
 HDMUL void fe_mul(fe &h, const fe &f, const fe &g) {
 #if defined(__CUDA_ARCH__)
+#if FE_MUL_ROWS
+    uint32_t t[16]; fe_mul_rows(t, f, g);
+#else
     uint32_t lo[15], hi[15], ex[15];
 #pragma unroll
     for (int k = 0; k < 15; k++) {
@@ -166,6 +285,7 @@ HDMUL void fe_mul(fe &h, const fe &f, const fe &g) {
         for (int i = i0 + 1; i <= i1; i++) FE_MAC(lo[k], hi[k], ex[k], f.v[i], g.v[k - i]);
     }
     uint32_t t[16]; fe_columns_to_words(t, lo, hi, ex);
+#endif
     fe_reduce512(h, t);
 #else
     uint32_t t[16]; for (int i = 0; i < 16; i++) t[i] = 0;
@@ -181,6 +301,9 @@ HDMUL void fe_mul(fe &h, const fe &f, const fe &g) {
 HDMUL void fe_sq(fe &h, const fe &f) {
 #if defined(__CUDA_ARCH__)
     // off-diagonal products once, doubled by a 1-bit shift of the whole 512-bit value, then the diagonal squares
+#if FE_MUL_ROWS
+    uint32_t t[16]; fe_sq_rows(t, f);
+#else
     uint32_t lo[15], hi[15], ex[15];
     lo[0] = hi[0] = ex[0] = 0; lo[14] = hi[14] = ex[14] = 0;
 #pragma unroll
@@ -192,6 +315,7 @@ HDMUL void fe_sq(fe &h, const fe &f) {
         for (int i = i0 + 1; i <= i1; i++) FE_MAC(lo[k], hi[k], ex[k], f.v[i], f.v[k - i]);
     }
     uint32_t t[16]; fe_columns_to_words(t, lo, hi, ex);
+#endif
 #pragma unroll
     for (int i = 15; i > 0; i--) t[i] = (t[i] << 1) | (t[i - 1] >> 31);
     t[0] <<= 1;

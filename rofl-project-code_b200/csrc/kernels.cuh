@@ -1101,21 +1101,78 @@ HD void rt_mul_acc(ge_p3 &acc, const niels_st *row0, const sc &x, const rt_table
 //     mode 1/2 (unfolded IPP round, np = half block): the G part uses the hi (mode 1, "L") or lo (mode 2, "R") half of every
 //       2np block, the H part the opposite half:  q < nG: j = (q/np)*2np + (hiG ? np : 0) + q%np
 struct rt_msm_args { const sc_st *scalars; uint32_t T, scalar_stride, nG, np; int mode; rt_tables rt; p3_st *partial; };
+// Table records are gathered from ~40 GB of HBM at random: every thread stages its next RTM_STAGES-1 records in its own
+// shared-memory slots with cp.async (no registers held across the latency, no block barrier: a thread only reads what it
+// copied itself), and the scalar of its next term likewise.  Slot layout [stage][16-byte piece][thread] -> conflict-free LDS.128.
+#ifndef RTM_STAGES
+#define RTM_STAGES 3
+#endif
+#ifdef ROFL_EMUL
+DEV void cp_async16(void *dst, const void *src) { *(uint4 *)dst = *(const uint4 *)src; }
+DEV void cp_async_commit() {}
+template <int N> DEV void cp_async_wait() {}
+#else
+DEV void cp_async16(void *dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }
+DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+struct rtm_stage { uint4 rec[RTM_STAGES][6][128]; uint4 scal[2][2][128]; };
+struct rtm_cursor { uint32_t xk[9]; const niels_st *row0; uint32_t term, w, flags; };      // producer side of one thread's record stream
 #ifdef KG_MSM
+DEV void rtm_produce(rtm_cursor &p, rtm_stage &sm, const rt_msm_args &a, const sc_st *scal, uint32_t t0, uint32_t stride, uint32_t nterm, uint32_t g, uint32_t total, uint32_t slot, int tid) {
+    if (g < total) {
+        if (p.w == (uint32_t)a.rt.nw) {                                                     // next term: its scalar was staged one term ago
+            sc x; const uint32_t t = t0 + p.term * stride;
+            if (p.term == 0) ld_sc(x, scal + t);
+            else { uint4 lo = sm.scal[p.term & 1][0][tid], hi = sm.scal[p.term & 1][1][tid]; x.v[0] = lo.x; x.v[1] = lo.y; x.v[2] = lo.z; x.v[3] = lo.w; x.v[4] = hi.x; x.v[5] = hi.y; x.v[6] = hi.z; x.v[7] = hi.w; }
+            const bool isG = t < a.nG; const uint32_t q = isG ? t : t - a.nG; uint32_t j = q;
+            if (a.mode) { bool hi = (a.mode == 1) == isG; j = (q / a.np) * 2 * a.np + (hi ? a.np : 0) + q % a.np; }
+            p.row0 = (isG ? a.rt.G : a.rt.H) + (size_t)j * rt_row_entries(a.rt);
+            msm_recode(p.xk, x, a.rt.K);
+            p.term++; p.w = 0;
+            if (p.term < nterm) { const uint4 *nx = (const uint4 *)(scal + t0 + p.term * stride); cp_async16(&sm.scal[p.term & 1][0][tid], nx); cp_async16(&sm.scal[p.term & 1][1][tid], nx + 1); }
+        }
+        const int dw = msm_digit(p.xk, (int)p.w, a.rt.c);
+        if (dw != 0) {
+            const uint4 *src = (const uint4 *)(p.row0 + (size_t)p.w * a.rt.B + (dw > 0 ? dw : -dw) - 1);
+            for (int i = 0; i < 6; i++) cp_async16(&sm.rec[slot][i][tid], src + i);
+        }
+        p.flags = (p.flags & ~(3u << (2 * slot))) | ((uint32_t)(dw != 0) | ((uint32_t)(dw < 0) << 1)) << (2 * slot);
+        p.w++;
+    }
+    cp_async_commit();
+}
 KERNEL void LB(128, 4) k_rt_msm(rt_msm_args a) {
-    __shared__ p3_st buf[128];
+    __shared__ rtm_stage sm;
     const int tid = threadIdx.x; const uint32_t msm = blockIdx.y;
     const sc_st *scal = a.scalars + (size_t)msm * a.scalar_stride;
-    const size_t rowsz = rt_row_entries(a.rt);
+    const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + tid;
+    const uint32_t nterm = t0 < a.T ? (a.T - t0 + stride - 1) / stride : 0, total = nterm * (uint32_t)a.rt.nw;
+    rtm_cursor p; p.term = 0; p.w = (uint32_t)a.rt.nw; p.flags = 0; p.row0 = nullptr;
     ge_p3 acc; ge_p3_0(acc);
-    for (uint32_t t = blockIdx.x * blockDim.x + tid; t < a.T; t += gridDim.x * blockDim.x) {
-        sc x; ld_sc(x, scal + t);
-        if (sc_iszero(x)) continue;
-        bool isG = t < a.nG; uint32_t q = isG ? t : t - a.nG, j = q;
-        if (a.mode) { bool hi = (a.mode == 1) == isG; j = (q / a.np) * 2 * a.np + (hi ? a.np : 0) + q % a.np; }
-        rt_mul_acc(acc, (isG ? a.rt.G : a.rt.H) + (size_t)j * rowsz, x, a.rt);
+    uint32_t pslot = 0, cslot = 0;
+    for (uint32_t g = 0; g < RTM_STAGES - 1; g++) { rtm_produce(p, sm, a, scal, t0, stride, nterm, g, total, pslot, tid); pslot = pslot + 1 == RTM_STAGES ? 0 : pslot + 1; }
+    for (uint32_t k = 0; k < total; k++) {
+        rtm_produce(p, sm, a, scal, t0, stride, nterm, k + RTM_STAGES - 1, total, pslot, tid); pslot = pslot + 1 == RTM_STAGES ? 0 : pslot + 1;
+        cp_async_wait<RTM_STAGES - 1>();
+        const uint32_t f = (p.flags >> (2 * cslot)) & 3u;
+        if (f & 1u) {
+            ge_niels n, m; const uint4 *q = &sm.rec[cslot][0][tid];
+            uint4 v0 = q[0], v1 = q[128], v2 = q[256], v3 = q[384], v4 = q[512], v5 = q[640];
+            n.yplusx.v[0] = v0.x; n.yplusx.v[1] = v0.y; n.yplusx.v[2] = v0.z; n.yplusx.v[3] = v0.w; n.yplusx.v[4] = v1.x; n.yplusx.v[5] = v1.y; n.yplusx.v[6] = v1.z; n.yplusx.v[7] = v1.w;
+            n.yminusx.v[0] = v2.x; n.yminusx.v[1] = v2.y; n.yminusx.v[2] = v2.z; n.yminusx.v[3] = v2.w; n.yminusx.v[4] = v3.x; n.yminusx.v[5] = v3.y; n.yminusx.v[6] = v3.z; n.yminusx.v[7] = v3.w;
+            n.xy2d.v[0] = v4.x; n.xy2d.v[1] = v4.y; n.xy2d.v[2] = v4.z; n.xy2d.v[3] = v4.w; n.xy2d.v[4] = v5.x; n.xy2d.v[5] = v5.y; n.xy2d.v[6] = v5.z; n.xy2d.v[7] = v5.w;
+            const bool neg = (f & 2u) != 0;
+            m.yplusx = n.yplusx; m.yminusx = n.yminusx; m.xy2d = n.xy2d;
+            fe nx; fe_neg(nx, n.xy2d); fe_carry(nx, nx);
+            fe_cmov(m.yplusx, n.yminusx, neg); fe_cmov(m.yminusx, n.yplusx, neg); fe_cmov(m.xy2d, nx, neg);
+            ge_madd(acc, acc, m);
+        }
+        cslot = cslot + 1 == RTM_STAGES ? 0 : cslot + 1;
     }
-    block_sum_p3(acc, buf, tid, blockDim.x);
+    cp_async_wait<0>();
+    __syncthreads();
+    block_sum_p3(acc, (p3_st *)&sm, tid, blockDim.x);
     if (tid == 0) st_p3(a.partial + (size_t)msm * gridDim.x + blockIdx.x, acc);
 }
 KLAUNCH(k_rt_msm, true, (rt_msm_args a), (a))
