@@ -46,7 +46,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.p.stdout], daemon=True); self.t.start()
             t0 = time.time()                     # nvidia-smi's start-up (NVML attach to every GPU of the box) stalls CUDA calls of running
             while not self.lines and time.time() - t0 < 15 and self.p.poll() is None:      # processes: let it finish before any timing
@@ -74,7 +74,8 @@ class ClockSampler:
             for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        print("clock samples (sm MHz):", sm, file=sys.stderr)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def cpu_reference_run(steps, warmup, sample_chunks=None):
@@ -172,11 +173,14 @@ def main():
         assert rc == 0 and ok == 1
         return e0.elapsed_time(e1), e1.elapsed_time(e2)
 
-    sampler = ClockSampler(local); sampler.start()      # started BEFORE the warm-up: nvidia-smi's own start-up (NVML init) stalls the driver for a moment
+    sampler = ClockSampler(local)
+    if not os.environ.get("BENCH_NO_CLOCKS"):          # (diagnostic switch: how much does the sampling itself perturb the steps?)
+        sampler.start()      # started BEFORE the warm-up: nvidia-smi's own start-up (NVML init) stalls the driver for a moment
     for it in range(args.warmup):
         step_resident(it); step_e2e(it)
     sampler.lines.clear()                               # keep only the samples taken during the timed regions
     imad_peak = lib.rofl_probe_imad_wide(api.h) if rank == 0 else 0.0       # roofline denominator, measured on this GPU before the timed region
+    print("== timed region starts", file=sys.stderr, flush=True)
     # ---- timed: resident (no per-kernel events inside the timed region)
     lib.rofl_prof_enable(0); lib.rofl_prof_reset()
     barrier()

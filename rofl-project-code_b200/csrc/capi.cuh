@@ -21,7 +21,7 @@ extern "C" int rofl_set_option(rofl_ctx *c, const char *name, long value) {
     else if (n == "rt_unfold") c->e.rt_unfold = (int)std::max<long>(0, std::min<long>(6, value));
     else if (n == "groups") c->e.groups = (int)std::max<long>(1, std::min<long>((long)c->e.gstreams.size(), value));
     else if (n == "rt_bits") {                                                                       // drops the cached tables: they are rebuilt at the new radix on next use
-        c->e.rt_bits = (int)std::max<long>(8, std::min<long>(10, value));
+        c->e.rt_bits = (int)std::max<long>(8, std::min<long>(RT_MAX_BITS, value));
         rt_sync(c->e.stream);
         for (auto &g : c->e.gens) { rt_free(g.second.RTG, c->e.stream); rt_free(g.second.RTH, c->e.stream); g.second.RTG = g.second.RTH = nullptr; g.second.rt_cap = 0; }
     }

@@ -31,14 +31,14 @@ struct rofl_engine {
     std::map<std::pair<uint64_t, int>, bsgs_entry> bsgs;
     std::mutex mu;
     int host_threads = 8;
-    int groups = 2;                       // chunk groups proved / verified concurrently on separate streams (hides per-round latency)
+    int groups = 3;                       // chunk groups proved / verified concurrently on separate streams (hides per-round latency)
     std::vector<cudaStream_t> gstreams;   // gstreams[0] == stream
     int use_rt = 1;                       // 0: never build generator tables (generic Pippenger / fold path only)
     int rt_unfold = 4;                    // IPP rounds computed over the original generators before the catch-up fold
     int tail_np = 32;                     // IPP rounds with half-size <= tail_np run in the fused on-device tail kernel (0 = off)
     std::mutex pin_mu; std::vector<std::pair<void *, size_t>> pins;      // pool of pinned host blocks for the per-round exchanges
     int use_frz = 1;                      // middle IPP rounds over frozen generators with on-the-fly Straus tables (kernels.cuh K6c)
-    int rt_bits = 10;                     // widest generator-table radix to try (8..10)
+    int rt_bits = RT_MAX_BITS;            // widest generator-table radix to try (8..11)
     double rt_mem_frac = 0.45;            // tables may take this fraction of the free device memory
 };
 
@@ -160,7 +160,7 @@ static inline bool engine_rt(rofl_engine &e, gens_entry &g, int n, int m, rt_tab
     const size_t cnt = (size_t)n * m;
     rt_sync(s); rt_free(g.RTG, s); rt_free(g.RTH, s); g.RTG = g.RTH = nullptr; g.rt_cap = 0; rt_sync(s);
     const size_t have = rt_free_mem();
-    int c = std::max(8, std::min(10, e.rt_bits));
+    int c = std::max(8, std::min(RT_MAX_BITS, e.rt_bits));
     for (; c >= 8; c--) {
         const size_t nw = msm_nw(c), B = (size_t)1 << (c - 1);
         if ((double)(2 * cnt * nw * B * sizeof(niels_st) + cnt * nw * sizeof(p3_st)) <= e.rt_mem_frac * (double)have) break;

@@ -41,11 +41,12 @@
 // the sign is applied to the operand (swap y+x / y-x, negate 2dxy resp. X and T) so that lanes of a warp with different
 // signs execute ONE addition instead of diverging into add and sub paths
 HD void acc_add_niels(ge_p3 &acc, const niels_st *p, bool neg) {
-    ge_niels n, m; ld_niels(n, p);
-    m.yplusx = n.yplusx; m.yminusx = n.yminusx; m.xy2d = n.xy2d;
-    fe nx; fe_neg(nx, n.xy2d); fe_carry(nx, nx);
-    fe_cmov(m.yplusx, n.yminusx, neg); fe_cmov(m.yminusx, n.yplusx, neg); fe_cmov(m.xy2d, nx, neg);
-    ge_madd(acc, acc, m);
+    // -Q = (y-x, y+x, -2dxy): the swap is an address select, the sign of C = T1*2dxy swaps G = D+C and F = D-C afterwards
+    const uint4 *q = (const uint4 *)p; ge_niels m;
+    ld_fe1(m.yplusx, q + (neg ? 2 : 0)); ld_fe1(m.yminusx, q + (neg ? 0 : 2)); ld_fe1(m.xy2d, q + 4);
+    ge_p1p1 t; ge_madd_p1p1(t, acc, m);
+    fe z = t.Z; fe_cmov(t.Z, t.T, neg); fe_cmov(t.T, z, neg);
+    ge_p1p1_to_p3(acc, t);
 }
 HD void acc_add_p3(ge_p3 &acc, const p3_st *p, bool neg) {
     ge_p3 q, nq; ld_p3(q, p); ge_neg(nq, q);
@@ -1044,6 +1045,7 @@ void launch_k_pairs_split(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *L, uint8_t
 // ===================================================================================================================
 // run-time radix 2^c (c = 8, 9 or 10): nw = ceil(254/c) windows of B = 2^(c-1) multiples; same signed recoding as k_msm
 #define RT_MAXW 32
+#define RT_MAX_BITS 11                    // widest table radix: 2^11 -> 24 windows of 1024 records (77 GB for 2 x 32768 generators)
 struct rt_tables { const niels_st *G, *H; int c, nw, B; uint32_t K[9]; };
 HD size_t rt_row_entries(const rt_tables &t) { return (size_t)t.nw * t.B; }      // niels records per generator
 #ifdef KG_TABLES
@@ -1118,6 +1120,18 @@ template <int N> DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0
 #endif
 struct rtm_stage { uint4 rec[RTM_STAGES][6][128]; uint4 scal[2][2][128]; };
 struct rtm_cursor { uint32_t xk[9]; const niels_st *row0; uint32_t term, w, flags; };      // producer side of one thread's record stream
+// acc +/- the record staged in `slot` of this thread
+DEV void rtm_consume(ge_p3 &acc, const rtm_stage &sm, uint32_t slot, int tid, bool neg) {
+    const uint4 *q = &sm.rec[slot][0][tid]; const uint32_t op = neg ? 256u : 0u, om = neg ? 0u : 256u;          // -Q: y+x and y-x swap by address
+    uint4 v0 = q[op], v1 = q[op + 128], v2 = q[om], v3 = q[om + 128], v4 = q[512], v5 = q[640];
+    ge_niels m;
+    m.yplusx.v[0] = v0.x; m.yplusx.v[1] = v0.y; m.yplusx.v[2] = v0.z; m.yplusx.v[3] = v0.w; m.yplusx.v[4] = v1.x; m.yplusx.v[5] = v1.y; m.yplusx.v[6] = v1.z; m.yplusx.v[7] = v1.w;
+    m.yminusx.v[0] = v2.x; m.yminusx.v[1] = v2.y; m.yminusx.v[2] = v2.z; m.yminusx.v[3] = v2.w; m.yminusx.v[4] = v3.x; m.yminusx.v[5] = v3.y; m.yminusx.v[6] = v3.z; m.yminusx.v[7] = v3.w;
+    m.xy2d.v[0] = v4.x; m.xy2d.v[1] = v4.y; m.xy2d.v[2] = v4.z; m.xy2d.v[3] = v4.w; m.xy2d.v[4] = v5.x; m.xy2d.v[5] = v5.y; m.xy2d.v[6] = v5.z; m.xy2d.v[7] = v5.w;
+    ge_p1p1 t; ge_madd_p1p1(t, acc, m);
+    fe z = t.Z; fe_cmov(t.Z, t.T, neg); fe_cmov(t.T, z, neg);                       // ... and the sign of C swaps G and F
+    ge_p1p1_to_p3(acc, t);
+}
 #ifdef KG_MSM
 DEV void rtm_produce(rtm_cursor &p, rtm_stage &sm, const rt_msm_args &a, const sc_st *scal, uint32_t t0, uint32_t stride, uint32_t nterm, uint32_t g, uint32_t total, uint32_t slot, int tid) {
     if (g < total) {
@@ -1156,18 +1170,7 @@ KERNEL void LB(128, 4) k_rt_msm(rt_msm_args a) {
         rtm_produce(p, sm, a, scal, t0, stride, nterm, k + RTM_STAGES - 1, total, pslot, tid); pslot = pslot + 1 == RTM_STAGES ? 0 : pslot + 1;
         cp_async_wait<RTM_STAGES - 1>();
         const uint32_t f = (p.flags >> (2 * cslot)) & 3u;
-        if (f & 1u) {
-            ge_niels n, m; const uint4 *q = &sm.rec[cslot][0][tid];
-            uint4 v0 = q[0], v1 = q[128], v2 = q[256], v3 = q[384], v4 = q[512], v5 = q[640];
-            n.yplusx.v[0] = v0.x; n.yplusx.v[1] = v0.y; n.yplusx.v[2] = v0.z; n.yplusx.v[3] = v0.w; n.yplusx.v[4] = v1.x; n.yplusx.v[5] = v1.y; n.yplusx.v[6] = v1.z; n.yplusx.v[7] = v1.w;
-            n.yminusx.v[0] = v2.x; n.yminusx.v[1] = v2.y; n.yminusx.v[2] = v2.z; n.yminusx.v[3] = v2.w; n.yminusx.v[4] = v3.x; n.yminusx.v[5] = v3.y; n.yminusx.v[6] = v3.z; n.yminusx.v[7] = v3.w;
-            n.xy2d.v[0] = v4.x; n.xy2d.v[1] = v4.y; n.xy2d.v[2] = v4.z; n.xy2d.v[3] = v4.w; n.xy2d.v[4] = v5.x; n.xy2d.v[5] = v5.y; n.xy2d.v[6] = v5.z; n.xy2d.v[7] = v5.w;
-            const bool neg = (f & 2u) != 0;
-            m.yplusx = n.yplusx; m.yminusx = n.yminusx; m.xy2d = n.xy2d;
-            fe nx; fe_neg(nx, n.xy2d); fe_carry(nx, nx);
-            fe_cmov(m.yplusx, n.yminusx, neg); fe_cmov(m.yminusx, n.yplusx, neg); fe_cmov(m.xy2d, nx, neg);
-            ge_madd(acc, acc, m);
-        }
+        if (f & 1u) rtm_consume(acc, sm, cslot, tid, (f & 2u) != 0);
         cslot = cslot + 1 == RTM_STAGES ? 0 : cslot + 1;
     }
     cp_async_wait<0>();
@@ -1219,7 +1222,8 @@ KLAUNCH(k_ipp_scalars_unf, true, (const sc_st *a, const sc_st *b, const sc_st *y
 struct catchup_args { rt_tables rt; p3_st *Gf, *Hf; const int16_t *digits; uint32_t nr, nblk, stride; };      // digits[((c*2+which)*nblk + t)*RT_MAXW + w]
 #ifdef KG_FOLD
 KERNEL void LB(128, 4) k_rt_catchup(catchup_args a) {
-    __shared__ int16_t dg[64 * RT_MAXW];
+    __shared__ rtm_stage sm;                                    // record staging as in k_rt_msm; the scalar slots hold the digits here
+    int16_t *dg = (int16_t *)sm.scal;                           // 64 * RT_MAXW digits = 4 KB
     int c = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
     for (uint32_t t = tid; t < a.nblk * RT_MAXW; t += blockDim.x) dg[t] = a.digits[((size_t)c * 2 + which) * a.nblk * RT_MAXW + t];
     __syncthreads();
@@ -1227,13 +1231,29 @@ KERNEL void LB(128, 4) k_rt_catchup(catchup_args a) {
     if (i >= a.nr) return;
     const niels_st *RT = which ? a.rt.H : a.rt.G;
     const size_t rowsz = rt_row_entries(a.rt);
+    const uint32_t nw = (uint32_t)a.rt.nw, total = a.nblk * nw;
     ge_p3 acc; ge_p3_0(acc);
-    for (uint32_t t = 0; t < a.nblk; t++) {
-        const niels_st *row0 = RT + ((size_t)t * a.nr + i) * rowsz;
-        for (int w = 0; w < a.rt.nw; w++) {
-            int d = dg[t * RT_MAXW + w];
-            if (d != 0) acc_add_niels(acc, row0 + (size_t)w * a.rt.B + (d > 0 ? d : -d) - 1, d < 0);
+    uint32_t pt = 0, pw = 0, flags = 0, pslot = 0, cslot = 0;
+    auto produce = [&](uint32_t g) {
+        if (g < total) {
+            const int d = dg[pt * RT_MAXW + pw];
+            if (d != 0) {
+                const uint4 *src = (const uint4 *)(RT + ((size_t)pt * a.nr + i) * rowsz + (size_t)pw * a.rt.B + (d > 0 ? d : -d) - 1);
+                for (int k = 0; k < 6; k++) cp_async16(&sm.rec[pslot][k][tid], src + k);
+            }
+            flags = (flags & ~(3u << (2 * pslot))) | ((uint32_t)(d != 0) | ((uint32_t)(d < 0) << 1)) << (2 * pslot);
+            if (++pw == nw) { pw = 0; pt++; }
         }
+        cp_async_commit();
+        pslot = pslot + 1 == RTM_STAGES ? 0 : pslot + 1;
+    };
+    for (uint32_t g = 0; g < RTM_STAGES - 1; g++) produce(g);
+    for (uint32_t k = 0; k < total; k++) {
+        produce(k + RTM_STAGES - 1);
+        cp_async_wait<RTM_STAGES - 1>();
+        const uint32_t f = (flags >> (2 * cslot)) & 3u;
+        if (f & 1u) rtm_consume(acc, sm, cslot, tid, (f & 2u) != 0);
+        cslot = cslot + 1 == RTM_STAGES ? 0 : cslot + 1;
     }
     st_p3((which ? a.Hf : a.Gf) + (size_t)c * a.stride + i, acc);
 }

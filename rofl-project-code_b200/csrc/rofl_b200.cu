@@ -106,7 +106,7 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
         if (const char *gv = getenv("ROFL_GROUPS")) c->e.groups = std::max(1, std::min(4, atoi(gv)));
         if (const char *gv = getenv("ROFL_RT")) c->e.use_rt = atoi(gv);                                   // 0 disables the generator tables
         if (const char *gv = getenv("ROFL_UNFOLD")) c->e.rt_unfold = std::max(0, std::min(6, atoi(gv)));   // unfolded IPP rounds (RT path)
-        if (const char *gv = getenv("ROFL_RT_BITS")) c->e.rt_bits = std::max(8, std::min(10, atoi(gv)));              // generator-table radix
+        if (const char *gv = getenv("ROFL_RT_BITS")) c->e.rt_bits = std::max(8, std::min(RT_MAX_BITS, atoi(gv)));              // generator-table radix
         if (const char *gv = getenv("ROFL_FRZ")) c->e.use_frz = atoi(gv) != 0;                                            // frozen-level middle rounds
         if (const char *gv = getenv("ROFL_TAIL")) c->e.tail_np = std::max(0, std::min(TAIL_MAX_F / 2, atoi(gv)));    // 0 disables the fused IPP tail
         engine_init(c->e);

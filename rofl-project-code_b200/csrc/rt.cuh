@@ -6,6 +6,7 @@
 #include <vector>
 #include <mutex>
 #include <cstdlib>
+#include <cstdio>
 #ifdef ROFL_EMUL
 #include "cuda_emul.h"
 inline void rt_check(int, const char *) {}
@@ -33,8 +34,8 @@ void rt_count_launch(const char *name);
 // Scratch allocation: a process-wide cache of device blocks (cudaMalloc once, reused forever).  The CUDA stream-ordered pool was the
 // first choice, but with two chunk groups allocating and freeing on two streams it made one stream wait for the other's long kernels
 // (cross-stream reuse), and forbidding that reuse made the pool grow with real allocations in the middle of a proof.
-// Here a block is preferably handed back to the stream that returned it (no waiting at all); only when none fits is a block of another
-// stream taken, ordered through the event recorded when it was returned.  Sizes are rounded up to 256 B; a block may serve requests down
+// Here a block is preferably handed back to the stream that returned it (no waiting at all); a block of another stream is taken only
+// if the event recorded at its return has completed, else a new block is allocated.  Sizes are rounded up to 256 B; a block may serve requests down
 // to half its size.
 struct rt_big_block { void *p; size_t n; int dev; cudaStream_t s; cudaEvent_t ev; };
 struct rt_big_cache {
@@ -44,15 +45,32 @@ struct rt_big_cache {
         int dev = 0; cudaGetDevice(&dev);
         rt_big_block b{}; bool found = false;
         { std::lock_guard<std::mutex> lk(mu);
-          // prefer a block this very stream returned (no cross-stream wait: waiting on another group's stream can cost tens of ms)
+          // a block this very stream returned needs no ordering at all; a block of another stream is taken only when the work that
+          // preceded its return has already finished (event complete): waiting for another group's stream stalled whole proofs for
+          // tens of ms and, once started, the groups kept stealing each other's blocks.  Otherwise allocate: the cache grows until
+          // every stream owns what it needs (a few steps), then no call allocates or waits any more.
           size_t best = free_list.size();
           for (int pass = 0; pass < 2 && best == free_list.size(); pass++)
-              for (size_t i = 0; i < free_list.size(); i++)
-                  if (free_list[i].dev == dev && (pass == 1 || free_list[i].s == s) && free_list[i].n >= n && free_list[i].n <= 2 * n &&
-                      (best == free_list.size() || free_list[i].n < free_list[best].n)) best = i;
+              for (size_t i = 0; i < free_list.size(); i++) {
+                  const rt_big_block &fb = free_list[i];
+                  if (fb.dev != dev || fb.n < n || fb.n > 2 * n || (best != free_list.size() && fb.n >= free_list[best].n)) continue;
+                  if (pass == 0 ? fb.s == s : (fb.s != s && cudaEventQuery(fb.ev) == cudaSuccess)) best = i;
+              }
           if (best < free_list.size()) { b = free_list[best]; free_list.erase(free_list.begin() + best); found = true; } }
+        static const bool trace = getenv("ROFL_ALLOC_TRACE") != nullptr;
+        if (trace && (!found || b.s != s)) fprintf(stderr, "[rofl alloc] %s %zu bytes (block %zu) stream %p\n", found ? "cross-stream reuse" : "cudaMalloc", n, found ? b.n : n, (void *)s);
         if (found) { if (b.s != s) rt_check(cudaStreamWaitEvent(s, b.ev, 0), "cudaStreamWaitEvent"); }
-        else { b.n = n; b.dev = dev; rt_check(cudaMalloc(&b.p, n), "cudaMalloc"); rt_check(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming), "cudaEventCreate"); }
+        else if (cudaMalloc(&b.p, n) == cudaSuccess) { b.n = n; b.dev = dev; rt_check(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming), "cudaEventCreate"); }
+        else {                                                       // out of memory: now a wait on another stream's block is the lesser evil
+            cudaGetLastError();
+            std::lock_guard<std::mutex> lk(mu);
+            size_t best = free_list.size();
+            for (size_t i = 0; i < free_list.size(); i++)
+                if (free_list[i].dev == dev && free_list[i].n >= n && (best == free_list.size() || free_list[i].n < free_list[best].n)) best = i;
+            if (best == free_list.size()) throw std::runtime_error("cudaMalloc: out of memory");
+            b = free_list[best]; free_list.erase(free_list.begin() + best);
+            rt_check(cudaStreamWaitEvent(s, b.ev, 0), "cudaStreamWaitEvent");
+        }
         b.s = s;
         std::lock_guard<std::mutex> lk(mu); live.push_back(b);
         return b.p;
