@@ -187,6 +187,8 @@ def main():
     t_p = t_v = 0.0
     per_step = []
     for it in range(args.steps):
+        if os.environ.get("ROFL_ALLOC_TRACE"):
+            print("== resident step", it, file=sys.stderr, flush=True)
         a, b, proofs = step_resident(100 + it); t_p += a; t_v += b; per_step.append((round(a, 2), round(b, 2)))
     barrier()
     if rank == 0:
@@ -202,16 +204,17 @@ def main():
     if rank == 0:
         print("e2e per-step (prove_ms, verify_ms):", per_step, file=sys.stderr)
     clocks = sampler.stop()
+    print("== profiling pass", file=sys.stderr, flush=True)
     # ---- per-kernel breakdown: the same K resident steps again with CUDA events around every launch of the main kernel families
     # (separate pass: creating / recording the events costs host time that must not leak into `value`)
-    api.set_option("groups", 1)             # one chunk group: every kernel is timed ALONE on the GPU (two groups overlap kernels of different rounds)
+    api.set_option("groups", 1)             # one chunk group: every kernel is timed ALONE on the GPU (several groups overlap kernels of different rounds)
     lib.rofl_prof_enable(1); lib.rofl_prof_reset()
     prof_step_ms = 0.0
     for it in range(args.steps):
         a, b, _ = step_resident(300 + it); prof_step_ms += a + b
     prof_step_ms /= args.steps
     torch.cuda.synchronize()
-    api.set_option("groups", 2)
+    api.set_option("groups", 3)
     prof = dict(fold_ms=lib.rofl_prof_ms(0), msm_ms=lib.rofl_prof_ms(1), commit_ms=lib.rofl_prof_ms(2), rt_ms=lib.rofl_prof_ms(4), tail_ms=lib.rofl_prof_ms(5),
                 rt_launches=lib.rofl_prof_launches(4), rt_madds=lib.rofl_prof_work(4))
     lib.rofl_prof_enable(0)
@@ -244,7 +247,7 @@ def main():
                     frac=(achieved / peak) if (achieved and peak) else None, traffic=traffic,
                     algorithmic=dict(mixed_additions_per_launch=madds / launches_rt, field_muls_per_addition=7, imad_wide_per_field_mul=IMAD_PER_FIELD_MUL, launches_per_step=launches_rt / K),
                     kernel_ms_per_launch=rt_ms / launches_rt, kernel_ms_per_step=rt_ms / K, kernel_share_of_step=rt_ms / K / prof_step_ms,
-                    share_note="share of the one-chunk-group step of the profiling pass (%.1f ms): the timed steps overlap two chunk groups" % prof_step_ms,
+                    share_note="share of the one-chunk-group step of the profiling pass (%.1f ms): the timed steps overlap three chunk groups" % prof_step_ms,
                     peak_source="rofl_probe_imad_wide: best of two mad.wide.u32 patterns (rotating multiplicands; carry-chained as in the field multiply), all SMs, best of 5, run before the timed region",
                     hbm=dict(achieved_gbs=madds * 96 / (rt_ms / 1e3) / 1e9 if rt_ms > 0 else None, peak_gbs=hbm_peak, note="table gathers: 96 B per mixed addition; MEASURED_PEAKS.json copy bandwidth" if peaks else "fallback 6650 GB/s"),
                     other_kernels_ms_per_step=dict(bucket_msm=prof["msm_ms"] / K, generator_fold=prof["fold_ms"] / K, ipp_tail=prof["tail_ms"] / K, commit=prof["commit_ms"] / K))

@@ -184,7 +184,7 @@ static inline bool engine_rt(rofl_engine &e, gens_entry &g, int n, int m, rt_tab
 // blocks per msm for the direct table MSM: every block of a wave runs ceil(T / (nb*128)) terms per thread, so pick the nb whose
 // waves (148 SMs x 4 resident blocks) x terms-per-thread product is smallest (+ a block-sum epilogue worth ~half a term)
 static inline int rt_blocks(size_t T, int C) {
-    const size_t slots = 148 * 4, max_nb = std::max<size_t>(1, std::min((T + 127) / 128, slots * 4 / (size_t)C));
+    const size_t slots = 148 * RTM_BLOCKS, max_nb = std::max<size_t>(1, std::min((T + 127) / 128, slots * 4 / (size_t)C));
     size_t best = 1; double best_cost = 1e300;
     for (size_t nb = 1; nb <= max_nb; nb++) {
         const double waves = (double)((nb * C + slots - 1) / slots), per = (double)((T + nb * 128 - 1) / (nb * 128));
@@ -636,6 +636,7 @@ static int engine_range_prove(rofl_engine &e, const float *d_values, const uint8
 static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int n, int m, int C, const gens_entry &g, const rt_tables *rt, const p3_st *d_Vp3, const uint8_t *h_V32,
                          const uint8_t *h_proofs, size_t plen, const std::vector<uint8_t> &keys, std::vector<int> &verdict) {
     verdict.assign(C, 0);
+    phase_trace tr(s);
     // RangeProof::from_bytes / InnerProductProof::from_bytes
     if (plen % 32 || plen < 7 * 32) return -1;
     size_t ne = plen / 32 - 7;
@@ -686,6 +687,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         for (int k = 0; k < lgN; k++) { memcpy(sp + 32 * (4 + k), ipp + 64 * k, 32); memcpy(sp + 32 * (4 + lgN + k), ipp + 64 * k + 32, 32); }
         memcpy(sp + 32 * (4 + 2 * lgN), e.H32, 32); memcpy(sp + 32 * (5 + 2 * lgN), e.B32, 32);
     });
+    tr.mark("v_transcripts");
     for (int c = 0; c < C; c++) { allu.push_back(y[c]); for (int k = 0; k < lgN; k++) allu.push_back(u[c][k]); }
     for (auto &v : allu) if (sc_iszero(v)) sc_from_u64(v, 1);                    // (probability 2^-252; keeps the batch inversion defined)
     sc_batch_invert(allu);
@@ -722,6 +724,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         sc_mul(tmp, a, b); sc_sub(tmp, t_x, tmp); sc_mul(tmp, w[c], tmp);                                        // w (t_x - a b)
         sc_sub(tmp2, delta, t_x); sc_mul(tmp2, cc[c], tmp2); sc_add(tmp, tmp, tmp2); put(5 + 2 * lgN, tmp);      // B
     });
+    tr.mark("v_host_scalars");
     const vtab_layout vt = vtab_make(lgN, ilog2_sz(m));
     dev_buf d_chal(sizeof(sc_st) * h_chal.size(), s), d_yinvpow2(sizeof(sc_st) * 32 * C, s), d_zpow2(sizeof(sc_st) * 32 * C, s);
     dev_buf d_tab(sizeof(sc_st) * (size_t)C * vt.total, s), d_gh(sizeof(sc_st) * 2 * N, s), d_var(sizeof(sc_st) * (size_t)C * vstride, s);
@@ -734,6 +737,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     LAUNCH(k_verify_tables, dim3((vt.total + m + 255) / 256, C), dim3(256), s, d_tab.as<sc_st>(), vt, d_var.as<sc_st>(), (uint32_t)m, d_chal.as<sc_st>(), chs, d_yinvpow2.as<sc_st>(), d_zpow2.as<sc_st>(), m);
     LAUNCH_COOP(k_verify_scalars, dim3((unsigned)((N + 63) / 64)), dim3(256), s, d_gh.as<sc_st>(), d_tab.as<sc_st>(), vt, d_chal.as<sc_st>(), chs, n, C);
     LAUNCH(k_decompress, dim3((unsigned)(((size_t)C * nsmall + 127) / 128)), dim3(128), s, d_sp.as<p3_st>(), (uint8_t *)nullptr, d_sp32.as<uint8_t>(), (size_t)C * nsmall, (size_t)C * nsmall, (const p3_st *)nullptr, d_bad.as<int>(), (size_t)nsmall);
+    tr.mark("v_scalar_kernels");
     // fixed generators: one 2N-term MSM (radix-256 tables when they exist, bucket MSM otherwise) -> d_fix
     {
         finalize_args f = {}; f.tabB = e.tabB; f.tabH = e.tabH; f.out_p3 = d_fix.as<p3_st>(); f.count = 1;
@@ -754,6 +758,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             run_finalize(s, f);
         }
     }
+    tr.mark("v_gen_msm");
     // commitments and proof points of ALL chunks: one sliced MSM over C*m + C*nsmall terms (scalars laid out the same way)
     {
         const uint32_t TV = (uint32_t)((size_t)C * m + (size_t)C * nsmall);
@@ -769,6 +774,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     std::vector<int> h_bad(C); int h_id = 0;
     rt_d2h(&h_id, d_id.p, sizeof(int), s); rt_d2h(h_bad.data(), d_bad.p, sizeof(int) * C, s);
     rt_sync(s);
+    tr.mark("v_var_msm");
     int all_ok = h_id;
     for (int c = 0; c < C; c++) all_ok &= (host_ok[c] && !h_bad[c]) ? 1 : 0;
     for (int c = 0; c < C; c++) verdict[c] = all_ok;
@@ -796,6 +802,7 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
         return -2;
     }
     const size_t C = std::min(n_proofs, (Dp + m - 1) / m);                        // zip(proofs, chunks)
+    phase_trace tr(s);
     dev_buf d_off(sizeof(p3_st), s), d_offs(sizeof(sc_st), s), d_Vp3(sizeof(p3_st) * Dp, s), d_V32(32 * Dp, s), d_bad(sizeof(int), s);
     { sc o; sc_from_u64(o, 1ULL << (range - 1)); sc_st os; sc_to_st(os, o); rt_h2d(d_offs.p, &os, sizeof(os), s);
       finalize_args f = {}; f.sBa = d_offs.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH; f.out_p3 = d_off.as<p3_st>(); f.count = 1;
@@ -805,6 +812,7 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
     std::vector<uint8_t> hV(32 * Dp); int bad = 0;
     rt_d2h(hV.data(), d_V32.p, hV.size(), s); rt_d2h(&bad, d_bad.p, sizeof(int), s);
     rt_sync(s);
+    tr.mark("v_decompress");
     if (bad) return -4;
     gens_entry &g = engine_gens(e, range, (int)m);
     rt_tables rt; const bool have_rt = engine_rt(e, g, range, (int)m, rt);

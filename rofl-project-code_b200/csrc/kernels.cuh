@@ -1109,6 +1109,9 @@ struct rt_msm_args { const sc_st *scalars; uint32_t T, scalar_stride, nG, np; in
 #ifndef RTM_STAGES
 #define RTM_STAGES 3
 #endif
+#ifndef RTM_BLOCKS
+#define RTM_BLOCKS 4                     // resident blocks per SM the table kernels are compiled for
+#endif
 #ifdef ROFL_EMUL
 DEV void cp_async16(void *dst, const void *src) { *(uint4 *)dst = *(const uint4 *)src; }
 DEV void cp_async_commit() {}
@@ -1156,7 +1159,7 @@ DEV void rtm_produce(rtm_cursor &p, rtm_stage &sm, const rt_msm_args &a, const s
     }
     cp_async_commit();
 }
-KERNEL void LB(128, 4) k_rt_msm(rt_msm_args a) {
+KERNEL void LB(128, RTM_BLOCKS) k_rt_msm(rt_msm_args a) {
     __shared__ rtm_stage sm;
     const int tid = threadIdx.x; const uint32_t msm = blockIdx.y;
     const sc_st *scal = a.scalars + (size_t)msm * a.scalar_stride;
@@ -1221,7 +1224,7 @@ KLAUNCH(k_ipp_scalars_unf, true, (const sc_st *a, const sc_st *b, const sc_st *y
 //   grid (blocks, C, 2): z = 0 -> G, 1 -> H
 struct catchup_args { rt_tables rt; p3_st *Gf, *Hf; const int16_t *digits; uint32_t nr, nblk, stride; };      // digits[((c*2+which)*nblk + t)*RT_MAXW + w]
 #ifdef KG_FOLD
-KERNEL void LB(128, 4) k_rt_catchup(catchup_args a) {
+KERNEL void LB(128, RTM_BLOCKS) k_rt_catchup(catchup_args a) {
     __shared__ rtm_stage sm;                                    // record staging as in k_rt_msm; the scalar slots hold the digits here
     int16_t *dg = (int16_t *)sm.scal;                           // 64 * RT_MAXW digits = 4 KB
     int c = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
