@@ -187,8 +187,8 @@ def main():
     t_p = t_v = 0.0
     per_step = []
     for it in range(args.steps):
-        if os.environ.get("ROFL_ALLOC_TRACE"):
-            print("== resident step", it, file=sys.stderr, flush=True)
+        if os.environ.get("ROFL_ALLOC_TRACE") or os.environ.get("ROFL_JITTER"):
+            print("== resident step", it, "t=%.0f ms" % (time.monotonic() * 1e3), file=sys.stderr, flush=True)
         a, b, proofs = step_resident(100 + it); t_p += a; t_v += b; per_step.append((round(a, 2), round(b, 2)))
     barrier()
     if rank == 0:

@@ -83,6 +83,26 @@ extern "C" double rofl_probe_imad_wide(rofl_ctx *c) {
 }
 extern "C" void *rofl_ctx_stream(rofl_ctx *c) { return c ? (void *)c->e.stream : nullptr; }
 
+
+// Diagnostic (ROFL_JITTER=1): a busy host thread that records the largest gap between two of its own clock readings per 100 ms
+// window (CLOCK_MONOTONIC, comparable with Python's time.monotonic()): a gap of milliseconds means the (virtual) CPU was taken away.
+#include <chrono>
+static std::atomic<bool> g_jit_stop{false};
+static std::thread *g_jit_thread = nullptr;
+static void jitter_start() {
+    if (g_jit_thread || !getenv("ROFL_JITTER")) return;
+    g_jit_thread = new std::thread([] {
+        using clk = std::chrono::steady_clock;
+        auto ms = [] { return std::chrono::duration<double, std::milli>(clk::now().time_since_epoch()).count(); };
+        double last = ms(), wstart = last, wmax = 0, hstart = last, hmax = 0;
+        fprintf(stderr, "[rofl jitter] probe thread running\n");
+        while (!g_jit_stop.load(std::memory_order_relaxed)) {
+            double t = ms(); if (t - last > wmax) wmax = t - last; last = t;
+            if (t - wstart >= 100.0) { if (wmax > 0.5) fprintf(stderr, "[rofl jitter] t=%.0f ms: clock gap %.2f ms\n", wstart, wmax); if (wmax > hmax) hmax = wmax; wstart = t; wmax = 0; }
+            if (t - hstart >= 2000.0) { fprintf(stderr, "[rofl jitter] heartbeat t=%.0f ms: largest gap of the last 2 s %.3f ms\n", t, hmax); hstart = t; hmax = 0; }
+        }
+    });
+}
 extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
     if (!out) return ROFL_ERR_ARGS;
     *out = nullptr;
@@ -95,6 +115,7 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
         if (prop.major < 10) throw std::runtime_error("rofl_b200 is built for sm_100a only");
         // the point formulas call fe_mul / fe_sq as real functions: give every thread room for the deepest call chain
         { size_t cur = 0; cudaDeviceGetLimit(&cur, cudaLimitStackSize); if (cur < 8192) rt_check(cudaDeviceSetLimit(cudaLimitStackSize, 8192), "cudaDeviceSetLimit(stack)"); }
+        jitter_start();
         rofl_ctx *c = new rofl_ctx();
         c->e.device = device;
         rt_check(cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking), "cudaStreamCreate");
