@@ -114,6 +114,12 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     w = WORKLOAD
+    # stdout carries exactly ONE JSON line: everything any library prints to fd 1 meanwhile (NCCL's version banner at NCCL_DEBUG=VERSION
+    # ignores NCCL_DEBUG_FILE) is sent to stderr, and the line is written to the saved descriptor at the end
+    sys.stdout.flush(); json_fd = os.dup(1); os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     if args.impl == "reference":
         if rank != 0:
@@ -123,7 +129,7 @@ def main():
                     scaling="weak", vs_baseline=None, dtype="u32 limbs (GF(2^255-19), mod l) on CPU u64", data="synthetic", impl="reference", config=w,
                     cpu_baseline=dict(value=r["value"], unit="elements/s", cores=r["cores"], kind="port", sample=r["sample"], prove_eps=r["prove_eps"], verify_eps=r["verify_eps"]),
                     e2e=dict(value=r["value"], unit="elements/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-        print(json.dumps(line)); return
+        emit(line); return
 
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's own version / debug lines off stdout: stdout carries the one JSON line
     import torch
@@ -264,7 +270,7 @@ def main():
             line["cpu_baseline"] = dict(value=r["value"], unit="elements/s", cores=r["cores"], kind="port", sample=r["sample"], prove_eps=r["prove_eps"], verify_eps=r["verify_eps"])
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = dict(value=None, unit="elements/s", cores=0, kind="port", sample=f"failed: {ex}")
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
