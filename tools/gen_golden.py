@@ -114,6 +114,16 @@ def main():
     rc, pf, pairs = oracle.crp_prove(vals, None, blind, 16, 7, bytes([6]) * 32); assert rc == 0 and oracle.crp_verify(pf, pairs) == 1
     prot["crp"] = {"values": [float(x) for x in vals], "blind_seed": "64" * 32, "seed": "06" * 32, "n_bits": 16, "frac": 7,
                    "proof": np.asarray(pf).tobytes().hex(), "pairs": np.asarray(pairs).tobytes().hex()}
+    # per-element proofs of the un-optimised encodings (enc types 2 and 3)
+    D = 5
+    r4 = np.random.default_rng(78)
+    vals = (r4.integers(-300, 300, D) / 128).astype(np.float32)
+    r1 = oracle.rnd_scalar_vec(b"\x65" * 32, D); r2s = oracle.rnd_scalar_vec(b"\x66" * 32, D)
+    rc, pf, pairs = oracle.rand_prove(vals, None, r1, 16, 7, bytes([11]) * 32); assert rc == 0 and oracle.rand_verify(pf, pairs) == 1
+    rc, sp, sc = oracle.square_rand_prove(vals, None, r1, r2s, 32, 7, bytes([11]) * 32); assert rc == 0 and oracle.square_rand_verify(sp, sc) == 1
+    prot["rand"] = {"values": [float(x) for x in vals], "r1_seed": "65" * 32, "r2_seed": "66" * 32, "seed": "0b" * 32, "frac": 7,
+                    "rand_n_bits": 16, "rand_proofs": np.asarray(pf).tobytes().hex(), "rand_pairs": np.asarray(pairs).tobytes().hex(),
+                    "square_rand_n_bits": 32, "square_rand_proofs": np.asarray(sp).tobytes().hex(), "square_rand_commits": np.asarray(sc).tobytes().hex()}
     # aggregate + discrete log
     x = np.array([[0.25, 1.25, -1.5, 100.5], [-0.75, 1.25, -2.0, 27.25], [0.5, 1.25, -3.0, 0.0078125]], np.float32)
     cs = np.stack([oracle.commit_f32(r, None, 16, 7) for r in x])
