@@ -216,9 +216,15 @@ def main():
     api.set_option("groups", 1)             # one chunk group: every kernel is timed ALONE on the GPU (several groups overlap kernels of different rounds)
     lib.rofl_prof_enable(1); lib.rofl_prof_reset()
     prof_step_ms = 0.0
+    prof_steps = []
     for it in range(args.steps):
+        k0 = sum(lib.rofl_prof_ms(i) for i in range(7))
         a, b, _ = step_resident(300 + it); prof_step_ms += a + b
+        torch.cuda.synchronize()
+        prof_steps.append((round(a + b, 2), round(sum(lib.rofl_prof_ms(i) for i in range(7)) - k0, 2)))
     prof_step_ms /= args.steps
+    if rank == 0:      # slow steps with an unchanged kernel sum = the GPU was waiting, not computing more slowly
+        print("profiling pass per-step (step_ms, event-timed kernel ms of the instrumented families):", prof_steps, file=sys.stderr)
     torch.cuda.synchronize()
     api.set_option("groups", 3)
     prof = dict(fold_ms=lib.rofl_prof_ms(0), msm_ms=lib.rofl_prof_ms(1), commit_ms=lib.rofl_prof_ms(2), rt_ms=lib.rofl_prof_ms(4), tail_ms=lib.rofl_prof_ms(5),

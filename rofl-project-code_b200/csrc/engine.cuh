@@ -12,6 +12,10 @@
 #include <map>
 #include <mutex>
 #include <thread>
+#include <atomic>
+#ifndef ROFL_EMUL
+#include <sys/resource.h>
+#endif
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -38,6 +42,7 @@ struct rofl_engine {
     int tail_np = 32;                     // IPP rounds with half-size <= tail_np run in the fused on-device tail kernel (0 = off)
     std::mutex pin_mu; std::vector<std::pair<void *, size_t>> pins;      // pool of pinned host blocks for the per-round exchanges
     int use_frz = 1;                      // middle IPP rounds over frozen generators with on-the-fly Straus tables (kernels.cuh K6c)
+    std::atomic<size_t> free_hint{0};     // free device memory when the generator tables were last (re)built: cudaMemGetInfo is NOT for the hot path
     int rt_bits = RT_MAX_BITS;            // widest generator-table radix to try (8..11)
     double rt_mem_frac = 0.45;            // tables may take this fraction of the free device memory
 };
@@ -85,13 +90,14 @@ static inline void key_words(uint32_t w[8], const uint8_t k[32]) { for (int i = 
 static inline void sc_to_st(sc_st &o, const sc &s) { for (int i = 0; i < 8; i++) o.w[i] = s.v[i]; }
 static inline void st_to_sc(sc &s, const sc_st &o) { for (int i = 0; i < 8; i++) s.v[i] = o.w[i]; }
 template <class F> static void parallel_for(size_t n, int threads, F f) {
+    rt_host_timer t_(&rt_host_prof::par, "parallel_for");
     if (n <= 1 || threads <= 1) { for (size_t i = 0; i < n; i++) f(i); return; }
     size_t nt = std::min<size_t>(threads, n); std::vector<std::thread> th;
     for (size_t t = 0; t < nt; t++) th.emplace_back([=] { for (size_t i = t; i < n; i += nt) f(i); });
     for (auto &x : th) x.join();
 }
 // light per-chunk host work (a few Keccak-f per chunk): thread start-up would cost more than the work
-template <class F> static void serial_for(size_t n, F f) { for (size_t i = 0; i < n; i++) f(i); }
+template <class F> static void serial_for(size_t n, F f) { rt_host_timer t_(&rt_host_prof::ser, "serial_for"); for (size_t i = 0; i < n; i++) f(i); }
 // Montgomery's trick: v[i] <- v[i]^-1 (all non-zero)
 static inline void sc_batch_invert(std::vector<sc> &v) {
     size_t n = v.size(); if (!n) return;
@@ -112,6 +118,7 @@ static inline void engine_init(rofl_engine &e) {
     uint8_t h[64]; sha3_512(h, e.B32, 32); ge_from_uniform_bytes(H, h); ge_compress(e.H32, H);     // PedersenGens::default / el_gamal.rs:31-40
     cudaStream_t s = e.stream;
     if (e.gstreams.empty()) e.gstreams.push_back(e.stream);
+    e.free_hint = rt_free_mem();
     e.tabB = (niels_st *)rt_malloc(sizeof(niels_st) * FB_WINDOWS * FB_ENTRIES, s);
     e.tabH = (niels_st *)rt_malloc(sizeof(niels_st) * FB_WINDOWS * FB_ENTRIES, s);
     dev_buf pts(64, s);
@@ -179,6 +186,7 @@ static inline bool engine_rt(rofl_engine &e, gens_entry &g, int n, int m, rt_tab
         rt_sync(s);
     }
     g.RTG = RTG; g.RTH = RTH; g.rt_cap = m; g.rt_c = c; t.G = RTG; t.H = RTH; out = t;
+    e.free_hint = rt_free_mem();
     return true;
 }
 // blocks per msm for the direct table MSM: every block of a wave runs ceil(T / (nb*128)) terms per thread, so pick the nb whose
@@ -247,6 +255,22 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     const int lgN = ilog2_sz(N);
     const size_t plen = 32 * (9 + 2 * (size_t)lgN);
     phase_trace tr(s);
+#ifndef ROFL_EMUL
+    struct host_prof_line {          // ROFL_HOSTPROF=1: one line per call with the host time of this thread by category
+        std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(); rt_host_prof p0 = rt_hostprof(); int C; struct rusage r0;
+        host_prof_line() { getrusage(RUSAGE_THREAD, &r0); }
+        ~host_prof_line() {
+            if (!rt_hostprof_on()) return;
+            struct rusage r1; getrusage(RUSAGE_THREAD, &r1);
+            auto tv = [](const timeval &a, const timeval &b) { return (a.tv_sec - b.tv_sec) * 1e3 + (a.tv_usec - b.tv_usec) / 1e3; };
+            fprintf(stderr, "[rofl host] rusage: user=%.2f ms sys=%.2f ms minor_faults=%ld major_faults=%ld vol_cs=%ld invol_cs=%ld\n", tv(r1.ru_utime, r0.ru_utime), tv(r1.ru_stime, r0.ru_stime),
+                    r1.ru_minflt - r0.ru_minflt, r1.ru_majflt - r0.ru_majflt, r1.ru_nvcsw - r0.ru_nvcsw, r1.ru_nivcsw - r0.ru_nivcsw);
+            const rt_host_prof &p = rt_hostprof(); const double tot = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            const double sy = p.sync - p0.sync, la = p.launch - p0.launch, co = p.copy - p0.copy, al = p.alloc - p0.alloc, pa = p.par - p0.par, se = p.ser - p0.ser;
+            fprintf(stderr, "[rofl host] prove_chunks C=%d total=%.2f sync=%.2f launch=%.2f copy=%.2f alloc=%.2f parallel_for=%.2f serial_for=%.2f other=%.2f ms\n", C, tot, sy, la, co, al, pa, se, tot - sy - la - co - al - pa - se);
+        }
+    } hpl; hpl.C = C;
+#endif
     // ---- device scratch
     dev_buf d_keys(32 * (size_t)C, s), d_sLR(sizeof(sc_st) * 2 * NT, s), d_sums(sizeof(sc_st) * 5 * C, s);
     { std::vector<uint32_t> kw(8 * (size_t)C); for (int c = 0; c < C; c++) key_words(&kw[8 * c], &keys[32 * c]); rt_h2d(d_keys.p, kw.data(), 32 * (size_t)C, s); }
@@ -392,7 +416,10 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         while (r < pre && 2 * ((N / 2) >> r) > FRZ_MAX_F) r++;
         const size_t fa = r < lgN ? 2 * ((N / 2) >> r) : 0;
         const double need = (double)C * 2 * fa * FRZ_Q * (FRZ_E + 1) * sizeof(p3_st);
-        if (pre - r >= 2 && fa >= 4 && need < 0.25 * (double)rt_free_mem()) { ra = r; FA = fa; cAstride = (uint32_t)(FA / ((N / 2) >> (pre - 1))); }
+        // (the budget check uses the free memory recorded when the tables were built: cudaMemGetInfo itself blocks for tens of
+        //  milliseconds every now and then -- it was the cause of the "slow steps" of DESIGN.md section 7)
+        if (e.free_hint.load() == 0) e.free_hint = rt_free_mem();
+        if (pre - r >= 2 && fa >= 4 && need < 0.25 * (double)e.free_hint.load()) { ra = r; FA = fa; cAstride = (uint32_t)(FA / ((N / 2) >> (pre - 1))); }
     }
     std::vector<sc> cAG((size_t)C * cAstride), cAH((size_t)C * cAstride);
     std::vector<sc_st> h_cA(2 * (size_t)C * cAstride);

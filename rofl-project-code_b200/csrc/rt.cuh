@@ -7,6 +7,29 @@
 #include <mutex>
 #include <cstdlib>
 #include <cstdio>
+// Diagnostic (ROFL_HOSTPROF=1): where a proof's HOST time goes -- stream waits, kernel launches, copies, allocation -- per calling
+// thread; prove_chunks prints one line per call.
+#include <chrono>
+struct rt_host_prof { double sync = 0, launch = 0, copy = 0, alloc = 0, par = 0, ser = 0; };
+inline bool rt_hostprof_on() { static const bool on = getenv("ROFL_HOSTPROF") != nullptr; return on; }
+inline rt_host_prof &rt_hostprof() { static thread_local rt_host_prof p; return p; }
+struct rt_host_gap { std::chrono::steady_clock::time_point last_end; const char *last_label = nullptr; int ordinal = 0; };
+inline rt_host_gap &rt_hostgap() { static thread_local rt_host_gap g; return g; }
+struct rt_host_timer {
+    double *slot; std::chrono::steady_clock::time_point t0; const char *label;
+    explicit rt_host_timer(double rt_host_prof::*m, const char *lb = "call") : slot(rt_hostprof_on() ? &(rt_hostprof().*m) : nullptr), label(lb) {
+        if (!slot) return;
+        t0 = std::chrono::steady_clock::now();
+        rt_host_gap &g = rt_hostgap();               // host time BETWEEN two runtime calls: report the long ones with their neighbours
+        if (g.last_label) { const double gap = std::chrono::duration<double, std::milli>(t0 - g.last_end).count(); if (gap > 3.0) fprintf(stderr, "[rofl gap] %.2f ms of host time between call #%d %s and %s\n", gap, g.ordinal, g.last_label, label); }
+        g.ordinal++;
+    }
+    ~rt_host_timer() {
+        if (!slot) return;
+        auto t1 = std::chrono::steady_clock::now(); *slot += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        rt_host_gap &g = rt_hostgap(); g.last_end = t1; g.last_label = label;
+    }
+};
 #ifdef ROFL_EMUL
 #include "cuda_emul.h"
 inline void rt_check(int, const char *) {}
@@ -85,15 +108,16 @@ struct rt_big_cache {
     }
 };
 inline rt_big_cache &rt_bigs() { static rt_big_cache c; return c; }
-inline void *rt_malloc(size_t n, cudaStream_t s) { return rt_bigs().take(n, s); }
-inline void rt_free(void *p, cudaStream_t s) { if (p && !rt_bigs().give(p, s)) cudaFreeAsync(p, s); }
-inline void rt_h2d(void *d, const void *h, size_t n, cudaStream_t s) { rt_check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "h2d"); }
-inline void rt_d2h(void *h, const void *d, size_t n, cudaStream_t s) { rt_check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "d2h"); }
+inline void *rt_malloc(size_t n, cudaStream_t s) { rt_host_timer t(&rt_host_prof::alloc, "rt_malloc"); return rt_bigs().take(n, s); }
+inline void rt_free(void *p, cudaStream_t s) { rt_host_timer t(&rt_host_prof::alloc, "rt_free"); if (p && !rt_bigs().give(p, s)) cudaFreeAsync(p, s); }
+inline void rt_h2d(void *d, const void *h, size_t n, cudaStream_t s) { rt_host_timer t(&rt_host_prof::copy, "h2d"); rt_check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "h2d"); }
+inline void rt_d2h(void *h, const void *d, size_t n, cudaStream_t s) { rt_host_timer t(&rt_host_prof::copy, "d2h"); rt_check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "d2h"); }
 inline void rt_d2d(void *d, const void *s_, size_t n, cudaStream_t s) { rt_check(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s), "d2d"); }
 inline void rt_memset(void *d, int v, size_t n, cudaStream_t s) { rt_check(cudaMemsetAsync(d, v, n, s), "memset"); }
 // Stream wait.  ROFL_SYNC=spin polls cudaStreamQuery instead (a proof has ~20 host round trips; measured on B200: no gain over the
 // blocking call, so blocking stays the default)
 inline void rt_sync(cudaStream_t s) {
+    rt_host_timer t(&rt_host_prof::sync, "sync");
     static const int spin = [] { const char *m = getenv("ROFL_SYNC"); return m && m[0] == 's' ? 1 : 0; }();
     if (!spin) { rt_check(cudaStreamSynchronize(s), "sync"); return; }
     for (;;) {

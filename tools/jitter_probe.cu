@@ -32,7 +32,7 @@ int main(int argc, char **argv) {
     double worst = 0, worstgap = 0; int slow = 0;
     for (int w = 0; w < W; w++) {
         double mean = cnt[w] ? sum[w] / cnt[w] * 1e3 : 0;
-        if (mx[w] * 1e3 > 300 || gap[w] * 1e3 > 300) { printf("%3d: %6d %8.1f %9.1f | %9.1f\n", w, cnt[w], mean, mx[w] * 1e3, gap[w] * 1e3); slow++; }
+        if (mx[w] * 1e3 > 300 || gap[w] * 1e3 > 300 || mean > 20.0) { printf("%3d: %6d %8.1f %9.1f | %9.1f\n", w, cnt[w], mean, mx[w] * 1e3, gap[w] * 1e3); slow++; }
         if (mx[w] > worst) worst = mx[w]; if (gap[w] > worstgap) worstgap = gap[w];
     }
     long total = 0; for (int c : cnt) total += c;

@@ -2,7 +2,7 @@
 # step-time noise A/B: tools/noise_ab.sh ROUNDS "ENV_A" "ENV_B" ... ; prints median / mean / slow-step count per run
 R=$1; shift
 for r in $(seq 1 $R); do for envs in "$@"; do
-  env $envs BENCH_NO_CLOCKS=1 timeout 300 python bench.py --steps 40 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep "per-step" | python -c "
+  env $envs BENCH_NO_CLOCKS=1 timeout 300 python bench.py --steps 40 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep -E "^(resident|e2e) per-step" | python -c "
 import sys,re,statistics as st
 tot=[]
 for l in sys.stdin:
