@@ -214,6 +214,7 @@ def main():
     # ---- per-kernel breakdown: the same K resident steps again with CUDA events around every launch of the main kernel families
     # (separate pass: creating / recording the events costs host time that must not leak into `value`)
     api.set_option("groups", 1)             # one chunk group: every kernel is timed ALONE on the GPU (several groups overlap kernels of different rounds)
+    step_resident(299); torch.cuda.synchronize()      # untimed: the one-group scratch sizes are new to the block cache
     lib.rofl_prof_enable(1); lib.rofl_prof_reset()
     prof_step_ms = 0.0
     prof_steps = []
