@@ -218,6 +218,25 @@ def test_compressed_rand_proof_parity_and_full_size(api, oracle):
     assert api.crp_prove(np.zeros(900001, np.float32), None, np.zeros((900001, 32), np.uint8), 16, 7, seed)[0] == -6
 
 
+def test_every_table_radix_gives_the_same_bytes(api, oracle):
+    """The generator-table radix is chosen by free memory (2^11 on an empty B200): force 8, 9, 10 and no tables at all and compare
+    proofs with the oracle byte for byte; the verifier accepts them at every radix."""
+    rng = np.random.default_rng(77)
+    D, rb, P, nb = 700, 16, 8, 16
+    mn, mx = oracle.clip_bounds(rb, nb, 7)
+    v = rng.uniform(mn, mx, D).astype(np.float32); bl = oracle.rnd_scalar_vec(b"\x70" * 32, D); seed = bytes([21] * 32)
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, rb, P, nb, 7, seed)
+    assert rc_o == 0
+    try:
+        for bits, use_rt in [(8, 1), (9, 1), (10, 1), (11, 1), (11, 0)]:
+            api.set_option("rt_bits", bits); api.set_option("use_rt", use_rt)
+            rc, p, c = api.range_prove(v, bl, rb, P, nb, 7, seed)
+            assert rc == 0 and (c == c_o).all() and (p == p_o).all(), (bits, use_rt)
+            assert api.range_verify(p, c, rb, seed) == 1
+    finally:
+        api.set_option("use_rt", 1); api.set_option("rt_bits", 11)
+
+
 def test_rand_and_square_rand_proof_parity_and_full_size(api, oracle):
     """Per-element proofs of the un-optimised encodings (enc types 2 and 3): byte parity at 3 000 elements, then configs[0]'s 5 000 x 4
     on the GPU alone with existing commitments (as params.rs creates them), tamper and format rejection."""
