@@ -141,6 +141,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     api = pkg.context(local)                       # raises without the CUDA library / device: no CPU fallback
     lib = api.lib
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 16)
+    host_threads = int(os.environ.get("BENCH_HOST_THREADS", "0")) or max(2, min(32, ncpu // max(1, world)))
+    lib.rofl_set_host_threads(api.h, host_threads)  # the ranks of one box share its cores: split them for the transcript threads
+    if rank == 0:
+        print("host cpus %d, ranks %d -> %d transcript threads per rank" % (ncpu, world, host_threads), file=sys.stderr)
     stream = torch.cuda.ExternalStream(lib.rofl_ctx_stream(api.h), device=torch.device("cuda", local))
     D, rb, P, nb, fr = w["D"], w["range_bits"], w["n_partition"], w["n_bits"], w["frac"]
     v_h = torch.from_numpy(synth(D, rb, nb, fr, 1000 + rank)).pin_memory()
