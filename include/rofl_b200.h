@@ -142,6 +142,19 @@ int rofl_enc_l2_compressed_encrypt(rofl_ctx *, const float *v, const uint8_t *bl
                                    size_t *out_proof_len, size_t *out_n_proofs, uint8_t *out_square_range_proof, size_t *out_sq_proof_len);
 int rofl_enc_l2_compressed_verify(rofl_ctx *, const uint8_t *enc_values96, size_t D, const uint8_t *square_proofs160, const uint8_t *range_proofs, size_t proof_len,
                                   size_t n_proofs, const uint8_t *square_range_proof, size_t sq_proof_len, int prove_range, int l2_range, const uint8_t seed[32]);
+/* The two un-optimised encodings end to end (same conventions as above):
+ *   EncParamsRange::{encrypt, verify}  (params.rs:467-510, 186-203)   enc_values = D x 64, rand_proofs = D x 128 (one RandProof per element, over the UNCLIPPED
+ *                                       plaintext as in the reference), range proofs over the first round(D * check_percentage) elements (all when >= 1)
+ *   EncParamsL2::{encrypt, verify}     (params.rs:607-646, 205-233)   enc_values = D x 96, square_proofs = D x 192 (SquareRandProof), range_proof[], square_range_proof */
+int rofl_enc_range_encrypt(rofl_ctx *, const float *v, const uint8_t *blind32, size_t D, int prove_range, size_t n_partition, float check_percentage, int n_bits, int frac,
+                           const uint8_t seed[32], uint8_t *out_enc_values64, uint8_t *out_rand_proofs128, uint8_t *out_range_proofs, size_t *out_proof_len, size_t *out_n_proofs);
+int rofl_enc_range_verify(rofl_ctx *, const uint8_t *enc_values64, size_t D, const uint8_t *rand_proofs128, const uint8_t *range_proofs, size_t proof_len, size_t n_proofs,
+                          int prove_range, float check_percentage, const uint8_t seed[32]);
+int rofl_enc_l2_encrypt(rofl_ctx *, const float *v, const uint8_t *blind32, size_t D, int prove_range, size_t n_partition, int l2_range, int n_bits, int frac,
+                        const uint8_t seed[32], uint8_t *out_enc_values96, uint8_t *out_square_proofs192, uint8_t *out_range_proofs, size_t *out_proof_len, size_t *out_n_proofs,
+                        uint8_t *out_square_range_proof, size_t *out_sq_proof_len);
+int rofl_enc_l2_verify(rofl_ctx *, const uint8_t *enc_values96, size_t D, const uint8_t *square_proofs192, const uint8_t *range_proofs, size_t proof_len, size_t n_proofs,
+                       const uint8_t *square_range_proof, size_t sq_proof_len, int prove_range, int l2_range, const uint8_t seed[32]);
 int rofl_square_prove(rofl_ctx *, const float *v, const uint8_t *value_com32, const uint8_t *r1_32, const uint8_t *r2_32, size_t D, int n_bits, int frac,
                       const uint8_t seed[32], uint8_t *out_proofs160, uint8_t *out_commits64);
 int rofl_square_prove_dev(rofl_ctx *, const float *v, const uint8_t *value_com32, const uint8_t *r1_32, const uint8_t *r2_32, size_t D, int n_bits, int frac,

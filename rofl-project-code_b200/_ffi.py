@@ -37,6 +37,10 @@ _SIGS = {
     "rofl_enc_range_compressed_encrypt": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p, c_u8p, C.POINTER(c_sz), C.POINTER(c_sz)]),
     "rofl_enc_range_compressed_verify": (C.c_int, [c_vp, c_u8p, c_sz, c_u8p, c_u8p, c_sz, c_sz, C.c_int, C.c_float, c_u8p]),
     "rofl_enc_l2_compressed_encrypt": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, c_sz, C.c_int, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, C.POINTER(c_sz), C.POINTER(c_sz), c_u8p, C.POINTER(c_sz)]),
+    "rofl_enc_range_encrypt": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, c_sz, C.c_float, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p, c_u8p, C.POINTER(c_sz), C.POINTER(c_sz)]),
+    "rofl_enc_range_verify": (C.c_int, [c_vp, c_u8p, c_sz, c_u8p, c_u8p, c_sz, c_sz, C.c_int, C.c_float, c_u8p]),
+    "rofl_enc_l2_encrypt": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, c_sz, C.c_int, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p, c_u8p, C.POINTER(c_sz), C.POINTER(c_sz), c_u8p, C.POINTER(c_sz)]),
+    "rofl_enc_l2_verify": (C.c_int, [c_vp, c_u8p, c_sz, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_sz, C.c_int, C.c_int, c_u8p]),
     "rofl_enc_l2_compressed_verify": (C.c_int, [c_vp, c_u8p, c_sz, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_sz, C.c_int, C.c_int, c_u8p]),
     "rofl_rand_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, c_u8p]),
     "rofl_rand_verify": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz]),
@@ -185,6 +189,35 @@ class Api:
     def enc_l2_compressed_verify(self, msg, seed=SEED0):
         enc = _u8(msg["enc_values"]).reshape(-1, 96); sp = _u8(msg["square_proof"]).reshape(-1, 160); p = _u8(msg["range_proof"]); p = p.reshape(p.shape[0], -1); sq = _u8(msg["square_range_proof"])
         rc = self.lib.rofl_enc_l2_compressed_verify(self.h, _ptr(enc), enc.shape[0], _ptr(sp), _ptr(p), p.shape[1], p.shape[0], _ptr(sq), sq.size, msg["range_bits"], msg["l2_range_bits"], _ptr(_u8(seed, 32)))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc
+
+    # ---- the un-optimised encodings end to end (params.rs EncParamsRange / EncParamsL2)
+    def enc_range_encrypt(self, v, blind, prove_range, n_partition, check_percentage, n_bits, frac, seed=SEED0):
+        v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
+        num = D if check_percentage >= 1.0 else int(np.floor(float(np.float32(np.float32(D) * np.float32(check_percentage))) + 0.5))      # llroundf
+        npf, plen = self.range_proof_shape(max(num, 1), prove_range, n_partition)
+        enc = np.zeros((D, 64), np.uint8); rp = np.zeros((D, 128), np.uint8); proofs = np.zeros((npf, max(plen, 1)), np.uint8); a, c = c_sz(), c_sz()
+        rc = self.lib.rofl_enc_range_encrypt(self.h, _ptr(v), _ptr(b), D, prove_range, n_partition, check_percentage, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(enc), _ptr(rp), _ptr(proofs), C.byref(a), C.byref(c))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc, dict(enc_values=enc, rand_proof=rp, range_proof=proofs[:c.value, :a.value] if rc == 0 else proofs, range_bits=prove_range)
+    def enc_range_verify(self, msg, check_percentage=1.0, seed=SEED0):
+        enc = _u8(msg["enc_values"]).reshape(-1, 64); rp = _u8(msg["rand_proof"]).reshape(-1, 128); p = _u8(msg["range_proof"]); p = p.reshape(p.shape[0], -1)
+        rc = self.lib.rofl_enc_range_verify(self.h, _ptr(enc), enc.shape[0], _ptr(rp), _ptr(p), p.shape[1], p.shape[0], msg["range_bits"], check_percentage, _ptr(_u8(seed, 32)))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc
+    def enc_l2_encrypt(self, v, blind, prove_range, n_partition, l2_range, n_bits, frac, seed=SEED0):
+        v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
+        npf, plen = self.range_proof_shape(D, prove_range, n_partition)
+        enc = np.zeros((D, 96), np.uint8); sp = np.zeros((D, 192), np.uint8); proofs = np.zeros((npf, max(plen, 1)), np.uint8)
+        sq = np.zeros(self.range_proof_len(max(l2_range, 1)), np.uint8); a, c, q = c_sz(), c_sz(), c_sz()
+        rc = self.lib.rofl_enc_l2_encrypt(self.h, _ptr(v), _ptr(b), D, prove_range, n_partition, l2_range, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(enc), _ptr(sp), _ptr(proofs),
+                                          C.byref(a), C.byref(c), _ptr(sq), C.byref(q))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc, dict(enc_values=enc, square_proof=sp, range_proof=proofs, square_range_proof=sq, range_bits=prove_range, l2_range_bits=l2_range)
+    def enc_l2_verify(self, msg, seed=SEED0):
+        enc = _u8(msg["enc_values"]).reshape(-1, 96); sp = _u8(msg["square_proof"]).reshape(-1, 192); p = _u8(msg["range_proof"]); p = p.reshape(p.shape[0], -1); sq = _u8(msg["square_range_proof"])
+        rc = self.lib.rofl_enc_l2_verify(self.h, _ptr(enc), enc.shape[0], _ptr(sp), _ptr(p), p.shape[1], p.shape[0], _ptr(sq), sq.size, msg["range_bits"], msg["l2_range_bits"], _ptr(_u8(seed, 32)))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
 

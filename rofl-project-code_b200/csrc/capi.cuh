@@ -278,6 +278,89 @@ extern "C" int rofl_enc_l2_compressed_verify(rofl_ctx *c, const uint8_t *enc_val
     return engine_l2_verify(c->e, square_range_proof, sq_plen, sum, l2_range, seed) == 1 ? 1 : 0;
     API_CATCH
 }
+// ---- the two un-optimised encodings end to end -------------------------------------------------------------------------------------------------
+// EncParamsRange::encrypt (params.rs:467-510): range proofs on the clipped values (all of them, or the first round(D * check_percentage)), then one
+// RandProof per element over the UNCLIPPED plaintext -- on the range proofs' commitments when everything was range-proved (create_randproof_vec_existing),
+// on fresh commitments otherwise (create_randproof_vec).  enc_values = D x 64 (L | R), rand_proofs = D x 128.
+extern "C" int rofl_enc_range_encrypt(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D, int prove_range, size_t n_partition, float check_percentage, int n_bits, int frac,
+                                      const uint8_t seed[32], uint8_t *enc_values64, uint8_t *rand_proofs128, uint8_t *range_proofs, size_t *plen, size_t *n_proofs) {
+    API_TRY
+    if (!D) return ROFL_ERR_ARGS;
+    cudaStream_t s = c->e.stream;
+    std::vector<float> clipped(D); rofl_clip_f32_to_range_vec(v, D, prove_range, n_bits, frac, clipped.data());                 // :475
+    const bool all = check_percentage >= 1.0f;
+    const size_t num = all ? D : (size_t)llroundf((float)D * check_percentage);                                                 // :487
+    if (num > D) return ROFL_ERR_ARGS;
+    staged_in dv(clipped.data(), 4 * D, s), dplain(v, 4 * D, s), db(blind, 32 * D, s); dev_buf dC(32 * D, s), dP(128 * D, s), dE(64 * D, s);
+    size_t a = 0, b = 0;
+    int rc = engine_range_prove(c->e, dv.b.as<float>(), db.b.as<uint8_t>(), num, prove_range, n_partition, n_bits, frac, seed, range_proofs, &a, &b, dC.as<uint8_t>());
+    if (plen) *plen = a; if (n_proofs) *n_proofs = b;
+    if (rc) return rc;
+    rc = engine_sigma_prove(c->e, 1, dplain.b.as<float>(), all ? dC.as<uint8_t>() : nullptr, db.b.as<uint8_t>(), nullptr, D, n_bits, frac, seed, dP.as<uint8_t>(), dE.as<uint8_t>());   // :498-503
+    if (rc) return rc;
+    rt_d2h(rand_proofs128, dP.p, 128 * D, s); rt_d2h(enc_values64, dE.p, 64 * D, s); rt_sync(s);
+    return 0;
+    API_CATCH
+}
+// EncModelParams::verify, EncRange arm (params.rs:186-203): every RandProof, then the range proofs over the first round(D * check_percentage) Pedersen halves
+extern "C" int rofl_enc_range_verify(rofl_ctx *c, const uint8_t *enc_values64, size_t D, const uint8_t *rand_proofs128, const uint8_t *range_proofs, size_t plen, size_t n_proofs,
+                                     int prove_range, float check_percentage, const uint8_t seed[32]) {
+    API_TRY
+    if (!D || !n_proofs) return ROFL_ERR_ARGS;
+    cudaStream_t s = c->e.stream;
+    staged_in dp(enc_values64, 64 * D, s), dpf(rand_proofs128, 128 * D, s); dev_buf dL(32 * D, s), dR(32 * D, s);
+    const int ok = engine_sigma_verify(c->e, 1, dpf.b.as<uint8_t>(), dp.b.as<uint8_t>(), D);
+    if (ok < 0) return 0;                                                                                                      // Err(_) -> false
+    const size_t num = (size_t)llroundf((float)D * check_percentage);
+    if (num == 0 || num > D) return 0;
+    LAUNCH(k_pairs_split, dim3((unsigned)((D + 255) / 256)), dim3(256), s, dL.as<uint8_t>(), dR.as<uint8_t>(), dp.b.as<uint8_t>(), D);
+    const int rr = engine_range_verify(c->e, range_proofs, plen, n_proofs, dL.as<uint8_t>(), num, prove_range, seed);
+    return (ok == 1 && rr == 1) ? 1 : 0;
+    API_CATCH
+}
+// EncParamsL2::encrypt (params.rs:607-646): range proofs, the sum-of-squares proof under fresh rand_scalars, one SquareRandProof per element on the range proofs' commitments.
+// enc_values = D x 96 (c.L | c.R | c_sq), square_proofs = D x 192.
+extern "C" int rofl_enc_l2_encrypt(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D, int prove_range, size_t n_partition, int l2_range, int n_bits, int frac,
+                                   const uint8_t seed[32], uint8_t *enc_values96, uint8_t *square_proofs192, uint8_t *range_proofs, size_t *plen, size_t *n_proofs,
+                                   uint8_t *square_range_proof, size_t *sq_plen) {
+    API_TRY
+    if (!D) return ROFL_ERR_ARGS;
+    cudaStream_t s = c->e.stream;
+    std::vector<float> clipped(D); rofl_clip_f32_to_range_vec(v, D, prove_range, n_bits, frac, clipped.data());                 // :616
+    std::vector<uint8_t> rnd(32 * D); { uint8_t k2[32]; derive_key(k2, seed, DOM_RND_VEC, 1); rofl_rnd_scalar_vec(k2, D, rnd.data()); }   // rand_scalars (:615)
+    staged_in dv(clipped.data(), 4 * D, s), db(blind, 32 * D, s), dr(rnd.data(), 32 * D, s); dev_buf dC(32 * D, s), dP(192 * D, s), dE(96 * D, s);
+    size_t a = 0, b = 0, q = 0;
+    int rc = engine_range_prove(c->e, dv.b.as<float>(), db.b.as<uint8_t>(), D, prove_range, n_partition, n_bits, frac, seed, range_proofs, &a, &b, dC.as<uint8_t>());
+    if (plen) *plen = a; if (n_proofs) *n_proofs = b;
+    if (rc) return rc;
+    uint8_t sum_commit[32];
+    rc = engine_l2_prove(c->e, clipped.data(), dv.b.as<float>(), dr.b.as<uint8_t>(), D, l2_range, n_bits, frac, seed, square_range_proof, &q, sum_commit);      // :624-630
+    if (sq_plen) *sq_plen = q;
+    if (rc) return rc;
+    rc = engine_sigma_prove(c->e, 2, dv.b.as<float>(), dC.as<uint8_t>(), db.b.as<uint8_t>(), dr.b.as<uint8_t>(), D, n_bits, frac, seed, dP.as<uint8_t>(), dE.as<uint8_t>());  // :631-637
+    if (rc) return rc;
+    rt_d2h(square_proofs192, dP.p, 192 * D, s); rt_d2h(enc_values96, dE.p, 96 * D, s); rt_sync(s);
+    return 0;
+    API_CATCH
+}
+// EncModelParams::verify, EncL2 arm (params.rs:205-233): every SquareRandProof, the range proofs over all c.L, the sum proof over sum c_sq
+extern "C" int rofl_enc_l2_verify(rofl_ctx *c, const uint8_t *enc_values96, size_t D, const uint8_t *square_proofs192, const uint8_t *range_proofs, size_t plen, size_t n_proofs,
+                                  const uint8_t *square_range_proof, size_t sq_plen, int prove_range, int l2_range, const uint8_t seed[32]) {
+    API_TRY
+    if (!D || !n_proofs) return ROFL_ERR_ARGS;
+    cudaStream_t s = c->e.stream;
+    staged_in de(enc_values96, 96 * D, s), dsp(square_proofs192, 192 * D, s); dev_buf dL(32 * D, s), dSc(64 * D, s), dCsq(32 * D, s);
+    const int ok = engine_sigma_verify(c->e, 2, dsp.b.as<uint8_t>(), de.b.as<uint8_t>(), D);
+    if (ok < 0) return 0;
+    LAUNCH(k_split96, dim3((unsigned)((D + 255) / 256)), dim3(256), s, dL.as<uint8_t>(), dSc.as<uint8_t>(), dCsq.as<uint8_t>(), de.b.as<uint8_t>(), D);
+    const int rr = engine_range_verify(c->e, range_proofs, plen, n_proofs, dL.as<uint8_t>(), D, prove_range, seed);
+    if (rr < 0) return 0;
+    uint8_t sum[32];
+    if (engine_points_sum(c->e, dCsq.as<uint8_t>(), D, sum) != 0) return 0;
+    const int rs = engine_l2_verify(c->e, square_range_proof, sq_plen, sum, l2_range, seed);
+    return (ok == 1 && rr == 1 && rs == 1) ? 1 : 0;
+    API_CATCH
+}
 extern "C" int rofl_square_prove_dev(rofl_ctx *c, const float *v, const uint8_t *vc, const uint8_t *r1, const uint8_t *r2, size_t D, int n_bits, int frac,
                                      const uint8_t seed[32], uint8_t *proofs, uint8_t *commits) {
     API_TRY return engine_square_prove(c->e, v, vc, r1, r2, D, n_bits, frac, seed, proofs, commits); API_CATCH

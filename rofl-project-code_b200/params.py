@@ -34,3 +34,31 @@ class EncParamsL2Compressed:
     @staticmethod
     def verify(msg, seed=SEED0):
         return bool(_c().enc_l2_compressed_verify(msg, seed))
+
+
+class EncParamsRange:
+    """params.rs:467-510 / :186-203 -- un-optimised L-inf encoding: one RandProof per element"""
+    @staticmethod
+    def encrypt(plaintext_vec, blinding_vec, prove_range, n_partition, check_percentage=1.0, seed=SEED0):
+        rc, msg = _c().enc_range_encrypt(plaintext_vec, blinding_vec, prove_range, n_partition, check_percentage, fp.N_BITS, fp.FRAC, seed)
+        if rc:
+            raise RuntimeError(f"encrypt failed ({rc}); the reference unwrap()s here")
+        return msg
+
+    @staticmethod
+    def verify(msg, check_percentage=1.0, seed=SEED0):
+        return bool(_c().enc_range_verify(msg, check_percentage, seed))
+
+
+class EncParamsL2:
+    """params.rs:607-646 / :205-233 -- un-optimised L2 encoding: one SquareRandProof per element"""
+    @staticmethod
+    def encrypt(plaintext_vec, blinding_vec, prove_range, n_partition, l2_range, seed=SEED0):
+        rc, msg = _c().enc_l2_encrypt(plaintext_vec, blinding_vec, prove_range, n_partition, l2_range, fp.N_BITS, fp.FRAC, seed)
+        if rc:
+            raise RuntimeError(f"encrypt failed ({rc}); the reference unwrap()s here")
+        return msg
+
+    @staticmethod
+    def verify(msg, seed=SEED0):
+        return bool(_c().enc_l2_verify(msg, seed))

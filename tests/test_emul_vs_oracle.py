@@ -248,6 +248,51 @@ def test_optimised_encodings_end_to_end(api, oracle):
         assert api.enc_l2_compressed_verify(bad, seed) == 0, field
 
 
+def test_unoptimised_encodings_end_to_end(api, oracle):
+    """EncParamsRange / EncParamsL2 (params.rs:467-510, 607-646, 186-233): encrypt == the oracle's pieces put together the reference's way,
+    verify accepts, honours check_percentage, rejects tampering; the reference's quirk that the RandProofs cover the UNCLIPPED plaintext."""
+    rng = np.random.default_rng(34)
+    D, P, seed = 6, 2, bytes([12] * 32)
+    v = (rng.integers(-100, 100, D) / 128).astype(np.float32); bl = oracle.rnd_scalar_vec(b"\x6c" * 32, D)
+    rc, msg = api.enc_range_encrypt(v, bl, 8, P, 1.0, 16, 7, seed)
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, 8, P, 16, 7, seed)
+    rc_r, pf_o, pairs_o = oracle.rand_prove(v, c_o, bl, 16, 7, seed)
+    assert rc == rc_o == rc_r == 0 and (msg["range_proof"] == p_o).all() and (msg["rand_proof"] == pf_o).all() and (msg["enc_values"] == pairs_o).all()
+    assert api.enc_range_verify(msg, 1.0, seed) == 1
+    bad = dict(msg); bad["rand_proof"] = msg["rand_proof"].copy(); bad["rand_proof"][2, 70] ^= 1
+    assert api.enc_range_verify(bad, 1.0, seed) == 0
+    bad = dict(msg); bad["range_proof"] = msg["range_proof"].copy(); bad["range_proof"][1, 40] ^= 1
+    assert api.enc_range_verify(bad, 1.0, seed) == 0
+    # probabilistic checking: range proofs over the first round(6 * 0.5) = 3 elements only, fresh commitments for the pairs
+    rc, half = api.enc_range_encrypt(v, bl, 8, P, 0.5, 16, 7, seed)
+    rc_o, p3, c3 = oracle.range_prove(v[:3], bl[:3], 8, P, 16, 7, seed)
+    rc_r, pf3, pairs3 = oracle.rand_prove(v, None, bl, 16, 7, seed)
+    assert rc == rc_o == rc_r == 0 and half["range_proof"].shape == p3.shape and (half["range_proof"] == p3).all() and (half["rand_proof"] == pf3).all() and (half["enc_values"] == pairs3).all()
+    assert api.enc_range_verify(half, 0.5, seed) == 1 and api.enc_range_verify(half, 1.0, seed) == 0
+    # quirk: a value outside the range is clipped for the range proof but not for the RandProof -> bytes as the reference would make them, verify fails
+    v2 = v.copy(); v2[4] = 5.0
+    clipped = oracle.clip_f32_to_range_vec(v2, 8, 16, 7) if hasattr(oracle, "clip_f32_to_range_vec") else np.clip(v2, *oracle.clip_bounds(8, 16, 7)).astype(np.float32)
+    rc, m2 = api.enc_range_encrypt(v2, bl, 8, P, 1.0, 16, 7, seed)
+    rc_o, p_o, c_o = oracle.range_prove(clipped, bl, 8, P, 16, 7, seed)
+    rc_r, pf_o, pairs_o = oracle.rand_prove(v2, c_o, bl, 16, 7, seed)
+    assert rc == rc_o == rc_r == 0 and (m2["range_proof"] == p_o).all() and (m2["rand_proof"] == pf_o).all() and (m2["enc_values"] == pairs_o).all()
+    assert api.enc_range_verify(m2, 1.0, seed) == 0
+    # --- L2 (fp 32/7, 8-bit L-inf, 32-bit L2)
+    rc, m3 = api.enc_l2_encrypt(v, bl, 8, P, 32, 32, 7, seed)
+    rnd = oracle.rnd_scalar_vec(oracle.derive_key(seed, 7, 1), D)
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, 8, P, 32, 7, seed)
+    rc_s, sumproof_o, sumcm_o = oracle.l2_prove(v, rnd, 32, 32, 7, seed)
+    rc_q, sp_o, sc_o = oracle.square_rand_prove(v, c_o, bl, rnd, 32, 7, seed)
+    assert rc == rc_o == rc_s == rc_q == 0
+    assert (m3["range_proof"] == p_o).all() and (m3["square_range_proof"] == sumproof_o).all() and (m3["square_proof"] == sp_o).all() and (m3["enc_values"] == sc_o).all()
+    assert api.enc_l2_verify(m3, seed) == 1
+    for field, (i, j) in [("enc_values", (2, 70)), ("square_proof", (3, 100)), ("range_proof", (1, 40)), ("square_range_proof", (None, 50))]:
+        bad = dict(m3); bad[field] = m3[field].copy()
+        if i is None: bad[field][j] ^= 1
+        else: bad[field][i, j] ^= 1
+        assert api.enc_l2_verify(bad, seed) == 0, field
+
+
 def test_rand_and_square_rand_proofs(api, oracle):
     """RandProof (enc type 2) and SquareRandProof (enc type 3): bytes, existing-commitment mode, tamper and format rejection."""
     rng = np.random.default_rng(55)

@@ -218,6 +218,37 @@ def test_compressed_rand_proof_parity_and_full_size(api, oracle):
     assert api.crp_prove(np.zeros(900001, np.float32), None, np.zeros((900001, 32), np.uint8), 16, 7, seed)[0] == -6
 
 
+def test_unoptimised_encodings_whole_messages(api, oracle):
+    """EncParamsRange / EncParamsL2 end to end through the C ABI: byte parity with the oracle's pieces at a small size, then configs[0]'s
+    5 000 parameters on the GPU alone (encrypt -> verify, probabilistic checking, tamper rejection)."""
+    rng = np.random.default_rng(35)
+    D, P, seed = 40, 4, bytes([14] * 32)
+    v = (rng.integers(-100, 100, D) / 128).astype(np.float32); bl = oracle.rnd_scalar_vec(b"\x6d" * 32, D)
+    rc, msg = api.enc_range_encrypt(v, bl, 8, P, 1.0, 16, 7, seed)
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, 8, P, 16, 7, seed)
+    rc_r, pf_o, pairs_o = oracle.rand_prove(v, c_o, bl, 16, 7, seed)
+    assert rc == rc_o == rc_r == 0 and (msg["range_proof"] == p_o).all() and (msg["rand_proof"] == pf_o).all() and (msg["enc_values"] == pairs_o).all()
+    rc, m3 = api.enc_l2_encrypt(v, bl, 8, P, 32, 32, 7, seed)
+    rnd = oracle.rnd_scalar_vec(oracle.derive_key(seed, 7, 1), D)
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, 8, P, 32, 7, seed)
+    rc_s, sumproof_o, _ = oracle.l2_prove(v, rnd, 32, 32, 7, seed)
+    rc_q, sp_o, sc_o = oracle.square_rand_prove(v, c_o, bl, rnd, 32, 7, seed)
+    assert rc == rc_o == rc_s == rc_q == 0
+    assert (m3["range_proof"] == p_o).all() and (m3["square_range_proof"] == sumproof_o).all() and (m3["square_proof"] == sp_o).all() and (m3["enc_values"] == sc_o).all()
+    D = 5000
+    v = (rng.integers(-24, 25, D) / 128).astype(np.float32); bl = api.rnd_scalar_vec(b"\x6e" * 32, D)
+    rc, msg = api.enc_range_encrypt(v, bl, 8, 64, 1.0, 16, 7, seed)
+    assert rc == 0 and api.enc_range_verify(msg, 1.0, seed) == 1
+    bad = dict(msg); bad["enc_values"] = msg["enc_values"].copy(); bad["enc_values"][D - 1, 32:] = msg["enc_values"][0, 32:]
+    assert api.enc_range_verify(bad, 1.0, seed) == 0
+    rc, part = api.enc_range_encrypt(v, bl, 8, 64, 0.25, 16, 7, seed)
+    assert rc == 0 and api.enc_range_verify(part, 0.25, seed) == 1
+    rc, m3 = api.enc_l2_encrypt(v, bl, 8, 64, 32, 32, 7, seed)
+    assert rc == 0 and api.enc_l2_verify(m3, seed) == 1
+    bad = dict(m3); bad["enc_values"] = m3["enc_values"].copy(); bad["enc_values"][7, 64:] = m3["enc_values"][8, 64:]
+    assert api.enc_l2_verify(bad, seed) == 0
+
+
 def test_every_table_radix_gives_the_same_bytes(api, oracle):
     """The generator-table radix is chosen by free memory (2^11 on an empty B200): force 8, 9, 10 and no tables at all and compare
     proofs with the oracle byte for byte; the verifier accepts them at every radix."""
