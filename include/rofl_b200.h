@@ -15,6 +15,10 @@
  *     runtime pair (n_bits in {8,16,32,64}, frac in 0..12).
  *   - every nonce the reference draws from rand::thread_rng() is drawn from ChaCha20 streams derived from `seed`
  *     (32 bytes) in the reference's draw order, so outputs are a pure function of (inputs, seed).
+ *     SECURITY: a prover seed must be SECRET and FRESH for every call (the nonces are a function of the seed alone: a repeated or
+ *     known seed leaks the witness, exactly like a repeated rng state would in the reference).  Fixed seeds are for parity tests only.
+ *     A verifier seed should be fresh too, but the verifier does not rely on it: its batching scalars are derived by Fiat-Shamir from
+ *     the seed AND every proof / commitment byte of the call, so a known seed does not help a forger (ts_kernels.cuh, k_verify_keys).
  *   - return codes: prove calls return 0 on success; verify calls return 1 (valid) / 0 (invalid, the reference's
  *     Ok(false)); negative values are errors (the reference's Err(..) or panic), positive prove codes are the
  *     reference's domain errors.  rofl_last_error() gives a message for the calling thread.
@@ -36,11 +40,12 @@ enum {
     ROFL_ERR_OVERFLOW = 3,             /* L2RangeProofError::OverflowError      (l2_range_proof_vec/errors.rs:4-31)       */
     ROFL_ERR_NORM_OUT_OF_RANGE = 4,    /* L2RangeProofError::NormOutOfRangeError                                         */
     ROFL_ERR_FORMAT = -1,              /* ProofError::FormatError (malformed proof / non-canonical scalar)               */
-    ROFL_ERR_BITSIZE = -1,             /* prove side: ProofError::InvalidBitsize (range not in {8,16,32,64})             */
-    ROFL_ERR_ARGS = -2,                /* bad arguments; verify side: ProofError::InvalidBitsize                          */
+    ROFL_ERR_ARGS = -2,                /* bad arguments (null / zero sizes / unsupported fixed-point configuration)      */
     ROFL_ERR_GENS = -3,                /* ProofError::InvalidGeneratorsLength                                             */
     ROFL_ERR_POINT = -4,               /* a commitment does not decode (the reference's decompress().unwrap() panics)    */
     ROFL_ERR_DLOG = -5,                /* no discrete log in range (bsgs32.rs:69-70 unwrap panic)                         */
+    ROFL_ERR_TOO_MANY = -6,            /* more than 900 000 pairs in a compressed rand proof (the reference's label table ends there) */
+    ROFL_ERR_BITSIZE = -7,             /* ProofError::InvalidBitsize (range not in {8,16,32,64}), prove and verify side   */
     ROFL_ERR_NAN = -98,                /* NaN input (Fix::saturating_from_float panics)                                   */
     ROFL_ERR_PARTITION = -99,          /* n_partition gives non power-of-two chunks (range_proof_vec/mod.rs:137-140 panic) */
     ROFL_ERR_CUDA = -100               /* CUDA runtime error / no device                                                   */
@@ -132,7 +137,10 @@ int rofl_square_rand_verify(rofl_ctx *, const uint8_t *proofs192, const uint8_t 
  *   EncParamsL2Compressed::{encrypt, verify}     (params.rs:797-845, 257-290)   enc_values = D x 96 (L | R | c_sq), square_proof D x 160,
  *                                                                               rand_proof 128 B, range_proof[], square_range_proof
  * encrypt: 0 ok or the error of the failing step; verify: 1 accept, 0 reject (an Err of any part is a reject in the reference too), < 0 bad arguments.
- * The deserialisation checks of the reference (`from_bytes`: points decode, scalars canonical) happen on the GPU inside the verify calls. */
+ * The deserialisation checks of the reference (`from_bytes`: points decode, scalars canonical) happen on the GPU inside the verify calls;
+ * rofl_enc_l2_compressed_verify returns ROFL_ERR_POINT when ANY of the three points of a 96-byte record does not decode -- c.R included, which
+ * that arm never uses afterwards (decode_l2enc_vec, params.rs:560-571 -> SquareRandProofCommitments::from_bytes, square_rand_proof/pedersen.rs:33-45
+ * -> ElGamalPair::from_bytes, rand_proof/el_gamal.rs:112-123; the reference unwrap()s, i.e. one client's malformed message panics the server task). */
 int rofl_enc_range_compressed_encrypt(rofl_ctx *, const float *v, const uint8_t *blind32, size_t D, int prove_range, size_t n_partition, int n_bits, int frac,
                                       const uint8_t seed[32], uint8_t *out_enc_values64, uint8_t *out_rand_proof128, uint8_t *out_range_proofs, size_t *out_proof_len, size_t *out_n_proofs);
 int rofl_enc_range_compressed_verify(rofl_ctx *, const uint8_t *enc_values64, size_t D, const uint8_t *rand_proof128, const uint8_t *range_proofs, size_t proof_len,
@@ -183,6 +191,10 @@ long rofl_prof_launches(int slot);        /* launches of that family; slot -1 = 
 double rofl_prof_work(int slot);          /* algorithmic work of that family since the last reset (slot 4, table MSM: mixed point additions) */
 double rofl_probe_imad_wide(rofl_ctx *);  /* measured IMAD.WIDE.U32 issue rate of this GPU, multiply-adds per second (roofline denominator) */
 void *rofl_ctx_stream(rofl_ctx *);        /* the cudaStream_t the context launches on */
+/* ---- test hooks: the warp-cooperative transcript absorb against the sequential code (0 equal / 1 different), and the Fiat-Shamir batching
+ *      scalars (c_i | rho_i, 2 x n_proofs x 32 bytes) rofl_range_verify derives for a call (return value as rofl_range_verify) */
+int rofl_debug_ts_absorb(rofl_ctx *, const uint8_t *V32, size_t m, int n, int label_id);
+int rofl_debug_verify_weights(rofl_ctx *, const uint8_t *proofs, size_t proof_len, size_t n_proofs, const uint8_t *commits32, size_t D, int range, const uint8_t seed[32], uint8_t *out_weights);
 #ifdef __cplusplus
 }
 #endif

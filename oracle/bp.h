@@ -44,6 +44,8 @@ static inline void bp_gens_chain(ge *out, char which, uint32_t party, int n) {
 typedef struct { int n, m; ge *G, *H; } bp_gens_t;     /* party-major: G[j*n + i] */
 static inline void bp_gens_new(bp_gens_t *g, int n, int m) {
     g->n = n; g->m = m; g->G = (ge *)malloc(sizeof(ge) * n * m); g->H = (ge *)malloc(sizeof(ge) * n * m);
+    /* the party chains are independent; inside a parallel region (one thread per chunk) this loop stays serial */
+#pragma omp parallel for schedule(static) if (m >= 64)
     for (int j = 0; j < m; j++) { bp_gens_chain(g->G + (size_t)j * n, 'G', j, n); bp_gens_chain(g->H + (size_t)j * n, 'H', j, n); }
 }
 static inline void bp_gens_free(bp_gens_t *g) { free(g->G); free(g->H); }
@@ -100,7 +102,18 @@ static inline void ge_msm_pippenger(ge *r, const sc *s, const ge *p, size_t n) {
     *r = acc; free(bk); free(dig);
 }
 static inline void ge_msm(ge *r, const sc *s, const ge *p, size_t n) {
-    if (n < 190) ge_msm_straus(r, s, p, n); else ge_msm_pippenger(r, s, p, n);
+    if (n < 190) { ge_msm_straus(r, s, p, n); return; }
+    if (n < 65536) { ge_msm_pippenger(r, s, p, n); return; }
+    /* one very large chunk (resnet18-full: 4.2 M points): term slices on the host threads, partial sums added up (same group element) */
+    enum { SL = 64 }; ge part[SL]; const size_t per = (n + SL - 1) / SL;
+#pragma omp parallel for schedule(dynamic)
+    for (int t = 0; t < SL; t++) {
+        const size_t b = (size_t)t * per, e = b + per < n ? b + per : n;
+        if (b < e) ge_msm_pippenger(&part[t], s + b, p + b, e - b); else ge_identity(&part[t]);
+    }
+    ge acc; ge_identity(&acc);
+    for (int t = 0; t < SL; t++) ge_add(&acc, &acc, &part[t]);
+    *r = acc;
 }
 /* two-term variable-time a*P + b*Q with width-5 NAFs (dalek vartime Straus on 2 points) */
 static inline void ge_double_scalarmult(ge *r, const sc *a, const ge *P, const sc *b, const ge *Q) {
@@ -181,10 +194,10 @@ static inline size_t rp_proof_len(size_t N) { return 32 * (9 + 2 * (size_t)ilog2
 
 /* ---- RangeProof::prove_multiple_with_rng (A.3).  values < 2^n, m = power of two.
  * proof_out: rp_proof_len(n*m) bytes; V_out: m*32 bytes compressed commitments.
- * returns 0 ok, -1 invalid bitsize, -2 invalid aggregation ------------------------------------ */
+ * returns 0 ok, -7 invalid bitsize, -2 invalid aggregation ------------------------------------ */
 static inline int rp_prove_multiple(uint8_t *proof_out, uint8_t *V_out, const bp_gens_t *bg, const pc_gens_t *pc,
                                     transcript *t, const uint64_t *values, const sc *blindings, int m, int n, rng_t *rng) {
-    if (!(n == 8 || n == 16 || n == 32 || n == 64)) return -1;
+    if (!(n == 8 || n == 16 || n == 32 || n == 64)) return -7;
     if (m <= 0 || (m & (m - 1)) || bg->n < n || bg->m < m) return -2;
     size_t N = (size_t)n * m;
     transcript_append(t, "dom-sep", (const uint8_t *)"rangeproof v1", 13);
@@ -272,7 +285,7 @@ static inline int rp_prove_multiple(uint8_t *proof_out, uint8_t *V_out, const bp
 }
 
 /* ---- RangeProof::from_bytes + verify_multiple_with_rng (A.3).
- * returns 1 accept, 0 VerificationError, -1 FormatError, -2 InvalidBitsize, -3 InvalidGeneratorsLength */
+ * returns 1 accept, 0 VerificationError, -1 FormatError, -7 InvalidBitsize, -3 InvalidGeneratorsLength */
 static inline int rp_verify_multiple(const uint8_t *proof, size_t proof_len, const uint8_t *V, const bp_gens_t *bg,
                                      const pc_gens_t *pc, transcript *t, int m, int n, rng_t *rng) {
     if (proof_len % 32 || proof_len < 7 * 32) return -1;
@@ -284,7 +297,7 @@ static inline int rp_verify_multiple(const uint8_t *proof, size_t proof_len, con
         !sc_from_canonical_bytes(&e_bl, proof + 192)) return -1;
     const uint8_t *ipp = proof + 224;
     if (!sc_from_canonical_bytes(&a, ipp + 64 * lg) || !sc_from_canonical_bytes(&b, ipp + 64 * lg + 32)) return -1;
-    if (!(n == 8 || n == 16 || n == 32 || n == 64)) return -2;
+    if (!(n == 8 || n == 16 || n == 32 || n == 64)) return -7;
     if (bg->n < n || bg->m < m) return -3;
     size_t N = (size_t)n * m;
     transcript_append(t, "dom-sep", (const uint8_t *)"rangeproof v1", 13);
@@ -345,7 +358,11 @@ static inline int rp_verify_multiple(const uint8_t *proof, size_t proof_len, con
         sc_mul(&ezj, &ezj, &z);
     }
     sc_from_u64(&ezj, 1);
-    for (int j = 0; j < m; j++) { sc_mul(&tmp, &c, &zz); sc_mul(&ms[q], &tmp, &ezj); ok &= ge_decompress(&mp[q++], V + 32 * j); sc_mul(&ezj, &ezj, &z); }
+    for (int j = 0; j < m; j++) { sc_mul(&tmp, &c, &zz); sc_mul(&ms[q + j], &tmp, &ezj); sc_mul(&ezj, &ezj, &z); }
+    { int okv = 1;
+#pragma omp parallel for schedule(static) reduction(&: okv) if (m >= 4096)
+      for (int j = 0; j < m; j++) okv &= ge_decompress(&mp[q + j], V + 32 * j);
+      ok &= okv; q += m; }
     int res = 0;
     if (ok) { ge chk; ge_msm(&chk, ms, mp, npts); res = ge_is_identity(&chk); }
     free(ms); free(mp); free(s); free(u_sq); free(u_inv_sq);

@@ -176,7 +176,7 @@ EXPORT size_t orc_next_pow2(size_t v) { return next_pow2(v); }
 EXPORT size_t orc_rp_proof_len(size_t N) { return rp_proof_len(N); }
 
 /* create_rangeproof (:16-102).  proofs_out: n_chunks * rp_proof_len(range*chunk) bytes, commits_out: D*32.
- * returns 0 ok, 1 WrongNumBlindingFactors (n/a here), 2 ValueOutOfRangeError, -1 InvalidBitsize,
+ * returns 0 ok, 1 WrongNumBlindingFactors (n/a here), 2 ValueOutOfRangeError, -7 InvalidBitsize,
  * -99 where the reference panics ("Should not get here": non power-of-two chunking), -2 bad fp config */
 EXPORT int orc_range_prove(uint8_t *proofs_out, uint8_t *commits_out, const float *values, const uint8_t *blind, size_t D,
                            int range, size_t n_partition, int n_bits, int frac, const uint8_t seed[32]) {
@@ -193,7 +193,7 @@ EXPORT int orc_range_prove(uint8_t *proofs_out, uint8_t *commits_out, const floa
         sc_from_bytes_mod_order(&bl[i], blind + 32 * i);
     }
     size_t n_chunks = Dp < n_partition ? Dp : n_partition, chunk = Dp / n_chunks;                 /* :54-55 */
-    if (!(range == 8 || range == 16 || range == 32 || range == 64)) { free(vals); free(bl); return -1; }
+    if (!(range == 8 || range == 16 || range == 32 || range == 64)) { free(vals); free(bl); return -7; }
     if (chunk & (chunk - 1) || chunk * n_chunks != Dp) { free(vals); free(bl); return -99; }
     bp_gens_t bg; bp_gens_new(&bg, range, (int)chunk);           /* identical for every chunk (:126 rebuilds it per chunk) */
     size_t plen = rp_proof_len((size_t)range * chunk);
@@ -213,7 +213,7 @@ EXPORT int orc_range_prove(uint8_t *proofs_out, uint8_t *commits_out, const floa
     bp_gens_free(&bg); free(V); free(vals); free(bl);
     return rc;
 }
-/* verify_rangeproof (:149-191).  returns 1 true, 0 false, <0 error (-1 format, -2 bitsize, -3 gens length, -4 bad point) */
+/* verify_rangeproof (:149-191).  returns 1 true, 0 false, <0 error (-1 format, -7 bitsize, -3 gens length, -4 bad point) */
 EXPORT int orc_range_verify(const uint8_t *proofs, size_t proof_len, size_t n_proofs, const uint8_t *commits, size_t D,
                             int range, const uint8_t seed[32]) {
     if (D == 0 || n_proofs == 0 || range < 1 || range > 64) return -2;
@@ -242,7 +242,7 @@ EXPORT int orc_range_verify(const uint8_t *proofs, size_t proof_len, size_t n_pr
 }
 
 /* ============================ l2_range_proof_vec (l2_range_proof_vec/mod.rs) ==================== */
-/* create_rangeproof_l2 (:15-140): returns 0 ok, 2 ValueOutOfRange, 3 OverflowError, 4 NormOutOfRange, -1 InvalidBitsize.
+/* create_rangeproof_l2 (:15-140): returns 0 ok, 2 ValueOutOfRange, 3 OverflowError, 4 NormOutOfRange, -7 InvalidBitsize.
  * proof_out: rp_proof_len(range) bytes; commit_out: 32 bytes (NOT shifted) */
 EXPORT int orc_l2_prove(uint8_t *proof_out, uint8_t *commit_out, const float *values, const uint8_t *blind, size_t D,
                         int range, int n_bits, int frac, const uint8_t seed[32]) {
@@ -262,7 +262,7 @@ EXPORT int orc_l2_prove(uint8_t *proof_out, uint8_t *commit_out, const float *va
     if (fabsf(vf - val_float) > 1.1920929e-7f) return 3;                                         /* :53-58 */
     if (vf > l2_clip_max(range, n_bits, frac)) return 4;                                         /* :60-64 */
     uint64_t v = read_from_bytes(&val, n_bits);                                                  /* :69-73 */
-    if (!(range == 8 || range == 16 || range == 32 || range == 64)) return -1;
+    if (!(range == 8 || range == 16 || range == 32 || range == 64)) return -7;
     bp_gens_t bg; bp_gens_new(&bg, 64, 1);                                                       /* :162 */
     transcript t; transcript_init(&t, "L2RangeProof");
     uint8_t key[32]; rng_t rng; orc_derive_key(key, seed, DOM_L2_PROVE, 0); rng_init(&rng, key);

@@ -9,7 +9,7 @@ import ctypes as _C
 import os as _os
 import subprocess as _sp
 
-from ._ffi import Api, RoflError, EXPORTED_SYMBOLS, SEED0, bind  # noqa: F401
+from ._ffi import Api, RoflError, EXPORTED_SYMBOLS, bind  # noqa: F401
 
 _DIR = _os.path.dirname(_os.path.abspath(__file__))
 LIB_PATH = _os.path.join(_DIR, "librofl_b200.so")

@@ -63,6 +63,8 @@ _SIGS = {
     "rofl_probe_imad_wide": (C.c_double, [c_vp]),
     "rofl_prof_launches": (C.c_long, [C.c_int]),
     "rofl_ctx_stream": (c_vp, [c_vp]),
+    "rofl_debug_ts_absorb": (C.c_int, [c_vp, c_u8p, c_sz, C.c_int, C.c_int]),
+    "rofl_debug_verify_weights": (C.c_int, [c_vp, c_u8p, c_sz, c_sz, c_u8p, c_sz, C.c_int, c_u8p, c_u8p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 
@@ -101,7 +103,13 @@ def _f32(x):
     return np.ascontiguousarray(x, dtype=np.float32)
 
 
-SEED0 = bytes(32)
+import os as _os
+
+
+def _seed(seed):
+    """Prover nonces and verifier weights are derived from `seed`: None draws 32 fresh bytes from the OS (what every production call must
+    use, see the SECURITY note of include/rofl_b200.h); parity tests pass fixed seeds."""
+    return _u8(_os.urandom(32) if seed is None else seed, 32)
 
 
 class Api:
@@ -128,10 +136,10 @@ class Api:
         return out
 
     # ---- per-element proofs of the un-optimised encodings
-    def rand_prove(self, v, value_com, blind, n_bits, frac, seed=SEED0):
+    def rand_prove(self, v, value_com, blind, n_bits, frac, seed=None):
         v = _f32(v); D = v.size; b = _u8(blind, 32 * D); vc = None if value_com is None else _u8(value_com, 32 * D)
         proofs = np.zeros((D, 128), np.uint8); pairs = np.zeros((D, 64), np.uint8)
-        rc = self.lib.rofl_rand_prove(self.h, _ptr(v), _ptr(vc), _ptr(b), D, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proofs), _ptr(pairs))
+        rc = self.lib.rofl_rand_prove(self.h, _ptr(v), _ptr(vc), _ptr(b), D, n_bits, frac, _ptr(_seed(seed)), _ptr(proofs), _ptr(pairs))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, proofs, pairs
     def rand_verify(self, proofs, pairs):
@@ -139,10 +147,10 @@ class Api:
         rc = self.lib.rofl_rand_verify(self.h, _ptr(p), _ptr(c), p.shape[0])
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
-    def square_rand_prove(self, v, value_com, r1, r2, n_bits, frac, seed=SEED0):
+    def square_rand_prove(self, v, value_com, r1, r2, n_bits, frac, seed=None):
         v = _f32(v); D = v.size; vc = None if value_com is None else _u8(value_com, 32 * D)
         proofs = np.zeros((D, 192), np.uint8); commits = np.zeros((D, 96), np.uint8)
-        rc = self.lib.rofl_square_rand_prove(self.h, _ptr(v), _ptr(vc), _ptr(_u8(r1, 32 * D)), _ptr(_u8(r2, 32 * D)), D, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proofs), _ptr(commits))
+        rc = self.lib.rofl_square_rand_prove(self.h, _ptr(v), _ptr(vc), _ptr(_u8(r1, 32 * D)), _ptr(_u8(r2, 32 * D)), D, n_bits, frac, _ptr(_seed(seed)), _ptr(proofs), _ptr(commits))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, proofs, commits
     def square_rand_verify(self, proofs, commits):
@@ -151,11 +159,11 @@ class Api:
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
     # ---- compressed randomness proof: (rc, proof[128], pairs[D, 64]) / 1|0|<0
-    def crp_prove(self, v, value_com, blind, n_bits, frac, seed=SEED0):
+    def crp_prove(self, v, value_com, blind, n_bits, frac, seed=None):
         v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
         proof = np.zeros(128, np.uint8); pairs = np.zeros((max(D, 1), 64), np.uint8)
         vc = None if value_com is None else _u8(value_com, 32 * D)
-        rc = self.lib.rofl_crp_prove(self.h, _ptr(v), _ptr(vc), _ptr(b), D, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proof), _ptr(pairs))
+        rc = self.lib.rofl_crp_prove(self.h, _ptr(v), _ptr(vc), _ptr(b), D, n_bits, frac, _ptr(_seed(seed)), _ptr(proof), _ptr(pairs))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, proof, pairs[:D]
     def crp_verify(self, proof, pairs):
@@ -165,61 +173,71 @@ class Api:
         return rc
 
     # ---- the optimised encodings end to end (params.rs EncParamsRangeCompressed / EncParamsL2Compressed); dicts of wire fields
-    def enc_range_compressed_encrypt(self, v, blind, prove_range, n_partition, n_bits, frac, seed=SEED0):
+    def enc_range_compressed_encrypt(self, v, blind, prove_range, n_partition, n_bits, frac, seed=None):
         v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
         npf, plen = self.range_proof_shape(D, prove_range, n_partition)
         enc = np.zeros((D, 64), np.uint8); rp = np.zeros(128, np.uint8); proofs = np.zeros((npf, max(plen, 1)), np.uint8); a, c = c_sz(), c_sz()
-        rc = self.lib.rofl_enc_range_compressed_encrypt(self.h, _ptr(v), _ptr(b), D, prove_range, n_partition, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(enc), _ptr(rp), _ptr(proofs), C.byref(a), C.byref(c))
+        rc = self.lib.rofl_enc_range_compressed_encrypt(self.h, _ptr(v), _ptr(b), D, prove_range, n_partition, n_bits, frac, _ptr(_seed(seed)), _ptr(enc), _ptr(rp), _ptr(proofs), C.byref(a), C.byref(c))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, dict(enc_values=enc, rand_proof=rp, range_proof=proofs, range_bits=prove_range)
-    def enc_range_compressed_verify(self, msg, check_percentage=1.0, seed=SEED0):
+    def enc_range_compressed_verify(self, msg, check_percentage=1.0, seed=None):
         enc = _u8(msg["enc_values"]).reshape(-1, 64); p = _u8(msg["range_proof"]); p = p.reshape(p.shape[0], -1)
-        rc = self.lib.rofl_enc_range_compressed_verify(self.h, _ptr(enc), enc.shape[0], _ptr(_u8(msg["rand_proof"], 128)), _ptr(p), p.shape[1], p.shape[0], msg["range_bits"], check_percentage, _ptr(_u8(seed, 32)))
+        rc = self.lib.rofl_enc_range_compressed_verify(self.h, _ptr(enc), enc.shape[0], _ptr(_u8(msg["rand_proof"], 128)), _ptr(p), p.shape[1], p.shape[0], msg["range_bits"], check_percentage, _ptr(_seed(seed)))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
-    def enc_l2_compressed_encrypt(self, v, blind, prove_range, n_partition, l2_range, n_bits, frac, seed=SEED0):
+    def enc_l2_compressed_encrypt(self, v, blind, prove_range, n_partition, l2_range, n_bits, frac, seed=None):
         v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
         npf, plen = self.range_proof_shape(D, prove_range, n_partition)
         enc = np.zeros((D, 96), np.uint8); sp = np.zeros((D, 160), np.uint8); rp = np.zeros(128, np.uint8); proofs = np.zeros((npf, max(plen, 1)), np.uint8)
         sq = np.zeros(self.range_proof_len(max(l2_range, 1)), np.uint8); a, c, q = c_sz(), c_sz(), c_sz()
-        rc = self.lib.rofl_enc_l2_compressed_encrypt(self.h, _ptr(v), _ptr(b), D, prove_range, n_partition, l2_range, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(enc), _ptr(sp), _ptr(rp), _ptr(proofs),
+        rc = self.lib.rofl_enc_l2_compressed_encrypt(self.h, _ptr(v), _ptr(b), D, prove_range, n_partition, l2_range, n_bits, frac, _ptr(_seed(seed)), _ptr(enc), _ptr(sp), _ptr(rp), _ptr(proofs),
                                                      C.byref(a), C.byref(c), _ptr(sq), C.byref(q))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, dict(enc_values=enc, square_proof=sp, rand_proof=rp, range_proof=proofs, square_range_proof=sq, range_bits=prove_range, l2_range_bits=l2_range)
-    def enc_l2_compressed_verify(self, msg, seed=SEED0):
+    def enc_l2_compressed_verify(self, msg, seed=None):
         enc = _u8(msg["enc_values"]).reshape(-1, 96); sp = _u8(msg["square_proof"]).reshape(-1, 160); p = _u8(msg["range_proof"]); p = p.reshape(p.shape[0], -1); sq = _u8(msg["square_range_proof"])
-        rc = self.lib.rofl_enc_l2_compressed_verify(self.h, _ptr(enc), enc.shape[0], _ptr(sp), _ptr(p), p.shape[1], p.shape[0], _ptr(sq), sq.size, msg["range_bits"], msg["l2_range_bits"], _ptr(_u8(seed, 32)))
+        rc = self.lib.rofl_enc_l2_compressed_verify(self.h, _ptr(enc), enc.shape[0], _ptr(sp), _ptr(p), p.shape[1], p.shape[0], _ptr(sq), sq.size, msg["range_bits"], msg["l2_range_bits"], _ptr(_seed(seed)))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
 
     # ---- the un-optimised encodings end to end (params.rs EncParamsRange / EncParamsL2)
-    def enc_range_encrypt(self, v, blind, prove_range, n_partition, check_percentage, n_bits, frac, seed=SEED0):
+    def enc_range_encrypt(self, v, blind, prove_range, n_partition, check_percentage, n_bits, frac, seed=None):
         v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
         num = D if check_percentage >= 1.0 else int(np.floor(float(np.float32(np.float32(D) * np.float32(check_percentage))) + 0.5))      # llroundf
         npf, plen = self.range_proof_shape(max(num, 1), prove_range, n_partition)
         enc = np.zeros((D, 64), np.uint8); rp = np.zeros((D, 128), np.uint8); proofs = np.zeros((npf, max(plen, 1)), np.uint8); a, c = c_sz(), c_sz()
-        rc = self.lib.rofl_enc_range_encrypt(self.h, _ptr(v), _ptr(b), D, prove_range, n_partition, check_percentage, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(enc), _ptr(rp), _ptr(proofs), C.byref(a), C.byref(c))
+        rc = self.lib.rofl_enc_range_encrypt(self.h, _ptr(v), _ptr(b), D, prove_range, n_partition, check_percentage, n_bits, frac, _ptr(_seed(seed)), _ptr(enc), _ptr(rp), _ptr(proofs), C.byref(a), C.byref(c))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, dict(enc_values=enc, rand_proof=rp, range_proof=proofs[:c.value, :a.value] if rc == 0 else proofs, range_bits=prove_range)
-    def enc_range_verify(self, msg, check_percentage=1.0, seed=SEED0):
+    def enc_range_verify(self, msg, check_percentage=1.0, seed=None):
         enc = _u8(msg["enc_values"]).reshape(-1, 64); rp = _u8(msg["rand_proof"]).reshape(-1, 128); p = _u8(msg["range_proof"]); p = p.reshape(p.shape[0], -1)
-        rc = self.lib.rofl_enc_range_verify(self.h, _ptr(enc), enc.shape[0], _ptr(rp), _ptr(p), p.shape[1], p.shape[0], msg["range_bits"], check_percentage, _ptr(_u8(seed, 32)))
+        rc = self.lib.rofl_enc_range_verify(self.h, _ptr(enc), enc.shape[0], _ptr(rp), _ptr(p), p.shape[1], p.shape[0], msg["range_bits"], check_percentage, _ptr(_seed(seed)))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
-    def enc_l2_encrypt(self, v, blind, prove_range, n_partition, l2_range, n_bits, frac, seed=SEED0):
+    def enc_l2_encrypt(self, v, blind, prove_range, n_partition, l2_range, n_bits, frac, seed=None):
         v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
         npf, plen = self.range_proof_shape(D, prove_range, n_partition)
         enc = np.zeros((D, 96), np.uint8); sp = np.zeros((D, 192), np.uint8); proofs = np.zeros((npf, max(plen, 1)), np.uint8)
         sq = np.zeros(self.range_proof_len(max(l2_range, 1)), np.uint8); a, c, q = c_sz(), c_sz(), c_sz()
-        rc = self.lib.rofl_enc_l2_encrypt(self.h, _ptr(v), _ptr(b), D, prove_range, n_partition, l2_range, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(enc), _ptr(sp), _ptr(proofs),
+        rc = self.lib.rofl_enc_l2_encrypt(self.h, _ptr(v), _ptr(b), D, prove_range, n_partition, l2_range, n_bits, frac, _ptr(_seed(seed)), _ptr(enc), _ptr(sp), _ptr(proofs),
                                           C.byref(a), C.byref(c), _ptr(sq), C.byref(q))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, dict(enc_values=enc, square_proof=sp, range_proof=proofs, square_range_proof=sq, range_bits=prove_range, l2_range_bits=l2_range)
-    def enc_l2_verify(self, msg, seed=SEED0):
+    def enc_l2_verify(self, msg, seed=None):
         enc = _u8(msg["enc_values"]).reshape(-1, 96); sp = _u8(msg["square_proof"]).reshape(-1, 192); p = _u8(msg["range_proof"]); p = p.reshape(p.shape[0], -1); sq = _u8(msg["square_range_proof"])
-        rc = self.lib.rofl_enc_l2_verify(self.h, _ptr(enc), enc.shape[0], _ptr(sp), _ptr(p), p.shape[1], p.shape[0], _ptr(sq), sq.size, msg["range_bits"], msg["l2_range_bits"], _ptr(_u8(seed, 32)))
+        rc = self.lib.rofl_enc_l2_verify(self.h, _ptr(enc), enc.shape[0], _ptr(sp), _ptr(p), p.shape[1], p.shape[0], _ptr(sq), sq.size, msg["range_bits"], msg["l2_range_bits"], _ptr(_seed(seed)))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
+
+    # ---- test hooks
+    def debug_ts_absorb(self, V32, n, label_id=0):
+        v = _u8(V32).reshape(-1, 32)
+        return self.lib.rofl_debug_ts_absorb(self.h, _ptr(v), v.shape[0], n, label_id)
+    def debug_verify_weights(self, proofs, commits, rng, seed):
+        p = _u8(proofs); p = p.reshape(p.shape[0], -1); c = _u8(commits).reshape(-1, 32); w = np.zeros((2, p.shape[0], 32), np.uint8)
+        rc = self.lib.rofl_debug_verify_weights(self.h, _ptr(p), p.shape[1], p.shape[0], _ptr(c), c.shape[0], rng, _ptr(_seed(seed)), _ptr(w))
+        if rc <= ROFL_ERR_CUDA: raise self._err(rc)
+        return rc, w
 
     def set_option(self, name, value):
         rc = self.lib.rofl_set_option(self.h, name.encode(), int(value))
@@ -243,7 +261,7 @@ class Api:
     def clip_f32_to_range_vec(self, v, rng, n_bits, frac):
         v = _f32(v); o = np.empty_like(v); self.lib.rofl_clip_f32_to_range_vec(_ptr(v), v.size, rng, n_bits, frac, _ptr(o)); return o
     def rnd_scalar_vec(self, seed, D):
-        o = np.zeros((D, 32), np.uint8); self.lib.rofl_rnd_scalar_vec(_ptr(_u8(seed, 32)), D, _ptr(o)); return o
+        o = np.zeros((D, 32), np.uint8); self.lib.rofl_rnd_scalar_vec(_ptr(_seed(seed)), D, _ptr(o)); return o
     def f32_to_scalar_vec(self, v, n_bits, frac):
         v = _f32(v); o = np.zeros((v.size, 32), np.uint8)
         rc = self.lib.rofl_f32_to_scalar_vec(self.h, _ptr(v), v.size, n_bits, frac, _ptr(o))
@@ -264,59 +282,59 @@ class Api:
         return (L, R) if want_R else L
 
     # ---- range proofs; return (rc, proofs[n_proofs, proof_len], commits[D, 32])
-    def range_prove(self, v, blind, rng, n_partition, n_bits, frac, seed=SEED0):
+    def range_prove(self, v, blind, rng, n_partition, n_bits, frac, seed=None):
         v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
         npf, plen = self.range_proof_shape(D, rng, n_partition)
         proofs = np.zeros((npf, max(plen, 1)), np.uint8); commits = np.zeros((D, 32), np.uint8)
         a, c = c_sz(), c_sz()
-        rc = self.lib.rofl_range_prove(self.h, _ptr(v), _ptr(b), D, rng, n_partition, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proofs), C.byref(a), C.byref(c), _ptr(commits))
+        rc = self.lib.rofl_range_prove(self.h, _ptr(v), _ptr(b), D, rng, n_partition, n_bits, frac, _ptr(_seed(seed)), _ptr(proofs), C.byref(a), C.byref(c), _ptr(commits))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, proofs, commits
     def range_prove_dev(self, v_ptr, blind_ptr, D, rng, n_partition, n_bits, frac, seed, commits_ptr):
         npf, plen = self.range_proof_shape(D, rng, n_partition)
         proofs = np.zeros((npf, max(plen, 1)), np.uint8); a, c = c_sz(), c_sz()
-        rc = self.lib.rofl_range_prove_dev(self.h, v_ptr, blind_ptr, D, rng, n_partition, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proofs), C.byref(a), C.byref(c), commits_ptr)
+        rc = self.lib.rofl_range_prove_dev(self.h, v_ptr, blind_ptr, D, rng, n_partition, n_bits, frac, _ptr(_seed(seed)), _ptr(proofs), C.byref(a), C.byref(c), commits_ptr)
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, proofs
-    def range_verify(self, proofs, commits, rng, seed=SEED0):
+    def range_verify(self, proofs, commits, rng, seed=None):
         p = _u8(proofs); p = p.reshape(p.shape[0], -1); c = _u8(commits).reshape(-1, 32)
-        rc = self.lib.rofl_range_verify(self.h, _ptr(p), p.shape[1], p.shape[0], _ptr(c), c.shape[0], rng, _ptr(_u8(seed, 32)))
+        rc = self.lib.rofl_range_verify(self.h, _ptr(p), p.shape[1], p.shape[0], _ptr(c), c.shape[0], rng, _ptr(_seed(seed)))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
-    def range_prove_shard(self, v, blind, chunk_len, chunk_begin, n_chunks, rng, n_bits, frac, seed=SEED0):
+    def range_prove_shard(self, v, blind, chunk_len, chunk_begin, n_chunks, rng, n_bits, frac, seed=None):
         """Chunks [chunk_begin, chunk_begin + n_chunks) of a larger update; v / blind hold the real elements of that slice."""
         v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
         plen = self.range_proof_len(rng * chunk_len)
         proofs = np.zeros((n_chunks, plen), np.uint8); commits = np.zeros((D, 32), np.uint8); a = c_sz()
-        rc = self.lib.rofl_range_prove_shard(self.h, _ptr(v), _ptr(b), D, chunk_len, chunk_begin, n_chunks, rng, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proofs), C.byref(a), _ptr(commits))
+        rc = self.lib.rofl_range_prove_shard(self.h, _ptr(v), _ptr(b), D, chunk_len, chunk_begin, n_chunks, rng, n_bits, frac, _ptr(_seed(seed)), _ptr(proofs), C.byref(a), _ptr(commits))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, proofs, commits
-    def range_verify_shard(self, proofs, commits, chunk_len, chunk_begin, rng, seed=SEED0):
+    def range_verify_shard(self, proofs, commits, chunk_len, chunk_begin, rng, seed=None):
         p = _u8(proofs); p = p.reshape(p.shape[0], -1); c = _u8(commits).reshape(-1, 32)
-        rc = self.lib.rofl_range_verify_shard(self.h, _ptr(p), p.shape[1], p.shape[0], _ptr(c), c.shape[0], chunk_len, chunk_begin, rng, _ptr(_u8(seed, 32)))
+        rc = self.lib.rofl_range_verify_shard(self.h, _ptr(p), p.shape[1], p.shape[0], _ptr(c), c.shape[0], chunk_len, chunk_begin, rng, _ptr(_seed(seed)))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
-    def range_verify_dev(self, proofs, commits_ptr, D, rng, seed=SEED0):
+    def range_verify_dev(self, proofs, commits_ptr, D, rng, seed=None):
         p = _u8(proofs); p = p.reshape(p.shape[0], -1)
-        rc = self.lib.rofl_range_verify_dev(self.h, _ptr(p), p.shape[1], p.shape[0], commits_ptr, D, rng, _ptr(_u8(seed, 32)))
+        rc = self.lib.rofl_range_verify_dev(self.h, _ptr(p), p.shape[1], p.shape[0], commits_ptr, D, rng, _ptr(_seed(seed)))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
-    def l2_prove(self, v, blind, rng, n_bits, frac, seed=SEED0):
+    def l2_prove(self, v, blind, rng, n_bits, frac, seed=None):
         v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
         proof = np.zeros(self.range_proof_len(max(rng, 1)), np.uint8); commit = np.zeros(32, np.uint8); a = c_sz()
-        rc = self.lib.rofl_l2_prove(self.h, _ptr(v), _ptr(b), D, rng, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proof), C.byref(a), _ptr(commit))
+        rc = self.lib.rofl_l2_prove(self.h, _ptr(v), _ptr(b), D, rng, n_bits, frac, _ptr(_seed(seed)), _ptr(proof), C.byref(a), _ptr(commit))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, proof, commit
-    def l2_verify(self, proof, commit, rng, seed=SEED0):
+    def l2_verify(self, proof, commit, rng, seed=None):
         p = _u8(proof)
-        rc = self.lib.rofl_l2_verify(self.h, _ptr(p), p.size, _ptr(_u8(commit, 32)), rng, _ptr(_u8(seed, 32)))
+        rc = self.lib.rofl_l2_verify(self.h, _ptr(p), p.size, _ptr(_u8(commit, 32)), rng, _ptr(_seed(seed)))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
     # ---- square proofs
-    def square_prove(self, v, value_com, r1, r2, n_bits, frac, seed=SEED0):
+    def square_prove(self, v, value_com, r1, r2, n_bits, frac, seed=None):
         v = _f32(v); D = v.size
         proofs = np.zeros((D, 160), np.uint8); commits = np.zeros((D, 64), np.uint8)
-        rc = self.lib.rofl_square_prove(self.h, _ptr(v), _ptr(_u8(value_com, 32 * D)), _ptr(_u8(r1, 32 * D)), _ptr(_u8(r2, 32 * D)), D, n_bits, frac, _ptr(_u8(seed, 32)), _ptr(proofs), _ptr(commits))
+        rc = self.lib.rofl_square_prove(self.h, _ptr(v), _ptr(_u8(value_com, 32 * D)), _ptr(_u8(r1, 32 * D)), _ptr(_u8(r2, 32 * D)), D, n_bits, frac, _ptr(_seed(seed)), _ptr(proofs), _ptr(commits))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, proofs, commits
     def square_verify(self, proofs, commits):

@@ -269,12 +269,21 @@ extern "C" int rofl_enc_l2_compressed_verify(rofl_ctx *c, const uint8_t *enc_val
     API_TRY
     if (!D || !n_proofs) return ROFL_ERR_ARGS;
     cudaStream_t s = c->e.stream;
-    staged_in de(enc_values96, 96 * D, s), dsp(square_proofs160, 160 * D, s); dev_buf dL(32 * D, s), dSc(64 * D, s), dCsq(32 * D, s);
+    staged_in de(enc_values96, 96 * D, s), dsp(square_proofs160, 160 * D, s); dev_buf dL(32 * D, s), dSc(64 * D, s), dCsq(32 * D, s), dbad(sizeof(int), s);
+    // decode_l2enc_vec (params.rs:560-571): every record must deserialise -- c.L, c_sq and also c.R, which this arm never uses afterwards
+    // (SquareRandProofCommitments::from_bytes -> ElGamalPair::from_bytes; the reference unwrap()s = panics, here the message is refused with ROFL_ERR_POINT)
+    rt_memset(dbad.p, 0, sizeof(int), s);
+    LAUNCH(k_validate_points, dim3((unsigned)((3 * D + 127) / 128)), dim3(128), s, de.b.as<uint8_t>(), (size_t)32, (size_t)0, 3 * D, dbad.as<int>());
     LAUNCH(k_split96, dim3((unsigned)((D + 255) / 256)), dim3(256), s, dL.as<uint8_t>(), dSc.as<uint8_t>(), dCsq.as<uint8_t>(), de.b.as<uint8_t>(), D);
-    if (engine_square_verify(c->e, dsp.b.as<uint8_t>(), dSc.as<uint8_t>(), D) != 1) return 0;
-    if (engine_range_verify(c->e, range_proofs, plen, n_proofs, dL.as<uint8_t>(), D, prove_range, seed) != 1) return 0;
+    int bad = 0; rt_d2h(&bad, dbad.p, sizeof(int), s);
+    const int sq = engine_square_verify(c->e, dsp.b.as<uint8_t>(), dSc.as<uint8_t>(), D);               // (synchronises the stream: `bad` is valid afterwards)
+    if (bad) return ROFL_ERR_POINT;
+    if (sq != 1) return 0;
+    const int rr = engine_range_verify(c->e, range_proofs, plen, n_proofs, dL.as<uint8_t>(), D, prove_range, seed);
+    if (rr == ROFL_ERR_POINT) return ROFL_ERR_POINT;
+    if (rr != 1) return 0;
     uint8_t sum[32];
-    if (engine_points_sum(c->e, dCsq.as<uint8_t>(), D, sum) != 0) return 0;
+    if (engine_points_sum(c->e, dCsq.as<uint8_t>(), D, sum) != 0) return ROFL_ERR_POINT;
     return engine_l2_verify(c->e, square_range_proof, sq_plen, sum, l2_range, seed) == 1 ? 1 : 0;
     API_CATCH
 }
@@ -424,5 +433,30 @@ extern "C" int rofl_dlog(rofl_ctx *c, const uint8_t *pts, size_t D, uint64_t ts,
     int rc = engine_dlog(c->e, dp.b.as<uint8_t>(), D, ts, bb, n_bits, frac, o.as<uint8_t>(), f.as<float>());
     if (osc) rt_d2h(osc, o.p, 32 * D, s); if (of) rt_d2h(of, f.p, 4 * D, s); rt_sync(s);
     return rc;
+    API_CATCH
+}
+
+// ---- test hooks (tests/test_emul_vs_oracle.py, tests/test_gpu_parity.py) ------------------------------------------------------------------------
+// the warp-cooperative V absorb (ts_kernels.cuh, k_ts_absorbV) against the sequential transcript code for the same m commitments: 0 equal, 1 different
+extern "C" int rofl_debug_ts_absorb(rofl_ctx *c, const uint8_t *V32, size_t m, int n, int label_id) {
+    API_TRY
+    std::lock_guard<std::mutex> lk(c->e.mu); cudaStream_t s = c->e.stream;
+    staged_in dv(V32, 32 * m, s); dev_buf d_ts(sizeof(transcript), s);
+    ts_absorb_args aa = {}; aa.ts = d_ts.as<transcript>(); aa.V32 = dv.b.as<uint8_t>(); aa.m = (uint32_t)m; aa.n = (uint32_t)n; aa.label_id = label_id;
+    LAUNCH_COOP(k_ts_absorbV, dim3(1), dim3(TS_THREADS), s, aa);
+    transcript got; rt_d2h(&got, d_ts.p, sizeof(transcript), s); rt_sync(s);
+    transcript t; transcript_init(t, label_id ? "L2RangeProof" : "RangeProof");
+    transcript_append(t, "dom-sep", (const uint8_t *)"rangeproof v1", 13);
+    transcript_append_u64(t, "n", (uint64_t)n); transcript_append_u64(t, "m", (uint64_t)m);
+    for (size_t j = 0; j < m; j++) transcript_append(t, "V", V32 + 32 * j, 32);
+    return (memcmp(t.st, got.st, sizeof(t.st)) || t.pos != got.pos || t.pos_begin != got.pos_begin) ? 1 : 0;
+    API_CATCH
+}
+// the batching scalars (c_i | rho_i, 2 x n_proofs x 32 bytes) the verifier derives for this call; return value as rofl_range_verify
+extern "C" int rofl_debug_verify_weights(rofl_ctx *c, const uint8_t *proofs, size_t plen, size_t np, const uint8_t *commits, size_t D, int range, const uint8_t seed[32], uint8_t *out_weights) {
+    API_TRY
+    if (!D) return ROFL_ERR_ARGS;
+    staged_in dc(commits, 32 * D, c->e.stream);
+    return engine_range_verify(c->e, proofs, plen, np, dc.b.as<uint8_t>(), D, range, seed, nullptr, out_weights);
     API_CATCH
 }

@@ -20,6 +20,7 @@
 #include <chrono>
 #include <cstdio>
 
+enum { ROFL_ERR_BITSIZE_ = -7 };          // include/rofl_b200.h ROFL_ERR_BITSIZE
 enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE = 4, DOM_L2_VERIFY = 5, DOM_CRP = 6, DOM_RND_VEC = 7, DOM_RANDPROOF = 8, DOM_SQUARE_RAND = 9 };
 enum { PROF_FOLD = 0, PROF_MSM = 1, PROF_COMMIT = 2, PROF_SQUARE = 3, PROF_RTMSM = 4, PROF_TAIL = 5, PROF_FRZ = 6, PROF_SLOTS = 8 };
 
@@ -37,6 +38,8 @@ struct rofl_engine {
     int host_threads = 8;
     int groups = 3;                       // chunk groups proved / verified concurrently on separate streams (hides per-round latency)
     std::vector<cudaStream_t> gstreams;   // gstreams[0] == stream
+    std::vector<cudaStream_t> sstreams;   // side stream of every group stream (work that runs beside the group's main sequence)
+    cudaStream_t side_for(cudaStream_t gs) const { for (size_t i = 0; i < gstreams.size() && i < sstreams.size(); i++) if (gstreams[i] == gs) return sstreams[i]; return gs; }
     int use_rt = 1;                       // 0: never build generator tables (generic Pippenger / fold path only)
     int rt_unfold = 4;                    // IPP rounds computed over the original generators before the catch-up fold
     int tail_np = 32;                     // IPP rounds with half-size <= tail_np run in the fused on-device tail kernel (0 = off)
@@ -249,29 +252,17 @@ static inline void fin_windows(finalize_args &f, const p3_st *win, const msm_pla
 // h_proofs (host).  d_vals: C*m shifted values, d_blind: C*m blindings (reduced), d_V32: C*m compressed commitments.
 // label = transcript label ("RangeProof" / "L2RangeProof"); keys = C ChaCha20 keys (host).
 // =============================================================================================================================
-static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int n, int m, int C, const gens_entry &g, const rt_tables *rt, const uint64_t *d_vals,
+static void prove_chunks(rofl_engine &e, cudaStream_t s, cudaStream_t side, int label_id, int n, int m, int C, const gens_entry &g, const rt_tables *rt, const uint64_t *d_vals,
                          const sc_st *d_blind, const uint8_t *d_V32, const std::vector<uint8_t> &keys, uint8_t *h_proofs) {
     const size_t N = (size_t)n * m, NT = N * C;
     const int lgN = ilog2_sz(N);
     const size_t plen = 32 * (9 + 2 * (size_t)lgN);
     phase_trace tr(s);
-#ifndef ROFL_EMUL
-    struct host_prof_line {          // ROFL_HOSTPROF=1: one line per call with the host time of this thread by category
-        std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(); rt_host_prof p0 = rt_hostprof(); int C; struct rusage r0;
-        host_prof_line() { getrusage(RUSAGE_THREAD, &r0); }
-        ~host_prof_line() {
-            if (!rt_hostprof_on()) return;
-            struct rusage r1; getrusage(RUSAGE_THREAD, &r1);
-            auto tv = [](const timeval &a, const timeval &b) { return (a.tv_sec - b.tv_sec) * 1e3 + (a.tv_usec - b.tv_usec) / 1e3; };
-            fprintf(stderr, "[rofl host] rusage: user=%.2f ms sys=%.2f ms minor_faults=%ld major_faults=%ld vol_cs=%ld invol_cs=%ld\n", tv(r1.ru_utime, r0.ru_utime), tv(r1.ru_stime, r0.ru_stime),
-                    r1.ru_minflt - r0.ru_minflt, r1.ru_majflt - r0.ru_majflt, r1.ru_nvcsw - r0.ru_nvcsw, r1.ru_nivcsw - r0.ru_nivcsw);
-            const rt_host_prof &p = rt_hostprof(); const double tot = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            const double sy = p.sync - p0.sync, la = p.launch - p0.launch, co = p.copy - p0.copy, al = p.alloc - p0.alloc, pa = p.par - p0.par, se = p.ser - p0.ser;
-            fprintf(stderr, "[rofl host] prove_chunks C=%d total=%.2f sync=%.2f launch=%.2f copy=%.2f alloc=%.2f parallel_for=%.2f serial_for=%.2f other=%.2f ms\n", C, tot, sy, la, co, al, pa, se, tot - sy - la - co - al - pa - se);
-        }
-    } hpl; hpl.C = C;
-#endif
-    // ---- device scratch
+    // ---- device scratch.  The Merlin transcripts live on the device (ts_kernels.cuh): nothing below waits for the host until the proofs are copied out.
+    dev_buf d_ts(sizeof(transcript) * (size_t)C, s), d_proofs(plen * (size_t)C, s);
+    rt_stream_after(side, s);
+    { ts_absorb_args aa = {}; aa.ts = d_ts.as<transcript>(); aa.V32 = d_V32; aa.m = (uint32_t)m; aa.n = (uint32_t)n; aa.label_id = label_id;      // V_1..V_m: independent of A and S, so it
+      LAUNCH_COOP(k_ts_absorbV, dim3(C), dim3(TS_THREADS), side, aa); }                                                                         // runs beside them on the side stream
     dev_buf d_keys(32 * (size_t)C, s), d_sLR(sizeof(sc_st) * 2 * NT, s), d_sums(sizeof(sc_st) * 5 * C, s);
     { std::vector<uint32_t> kw(8 * (size_t)C); for (int c = 0; c < C; c++) key_words(&kw[8 * c], &keys[32 * c]); rt_h2d(d_keys.p, kw.data(), 32 * (size_t)C, s); }
     LAUNCH(k_nonces, dim3((unsigned)((NT + 255) / 256)), dim3(256), s, d_sLR.as<sc_st>(), d_keys.as<uint32_t>(), n, m, NT);
@@ -304,28 +295,12 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         f.out32 = d_AS.as<uint8_t>() + 32 * (size_t)C; f.count = C;
         run_finalize(s, f);
     }
-    std::vector<uint8_t> hV(32 * (size_t)C * m), hAS(64 * (size_t)C);
-    rt_d2h(hV.data(), d_V32, hV.size(), s); rt_d2h(hAS.data(), d_AS.p, hAS.size(), s);
-    rt_sync(s);
     // ---- transcripts: V..., A, S -> y, z
-    std::vector<transcript> ts(C);
-    std::vector<sc> y(C), z(C), yinv(C);
-    parallel_for(C, e.host_threads, [&](size_t c) {
-        transcript &t = ts[c]; transcript_init(t, label);
-        transcript_append(t, "dom-sep", (const uint8_t *)"rangeproof v1", 13);
-        transcript_append_u64(t, "n", (uint64_t)n); transcript_append_u64(t, "m", (uint64_t)m);
-        for (int j = 0; j < m; j++) transcript_append(t, "V", &hV[32 * (c * m + j)], 32);
-        uint8_t *o = h_proofs + plen * c;
-        memcpy(o, &hAS[32 * c], 32); memcpy(o + 32, &hAS[32 * (C + c)], 32);
-        transcript_append(t, "A", o, 32); transcript_append(t, "S", o + 32, 32);
-        ts_challenge_scalar(t, "y", y[c]); ts_challenge_scalar(t, "z", z[c]);
-    });
-    yinv = y; sc_batch_invert(yinv);
-    std::vector<sc_st> h_ypow2(32 * (size_t)C), h_zpow2(32 * (size_t)C), h_yinvpow2(32 * (size_t)C), h_z(C);
-    for (int c = 0; c < C; c++) { sc_pow2_table(&h_ypow2[32 * c], y[c]); sc_pow2_table(&h_zpow2[32 * c], z[c]); sc_pow2_table(&h_yinvpow2[32 * c], yinv[c]); sc_to_st(h_z[c], z[c]); }
+    rt_stream_after(s, side);
     dev_buf d_ypow2(sizeof(sc_st) * 32 * C, s), d_zpow2(sizeof(sc_st) * 32 * C, s), d_yinvpow2(sizeof(sc_st) * 32 * C, s), d_z(sizeof(sc_st) * C, s);
-    rt_h2d(d_ypow2.p, h_ypow2.data(), sizeof(sc_st) * 32 * C, s); rt_h2d(d_zpow2.p, h_zpow2.data(), sizeof(sc_st) * 32 * C, s);
-    rt_h2d(d_yinvpow2.p, h_yinvpow2.data(), sizeof(sc_st) * 32 * C, s); rt_h2d(d_z.p, h_z.data(), sizeof(sc_st) * C, s);
+    { ts_yz_args ya = {}; ya.ts = d_ts.as<transcript>(); ya.AS = d_AS.as<uint8_t>(); ya.proofs = d_proofs.as<uint8_t>(); ya.plen = (uint32_t)plen; ya.C = (uint32_t)C;
+      ya.ypow2 = d_ypow2.as<sc_st>(); ya.zpow2 = d_zpow2.as<sc_st>(); ya.yinvpow2 = d_yinvpow2.as<sc_st>(); ya.z = d_z.as<sc_st>();
+      LAUNCH_COOP(k_ts_yz, dim3(C), dim3(TS_THREADS), s, ya); }
     // ---- polynomials
     const int nbP = (int)std::min<size_t>(256, (N + 255) / 256);
     dev_buf d_a(sizeof(sc_st) * NT, s), d_b(sizeof(sc_st) * NT, s), d_part(sizeof(sc_st) * 3 * (size_t)C * nbP, s), d_tsum(sizeof(sc_st) * 3 * C, s);
@@ -340,48 +315,18 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     LAUNCH_COOP(k_poly, dim3(nbP, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_part.as<sc_st>(), d_vals, ytab, ztab, d_zpow2.as<sc_st>(), n, m);
     LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_tsum.as<sc_st>(), d_part.as<sc_st>(), nbP, 3);
     LAUNCH_COOP(k_party_sums, dim3(C), dim3(256), s, d_sums.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, d_z.as<sc_st>(), n, m, 1);
-    std::vector<sc_st> h_tsum(3 * (size_t)C), h_sums(5 * (size_t)C);
-    rt_d2h(h_tsum.data(), d_tsum.p, sizeof(sc_st) * 3 * C, s); rt_d2h(h_sums.data(), d_sums.p, sizeof(sc_st) * 5 * C, s);
-    rt_sync(s);
-    std::vector<sc> t0(C), t1(C), t2(C);
-    std::vector<sc_st> h_t12(2 * (size_t)C);
-    for (int c = 0; c < C; c++) {
-        sc tt; st_to_sc(t0[c], h_tsum[c]); st_to_sc(tt, h_tsum[C + c]); st_to_sc(t2[c], h_tsum[2 * C + c]);
-        sc_sub(tt, tt, t0[c]); sc_sub(t1[c], tt, t2[c]);
-        sc_to_st(h_t12[c], t1[c]); sc_to_st(h_t12[C + c], t2[c]);
-    }
     dev_buf d_t12(sizeof(sc_st) * 2 * C, s), d_T12(64 * (size_t)C, s);
-    rt_h2d(d_t12.p, h_t12.data(), sizeof(sc_st) * 2 * C, s);
+    LAUNCH(k_ts_t12, dim3((unsigned)((C + 63) / 64)), dim3(64), s, d_t12.as<sc_st>(), d_tsum.as<sc_st>(), (uint32_t)C);
     {
         finalize_args f = {}; f.sBa = d_t12.as<sc_st>(); f.sHa = d_sums.as<sc_st>() + 2 * C; f.tabB = e.tabB; f.tabH = e.tabH;
         f.out32 = d_T12.as<uint8_t>(); f.count = 2 * C;
         run_finalize(s, f);
     }
-    std::vector<uint8_t> hT(64 * (size_t)C);
-    rt_d2h(hT.data(), d_T12.p, hT.size(), s);
-    rt_sync(s);
     // ---- x, shares, w
-    std::vector<sc> x(C), w(C);
-    std::vector<sc_st> h_x(C), h_w2(2 * (size_t)C);
-    serial_for(C, [&](size_t c) {
-        transcript &t = ts[c]; uint8_t *o = h_proofs + plen * c;
-        memcpy(o + 64, &hT[32 * c], 32); memcpy(o + 96, &hT[32 * (C + c)], 32);
-        transcript_append(t, "T_1", o + 64, 32); transcript_append(t, "T_2", o + 96, 32);
-        ts_challenge_scalar(t, "x", x[c]);
-        sc xx, tx, txb, eb, tmp, sa, ss, st1, st2, szg;
-        sc_mul(xx, x[c], x[c]);
-        st_to_sc(sa, h_sums[c]); st_to_sc(ss, h_sums[C + c]); st_to_sc(st1, h_sums[2 * C + c]); st_to_sc(st2, h_sums[3 * C + c]); st_to_sc(szg, h_sums[4 * C + c]);
-        sc_mul(tmp, t1[c], x[c]); sc_add(tx, t0[c], tmp); sc_mul(tmp, t2[c], xx); sc_add(tx, tx, tmp);
-        sc_mul(tmp, st1, x[c]); sc_add(txb, szg, tmp); sc_mul(tmp, st2, xx); sc_add(txb, txb, tmp);
-        sc_mul(tmp, ss, x[c]); sc_add(eb, sa, tmp);
-        sc_tobytes(o + 128, tx); sc_tobytes(o + 160, txb); sc_tobytes(o + 192, eb);
-        transcript_append(t, "t_x", o + 128, 32); transcript_append(t, "t_x_blinding", o + 160, 32); transcript_append(t, "e_blinding", o + 192, 32);
-        ts_challenge_scalar(t, "w", w[c]);
-        transcript_append(t, "dom-sep", (const uint8_t *)"ipp v1", 6); transcript_append_u64(t, "n", (uint64_t)N);
-        sc_to_st(h_x[c], x[c]); sc_to_st(h_w2[c], w[c]); sc_to_st(h_w2[C + c], w[c]);
-    });
     dev_buf d_x(sizeof(sc_st) * C, s), d_w2(sizeof(sc_st) * 2 * C, s), d_yinv(sizeof(sc_st) * NT, s);
-    rt_h2d(d_x.p, h_x.data(), sizeof(sc_st) * C, s); rt_h2d(d_w2.p, h_w2.data(), sizeof(sc_st) * 2 * C, s);
+    { ts_x_args xa = {}; xa.ts = d_ts.as<transcript>(); xa.T12 = d_T12.as<uint8_t>(); xa.proofs = d_proofs.as<uint8_t>(); xa.plen = (uint32_t)plen; xa.C = (uint32_t)C;
+      xa.tsum = d_tsum.as<sc_st>(); xa.sums = d_sums.as<sc_st>(); xa.x = d_x.as<sc_st>(); xa.w2 = d_w2.as<sc_st>(); xa.N = (uint64_t)N;
+      LAUNCH(k_ts_x, dim3((unsigned)((C + TS_THREADS - 1) / TS_THREADS)), dim3(TS_THREADS), s, xa); }
     LAUNCH(k_lr, dim3((unsigned)((NT + 255) / 256)), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_yinv.as<sc_st>(), d_x.as<sc_st>(), yitab, N, NT);
     tr.mark("pre_ipp");
     // ---- inner product argument
@@ -389,12 +334,8 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     const size_t half = (N / 2 <= (size_t)std::min(e.tail_np, TAIL_MAX_F / 2)) ? N : (N / 2 ? N / 2 : 1);
     dev_buf d_Gf(sizeof(p3_st) * half * C, s), d_Hf(sizeof(p3_st) * half * C, s);
     sc_st *msmL = d_sLR.as<sc_st>(), *msmR = d_sLR.as<sc_st>() + NT;         // s_L / s_R are dead after k_lr: reuse as MSM scalar buffers
-    dev_buf d_cLR(sizeof(sc_st) * 2 * C, s), d_LR(64 * (size_t)C, s), d_u2(sizeof(sc_st) * C, s), d_uinv2(sizeof(sc_st) * C, s), d_nafs(512 * (size_t)C, s);
-    std::vector<sc> uprod(C), uinvprod(C);
-    for (int c = 0; c < C; c++) { sc_from_u64(uprod[c], 1); sc_from_u64(uinvprod[c], 1); }
-    pinned_buf pinLR(e, 64 * (size_t)C); uint8_t *hLR = pinLR.as<uint8_t>();
-    std::vector<sc> u(C), uinv(C);
-    std::vector<sc_st> h_u2(C), h_uinv2(C); std::vector<int8_t> h_nafs(512 * (size_t)C);
+    dev_buf d_cLR(sizeof(sc_st) * 2 * C, s), d_LR(64 * (size_t)C, s), d_u2(sizeof(sc_st) * C, s), d_uinv2(sizeof(sc_st) * C, s), d_nafs(512 * (size_t)C, s), d_up(sizeof(sc_st) * 2 * (size_t)C, s);
+    { std::vector<sc_st> h_up(2 * (size_t)C); sc one; sc_from_u64(one, 1); for (auto &v : h_up) sc_to_st(v, one); rt_h2d(d_up.p, h_up.data(), sizeof(sc_st) * h_up.size(), s); }
     // RT path: the first r_unf rounds take L/R as table MSMs over the ORIGINAL generators (no generator folding), then one
     // catch-up fold builds G"/H" of length N >> r_unf directly from the tables
     // rounds with half-size <= tail_np run in the fused on-device tail kernel; `pre` rounds come before it
@@ -403,10 +344,14 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     const int r_unf = rt ? std::min({e.rt_unfold, lgN, pre}) : 0;
     const int nbU = rt ? rt_blocks(N, 2 * C) : 1;
     const uint32_t cstride = 1u << (r_unf > 0 ? r_unf : 0);
-    std::vector<sc> cG((size_t)C * cstride), cH((size_t)C * cstride);
-    std::vector<sc_st> h_cGH(2 * (size_t)C * cstride);
-    for (int c = 0; c < C; c++) { sc_from_u64(cG[(size_t)c * cstride], 1); sc_from_u64(cH[(size_t)c * cstride], 1); }
+    // coefficient tables of the unfolded rounds [G | H][C][cstride], kept on the device: k_ts_round doubles them after every challenge
+    auto coef_init = [&](dev_buf &d, uint32_t stride) {
+        std::vector<sc_st> h(2 * (size_t)C * stride); memset(h.data(), 0, sizeof(sc_st) * h.size());
+        for (size_t c = 0; c < 2 * (size_t)C; c++) h[c * stride].w[0] = 1;
+        rt_h2d(d.p, h.data(), sizeof(sc_st) * h.size(), s);
+    };
     dev_buf d_cGH(sizeof(sc_st) * 2 * (size_t)C * cstride, s), d_partU(sizeof(p3_st) * 2 * (size_t)C * nbU, s), d_digs(sizeof(int16_t) * 2 * (size_t)C * cstride * RT_MAXW, s);
+    coef_init(d_cGH, cstride);
     const int nbQ = (int)std::min<size_t>(256, (N / 2 + 255) / 256);
     dev_buf d_partQ(sizeof(sc_st) * 2 * (size_t)C * nbQ, s);
     // frozen level (kernels.cuh K6c): rounds ra .. pre-1 run over the generators as they are at round ra (FA of G" and of H" per chunk)
@@ -421,11 +366,10 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         if (e.free_hint.load() == 0) e.free_hint = rt_free_mem();
         if (pre - r >= 2 && fa >= 4 && need < 0.25 * (double)e.free_hint.load()) { ra = r; FA = fa; cAstride = (uint32_t)(FA / ((N / 2) >> (pre - 1))); }
     }
-    std::vector<sc> cAG((size_t)C * cAstride), cAH((size_t)C * cAstride);
-    std::vector<sc_st> h_cA(2 * (size_t)C * cAstride);
-    for (int c = 0; c < C; c++) { sc_from_u64(cAG[(size_t)c * cAstride], 1); sc_from_u64(cAH[(size_t)c * cAstride], 1); }
     dev_buf d_cA(sizeof(sc_st) * 2 * (size_t)C * cAstride, s), d_frzV(sizeof(p3_st) * 2 * (size_t)C * 8, s);
+    coef_init(d_cA, cAstride);
     dev_buf d_frzT(ra >= 0 ? sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q * FRZ_E : 16, s);
+    dev_buf d_dg(ra >= 0 ? 2 * (size_t)C * cAstride * 64 : 16, s);             // radix-16 digits of the frozen level's coefficients when it is left
     int round = 0;
     bool tail_done = false;
     for (size_t np = N / 2; np >= 1; np /= 2, round++) {
@@ -441,13 +385,7 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         const bool frozen = ra >= 0 && round >= ra;
         if (round == pre) tr.mark("middle");
         if (round == pre && frozen) {       // leave the frozen level: the 2*np generators the tail starts from, straight from the tables
-            const uint32_t nblk = (uint32_t)(FA / (2 * np));
-            std::vector<int8_t> h_dg(2 * (size_t)C * nblk * 64);
-            for (int c = 0; c < C; c++) for (uint32_t t = 0; t < nblk; t++) {
-                sc_radix16(&h_dg[(((size_t)c * 2 + 0) * nblk + t) * 64], cAG[(size_t)c * cAstride + t]);
-                sc_radix16(&h_dg[(((size_t)c * 2 + 1) * nblk + t) * 64], cAH[(size_t)c * cAstride + t]);
-            }
-            dev_buf d_dg(h_dg.size(), s); rt_h2d(d_dg.p, h_dg.data(), h_dg.size(), s);
+            const uint32_t nblk = (uint32_t)(FA / (2 * np));                  // == cAstride: the digits were written by the last frozen round's k_ts_round
             frz_exit_args xa = {}; xa.T = d_frzT.as<p3_st>(); xa.digs = d_dg.as<int8_t>(); xa.Gf = d_Gf.as<p3_st>(); xa.Hf = d_Hf.as<p3_st>();
             xa.F = (uint32_t)FA; xa.Fo = (uint32_t)(2 * np); xa.nblk = nblk; xa.stride = (uint32_t)half;
             dev_buf d_xV(sizeof(p3_st) * (size_t)C * 2 * xa.Fo * 8, s); xa.V = d_xV.as<p3_st>();
@@ -458,11 +396,6 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
         }
         if (round == pre) tr.mark("exit");
         if (round == pre) {          // np <= tail_np: every remaining round in one launch (kernels.cuh, k_ipp_tail)
-            const int rounds_left = lgN - round; const uint32_t ostride = 64 * (uint32_t)rounds_left + 64;
-            std::vector<sc_st> h_up(2 * (size_t)C);
-            for (int c = 0; c < C; c++) { sc_to_st(h_up[c], uprod[c]); sc_to_st(h_up[C + c], uinvprod[c]); }
-            dev_buf d_ts(sizeof(transcript) * (size_t)C, s), d_up(sizeof(sc_st) * 2 * (size_t)C, s), d_tail((size_t)ostride * C, s);
-            rt_h2d(d_ts.p, ts.data(), sizeof(transcript) * (size_t)C, s); rt_h2d(d_up.p, h_up.data(), sizeof(sc_st) * 2 * (size_t)C, s);
             // freeze the 2*np generators the tail works on: Straus tables (kernels.cuh K6c), built once for all its rounds
             const uint32_t Ft = (uint32_t)(2 * np);
             if (round == 0) LAUNCH(k_niels_to_p3, dim3((Ft + 127) / 128, C), dim3(128), s, d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), g.G, g.H, Ft, (uint32_t)half);
@@ -474,21 +407,16 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             ta.a = d_a.as<sc_st>(); ta.b = d_b.as<sc_st>(); ta.yinv = d_yinv.as<sc_st>(); ta.N = N;
             ta.ts = d_ts.as<transcript>(); ta.w = d_w2.as<sc_st>(); ta.uprod = d_up.as<sc_st>(); ta.uinvprod = d_up.as<sc_st>() + C; ta.tabB = e.tabB;
             dev_buf d_tscr(sizeof(p3_st) * 512 * (size_t)C, s); ta.scratch = d_tscr.as<p3_st>();
-            ta.out = d_tail.as<uint8_t>(); ta.out_stride = ostride; ta.F = Ft;
+            ta.out = d_proofs.as<uint8_t>() + 224 + 64 * (size_t)round; ta.out_stride = (uint32_t)plen; ta.F = Ft;
             LAUNCH_COOP(k_ipp_tail, dim3(C), dim3(TAIL_THREADS), s, ta);
             rt_prof_end(PROF_TAIL, tk, s);
-            std::vector<uint8_t> h_tail((size_t)ostride * C);
-            rt_d2h(h_tail.data(), d_tail.p, h_tail.size(), s); rt_sync(s);
-            for (int c = 0; c < C; c++) memcpy(h_proofs + plen * c + 224 + 64 * (size_t)round, &h_tail[(size_t)ostride * c], ostride);
-            tail_done = true; tr.mark("tail");
+            tail_done = true;
             break;
         }
         const int nbI = (int)std::min<size_t>(256, (np + 255) / 256);
         const bool unfolded = round < r_unf;
         if (frozen) {
-            const uint32_t nblk = (uint32_t)(FA / (2 * np)); const int nbQA = (int)std::min<size_t>(256, (FA / 2 + 255) / 256);
-            for (int c = 0; c < C; c++) for (uint32_t t = 0; t < nblk; t++) { sc_to_st(h_cA[(size_t)c * cAstride + t], cAG[(size_t)c * cAstride + t]); sc_to_st(h_cA[((size_t)C + c) * cAstride + t], cAH[(size_t)c * cAstride + t]); }
-            rt_h2d(d_cA.p, h_cA.data(), sizeof(sc_st) * h_cA.size(), s);
+            const int nbQA = (int)std::min<size_t>(256, (FA / 2 + 255) / 256);
             LAUNCH_COOP(k_ipp_scalars_unf, dim3(nbQA, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), d_cA.as<sc_st>(), d_cA.as<sc_st>() + (size_t)C * cAstride, cAstride,
                         msmL, msmR, d_partQ.as<sc_st>(), N, (uint32_t)np, (uint32_t)FA);
             LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_partQ.as<sc_st>(), nbQA, 2);
@@ -500,9 +428,6 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
             run_finalize(s, f);
         } else if (unfolded) {
-            const uint32_t nblk = 1u << round;
-            for (int c = 0; c < C; c++) for (uint32_t t = 0; t < nblk; t++) { sc_to_st(h_cGH[(size_t)c * cstride + t], cG[(size_t)c * cstride + t]); sc_to_st(h_cGH[((size_t)C + c) * cstride + t], cH[(size_t)c * cstride + t]); }
-            rt_h2d(d_cGH.p, h_cGH.data(), sizeof(sc_st) * h_cGH.size(), s);
             LAUNCH_COOP(k_ipp_scalars_unf, dim3(nbQ, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), d_cGH.as<sc_st>(), d_cGH.as<sc_st>() + (size_t)C * cstride, cstride,
                         msmL, msmR, d_partQ.as<sc_st>(), N, (uint32_t)np, (uint32_t)N);
             LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_partQ.as<sc_st>(), nbQ, 2);
@@ -532,50 +457,24 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
             run_finalize(s, f);
         }
-        rt_d2h(hLR, d_LR.p, 64 * (size_t)C, s);
-        rt_sync(s);
-        serial_for(C, [&](size_t c) {
-            transcript &t = ts[c]; uint8_t *o = h_proofs + plen * c + 224 + 64 * round;
-            memcpy(o, &hLR[32 * c], 32); memcpy(o + 32, &hLR[32 * (C + c)], 32);
-            transcript_append(t, "L", o, 32); transcript_append(t, "R", o + 32, 32);
-            ts_challenge_scalar(t, "u", u[c]);
-        });
-        uinv = u; sc_batch_invert(uinv);
-        const int lgnp = ilog2_sz(np);
-        for (int c = 0; c < C; c++) {
-            sc u2, ui2, sH, yp;
-            sc_mul(u2, u[c], u[c]); sc_mul(ui2, uinv[c], uinv[c]);
-            st_to_sc(yp, h_yinvpow2[32 * c + lgnp]); sc_mul(sH, ui2, yp);            // u^-2 y^-np
-            sc_to_st(h_u2[c], u2); sc_to_st(h_uinv2[c], ui2);
-            if (frozen) {
-                const uint32_t nblk = (uint32_t)(FA / (2 * np)); sc *g0 = &cAG[(size_t)c * cAstride], *h0 = &cAH[(size_t)c * cAstride];
-                if (2 * nblk <= cAstride) for (uint32_t t = nblk; t-- > 0;) { sc gt = g0[t], ht = h0[t]; g0[2 * t] = gt; sc_mul(g0[2 * t + 1], gt, u2); h0[2 * t] = ht; sc_mul(h0[2 * t + 1], ht, sH); }
-            } else if (unfolded) {       // coefficient tables of the next level: c'[2t] = c[t], c'[2t+1] = c[t] * s
-                const uint32_t nblk = 1u << round; sc *g0 = &cG[(size_t)c * cstride], *h0 = &cH[(size_t)c * cstride];
-                for (uint32_t t = nblk; t-- > 0;) { sc gt = g0[t], ht = h0[t]; g0[2 * t] = gt; sc_mul(g0[2 * t + 1], gt, u2); h0[2 * t] = ht; sc_mul(h0[2 * t + 1], ht, sH); }
-            } else { sc_naf(&h_nafs[512 * c], u2, FOLD_W); sc_naf(&h_nafs[512 * c + 256], sH, FOLD_W); }
-            sc_mul(uprod[c], uprod[c], u[c]); sc_mul(uinvprod[c], uinvprod[c], uinv[c]);
+        // ---- L, R -> u on the device, with everything the next kernels need from it (ts_kernels.cuh, k_ts_round)
+        const bool catchup = unfolded && round + 1 == r_unf && np >= 2, fold = !frozen && !unfolded && np >= 2;
+        {
+            ts_round_args t = {}; t.ts = d_ts.as<transcript>(); t.LR = d_LR.as<uint8_t>(); t.proofs = d_proofs.as<uint8_t>(); t.plen = (uint32_t)plen; t.off = (uint32_t)(224 + 64 * round); t.C = (uint32_t)C;
+            t.yinvpow2 = d_yinvpow2.as<sc_st>(); t.lgnp = ilog2_sz(np); t.u2 = d_u2.as<sc_st>(); t.uinv2 = d_uinv2.as<sc_st>(); t.up = d_up.as<sc_st>();
+            if (frozen) { t.coefG = d_cA.as<sc_st>(); t.coefH = d_cA.as<sc_st>() + (size_t)C * cAstride; t.cstride = cAstride; t.nblk = (uint32_t)(FA / (2 * np)); if (round + 1 == pre && pre < lgN) { t.emit = 3; t.digs8 = d_dg.as<int8_t>(); } }
+            else if (unfolded) { t.coefG = d_cGH.as<sc_st>(); t.coefH = d_cGH.as<sc_st>() + (size_t)C * cstride; t.cstride = cstride; t.nblk = 1u << round;
+                                 if (catchup) { t.emit = 2; t.digs16 = d_digs.as<int16_t>(); for (int i = 0; i < 9; i++) t.rtK[i] = rt->K[i]; t.rtc = rt->c; t.rtnw = rt->nw; } }
+            else if (fold) { t.emit = 1; t.nafs = d_nafs.as<int8_t>(); }
+            LAUNCH_COOP(k_ts_round, dim3(C), dim3(TS_THREADS), s, t);
         }
-        rt_h2d(d_u2.p, h_u2.data(), sizeof(sc_st) * C, s); rt_h2d(d_uinv2.p, h_uinv2.data(), sizeof(sc_st) * C, s);
         LAUNCH(k_ipp_fold_scalars, dim3((unsigned)((np + 255) / 256), C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_u2.as<sc_st>(), d_uinv2.as<sc_st>(), N, (uint32_t)np);
-        if (frozen) {
-            // nothing to fold: the generators stay frozen, only the coefficient tables grew
-        } else if (unfolded) {
-            if (round + 1 == r_unf && np >= 2) {          // catch-up: G", H" of length np straight from the tables
-                const uint32_t nblk = 1u << r_unf;
-                std::vector<int16_t> h_digs(2 * (size_t)C * nblk * RT_MAXW);
-                for (int c = 0; c < C; c++) for (uint32_t t = 0; t < nblk; t++) {
-                    rt_digits(&h_digs[(((size_t)c * 2 + 0) * nblk + t) * RT_MAXW], cG[(size_t)c * cstride + t], *rt);
-                    rt_digits(&h_digs[(((size_t)c * 2 + 1) * nblk + t) * RT_MAXW], cH[(size_t)c * cstride + t], *rt);
-                }
-                rt_h2d(d_digs.p, h_digs.data(), sizeof(int16_t) * h_digs.size(), s);
-                catchup_args ca = {}; ca.rt = *rt; ca.Gf = d_Gf.as<p3_st>(); ca.Hf = d_Hf.as<p3_st>(); ca.digits = d_digs.as<int16_t>(); ca.nr = (uint32_t)np; ca.nblk = nblk; ca.stride = (uint32_t)half;
-                void *tk = rt_prof_begin(PROF_FOLD, s);
-                LAUNCH_COOP(k_rt_catchup, dim3((unsigned)((np + 127) / 128), C, 2), dim3(128), s, ca);
-                rt_prof_end(PROF_FOLD, tk, s);
-            }
-        } else if (np >= 2) {
-            rt_h2d(d_nafs.p, h_nafs.data(), h_nafs.size(), s);
+        if (catchup) {               // G", H" of length np straight from the tables
+            catchup_args ca = {}; ca.rt = *rt; ca.Gf = d_Gf.as<p3_st>(); ca.Hf = d_Hf.as<p3_st>(); ca.digits = d_digs.as<int16_t>(); ca.nr = (uint32_t)np; ca.nblk = 1u << r_unf; ca.stride = (uint32_t)half;
+            void *tk = rt_prof_begin(PROF_FOLD, s);
+            LAUNCH_COOP(k_rt_catchup, dim3((unsigned)((np + 127) / 128), C, 2), dim3(128), s, ca);
+            rt_prof_end(PROF_FOLD, tk, s);
+        } else if (fold) {
             fold_args fa = {}; fa.Gn = round == 0 ? g.G : nullptr; fa.Hn = round == 0 ? g.H : nullptr;
             fa.Gf = d_Gf.as<p3_st>(); fa.Hf = d_Hf.as<p3_st>(); fa.nafs = d_nafs.as<int8_t>(); fa.np = (uint32_t)np; fa.stride = (uint32_t)half;
             void *tk = rt_prof_begin(PROF_FOLD, s);
@@ -583,17 +482,13 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
             rt_prof_end(PROF_FOLD, tk, s);
         }
     }
-    if (tail_done) return;
-    // ---- final a, b: a = a^ prod u_k, b = b^ prod u_k^-1
-    std::vector<sc_st> h_ab(2 * (size_t)C);
-    for (int c = 0; c < C; c++) { rt_d2h(&h_ab[2 * c], d_a.as<sc_st>() + (size_t)c * N, sizeof(sc_st), s); rt_d2h(&h_ab[2 * c + 1], d_b.as<sc_st>() + (size_t)c * N, sizeof(sc_st), s); }
-    rt_sync(s);
-    for (int c = 0; c < C; c++) {
-        sc a, b; st_to_sc(a, h_ab[2 * c]); st_to_sc(b, h_ab[2 * c + 1]);
-        sc_mul(a, a, uprod[c]); sc_mul(b, b, uinvprod[c]);
-        uint8_t *o = h_proofs + plen * c + 224 + 64 * lgN;
-        sc_tobytes(o, a); sc_tobytes(o + 32, b);
+    if (!tail_done) {            // final a, b: a = a^ prod u_k, b = b^ prod u_k^-1
+        ts_final_args fa = {}; fa.a = d_a.as<sc_st>(); fa.b = d_b.as<sc_st>(); fa.up = d_up.as<sc_st>(); fa.proofs = d_proofs.as<uint8_t>(); fa.plen = (uint32_t)plen; fa.off = (uint32_t)(224 + 64 * lgN); fa.C = (uint32_t)C; fa.N = N;
+        LAUNCH(k_ts_final, dim3((unsigned)((C + 63) / 64)), dim3(64), s, fa);
     }
+    rt_d2h(h_proofs, d_proofs.p, plen * (size_t)C, s);
+    rt_sync(s);
+    tr.mark("ipp");
 }
 
 
@@ -611,7 +506,7 @@ template <class F> static void for_chunk_groups(rofl_engine &e, size_t C, F f) {
 
 // =============================================================================================================================
 // range_proof_vec::create_rangeproof (range_proof_vec/mod.rs:16-102).  d_values / d_blind / d_commits are device pointers.
-// returns 0 ok, 2 ValueOutOfRangeError, -1 InvalidBitsize, -2 bad arguments, -98 NaN input (reference panics),
+// returns 0 ok, 2 ValueOutOfRangeError, -7 InvalidBitsize, -2 bad arguments, -98 NaN input (reference panics),
 // -99 non power-of-two chunking (reference panics "Should not get here")
 // =============================================================================================================================
 // A shard = chunks [chunk_begin, chunk_begin + n_chunks) of a larger update (chunk length m): the caller passes only that
@@ -641,7 +536,7 @@ static int engine_range_prove(rofl_engine &e, const float *d_values, const uint8
     int flags = 0; rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_sync(s);
     if (flags & 2) return 2;                                                         // :26-29
     if (flags & 1) return -98;
-    if (!bitsize_ok) return -1;
+    if (!bitsize_ok) return ROFL_ERR_BITSIZE_;
     if (!chunk_ok) return -99;
     gens_entry &g = engine_gens(e, range, (int)m);
     rt_tables rt; const bool have_rt = engine_rt(e, g, range, (int)m, rt);
@@ -650,117 +545,64 @@ static int engine_range_prove(rofl_engine &e, const float *d_values, const uint8
     const size_t plen = 32 * (9 + 2 * (size_t)ilog2_sz((size_t)range * m));
     for_chunk_groups(e, C, [&](size_t, size_t c0, size_t c1, cudaStream_t gs) {
         std::vector<uint8_t> k(keys.begin() + 32 * c0, keys.begin() + 32 * c1);
-        prove_chunks(e, gs, "RangeProof", range, (int)m, (int)(c1 - c0), g, have_rt ? &rt : nullptr, d_vals.as<uint64_t>() + c0 * m, d_bl.as<sc_st>() + c0 * m, d_V.as<uint8_t>() + 32 * c0 * m, k, h_proofs + plen * c0);
+        prove_chunks(e, gs, e.side_for(gs), 0, range, (int)m, (int)(c1 - c0), g, have_rt ? &rt : nullptr, d_vals.as<uint64_t>() + c0 * m, d_bl.as<sc_st>() + c0 * m, d_V.as<uint8_t>() + 32 * c0 * m, k, h_proofs + plen * c0);
     });
     *proof_len = plen; *n_proofs = C;
     return 0;
 }
 
 // =============================================================================================================================
-// RangeProof::verify_multiple for C chunks: d_Vp3 / h_V32 hold C*m (shifted) commitments.
-// verdict[c] = 1 accept / 0 VerificationError.  returns 0 or a negative error (-1 FormatError).
+// RangeProof::verify_multiple for C chunks: d_Vp3 / d_V32 hold C*m (shifted) commitments as points / encodings (device).
+// The transcripts are replayed on the device (ts_kernels.cuh) and all chunks are checked with ONE random linear combination whose weights
+// are derived by Fiat-Shamir from the seed and every proof / commitment of the call.
+// verdict[c] = 1 accept / 0 VerificationError.  returns 0 or a negative error (-1 FormatError).  d_xbad (nullable): one more device flag
+// word fetched with the result (the caller's "a commitment did not decode").
 // =============================================================================================================================
-static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int n, int m, int C, const gens_entry &g, const rt_tables *rt, const p3_st *d_Vp3, const uint8_t *h_V32,
-                         const uint8_t *h_proofs, size_t plen, const std::vector<uint8_t> &keys, std::vector<int> &verdict) {
-    verdict.assign(C, 0);
-    phase_trace tr(s);
-    // RangeProof::from_bytes / InnerProductProof::from_bytes
+static inline int range_proof_format_check(const uint8_t *h_proofs, size_t plen, size_t C, size_t *lg_out) {       // RangeProof::from_bytes / InnerProductProof::from_bytes
     if (plen % 32 || plen < 7 * 32) return -1;
-    size_t ne = plen / 32 - 7;
+    const size_t ne = plen / 32 - 7;
     if (ne < 2 || (ne - 2) % 2) return -1;
     const size_t lg = (ne - 2) / 2; if (lg >= 32) return -1;
-    for (int c = 0; c < C; c++) {
+    for (size_t c = 0; c < C; c++) {
         const uint8_t *p = h_proofs + plen * c; sc t;
         for (size_t off : {(size_t)128, (size_t)160, (size_t)192, 224 + 64 * lg, 224 + 64 * lg + 32}) { sc_frombytes(t, p + off); if (!sc_is_canonical(t)) return -1; }
     }
+    if (lg_out) *lg_out = lg;
+    return 0;
+}
+static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, int m, int C, const gens_entry &g, const rt_tables *rt, const p3_st *d_Vp3, const uint8_t *d_V32,
+                         const uint8_t *h_proofs, size_t plen, const uint8_t seed[32], uint32_t dom, uint64_t c_off, std::vector<int> &verdict, const int *d_xbad = nullptr, int *h_xbad = nullptr, uint8_t *h_weights = nullptr) {
+    verdict.assign(C, 0);
+    phase_trace tr(s);
+    size_t lg = 0;
+    if (range_proof_format_check(h_proofs, plen, (size_t)C, &lg)) return -1;
     const size_t N = (size_t)n * m;
-    if ((m & (m - 1)) || N != ((size_t)1 << lg)) return 0;                      // verification_scalars: n != 1 << lg_n -> VerificationError (all chunks false)
-    const int lgN = (int)lg, nsmall = 6 + 2 * lgN;
+    if ((m & (m - 1)) || N != ((size_t)1 << lg)) {                      // verification_scalars: n != 1 << lg_n -> VerificationError (all chunks false)
+        if (d_xbad) { rt_d2h(h_xbad, d_xbad, sizeof(int), s); rt_sync(s); }
+        return 0;
+    }
+    const int lgN = (int)lg, nsmall = 6 + 2 * lgN, lgm = ilog2_sz((size_t)m);
     // all C chunks are checked with ONE equation: sum_c rho_c * (chunk c's mega-check) == identity (kernels.cuh, k_verify_scalars)
     const int chs = 5 + 2 * lgN;
     const uint32_t vstride = (uint32_t)(m + nsmall);
-    std::vector<sc_st> h_chal((size_t)C * chs), h_small((size_t)C * nsmall), h_yinvpow2(32 * (size_t)C), h_zpow2(32 * (size_t)C);
-    std::vector<uint8_t> h_smallpts(32 * (size_t)C * nsmall);
-    std::vector<int> host_ok(C, 1);
-    std::vector<sc> y(C), yinv(C), z(C), x(C), w(C), cc(C), rho(C);
-    std::vector<std::vector<sc>> u(C, std::vector<sc>(lgN));
-    std::vector<sc> allu; allu.reserve((size_t)C * (lgN + 1));
-    parallel_for(C, e.host_threads, [&](size_t c) {
-        const uint8_t *p = h_proofs + plen * c, *ipp = p + 224;
-        transcript t; transcript_init(t, label);
-        transcript_append(t, "dom-sep", (const uint8_t *)"rangeproof v1", 13);
-        transcript_append_u64(t, "n", (uint64_t)n); transcript_append_u64(t, "m", (uint64_t)m);
-        for (int j = 0; j < m; j++) transcript_append(t, "V", h_V32 + 32 * (c * m + j), 32);
-        int ok = 1;
-        ok &= !is_zero32(p) && !is_zero32(p + 32) && !is_zero32(p + 64) && !is_zero32(p + 96);          // validate_and_append_point
-        transcript_append(t, "A", p, 32); transcript_append(t, "S", p + 32, 32);
-        ts_challenge_scalar(t, "y", y[c]); ts_challenge_scalar(t, "z", z[c]);
-        transcript_append(t, "T_1", p + 64, 32); transcript_append(t, "T_2", p + 96, 32);
-        ts_challenge_scalar(t, "x", x[c]);
-        transcript_append(t, "t_x", p + 128, 32); transcript_append(t, "t_x_blinding", p + 160, 32); transcript_append(t, "e_blinding", p + 192, 32);
-        ts_challenge_scalar(t, "w", w[c]);
-        uint32_t kw[8]; key_words(kw, &keys[32 * c]); nonce_scalar(cc[c], kw, 0);                     // batching scalar c <- rng
-        nonce_scalar(rho[c], kw, 1);                                                                   // cross-chunk weight
-        transcript_append(t, "dom-sep", (const uint8_t *)"ipp v1", 6); transcript_append_u64(t, "n", (uint64_t)N);
-        for (int k = 0; k < lgN; k++) {
-            ok &= !is_zero32(ipp + 64 * k) && !is_zero32(ipp + 64 * k + 32);
-            transcript_append(t, "L", ipp + 64 * k, 32); transcript_append(t, "R", ipp + 64 * k + 32, 32);
-            ts_challenge_scalar(t, "u", u[c][k]);
-        }
-        host_ok[c] = ok;
-        // small points: A S T1 T2 L.. R.. H B
-        uint8_t *sp = &h_smallpts[32 * c * nsmall];
-        memcpy(sp, p, 128);
-        for (int k = 0; k < lgN; k++) { memcpy(sp + 32 * (4 + k), ipp + 64 * k, 32); memcpy(sp + 32 * (4 + lgN + k), ipp + 64 * k + 32, 32); }
-        memcpy(sp + 32 * (4 + 2 * lgN), e.H32, 32); memcpy(sp + 32 * (5 + 2 * lgN), e.B32, 32);
-    });
-    tr.mark("v_transcripts");
-    for (int c = 0; c < C; c++) { allu.push_back(y[c]); for (int k = 0; k < lgN; k++) allu.push_back(u[c][k]); }
-    for (auto &v : allu) if (sc_iszero(v)) sc_from_u64(v, 1);                    // (probability 2^-252; keeps the batch inversion defined)
-    sc_batch_invert(allu);
-    parallel_for(C, e.host_threads, [&](size_t c) {
-        const uint8_t *p = h_proofs + plen * c, *ipp = p + 224;
-        const sc *inv = &allu[c * (lgN + 1)];
-        const sc &r = rho[c];
-        yinv[c] = inv[0];
-        sc t_x, t_xb, e_bl, a, b, zz, tmp, tmp2;
-        sc_frombytes(t_x, p + 128); sc_frombytes(t_xb, p + 160); sc_frombytes(e_bl, p + 192);
-        sc_frombytes(a, ipp + 64 * lgN); sc_frombytes(b, ipp + 64 * lgN + 32);
-        sc_mul(zz, z[c], z[c]);
-        sc_st *ch = &h_chal[c * chs];
-        sc_mul(tmp, r, z[c]); sc_to_st(ch[0], tmp); sc_mul(tmp, r, zz); sc_to_st(ch[1], tmp);
-        sc_mul(tmp, r, a); sc_to_st(ch[2], tmp); sc_mul(tmp, r, b); sc_to_st(ch[3], tmp); sc_to_st(ch[4], cc[c]);
-        sc_st *sm = &h_small[c * nsmall];
-        sc cx; sc_mul(cx, cc[c], x[c]);
-        auto put = [&](int i, const sc &v) { sc t; sc_mul(t, v, r); sc_to_st(sm[i], t); };                  // every small scalar carries rho_c
-        sc_to_st(sm[0], r); put(1, x[c]); put(2, cx); sc_mul(tmp, cx, x[c]); put(3, tmp);
-        for (int k = 0; k < lgN; k++) {
-            sc_to_st(ch[5 + k], u[c][k]); sc_to_st(ch[5 + lgN + k], inv[1 + k]);
-            sc_mul(tmp, u[c][k], u[c][k]); put(4 + k, tmp);
-            sc_mul(tmp, inv[1 + k], inv[1 + k]); put(4 + lgN + k, tmp);
-        }
-        sc_mul(tmp, cc[c], t_xb); sc_add(tmp, tmp, e_bl); sc_neg(tmp, tmp); put(4 + 2 * lgN, tmp);      // H: -e_bl - c t_x_bl
-        // delta = (z - zz) sum_{i<N} y^i - z^3 (2^n - 1) sum_{j<m} z^j ; sums of powers via prod (1 + s^(2^b))
-        sc_pow2_table(&h_yinvpow2[32 * c], yinv[c]); sc_pow2_table(&h_zpow2[32 * c], z[c]);
-        sc one, sum_y, sum_z, pw, delta, s2; sc_from_u64(one, 1); sc_from_u64(sum_y, 1); sc_from_u64(sum_z, 1);
-        pw = y[c]; for (int bb = 0; bb < lgN; bb++) { sc_add(tmp, one, pw); sc_mul(sum_y, sum_y, tmp); sc_mul(pw, pw, pw); }
-        pw = z[c]; for (int bb = 0; bb < ilog2_sz(m); bb++) { sc_add(tmp, one, pw); sc_mul(sum_z, sum_z, tmp); sc_mul(pw, pw, pw); }
-        sc_from_u64(s2, n == 64 ? ~0ULL : ((1ULL << n) - 1));
-        sc_sub(delta, z[c], zz); sc_mul(delta, delta, sum_y);
-        sc_mul(tmp, zz, z[c]); sc_mul(tmp, tmp, s2); sc_mul(tmp, tmp, sum_z); sc_sub(delta, delta, tmp);
-        sc_mul(tmp, a, b); sc_sub(tmp, t_x, tmp); sc_mul(tmp, w[c], tmp);                                        // w (t_x - a b)
-        sc_sub(tmp2, delta, t_x); sc_mul(tmp2, cc[c], tmp2); sc_add(tmp, tmp, tmp2); put(5 + 2 * lgN, tmp);      // B
-    });
-    tr.mark("v_host_scalars");
-    const vtab_layout vt = vtab_make(lgN, ilog2_sz(m));
-    dev_buf d_chal(sizeof(sc_st) * h_chal.size(), s), d_yinvpow2(sizeof(sc_st) * 32 * C, s), d_zpow2(sizeof(sc_st) * 32 * C, s);
+    const vtab_layout vt = vtab_make(lgN, lgm);
+    dev_buf d_proofs(plen * (size_t)C, s), d_ts(sizeof(transcript) * (size_t)C, s), d_vch(sizeof(sc_st) * (size_t)C * (4 + lgN), s), d_digest(32 * (size_t)C, s), d_ccrho(sizeof(sc_st) * 2 * (size_t)C, s);
+    dev_buf d_chal(sizeof(sc_st) * (size_t)C * chs, s), d_yinvpow2(sizeof(sc_st) * 32 * C, s), d_zpow2(sizeof(sc_st) * 32 * C, s);
     dev_buf d_tab(sizeof(sc_st) * (size_t)C * vt.total, s), d_gh(sizeof(sc_st) * 2 * N, s), d_var(sizeof(sc_st) * (size_t)C * vstride, s);
-    dev_buf d_sp32(h_smallpts.size(), s), d_sp(sizeof(p3_st) * (size_t)C * nsmall, s), d_bad(sizeof(int) * C, s), d_id(sizeof(int), s), d_fix(sizeof(p3_st), s);
-    rt_h2d(d_chal.p, h_chal.data(), sizeof(sc_st) * h_chal.size(), s);
-    rt_h2d(d_yinvpow2.p, h_yinvpow2.data(), sizeof(sc_st) * 32 * C, s); rt_h2d(d_zpow2.p, h_zpow2.data(), sizeof(sc_st) * 32 * C, s);
-    rt_h2d(d_sp32.p, h_smallpts.data(), h_smallpts.size(), s);
+    dev_buf d_sp32(32 * (size_t)C * nsmall, s), d_sp(sizeof(p3_st) * (size_t)C * nsmall, s), d_bad(sizeof(int) * C, s), d_id(sizeof(int), s), d_fix(sizeof(p3_st), s);
+    rt_h2d(d_proofs.p, h_proofs, plen * (size_t)C, s);
     rt_memset(d_bad.p, 0, sizeof(int) * C, s);
-    rt_h2d(d_var.as<sc_st>() + (size_t)C * m, h_small.data(), sizeof(sc_st) * h_small.size(), s);
+    { ts_absorb_args aa = {}; aa.ts = d_ts.as<transcript>(); aa.V32 = d_V32; aa.m = (uint32_t)m; aa.n = (uint32_t)n; aa.label_id = label_id;
+      LAUNCH_COOP(k_ts_absorbV, dim3(C), dim3(TS_THREADS), s, aa); }
+    { ts_verify_args va = {}; va.ts = d_ts.as<transcript>(); va.proofs = d_proofs.as<uint8_t>(); va.plen = (uint32_t)plen; va.C = (uint32_t)C; va.lgN = lgN; va.N = (uint64_t)N;
+      va.chal = d_vch.as<sc_st>(); va.digest = d_digest.as<uint8_t>(); va.bad = d_bad.as<int>(); va.sp32 = d_sp32.as<uint8_t>(); memcpy(va.B32, e.B32, 32); memcpy(va.H32, e.H32, 32);
+      LAUNCH(k_ts_verify, dim3((unsigned)((C + TS_THREADS - 1) / TS_THREADS)), dim3(TS_THREADS), s, va); }
+    { verify_keys_args ka = {}; ka.digest = d_digest.as<uint8_t>(); ka.C = (uint32_t)C; ka.dom = dom; ka.c_off = c_off; memcpy(ka.seed, seed, 32); ka.ccrho = d_ccrho.as<sc_st>();
+      LAUNCH_COOP(k_verify_keys, dim3(1), dim3(256), s, ka); }
+    { verify_prep_args pa = {}; pa.proofs = d_proofs.as<uint8_t>(); pa.plen = (uint32_t)plen; pa.C = (uint32_t)C; pa.lgN = lgN; pa.lgm = lgm; pa.n = n; pa.vch = d_vch.as<sc_st>(); pa.ccrho = d_ccrho.as<sc_st>();
+      pa.chal = d_chal.as<sc_st>(); pa.chs = chs; pa.small = d_var.as<sc_st>() + (size_t)C * m; pa.nsmall = nsmall; pa.yinvpow2 = d_yinvpow2.as<sc_st>(); pa.zpow2 = d_zpow2.as<sc_st>();
+      LAUNCH_COOP(k_verify_prep, dim3(C), dim3(TS_THREADS), s, pa); }
+    tr.mark("v_transcripts");
     LAUNCH(k_verify_tables, dim3((vt.total + m + 255) / 256, C), dim3(256), s, d_tab.as<sc_st>(), vt, d_var.as<sc_st>(), (uint32_t)m, d_chal.as<sc_st>(), chs, d_yinvpow2.as<sc_st>(), d_zpow2.as<sc_st>(), m);
     LAUNCH_COOP(k_verify_scalars, dim3((unsigned)((N + 63) / 64)), dim3(256), s, d_gh.as<sc_st>(), d_tab.as<sc_st>(), vt, d_chal.as<sc_st>(), chs, n, C);
     LAUNCH(k_decompress, dim3((unsigned)(((size_t)C * nsmall + 127) / 128)), dim3(128), s, d_sp.as<p3_st>(), (uint8_t *)nullptr, d_sp32.as<uint8_t>(), (size_t)C * nsmall, (size_t)C * nsmall, (const p3_st *)nullptr, d_bad.as<int>(), (size_t)nsmall);
@@ -800,18 +642,20 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, const char *label, int 
     }
     std::vector<int> h_bad(C); int h_id = 0;
     rt_d2h(&h_id, d_id.p, sizeof(int), s); rt_d2h(h_bad.data(), d_bad.p, sizeof(int) * C, s);
+    if (d_xbad) rt_d2h(h_xbad, d_xbad, sizeof(int), s);
+    if (h_weights) rt_d2h(h_weights, d_ccrho.p, sizeof(sc_st) * 2 * (size_t)C, s);
     rt_sync(s);
     tr.mark("v_var_msm");
     int all_ok = h_id;
-    for (int c = 0; c < C; c++) all_ok &= (host_ok[c] && !h_bad[c]) ? 1 : 0;
+    for (int c = 0; c < C; c++) all_ok &= h_bad[c] ? 0 : 1;
     for (int c = 0; c < C; c++) verdict[c] = all_ok;
     return 0;
 }
 
 // range_proof_vec::verify_rangeproof (range_proof_vec/mod.rs:149-191).  d_commits: D compressed points (device).
-// returns 1 true, 0 false, -1 FormatError, -2 InvalidBitsize / bad args, -3 InvalidGeneratorsLength, -4 undecodable commitment
+// returns 1 true, 0 false, -1 FormatError, -7 InvalidBitsize, -2 bad args, -3 InvalidGeneratorsLength, -4 undecodable commitment
 static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t plen, size_t n_proofs, const uint8_t *d_commits, size_t D,
-                               int range, const uint8_t seed[32], const shard_spec *shard = nullptr) {
+                               int range, const uint8_t seed[32], const shard_spec *shard = nullptr, uint8_t *h_weights = nullptr) {
     if (n_proofs == 0 || range < 1 || range > 64) return -2;
     if (shard ? (shard->m == 0 || shard->n_chunks != n_proofs || D > shard->m * shard->n_chunks) : D == 0) return -2;
     std::lock_guard<std::mutex> lk(e.mu);
@@ -820,14 +664,8 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
     const size_t c_off = shard ? shard->chunk_begin : 0;
     if (m == 0) return -3;
     // RangeProof::from_bytes happens when the caller deserialises (params.rs:444-458): format errors come first
-    if (plen % 32 || plen < 7 * 32) return -1;
-    { size_t ne = plen / 32 - 7; if (ne < 2 || (ne - 2) % 2 || (ne - 2) / 2 >= 32) return -1; }
-    if (!(range == 8 || range == 16 || range == 32 || range == 64)) {
-        // scalars must still be canonical for from_bytes to succeed; check then report InvalidBitsize
-        size_t lg = (plen / 32 - 9) / 2;
-        for (size_t c = 0; c < n_proofs; c++) { const uint8_t *p = h_proofs + plen * c; sc t; for (size_t off : {(size_t)128, (size_t)160, (size_t)192, 224 + 64 * lg, 224 + 64 * lg + 32}) { sc_frombytes(t, p + off); if (!sc_is_canonical(t)) return -1; } }
-        return -2;
-    }
+    if (range_proof_format_check(h_proofs, plen, n_proofs, nullptr)) return -1;
+    if (!(range == 8 || range == 16 || range == 32 || range == 64)) return ROFL_ERR_BITSIZE_;
     const size_t C = std::min(n_proofs, (Dp + m - 1) / m);                        // zip(proofs, chunks)
     phase_trace tr(s);
     dev_buf d_off(sizeof(p3_st), s), d_offs(sizeof(sc_st), s), d_Vp3(sizeof(p3_st) * Dp, s), d_V32(32 * Dp, s), d_bad(sizeof(int), s);
@@ -836,25 +674,15 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
       run_finalize(s, f); }
     rt_memset(d_bad.p, 0, sizeof(int), s);
     LAUNCH(k_decompress, dim3((unsigned)((Dp + 127) / 128)), dim3(128), s, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), d_commits, D, Dp, d_off.as<p3_st>(), d_bad.as<int>(), Dp);
-    std::vector<uint8_t> hV(32 * Dp); int bad = 0;
-    rt_d2h(hV.data(), d_V32.p, hV.size(), s); rt_d2h(&bad, d_bad.p, sizeof(int), s);
-    rt_sync(s);
     tr.mark("v_decompress");
-    if (bad) return -4;
     gens_entry &g = engine_gens(e, range, (int)m);
     rt_tables rt; const bool have_rt = engine_rt(e, g, range, (int)m, rt);
-    std::vector<uint8_t> keys(32 * C);
-    for (size_t c = 0; c < C; c++) derive_key(&keys[32 * c], seed, DOM_RANGE_VERIFY, c_off + c);
     // one group: every chunk goes into the same batched check (kernels.cuh, k_verify_scalars), splitting would repeat the generator MSM
-    std::vector<int> rcs(2, 1);
-    [&](auto f) { f((size_t)0, (size_t)0, C, e.stream); }([&](size_t gi, size_t c0, size_t c1, cudaStream_t gs) {
-        std::vector<uint8_t> k(keys.begin() + 32 * c0, keys.begin() + 32 * c1); std::vector<int> verdict;
-        int rc = verify_chunks(e, gs, "RangeProof", range, (int)m, (int)(c1 - c0), g, have_rt ? &rt : nullptr, d_Vp3.as<p3_st>() + c0 * m, hV.data() + 32 * c0 * m, h_proofs + plen * c0, plen, k, verdict);
-        int res = 1; for (int v : verdict) res &= v;                               // :183-190
-        rcs[gi] = rc < 0 ? rc : res;
-    });
-    int res = 1;
-    for (int r : rcs) { if (r < 0) return r; res &= r; }
+    std::vector<int> verdict; int bad = 0;
+    const int rc = verify_chunks(e, s, 0, range, (int)m, (int)C, g, have_rt ? &rt : nullptr, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), h_proofs, plen, seed, DOM_RANGE_VERIFY, c_off, verdict, d_bad.as<int>(), &bad, h_weights);
+    if (bad) return -4;
+    if (rc < 0) return rc;
+    int res = 1; for (int v : verdict) res &= v;                               // :183-190
     return res;
 }
 
@@ -862,7 +690,7 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
 // l2_range_proof_vec::create_rangeproof_l2 (l2_range_proof_vec/mod.rs:15-140): one m=1 proof on sum x_i^2 with blinding sum r_i.
 // h_values is a HOST copy of the values: the reference cross-checks the scalar sum against a sequential f32 fold (:44-58)
 // whose rounding depends on the summation order, so that O(D) fold runs on the host exactly as written.
-// returns 0 ok, 2 ValueOutOfRange, 3 OverflowError, 4 NormOutOfRange, -1 InvalidBitsize, -2 bad args
+// returns 0 ok, 2 ValueOutOfRange, 3 OverflowError, 4 NormOutOfRange, -7 InvalidBitsize, -2 bad args
 // =============================================================================================================================
 static int engine_l2_prove(rofl_engine &e, const float *h_values, const float *d_values, const uint8_t *d_blind, size_t D, int range,
                            int n_bits, int frac, const uint8_t seed[32], uint8_t *h_proof, size_t *proof_len, uint8_t *h_commit) {
@@ -890,7 +718,7 @@ static int engine_l2_prove(rofl_engine &e, const float *h_values, const float *d
     const float vf = scalar_to_f32(val, n_bits, frac);
     if (fabsf(vf - val_float) > 1.1920929e-7f) return 3;
     if (vf > l2_clip_max_f(range, n_bits, frac)) return 4;
-    if (!(range == 8 || range == 16 || range == 32 || range == 64)) return -1;
+    if (!(range == 8 || range == 16 || range == 32 || range == 64)) return ROFL_ERR_BITSIZE_;
     uint64_t v = (((uint64_t)val.v[1] << 32) | val.v[0]) & fix_max(n_bits);      // :69-73 read_from_bytes
     // V = v B + bsum H
     dev_buf d_v(8, s), d_bl(sizeof(sc_st), s), d_vs(sizeof(sc_st), s), d_V(32, s);
@@ -900,7 +728,7 @@ static int engine_l2_prove(rofl_engine &e, const float *h_values, const float *d
       run_finalize(s, f); }
     gens_entry &g = engine_gens(e, range, 1);                                     // BulletproofGens::new(64, 1) restricted to n = range (:162)
     std::vector<uint8_t> keys(32); derive_key(keys.data(), seed, DOM_L2_PROVE, 0);
-    prove_chunks(e, s, "L2RangeProof", range, 1, 1, g, nullptr, d_v.as<uint64_t>(), d_bl.as<sc_st>(), d_V.as<uint8_t>(), keys, h_proof);
+    prove_chunks(e, s, s, 1, range, 1, 1, g, nullptr, d_v.as<uint64_t>(), d_bl.as<sc_st>(), d_V.as<uint8_t>(), keys, h_proof);
     rt_d2h(h_commit, d_V.p, 32, s); rt_sync(s);
     *proof_len = 32 * (9 + 2 * (size_t)ilog2_sz((size_t)range));
     return 0;
@@ -909,22 +737,18 @@ static int engine_l2_prove(rofl_engine &e, const float *h_values, const float *d
 static int engine_l2_verify(rofl_engine &e, const uint8_t *h_proof, size_t plen, const uint8_t *h_commit, int range, const uint8_t seed[32]) {
     std::lock_guard<std::mutex> lk(e.mu);
     cudaStream_t s = e.stream;
-    if (plen % 32 || plen < 7 * 32) return -1;
-    { size_t ne = plen / 32 - 7; if (ne < 2 || (ne - 2) % 2 || (ne - 2) / 2 >= 32) return -1; }
+    if (range_proof_format_check(h_proof, plen, 1, nullptr)) return -1;
     dev_buf d_c(32, s), d_Vp3(sizeof(p3_st), s), d_V32(32, s), d_bad(sizeof(int), s);
     rt_h2d(d_c.p, h_commit, 32, s); rt_memset(d_bad.p, 0, sizeof(int), s);
     LAUNCH(k_decompress, dim3(1), dim3(128), s, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), d_c.as<uint8_t>(), (size_t)1, (size_t)1, (const p3_st *)nullptr, d_bad.as<int>(), (size_t)1);
-    uint8_t hV[32]; int bad = 0; rt_d2h(hV, d_V32.p, 32, s); rt_d2h(&bad, d_bad.p, sizeof(int), s); rt_sync(s);
-    if (bad) return -4;
     if (!(range == 8 || range == 16 || range == 32 || range == 64)) {
-        size_t lg = (plen / 32 - 9) / 2; const uint8_t *p = h_proof; sc t;
-        for (size_t off : {(size_t)128, (size_t)160, (size_t)192, 224 + 64 * lg, 224 + 64 * lg + 32}) { sc_frombytes(t, p + off); if (!sc_is_canonical(t)) return -1; }
-        return -2;
+        int bad = 0; rt_d2h(&bad, d_bad.p, sizeof(int), s); rt_sync(s);
+        return bad ? -4 : ROFL_ERR_BITSIZE_;
     }
     gens_entry &g = engine_gens(e, range, 1);
-    std::vector<uint8_t> keys(32); derive_key(keys.data(), seed, DOM_L2_VERIFY, 0);
-    std::vector<int> verdict;
-    int rc = verify_chunks(e, s, "L2RangeProof", range, 1, 1, g, nullptr, d_Vp3.as<p3_st>(), hV, h_proof, plen, keys, verdict);
+    std::vector<int> verdict; int bad = 0;
+    const int rc = verify_chunks(e, s, 1, range, 1, 1, g, nullptr, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), h_proof, plen, seed, DOM_L2_VERIFY, 0, verdict, d_bad.as<int>(), &bad);
+    if (bad) return -4;
     if (rc < 0) return rc;
     return verdict.empty() ? 0 : verdict[0];
 }

@@ -35,6 +35,7 @@
 #define KG_FOLD 1
 #define KG_SQUARE 1
 #define KG_BSGS 1
+#define KG_TS 1
 #endif
 
 // a point operand that is either a fixed generator (niels) or a variable point (p3)
@@ -983,6 +984,15 @@ KERNEL void LB(256, 2) k_split96(uint8_t *L, uint8_t *sq64, uint8_t *csq, const 
     ld_bytes32(b, in96 + 96 * i + 64); st_bytes32(sq64 + 64 * i + 32, b); st_bytes32(csq + 32 * i, b);
 }
 KLAUNCH(k_split96, false, (uint8_t *L, uint8_t *sq64, uint8_t *csq, const uint8_t *in96, size_t D), (L, sq64, csq, in96, D))
+// from_bytes validation of one column of compressed points inside fixed-width wire records: *bad = 1 if record i's 32 bytes at `offset` do
+// not decode (ElGamalPair::from_bytes, rand_proof/el_gamal.rs:112-123; SquareRandProofCommitments::from_bytes, square_rand_proof/pedersen.rs:33-45)
+KERNEL void LB(128, 2) k_validate_points(const uint8_t *rec, size_t stride, size_t offset, size_t D, int *bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    uint8_t b[32]; ld_bytes32(b, rec + stride * i + offset);
+    ge_p3 p; if (!ge_decompress(p, b)) atomicOr(bad, 1);
+}
+KLAUNCH(k_validate_points, false, (const uint8_t *rec, size_t stride, size_t offset, size_t D, int *bad), (rec, stride, offset, D, bad))
 // partial[blockIdx.x] = sum of this block's share of D compressed points (params.rs:267: enc_values.iter().map(|x| x.c_sq).sum())
 KERNEL void LB(128, 2) k_points_sum(p3_st *partial, const uint8_t *pts32, size_t D, int *bad) {
     __shared__ p3_st buf[128];
@@ -1030,6 +1040,7 @@ void launch_k_f32_to_scalar(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, con
 void launch_k_scalar_to_f32(dim3 g_, dim3 b_, cudaStream_t s_, float *out, const uint8_t *in, size_t D, int n_bits, int frac);
 void launch_k_l2_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, int *flags);
 void launch_k_join96(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out96, const uint8_t *pairs64, const uint8_t *sq64, size_t D);
+void launch_k_validate_points(dim3 g_, dim3 b_, cudaStream_t s_, const uint8_t *rec, size_t stride, size_t offset, size_t D, int *bad);
 void launch_k_split96(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *L, uint8_t *sq64, uint8_t *csq, const uint8_t *in96, size_t D);
 void launch_k_points_sum(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *partial, const uint8_t *pts32, size_t D, int *bad);
 void launch_k_crp_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, pow_tab ctab, int *flags);
@@ -1518,3 +1529,5 @@ KLAUNCH(k_niels_to_p3, false, (p3_st *Gf, p3_st *Hf, const niels_st *G, const ni
 #endif
 void launch_k_ipp_tail(dim3 g_, dim3 b_, cudaStream_t s_, tail_args a);
 void launch_k_niels_to_p3(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *Gf, p3_st *Hf, const niels_st *G, const niels_st *H, uint32_t F, uint32_t stride);
+
+#include "ts_kernels.cuh"

@@ -124,6 +124,7 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
         unsigned hc = std::thread::hardware_concurrency(); c->e.host_threads = hc ? (int)std::min(hc, 32u) : 8;
         c->e.gstreams.push_back(c->e.stream);
         for (int i = 1; i < 4; i++) { cudaStream_t st; rt_check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate"); c->e.gstreams.push_back(st); }
+        for (int i = 0; i < 4; i++) { cudaStream_t st; rt_check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate"); c->e.sstreams.push_back(st); }
         if (const char *gv = getenv("ROFL_GROUPS")) c->e.groups = std::max(1, std::min(4, atoi(gv)));
         if (const char *gv = getenv("ROFL_RT")) c->e.use_rt = atoi(gv);                                   // 0 disables the generator tables
         if (const char *gv = getenv("ROFL_UNFOLD")) c->e.rt_unfold = std::max(0, std::min(6, atoi(gv)));   // unfolded IPP rounds (RT path)
@@ -137,6 +138,6 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
 }
 extern "C" void rofl_ctx_destroy(rofl_ctx *c) {
     if (!c) return;
-    try { cudaSetDevice(c->e.device); engine_destroy(c->e); for (auto st : c->e.gstreams) cudaStreamDestroy(st); } catch (...) {}
+    try { cudaSetDevice(c->e.device); engine_destroy(c->e); for (auto st : c->e.gstreams) cudaStreamDestroy(st); for (auto st : c->e.sstreams) cudaStreamDestroy(st); } catch (...) {}
     delete c;
 }

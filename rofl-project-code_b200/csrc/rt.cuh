@@ -41,6 +41,7 @@ inline void rt_d2d(void *d, const void *s, size_t n, cudaStream_t) { memcpy(d, s
 inline void rt_memset(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); }
 inline void rt_sync(cudaStream_t) {}
 inline size_t rt_free_mem() { return (size_t)8 << 30; }
+inline void rt_stream_after(cudaStream_t, cudaStream_t) {}
 inline void *rt_host_alloc(size_t n) { return malloc(n ? n : 1); }
 inline void rt_set_device(int) {}
 inline void rt_host_free(void *p) { free(p); }
@@ -130,6 +131,13 @@ inline void rt_sync(cudaStream_t s) {
     }
 }
 inline size_t rt_free_mem() { size_t f = 0, t = 0; cudaMemGetInfo(&f, &t); return f; }
+// work queued on `waiter` from now on starts after everything queued on `producer` so far (fork / join of a side stream)
+inline void rt_stream_after(cudaStream_t waiter, cudaStream_t producer) {
+    if (waiter == producer) return;
+    cudaEvent_t ev; rt_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate");
+    rt_check(cudaEventRecord(ev, producer), "cudaEventRecord"); rt_check(cudaStreamWaitEvent(waiter, ev, 0), "cudaStreamWaitEvent");
+    cudaEventDestroy(ev);
+}
 inline void rt_set_device(int d) { rt_check(cudaSetDevice(d), "cudaSetDevice"); }     // the current device is per host thread
 inline void *rt_host_alloc(size_t n) { void *p = nullptr; rt_check(cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault), "cudaHostAlloc"); return p; }     // pinned: async copies really are async
 inline void rt_host_free(void *p) { if (p) cudaFreeHost(p); }

@@ -1,0 +1,366 @@
+// Device-side Fiat-Shamir: the Merlin / STROBE-128 transcripts of the Bulletproofs range proofs run on the GPU, so a whole
+// RangeProof::prove_multiple / verify_multiple (bulletproofs 4.0.0; call sites rofl_crypto/src/range_proof_vec/mod.rs:124-135,
+// 200-209) is ONE stream of kernel launches with no host round trip between its challenges.
+//   k_ts_absorbV : Transcript::new(label); rangeproof_domain_sep(n, m); append_point("V", V_j) for the m commitments of a chunk.
+//                  One warp per chunk: the 41*m stream bytes of a block of the sponge are generated in parallel (their STROBE
+//                  framing bytes are a closed form of the stream position) and Keccak-f[1600] runs with one lane per 64-bit word.
+//   k_ts_yz      : append A, S -> y, z (+ y^-1 and the 2^b-th power tables the polynomial kernels index)
+//   k_ts_t12     : t1 = <l0+l1, r0+r1> - t0 - t2
+//   k_ts_x       : append T_1, T_2 -> x;  t_x, t_x_blinding, e_blinding -> w;  innerproduct_domain_sep(N)
+//   k_ts_round   : append L, R -> u;  u^2, u^-2, u^-2 y^-n', running products, the coefficient tables of the unfolded / frozen
+//                  rounds and the digit strings the next generator kernel consumes
+//   k_ts_final   : a = a^ prod u_k, b = b^ prod u_k^-1 (proofs without the fused tail kernel)
+//   k_ts_verify / k_verify_keys / k_verify_prep : the verifier's replay, the Fiat-Shamir derivation of its batching scalars over ALL
+//                  chunks of the call, and the per-chunk scalar block of the batched check (kernels.cuh K7)
+// Included by kernels.cuh (kernel group KG_TS).
+#pragma once
+
+#ifdef ROFL_EMUL
+#define TS_WSYNC() __syncthreads()
+#else
+#define TS_WSYNC() __syncwarp()
+#endif
+#define TS_THREADS 32
+
+// gather form of rho + pi: B[d] = rotl(A[KC_SRC_[d]] ^ D[KC_SRC_[d] % 5], KC_ROT_[d])
+HASH_CONST uint8_t KC_SRC_[25] = {0, 6, 12, 18, 24, 3, 9, 10, 16, 22, 1, 7, 13, 19, 20, 4, 5, 11, 17, 23, 2, 8, 14, 15, 21};
+HASH_CONST uint8_t KC_ROT_[25] = {0, 44, 43, 21, 14, 28, 20, 3, 45, 61, 1, 6, 25, 8, 18, 27, 36, 10, 15, 56, 62, 55, 39, 41, 2};
+
+// STROBE state of one transcript in shared memory while a warp works on it
+struct strobe_sh { uint64_t st[25]; uint64_t C[5]; uint64_t B[25]; uint32_t pos, pos_begin; };
+
+#ifdef KG_TS
+// Keccak-f[1600], lane t < 25 owns word t; every lane of the warp must call
+DEV void keccak_coop(strobe_sh &h, int lane) {
+    const int x = lane % 5, row = lane - x;
+    const int src = lane < 25 ? KC_SRC_[lane] : 0, rot = lane < 25 ? KC_ROT_[lane] : 0, sx = src % 5;
+    for (int r = 0; r < 24; r++) {
+        if (lane < 5) h.C[lane] = h.st[lane] ^ h.st[lane + 5] ^ h.st[lane + 10] ^ h.st[lane + 15] ^ h.st[lane + 20];
+        TS_WSYNC();
+        if (lane < 25) {
+            const uint64_t v = h.st[src] ^ h.C[(sx + 4) % 5] ^ rotl64_(h.C[(sx + 1) % 5], 1);
+            h.B[lane] = rot ? rotl64_(v, rot) : v;
+        }
+        TS_WSYNC();
+        if (lane < 25) {
+            uint64_t v = h.B[lane] ^ (~h.B[row + (x + 1) % 5] & h.B[row + (x + 2) % 5]);
+            if (lane == 0) v ^= KECCAK_RC_[r];
+            h.st[lane] = v;
+        }
+        TS_WSYNC();
+    }
+}
+// m x Transcript::append_message(label (1 byte), 32-byte message) = per message the 41 stream bytes
+//   [pos_begin'] [M|A = 0x12] [label] [32 0 0 0]   [pos_begin''] [A = 0x02] [32 message bytes]
+// where the two pos_begin bytes are (begin position of the PREVIOUS operation) + 1 if that operation began in the current sponge
+// block and 0 otherwise (Strobe128::begin_op / run_f).  Byte k of the stream lands at absolute position A0 + k
+// (A0 = position at entry), so every byte is a function of k alone and the lanes fill a 166-byte block together.
+DEV void strobe_absorb_many_coop(strobe_sh &h, int lane, uint8_t label, const uint8_t *msgs, size_t m) {
+    if (m == 0) return;
+    const uint64_t A0 = h.pos, total = 41 * (uint64_t)m, A_end = A0 + total, nfull = A_end / STROBE_R;
+    const uint8_t pb0 = (uint8_t)h.pos_begin;
+    uint8_t *st8 = (uint8_t *)h.st;
+    for (uint64_t e = 0; e <= nfull; e++) {
+        for (uint32_t p = lane; p < STROBE_R; p += TS_THREADS) {
+            const uint64_t A = STROBE_R * e + p;
+            if (A < A0 || A >= A_end) continue;
+            const uint64_t k = A - A0, j = k / 41, a1 = A0 + 41 * j, a2 = a1 + 7; const uint32_t r = (uint32_t)(k % 41);
+            uint8_t b;
+            if (r == 0) { const uint64_t ap = a1 - 34; b = j == 0 ? pb0 : (ap / STROBE_R == a1 / STROBE_R ? (uint8_t)(ap % STROBE_R + 1) : 0); }
+            else if (r == 1) b = 0x12;
+            else if (r == 2) b = label;
+            else if (r == 3) b = 32;
+            else if (r < 7) b = 0;
+            else if (r == 7) b = a1 / STROBE_R == a2 / STROBE_R ? (uint8_t)(a1 % STROBE_R + 1) : 0;
+            else if (r == 8) b = 0x02;
+            else b = msgs[32 * j + (r - 9)];
+            st8[p] ^= b;
+        }
+        TS_WSYNC();
+        if (e < nfull) {                      // run_f closing block e: pos = 166, pos_begin = begin of the last operation if it lies in this block
+            if (lane == 0) {
+                const uint64_t last = STROBE_R * e + (STROBE_R - 1), k = last - A0, j = k / 41; const uint32_t r = (uint32_t)(k % 41);
+                const uint64_t a = A0 + 41 * j + (r >= 7 ? 7 : 0);
+                st8[STROBE_R] ^= a / STROBE_R == e ? (uint8_t)(a % STROBE_R + 1) : 0;
+                st8[STROBE_R + 1] ^= 0x04 ^ 0x80;
+            }
+            TS_WSYNC();
+            keccak_coop(h, lane);
+        }
+    }
+    if (lane == 0) {
+        const uint64_t a2l = A0 + 41 * (uint64_t)(m - 1) + 7;
+        h.pos = (uint32_t)(A_end % STROBE_R);
+        h.pos_begin = a2l / STROBE_R == A_end / STROBE_R ? (uint32_t)(a2l % STROBE_R + 1) : 0;
+    }
+    TS_WSYNC();
+}
+DEV bool is_zero32_(const uint8_t *b) { uint8_t z = 0; for (int i = 0; i < 32; i++) z |= b[i]; return z == 0; }
+DEV void ts_challenge_sc(transcript &t, const char *label, sc &out) { uint8_t b[64]; transcript_challenge(t, label, b, 64); sc_from_bytes_wide(out, b); }
+DEV void ts_append32(transcript &t, const char *label, const uint8_t *p) { transcript_append(t, label, p, 32); }
+#endif
+
+// ---- prover ----------------------------------------------------------------------------------------------------------------
+struct ts_absorb_args { transcript *ts; const uint8_t *V32; uint32_t m, n; int label_id; };       // label_id 0 "RangeProof", 1 "L2RangeProof"
+struct ts_yz_args { transcript *ts; const uint8_t *AS; uint8_t *proofs; uint32_t plen, C; sc_st *ypow2, *zpow2, *yinvpow2, *z; };
+struct ts_x_args { transcript *ts; const uint8_t *T12; uint8_t *proofs; uint32_t plen, C; const sc_st *tsum, *sums; sc_st *x, *w2; uint64_t N; };
+struct ts_round_args {
+    transcript *ts; const uint8_t *LR; uint8_t *proofs; uint32_t plen, off, C;
+    const sc_st *yinvpow2; int lgnp;
+    sc_st *u2, *uinv2, *up;                        // [C], [C], [2C] (prod u | prod u^-1)
+    sc_st *coefG, *coefH; uint32_t cstride, nblk;  // coefficient tables (nullable): c'[2t] = c[t], c'[2t+1] = c[t] s when 2 nblk <= cstride
+    int emit;                                      // 0 nothing, 1 width-FOLD_W NAFs of (u^2, u^-2 y^-n'), 2 table digits of the coefficients, 3 radix-16 digits of them
+    uint32_t rtK[9]; int rtc, rtnw;
+    int8_t *nafs; int16_t *digs16; int8_t *digs8;
+};
+struct ts_final_args { const sc_st *a, *b, *up; uint8_t *proofs; uint32_t plen, off, C; size_t N; };
+#ifdef KG_TS
+KERNEL void LB(TS_THREADS, 1) k_ts_absorbV(ts_absorb_args a) {
+    __shared__ strobe_sh h;
+    const int c = blockIdx.x, lane = threadIdx.x;
+    if (lane == 0) {
+        transcript t; transcript_init(t, a.label_id ? "L2RangeProof" : "RangeProof");
+        transcript_append(t, "dom-sep", (const uint8_t *)"rangeproof v1", 13);
+        transcript_append_u64(t, "n", (uint64_t)a.n); transcript_append_u64(t, "m", (uint64_t)a.m);
+        for (int i = 0; i < 25; i++) h.st[i] = t.st[i];
+        h.pos = t.pos; h.pos_begin = t.pos_begin;
+    }
+    TS_WSYNC();
+    strobe_absorb_many_coop(h, lane, (uint8_t)'V', a.V32 + 32 * (size_t)c * a.m, a.m);
+    if (lane < 25) a.ts[c].st[lane] = h.st[lane];
+    if (lane == 0) { a.ts[c].pos = (uint8_t)h.pos; a.ts[c].pos_begin = (uint8_t)h.pos_begin; a.ts[c].cur_flags = 2; }
+}
+KLAUNCH(k_ts_absorbV, true, (ts_absorb_args a), (a))
+KERNEL void LB(TS_THREADS, 1) k_ts_yz(ts_yz_args a) {
+    __shared__ sc_st sh[3];
+    const uint32_t c = blockIdx.x; const int lane = threadIdx.x;
+    if (lane == 0) {
+        transcript t = a.ts[c];
+        uint8_t A[32], S[32]; ld_bytes32(A, a.AS + 32 * (size_t)c); ld_bytes32(S, a.AS + 32 * (size_t)(a.C + c));
+        uint8_t *o = a.proofs + (size_t)a.plen * c; st_bytes32(o, A); st_bytes32(o + 32, S);
+        ts_append32(t, "A", A); ts_append32(t, "S", S);
+        sc y, z, yi; ts_challenge_sc(t, "y", y); ts_challenge_sc(t, "z", z); sc_invert_vartime(yi, y);
+        a.ts[c] = t;
+        st_sc(sh, y); st_sc(sh + 1, z); st_sc(sh + 2, yi); st_sc(a.z + c, z);
+    }
+    TS_WSYNC();
+    if (lane < 3) {
+        sc cur; ld_sc(cur, sh + lane);
+        sc_st *tab = (lane == 0 ? a.ypow2 : lane == 1 ? a.zpow2 : a.yinvpow2) + 32 * (size_t)c;
+        for (int b = 0; b < 32; b++) { st_sc(tab + b, cur); sc_mul(cur, cur, cur); }
+    }
+}
+KLAUNCH(k_ts_yz, true, (ts_yz_args a), (a))
+// t12[c] = t1 = tsum[C + c] - t0 - t2, t12[C + c] = t2     (tsum = t0 | <l0+l1, r0+r1> | t2, k_poly / k_sc_sum)
+KERNEL void k_ts_t12(sc_st *t12, const sc_st *tsum, uint32_t C) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    sc t0, tt, t2; ld_sc(t0, tsum + c); ld_sc(tt, tsum + C + c); ld_sc(t2, tsum + 2 * C + c);
+    sc_sub(tt, tt, t0); sc_sub(tt, tt, t2);
+    st_sc(t12 + c, tt); st_sc(t12 + C + c, t2);
+}
+KLAUNCH(k_ts_t12, false, (sc_st *t12, const sc_st *tsum, uint32_t C), (t12, tsum, C))
+KERNEL void LB(TS_THREADS, 1) k_ts_x(ts_x_args a) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x, C = a.C;
+    if (c >= C) return;
+    transcript t = a.ts[c];
+    uint8_t *o = a.proofs + (size_t)a.plen * c;
+    uint8_t T1[32], T2[32]; ld_bytes32(T1, a.T12 + 32 * (size_t)c); ld_bytes32(T2, a.T12 + 32 * (size_t)(C + c));
+    st_bytes32(o + 64, T1); st_bytes32(o + 96, T2);
+    ts_append32(t, "T_1", T1); ts_append32(t, "T_2", T2);
+    sc x, w; ts_challenge_sc(t, "x", x);
+    sc t0, t1, t2, sa, ss, st1, st2, szg, xx, tx, txb, eb, tmp;
+    ld_sc(t0, a.tsum + c); ld_sc(t1, a.tsum + C + c); ld_sc(t2, a.tsum + 2 * C + c); sc_sub(t1, t1, t0); sc_sub(t1, t1, t2);
+    ld_sc(sa, a.sums + c); ld_sc(ss, a.sums + C + c); ld_sc(st1, a.sums + 2 * C + c); ld_sc(st2, a.sums + 3 * C + c); ld_sc(szg, a.sums + 4 * C + c);
+    sc_mul(xx, x, x);
+    sc_mul(tmp, t1, x); sc_add(tx, t0, tmp); sc_mul(tmp, t2, xx); sc_add(tx, tx, tmp);
+    sc_mul(tmp, st1, x); sc_add(txb, szg, tmp); sc_mul(tmp, st2, xx); sc_add(txb, txb, tmp);
+    sc_mul(tmp, ss, x); sc_add(eb, sa, tmp);
+    uint8_t b[32];
+    sc_tobytes(b, tx); st_bytes32(o + 128, b); ts_append32(t, "t_x", b);
+    sc_tobytes(b, txb); st_bytes32(o + 160, b); ts_append32(t, "t_x_blinding", b);
+    sc_tobytes(b, eb); st_bytes32(o + 192, b); ts_append32(t, "e_blinding", b);
+    ts_challenge_sc(t, "w", w);
+    transcript_append(t, "dom-sep", (const uint8_t *)"ipp v1", 6); transcript_append_u64(t, "n", a.N);
+    a.ts[c] = t;
+    st_sc(a.x + c, x); st_sc(a.w2 + c, w); st_sc(a.w2 + C + c, w);
+}
+KLAUNCH(k_ts_x, false, (ts_x_args a), (a))
+KERNEL void LB(TS_THREADS, 1) k_ts_round(ts_round_args a) {
+    __shared__ sc_st sf[2];                                       // u^2 | u^-2 y^-n'
+    const uint32_t c = blockIdx.x, C = a.C; const int lane = threadIdx.x;
+    if (lane == 0) {
+        transcript t = a.ts[c];
+        uint8_t L[32], R[32]; ld_bytes32(L, a.LR + 32 * (size_t)c); ld_bytes32(R, a.LR + 32 * (size_t)(C + c));
+        uint8_t *o = a.proofs + (size_t)a.plen * c + a.off; st_bytes32(o, L); st_bytes32(o + 32, R);
+        ts_append32(t, "L", L); ts_append32(t, "R", R);
+        sc u, ui, u2, ui2, sH, yp, p; ts_challenge_sc(t, "u", u); sc_invert_vartime(ui, u);
+        a.ts[c] = t;
+        sc_mul(u2, u, u); sc_mul(ui2, ui, ui); ld_sc(yp, a.yinvpow2 + 32 * (size_t)c + a.lgnp); sc_mul(sH, ui2, yp);
+        st_sc(a.u2 + c, u2); st_sc(a.uinv2 + c, ui2); st_sc(sf, u2); st_sc(sf + 1, sH);
+        ld_sc(p, a.up + c); sc_mul(p, p, u); st_sc(a.up + c, p);
+        ld_sc(p, a.up + C + c); sc_mul(p, p, ui); st_sc(a.up + C + c, p);
+        if (a.emit == 1) { sc_naf(a.nafs + ((size_t)c * 2) * 256, u2, FOLD_W); sc_naf(a.nafs + ((size_t)c * 2 + 1) * 256, sH, FOLD_W); }
+    }
+    TS_WSYNC();
+    uint32_t nout = a.nblk;
+    if (a.coefG && 2 * a.nblk <= a.cstride) {
+        sc_st *g0 = a.coefG + (size_t)c * a.cstride, *h0 = a.coefH + (size_t)c * a.cstride;
+        // in place, highest block first inside a pass of 32: every lane reads its entries before any lane writes
+        for (uint32_t base = (a.nblk - 1) / TS_THREADS * TS_THREADS;; base -= TS_THREADS) {
+            const uint32_t t = base + lane; sc gt, ht;
+            if (t < a.nblk) { ld_sc(gt, g0 + t); ld_sc(ht, h0 + t); }
+            TS_WSYNC();
+            if (t < a.nblk) { sc f, x; st_sc(g0 + 2 * t, gt); ld_sc(f, sf); sc_mul(x, gt, f); st_sc(g0 + 2 * t + 1, x); st_sc(h0 + 2 * t, ht); ld_sc(f, sf + 1); sc_mul(x, ht, f); st_sc(h0 + 2 * t + 1, x); }
+            TS_WSYNC();
+            if (base == 0) break;
+        }
+        nout = 2 * a.nblk;
+    }
+    if (a.coefG && a.emit >= 2) {
+        for (uint32_t t = lane; t < 2 * nout; t += TS_THREADS) {
+            const uint32_t which = t / nout, i = t % nout;
+            sc v; ld_sc(v, (which ? a.coefH : a.coefG) + (size_t)c * a.cstride + i);
+            if (a.emit == 2) {
+                uint32_t xk[9]; msm_recode(xk, v, a.rtK); int16_t *d = a.digs16 + (((size_t)c * 2 + which) * nout + i) * RT_MAXW;
+                for (int w = 0; w < a.rtnw; w++) d[w] = (int16_t)msm_digit(xk, w, a.rtc);
+            } else sc_radix16(a.digs8 + (((size_t)c * 2 + which) * nout + i) * 64, v);
+        }
+    }
+}
+KLAUNCH(k_ts_round, true, (ts_round_args a), (a))
+KERNEL void k_ts_final(ts_final_args a) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.C) return;
+    sc x, y, p; ld_sc(x, a.a + (size_t)c * a.N); ld_sc(y, a.b + (size_t)c * a.N);
+    ld_sc(p, a.up + c); sc_mul(x, x, p); ld_sc(p, a.up + a.C + c); sc_mul(y, y, p);
+    uint8_t *o = a.proofs + (size_t)a.plen * c + a.off; uint8_t e[32];
+    sc_tobytes(e, x); st_bytes32(o, e); sc_tobytes(e, y); st_bytes32(o + 32, e);
+}
+KLAUNCH(k_ts_final, false, (ts_final_args a), (a))
+#endif
+void launch_k_ts_absorbV(dim3 g_, dim3 b_, cudaStream_t s_, ts_absorb_args a);
+void launch_k_ts_yz(dim3 g_, dim3 b_, cudaStream_t s_, ts_yz_args a);
+void launch_k_ts_t12(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *t12, const sc_st *tsum, uint32_t C);
+void launch_k_ts_x(dim3 g_, dim3 b_, cudaStream_t s_, ts_x_args a);
+void launch_k_ts_round(dim3 g_, dim3 b_, cudaStream_t s_, ts_round_args a);
+void launch_k_ts_final(dim3 g_, dim3 b_, cudaStream_t s_, ts_final_args a);
+
+// ---- verifier --------------------------------------------------------------------------------------------------------------
+// k_ts_verify: replay of RangeProof::verify_multiple's transcript for every chunk: challenges chal[c] = y z x w u_0..u_(lgN-1),
+//   bad[c] |= 1 when A, S, T_1, T_2, L_k or R_k is the identity encoding (validate_and_append_point), the chunk's small points
+//   sp32[c] = A S T1 T2 L.. R.. H B, and digest[c] = 32 challenge bytes drawn after a and b have been absorbed as well: the digest binds
+//   EVERY byte of the chunk's proof and commitments.
+// k_verify_keys: the batching scalars.  bulletproofs draws its per-proof scalar c from transcript.build_rng().finalize(thread_rng); here
+//   (c_i, rho_i) = ChaCha20(SHA3-256(SHA3-256(seed | C | digest_0 .. digest_(C-1)) | domain | chunk index)): a function of the verifier's
+//   seed AND of all proofs of the call, so that the random linear combination over chunks stays sound even for a known seed.
+// k_verify_prep: per-chunk scalar block of the batched check (layout: kernels.cuh K7)
+struct ts_verify_args { const transcript *ts; const uint8_t *proofs; uint32_t plen, C; int lgN; uint64_t N; sc_st *chal; uint8_t *digest; int *bad; uint8_t *sp32; uint8_t B32[32], H32[32]; };
+struct verify_keys_args { const uint8_t *digest; uint32_t C, dom; uint64_t c_off; uint8_t seed[32]; sc_st *ccrho; };       // ccrho[c] = c_c, ccrho[C + c] = rho_c
+struct verify_prep_args {
+    const uint8_t *proofs; uint32_t plen, C; int lgN, lgm, n; const sc_st *vch, *ccrho;
+    sc_st *chal; int chs; sc_st *small; int nsmall; sc_st *yinvpow2, *zpow2;
+};
+#ifdef KG_TS
+KERNEL void LB(TS_THREADS, 1) k_ts_verify(ts_verify_args a) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.C) return;
+    const int lgN = a.lgN, nsmall = 6 + 2 * lgN;
+    const uint8_t *p = a.proofs + (size_t)a.plen * c, *ipp = p + 224;
+    uint8_t *sp = a.sp32 + 32 * (size_t)c * nsmall;
+    sc_st *ch = a.chal + (size_t)c * (4 + lgN);
+    transcript t = a.ts[c];
+    uint8_t b[32]; int ok = 1; sc s;
+    ld_bytes32(b, p); ok &= !is_zero32_(b); st_bytes32(sp, b); ts_append32(t, "A", b);
+    ld_bytes32(b, p + 32); ok &= !is_zero32_(b); st_bytes32(sp + 32, b); ts_append32(t, "S", b);
+    ts_challenge_sc(t, "y", s); st_sc(ch, s); ts_challenge_sc(t, "z", s); st_sc(ch + 1, s);
+    ld_bytes32(b, p + 64); ok &= !is_zero32_(b); st_bytes32(sp + 64, b); ts_append32(t, "T_1", b);
+    ld_bytes32(b, p + 96); ok &= !is_zero32_(b); st_bytes32(sp + 96, b); ts_append32(t, "T_2", b);
+    ts_challenge_sc(t, "x", s); st_sc(ch + 2, s);
+    ld_bytes32(b, p + 128); ts_append32(t, "t_x", b); ld_bytes32(b, p + 160); ts_append32(t, "t_x_blinding", b); ld_bytes32(b, p + 192); ts_append32(t, "e_blinding", b);
+    ts_challenge_sc(t, "w", s); st_sc(ch + 3, s);
+    transcript_append(t, "dom-sep", (const uint8_t *)"ipp v1", 6); transcript_append_u64(t, "n", a.N);
+    for (int k = 0; k < lgN; k++) {
+        ld_bytes32(b, ipp + 64 * k); ok &= !is_zero32_(b); st_bytes32(sp + 32 * (4 + k), b); ts_append32(t, "L", b);
+        ld_bytes32(b, ipp + 64 * k + 32); ok &= !is_zero32_(b); st_bytes32(sp + 32 * (4 + lgN + k), b); ts_append32(t, "R", b);
+        ts_challenge_sc(t, "u", s); st_sc(ch + 4 + k, s);
+    }
+    st_bytes32(sp + 32 * (4 + 2 * lgN), a.H32); st_bytes32(sp + 32 * (5 + 2 * lgN), a.B32);
+    ld_bytes32(b, ipp + 64 * lgN); ts_append32(t, "a", b); ld_bytes32(b, ipp + 64 * lgN + 32); ts_append32(t, "b", b);
+    transcript_challenge(t, "rofl-batch", b, 32); st_bytes32(a.digest + 32 * (size_t)c, b);
+    if (!ok) a.bad[c] = 1;
+}
+KLAUNCH(k_ts_verify, false, (ts_verify_args a), (a))
+KERNEL void LB(256, 1) k_verify_keys(verify_keys_args a) {
+    __shared__ uint8_t glob[32];
+    if (threadIdx.x == 0) {
+        sponge s; sponge_init(s, 136); sponge_absorb(s, a.seed, 32);
+        uint8_t cb[8]; for (int i = 0; i < 8; i++) cb[i] = (uint8_t)((uint64_t)a.C >> (8 * i));
+        sponge_absorb(s, cb, 8);
+        for (uint32_t c = 0; c < a.C; c++) { uint8_t d[32]; ld_bytes32(d, a.digest + 32 * (size_t)c); sponge_absorb(s, d, 32); }
+        sponge_finish(s, 0x06); sponge_squeeze(s, glob, 32);
+    }
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < a.C; c += blockDim.x) {
+        uint8_t buf[44], key[32]; for (int i = 0; i < 32; i++) buf[i] = glob[i];
+        const uint64_t idx = a.c_off + c;
+        for (int i = 0; i < 4; i++) buf[32 + i] = (uint8_t)(a.dom >> (8 * i));
+        for (int i = 0; i < 8; i++) buf[36 + i] = (uint8_t)(idx >> (8 * i));
+        sha3_256(key, buf, 44);
+        uint32_t kw[8]; for (int i = 0; i < 8; i++) kw[i] = (uint32_t)key[4 * i] | ((uint32_t)key[4 * i + 1] << 8) | ((uint32_t)key[4 * i + 2] << 16) | ((uint32_t)key[4 * i + 3] << 24);
+        sc v; nonce_scalar(v, kw, 0); st_sc(a.ccrho + c, v); nonce_scalar(v, kw, 1); st_sc(a.ccrho + a.C + c, v);
+    }
+}
+KLAUNCH(k_verify_keys, true, (verify_keys_args a), (a))
+KERNEL void LB(TS_THREADS, 1) k_verify_prep(verify_prep_args a) {
+    __shared__ sc_st inv[34];                                     // y^-1, u_k^-1
+    const uint32_t c = blockIdx.x, C = a.C; const int lane = threadIdx.x, lgN = a.lgN;
+    const sc_st *vch = a.vch + (size_t)c * (4 + lgN);
+    if (lane == 0) {                                             // Montgomery's trick over y, u_0 .. u_(lgN-1) (zero, probability 2^-252, is replaced by 1)
+        sc pre[34], v[34], acc, one; sc_from_u64(one, 1); acc = one;
+        for (int i = 0; i <= lgN; i++) { ld_sc(v[i], i == 0 ? vch : vch + 3 + i); if (sc_iszero(v[i])) v[i] = one; pre[i] = acc; sc_mul(acc, acc, v[i]); }
+        sc iv; sc_invert_vartime(iv, acc);
+        for (int i = lgN; i >= 0; i--) { sc t; sc_mul(t, iv, pre[i]); sc_mul(iv, iv, v[i]); st_sc(inv + i, t); }
+    }
+    TS_WSYNC();
+    sc rho, cc; ld_sc(cc, a.ccrho + c); ld_sc(rho, a.ccrho + C + c);
+    sc_st *ch = a.chal + (size_t)c * a.chs, *sm = a.small + (size_t)c * a.nsmall;
+    if (lane == 1 || lane == 2) {
+        sc cur; ld_sc(cur, lane == 1 ? inv : vch + 1);
+        sc_st *tab = (lane == 1 ? a.yinvpow2 : a.zpow2) + 32 * (size_t)c;
+        for (int b = 0; b < 32; b++) { st_sc(tab + b, cur); sc_mul(cur, cur, cur); }
+    }
+    for (int k = lane - 3; k >= 0 && k < lgN; k += TS_THREADS - 3) {
+        sc u, ui, t; ld_sc(u, vch + 4 + k); ld_sc(ui, inv + 1 + k);
+        st_sc(ch + 5 + k, u); st_sc(ch + 5 + lgN + k, ui);
+        sc_mul(t, u, u); sc_mul(t, t, rho); st_sc(sm + 4 + k, t);
+        sc_mul(t, ui, ui); sc_mul(t, t, rho); st_sc(sm + 4 + lgN + k, t);
+    }
+    if (lane == 0) {
+        const uint8_t *p = a.proofs + (size_t)a.plen * c, *ipp = p + 224; uint8_t b32[32];
+        sc y, z, x, w, t_x, t_xb, e_bl, pa, pb, zz, tmp, tmp2, cx;
+        ld_sc(y, vch); ld_sc(z, vch + 1); ld_sc(x, vch + 2); ld_sc(w, vch + 3);
+        ld_bytes32(b32, p + 128); sc_frombytes(t_x, b32); ld_bytes32(b32, p + 160); sc_frombytes(t_xb, b32); ld_bytes32(b32, p + 192); sc_frombytes(e_bl, b32);
+        ld_bytes32(b32, ipp + 64 * lgN); sc_frombytes(pa, b32); ld_bytes32(b32, ipp + 64 * lgN + 32); sc_frombytes(pb, b32);
+        sc_mul(zz, z, z);
+        sc_mul(tmp, rho, z); st_sc(ch, tmp); sc_mul(tmp, rho, zz); st_sc(ch + 1, tmp);
+        sc_mul(tmp, rho, pa); st_sc(ch + 2, tmp); sc_mul(tmp, rho, pb); st_sc(ch + 3, tmp); st_sc(ch + 4, cc);
+        sc_mul(cx, cc, x);
+        st_sc(sm, rho); sc_mul(tmp, x, rho); st_sc(sm + 1, tmp); sc_mul(tmp, cx, rho); st_sc(sm + 2, tmp); sc_mul(tmp, cx, x); sc_mul(tmp, tmp, rho); st_sc(sm + 3, tmp);
+        sc_mul(tmp, cc, t_xb); sc_add(tmp, tmp, e_bl); sc_neg(tmp, tmp); sc_mul(tmp, tmp, rho); st_sc(sm + 4 + 2 * lgN, tmp);       // H: -e_bl - c t_x_bl
+        // delta = (z - zz) sum_{i<N} y^i - z^3 (2^n - 1) sum_{j<m} z^j ; sums of powers via prod (1 + s^(2^b))
+        sc one, sum_y, sum_z, pw, delta, s2; sc_from_u64(one, 1); sum_y = one; sum_z = one;
+        pw = y; for (int bb = 0; bb < lgN; bb++) { sc_add(tmp, one, pw); sc_mul(sum_y, sum_y, tmp); sc_mul(pw, pw, pw); }
+        pw = z; for (int bb = 0; bb < a.lgm; bb++) { sc_add(tmp, one, pw); sc_mul(sum_z, sum_z, tmp); sc_mul(pw, pw, pw); }
+        sc_from_u64(s2, a.n == 64 ? ~0ULL : ((1ULL << a.n) - 1));
+        sc_sub(delta, z, zz); sc_mul(delta, delta, sum_y);
+        sc_mul(tmp, zz, z); sc_mul(tmp, tmp, s2); sc_mul(tmp, tmp, sum_z); sc_sub(delta, delta, tmp);
+        sc_mul(tmp, pa, pb); sc_sub(tmp, t_x, tmp); sc_mul(tmp, w, tmp);                                              // w (t_x - a b)
+        sc_sub(tmp2, delta, t_x); sc_mul(tmp2, cc, tmp2); sc_add(tmp, tmp, tmp2); sc_mul(tmp, tmp, rho); st_sc(sm + 5 + 2 * lgN, tmp);      // B
+    }
+}
+KLAUNCH(k_verify_prep, true, (verify_prep_args a), (a))
+#endif
+void launch_k_ts_verify(dim3 g_, dim3 b_, cudaStream_t s_, ts_verify_args a);
+void launch_k_verify_keys(dim3 g_, dim3 b_, cudaStream_t s_, verify_keys_args a);
+void launch_k_verify_prep(dim3 g_, dim3 b_, cudaStream_t s_, verify_prep_args a);

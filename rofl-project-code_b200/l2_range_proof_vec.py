@@ -1,5 +1,5 @@
 """rofl_crypto::l2_range_proof_vec (l2_range_proof_vec/mod.rs:15-253)."""
-from . import fp, SEED0
+from . import fp
 
 
 class L2RangeProofError(Exception):
@@ -14,7 +14,7 @@ def _c():
     return context()
 
 
-def create_rangeproof_l2(value_vec_clipped, blinding_vec, prove_range, n_partition=1, seed=SEED0):
+def create_rangeproof_l2(value_vec_clipped, blinding_vec, prove_range, n_partition=1, seed=None):
     """-> (proof bytes, commitment 32 bytes)     (:15-140; n_partition is unused by the reference beyond min(1, .))"""
     rc, proof, commit = _c().l2_prove(value_vec_clipped, blinding_vec, prove_range, fp.N_BITS, fp.FRAC, seed)
     if rc:
@@ -22,7 +22,7 @@ def create_rangeproof_l2(value_vec_clipped, blinding_vec, prove_range, n_partiti
     return proof, commit
 
 
-def verify_rangeproof_l2(range_proof, commit, prove_range, seed=SEED0):         # :185-228
+def verify_rangeproof_l2(range_proof, commit, prove_range, seed=None):         # :185-228
     rc = _c().l2_verify(range_proof, commit, prove_range, seed)
     if rc < 0:
         raise L2RangeProofError(f"ProofError ({rc})")

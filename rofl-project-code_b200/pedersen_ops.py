@@ -1,7 +1,7 @@
 """rofl_crypto::pedersen_ops (pedersen_ops.rs:9-127) and the ElGamal right halves (rand_proof/el_gamal.rs:57-69).
 Points are (D, 32) uint8 arrays of compressed ristretto255 encodings, scalars (D, 32) little-endian."""
 import numpy as np
-from . import fp, SEED0
+from . import fp
 
 
 def _c():
@@ -41,7 +41,7 @@ def default_discrete_log_vec(rp_vec):                  # pedersen_ops.rs:27-35
     return discrete_log_vec_table(rp_vec, BSGSTable.default())
 
 
-def rnd_scalar_vec(length, seed=SEED0):                # pedersen_ops.rs:124-127 (seeded ChaCha20 instead of thread_rng)
+def rnd_scalar_vec(length, seed=None):                # pedersen_ops.rs:124-127 (seeded ChaCha20 instead of thread_rng)
     return _c().rnd_scalar_vec(seed, length)
 
 

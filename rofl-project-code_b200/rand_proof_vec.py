@@ -1,6 +1,6 @@
 """rofl_crypto::rand_proof_vec (rand_proof_vec/mod.rs:14-118): per-element ElGamal randomness proofs of the un-optimised range encoding
 (enc type 2).  RandProof = 128 bytes (C'_L | C'_R | z_m | z_r, rand_proof/mod.rs:87-97); ElGamalPair = 64 bytes (L | R)."""
-from . import fp, SEED0
+from . import fp
 
 
 class RandProofError(Exception):
@@ -12,7 +12,7 @@ def _c():
     return context()
 
 
-def create_randproof_vec(value_vec, random_vec, seed=SEED0):                                   # :14-49
+def create_randproof_vec(value_vec, random_vec, seed=None):                                   # :14-49
     if len(value_vec) != len(random_vec):
         raise RandProofError("WrongNumBlindingFactors")
     rc, proofs, pairs = _c().rand_prove(value_vec, None, random_vec, fp.N_BITS, fp.FRAC, seed)
@@ -21,7 +21,7 @@ def create_randproof_vec(value_vec, random_vec, seed=SEED0):                    
     return proofs, pairs
 
 
-def create_randproof_vec_existing(value_vec, existing_value_com_vec, random_vec, seed=SEED0):  # :51-89
+def create_randproof_vec_existing(value_vec, existing_value_com_vec, random_vec, seed=None):  # :51-89
     if len(value_vec) != len(random_vec):
         raise RandProofError("WrongNumBlindingFactors")
     rc, proofs, pairs = _c().rand_prove(value_vec, existing_value_com_vec, random_vec, fp.N_BITS, fp.FRAC, seed)

@@ -1,6 +1,6 @@
 """rofl_crypto::square_proof_vec (square_proof_vec/mod.rs:19-160).  SquareProof = 160 bytes
 (C'_l | C'_sq | z_m | z_r1 | z_r2, square_proof/mod.rs:118-125), SquareProofCommitments = 64 bytes (c_l | c_sq)."""
-from . import fp, SEED0
+from . import fp
 
 
 class L2RangeProofError(Exception):
@@ -12,7 +12,7 @@ def _c():
     return context()
 
 
-def create_l2rangeproof_vec_existing(value_vec, value_com_vec, random_vec, random_vec_2, seed=SEED0):      # :19-75
+def create_l2rangeproof_vec_existing(value_vec, value_com_vec, random_vec, random_vec_2, seed=None):      # :19-75
     if len(value_vec) != len(random_vec):
         raise L2RangeProofError("WrongNumBlindingFactors")
     rc, proofs, commits = _c().square_prove(value_vec, value_com_vec, random_vec, random_vec_2, fp.N_BITS, fp.FRAC, seed)

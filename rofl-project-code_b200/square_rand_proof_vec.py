@@ -1,7 +1,7 @@
 """rofl_crypto::square_rand_proof_vec (square_rand_proof_vec/mod.rs:18-160): per-element square + randomness proofs of the un-optimised L2
 encoding (enc type 3).  SquareRandProof = 192 bytes (C'.L | C'.R | C'_sq | z_m | z_r1 | z_r2, square_rand_proof/mod.rs:118-125);
 SquareRandProofCommitments = 96 bytes (c.L | c.R | c_sq, square_rand_proof/pedersen.rs:21-30)."""
-from . import fp, SEED0
+from . import fp
 
 
 class L2RangeProofError(Exception):
@@ -13,7 +13,7 @@ def _c():
     return context()
 
 
-def create_l2rangeproof_vec(value_vec, random_vec, random_vec_2, seed=SEED0):                              # :72-127
+def create_l2rangeproof_vec(value_vec, random_vec, random_vec_2, seed=None):                              # :72-127
     if len(value_vec) != len(random_vec):
         raise L2RangeProofError("WrongNumBlindingFactors")
     rc, proofs, commits = _c().square_rand_prove(value_vec, None, random_vec, random_vec_2, fp.N_BITS, fp.FRAC, seed)
@@ -22,7 +22,7 @@ def create_l2rangeproof_vec(value_vec, random_vec, random_vec_2, seed=SEED0):   
     return proofs, commits
 
 
-def create_l2rangeproof_vec_existing(value_vec, value_com_vec, random_vec, random_vec_2, seed=SEED0):      # :18-70
+def create_l2rangeproof_vec_existing(value_vec, value_com_vec, random_vec, random_vec_2, seed=None):      # :18-70
     if len(value_vec) != len(random_vec):
         raise L2RangeProofError("WrongNumBlindingFactors")
     rc, proofs, commits = _c().square_rand_prove(value_vec, value_com_vec, random_vec, random_vec_2, fp.N_BITS, fp.FRAC, seed)

@@ -64,7 +64,7 @@ def test_range_prove_errors(api, oracle):
     z = np.zeros((8, 32), np.uint8)
     assert api.range_prove(np.full(8, 1.5, np.float32), z, 8, 4, 16, 7)[0] == 2
     assert api.range_prove(np.zeros(8, np.float32), z, 8, 3, 16, 7)[0] == -99
-    assert api.range_prove(np.zeros(8, np.float32), z, 12, 4, 16, 7)[0] == -1
+    assert api.range_prove(np.zeros(8, np.float32), z, 12, 4, 16, 7)[0] == -7 == oracle.range_prove(np.zeros(8, np.float32), z, 12, 4, 16, 7)[0]
 
 
 def test_l2_and_square(api, oracle):
@@ -245,7 +245,7 @@ def test_optimised_encodings_end_to_end(api, oracle):
         bad = dict(m2); bad[field] = m2[field].copy()
         if i is None: bad[field][j] ^= 1
         else: bad[field][i, j] ^= 1
-        assert api.enc_l2_compressed_verify(bad, seed) == 0, field
+        assert api.enc_l2_compressed_verify(bad, seed) in (0, -4), field
 
 
 def test_unoptimised_encodings_end_to_end(api, oracle):
@@ -322,3 +322,54 @@ def test_rand_and_square_rand_proofs(api, oracle):
     assert api.square_rand_verify(sp, bad) == 0 and oracle.square_rand_verify(sp, bad) == 0
     badp = sp.copy(); badp[6, 160:] = 0xff
     assert api.square_rand_verify(badp, sc) == -1 and oracle.square_rand_verify(badp, sc) == -1
+
+
+def test_device_transcript_absorb_matches_sequential(api):
+    """ts_kernels.cuh k_ts_absorbV: the warp-cooperative absorb of m commitments (closed-form STROBE framing bytes, one lane per Keccak word)
+    against the sequential Merlin code, for every alignment of the 41-byte records against the 166-byte sponge rate."""
+    rng = np.random.default_rng(77)
+    for m in list(range(1, 48)) + [83, 166, 167, 331]:
+        V = rng.integers(0, 256, (m, 32), dtype=np.uint8)
+        assert api.debug_ts_absorb(V, 8 if m % 2 else 16, m % 2) == 0, m
+
+
+def test_verifier_weights_are_bound_to_every_proof_of_the_call(api, oracle):
+    """The batched verifier's scalars (c_i, rho_i) are Fiat-Shamir outputs over the seed AND all proofs / commitments of the call: changing any
+    chunk changes the weights of ALL chunks, so a prover who knows the seed still cannot craft chunks whose errors cancel (the reference
+    verifies chunk by chunk with thread_rng, range_proof_vec/mod.rs:178-190)."""
+    rng = np.random.default_rng(78)
+    D, P = 16, 4
+    v = rng.uniform(-0.9, 0.9, D).astype(np.float32); bl = oracle.rnd_scalar_vec(b"\x71" * 32, D)
+    rc, p, c = api.range_prove(v, bl, 8, P, 16, 7, b"\x72" * 32)
+    seed = bytes(32)                                               # a seed the attacker knows
+    ok, w0 = api.debug_verify_weights(p, c, 8, seed)
+    assert ok == 1 and len({w0[k, i].tobytes() for k in range(2) for i in range(P)}) == 2 * P
+    ok, w1 = api.debug_verify_weights(p, c, 8, seed)
+    assert (w1 == w0).all()                                        # deterministic
+    ok, w2 = api.debug_verify_weights(p, c, 8, b"\x01" * 32)
+    assert ok == 1 and all((w2[k, i] != w0[k, i]).any() for k in range(2) for i in range(P))
+    for what in ("proof_point", "proof_scalar", "commitment"):
+        pp, cc = p.copy(), c.copy()
+        if what == "proof_point": pp[P - 1, 224 + 3] ^= 1           # L_1 of the last chunk
+        elif what == "proof_scalar": pp[P - 1, -32] ^= 1            # b of the last chunk (stays canonical: low byte)
+        else: cc[D - 1] = c[0]
+        ok, w = api.debug_verify_weights(pp, cc, 8, seed)
+        assert ok in (0, 1)
+        assert all((w[k, i] != w0[k, i]).any() for k in range(2) for i in range(P)), what      # chunk 0's weights moved although only the last chunk changed
+
+
+def test_l2_compressed_message_with_undecodable_R_is_refused(api, oracle):
+    """decode_l2enc_vec (params.rs:560-571) deserialises c.L, c.R and c_sq of every record; EncL2Compressed::verify never looks at c.R again, so the
+    validation has to happen at the boundary (square_rand_proof/pedersen.rs:33-45, rand_proof/el_gamal.rs:112-123)."""
+    rng = np.random.default_rng(79)
+    D, P, seed = 6, 2, bytes([12] * 32)
+    v = (rng.integers(-24, 25, D) / 128).astype(np.float32); bl = oracle.rnd_scalar_vec(b"\x73" * 32, D)
+    rc, m = api.enc_l2_compressed_encrypt(v, bl, 8, P, 32, 32, 7, seed)
+    assert rc == 0 and api.enc_l2_compressed_verify(m, seed) == 1
+    for col in (0, 32, 64):
+        bad = dict(m); bad["enc_values"] = m["enc_values"].copy(); bad["enc_values"][D - 2, col:col + 32] = 0xff
+        assert not oracle.point_valid(bad["enc_values"][D - 2, col:col + 32])
+        assert api.enc_l2_compressed_verify(bad, seed) == -4, col
+    # a VALID but different R is not this arm's business (the reference does not check the rand proof here: params.rs:257-289)
+    ok = dict(m); ok["enc_values"] = m["enc_values"].copy(); ok["enc_values"][1, 32:64] = np.frombuffer(oracle.basepoint(), np.uint8)
+    assert api.enc_l2_compressed_verify(ok, seed) == 1

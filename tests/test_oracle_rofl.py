@@ -123,7 +123,7 @@ def test_rangeproof_out_of_range_and_bad_partition(oracle):    # :26-29 ValueOut
     rc, _, _ = oracle.range_prove(np.zeros(8, np.float32), np.zeros((8, 32), np.uint8), 8, 3, NB, FR)
     assert rc == -99
     rc, _, _ = oracle.range_prove(np.zeros(8, np.float32), np.zeros((8, 32), np.uint8), 12, 4, NB, FR)
-    assert rc == -1            # InvalidBitsize
+    assert rc == -7            # InvalidBitsize
 
 
 def test_rangeproof_cancelling_blindings(oracle):           # :369-399
