@@ -232,7 +232,7 @@ def main():
     if rank == 0:      # slow steps with an unchanged kernel sum = the GPU was waiting, not computing more slowly
         print("profiling pass per-step (step_ms, event-timed kernel ms of the instrumented families):", prof_steps, file=sys.stderr)
     torch.cuda.synchronize()
-    api.set_option("groups", 3)
+    api.set_option("groups", int(os.environ.get("BENCH_GROUPS", "3")))
     prof = dict(fold_ms=lib.rofl_prof_ms(0), msm_ms=lib.rofl_prof_ms(1), commit_ms=lib.rofl_prof_ms(2), rt_ms=lib.rofl_prof_ms(4), tail_ms=lib.rofl_prof_ms(5),
                 rt_launches=lib.rofl_prof_launches(4), rt_madds=lib.rofl_prof_work(4))
     lib.rofl_prof_enable(0)

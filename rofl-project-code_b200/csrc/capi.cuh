@@ -7,7 +7,7 @@
 struct rofl_ctx { rofl_engine e; };
 static thread_local std::string g_last_error;
 // every entry point may be called from any host thread: bind that thread to the context's GPU first
-#define API_TRY try { if (c) rt_set_device(c->e.device);
+#define API_TRY if (!c) return ROFL_ERR_ARGS; try { rt_set_device(c->e.device);
 #define API_CATCH } catch (const std::exception &ex) { g_last_error = ex.what(); return ROFL_ERR_CUDA; }
 
 extern "C" const char *rofl_last_error(void) { return g_last_error.c_str(); }
@@ -15,18 +15,16 @@ extern "C" void rofl_set_host_threads(rofl_ctx *c, int n) { if (c && n > 0) c->e
 extern "C" int rofl_set_option(rofl_ctx *c, const char *name, long value) {
     if (!c || !name) return ROFL_ERR_ARGS;
     try { rt_set_device(c->e.device); } catch (...) { return ROFL_ERR_CUDA; }
-    std::lock_guard<std::mutex> lk(c->e.mu);
     std::string n(name);
     if (n == "use_rt") c->e.use_rt = value != 0;
     else if (n == "rt_unfold") c->e.rt_unfold = (int)std::max<long>(0, std::min<long>(6, value));
-    else if (n == "groups") c->e.groups = (int)std::max<long>(1, std::min<long>((long)c->e.gstreams.size(), value));
-    else if (n == "rt_bits") {                                                                       // drops the cached tables: they are rebuilt at the new radix on next use
-        c->e.rt_bits = (int)std::max<long>(8, std::min<long>(RT_MAX_BITS, value));
-        rt_sync(c->e.stream);
-        for (auto &g : c->e.gens) { rt_free(g.second.RTG, c->e.stream); rt_free(g.second.RTH, c->e.stream); g.second.RTG = g.second.RTH = nullptr; g.second.rt_cap = 0; }
-    }
+    else if (n == "groups") c->e.groups = (int)std::max<long>(1, std::min<long>(ROFL_MAX_GROUPS, value));
+    else if (n == "rt_bits") { c->e.rt_bits = (int)std::max<long>(8, std::min<long>(RT_MAX_BITS, value)); engine_drop_rt(c->e); }      // the cached tables of the device are rebuilt at the new radix on next use
+    else if (n == "drop_tables") engine_drop_rt(c->e);
     else if (n == "frozen") c->e.use_frz = value != 0;
     else if (n == "tail_np") c->e.tail_np = (int)std::max<long>(0, std::min<long>(TAIL_MAX_F / 2, value));
+    else if (n == "rt_per") c->e.rt_per = (int)std::max<long>(0, std::min<long>(64, value));
+    else if (n == "max_lanes") c->e.max_lanes = (int)std::max<long>(1, std::min<long>(64, value));
     else return ROFL_ERR_ARGS;
     return ROFL_OK;
 }
@@ -55,7 +53,7 @@ struct staged_in { dev_buf b; staged_in(const void *h, size_t n, cudaStream_t s)
 extern "C" int rofl_field_selftest(rofl_ctx *c, const uint8_t *a32, const uint8_t *b32, size_t n, uint8_t *out) {
     API_TRY
     if (!n) return 0;
-    std::lock_guard<std::mutex> lk(c->e.mu); cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in da(a32, 32 * n, s), db(b32, 32 * n, s); dev_buf o(192 * n, s);
     LAUNCH(k_field_selftest, dim3((unsigned)((n + 127) / 128)), dim3(128), s, o.as<uint8_t>(), da.b.as<uint8_t>(), db.b.as<uint8_t>(), n);
     rt_d2h(out, o.p, 192 * n, s); rt_sync(s);
@@ -66,7 +64,7 @@ extern "C" int rofl_f32_to_scalar_vec(rofl_ctx *c, const float *v, size_t D, int
     API_TRY
     if (!fp_ok(n_bits, frac)) return ROFL_ERR_ARGS;
     if (!D) return 0;
-    std::lock_guard<std::mutex> lk(c->e.mu); cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dv(v, 4 * D, s); dev_buf o(32 * D, s), fl(sizeof(int), s); rt_memset(fl.p, 0, sizeof(int), s);
     LAUNCH(k_f32_to_scalar, dim3((unsigned)((D + 255) / 256)), dim3(256), s, o.as<uint8_t>(), dv.b.as<float>(), D, n_bits, frac, fl.as<int>());
     int f = 0; rt_d2h(out, o.p, 32 * D, s); rt_d2h(&f, fl.p, sizeof(int), s); rt_sync(s);
@@ -77,7 +75,7 @@ extern "C" int rofl_scalar_to_f32_vec(rofl_ctx *c, const uint8_t *sc32, size_t D
     API_TRY
     if (!fp_ok(n_bits, frac)) return ROFL_ERR_ARGS;
     if (!D) return 0;
-    std::lock_guard<std::mutex> lk(c->e.mu); cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in ds(sc32, 32 * D, s); dev_buf o(4 * D, s);
     LAUNCH(k_scalar_to_f32, dim3((unsigned)((D + 255) / 256)), dim3(256), s, o.as<float>(), ds.b.as<uint8_t>(), D, n_bits, frac);
     rt_d2h(out, o.p, 4 * D, s); rt_sync(s);
@@ -90,7 +88,7 @@ extern "C" int rofl_commit_dev(rofl_ctx *c, const float *v, const uint8_t *blind
 extern "C" int rofl_commit(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, uint8_t *L, uint8_t *R) {
     API_TRY
     if (!D) return 0;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dv(v, 4 * D, s), db(blind, blind ? 32 * D : 0, s); dev_buf dL(32 * D, s), dR(32 * D, s);
     int rc = engine_commit(c->e, dv.b.as<float>(), blind ? db.b.as<uint8_t>() : nullptr, D, n_bits, frac, dL.as<uint8_t>(), (R && blind) ? dR.as<uint8_t>() : nullptr);
     if (rc) return rc;
@@ -111,7 +109,7 @@ extern "C" int rofl_range_prove(rofl_ctx *c, const float *v, const uint8_t *blin
                                 uint8_t *proofs, size_t *plen, size_t *np, uint8_t *commits) {
     API_TRY
     if (!D) return ROFL_ERR_ARGS;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dv(v, 4 * D, s), db(blind, 32 * D, s); dev_buf dC(32 * D, s);
     size_t a = 0, b = 0;
     int rc = engine_range_prove(c->e, dv.b.as<float>(), db.b.as<uint8_t>(), D, range, P, n_bits, frac, seed, proofs, &a, &b, dC.as<uint8_t>());
@@ -127,7 +125,8 @@ extern "C" int rofl_range_verify_dev(rofl_ctx *c, const uint8_t *proofs, size_t 
 extern "C" int rofl_range_verify(rofl_ctx *c, const uint8_t *proofs, size_t plen, size_t np, const uint8_t *commits, size_t D, int range, const uint8_t seed[32]) {
     API_TRY
     if (!D) return ROFL_ERR_ARGS;
-    staged_in dc(commits, 32 * D, c->e.stream);
+    lane_guard lg(c->e);
+    staged_in dc(commits, 32 * D, lg.s());
     return engine_range_verify(c->e, proofs, plen, np, dc.b.as<uint8_t>(), D, range, seed);
     API_CATCH
 }
@@ -135,7 +134,7 @@ extern "C" int rofl_range_verify(rofl_ctx *c, const uint8_t *proofs, size_t plen
 extern "C" int rofl_range_prove_shard(rofl_ctx *c, const float *v, const uint8_t *blind, size_t D_shard, size_t chunk_len, size_t chunk_begin, size_t n_chunks, int range,
                                       int n_bits, int frac, const uint8_t seed[32], uint8_t *proofs, size_t *plen, uint8_t *commits) {
     API_TRY
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dv(v, 4 * D_shard, s), db(blind, 32 * D_shard, s); dev_buf dC(32 * (D_shard ? D_shard : 1), s);
     shard_spec sh = {chunk_len, chunk_begin, n_chunks};
     size_t a = 0, b = 0;
@@ -150,7 +149,8 @@ extern "C" int rofl_range_prove_shard(rofl_ctx *c, const float *v, const uint8_t
 extern "C" int rofl_range_verify_shard(rofl_ctx *c, const uint8_t *proofs, size_t plen, size_t n_chunks, const uint8_t *commits, size_t D_shard, size_t chunk_len, size_t chunk_begin,
                                        int range, const uint8_t seed[32]) {
     API_TRY
-    staged_in dc(commits, 32 * D_shard, c->e.stream);
+    lane_guard lg(c->e);
+    staged_in dc(commits, 32 * D_shard, lg.s());
     shard_spec sh = {chunk_len, chunk_begin, n_chunks};
     return engine_range_verify(c->e, proofs, plen, n_chunks, dc.b.as<uint8_t>(), D_shard, range, seed, &sh);
     API_CATCH
@@ -159,7 +159,7 @@ extern "C" int rofl_l2_prove(rofl_ctx *c, const float *v, const uint8_t *blind, 
                              uint8_t *proof, size_t *plen, uint8_t *commit) {
     API_TRY
     if (!D) return ROFL_ERR_ARGS;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dv(v, 4 * D, s), db(blind, 32 * D, s);
     size_t a = 0;
     int rc = engine_l2_prove(c->e, v, dv.b.as<float>(), db.b.as<uint8_t>(), D, range, n_bits, frac, seed, proof, &a, commit);
@@ -175,7 +175,7 @@ static int sigma_prove_host(rofl_ctx *c, int kind, const float *v, const uint8_t
                             uint8_t *proofs, uint8_t *commits) {
     if (!D) return 0;
     const size_t pw = kind == 1 ? 128 : 192, cw = kind == 1 ? 64 : 96;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dv(v, 4 * D, s), dvc(vc, vc ? 32 * D : 0, s), d1(r1, 32 * D, s), d2(r2, r2 ? 32 * D : 0, s); dev_buf dp(pw * D, s), dc(cw * D, s);
     int rc = engine_sigma_prove(c->e, kind, dv.b.as<float>(), vc ? dvc.b.as<uint8_t>() : nullptr, d1.b.as<uint8_t>(), r2 ? d2.b.as<uint8_t>() : nullptr, D, n_bits, frac, seed, dp.as<uint8_t>(), dc.as<uint8_t>());
     if (rc) return rc;
@@ -185,7 +185,8 @@ static int sigma_prove_host(rofl_ctx *c, int kind, const float *v, const uint8_t
 static int sigma_verify_host(rofl_ctx *c, int kind, const uint8_t *proofs, const uint8_t *commits, size_t D) {
     if (!D) return 1;
     const size_t pw = kind == 1 ? 128 : 192, cw = kind == 1 ? 64 : 96;
-    staged_in dp(proofs, pw * D, c->e.stream), dc(commits, cw * D, c->e.stream);
+    lane_guard lg(c->e);
+    staged_in dp(proofs, pw * D, lg.s()), dc(commits, cw * D, lg.s());
     return engine_sigma_verify(c->e, kind, dp.b.as<uint8_t>(), dc.b.as<uint8_t>(), D);
 }
 extern "C" int rofl_rand_prove(rofl_ctx *c, const float *v, const uint8_t *value_com32, const uint8_t *blind32, size_t D, int n_bits, int frac, const uint8_t seed[32],
@@ -204,7 +205,7 @@ extern "C" int rofl_enc_range_compressed_encrypt(rofl_ctx *c, const float *v, co
                                                  const uint8_t seed[32], uint8_t *enc_values64, uint8_t *rand_proof128, uint8_t *range_proofs, size_t *plen, size_t *n_proofs) {
     API_TRY
     if (!D) return ROFL_ERR_ARGS;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     std::vector<float> clipped(D); rofl_clip_f32_to_range_vec(v, D, prove_range, n_bits, frac, clipped.data());                 // :709
     staged_in dv(clipped.data(), 4 * D, s), db(blind, 32 * D, s); dev_buf dC(32 * D, s);
     size_t a = 0, b = 0;
@@ -225,7 +226,7 @@ extern "C" int rofl_enc_range_compressed_verify(rofl_ctx *c, const uint8_t *enc_
     if (ok != 1) return 0;
     const size_t num = (size_t)llroundf((float)D * check_percentage);                                                                   // :243-244
     if (num == 0 || num > D) return 0;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dp(enc_values64, 64 * D, s); dev_buf dL(32 * D, s), dR(32 * D, s);
     LAUNCH(k_pairs_split, dim3((unsigned)((D + 255) / 256)), dim3(256), s, dL.as<uint8_t>(), dR.as<uint8_t>(), dp.b.as<uint8_t>(), D);
     int rr = engine_range_verify(c->e, range_proofs, plen, n_proofs, dL.as<uint8_t>(), num, prove_range, seed);
@@ -239,7 +240,7 @@ extern "C" int rofl_enc_l2_compressed_encrypt(rofl_ctx *c, const float *v, const
                                               size_t *n_proofs, uint8_t *square_range_proof, size_t *sq_plen) {
     API_TRY
     if (!D) return ROFL_ERR_ARGS;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     std::vector<float> clipped(D); rofl_clip_f32_to_range_vec(v, D, prove_range, n_bits, frac, clipped.data());                 // :806
     std::vector<uint8_t> rnd(32 * D); { uint8_t k2[32]; derive_key(k2, seed, DOM_RND_VEC, 1); rofl_rnd_scalar_vec(k2, D, rnd.data()); }   // rand_scalars (:805)
     staged_in dv(clipped.data(), 4 * D, s), db(blind, 32 * D, s), dr(rnd.data(), 32 * D, s); dev_buf dC(32 * D, s), dPairs(64 * D, s), dSp(160 * D, s), dSc(64 * D, s), dEnc(96 * D, s);
@@ -268,7 +269,7 @@ extern "C" int rofl_enc_l2_compressed_verify(rofl_ctx *c, const uint8_t *enc_val
                                              size_t n_proofs, const uint8_t *square_range_proof, size_t sq_plen, int prove_range, int l2_range, const uint8_t seed[32]) {
     API_TRY
     if (!D || !n_proofs) return ROFL_ERR_ARGS;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in de(enc_values96, 96 * D, s), dsp(square_proofs160, 160 * D, s); dev_buf dL(32 * D, s), dSc(64 * D, s), dCsq(32 * D, s), dbad(sizeof(int), s);
     // decode_l2enc_vec (params.rs:560-571): every record must deserialise -- c.L, c_sq and also c.R, which this arm never uses afterwards
     // (SquareRandProofCommitments::from_bytes -> ElGamalPair::from_bytes; the reference unwrap()s = panics, here the message is refused with ROFL_ERR_POINT)
@@ -295,7 +296,7 @@ extern "C" int rofl_enc_range_encrypt(rofl_ctx *c, const float *v, const uint8_t
                                       const uint8_t seed[32], uint8_t *enc_values64, uint8_t *rand_proofs128, uint8_t *range_proofs, size_t *plen, size_t *n_proofs) {
     API_TRY
     if (!D) return ROFL_ERR_ARGS;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     std::vector<float> clipped(D); rofl_clip_f32_to_range_vec(v, D, prove_range, n_bits, frac, clipped.data());                 // :475
     const bool all = check_percentage >= 1.0f;
     const size_t num = all ? D : (size_t)llroundf((float)D * check_percentage);                                                 // :487
@@ -316,7 +317,7 @@ extern "C" int rofl_enc_range_verify(rofl_ctx *c, const uint8_t *enc_values64, s
                                      int prove_range, float check_percentage, const uint8_t seed[32]) {
     API_TRY
     if (!D || !n_proofs) return ROFL_ERR_ARGS;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dp(enc_values64, 64 * D, s), dpf(rand_proofs128, 128 * D, s); dev_buf dL(32 * D, s), dR(32 * D, s);
     const int ok = engine_sigma_verify(c->e, 1, dpf.b.as<uint8_t>(), dp.b.as<uint8_t>(), D);
     if (ok < 0) return 0;                                                                                                      // Err(_) -> false
@@ -334,7 +335,7 @@ extern "C" int rofl_enc_l2_encrypt(rofl_ctx *c, const float *v, const uint8_t *b
                                    uint8_t *square_range_proof, size_t *sq_plen) {
     API_TRY
     if (!D) return ROFL_ERR_ARGS;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     std::vector<float> clipped(D); rofl_clip_f32_to_range_vec(v, D, prove_range, n_bits, frac, clipped.data());                 // :616
     std::vector<uint8_t> rnd(32 * D); { uint8_t k2[32]; derive_key(k2, seed, DOM_RND_VEC, 1); rofl_rnd_scalar_vec(k2, D, rnd.data()); }   // rand_scalars (:615)
     staged_in dv(clipped.data(), 4 * D, s), db(blind, 32 * D, s), dr(rnd.data(), 32 * D, s); dev_buf dC(32 * D, s), dP(192 * D, s), dE(96 * D, s);
@@ -357,7 +358,7 @@ extern "C" int rofl_enc_l2_verify(rofl_ctx *c, const uint8_t *enc_values96, size
                                   const uint8_t *square_range_proof, size_t sq_plen, int prove_range, int l2_range, const uint8_t seed[32]) {
     API_TRY
     if (!D || !n_proofs) return ROFL_ERR_ARGS;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in de(enc_values96, 96 * D, s), dsp(square_proofs192, 192 * D, s); dev_buf dL(32 * D, s), dSc(64 * D, s), dCsq(32 * D, s);
     const int ok = engine_sigma_verify(c->e, 2, dsp.b.as<uint8_t>(), de.b.as<uint8_t>(), D);
     if (ok < 0) return 0;
@@ -377,7 +378,7 @@ extern "C" int rofl_square_prove_dev(rofl_ctx *c, const float *v, const uint8_t 
 extern "C" int rofl_crp_prove(rofl_ctx *c, const float *v, const uint8_t *value_com32, const uint8_t *blind, size_t D, int n_bits, int frac, const uint8_t seed[32],
                               uint8_t *proof128, uint8_t *pairs64) {
     API_TRY
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dv(v, 4 * D, s), db(blind, 32 * D, s), dc(value_com32, value_com32 ? 32 * D : 0, s);
     return engine_crp_prove(c->e, dv.b.as<float>(), value_com32 ? dc.b.as<uint8_t>() : nullptr, db.b.as<uint8_t>(), D, n_bits, frac, seed, proof128, pairs64);
     API_CATCH
@@ -389,7 +390,7 @@ extern "C" int rofl_square_prove(rofl_ctx *c, const float *v, const uint8_t *vc,
                                  const uint8_t seed[32], uint8_t *proofs, uint8_t *commits) {
     API_TRY
     if (!D) return 0;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dv(v, 4 * D, s), dvc(vc, 32 * D, s), d1(r1, 32 * D, s), d2(r2, 32 * D, s); dev_buf dp(160 * D, s), dc(64 * D, s);
     int rc = engine_square_prove(c->e, dv.b.as<float>(), dvc.b.as<uint8_t>(), d1.b.as<uint8_t>(), d2.b.as<uint8_t>(), D, n_bits, frac, seed, dp.as<uint8_t>(), dc.as<uint8_t>());
     if (rc) return rc;
@@ -403,7 +404,7 @@ extern "C" int rofl_square_verify_dev(rofl_ctx *c, const uint8_t *proofs, const 
 extern "C" int rofl_square_verify(rofl_ctx *c, const uint8_t *proofs, const uint8_t *commits, size_t D) {
     API_TRY
     if (!D) return 1;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dp(proofs, 160 * D, s), dc(commits, 64 * D, s);
     return engine_square_verify(c->e, dp.b.as<uint8_t>(), dc.b.as<uint8_t>(), D);
     API_CATCH
@@ -414,7 +415,7 @@ extern "C" int rofl_aggregate_dev(rofl_ctx *c, const uint8_t *pts, size_t nc, si
 extern "C" int rofl_aggregate(rofl_ctx *c, const uint8_t *pts, size_t nc, size_t D, int init, uint8_t *out) {
     API_TRY
     if (!D) return 0;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dp(pts, 32 * nc * D, s); dev_buf o(32 * D, s);
     int rc = engine_aggregate(c->e, dp.b.as<uint8_t>(), nc, D, init, o.as<uint8_t>());
     if (rc) return rc;
@@ -428,7 +429,7 @@ extern "C" int rofl_dlog_dev(rofl_ctx *c, const uint8_t *pts, size_t D, uint64_t
 extern "C" int rofl_dlog(rofl_ctx *c, const uint8_t *pts, size_t D, uint64_t ts, int bb, int n_bits, int frac, uint8_t *osc, float *of) {
     API_TRY
     if (!D) return 0;
-    cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dp(pts, 32 * D, s); dev_buf o(32 * D, s), f(4 * D, s);
     int rc = engine_dlog(c->e, dp.b.as<uint8_t>(), D, ts, bb, n_bits, frac, o.as<uint8_t>(), f.as<float>());
     if (osc) rt_d2h(osc, o.p, 32 * D, s); if (of) rt_d2h(of, f.p, 4 * D, s); rt_sync(s);
@@ -440,7 +441,7 @@ extern "C" int rofl_dlog(rofl_ctx *c, const uint8_t *pts, size_t D, uint64_t ts,
 // the warp-cooperative V absorb (ts_kernels.cuh, k_ts_absorbV) against the sequential transcript code for the same m commitments: 0 equal, 1 different
 extern "C" int rofl_debug_ts_absorb(rofl_ctx *c, const uint8_t *V32, size_t m, int n, int label_id) {
     API_TRY
-    std::lock_guard<std::mutex> lk(c->e.mu); cudaStream_t s = c->e.stream;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
     staged_in dv(V32, 32 * m, s); dev_buf d_ts(sizeof(transcript), s);
     ts_absorb_args aa = {}; aa.ts = d_ts.as<transcript>(); aa.V32 = dv.b.as<uint8_t>(); aa.m = (uint32_t)m; aa.n = (uint32_t)n; aa.label_id = label_id;
     LAUNCH_COOP(k_ts_absorbV, dim3(1), dim3(TS_THREADS), s, aa);
@@ -456,7 +457,8 @@ extern "C" int rofl_debug_ts_absorb(rofl_ctx *c, const uint8_t *V32, size_t m, i
 extern "C" int rofl_debug_verify_weights(rofl_ctx *c, const uint8_t *proofs, size_t plen, size_t np, const uint8_t *commits, size_t D, int range, const uint8_t seed[32], uint8_t *out_weights) {
     API_TRY
     if (!D) return ROFL_ERR_ARGS;
-    staged_in dc(commits, 32 * D, c->e.stream);
+    lane_guard lg(c->e);
+    staged_in dc(commits, 32 * D, lg.s());
     return engine_range_verify(c->e, proofs, plen, np, dc.b.as<uint8_t>(), D, range, seed, nullptr, out_weights);
     API_CATCH
 }

@@ -11,6 +11,8 @@
 #include "rt.cuh"
 #include <map>
 #include <mutex>
+#include <shared_mutex>
+#include <condition_variable>
 #include <thread>
 #include <atomic>
 #ifndef ROFL_EMUL
@@ -25,29 +27,80 @@ enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE =
 enum { PROF_FOLD = 0, PROF_MSM = 1, PROF_COMMIT = 2, PROF_SQUARE = 3, PROF_RTMSM = 4, PROF_TAIL = 5, PROF_FRZ = 6, PROF_SLOTS = 8 };
 
 struct gens_entry { int n = 0; int cap = 0; niels_st *G = nullptr, *H = nullptr;
-                    int rt_cap = 0, rt_c = 8; niels_st *RTG = nullptr, *RTH = nullptr; };     // radix-2^rt_c tables (RT path)
+                    int rt_cap = 0, rt_c = 8; niels_st *RTG = nullptr, *RTH = nullptr; size_t rt_bytes = 0; uint64_t last_use = 0; };     // radix-2^rt_c tables (RT path)
 struct bsgs_entry { unsigned long long *keys = nullptr; uint32_t *vals = nullptr; uint32_t cap = 0; uint64_t size = 0; };
-struct rofl_engine {
-    int device = 0;
-    cudaStream_t stream = 0;
+// Everything that is a function of the DEVICE alone lives once per device and process and is shared by all contexts on it: the fixed-base
+// tables of B / B_blinding, the Bulletproofs generators, their radix-2^c tables (tens of GB) and the BSGS tables (server.rs:54,84 shares one
+// Arc<BSGSTable> between its workers the same way).  tab_mu: calls hold it SHARED while they use cached tables; building, regrowing or
+// dropping a table takes it EXCLUSIVE, i.e. waits until no call is using the old arrays.
+struct dev_shared {
+    int device = 0, refs = 0;
     niels_st *tabB = nullptr, *tabH = nullptr;
     uint8_t B32[32], H32[32];
     std::map<int, gens_entry> gens;
     std::map<std::pair<uint64_t, int>, bsgs_entry> bsgs;
-    std::mutex mu;
+    std::shared_mutex tab_mu;
+    std::atomic<size_t> free_hint{0};     // free device memory when the generator tables were last (re)built: cudaMemGetInfo is NOT for the hot path
+    std::atomic<uint64_t> clock{0};       // LRU stamps of the generator tables
+};
+struct tables_use {
+    dev_shared &sh; bool excl = false;
+    explicit tables_use(dev_shared &s) : sh(s) { sh.tab_mu.lock_shared(); }
+    ~tables_use() { if (excl) sh.tab_mu.unlock(); else sh.tab_mu.unlock_shared(); }
+    // not atomic: re-check the condition after it.  There is no way back to shared (that would open a second gap in which another caller
+    // could evict what was just built): a call that had to build a table keeps the device's tables to itself until it returns.
+    void upgrade() { if (!excl) { sh.tab_mu.unlock_shared(); sh.tab_mu.lock(); excl = true; } }
+    tables_use(const tables_use &) = delete; tables_use &operator=(const tables_use &) = delete;
+};
+// A lane = the streams one caller works on: per chunk group a queue (high-priority stream for the latency-bound Fiat-Shamir chain, normal
+// stream for the bulk kernels, rt.cuh `chain`) and a side stream.  Concurrent callers of one context (rofl_service runs one verify() per
+// client on a rayon pool, server.rs:516-522,666) get different lanes, i.e. run on different streams; the cached tables are shared.
+#define ROFL_MAX_GROUPS 4
+struct lane { chain q[ROFL_MAX_GROUPS]; cudaStream_t side[ROFL_MAX_GROUPS]; bool busy = false; };
+struct rofl_engine {
+    int device = 0;
+    dev_shared *sh = nullptr;
+    std::mutex lane_mu; std::condition_variable lane_cv; std::vector<lane *> lanes; int max_lanes = 8;
     int host_threads = 8;
-    int groups = 3;                       // chunk groups proved / verified concurrently on separate streams (hides per-round latency)
-    std::vector<cudaStream_t> gstreams;   // gstreams[0] == stream
-    std::vector<cudaStream_t> sstreams;   // side stream of every group stream (work that runs beside the group's main sequence)
-    cudaStream_t side_for(cudaStream_t gs) const { for (size_t i = 0; i < gstreams.size() && i < sstreams.size(); i++) if (gstreams[i] == gs) return sstreams[i]; return gs; }
+    int groups = 3;                       // chunk groups proved concurrently on separate queues (the latency-bound chain of one overlaps the bulk kernels of the others)
     int use_rt = 1;                       // 0: never build generator tables (generic Pippenger / fold path only)
     int rt_unfold = 4;                    // IPP rounds computed over the original generators before the catch-up fold
     int tail_np = 32;                     // IPP rounds with half-size <= tail_np run in the fused on-device tail kernel (0 = off)
-    std::mutex pin_mu; std::vector<std::pair<void *, size_t>> pins;      // pool of pinned host blocks for the per-round exchanges
+    std::mutex pin_mu; std::vector<std::pair<void *, size_t>> pins;      // pool of pinned host blocks
     int use_frz = 1;                      // middle IPP rounds over frozen generators with on-the-fly Straus tables (kernels.cuh K6c)
-    std::atomic<size_t> free_hint{0};     // free device memory when the generator tables were last (re)built: cudaMemGetInfo is NOT for the hot path
     int rt_bits = RT_MAX_BITS;            // widest generator-table radix to try (8..11)
+    int rt_per = 2;                       // table-MSM terms per thread and block: short blocks let the other groups' small kernels in quickly
     double rt_mem_frac = 0.45;            // tables may take this fraction of the free device memory
+};
+static thread_local lane *tl_lane = nullptr; static thread_local rofl_engine *tl_lane_engine = nullptr; static thread_local int tl_lane_depth = 0;
+static inline lane *lane_new() {
+    lane *l = new lane();
+    for (int g = 0; g < ROFL_MAX_GROUPS; g++) { cudaStream_t hi = rt_stream_create(true), lo = rt_stream_create(false); l->q[g] = chain(hi, lo); l->side[g] = rt_stream_create(true); }
+    return l;
+}
+static inline void lane_delete(lane *l) { for (int g = 0; g < ROFL_MAX_GROUPS; g++) { rt_stream_destroy(l->q[g].hi); if (l->q[g].lo != l->q[g].hi) rt_stream_destroy(l->q[g].lo); rt_stream_destroy(l->side[g]); } delete l; }
+// the calling thread's lane for the duration of an API call (nested engine calls of the same thread share it)
+struct lane_guard {
+    rofl_engine &e; lane *ln = nullptr;
+    explicit lane_guard(rofl_engine &eng) : e(eng) {
+        if (tl_lane && tl_lane_engine == &e) { ln = tl_lane; tl_lane_depth++; return; }
+        if (tl_lane) throw std::runtime_error("rofl_b200: nested calls into two contexts from one thread");
+        std::unique_lock<std::mutex> lk(e.lane_mu);
+        for (;;) {
+            for (lane *l : e.lanes) if (!l->busy) { ln = l; break; }
+            if (ln) break;
+            if ((int)e.lanes.size() < e.max_lanes) { ln = lane_new(); e.lanes.push_back(ln); break; }
+            e.lane_cv.wait(lk);
+        }
+        ln->busy = true; tl_lane = ln; tl_lane_engine = &e; tl_lane_depth = 1;
+    }
+    ~lane_guard() {
+        if (--tl_lane_depth > 0) return;
+        { std::lock_guard<std::mutex> lk(e.lane_mu); ln->busy = false; }
+        e.lane_cv.notify_one(); tl_lane = nullptr; tl_lane_engine = nullptr;
+    }
+    cudaStream_t s() const { return ln->q[0].hi; }
+    lane_guard(const lane_guard &) = delete; lane_guard &operator=(const lane_guard &) = delete;
 };
 
 // pinned host scratch with scope lifetime, recycled through the engine's pool (cudaHostAlloc is far too slow to call per proof)
@@ -116,88 +169,126 @@ static inline bool is_zero32(const uint8_t *b) { uint8_t z = 0; for (int i = 0; 
 static inline void sc_pow2_table(sc_st *tab, const sc &s) { sc c = s; for (int b = 0; b < 32; b++) { sc_to_st(tab[b], c); sc_mul(c, c, c); } }
 
 // ---- engine lifetime ------------------------------------------------------------------------------------------------------
+static std::mutex g_shared_mu; static std::map<int, dev_shared *> g_shared;
 static inline void engine_init(rofl_engine &e) {
-    ge_p3 B, H; ge_base(B); ge_compress(e.B32, B);
-    uint8_t h[64]; sha3_512(h, e.B32, 32); ge_from_uniform_bytes(H, h); ge_compress(e.H32, H);     // PedersenGens::default / el_gamal.rs:31-40
-    cudaStream_t s = e.stream;
-    if (e.gstreams.empty()) e.gstreams.push_back(e.stream);
-    e.free_hint = rt_free_mem();
-    e.tabB = (niels_st *)rt_malloc(sizeof(niels_st) * FB_WINDOWS * FB_ENTRIES, s);
-    e.tabH = (niels_st *)rt_malloc(sizeof(niels_st) * FB_WINDOWS * FB_ENTRIES, s);
+    {
+        std::lock_guard<std::mutex> lk(g_shared_mu);
+        dev_shared *&sh = g_shared[e.device];
+        if (!sh) { sh = new dev_shared(); sh->device = e.device; }
+        sh->refs++; e.sh = sh;
+    }
+    if (e.lanes.empty()) e.lanes.push_back(lane_new());
+    dev_shared &sh = *e.sh;
+    std::unique_lock<std::shared_mutex> ex(sh.tab_mu);
+    if (sh.tabB) return;
+    ge_p3 B, H; ge_base(B); ge_compress(sh.B32, B);
+    uint8_t h[64]; sha3_512(h, sh.B32, 32); ge_from_uniform_bytes(H, h); ge_compress(sh.H32, H);     // PedersenGens::default / el_gamal.rs:31-40
+    cudaStream_t s = e.lanes[0]->q[0].hi;
+    sh.free_hint = rt_free_mem();
+    sh.tabB = (niels_st *)rt_raw_malloc(sizeof(niels_st) * FB_WINDOWS * FB_ENTRIES);
+    sh.tabH = (niels_st *)rt_raw_malloc(sizeof(niels_st) * FB_WINDOWS * FB_ENTRIES);
     dev_buf pts(64, s);
-    rt_h2d(pts.as<uint8_t>(), e.B32, 32, s); rt_h2d(pts.as<uint8_t>() + 32, e.H32, 32, s);
+    rt_h2d(pts.as<uint8_t>(), sh.B32, 32, s); rt_h2d(pts.as<uint8_t>() + 32, sh.H32, 32, s);
     int nent = FB_WINDOWS * FB_ENTRIES;
-    LAUNCH(k_fb_table_build, dim3((nent + 63) / 64), dim3(64), s, e.tabB, pts.as<uint8_t>());
-    LAUNCH(k_fb_table_build, dim3((nent + 63) / 64), dim3(64), s, e.tabH, pts.as<uint8_t>() + 32);
+    LAUNCH(k_fb_table_build, dim3((nent + 63) / 64), dim3(64), s, sh.tabB, pts.as<uint8_t>());
+    LAUNCH(k_fb_table_build, dim3((nent + 63) / 64), dim3(64), s, sh.tabH, pts.as<uint8_t>() + 32);
     rt_sync(s);
 }
 static inline void engine_destroy(rofl_engine &e) {
-    cudaStream_t s = e.stream;
-    rt_sync(s);
-    rt_free(e.tabB, s); rt_free(e.tabH, s);
-    for (auto &g : e.gens) { rt_free(g.second.G, s); rt_free(g.second.H, s); rt_free(g.second.RTG, s); rt_free(g.second.RTH, s); }
-    for (auto &b : e.bsgs) { rt_free(b.second.keys, s); rt_free(b.second.vals, s); }
+    for (lane *l : e.lanes) { for (int g = 0; g < ROFL_MAX_GROUPS; g++) { rt_sync(l->q[g].hi); rt_sync(l->q[g].lo); rt_sync(l->side[g]); } lane_delete(l); }
+    e.lanes.clear();
     for (auto &pp : e.pins) rt_host_free(pp.first);
     e.pins.clear();
-    e.gens.clear(); e.bsgs.clear();
-    rt_sync(s);
+    std::lock_guard<std::mutex> lk(g_shared_mu);
+    dev_shared *sh = e.sh; e.sh = nullptr;
+    if (!sh || --sh->refs > 0) return;
+    rt_raw_free(sh->tabB); rt_raw_free(sh->tabH);
+    for (auto &g : sh->gens) { rt_raw_free(g.second.G); rt_raw_free(g.second.H); rt_raw_free(g.second.RTG); rt_raw_free(g.second.RTH); }
+    for (auto &b : sh->bsgs) { rt_raw_free(b.second.keys); rt_raw_free(b.second.vals); }
+    g_shared.erase(sh->device); delete sh;
+    rt_trim();
 }
-// BulletproofGens::new(n, m): cached per n, capacity grows (the reference rebuilds them per chunk per call,
-// range_proof_vec/mod.rs:126,201)
-static inline gens_entry &engine_gens(rofl_engine &e, int n, int m) {
-    gens_entry &g = e.gens[n];
-    if (g.cap >= m) return g;
-    cudaStream_t s = e.stream;
-    int newcap = std::max(m, g.cap * 2);
-    niels_st *G = (niels_st *)rt_malloc(sizeof(niels_st) * (size_t)n * newcap, s);
-    niels_st *H = (niels_st *)rt_malloc(sizeof(niels_st) * (size_t)n * newcap, s);
-    if (g.cap) { rt_d2d(G, g.G, sizeof(niels_st) * (size_t)n * g.cap, s); rt_d2d(H, g.H, sizeof(niels_st) * (size_t)n * g.cap, s); }
-    int cnt = 2 * (newcap - g.cap);
-    LAUNCH(k_gens_build, dim3((cnt + 63) / 64), dim3(64), s, G, H, n, g.cap, newcap);
-    rt_sync(s);
-    rt_free(g.G, s); rt_free(g.H, s);
-    g.n = n; g.cap = newcap; g.G = G; g.H = H;
-    return g;
-}
-
-// radix-2^c generator tables for the first m parties of the n-bit generators (c = 10, 9 or 8: the widest that fits the memory
-// budget; wider = fewer additions per term); returns false when not even c = 8 fits
-static inline bool engine_rt(rofl_engine &e, gens_entry &g, int n, int m, rt_tables &out) {
-    if (!e.use_rt) return false;
-    auto fill = [&](rt_tables &t, int c) { t.c = c; t.nw = msm_nw(c); t.B = 1 << (c - 1); msm_recode_const(t.K, c); };
-    if (g.rt_cap >= m) { out.G = g.RTG; out.H = g.RTH; fill(out, g.rt_c); return true; }
-    cudaStream_t s = e.stream;
-    const size_t cnt = (size_t)n * m;
-    rt_sync(s); rt_free(g.RTG, s); rt_free(g.RTH, s); g.RTG = g.RTH = nullptr; g.rt_cap = 0; rt_sync(s);
-    const size_t have = rt_free_mem();
-    int c = std::max(8, std::min(RT_MAX_BITS, e.rt_bits));
-    for (; c >= 8; c--) {
-        const size_t nw = msm_nw(c), B = (size_t)1 << (c - 1);
-        if ((double)(2 * cnt * nw * B * sizeof(niels_st) + cnt * nw * sizeof(p3_st)) <= e.rt_mem_frac * (double)have) break;
-    }
-    if (c < 8) return false;
-    rt_tables t; fill(t, c);
-    const size_t bytes = cnt * rt_row_entries(t) * sizeof(niels_st);
-    niels_st *RTG = (niels_st *)rt_malloc(bytes, s), *RTH = (niels_st *)rt_malloc(bytes, s);
-    {
-        dev_buf P(cnt * t.nw * sizeof(p3_st), s);
-        const size_t rows = cnt * t.nw, thr = rows * (t.B / 16);
-        for (int which = 0; which < 2; which++) {
-            LAUNCH(k_rt_shifts, dim3((unsigned)((cnt + 127) / 128)), dim3(128), s, P.as<p3_st>(), which ? g.H : g.G, (uint32_t)cnt, t.c, t.nw);
-            LAUNCH(k_rt_rows, dim3((unsigned)((thr + 127) / 128)), dim3(128), s, which ? RTH : RTG, P.as<p3_st>(), rows, t.B);
-        }
+// BulletproofGens::new(n, m): cached per n and device, capacity grows (the reference rebuilds them per chunk per call,
+// range_proof_vec/mod.rs:126,201).  Returns a copy of the entry; the arrays stay valid while the caller's tables_use is held.
+static inline gens_entry engine_gens(rofl_engine &e, tables_use &tu, cudaStream_t s, int n, int m) {
+    dev_shared &sh = *e.sh;
+    for (;;) {
+        auto it = sh.gens.find(n);
+        if (it != sh.gens.end() && it->second.cap >= m) return it->second;
+        tu.upgrade();
+        gens_entry &g = sh.gens[n];
+        if (g.cap >= m) continue;
+        int newcap = std::max(m, g.cap * 2);
+        niels_st *G = (niels_st *)rt_raw_malloc(sizeof(niels_st) * (size_t)n * newcap);
+        niels_st *H = (niels_st *)rt_raw_malloc(sizeof(niels_st) * (size_t)n * newcap);
+        if (g.cap) { rt_d2d(G, g.G, sizeof(niels_st) * (size_t)n * g.cap, s); rt_d2d(H, g.H, sizeof(niels_st) * (size_t)n * g.cap, s); }
+        int cnt = 2 * (newcap - g.cap);
+        LAUNCH(k_gens_build, dim3((cnt + 63) / 64), dim3(64), s, G, H, n, g.cap, newcap);
         rt_sync(s);
+        rt_raw_free(g.G); rt_raw_free(g.H);
+        g.n = n; g.cap = newcap; g.G = G; g.H = H;
     }
-    g.RTG = RTG; g.RTH = RTH; g.rt_cap = m; g.rt_c = c; t.G = RTG; t.H = RTH; out = t;
-    e.free_hint = rt_free_mem();
-    return true;
+}
+static inline void rt_fill(rt_tables &t, int c) { t.c = c; t.nw = msm_nw(c); t.B = 1 << (c - 1); msm_recode_const(t.K, c); }
+static inline size_t rt_table_bytes(size_t cnt, int c) { return 2 * cnt * (size_t)msm_nw(c) * ((size_t)1 << (c - 1)) * sizeof(niels_st); }
+// radix-2^c generator tables for the first m parties of the n-bit generators (c = 11 .. 8: the widest that fits the memory budget; wider =
+// fewer additions per term); returns false when not even c = 8 fits.  The tables of other (n, m) are evicted, least recently used first,
+// when that lets this one have a wider radix: the current workload gets the best tables the device can hold.
+static inline bool engine_rt(rofl_engine &e, tables_use &tu, cudaStream_t s, int n, int m, rt_tables &out) {
+    if (!e.use_rt) return false;
+    dev_shared &sh = *e.sh;
+    for (;;) {
+        gens_entry &g = sh.gens[n];                          // exists: engine_gens ran first
+        if (g.rt_cap >= m) { g.last_use = ++sh.clock; out.G = g.RTG; out.H = g.RTH; rt_fill(out, g.rt_c); return true; }
+        if (!tu.excl) { tu.upgrade(); continue; }
+        const size_t cnt = (size_t)n * m;
+        rt_sync(s); rt_raw_free(g.RTG); rt_raw_free(g.RTH); g.RTG = g.RTH = nullptr; g.rt_cap = 0; g.rt_bytes = 0;
+        rt_trim();
+        const int want = std::max(8, std::min(RT_MAX_BITS, e.rt_bits));
+        int c = 0;
+        for (;;) {
+            const size_t have = rt_free_mem();
+            for (c = want; c >= 8; c--) if ((double)(rt_table_bytes(cnt, c) + cnt * msm_nw(c) * sizeof(p3_st)) <= e.rt_mem_frac * (double)have) break;
+            if (c == want) break;
+            gens_entry *victim = nullptr;                    // not the widest radix: drop the least recently used tables of another (n, m) and look again
+            for (auto &kv : sh.gens) if (&kv.second != &g && kv.second.RTG && (!victim || kv.second.last_use < victim->last_use)) victim = &kv.second;
+            if (!victim) break;
+            rt_raw_free(victim->RTG); rt_raw_free(victim->RTH); victim->RTG = victim->RTH = nullptr; victim->rt_cap = 0; victim->rt_bytes = 0;
+        }
+        if (c < 8) { sh.free_hint = rt_free_mem(); return false; }
+        rt_tables t; rt_fill(t, c);
+        const size_t bytes = cnt * rt_row_entries(t) * sizeof(niels_st);
+        niels_st *RTG = (niels_st *)rt_raw_malloc(bytes), *RTH = (niels_st *)rt_raw_malloc(bytes);
+        {
+            dev_buf P(cnt * t.nw * sizeof(p3_st), s);
+            const size_t rows = cnt * t.nw, thr = rows * (t.B / 16);
+            for (int which = 0; which < 2; which++) {
+                LAUNCH(k_rt_shifts, dim3((unsigned)((cnt + 127) / 128)), dim3(128), s, P.as<p3_st>(), which ? g.H : g.G, (uint32_t)cnt, t.c, t.nw);
+                LAUNCH(k_rt_rows, dim3((unsigned)((thr + 127) / 128)), dim3(128), s, which ? RTH : RTG, P.as<p3_st>(), rows, t.B);
+            }
+            rt_sync(s);
+        }
+        g.RTG = RTG; g.RTH = RTH; g.rt_cap = m; g.rt_c = c; g.rt_bytes = 2 * bytes;
+        rt_trim();                                           // the build scratch goes back to CUDA before the free memory is recorded
+        sh.free_hint = rt_free_mem();
+    }
+}
+// drop every cached generator table of the device (they are rebuilt on next use)
+static inline void engine_drop_rt(rofl_engine &e) {
+    std::unique_lock<std::shared_mutex> ex(e.sh->tab_mu);
+    for (auto &g : e.sh->gens) { rt_raw_free(g.second.RTG); rt_raw_free(g.second.RTH); g.second.RTG = g.second.RTH = nullptr; g.second.rt_cap = 0; g.second.rt_bytes = 0; }
 }
 // blocks per msm for the direct table MSM: every block of a wave runs ceil(T / (nb*128)) terms per thread, so pick the nb whose
 // waves (148 SMs x 4 resident blocks) x terms-per-thread product is smallest (+ a block-sum epilogue worth ~half a term)
-static inline int rt_blocks(size_t T, int C) {
-    const size_t slots = 148 * RTM_BLOCKS, max_nb = std::max<size_t>(1, std::min((T + 127) / 128, slots * 4 / (size_t)C));
+static inline int rt_blocks(size_t T, int C, int per_max = 0) {
+    const size_t slots = 148 * RTM_BLOCKS, max_nb = std::max<size_t>(1, (T + 127) / 128);
+    if (per_max > 0) {           // at most per_max terms per thread: blocks of ~100 us, several waves (the gaps at their ends are filled by the other chunk groups)
+        const size_t nb = std::min(max_nb, (T + 128 * (size_t)per_max - 1) / (128 * (size_t)per_max));
+        return (int)std::max<size_t>(1, nb);
+    }
+    const size_t lim = std::max<size_t>(1, std::min(max_nb, slots * 4 / (size_t)C));
     size_t best = 1; double best_cost = 1e300;
-    for (size_t nb = 1; nb <= max_nb; nb++) {
+    for (size_t nb = 1; nb <= lim; nb++) {
         const double waves = (double)((nb * C + slots - 1) / slots), per = (double)((T + nb * 128 - 1) / (nb * 128));
         const double cost = waves * (per + 0.5);
         if (cost < best_cost * 0.999) { best_cost = cost; best = nb; }
@@ -252,108 +343,108 @@ static inline void fin_windows(finalize_args &f, const p3_st *win, const msm_pla
 // h_proofs (host).  d_vals: C*m shifted values, d_blind: C*m blindings (reduced), d_V32: C*m compressed commitments.
 // label = transcript label ("RangeProof" / "L2RangeProof"); keys = C ChaCha20 keys (host).
 // =============================================================================================================================
-static void prove_chunks(rofl_engine &e, cudaStream_t s, cudaStream_t side, int label_id, int n, int m, int C, const gens_entry &g, const rt_tables *rt, const uint64_t *d_vals,
+static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_id, int n, int m, int C, const gens_entry &g, const rt_tables *rt, const uint64_t *d_vals,
                          const sc_st *d_blind, const uint8_t *d_V32, const std::vector<uint8_t> &keys, uint8_t *h_proofs) {
     const size_t N = (size_t)n * m, NT = N * C;
     const int lgN = ilog2_sz(N);
     const size_t plen = 32 * (9 + 2 * (size_t)lgN);
-    phase_trace tr(s);
+    phase_trace tr(q.hi);
     // ---- device scratch.  The Merlin transcripts live on the device (ts_kernels.cuh): nothing below waits for the host until the proofs are copied out.
-    dev_buf d_ts(sizeof(transcript) * (size_t)C, s), d_proofs(plen * (size_t)C, s);
-    rt_stream_after(side, s);
+    dev_buf d_ts(sizeof(transcript) * (size_t)C, q), d_proofs(plen * (size_t)C, q);
+    rt_stream_after(side, q.small());
     { ts_absorb_args aa = {}; aa.ts = d_ts.as<transcript>(); aa.V32 = d_V32; aa.m = (uint32_t)m; aa.n = (uint32_t)n; aa.label_id = label_id;      // V_1..V_m: independent of A and S, so it
       LAUNCH_COOP(k_ts_absorbV, dim3(C), dim3(TS_THREADS), side, aa); }                                                                         // runs beside them on the side stream
-    dev_buf d_keys(32 * (size_t)C, s), d_sLR(sizeof(sc_st) * 2 * NT, s), d_sums(sizeof(sc_st) * 5 * C, s);
-    { std::vector<uint32_t> kw(8 * (size_t)C); for (int c = 0; c < C; c++) key_words(&kw[8 * c], &keys[32 * c]); rt_h2d(d_keys.p, kw.data(), 32 * (size_t)C, s); }
-    LAUNCH(k_nonces, dim3((unsigned)((NT + 255) / 256)), dim3(256), s, d_sLR.as<sc_st>(), d_keys.as<uint32_t>(), n, m, NT);
-    LAUNCH_COOP(k_party_sums, dim3(C), dim3(256), s, d_sums.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, (const sc_st *)nullptr, n, m, 0);
+    dev_buf d_keys(32 * (size_t)C, q), d_sLR(sizeof(sc_st) * 2 * NT, q), d_sums(sizeof(sc_st) * 5 * C, q);
+    { std::vector<uint32_t> kw(8 * (size_t)C); for (int c = 0; c < C; c++) key_words(&kw[8 * c], &keys[32 * c]); rt_h2d(d_keys.p, kw.data(), 32 * (size_t)C, q.small()); }
+    LAUNCH(k_nonces, dim3((unsigned)((NT + 255) / 256)), dim3(256), q.big(), d_sLR.as<sc_st>(), d_keys.as<uint32_t>(), n, m, NT);
+    LAUNCH_COOP(k_party_sums, dim3(C), dim3(256), q.small(), d_sums.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, (const sc_st *)nullptr, n, m, 0);
     // ---- A
     const int nbA = (int)std::min<size_t>(64, (N + 511) / 512);
-    dev_buf d_partA(sizeof(p3_st) * (size_t)C * nbA, s), d_AS(64 * (size_t)C, s);
-    LAUNCH_COOP(k_bits_sum, dim3(nbA, C), dim3(128), s, d_partA.as<p3_st>(), d_vals, g.G, g.H, n, m);
+    dev_buf d_partA(sizeof(p3_st) * (size_t)C * nbA, q), d_AS(64 * (size_t)C, q);
+    LAUNCH_COOP(k_bits_sum, dim3(nbA, C), dim3(128), q.big(), d_partA.as<p3_st>(), d_vals, g.G, g.H, n, m);
     {
-        finalize_args f = {}; f.partial = d_partA.as<p3_st>(); f.npartial = nbA; f.sHa = d_sums.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
+        finalize_args f = {}; f.partial = d_partA.as<p3_st>(); f.npartial = nbA; f.sHa = d_sums.as<sc_st>(); f.tabB = e.sh->tabB; f.tabH = e.sh->tabH;
         f.out32 = d_AS.as<uint8_t>(); f.count = C;
-        run_finalize(s, f);
+        run_finalize(q.small(), f);
     }
     // ---- S = (sum s_bl) H + <s_L, G> + <s_R, H>
     if (rt) {
-        const int nbS = rt_blocks(2 * N, C);
-        dev_buf d_partS(sizeof(p3_st) * (size_t)C * nbS, s);
+        const int nbS = rt_blocks(2 * N, C, e.rt_per);
+        dev_buf d_partS(sizeof(p3_st) * (size_t)C * nbS, q);
         rt_msm_args a = {}; a.scalars = d_sLR.as<sc_st>(); a.T = (uint32_t)(2 * N); a.scalar_stride = (uint32_t)(2 * N); a.nG = (uint32_t)N; a.mode = 0; a.rt = *rt; a.partial = d_partS.as<p3_st>();
-        run_rt_msm(e, s, a, nbS, C);
-        finalize_args f = {}; f.partial = d_partS.as<p3_st>(); f.npartial = nbS; f.sHa = d_sums.as<sc_st>() + C; f.tabB = e.tabB; f.tabH = e.tabH;
+        run_rt_msm(e, q.big(), a, nbS, C);
+        finalize_args f = {}; f.partial = d_partS.as<p3_st>(); f.npartial = nbS; f.sHa = d_sums.as<sc_st>() + C; f.tabB = e.sh->tabB; f.tabH = e.sh->tabH;
         f.out32 = d_AS.as<uint8_t>() + 32 * (size_t)C; f.count = C;
-        run_finalize(s, f);
+        run_finalize(q.small(), f);
     } else {
         const msm_plan pl = msm_plan_for(2 * N, C);
-        dev_buf d_winS(sizeof(p3_st) * pl.out_count(C), s);
+        dev_buf d_winS(sizeof(p3_st) * pl.out_count(C), q);
         msm_args a = {}; a.v[0].scalars = d_sLR.as<sc_st>(); a.split = (uint32_t)C; a.T = (uint32_t)(2 * N); a.scalar_stride = (uint32_t)(2 * N);
         a.v[0].seg[0] = mk_seg(g.G, (uint32_t)N, 0, 0); a.v[0].seg[1] = mk_seg(g.H, (uint32_t)N, 0, 0); a.nseg = 2; a.out = d_winS.as<p3_st>();
-        run_msm(e, s, a, pl, C);
-        finalize_args f = {}; fin_windows(f, d_winS.as<p3_st>(), pl); f.sHa = d_sums.as<sc_st>() + C; f.tabB = e.tabB; f.tabH = e.tabH;
+        run_msm(e, q.big(), a, pl, C);
+        finalize_args f = {}; fin_windows(f, d_winS.as<p3_st>(), pl); f.sHa = d_sums.as<sc_st>() + C; f.tabB = e.sh->tabB; f.tabH = e.sh->tabH;
         f.out32 = d_AS.as<uint8_t>() + 32 * (size_t)C; f.count = C;
-        run_finalize(s, f);
+        run_finalize(q.small(), f);
     }
     // ---- transcripts: V..., A, S -> y, z
-    rt_stream_after(s, side);
-    dev_buf d_ypow2(sizeof(sc_st) * 32 * C, s), d_zpow2(sizeof(sc_st) * 32 * C, s), d_yinvpow2(sizeof(sc_st) * 32 * C, s), d_z(sizeof(sc_st) * C, s);
+    rt_stream_after(q.small(), side);
+    dev_buf d_ypow2(sizeof(sc_st) * 32 * C, q), d_zpow2(sizeof(sc_st) * 32 * C, q), d_yinvpow2(sizeof(sc_st) * 32 * C, q), d_z(sizeof(sc_st) * C, q);
     { ts_yz_args ya = {}; ya.ts = d_ts.as<transcript>(); ya.AS = d_AS.as<uint8_t>(); ya.proofs = d_proofs.as<uint8_t>(); ya.plen = (uint32_t)plen; ya.C = (uint32_t)C;
       ya.ypow2 = d_ypow2.as<sc_st>(); ya.zpow2 = d_zpow2.as<sc_st>(); ya.yinvpow2 = d_yinvpow2.as<sc_st>(); ya.z = d_z.as<sc_st>();
-      LAUNCH_COOP(k_ts_yz, dim3(C), dim3(TS_THREADS), s, ya); }
+      LAUNCH_COOP(k_ts_yz, dim3(C), dim3(TS_THREADS), q.small(), ya); }
     // ---- polynomials
     const int nbP = (int)std::min<size_t>(256, (N + 255) / 256);
-    dev_buf d_a(sizeof(sc_st) * NT, s), d_b(sizeof(sc_st) * NT, s), d_part(sizeof(sc_st) * 3 * (size_t)C * nbP, s), d_tsum(sizeof(sc_st) * 3 * C, s);
+    dev_buf d_a(sizeof(sc_st) * NT, q), d_b(sizeof(sc_st) * NT, q), d_part(sizeof(sc_st) * 3 * (size_t)C * nbP, q), d_tsum(sizeof(sc_st) * 3 * C, q);
     // split power tables for y^k, y^-k (k < N) and z^j (j < m)
     const int lgm = ilog2_sz((size_t)m);
     pow_tab ytab = {nullptr, lgN / 2, lgN - lgN / 2}, yitab = ytab, ztab = {nullptr, lgm / 2, lgm - lgm / 2};
-    dev_buf d_ptab(sizeof(sc_st) * (size_t)C * (2 * pow_tab_size(ytab) + pow_tab_size(ztab)), s);
+    dev_buf d_ptab(sizeof(sc_st) * (size_t)C * (2 * pow_tab_size(ytab) + pow_tab_size(ztab)), q);
     ytab.tab = d_ptab.as<sc_st>(); yitab.tab = ytab.tab + (size_t)C * pow_tab_size(ytab); ztab.tab = yitab.tab + (size_t)C * pow_tab_size(yitab);
-    LAUNCH(k_pow_tables, dim3((pow_tab_size(ytab) + 255) / 256, C), dim3(256), s, (sc_st *)ytab.tab, d_ypow2.as<sc_st>(), ytab.L, ytab.H);
-    LAUNCH(k_pow_tables, dim3((pow_tab_size(yitab) + 255) / 256, C), dim3(256), s, (sc_st *)yitab.tab, d_yinvpow2.as<sc_st>(), yitab.L, yitab.H);
-    LAUNCH(k_pow_tables, dim3((pow_tab_size(ztab) + 255) / 256, C), dim3(256), s, (sc_st *)ztab.tab, d_zpow2.as<sc_st>(), ztab.L, ztab.H);
-    LAUNCH_COOP(k_poly, dim3(nbP, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_part.as<sc_st>(), d_vals, ytab, ztab, d_zpow2.as<sc_st>(), n, m);
-    LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_tsum.as<sc_st>(), d_part.as<sc_st>(), nbP, 3);
-    LAUNCH_COOP(k_party_sums, dim3(C), dim3(256), s, d_sums.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, d_z.as<sc_st>(), n, m, 1);
-    dev_buf d_t12(sizeof(sc_st) * 2 * C, s), d_T12(64 * (size_t)C, s);
-    LAUNCH(k_ts_t12, dim3((unsigned)((C + 63) / 64)), dim3(64), s, d_t12.as<sc_st>(), d_tsum.as<sc_st>(), (uint32_t)C);
+    LAUNCH(k_pow_tables, dim3((pow_tab_size(ytab) + 255) / 256, C), dim3(256), q.small(), (sc_st *)ytab.tab, d_ypow2.as<sc_st>(), ytab.L, ytab.H);
+    LAUNCH(k_pow_tables, dim3((pow_tab_size(yitab) + 255) / 256, C), dim3(256), q.small(), (sc_st *)yitab.tab, d_yinvpow2.as<sc_st>(), yitab.L, yitab.H);
+    LAUNCH(k_pow_tables, dim3((pow_tab_size(ztab) + 255) / 256, C), dim3(256), q.small(), (sc_st *)ztab.tab, d_zpow2.as<sc_st>(), ztab.L, ztab.H);
+    LAUNCH_COOP(k_poly, dim3(nbP, C), dim3(256), q.big(), d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_part.as<sc_st>(), d_vals, ytab, ztab, d_zpow2.as<sc_st>(), n, m);
+    LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), q.small(), d_tsum.as<sc_st>(), d_part.as<sc_st>(), nbP, 3);
+    LAUNCH_COOP(k_party_sums, dim3(C), dim3(256), q.small(), d_sums.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, d_z.as<sc_st>(), n, m, 1);
+    dev_buf d_t12(sizeof(sc_st) * 2 * C, q), d_T12(64 * (size_t)C, q);
+    LAUNCH(k_ts_t12, dim3((unsigned)((C + 63) / 64)), dim3(64), q.small(), d_t12.as<sc_st>(), d_tsum.as<sc_st>(), (uint32_t)C);
     {
-        finalize_args f = {}; f.sBa = d_t12.as<sc_st>(); f.sHa = d_sums.as<sc_st>() + 2 * C; f.tabB = e.tabB; f.tabH = e.tabH;
+        finalize_args f = {}; f.sBa = d_t12.as<sc_st>(); f.sHa = d_sums.as<sc_st>() + 2 * C; f.tabB = e.sh->tabB; f.tabH = e.sh->tabH;
         f.out32 = d_T12.as<uint8_t>(); f.count = 2 * C;
-        run_finalize(s, f);
+        run_finalize(q.small(), f);
     }
     // ---- x, shares, w
-    dev_buf d_x(sizeof(sc_st) * C, s), d_w2(sizeof(sc_st) * 2 * C, s), d_yinv(sizeof(sc_st) * NT, s);
+    dev_buf d_x(sizeof(sc_st) * C, q), d_w2(sizeof(sc_st) * 2 * C, q), d_yinv(sizeof(sc_st) * NT, q);
     { ts_x_args xa = {}; xa.ts = d_ts.as<transcript>(); xa.T12 = d_T12.as<uint8_t>(); xa.proofs = d_proofs.as<uint8_t>(); xa.plen = (uint32_t)plen; xa.C = (uint32_t)C;
       xa.tsum = d_tsum.as<sc_st>(); xa.sums = d_sums.as<sc_st>(); xa.x = d_x.as<sc_st>(); xa.w2 = d_w2.as<sc_st>(); xa.N = (uint64_t)N;
-      LAUNCH(k_ts_x, dim3((unsigned)((C + TS_THREADS - 1) / TS_THREADS)), dim3(TS_THREADS), s, xa); }
-    LAUNCH(k_lr, dim3((unsigned)((NT + 255) / 256)), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_yinv.as<sc_st>(), d_x.as<sc_st>(), yitab, N, NT);
+      LAUNCH(k_ts_x, dim3((unsigned)((C + TS_THREADS - 1) / TS_THREADS)), dim3(TS_THREADS), q.small(), xa); }
+    LAUNCH(k_lr, dim3((unsigned)((NT + 255) / 256)), dim3(256), q.big(), d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_yinv.as<sc_st>(), d_x.as<sc_st>(), yitab, N, NT);
     tr.mark("pre_ipp");
     // ---- inner product argument
     // folded generators [C][half]; a tail that starts at round 0 keeps all N original generators there instead
     const size_t half = (N / 2 <= (size_t)std::min(e.tail_np, TAIL_MAX_F / 2)) ? N : (N / 2 ? N / 2 : 1);
-    dev_buf d_Gf(sizeof(p3_st) * half * C, s), d_Hf(sizeof(p3_st) * half * C, s);
+    dev_buf d_Gf(sizeof(p3_st) * half * C, q), d_Hf(sizeof(p3_st) * half * C, q);
     sc_st *msmL = d_sLR.as<sc_st>(), *msmR = d_sLR.as<sc_st>() + NT;         // s_L / s_R are dead after k_lr: reuse as MSM scalar buffers
-    dev_buf d_cLR(sizeof(sc_st) * 2 * C, s), d_LR(64 * (size_t)C, s), d_u2(sizeof(sc_st) * C, s), d_uinv2(sizeof(sc_st) * C, s), d_nafs(512 * (size_t)C, s), d_up(sizeof(sc_st) * 2 * (size_t)C, s);
-    { std::vector<sc_st> h_up(2 * (size_t)C); sc one; sc_from_u64(one, 1); for (auto &v : h_up) sc_to_st(v, one); rt_h2d(d_up.p, h_up.data(), sizeof(sc_st) * h_up.size(), s); }
+    dev_buf d_cLR(sizeof(sc_st) * 2 * C, q), d_LR(64 * (size_t)C, q), d_u2(sizeof(sc_st) * C, q), d_uinv2(sizeof(sc_st) * C, q), d_nafs(512 * (size_t)C, q), d_up(sizeof(sc_st) * 2 * (size_t)C, q);
+    { std::vector<sc_st> h_up(2 * (size_t)C); sc one; sc_from_u64(one, 1); for (auto &v : h_up) sc_to_st(v, one); rt_h2d(d_up.p, h_up.data(), sizeof(sc_st) * h_up.size(), q.small()); }
     // RT path: the first r_unf rounds take L/R as table MSMs over the ORIGINAL generators (no generator folding), then one
     // catch-up fold builds G"/H" of length N >> r_unf directly from the tables
     // rounds with half-size <= tail_np run in the fused on-device tail kernel; `pre` rounds come before it
     const size_t tail_np = (size_t)std::min(e.tail_np, TAIL_MAX_F / 2);
     int pre = 0; while (pre < lgN && ((N / 2) >> pre) > tail_np) pre++;
     const int r_unf = rt ? std::min({e.rt_unfold, lgN, pre}) : 0;
-    const int nbU = rt ? rt_blocks(N, 2 * C) : 1;
+    const int nbU = rt ? rt_blocks(N, 2 * C, e.rt_per) : 1;
     const uint32_t cstride = 1u << (r_unf > 0 ? r_unf : 0);
     // coefficient tables of the unfolded rounds [G | H][C][cstride], kept on the device: k_ts_round doubles them after every challenge
     auto coef_init = [&](dev_buf &d, uint32_t stride) {
         std::vector<sc_st> h(2 * (size_t)C * stride); memset(h.data(), 0, sizeof(sc_st) * h.size());
         for (size_t c = 0; c < 2 * (size_t)C; c++) h[c * stride].w[0] = 1;
-        rt_h2d(d.p, h.data(), sizeof(sc_st) * h.size(), s);
+        rt_h2d(d.p, h.data(), sizeof(sc_st) * h.size(), q.small());
     };
-    dev_buf d_cGH(sizeof(sc_st) * 2 * (size_t)C * cstride, s), d_partU(sizeof(p3_st) * 2 * (size_t)C * nbU, s), d_digs(sizeof(int16_t) * 2 * (size_t)C * cstride * RT_MAXW, s);
+    dev_buf d_cGH(sizeof(sc_st) * 2 * (size_t)C * cstride, q), d_partU(sizeof(p3_st) * 2 * (size_t)C * nbU, q), d_digs(sizeof(int16_t) * 2 * (size_t)C * cstride * RT_MAXW, q);
     coef_init(d_cGH, cstride);
     const int nbQ = (int)std::min<size_t>(256, (N / 2 + 255) / 256);
-    dev_buf d_partQ(sizeof(sc_st) * 2 * (size_t)C * nbQ, s);
+    dev_buf d_partQ(sizeof(sc_st) * 2 * (size_t)C * nbQ, q);
     // frozen level (kernels.cuh K6c): rounds ra .. pre-1 run over the generators as they are at round ra (FA of G" and of H" per chunk)
     int ra = -1; size_t FA = 0; uint32_t cAstride = 1;
     if (e.use_frz) {
@@ -363,24 +454,25 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, cudaStream_t side, int 
         const double need = (double)C * 2 * fa * FRZ_Q * (FRZ_E + 1) * sizeof(p3_st);
         // (the budget check uses the free memory recorded when the tables were built: cudaMemGetInfo itself blocks for tens of
         //  milliseconds every now and then -- it was the cause of the "slow steps" of DESIGN.md section 7)
-        if (e.free_hint.load() == 0) e.free_hint = rt_free_mem();
-        if (pre - r >= 2 && fa >= 4 && need < 0.25 * (double)e.free_hint.load()) { ra = r; FA = fa; cAstride = (uint32_t)(FA / ((N / 2) >> (pre - 1))); }
+        if (e.sh->free_hint.load() == 0) e.sh->free_hint = rt_free_mem();
+        if (pre - r >= 2 && fa >= 4 && need < 0.25 * (double)e.sh->free_hint.load()) { ra = r; FA = fa; cAstride = (uint32_t)(FA / ((N / 2) >> (pre - 1))); }
     }
-    dev_buf d_cA(sizeof(sc_st) * 2 * (size_t)C * cAstride, s), d_frzV(sizeof(p3_st) * 2 * (size_t)C * 8, s);
+    dev_buf d_cA(sizeof(sc_st) * 2 * (size_t)C * cAstride, q), d_frzV(sizeof(p3_st) * 2 * (size_t)C * 8, q);
     coef_init(d_cA, cAstride);
-    dev_buf d_frzT(ra >= 0 ? sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q * FRZ_E : 16, s);
-    dev_buf d_dg(ra >= 0 ? 2 * (size_t)C * cAstride * 64 : 16, s);             // radix-16 digits of the frozen level's coefficients when it is left
+    dev_buf d_frzT(ra >= 0 ? sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q * FRZ_E : 16, q);
+    dev_buf d_dg(ra >= 0 ? 2 * (size_t)C * cAstride * 64 : 16, q);             // radix-16 digits of the frozen level's coefficients when it is left
     int round = 0;
     bool tail_done = false;
     for (size_t np = N / 2; np >= 1; np /= 2, round++) {
         if (round == r_unf) tr.mark("unfolded");
         if (round == ra) {           // enter the frozen level: Straus tables of the current G", H"
-            dev_buf d_bases(sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q, s);      // returned stream-ordered: the kernels below may still be running
-            void *tk = rt_prof_begin(PROF_FRZ, s);
-            LAUNCH(k_frz_bases, dim3((unsigned)((2 * FA + 127) / 128), C), dim3(128), s, d_bases.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), (uint32_t)FA, (uint32_t)half);
+            dev_buf d_bases(sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q, q);      // returned stream-ordered: the kernels below may still be running
+            q.big();
+            void *tk = rt_prof_begin(PROF_FRZ, q.cur ? q.lo : q.hi);
+            LAUNCH(k_frz_bases, dim3((unsigned)((2 * FA + 127) / 128), C), dim3(128), q.big(), d_bases.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), (uint32_t)FA, (uint32_t)half);
             const size_t cnt = (size_t)C * 2 * FA * FRZ_Q;
-            LAUNCH(k_frz_tables, dim3((unsigned)((cnt + 127) / 128)), dim3(128), s, d_frzT.as<p3_st>(), d_bases.as<p3_st>(), cnt);
-            rt_prof_end(PROF_FRZ, tk, s);
+            LAUNCH(k_frz_tables, dim3((unsigned)((cnt + 127) / 128)), dim3(128), q.big(), d_frzT.as<p3_st>(), d_bases.as<p3_st>(), cnt);
+            rt_prof_end(PROF_FRZ, tk, q.cur ? q.lo : q.hi);
         }
         const bool frozen = ra >= 0 && round >= ra;
         if (round == pre) tr.mark("middle");
@@ -388,28 +480,28 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, cudaStream_t side, int 
             const uint32_t nblk = (uint32_t)(FA / (2 * np));                  // == cAstride: the digits were written by the last frozen round's k_ts_round
             frz_exit_args xa = {}; xa.T = d_frzT.as<p3_st>(); xa.digs = d_dg.as<int8_t>(); xa.Gf = d_Gf.as<p3_st>(); xa.Hf = d_Hf.as<p3_st>();
             xa.F = (uint32_t)FA; xa.Fo = (uint32_t)(2 * np); xa.nblk = nblk; xa.stride = (uint32_t)half;
-            dev_buf d_xV(sizeof(p3_st) * (size_t)C * 2 * xa.Fo * 8, s); xa.V = d_xV.as<p3_st>();
-            void *tk = rt_prof_begin(PROF_FRZ, s);
-            LAUNCH_COOP(k_frz_exit, dim3((unsigned)(2 * np), C, 2), dim3(128), s, xa);
-            LAUNCH(k_frz_exit_chain, dim3((unsigned)(((size_t)C * 2 * xa.Fo + 127) / 128)), dim3(128), s, xa, (uint32_t)C);
-            rt_prof_end(PROF_FRZ, tk, s);
+            dev_buf d_xV(sizeof(p3_st) * (size_t)C * 2 * xa.Fo * 8, q); xa.V = d_xV.as<p3_st>();
+            void *tk = rt_prof_begin(PROF_FRZ, q.cur ? q.lo : q.hi);
+            LAUNCH_COOP(k_frz_exit, dim3((unsigned)(2 * np), C, 2), dim3(128), q.small(), xa);
+            LAUNCH(k_frz_exit_chain, dim3((unsigned)(((size_t)C * 2 * xa.Fo + 127) / 128)), dim3(128), q.small(), xa, (uint32_t)C);
+            rt_prof_end(PROF_FRZ, tk, q.cur ? q.lo : q.hi);
         }
         if (round == pre) tr.mark("exit");
         if (round == pre) {          // np <= tail_np: every remaining round in one launch (kernels.cuh, k_ipp_tail)
             // freeze the 2*np generators the tail works on: Straus tables (kernels.cuh K6c), built once for all its rounds
             const uint32_t Ft = (uint32_t)(2 * np);
-            if (round == 0) LAUNCH(k_niels_to_p3, dim3((Ft + 127) / 128, C), dim3(128), s, d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), g.G, g.H, Ft, (uint32_t)half);
-            dev_buf d_tb(sizeof(p3_st) * (size_t)C * 2 * Ft * FRZ_Q, s), d_tT(sizeof(p3_st) * (size_t)C * 2 * Ft * FRZ_Q * FRZ_E, s);
-            void *tk = rt_prof_begin(PROF_TAIL, s);
-            LAUNCH(k_frz_bases, dim3((2 * Ft + 127) / 128, C), dim3(128), s, d_tb.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), Ft, (uint32_t)half);
-            LAUNCH(k_frz_tables, dim3((unsigned)(((size_t)C * 2 * Ft * FRZ_Q + 127) / 128)), dim3(128), s, d_tT.as<p3_st>(), d_tb.as<p3_st>(), (size_t)C * 2 * Ft * FRZ_Q);
+            if (round == 0) LAUNCH(k_niels_to_p3, dim3((Ft + 127) / 128, C), dim3(128), q.small(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), g.G, g.H, Ft, (uint32_t)half);
+            dev_buf d_tb(sizeof(p3_st) * (size_t)C * 2 * Ft * FRZ_Q, q), d_tT(sizeof(p3_st) * (size_t)C * 2 * Ft * FRZ_Q * FRZ_E, q);
+            void *tk = rt_prof_begin(PROF_TAIL, q.cur ? q.lo : q.hi);
+            LAUNCH(k_frz_bases, dim3((2 * Ft + 127) / 128, C), dim3(128), q.small(), d_tb.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), Ft, (uint32_t)half);
+            LAUNCH(k_frz_tables, dim3((unsigned)(((size_t)C * 2 * Ft * FRZ_Q + 127) / 128)), dim3(128), q.small(), d_tT.as<p3_st>(), d_tb.as<p3_st>(), (size_t)C * 2 * Ft * FRZ_Q);
             tail_args ta = {}; ta.T = d_tT.as<p3_st>();
             ta.a = d_a.as<sc_st>(); ta.b = d_b.as<sc_st>(); ta.yinv = d_yinv.as<sc_st>(); ta.N = N;
-            ta.ts = d_ts.as<transcript>(); ta.w = d_w2.as<sc_st>(); ta.uprod = d_up.as<sc_st>(); ta.uinvprod = d_up.as<sc_st>() + C; ta.tabB = e.tabB;
-            dev_buf d_tscr(sizeof(p3_st) * 512 * (size_t)C, s); ta.scratch = d_tscr.as<p3_st>();
+            ta.ts = d_ts.as<transcript>(); ta.w = d_w2.as<sc_st>(); ta.uprod = d_up.as<sc_st>(); ta.uinvprod = d_up.as<sc_st>() + C; ta.tabB = e.sh->tabB;
+            dev_buf d_tscr(sizeof(p3_st) * 512 * (size_t)C, q); ta.scratch = d_tscr.as<p3_st>();
             ta.out = d_proofs.as<uint8_t>() + 224 + 64 * (size_t)round; ta.out_stride = (uint32_t)plen; ta.F = Ft;
-            LAUNCH_COOP(k_ipp_tail, dim3(C), dim3(TAIL_THREADS), s, ta);
-            rt_prof_end(PROF_TAIL, tk, s);
+            LAUNCH_COOP(k_ipp_tail, dim3(C), dim3(TAIL_THREADS), q.small(), ta);
+            rt_prof_end(PROF_TAIL, tk, q.cur ? q.lo : q.hi);
             tail_done = true;
             break;
         }
@@ -417,32 +509,32 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, cudaStream_t side, int 
         const bool unfolded = round < r_unf;
         if (frozen) {
             const int nbQA = (int)std::min<size_t>(256, (FA / 2 + 255) / 256);
-            LAUNCH_COOP(k_ipp_scalars_unf, dim3(nbQA, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), d_cA.as<sc_st>(), d_cA.as<sc_st>() + (size_t)C * cAstride, cAstride,
+            LAUNCH_COOP(k_ipp_scalars_unf, dim3(nbQA, C), dim3(256), q.small(), d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), d_cA.as<sc_st>(), d_cA.as<sc_st>() + (size_t)C * cAstride, cAstride,
                         msmL, msmR, d_partQ.as<sc_st>(), N, (uint32_t)np, (uint32_t)FA);
-            LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_partQ.as<sc_st>(), nbQA, 2);
+            LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), q.small(), d_cLR.as<sc_st>(), d_partQ.as<sc_st>(), nbQA, 2);
             frz_reduce_args ra_ = {}; ra_.T = d_frzT.as<p3_st>(); ra_.msmL = msmL; ra_.msmR = msmR; ra_.V = d_frzV.as<p3_st>(); ra_.F = (uint32_t)FA; ra_.np = (uint32_t)np; ra_.C = (uint32_t)C;
-            void *tk = rt_prof_begin(PROF_FRZ, s);
-            LAUNCH_COOP(k_frz_reduce, dim3(8, 2 * C), dim3(128), s, ra_);
-            rt_prof_end(PROF_FRZ, tk, s);
-            finalize_args f = {}; f.windows = d_frzV.as<p3_st>(); f.c = 4; f.nw = 8; f.slices = 1; f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
+            void *tk = rt_prof_begin(PROF_FRZ, q.cur ? q.lo : q.hi);
+            LAUNCH_COOP(k_frz_reduce, dim3(8, 2 * C), dim3(128), q.small(), ra_);
+            rt_prof_end(PROF_FRZ, tk, q.cur ? q.lo : q.hi);
+            finalize_args f = {}; f.windows = d_frzV.as<p3_st>(); f.c = 4; f.nw = 8; f.slices = 1; f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.sh->tabB; f.tabH = e.sh->tabH;
             f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
-            run_finalize(s, f);
+            run_finalize(q.small(), f);
         } else if (unfolded) {
-            LAUNCH_COOP(k_ipp_scalars_unf, dim3(nbQ, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), d_cGH.as<sc_st>(), d_cGH.as<sc_st>() + (size_t)C * cstride, cstride,
+            LAUNCH_COOP(k_ipp_scalars_unf, dim3(nbQ, C), dim3(256), q.big(), d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), d_cGH.as<sc_st>(), d_cGH.as<sc_st>() + (size_t)C * cstride, cstride,
                         msmL, msmR, d_partQ.as<sc_st>(), N, (uint32_t)np, (uint32_t)N);
-            LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_partQ.as<sc_st>(), nbQ, 2);
+            LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), q.small(), d_cLR.as<sc_st>(), d_partQ.as<sc_st>(), nbQ, 2);
             rt_msm_args aL = {}; aL.scalars = msmL; aL.T = (uint32_t)N; aL.scalar_stride = (uint32_t)N; aL.nG = (uint32_t)(N / 2); aL.np = (uint32_t)np; aL.mode = 1; aL.rt = *rt; aL.partial = d_partU.as<p3_st>();
             rt_msm_args aR = aL; aR.scalars = msmR; aR.mode = 2; aR.partial = d_partU.as<p3_st>() + (size_t)C * nbU;
-            run_rt_msm(e, s, aL, nbU, C); run_rt_msm(e, s, aR, nbU, C);
-            finalize_args f = {}; f.partial = d_partU.as<p3_st>(); f.npartial = nbU; f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
+            run_rt_msm(e, q.big(), aL, nbU, C); run_rt_msm(e, q.big(), aR, nbU, C);
+            finalize_args f = {}; f.partial = d_partU.as<p3_st>(); f.npartial = nbU; f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.sh->tabB; f.tabH = e.sh->tabH;
             f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
-            run_finalize(s, f);
+            run_finalize(q.small(), f);
         } else {
-            LAUNCH_COOP(k_ipp_scalars, dim3(nbI, C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), msmL, msmR, d_part.as<sc_st>(), N, (uint32_t)np);
-            LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), s, d_cLR.as<sc_st>(), d_part.as<sc_st>(), nbI, 2);
+            LAUNCH_COOP(k_ipp_scalars, dim3(nbI, C), dim3(256), q.small(), d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), msmL, msmR, d_part.as<sc_st>(), N, (uint32_t)np);
+            LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), q.small(), d_cLR.as<sc_st>(), d_part.as<sc_st>(), nbI, 2);
             // L and R of every chunk in one launch: msm = lr*C + c
             const msm_plan pl = msm_plan_for(2 * np, 2 * (size_t)C);
-            dev_buf d_win(sizeof(p3_st) * pl.out_count(2 * (size_t)C), s);
+            dev_buf d_win(sizeof(p3_st) * pl.out_count(2 * (size_t)C), q);
             msm_args a = {}; a.v[0].scalars = msmL; a.v[1].scalars = msmR; a.split = (uint32_t)C;
             a.T = (uint32_t)(2 * np); a.scalar_stride = (uint32_t)(2 * np); a.nseg = 2; a.out = d_win.as<p3_st>();
             if (round == 0) {
@@ -452,10 +544,10 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, cudaStream_t side, int 
                 a.v[0].seg[0] = mk_seg(d_Gf.as<p3_st>() + np, (uint32_t)np, (uint32_t)half, 1); a.v[0].seg[1] = mk_seg(d_Hf.as<p3_st>(), (uint32_t)np, (uint32_t)half, 1);
                 a.v[1].seg[0] = mk_seg(d_Gf.as<p3_st>(), (uint32_t)np, (uint32_t)half, 1);      a.v[1].seg[1] = mk_seg(d_Hf.as<p3_st>() + np, (uint32_t)np, (uint32_t)half, 1);
             }
-            run_msm(e, s, a, pl, 2 * (uint32_t)C);
-            finalize_args f = {}; fin_windows(f, d_win.as<p3_st>(), pl); f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH;
+            run_msm(e, q.big(), a, pl, 2 * (uint32_t)C);
+            finalize_args f = {}; fin_windows(f, d_win.as<p3_st>(), pl); f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.sh->tabB; f.tabH = e.sh->tabH;
             f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
-            run_finalize(s, f);
+            run_finalize(q.small(), f);
         }
         // ---- L, R -> u on the device, with everything the next kernels need from it (ts_kernels.cuh, k_ts_round)
         const bool catchup = unfolded && round + 1 == r_unf && np >= 2, fold = !frozen && !unfolded && np >= 2;
@@ -466,39 +558,41 @@ static void prove_chunks(rofl_engine &e, cudaStream_t s, cudaStream_t side, int 
             else if (unfolded) { t.coefG = d_cGH.as<sc_st>(); t.coefH = d_cGH.as<sc_st>() + (size_t)C * cstride; t.cstride = cstride; t.nblk = 1u << round;
                                  if (catchup) { t.emit = 2; t.digs16 = d_digs.as<int16_t>(); for (int i = 0; i < 9; i++) t.rtK[i] = rt->K[i]; t.rtc = rt->c; t.rtnw = rt->nw; } }
             else if (fold) { t.emit = 1; t.nafs = d_nafs.as<int8_t>(); }
-            LAUNCH_COOP(k_ts_round, dim3(C), dim3(TS_THREADS), s, t);
+            LAUNCH_COOP(k_ts_round, dim3(C), dim3(TS_THREADS), q.small(), t);
         }
-        LAUNCH(k_ipp_fold_scalars, dim3((unsigned)((np + 255) / 256), C), dim3(256), s, d_a.as<sc_st>(), d_b.as<sc_st>(), d_u2.as<sc_st>(), d_uinv2.as<sc_st>(), N, (uint32_t)np);
+        LAUNCH(k_ipp_fold_scalars, dim3((unsigned)((np + 255) / 256), C), dim3(256), q.small(), d_a.as<sc_st>(), d_b.as<sc_st>(), d_u2.as<sc_st>(), d_uinv2.as<sc_st>(), N, (uint32_t)np);
         if (catchup) {               // G", H" of length np straight from the tables
             catchup_args ca = {}; ca.rt = *rt; ca.Gf = d_Gf.as<p3_st>(); ca.Hf = d_Hf.as<p3_st>(); ca.digits = d_digs.as<int16_t>(); ca.nr = (uint32_t)np; ca.nblk = 1u << r_unf; ca.stride = (uint32_t)half;
-            void *tk = rt_prof_begin(PROF_FOLD, s);
-            LAUNCH_COOP(k_rt_catchup, dim3((unsigned)((np + 127) / 128), C, 2), dim3(128), s, ca);
-            rt_prof_end(PROF_FOLD, tk, s);
+            q.big();
+            void *tk = rt_prof_begin(PROF_FOLD, q.cur ? q.lo : q.hi);
+            LAUNCH_COOP(k_rt_catchup, dim3((unsigned)((np + 127) / 128), C, 2), dim3(128), q.big(), ca);
+            rt_prof_end(PROF_FOLD, tk, q.cur ? q.lo : q.hi);
         } else if (fold) {
             fold_args fa = {}; fa.Gn = round == 0 ? g.G : nullptr; fa.Hn = round == 0 ? g.H : nullptr;
             fa.Gf = d_Gf.as<p3_st>(); fa.Hf = d_Hf.as<p3_st>(); fa.nafs = d_nafs.as<int8_t>(); fa.np = (uint32_t)np; fa.stride = (uint32_t)half;
-            void *tk = rt_prof_begin(PROF_FOLD, s);
-            LAUNCH_COOP(k_ipp_fold_points, dim3((unsigned)((np + 127) / 128), C, 2), dim3(128), s, fa);
-            rt_prof_end(PROF_FOLD, tk, s);
+            q.big();
+            void *tk = rt_prof_begin(PROF_FOLD, q.cur ? q.lo : q.hi);
+            LAUNCH_COOP(k_ipp_fold_points, dim3((unsigned)((np + 127) / 128), C, 2), dim3(128), q.big(), fa);
+            rt_prof_end(PROF_FOLD, tk, q.cur ? q.lo : q.hi);
         }
     }
     if (!tail_done) {            // final a, b: a = a^ prod u_k, b = b^ prod u_k^-1
         ts_final_args fa = {}; fa.a = d_a.as<sc_st>(); fa.b = d_b.as<sc_st>(); fa.up = d_up.as<sc_st>(); fa.proofs = d_proofs.as<uint8_t>(); fa.plen = (uint32_t)plen; fa.off = (uint32_t)(224 + 64 * lgN); fa.C = (uint32_t)C; fa.N = N;
-        LAUNCH(k_ts_final, dim3((unsigned)((C + 63) / 64)), dim3(64), s, fa);
+        LAUNCH(k_ts_final, dim3((unsigned)((C + 63) / 64)), dim3(64), q.small(), fa);
     }
-    rt_d2h(h_proofs, d_proofs.p, plen * (size_t)C, s);
-    rt_sync(s);
+    rt_d2h(h_proofs, d_proofs.p, plen * (size_t)C, q.small());
+    rt_sync(q.small());
     tr.mark("ipp");
 }
 
 
-// run f(group, c0, c1, stream) for `groups` contiguous chunk ranges concurrently (one host thread + one stream per group)
-template <class F> static void for_chunk_groups(rofl_engine &e, size_t C, F f) {
-    size_t G = std::max<size_t>(1, std::min<size_t>({(size_t)e.groups, e.gstreams.size(), C}));
-    if (G == 1) { f(0, (size_t)0, C, e.stream); return; }
+// run f(group, c0, c1, queue, side stream) for `groups` contiguous chunk ranges concurrently (one host thread + one queue per group)
+template <class F> static void for_chunk_groups(rofl_engine &e, lane &ln, size_t C, F f) {
+    size_t G = std::max<size_t>(1, std::min<size_t>({(size_t)e.groups, (size_t)ROFL_MAX_GROUPS, C}));
+    if (G == 1) { f(0, (size_t)0, C, ln.q[0], ln.side[0]); return; }
     std::vector<std::thread> th; std::vector<std::string> errs(G);
     for (size_t gi = 0; gi < G; gi++) th.emplace_back([&, gi] {
-        try { rt_set_device(e.device); f(gi, C * gi / G, C * (gi + 1) / G, e.gstreams[gi]); } catch (const std::exception &ex) { errs[gi] = ex.what(); }
+        try { rt_set_device(e.device); f(gi, C * gi / G, C * (gi + 1) / G, ln.q[gi], ln.side[gi]); } catch (const std::exception &ex) { errs[gi] = ex.what(); }
     });
     for (auto &t : th) t.join();
     for (auto &m : errs) if (!m.empty()) throw std::runtime_error(m);
@@ -518,8 +612,8 @@ static int engine_range_prove(rofl_engine &e, const float *d_values, const uint8
                               const shard_spec *shard = nullptr) {
     if (!fp_ok(n_bits, frac) || range < 1 || range > n_bits) return -2;
     if (shard ? (shard->m == 0 || shard->n_chunks == 0 || D > shard->m * shard->n_chunks) : (D == 0 || n_partition == 0)) return -2;
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     const size_t Dp = shard ? shard->m * shard->n_chunks : next_pow2_sz(D);
     const size_t C = shard ? shard->n_chunks : std::min(Dp, n_partition), m = Dp / C;                         // :54-55
     const size_t c_off = shard ? shard->chunk_begin : 0;
@@ -528,7 +622,7 @@ static int engine_range_prove(rofl_engine &e, const float *d_values, const uint8
     dev_buf d_V(32 * Dp, s), d_vals(8 * Dp, s), d_bl(sizeof(sc_st) * Dp, s), d_flags(sizeof(int), s);
     rt_memset(d_flags.p, 0, sizeof(int), s);
     commit_args ca = {}; ca.values = d_values; ca.blind = d_blind; ca.D = D; ca.Dp = Dp; ca.n_bits = n_bits; ca.frac = frac;
-    ca.shift_bits = range; ca.mx = clip_max_f(range, n_bits, frac); ca.mn = -ca.mx; ca.tabB = e.tabB; ca.tabH = e.tabH;
+    ca.shift_bits = range; ca.mx = clip_max_f(range, n_bits, frac); ca.mn = -ca.mx; ca.tabB = e.sh->tabB; ca.tabH = e.sh->tabH;
     ca.V = d_V.as<uint8_t>(); ca.C = d_commits; ca.vals = d_vals.as<uint64_t>(); ca.blind_sc = d_bl.as<sc_st>(); ca.flags = d_flags.as<int>();
     void *tk = rt_prof_begin(PROF_COMMIT, s);
     LAUNCH(k_commit, dim3((unsigned)((Dp + 127) / 128)), dim3(128), s, ca);
@@ -538,14 +632,16 @@ static int engine_range_prove(rofl_engine &e, const float *d_values, const uint8
     if (flags & 1) return -98;
     if (!bitsize_ok) return ROFL_ERR_BITSIZE_;
     if (!chunk_ok) return -99;
-    gens_entry &g = engine_gens(e, range, (int)m);
-    rt_tables rt; const bool have_rt = engine_rt(e, g, range, (int)m, rt);
+    tables_use tu(*e.sh);
+    engine_gens(e, tu, s, range, (int)m);
+    rt_tables rt; const bool have_rt = engine_rt(e, tu, s, range, (int)m, rt);
+    const gens_entry g = engine_gens(e, tu, s, range, (int)m);          // (read after engine_rt: an upgrade of the lock inside it lets others regrow the arrays)
     std::vector<uint8_t> keys(32 * C);
     for (size_t c = 0; c < C; c++) derive_key(&keys[32 * c], seed, DOM_RANGE_PROVE, c_off + c);
     const size_t plen = 32 * (9 + 2 * (size_t)ilog2_sz((size_t)range * m));
-    for_chunk_groups(e, C, [&](size_t, size_t c0, size_t c1, cudaStream_t gs) {
+    for_chunk_groups(e, *lg.ln, C, [&](size_t, size_t c0, size_t c1, chain &gq, cudaStream_t side) {
         std::vector<uint8_t> k(keys.begin() + 32 * c0, keys.begin() + 32 * c1);
-        prove_chunks(e, gs, e.side_for(gs), 0, range, (int)m, (int)(c1 - c0), g, have_rt ? &rt : nullptr, d_vals.as<uint64_t>() + c0 * m, d_bl.as<sc_st>() + c0 * m, d_V.as<uint8_t>() + 32 * c0 * m, k, h_proofs + plen * c0);
+        prove_chunks(e, gq, side, 0, range, (int)m, (int)(c1 - c0), g, have_rt ? &rt : nullptr, d_vals.as<uint64_t>() + c0 * m, d_bl.as<sc_st>() + c0 * m, d_V.as<uint8_t>() + 32 * c0 * m, k, h_proofs + plen * c0);
     });
     *proof_len = plen; *n_proofs = C;
     return 0;
@@ -595,7 +691,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, in
     { ts_absorb_args aa = {}; aa.ts = d_ts.as<transcript>(); aa.V32 = d_V32; aa.m = (uint32_t)m; aa.n = (uint32_t)n; aa.label_id = label_id;
       LAUNCH_COOP(k_ts_absorbV, dim3(C), dim3(TS_THREADS), s, aa); }
     { ts_verify_args va = {}; va.ts = d_ts.as<transcript>(); va.proofs = d_proofs.as<uint8_t>(); va.plen = (uint32_t)plen; va.C = (uint32_t)C; va.lgN = lgN; va.N = (uint64_t)N;
-      va.chal = d_vch.as<sc_st>(); va.digest = d_digest.as<uint8_t>(); va.bad = d_bad.as<int>(); va.sp32 = d_sp32.as<uint8_t>(); memcpy(va.B32, e.B32, 32); memcpy(va.H32, e.H32, 32);
+      va.chal = d_vch.as<sc_st>(); va.digest = d_digest.as<uint8_t>(); va.bad = d_bad.as<int>(); va.sp32 = d_sp32.as<uint8_t>(); memcpy(va.B32, e.sh->B32, 32); memcpy(va.H32, e.sh->H32, 32);
       LAUNCH(k_ts_verify, dim3((unsigned)((C + TS_THREADS - 1) / TS_THREADS)), dim3(TS_THREADS), s, va); }
     { verify_keys_args ka = {}; ka.digest = d_digest.as<uint8_t>(); ka.C = (uint32_t)C; ka.dom = dom; ka.c_off = c_off; memcpy(ka.seed, seed, 32); ka.ccrho = d_ccrho.as<sc_st>();
       LAUNCH_COOP(k_verify_keys, dim3(1), dim3(256), s, ka); }
@@ -609,7 +705,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, in
     tr.mark("v_scalar_kernels");
     // fixed generators: one 2N-term MSM (radix-256 tables when they exist, bucket MSM otherwise) -> d_fix
     {
-        finalize_args f = {}; f.tabB = e.tabB; f.tabH = e.tabH; f.out_p3 = d_fix.as<p3_st>(); f.count = 1;
+        finalize_args f = {}; f.tabB = e.sh->tabB; f.tabH = e.sh->tabH; f.out_p3 = d_fix.as<p3_st>(); f.count = 1;
         if (rt) {
             const int nbV = rt_blocks(2 * N, 1);
             dev_buf d_partV(sizeof(p3_st) * (size_t)nbV, s);
@@ -637,7 +733,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, in
         a.v[0].seg[0] = mk_seg(d_Vp3, (uint32_t)((size_t)C * m), 0, 1); a.v[0].seg[1] = mk_seg(d_sp.p, (uint32_t)((size_t)C * nsmall), 0, 1);
         run_msm(e, s, a, pl, 1);
         finalize_args f = {}; fin_windows(f, d_winV.as<p3_st>(), pl);
-        f.partial = d_fix.as<p3_st>(); f.npartial = 1; f.tabB = e.tabB; f.tabH = e.tabH; f.is_id = d_id.as<int>(); f.count = 1;
+        f.partial = d_fix.as<p3_st>(); f.npartial = 1; f.tabB = e.sh->tabB; f.tabH = e.sh->tabH; f.is_id = d_id.as<int>(); f.count = 1;
         run_finalize(s, f);
     }
     std::vector<int> h_bad(C); int h_id = 0;
@@ -658,8 +754,8 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
                                int range, const uint8_t seed[32], const shard_spec *shard = nullptr, uint8_t *h_weights = nullptr) {
     if (n_proofs == 0 || range < 1 || range > 64) return -2;
     if (shard ? (shard->m == 0 || shard->n_chunks != n_proofs || D > shard->m * shard->n_chunks) : D == 0) return -2;
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     const size_t Dp = shard ? shard->m * shard->n_chunks : next_pow2_sz(D), m = Dp / n_proofs;                     // :168
     const size_t c_off = shard ? shard->chunk_begin : 0;
     if (m == 0) return -3;
@@ -670,13 +766,15 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
     phase_trace tr(s);
     dev_buf d_off(sizeof(p3_st), s), d_offs(sizeof(sc_st), s), d_Vp3(sizeof(p3_st) * Dp, s), d_V32(32 * Dp, s), d_bad(sizeof(int), s);
     { sc o; sc_from_u64(o, 1ULL << (range - 1)); sc_st os; sc_to_st(os, o); rt_h2d(d_offs.p, &os, sizeof(os), s);
-      finalize_args f = {}; f.sBa = d_offs.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH; f.out_p3 = d_off.as<p3_st>(); f.count = 1;
+      finalize_args f = {}; f.sBa = d_offs.as<sc_st>(); f.tabB = e.sh->tabB; f.tabH = e.sh->tabH; f.out_p3 = d_off.as<p3_st>(); f.count = 1;
       run_finalize(s, f); }
     rt_memset(d_bad.p, 0, sizeof(int), s);
     LAUNCH(k_decompress, dim3((unsigned)((Dp + 127) / 128)), dim3(128), s, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), d_commits, D, Dp, d_off.as<p3_st>(), d_bad.as<int>(), Dp);
     tr.mark("v_decompress");
-    gens_entry &g = engine_gens(e, range, (int)m);
-    rt_tables rt; const bool have_rt = engine_rt(e, g, range, (int)m, rt);
+    tables_use tu(*e.sh);
+    engine_gens(e, tu, s, range, (int)m);
+    rt_tables rt; const bool have_rt = engine_rt(e, tu, s, range, (int)m, rt);
+    const gens_entry g = engine_gens(e, tu, s, range, (int)m);
     // one group: every chunk goes into the same batched check (kernels.cuh, k_verify_scalars), splitting would repeat the generator MSM
     std::vector<int> verdict; int bad = 0;
     const int rc = verify_chunks(e, s, 0, range, (int)m, (int)C, g, have_rt ? &rt : nullptr, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), h_proofs, plen, seed, DOM_RANGE_VERIFY, c_off, verdict, d_bad.as<int>(), &bad, h_weights);
@@ -695,8 +793,8 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
 static int engine_l2_prove(rofl_engine &e, const float *h_values, const float *d_values, const uint8_t *d_blind, size_t D, int range,
                            int n_bits, int frac, const uint8_t seed[32], uint8_t *h_proof, size_t *proof_len, uint8_t *h_commit) {
     if (!fp_ok(n_bits, frac) || D == 0 || range < 1) return -2;
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     const float mx = clip_max_f(range, n_bits, frac), mn = -mx;
     for (size_t i = 0; i < D; i++) if (mn > h_values[i] || h_values[i] > mx) return 2;
     const int nb = (int)std::min<size_t>(256, (D + 255) / 256);
@@ -724,19 +822,20 @@ static int engine_l2_prove(rofl_engine &e, const float *h_values, const float *d
     dev_buf d_v(8, s), d_bl(sizeof(sc_st), s), d_vs(sizeof(sc_st), s), d_V(32, s);
     sc vs; sc_from_u64(vs, v); sc_st t; sc_to_st(t, vs); rt_h2d(d_vs.p, &t, sizeof(t), s);
     sc_to_st(t, bsum); rt_h2d(d_bl.p, &t, sizeof(t), s); rt_h2d(d_v.p, &v, 8, s);
-    { finalize_args f = {}; f.sBa = d_vs.as<sc_st>(); f.sHa = d_bl.as<sc_st>(); f.tabB = e.tabB; f.tabH = e.tabH; f.out32 = d_V.as<uint8_t>(); f.count = 1;
+    { finalize_args f = {}; f.sBa = d_vs.as<sc_st>(); f.sHa = d_bl.as<sc_st>(); f.tabB = e.sh->tabB; f.tabH = e.sh->tabH; f.out32 = d_V.as<uint8_t>(); f.count = 1;
       run_finalize(s, f); }
-    gens_entry &g = engine_gens(e, range, 1);                                     // BulletproofGens::new(64, 1) restricted to n = range (:162)
+    tables_use tu(*e.sh);
+    const gens_entry g = engine_gens(e, tu, s, range, 1);                         // BulletproofGens::new(64, 1) restricted to n = range (:162)
     std::vector<uint8_t> keys(32); derive_key(keys.data(), seed, DOM_L2_PROVE, 0);
-    prove_chunks(e, s, s, 1, range, 1, 1, g, nullptr, d_v.as<uint64_t>(), d_bl.as<sc_st>(), d_V.as<uint8_t>(), keys, h_proof);
+    prove_chunks(e, lg.ln->q[0], lg.ln->side[0], 1, range, 1, 1, g, nullptr, d_v.as<uint64_t>(), d_bl.as<sc_st>(), d_V.as<uint8_t>(), keys, h_proof);
     rt_d2h(h_commit, d_V.p, 32, s); rt_sync(s);
     *proof_len = 32 * (9 + 2 * (size_t)ilog2_sz((size_t)range));
     return 0;
 }
 // verify_rangeproof_l2 (:185-228)
 static int engine_l2_verify(rofl_engine &e, const uint8_t *h_proof, size_t plen, const uint8_t *h_commit, int range, const uint8_t seed[32]) {
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     if (range_proof_format_check(h_proof, plen, 1, nullptr)) return -1;
     dev_buf d_c(32, s), d_Vp3(sizeof(p3_st), s), d_V32(32, s), d_bad(sizeof(int), s);
     rt_h2d(d_c.p, h_commit, 32, s); rt_memset(d_bad.p, 0, sizeof(int), s);
@@ -745,7 +844,8 @@ static int engine_l2_verify(rofl_engine &e, const uint8_t *h_proof, size_t plen,
         int bad = 0; rt_d2h(&bad, d_bad.p, sizeof(int), s); rt_sync(s);
         return bad ? -4 : ROFL_ERR_BITSIZE_;
     }
-    gens_entry &g = engine_gens(e, range, 1);
+    tables_use tu(*e.sh);
+    const gens_entry g = engine_gens(e, tu, s, range, 1);
     std::vector<int> verdict; int bad = 0;
     const int rc = verify_chunks(e, s, 1, range, 1, 1, g, nullptr, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), h_proof, plen, seed, DOM_L2_VERIFY, 0, verdict, d_bad.as<int>(), &bad);
     if (bad) return -4;
@@ -760,12 +860,12 @@ static int engine_square_prove(rofl_engine &e, const float *d_values, const uint
                                int n_bits, int frac, const uint8_t seed[32], uint8_t *d_proofs, uint8_t *d_commits) {
     if (!fp_ok(n_bits, frac)) return -2;
     if (D == 0) return 0;
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     dev_buf d_flags(sizeof(int), s); rt_memset(d_flags.p, 0, sizeof(int), s);
     square_args a = {}; a.values = d_values; a.value_com = d_value_com; a.r1 = d_r1; a.r2 = d_r2; a.D = D; a.n_bits = n_bits; a.frac = frac;
     uint8_t key[32]; derive_key(key, seed, DOM_SQUARE, 0); key_words(a.key, key);
-    a.tabB = e.tabB; a.tabH = e.tabH; a.proofs = d_proofs; a.commits = d_commits; a.flags = d_flags.as<int>();
+    a.tabB = e.sh->tabB; a.tabH = e.sh->tabH; a.proofs = d_proofs; a.commits = d_commits; a.flags = d_flags.as<int>();
     void *tk = rt_prof_begin(PROF_SQUARE, s);
     LAUNCH(k_square_prove, dim3((unsigned)((D + 127) / 128)), dim3(128), s, a);
     rt_prof_end(PROF_SQUARE, tk, s);
@@ -776,11 +876,11 @@ static int engine_square_prove(rofl_engine &e, const float *d_values, const uint
 }
 static int engine_square_verify(rofl_engine &e, const uint8_t *d_proofs, const uint8_t *d_commits, size_t D) {
     if (D == 0) return 1;
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     dev_buf d_res(2 * sizeof(int), s); int init[2] = {1, 0}; rt_h2d(d_res.p, init, sizeof(init), s);
     void *tk = rt_prof_begin(PROF_SQUARE, s);
-    LAUNCH(k_square_verify, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_proofs, d_commits, D, e.tabB, e.tabH, d_res.as<int>());
+    LAUNCH(k_square_verify, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_proofs, d_commits, D, e.sh->tabB, e.sh->tabH, d_res.as<int>());
     rt_prof_end(PROF_SQUARE, tk, s);
     int res[2]; rt_d2h(res, d_res.p, sizeof(res), s); rt_sync(s);
     if (res[1]) return -1;
@@ -818,14 +918,14 @@ static int engine_crp_prove(rofl_engine &e, const float *d_values, const uint8_t
                             const uint8_t seed[32], uint8_t *h_proof, uint8_t *h_pairs) {
     if (!fp_ok(n_bits, frac)) return -2;
     if (D > CRP_MAX_D) return -6;
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     const size_t Dn = D ? D : 1;
     dev_buf d_L(32 * Dn, s), d_R(32 * Dn, s), d_pairs(64 * Dn, s), d_flags(sizeof(int), s), d_bad(sizeof(int), s);
     rt_memset(d_flags.p, 0, sizeof(int), s); rt_memset(d_bad.p, 0, sizeof(int), s);
     if (D) {
         commit_args ca = {}; ca.values = d_values; ca.blind = d_blind; ca.D = D; ca.Dp = D; ca.n_bits = n_bits; ca.frac = frac;
-        ca.tabB = e.tabB; ca.tabH = e.tabH; ca.C = d_value_com ? nullptr : d_L.as<uint8_t>(); ca.R = d_R.as<uint8_t>(); ca.flags = d_flags.as<int>();   // R_i = r_i B (el_gamal.rs:57-69)
+        ca.tabB = e.sh->tabB; ca.tabH = e.sh->tabH; ca.C = d_value_com ? nullptr : d_L.as<uint8_t>(); ca.R = d_R.as<uint8_t>(); ca.flags = d_flags.as<int>();   // R_i = r_i B (el_gamal.rs:57-69)
         LAUNCH(k_commit, dim3((unsigned)((D + 127) / 128)), dim3(128), s, ca);
         if (d_value_com) {          // prove_existing: the caller's commitments must at least decode (the reference holds RistrettoPoints)
             dev_buf d_tmp(sizeof(p3_st) * D, s);
@@ -840,7 +940,7 @@ static int engine_crp_prove(rofl_engine &e, const float *d_values, const uint8_t
     sc_st h_sB[2], h_sH[2]; sc_to_st(h_sB[0], mp); sc_to_st(h_sH[0], rp); sc_to_st(h_sB[1], rp); sc_to_st(h_sH[1], zero);
     dev_buf d_s(sizeof(sc_st) * 4, s), d_cp(64, s);
     rt_h2d(d_s.p, h_sB, sizeof(h_sB), s); rt_h2d(d_s.as<sc_st>() + 2, h_sH, sizeof(h_sH), s);
-    { finalize_args f = {}; f.sBa = d_s.as<sc_st>(); f.sHa = d_s.as<sc_st>() + 2; f.tabB = e.tabB; f.tabH = e.tabH; f.out32 = d_cp.as<uint8_t>(); f.count = 2; run_finalize(s, f); }
+    { finalize_args f = {}; f.sBa = d_s.as<sc_st>(); f.sHa = d_s.as<sc_st>() + 2; f.tabB = e.sh->tabB; f.tabH = e.sh->tabH; f.out32 = d_cp.as<uint8_t>(); f.count = 2; run_finalize(s, f); }
     int flags = 0, bad = 0;
     rt_d2h(h_proof, d_cp.p, 64, s); rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_d2h(&bad, d_bad.p, sizeof(int), s);
     rt_sync(s);
@@ -866,8 +966,8 @@ static int engine_crp_verify(rofl_engine &e, const uint8_t *h_proof, const uint8
     if (D > CRP_MAX_D) return -6;
     sc zm, zr; sc_frombytes(zm, h_proof + 64); sc_frombytes(zr, h_proof + 96);
     if (!sc_is_canonical(zm) || !sc_is_canonical(zr)) return -1;
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     const size_t Dn = D ? D : 1;
     dev_buf d_pairs(64 * Dn, s), d_LR32(64 * Dn, s), d_LR(sizeof(p3_st) * 2 * Dn, s), d_cp32(64, s), d_cp(sizeof(p3_st) * 2, s), d_bad(sizeof(int) * 2, s);
     rt_memset(d_bad.p, 0, sizeof(int) * 2, s);
@@ -884,7 +984,7 @@ static int engine_crp_verify(rofl_engine &e, const uint8_t *h_proof, const uint8
     sc_st h_s[4]; sc_to_st(h_s[0], nzm); sc_to_st(h_s[1], nzr); sc_to_st(h_s[2], nzr); sc_to_st(h_s[3], zero);      // sB = [-z_m, -z_r], sH = [-z_r, 0]
     dev_buf d_s(sizeof(sc_st) * 4, s), d_id(sizeof(int) * 2, s);
     rt_h2d(d_s.p, h_s, sizeof(h_s), s);
-    finalize_args f = {}; f.partial = d_cp.as<p3_st>(); f.npartial = 1; f.sBa = d_s.as<sc_st>(); f.sHa = d_s.as<sc_st>() + 2; f.tabB = e.tabB; f.tabH = e.tabH;
+    finalize_args f = {}; f.partial = d_cp.as<p3_st>(); f.npartial = 1; f.sBa = d_s.as<sc_st>(); f.sHa = d_s.as<sc_st>() + 2; f.tabB = e.sh->tabB; f.tabH = e.sh->tabH;
     f.is_id = d_id.as<int>(); f.count = 2;
     if (D) {
         dev_buf d_ct(sizeof(sc_st) * (32 + ((size_t)2 << ((ilog2_sz(D + 2) + 1) / 2 + 1))), s), d_pw(sizeof(sc_st) * D, s);
@@ -913,12 +1013,12 @@ static int engine_sigma_prove(rofl_engine &e, int kind, const float *d_values, c
                               int n_bits, int frac, const uint8_t seed[32], uint8_t *d_proofs, uint8_t *d_commits) {
     if (!fp_ok(n_bits, frac) || (kind != 1 && kind != 2)) return -2;
     if (D == 0) return 0;
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     dev_buf d_flags(sizeof(int), s); rt_memset(d_flags.p, 0, sizeof(int), s);
     sigma_args a = {}; a.kind = kind; a.values = d_values; a.value_com = d_value_com; a.r1 = d_r1; a.r2 = d_r2; a.D = D; a.n_bits = n_bits; a.frac = frac;
     uint8_t key[32]; derive_key(key, seed, kind == 1 ? DOM_RANDPROOF : DOM_SQUARE_RAND, 0); key_words(a.key, key);
-    a.tabB = e.tabB; a.tabH = e.tabH; a.proofs = d_proofs; a.commits = d_commits; a.flags = d_flags.as<int>();
+    a.tabB = e.sh->tabB; a.tabH = e.sh->tabH; a.proofs = d_proofs; a.commits = d_commits; a.flags = d_flags.as<int>();
     void *tk = rt_prof_begin(PROF_SQUARE, s);
     LAUNCH(k_sigma_prove, dim3((unsigned)((D + 127) / 128)), dim3(128), s, a);
     rt_prof_end(PROF_SQUARE, tk, s);
@@ -930,10 +1030,10 @@ static int engine_sigma_prove(rofl_engine &e, int kind, const float *d_values, c
 static int engine_sigma_verify(rofl_engine &e, int kind, const uint8_t *d_proofs, const uint8_t *d_commits, size_t D) {
     if (kind != 1 && kind != 2) return -2;
     if (D == 0) return 1;
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     dev_buf d_res(2 * sizeof(int), s); int init[2] = {1, 0}; rt_h2d(d_res.p, init, sizeof(init), s);
-    LAUNCH(k_sigma_verify, dim3((unsigned)((D + 127) / 128)), dim3(128), s, kind, d_proofs, d_commits, D, e.tabB, e.tabH, d_res.as<int>());
+    LAUNCH(k_sigma_verify, dim3((unsigned)((D + 127) / 128)), dim3(128), s, kind, d_proofs, d_commits, D, e.sh->tabB, e.sh->tabH, d_res.as<int>());
     int res[2]; rt_d2h(res, d_res.p, sizeof(res), s); rt_sync(s);
     if (res[1]) return -1;
     return res[0] ? 1 : 0;
@@ -941,13 +1041,13 @@ static int engine_sigma_verify(rofl_engine &e, int kind, const uint8_t *d_proofs
 
 // sum of D compressed points -> compressed (device in, host out); -4 if one does not decode
 static int engine_points_sum(rofl_engine &e, const uint8_t *d_pts, size_t D, uint8_t *h_out32) {
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     const int nb = (int)std::max<size_t>(1, std::min<size_t>(296, (D + 127) / 128));
     dev_buf d_part(sizeof(p3_st) * nb, s), d_bad(sizeof(int), s), d_out(32, s);
     rt_memset(d_bad.p, 0, sizeof(int), s);
     LAUNCH_COOP(k_points_sum, dim3(nb), dim3(128), s, d_part.as<p3_st>(), d_pts, D, d_bad.as<int>());
-    finalize_args f = {}; f.partial = d_part.as<p3_st>(); f.npartial = nb; f.tabB = e.tabB; f.tabH = e.tabH; f.out32 = d_out.as<uint8_t>(); f.count = 1;
+    finalize_args f = {}; f.partial = d_part.as<p3_st>(); f.npartial = nb; f.tabB = e.sh->tabB; f.tabH = e.sh->tabH; f.out32 = d_out.as<uint8_t>(); f.count = 1;
     run_finalize(s, f);
     int bad = 0; rt_d2h(h_out32, d_out.p, 32, s); rt_d2h(&bad, d_bad.p, sizeof(int), s); rt_sync(s);
     return bad ? -4 : 0;
@@ -959,11 +1059,11 @@ static int engine_points_sum(rofl_engine &e, const uint8_t *d_pts, size_t D, uin
 static int engine_commit(rofl_engine &e, const float *d_values, const uint8_t *d_blind, size_t D, int n_bits, int frac, uint8_t *d_L, uint8_t *d_R) {
     if (!fp_ok(n_bits, frac)) return -2;
     if (D == 0) return 0;
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     dev_buf d_flags(sizeof(int), s); rt_memset(d_flags.p, 0, sizeof(int), s);
     commit_args ca = {}; ca.values = d_values; ca.blind = d_blind; ca.D = D; ca.Dp = D; ca.n_bits = n_bits; ca.frac = frac;
-    ca.tabB = e.tabB; ca.tabH = e.tabH; ca.C = d_L; ca.R = d_blind ? d_R : nullptr; ca.flags = d_flags.as<int>();
+    ca.tabB = e.sh->tabB; ca.tabH = e.sh->tabH; ca.C = d_L; ca.R = d_blind ? d_R : nullptr; ca.flags = d_flags.as<int>();
     void *tk = rt_prof_begin(PROF_COMMIT, s);
     LAUNCH(k_commit, dim3((unsigned)((D + 127) / 128)), dim3(128), s, ca);
     rt_prof_end(PROF_COMMIT, tk, s);
@@ -972,38 +1072,42 @@ static int engine_commit(rofl_engine &e, const float *d_values, const uint8_t *d
 }
 static int engine_aggregate(rofl_engine &e, const uint8_t *d_pts, size_t n_clients, size_t D, int init_base, uint8_t *d_out) {
     if (D == 0) return 0;
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
     dev_buf d_bad(sizeof(int), s); rt_memset(d_bad.p, 0, sizeof(int), s);
     LAUNCH(k_aggregate, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_out, d_pts, n_clients, D, init_base, d_bad.as<int>());
     int bad = 0; rt_d2h(&bad, d_bad.p, sizeof(int), s); rt_sync(s);
     return bad ? -4 : 0;
 }
-static bsgs_entry &engine_bsgs(rofl_engine &e, uint64_t table_size, int bsgs_bits) {
+static bsgs_entry engine_bsgs(rofl_engine &e, tables_use &tu, cudaStream_t s, uint64_t table_size, int bsgs_bits) {
+    dev_shared &sh = *e.sh;
     auto key = std::make_pair(table_size, bsgs_bits);
-    auto it = e.bsgs.find(key);
-    if (it != e.bsgs.end()) return it->second;
-    cudaStream_t s = e.stream;
-    bsgs_entry b; b.cap = 1; while (b.cap < 4 * (table_size + 1)) b.cap <<= 1;
-    b.keys = (unsigned long long *)rt_malloc(8 * (size_t)b.cap, s); b.vals = (uint32_t *)rt_malloc(4 * (size_t)b.cap, s);
-    rt_memset(b.keys, 0xff, 8 * (size_t)b.cap, s); rt_memset(b.vals, 0, 4 * (size_t)b.cap, s);
-    dev_buf d_cnt(sizeof(int), s); rt_memset(d_cnt.p, 0, sizeof(int), s);
-    LAUNCH(k_bsgs_build, dim3((unsigned)((table_size + 1 + 127) / 128)), dim3(128), s, b.keys, b.vals, b.cap, (uint32_t)table_size, e.tabB, d_cnt.as<int>());
-    int cnt = 0; rt_d2h(&cnt, d_cnt.p, sizeof(int), s); rt_sync(s);
-    b.size = (uint64_t)cnt - 1;                                                   // get_size (bsgs32.rs:44-46)
-    return e.bsgs[key] = b;
+    for (;;) {
+        auto it = sh.bsgs.find(key);
+        if (it != sh.bsgs.end()) return it->second;
+        if (!tu.excl) { tu.upgrade(); continue; }
+        bsgs_entry b; b.cap = 1; while (b.cap < 4 * (table_size + 1)) b.cap <<= 1;
+        b.keys = (unsigned long long *)rt_raw_malloc(8 * (size_t)b.cap); b.vals = (uint32_t *)rt_raw_malloc(4 * (size_t)b.cap);
+        rt_memset(b.keys, 0xff, 8 * (size_t)b.cap, s); rt_memset(b.vals, 0, 4 * (size_t)b.cap, s);
+        dev_buf d_cnt(sizeof(int), s); rt_memset(d_cnt.p, 0, sizeof(int), s);
+        LAUNCH(k_bsgs_build, dim3((unsigned)((table_size + 1 + 127) / 128)), dim3(128), s, b.keys, b.vals, b.cap, (uint32_t)table_size, sh.tabB, d_cnt.as<int>());
+        int cnt = 0; rt_d2h(&cnt, d_cnt.p, sizeof(int), s); rt_sync(s);
+        b.size = (uint64_t)cnt - 1;                                                   // get_size (bsgs32.rs:44-46)
+        sh.bsgs[key] = b;
+    }
 }
 // returns 0, -4 undecodable point, -5 where the reference panics (no discrete log within range for either sign, bsgs32.rs:69-70)
 static int engine_dlog(rofl_engine &e, const uint8_t *d_pts, size_t D, uint64_t table_size, int bsgs_bits, int n_bits, int frac, uint8_t *d_out_sc, float *d_out_f32) {
     if (table_size == 0 || table_size > (1ull << 28) || bsgs_bits < 1 || bsgs_bits > 32) return -2;
     if (D == 0) return 0;
-    std::lock_guard<std::mutex> lk(e.mu);
-    cudaStream_t s = e.stream;
-    bsgs_entry &b = engine_bsgs(e, table_size, bsgs_bits);
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
+    tables_use tu(*e.sh);
+    const bsgs_entry b = engine_bsgs(e, tu, s, table_size, bsgs_bits);
     uint64_t max_it = b.size ? (1ULL << bsgs_bits) / b.size : 0;                  // bsgs32.rs:60-62
     dev_buf d_flags(sizeof(int), s); rt_memset(d_flags.p, 0, sizeof(int), s);
     LAUNCH(k_bsgs_solve, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_out_sc, d_out_f32, d_pts, D, b.keys, b.vals, b.cap, (uint32_t)table_size, b.size, max_it,
-           bsgs_bits, n_bits, frac, e.tabB, d_flags.as<int>());
+           bsgs_bits, n_bits, frac, e.sh->tabB, d_flags.as<int>());
     int flags = 0; rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_sync(s);
     if (flags & 4) return -4;
     if (flags & 8) return -5;

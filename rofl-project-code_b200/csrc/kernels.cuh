@@ -412,7 +412,7 @@ struct finalize_args {
 #ifdef KG_MSM
 KERNEL void LB(FIN_THREADS, 1) k_finalize(finalize_args a) {
     __shared__ p3_st sw[MSM_MAXW + 3];
-    __shared__ p3_st ex[32];
+    __shared__ p3_st ex[96];
     const int idx = blockIdx.x, tid = threadIdx.x;
     if (a.windows && tid < a.nw) {
         const p3_st *src = a.windows + (size_t)idx * a.slices * a.nw + tid;
@@ -420,18 +420,28 @@ KERNEL void LB(FIN_THREADS, 1) k_finalize(finalize_args a) {
         for (uint32_t s = 1; s < a.slices; s++) acc_add_p3(r, src + (size_t)s * a.nw, false);
         st_p3(sw + tid, r);
     }
-    if (tid >= 96) {
-        const int j = tid - 96;
+    // 96 helper threads: one radix-256 window of sB*B each (32), one of sH*H each (32), the extra points (32, strided); then a tree over the 96
+    if (tid >= 32) {
+        const int j = tid - 32;
         ge_p3 r; ge_p3_0(r);
-        if (j == 0) { if (a.sBa) { sc s; ld_sc(s, a.sBa + idx); if (a.sBb) { sc t; ld_sc(t, a.sBb + idx); sc_mul(s, s, t); } fb_mul_acc(r, a.tabB, s, 32); } }
-        else if (j == 1) { if (a.sHa) { sc s; ld_sc(s, a.sHa + idx); if (a.sHb) { sc t; ld_sc(t, a.sHb + idx); sc_mul(s, s, t); } fb_mul_acc(r, a.tabH, s, 32); } }
-        else for (int k = j - 2; k < a.npartial; k += 30) acc_add_p3(r, a.partial + (size_t)idx * a.npartial + k, false);
+        if (j < 64) {
+            const bool isH = j >= 32; const int w = j & 31;
+            const sc_st *sa = isH ? a.sHa : a.sBa, *sb = isH ? a.sHb : a.sBb;
+            if (sa) {
+                sc s; ld_sc(s, sa + idx); if (sb) { sc t; ld_sc(t, sb + idx); sc_mul(s, s, t); }
+                int16_t d[32]; sc_radix256(d, s);
+                const int di = d[w];
+                if (di != 0) { ge_niels n; ld_niels(n, (isH ? a.tabH : a.tabB) + w * FB_ENTRIES + (di > 0 ? di : -di) - 1); ge_madd_signed(r, r, n, di < 0); }
+            }
+        } else for (int k = j - 64; k < a.npartial; k += 32) acc_add_p3(r, a.partial + (size_t)idx * a.npartial + k, false);
         st_p3(ex + j, r);
     }
     __syncthreads();
-    for (int s = 16; s > 0; s >>= 1) {
-        if (tid >= 96 && tid - 96 < s) { ge_p3 x, y; ld_p3(x, ex + tid - 96); ld_p3(y, ex + tid - 96 + s); ge_add(x, x, y); st_p3(ex + tid - 96, x); }
+    for (int n = 96; n > 1;) {
+        const int half = (n + 1) / 2;
+        if (tid < n - half) { ge_p3 x, y; ld_p3(x, ex + tid); ld_p3(y, ex + tid + half); ge_add(x, x, y); st_p3(ex + tid, x); }
         __syncthreads();
+        n = half;
     }
     if (tid != 0) return;
     ge_p3 r; ld_p3(r, ex);

@@ -64,7 +64,7 @@ extern "C" double rofl_probe_imad_wide(rofl_ctx *c) {
     if (!c) return 0.0;
     try {
         rt_set_device(c->e.device);
-        std::lock_guard<std::mutex> lk(c->e.mu); cudaStream_t s = c->e.stream;
+        lane_guard lg(c->e); cudaStream_t s = lg.s();
         cudaDeviceProp prop; rt_check(cudaGetDeviceProperties(&prop, c->e.device), "props");
         const int tpb = 256, blocks = prop.multiProcessorCount * 32, iters = 4096;
         dev_buf buf(sizeof(uint64_t) * (size_t)tpb * blocks, s);
@@ -81,7 +81,7 @@ extern "C" double rofl_probe_imad_wide(rofl_ctx *c) {
         return (double)tpb * blocks * iters * 8 / (best * 1e-3);
     } catch (const std::exception &ex) { g_last_error = ex.what(); return 0.0; }
 }
-extern "C" void *rofl_ctx_stream(rofl_ctx *c) { return c ? (void *)c->e.stream : nullptr; }
+extern "C" void *rofl_ctx_stream(rofl_ctx *c) { return (c && !c->e.lanes.empty()) ? (void *)c->e.lanes[0]->q[0].hi : nullptr; }      // lane 0: the one a single-threaded caller always gets
 
 
 // Diagnostic (ROFL_JITTER=1): a busy host thread that records the largest gap between two of its own clock readings per 100 ms
@@ -118,14 +118,9 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
         jitter_start();
         rofl_ctx *c = new rofl_ctx();
         c->e.device = device;
-        rt_check(cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking), "cudaStreamCreate");
-        // keep freed scratch in the pool between calls
-        // (scratch comes from rt.cuh's own block cache, not from the CUDA stream-ordered pool: see rt_malloc)
         unsigned hc = std::thread::hardware_concurrency(); c->e.host_threads = hc ? (int)std::min(hc, 32u) : 8;
-        c->e.gstreams.push_back(c->e.stream);
-        for (int i = 1; i < 4; i++) { cudaStream_t st; rt_check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate"); c->e.gstreams.push_back(st); }
-        for (int i = 0; i < 4; i++) { cudaStream_t st; rt_check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate"); c->e.sstreams.push_back(st); }
-        if (const char *gv = getenv("ROFL_GROUPS")) c->e.groups = std::max(1, std::min(4, atoi(gv)));
+        if (const char *gv = getenv("ROFL_GROUPS")) c->e.groups = std::max(1, std::min(ROFL_MAX_GROUPS, atoi(gv)));
+        if (const char *gv = getenv("ROFL_RT_PER")) c->e.rt_per = std::max(0, std::min(64, atoi(gv)));                     // table-MSM terms per thread (0 = one wave)
         if (const char *gv = getenv("ROFL_RT")) c->e.use_rt = atoi(gv);                                   // 0 disables the generator tables
         if (const char *gv = getenv("ROFL_UNFOLD")) c->e.rt_unfold = std::max(0, std::min(6, atoi(gv)));   // unfolded IPP rounds (RT path)
         if (const char *gv = getenv("ROFL_RT_BITS")) c->e.rt_bits = std::max(8, std::min(RT_MAX_BITS, atoi(gv)));              // generator-table radix
@@ -138,6 +133,6 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
 }
 extern "C" void rofl_ctx_destroy(rofl_ctx *c) {
     if (!c) return;
-    try { cudaSetDevice(c->e.device); engine_destroy(c->e); for (auto st : c->e.gstreams) cudaStreamDestroy(st); for (auto st : c->e.sstreams) cudaStreamDestroy(st); } catch (...) {}
+    try { cudaSetDevice(c->e.device); engine_destroy(c->e); } catch (...) {}
     delete c;
 }

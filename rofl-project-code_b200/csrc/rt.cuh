@@ -42,6 +42,11 @@ inline void rt_memset(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n);
 inline void rt_sync(cudaStream_t) {}
 inline size_t rt_free_mem() { return (size_t)8 << 30; }
 inline void rt_stream_after(cudaStream_t, cudaStream_t) {}
+inline cudaStream_t rt_stream_create(bool) { return nullptr; }
+inline void rt_stream_destroy(cudaStream_t) {}
+inline void *rt_raw_malloc(size_t n) { return rt_malloc(n, nullptr); }
+inline void rt_raw_free(void *p) { free(p); }
+inline void rt_trim() {}
 inline void *rt_host_alloc(size_t n) { return malloc(n ? n : 1); }
 inline void rt_set_device(int) {}
 inline void rt_host_free(void *p) { free(p); }
@@ -84,7 +89,7 @@ struct rt_big_cache {
         static const bool trace = getenv("ROFL_ALLOC_TRACE") != nullptr;
         if (trace && (!found || b.s != s)) fprintf(stderr, "[rofl alloc] %s %zu bytes (block %zu) stream %p\n", found ? "cross-stream reuse" : "cudaMalloc", n, found ? b.n : n, (void *)s);
         if (found) { if (b.s != s) rt_check(cudaStreamWaitEvent(s, b.ev, 0), "cudaStreamWaitEvent"); }
-        else if (cudaMalloc(&b.p, n) == cudaSuccess) { b.n = n; b.dev = dev; rt_check(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming), "cudaEventCreate"); }
+        else if (cudaMalloc(&b.p, n) == cudaSuccess || (cudaGetLastError(), trim(), cudaMalloc(&b.p, n) == cudaSuccess)) { b.n = n; b.dev = dev; rt_check(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming), "cudaEventCreate"); }
         else {                                                       // out of memory: now a wait on another stream's block is the lesser evil
             cudaGetLastError();
             std::lock_guard<std::mutex> lk(mu);
@@ -98,6 +103,14 @@ struct rt_big_cache {
         b.s = s;
         std::lock_guard<std::mutex> lk(mu); live.push_back(b);
         return b.p;
+    }
+    // hand every cached free block of this device back to CUDA (before a large long-lived allocation measures the free memory, or when cudaMalloc fails)
+    void trim() {
+        int dev = 0; cudaGetDevice(&dev);
+        std::vector<rt_big_block> out;
+        { std::lock_guard<std::mutex> lk(mu);
+          for (size_t i = 0; i < free_list.size();) { if (free_list[i].dev == dev) { out.push_back(free_list[i]); free_list.erase(free_list.begin() + i); } else i++; } }
+        for (auto &b : out) { cudaEventSynchronize(b.ev); cudaFree(b.p); cudaEventDestroy(b.ev); }
     }
     bool give(void *p, cudaStream_t s) {
         std::lock_guard<std::mutex> lk(mu);
@@ -131,6 +144,16 @@ inline void rt_sync(cudaStream_t s) {
     }
 }
 inline size_t rt_free_mem() { size_t f = 0, t = 0; cudaMemGetInfo(&f, &t); return f; }
+inline void rt_trim() { rt_bigs().trim(); }
+// long-lived allocations (generator tables, BSGS tables): straight from / back to CUDA, never through the scratch cache
+inline void *rt_raw_malloc(size_t n) { void *p = nullptr; if (cudaMalloc(&p, n ? n : 256) != cudaSuccess) { cudaGetLastError(); rt_trim(); rt_check(cudaMalloc(&p, n ? n : 256), "cudaMalloc"); } return p; }
+inline void rt_raw_free(void *p) { if (p) cudaFree(p); }
+// high = the greatest priority of the device: pending blocks of such a stream are dispatched before those of normal streams
+inline cudaStream_t rt_stream_create(bool high) {
+    int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStream_t s; rt_check(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high ? hi : lo), "cudaStreamCreateWithPriority"); return s;
+}
+inline void rt_stream_destroy(cudaStream_t s) { if (s) cudaStreamDestroy(s); }
 // work queued on `waiter` from now on starts after everything queued on `producer` so far (fork / join of a side stream)
 inline void rt_stream_after(cudaStream_t waiter, cudaStream_t producer) {
     if (waiter == producer) return;
@@ -149,11 +172,24 @@ void rt_prof_work(int slot, double units);        // algorithmic work of the lau
 #define LAUNCH(k, grid, block, stream, ...) launch_##k(grid, block, stream, __VA_ARGS__)
 #define LAUNCH_COOP LAUNCH
 
+// One logical in-order queue over two CUDA streams of different priority.  The prover's throughput kernels (table MSMs, catch-up, table
+// builds: thousands of long-running blocks) go to `lo`, the short latency-bound kernels of the Fiat-Shamir chain to `hi`, so that the chain
+// of one chunk group is dispatched ahead of the bulk work of the other groups instead of waiting for a block slot behind it (DESIGN.md
+// section 3 "scheduling").  Every switch is an event dependency, so the order of the queue is the program order.
+struct chain {
+    cudaStream_t hi = nullptr, lo = nullptr; int cur = 0;
+    chain() {}
+    chain(cudaStream_t h, cudaStream_t l) : hi(h), lo(l ? l : h) {}
+    cudaStream_t on(int big) { if (big != cur) { rt_stream_after(big ? lo : hi, cur ? lo : hi); cur = big; } return cur ? lo : hi; }
+    cudaStream_t small() { return on(0); }
+    cudaStream_t big() { return on(1); }
+};
 // stream-ordered scratch allocation with scope lifetime
 struct dev_buf {
-    void *p = nullptr; cudaStream_t s;
+    void *p = nullptr; cudaStream_t s; chain *q = nullptr;
     dev_buf(size_t n, cudaStream_t st) : s(st) { p = rt_malloc(n, st); }
-    ~dev_buf() { rt_free(p, s); }
+    dev_buf(size_t n, chain &c) : s(c.hi), q(&c) { p = rt_malloc(n, c.hi); }          // owned by the queue: returned on its `hi` stream after joining `lo`
+    ~dev_buf() { rt_free(p, q ? q->small() : s); }
     dev_buf(const dev_buf &) = delete; dev_buf &operator=(const dev_buf &) = delete;
     template <class T> T *as() const { return (T *)p; }
 };

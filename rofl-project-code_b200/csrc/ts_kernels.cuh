@@ -34,16 +34,17 @@ struct strobe_sh { uint64_t st[25]; uint64_t C[5]; uint64_t B[25]; uint32_t pos,
 DEV void keccak_coop(strobe_sh &h, int lane) {
     const int x = lane % 5, row = lane - x;
     const int src = lane < 25 ? KC_SRC_[lane] : 0, rot = lane < 25 ? KC_ROT_[lane] : 0, sx = src % 5;
+    const int d1 = (sx + 4) % 5, d2 = (sx + 1) % 5, c1 = row + (x + 1) % 5, c2 = row + (x + 2) % 5;
     for (int r = 0; r < 24; r++) {
         if (lane < 5) h.C[lane] = h.st[lane] ^ h.st[lane + 5] ^ h.st[lane + 10] ^ h.st[lane + 15] ^ h.st[lane + 20];
         TS_WSYNC();
         if (lane < 25) {
-            const uint64_t v = h.st[src] ^ h.C[(sx + 4) % 5] ^ rotl64_(h.C[(sx + 1) % 5], 1);
+            const uint64_t v = h.st[src] ^ h.C[d1] ^ rotl64_(h.C[d2], 1);
             h.B[lane] = rot ? rotl64_(v, rot) : v;
         }
         TS_WSYNC();
         if (lane < 25) {
-            uint64_t v = h.B[lane] ^ (~h.B[row + (x + 1) % 5] & h.B[row + (x + 2) % 5]);
+            uint64_t v = h.B[lane] ^ (~h.B[c1] & h.B[c2]);
             if (lane == 0) v ^= KECCAK_RC_[r];
             h.st[lane] = v;
         }
@@ -55,33 +56,35 @@ DEV void keccak_coop(strobe_sh &h, int lane) {
 // where the two pos_begin bytes are (begin position of the PREVIOUS operation) + 1 if that operation began in the current sponge
 // block and 0 otherwise (Strobe128::begin_op / run_f).  Byte k of the stream lands at absolute position A0 + k
 // (A0 = position at entry), so every byte is a function of k alone and the lanes fill a 166-byte block together.
-DEV void strobe_absorb_many_coop(strobe_sh &h, int lane, uint8_t label, const uint8_t *msgs, size_t m) {
+DEV void strobe_absorb_many_coop(strobe_sh &h, int lane, uint8_t label, const uint8_t *msgs, uint32_t m) {
     if (m == 0) return;
-    const uint64_t A0 = h.pos, total = 41 * (uint64_t)m, A_end = A0 + total, nfull = A_end / STROBE_R;
+    // 32-bit positions (m < 2^26 commitments per chunk): constant divisions become multiply-shifts, a 64-bit division costs ~100 instructions
+    const uint32_t A0 = h.pos, total = 41u * m, A_end = A0 + total, nfull = A_end / STROBE_R;
     const uint8_t pb0 = (uint8_t)h.pos_begin;
     uint8_t *st8 = (uint8_t *)h.st;
-    for (uint64_t e = 0; e <= nfull; e++) {
+    for (uint32_t e = 0; e <= nfull; e++) {
+        const uint32_t base = STROBE_R * e;
         for (uint32_t p = lane; p < STROBE_R; p += TS_THREADS) {
-            const uint64_t A = STROBE_R * e + p;
+            const uint32_t A = base + p;
             if (A < A0 || A >= A_end) continue;
-            const uint64_t k = A - A0, j = k / 41, a1 = A0 + 41 * j, a2 = a1 + 7; const uint32_t r = (uint32_t)(k % 41);
+            const uint32_t k = A - A0, j = k / 41u, r = k - 41u * j, a1 = A0 + 41u * j, a2 = a1 + 7;
             uint8_t b;
-            if (r == 0) { const uint64_t ap = a1 - 34; b = j == 0 ? pb0 : (ap / STROBE_R == a1 / STROBE_R ? (uint8_t)(ap % STROBE_R + 1) : 0); }
+            if (r >= 9) b = msgs[32 * (size_t)j + (r - 9)];
+            else if (r == 0) { const uint32_t ap = a1 - 34; b = j == 0 ? pb0 : (ap >= base ? (uint8_t)(ap - base + 1) : 0); }      // a1 lies in block e (it IS position A)
             else if (r == 1) b = 0x12;
             else if (r == 2) b = label;
             else if (r == 3) b = 32;
             else if (r < 7) b = 0;
-            else if (r == 7) b = a1 / STROBE_R == a2 / STROBE_R ? (uint8_t)(a1 % STROBE_R + 1) : 0;
-            else if (r == 8) b = 0x02;
-            else b = msgs[32 * j + (r - 9)];
+            else if (r == 7) b = a1 >= base ? (uint8_t)(a1 - base + 1) : 0;                                                     // a2 = A lies in block e
+            else b = 0x02;
             st8[p] ^= b;
         }
         TS_WSYNC();
         if (e < nfull) {                      // run_f closing block e: pos = 166, pos_begin = begin of the last operation if it lies in this block
             if (lane == 0) {
-                const uint64_t last = STROBE_R * e + (STROBE_R - 1), k = last - A0, j = k / 41; const uint32_t r = (uint32_t)(k % 41);
-                const uint64_t a = A0 + 41 * j + (r >= 7 ? 7 : 0);
-                st8[STROBE_R] ^= a / STROBE_R == e ? (uint8_t)(a % STROBE_R + 1) : 0;
+                const uint32_t last = base + (STROBE_R - 1), k = last - A0, j = k / 41u, r = k - 41u * j;
+                const uint32_t a = A0 + 41u * j + (r >= 7 ? 7 : 0);
+                st8[STROBE_R] ^= a >= base ? (uint8_t)(a - base + 1) : 0;
                 st8[STROBE_R + 1] ^= 0x04 ^ 0x80;
             }
             TS_WSYNC();
@@ -89,9 +92,9 @@ DEV void strobe_absorb_many_coop(strobe_sh &h, int lane, uint8_t label, const ui
         }
     }
     if (lane == 0) {
-        const uint64_t a2l = A0 + 41 * (uint64_t)(m - 1) + 7;
-        h.pos = (uint32_t)(A_end % STROBE_R);
-        h.pos_begin = a2l / STROBE_R == A_end / STROBE_R ? (uint32_t)(a2l % STROBE_R + 1) : 0;
+        const uint32_t a2l = A0 + 41u * (m - 1) + 7, cur = A_end / STROBE_R * STROBE_R;
+        h.pos = A_end - cur;
+        h.pos_begin = a2l >= cur ? a2l - cur + 1 : 0;
     }
     TS_WSYNC();
 }

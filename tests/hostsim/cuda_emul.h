@@ -10,6 +10,7 @@
 #include <barrier>
 #include <functional>
 #include <memory>
+#include <mutex>
 
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 inline thread_local dim3 threadIdx, blockIdx;
@@ -33,7 +34,9 @@ typedef void *cudaStream_t;
 enum { cudaSuccess = 0 };
 
 // cooperative launch: one OS thread per CUDA thread of a block, blocks run one after another
+inline std::mutex &emu_launch_mu() { static std::mutex m; return m; }
 template <class F> void emu_launch(dim3 grid, dim3 block, bool coop, F body) {
+    std::lock_guard<std::mutex> one_at_a_time(emu_launch_mu());      // gridDim / blockDim / `__shared__` statics are process-wide: launches of different host threads (chunk groups) take turns
     gridDim = grid; blockDim = block;
     for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
         if (!coop) {

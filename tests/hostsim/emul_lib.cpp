@@ -7,7 +7,7 @@
 #include "../../rofl-project-code_b200/csrc/capi.cuh"
 #pragma GCC visibility push(default)
 extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
-    rofl_ctx *c = new rofl_ctx(); c->e.device = device; c->e.stream = nullptr; c->e.host_threads = 4; c->e.rt_bits = 8;   // small tables: the CPU emulation builds them thread by thread
+    rofl_ctx *c = new rofl_ctx(); c->e.device = device; c->e.host_threads = 4; c->e.rt_bits = 8;   // small tables: the CPU emulation builds them thread by thread
     engine_init(c->e); *out = c; return 0;
 }
 extern "C" void rofl_ctx_destroy(rofl_ctx *c) { if (!c) return; engine_destroy(c->e); delete c; }

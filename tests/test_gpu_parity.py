@@ -508,3 +508,33 @@ def test_l2_compressed_message_with_undecodable_point_is_refused(api, oracle):
         assert api.enc_l2_compressed_verify(bad, seed) == -4, col
     ok = dict(m); ok["enc_values"] = m["enc_values"].copy(); ok["enc_values"][1, 32:64] = np.frombuffer(oracle.basepoint(), np.uint8)
     assert api.enc_l2_compressed_verify(ok, seed) == 1          # a valid but different R: this arm does not check the rand proof (params.rs:257-289)
+
+
+def test_concurrent_callers_share_one_context(api, oracle):      # a threaded test with 8 callers on one GPU
+    """rofl_service calls verify() for many clients at once from a rayon pool (server.rs:516-522,666) and proves several clients per process
+    (bin/basic_client.rs:136-161): concurrent callers of ONE context run on separate lanes (streams) and share the cached tables; every
+    caller must get exactly the bytes / verdicts of a lone caller."""
+    import threading
+    rng = np.random.default_rng(80)
+    jobs = []
+    for k in range(8):
+        D = [5000, 800, 62006, 1600, 70, 4000, 12000, 9][k]; P = [64, 4, 64, 16, 2, 64, 32, 1][k]
+        v = rng.uniform(-0.9, 0.9, D).astype(np.float32); bl = oracle.rnd_scalar_vec(bytes([0x60 + k]) * 32, D)
+        jobs.append((v, bl, P, bytes([0x20 + k]) * 32))
+    want = [api.range_prove(v, bl, 8, P, 16, 7, seed) for v, bl, P, seed in jobs]
+    got, errs = [None] * len(jobs), []
+    def run(i):
+        try:
+            v, bl, P, seed = jobs[i]
+            rc, p, c = api.range_prove(v, bl, 8, P, 16, 7, seed)
+            ok = api.range_verify(p, c, 8, seed)
+            bad = c.copy(); bad[0] = c[-1] if len(c) > 1 else np.frombuffer(oracle.basepoint(), np.uint8)
+            got[i] = (rc, p, c, ok, api.range_verify(p, bad, 8, seed))
+        except Exception as ex:  # noqa: BLE001
+            errs.append(repr(ex))
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+    for x in th: x.start()
+    for x in th: x.join()
+    assert not errs, errs
+    for (rc0, p0, c0), (rc, p, c, ok, okbad) in zip(want, got):
+        assert rc == rc0 == 0 and (p == p0).all() and (c == c0).all() and ok == 1 and okbad == 0
