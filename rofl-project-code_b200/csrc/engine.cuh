@@ -69,13 +69,19 @@ struct rofl_engine {
     std::mutex pin_mu; std::vector<std::pair<void *, size_t>> pins;      // pool of pinned host blocks
     int use_frz = 1;                      // middle IPP rounds over frozen generators with on-the-fly Straus tables (kernels.cuh K6c)
     int rt_bits = RT_MAX_BITS;            // widest generator-table radix to try (8..11)
+    double group_w[ROFL_MAX_GROUPS] = {1.0, 1.0, 1.0, 1.0};      // relative chunk counts of the groups
+    int ts_host_m = 8192;                 // chunks with more commitments than this absorb them on the host (absorb_commitments)
     int rt_per = 2;                       // table-MSM terms per thread and block: short blocks let the other groups' small kernels in quickly
     double rt_mem_frac = 0.45;            // tables may take this fraction of the free device memory
 };
 static thread_local lane *tl_lane = nullptr; static thread_local rofl_engine *tl_lane_engine = nullptr; static thread_local int tl_lane_depth = 0;
 static inline lane *lane_new() {
     lane *l = new lane();
-    for (int g = 0; g < ROFL_MAX_GROUPS; g++) { cudaStream_t hi = rt_stream_create(true), lo = rt_stream_create(false); l->q[g] = chain(hi, lo); l->side[g] = rt_stream_create(true); }
+    // the short kernels of every group's Fiat-Shamir chain run at the greatest priority; the bulk streams are ORDERED (group 0 before group 1
+    // before ..): equal priorities make the groups march in lock step (all in a bulk kernel, then all in a small one -- no overlap at all),
+    // ordered ones let group 0 race ahead, so that its latency-bound last rounds run under the bulk kernels of the groups behind it
+    static const int ordered = getenv("ROFL_PRIO_ORDERED") ? atoi(getenv("ROFL_PRIO_ORDERED")) : 1, flat = getenv("ROFL_PRIO_FLAT") != nullptr;
+    for (int g = 0; g < ROFL_MAX_GROUPS; g++) { cudaStream_t hi = rt_stream_create(flat ? 1 : 0), lo = rt_stream_create(ordered ? 1 + g : 1); l->q[g] = chain(hi, lo); l->side[g] = rt_stream_create(0); }
     return l;
 }
 static inline void lane_delete(lane *l) { for (int g = 0; g < ROFL_MAX_GROUPS; g++) { rt_stream_destroy(l->q[g].hi); if (l->q[g].lo != l->q[g].hi) rt_stream_destroy(l->q[g].lo); rt_stream_destroy(l->side[g]); } delete l; }
@@ -338,6 +344,27 @@ static inline msm_seg mk_seg(const void *base, uint32_t count, uint32_t stride, 
 static inline void run_finalize(cudaStream_t s, const finalize_args &f) { LAUNCH_COOP(k_finalize, dim3(f.count), dim3(FIN_THREADS), s, f); }
 static inline void fin_windows(finalize_args &f, const p3_st *win, const msm_plan &p) { f.windows = win; f.c = p.c; f.nw = p.nw; f.slices = p.slices; }
 
+
+// V_1..V_m into the transcripts of C chunks.  Small chunks: on the device (ts_kernels.cuh, one warp per chunk, ~2.5 us per sponge block).  Large
+// chunks (resnet18-full: 2^18 commitments = 65 000 sequential Keccak-f per chunk, only C warps busy): the host's cores are ~5x faster per
+// permutation, so the commitments are copied out, absorbed by host threads (one per chunk) and the 208-byte states copied back.
+static void absorb_commitments(rofl_engine &e, cudaStream_t s, transcript *d_ts, const uint8_t *d_V32, int label_id, int n, int m, int C) {
+    if (m <= e.ts_host_m) {
+        ts_absorb_args aa = {}; aa.ts = d_ts; aa.V32 = d_V32; aa.m = (uint32_t)m; aa.n = (uint32_t)n; aa.label_id = label_id;
+        LAUNCH_COOP(k_ts_absorbV, dim3(C), dim3(TS_THREADS), s, aa);
+        return;
+    }
+    std::vector<uint8_t> hV(32 * (size_t)C * m); std::vector<transcript> ts(C);
+    rt_d2h(hV.data(), d_V32, hV.size(), s); rt_sync(s);
+    parallel_for(C, e.host_threads, [&](size_t c) {
+        transcript &t = ts[c]; transcript_init(t, label_id ? "L2RangeProof" : "RangeProof");
+        transcript_append(t, "dom-sep", (const uint8_t *)"rangeproof v1", 13);
+        transcript_append_u64(t, "n", (uint64_t)n); transcript_append_u64(t, "m", (uint64_t)m);
+        for (int j = 0; j < m; j++) transcript_append(t, "V", &hV[32 * (c * (size_t)m + j)], 32);
+    });
+    rt_h2d(d_ts, ts.data(), sizeof(transcript) * (size_t)C, s); rt_sync(s);
+}
+
 // =============================================================================================================================
 // RangeProof::prove_multiple for C chunks in lock step.  All pointers are device pointers except
 // h_proofs (host).  d_vals: C*m shifted values, d_blind: C*m blindings (reduced), d_V32: C*m compressed commitments.
@@ -352,8 +379,6 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
     // ---- device scratch.  The Merlin transcripts live on the device (ts_kernels.cuh): nothing below waits for the host until the proofs are copied out.
     dev_buf d_ts(sizeof(transcript) * (size_t)C, q), d_proofs(plen * (size_t)C, q);
     rt_stream_after(side, q.small());
-    { ts_absorb_args aa = {}; aa.ts = d_ts.as<transcript>(); aa.V32 = d_V32; aa.m = (uint32_t)m; aa.n = (uint32_t)n; aa.label_id = label_id;      // V_1..V_m: independent of A and S, so it
-      LAUNCH_COOP(k_ts_absorbV, dim3(C), dim3(TS_THREADS), side, aa); }                                                                         // runs beside them on the side stream
     dev_buf d_keys(32 * (size_t)C, q), d_sLR(sizeof(sc_st) * 2 * NT, q), d_sums(sizeof(sc_st) * 5 * C, q);
     { std::vector<uint32_t> kw(8 * (size_t)C); for (int c = 0; c < C; c++) key_words(&kw[8 * c], &keys[32 * c]); rt_h2d(d_keys.p, kw.data(), 32 * (size_t)C, q.small()); }
     LAUNCH(k_nonces, dim3((unsigned)((NT + 255) / 256)), dim3(256), q.big(), d_sLR.as<sc_st>(), d_keys.as<uint32_t>(), n, m, NT);
@@ -386,7 +411,8 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
         f.out32 = d_AS.as<uint8_t>() + 32 * (size_t)C; f.count = C;
         run_finalize(q.small(), f);
     }
-    // ---- transcripts: V..., A, S -> y, z
+    // ---- transcripts: V_1..V_m are independent of A and S: absorbed on the side stream while the kernels queued above run
+    absorb_commitments(e, side, d_ts.as<transcript>(), d_V32, label_id, n, m, C);
     rt_stream_after(q.small(), side);
     dev_buf d_ypow2(sizeof(sc_st) * 32 * C, q), d_zpow2(sizeof(sc_st) * 32 * C, q), d_yinvpow2(sizeof(sc_st) * 32 * C, q), d_z(sizeof(sc_st) * C, q);
     { ts_yz_args ya = {}; ya.ts = d_ts.as<transcript>(); ya.AS = d_AS.as<uint8_t>(); ya.proofs = d_proofs.as<uint8_t>(); ya.plen = (uint32_t)plen; ya.C = (uint32_t)C;
@@ -590,9 +616,14 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
 template <class F> static void for_chunk_groups(rofl_engine &e, lane &ln, size_t C, F f) {
     size_t G = std::max<size_t>(1, std::min<size_t>({(size_t)e.groups, (size_t)ROFL_MAX_GROUPS, C}));
     if (G == 1) { f(0, (size_t)0, C, ln.q[0], ln.side[0]); return; }
+    // chunk ranges proportional to the group weights: the LAST group's latency-bound end is the only one nothing overlaps, so it gets the fewest chunks
+    std::vector<size_t> cut(G + 1, 0); double tot = 0, acc = 0;
+    for (size_t gi = 0; gi < G; gi++) tot += e.group_w[gi];
+    for (size_t gi = 0; gi < G; gi++) { acc += e.group_w[gi]; cut[gi + 1] = gi + 1 == G ? C : std::min(C, std::max(cut[gi] + 1, (size_t)(acc / tot * (double)C + 0.5))); }
+    for (size_t gi = G; gi-- > 0;) if (cut[gi + 1] <= cut[gi]) cut[gi] = cut[gi + 1] - 1;          // every group at least one chunk
     std::vector<std::thread> th; std::vector<std::string> errs(G);
     for (size_t gi = 0; gi < G; gi++) th.emplace_back([&, gi] {
-        try { rt_set_device(e.device); f(gi, C * gi / G, C * (gi + 1) / G, ln.q[gi], ln.side[gi]); } catch (const std::exception &ex) { errs[gi] = ex.what(); }
+        try { rt_set_device(e.device); f(gi, cut[gi], cut[gi + 1], ln.q[gi], ln.side[gi]); } catch (const std::exception &ex) { errs[gi] = ex.what(); }
     });
     for (auto &t : th) t.join();
     for (auto &m : errs) if (!m.empty()) throw std::runtime_error(m);
@@ -688,8 +719,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, in
     dev_buf d_sp32(32 * (size_t)C * nsmall, s), d_sp(sizeof(p3_st) * (size_t)C * nsmall, s), d_bad(sizeof(int) * C, s), d_id(sizeof(int), s), d_fix(sizeof(p3_st), s);
     rt_h2d(d_proofs.p, h_proofs, plen * (size_t)C, s);
     rt_memset(d_bad.p, 0, sizeof(int) * C, s);
-    { ts_absorb_args aa = {}; aa.ts = d_ts.as<transcript>(); aa.V32 = d_V32; aa.m = (uint32_t)m; aa.n = (uint32_t)n; aa.label_id = label_id;
-      LAUNCH_COOP(k_ts_absorbV, dim3(C), dim3(TS_THREADS), s, aa); }
+    absorb_commitments(e, s, d_ts.as<transcript>(), d_V32, label_id, n, m, C);
     { ts_verify_args va = {}; va.ts = d_ts.as<transcript>(); va.proofs = d_proofs.as<uint8_t>(); va.plen = (uint32_t)plen; va.C = (uint32_t)C; va.lgN = lgN; va.N = (uint64_t)N;
       va.chal = d_vch.as<sc_st>(); va.digest = d_digest.as<uint8_t>(); va.bad = d_bad.as<int>(); va.sp32 = d_sp32.as<uint8_t>(); memcpy(va.B32, e.sh->B32, 32); memcpy(va.H32, e.sh->H32, 32);
       LAUNCH(k_ts_verify, dim3((unsigned)((C + TS_THREADS - 1) / TS_THREADS)), dim3(TS_THREADS), s, va); }

@@ -18,7 +18,7 @@
 #define LB(t, b) __launch_bounds__(t, b)
 #define DEV __device__ __forceinline__
 // host-side launcher defined next to each kernel (the kernels are split over several translation units, see Makefile)
-#define KLAUNCH(k, coop, PARAMS, ARGS) void launch_##k(dim3 g_, dim3 b_, cudaStream_t s_, KL_UNPACK PARAMS) { rt_host_timer t_(&rt_host_prof::launch, #k); k<<<g_, b_, 0, s_>>> ARGS; rt_check(cudaGetLastError(), #k); rt_count_launch(#k); }
+#define KLAUNCH(k, coop, PARAMS, ARGS) void launch_##k(dim3 g_, dim3 b_, cudaStream_t s_, KL_UNPACK PARAMS) { rt_host_timer t_(&rt_host_prof::launch, #k); void *tl_ = rt_timeline_begin(#k, s_, g_.x * g_.y * g_.z); k<<<g_, b_, 0, s_>>> ARGS; rt_check(cudaGetLastError(), #k); rt_timeline_end(tl_, s_); rt_count_launch(#k); }
 #else
 #define KERNEL static
 #define LB(t, b)

@@ -14,6 +14,29 @@ static double g_prof_work[PROF_SLOTS];
 static std::atomic<long> g_launches{0};
 
 void rt_count_launch(const char *) { g_launches++; }
+// ---- ROFL_TIMELINE=1: start / end of every kernel on its stream (events), relative to the first launch after the last dump
+struct tl_rec { const char *name; cudaStream_t s; unsigned blocks; cudaEvent_t a, b; };
+static std::mutex g_tl_mu; static std::vector<tl_rec *> g_tl; static cudaEvent_t g_tl_base = nullptr;
+static const bool g_tl_on = getenv("ROFL_TIMELINE") != nullptr;
+void *rt_timeline_begin(const char *name, cudaStream_t s, unsigned blocks) {
+    if (!g_tl_on) return nullptr;
+    tl_rec *r = new tl_rec{name, s, blocks, nullptr, nullptr};
+    cudaEventCreate(&r->a); cudaEventCreate(&r->b);
+    { std::lock_guard<std::mutex> lk(g_tl_mu); if (!g_tl_base) { cudaEventCreate(&g_tl_base); cudaEventRecord(g_tl_base, s); } g_tl.push_back(r); }
+    cudaEventRecord(r->a, s);
+    return r;
+}
+void rt_timeline_end(void *tok, cudaStream_t s) { if (tok) cudaEventRecord(((tl_rec *)tok)->b, s); }
+extern "C" void rofl_timeline_dump(const char *path) {
+    if (!g_tl_on) return;
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_tl_mu);
+    FILE *f = fopen(path, "a"); if (!f) return;
+    fprintf(f, "# name stream blocks start_ms end_ms\n");
+    for (tl_rec *r : g_tl) { float t0 = 0, t1 = 0; cudaEventElapsedTime(&t0, g_tl_base, r->a); cudaEventElapsedTime(&t1, g_tl_base, r->b); fprintf(f, "%s %p %u %.3f %.3f\n", r->name, (void *)r->s, r->blocks, t0, t1); cudaEventDestroy(r->a); cudaEventDestroy(r->b); delete r; }
+    g_tl.clear(); if (g_tl_base) { cudaEventDestroy(g_tl_base); g_tl_base = nullptr; }
+    fclose(f);
+}
 void *rt_prof_begin(int, cudaStream_t s) {
     if (!g_prof_on.load()) return nullptr;
     cudaEvent_t a; cudaEventCreate(&a); cudaEventRecord(a, s); return (void *)a;
@@ -121,6 +144,7 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
         unsigned hc = std::thread::hardware_concurrency(); c->e.host_threads = hc ? (int)std::min(hc, 32u) : 8;
         if (const char *gv = getenv("ROFL_GROUPS")) c->e.groups = std::max(1, std::min(ROFL_MAX_GROUPS, atoi(gv)));
         if (const char *gv = getenv("ROFL_RT_PER")) c->e.rt_per = std::max(0, std::min(64, atoi(gv)));                     // table-MSM terms per thread (0 = one wave)
+        if (const char *gv = getenv("ROFL_SPLIT")) { double w[ROFL_MAX_GROUPS]; int k = sscanf(gv, "%lf,%lf,%lf,%lf", &w[0], &w[1], &w[2], &w[3]); for (int i = 0; i < k; i++) if (w[i] > 0) c->e.group_w[i] = w[i]; }      // relative group sizes
         if (const char *gv = getenv("ROFL_RT")) c->e.use_rt = atoi(gv);                                   // 0 disables the generator tables
         if (const char *gv = getenv("ROFL_UNFOLD")) c->e.rt_unfold = std::max(0, std::min(6, atoi(gv)));   // unfolded IPP rounds (RT path)
         if (const char *gv = getenv("ROFL_RT_BITS")) c->e.rt_bits = std::max(8, std::min(RT_MAX_BITS, atoi(gv)));              // generator-table radix

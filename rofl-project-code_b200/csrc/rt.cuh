@@ -42,7 +42,7 @@ inline void rt_memset(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n);
 inline void rt_sync(cudaStream_t) {}
 inline size_t rt_free_mem() { return (size_t)8 << 30; }
 inline void rt_stream_after(cudaStream_t, cudaStream_t) {}
-inline cudaStream_t rt_stream_create(bool) { return nullptr; }
+inline cudaStream_t rt_stream_create(int) { return nullptr; }
 inline void rt_stream_destroy(cudaStream_t) {}
 inline void *rt_raw_malloc(size_t n) { return rt_malloc(n, nullptr); }
 inline void rt_raw_free(void *p) { free(p); }
@@ -60,6 +60,9 @@ inline void rt_check(cudaError_t e, const char *what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 void rt_count_launch(const char *name);
+// ROFL_TIMELINE=1 (diagnostic): a CUDA event before and after EVERY launch, dumped per stream by rofl_timeline_dump()
+void *rt_timeline_begin(const char *name, cudaStream_t s, unsigned blocks);
+void rt_timeline_end(void *tok, cudaStream_t s);
 // Scratch allocation: a process-wide cache of device blocks (cudaMalloc once, reused forever).  The CUDA stream-ordered pool was the
 // first choice, but with two chunk groups allocating and freeing on two streams it made one stream wait for the other's long kernels
 // (cross-stream reuse), and forbidding that reuse made the pool grow with real allocations in the middle of a proof.
@@ -148,10 +151,12 @@ inline void rt_trim() { rt_bigs().trim(); }
 // long-lived allocations (generator tables, BSGS tables): straight from / back to CUDA, never through the scratch cache
 inline void *rt_raw_malloc(size_t n) { void *p = nullptr; if (cudaMalloc(&p, n ? n : 256) != cudaSuccess) { cudaGetLastError(); rt_trim(); rt_check(cudaMalloc(&p, n ? n : 256), "cudaMalloc"); } return p; }
 inline void rt_raw_free(void *p) { if (p) cudaFree(p); }
-// high = the greatest priority of the device: pending blocks of such a stream are dispatched before those of normal streams
-inline cudaStream_t rt_stream_create(bool high) {
-    int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    cudaStream_t s; rt_check(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high ? hi : lo), "cudaStreamCreateWithPriority"); return s;
+// level 0 = the greatest priority of the device, 1, 2, .. = lower (clamped to the least): pending blocks of a higher-priority stream are
+// dispatched before those of lower ones whenever a block slot frees up (no preemption of running blocks)
+inline cudaStream_t rt_stream_create(int level) {
+    int least = 0, greatest = 0; cudaDeviceGetStreamPriorityRange(&least, &greatest);          // numerically: greatest <= least
+    int p = greatest + level; if (p > least) p = least;
+    cudaStream_t s; rt_check(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, p), "cudaStreamCreateWithPriority"); return s;
 }
 inline void rt_stream_destroy(cudaStream_t s) { if (s) cudaStreamDestroy(s); }
 // work queued on `waiter` from now on starts after everything queued on `producer` so far (fork / join of a side stream)

@@ -58,16 +58,26 @@ def prove_range_sharded(api, values, blind, range_bits, n_partition, n_bits, fra
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist is not None else (0, 1)
     sh = shard_of(D, n_partition, rank, world)
     e0, e1 = sh["elem_begin"], sh["elem_end"]
-    if sh["n_chunks"]:
-        rc, proofs, commits = api.range_prove_shard(values[e0:e1], blind[e0:e1], sh["chunk_len"], sh["chunk_begin"], sh["n_chunks"], range_bits, n_bits, frac, seed)
-    else:
-        rc, proofs, commits = 0, np.zeros((0, 0), np.uint8), np.zeros((0, 32), np.uint8)
+    err = None
+    try:
+        if sh["n_chunks"]:
+            rc, proofs, commits = api.range_prove_shard(values[e0:e1], blind[e0:e1], sh["chunk_len"], sh["chunk_begin"], sh["n_chunks"], range_bits, n_bits, frac, seed)
+        else:
+            rc, proofs, commits = 0, np.zeros((0, 0), np.uint8), np.zeros((0, 32), np.uint8)
+    except Exception as ex:  # noqa: BLE001  (a CUDA error on one rank must not leave the others hanging in the collective below)
+        err, rc, proofs, commits = ex, -100, np.zeros((0, 0), np.uint8), np.zeros((0, 32), np.uint8)
     if world == 1:
+        if err is not None:
+            raise err
         return rc, proofs, commits
     import torch
-    rcs = torch.tensor([rc], dtype=torch.int32, device=device); dist.all_reduce(rcs, op=dist.ReduceOp.MAX, group=group)
-    if int(rcs.item()) != 0:
-        return int(rcs.item()), None, None
+    # error codes are negative, the reference's domain errors positive, 0 = ok: the job fails if ANY rank failed (MIN finds errors, MAX domain errors)
+    lo = torch.tensor([rc], dtype=torch.int32, device=device); hi = lo.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group); dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    if err is not None:
+        raise err
+    if int(lo.item()) < 0 or int(hi.item()) != 0:
+        return (int(lo.item()) if int(lo.item()) < 0 else int(hi.item())), None, None
     plen = api.range_proof_len(range_bits * sh["chunk_len"])
     parts_p = _all_gather_bytes(dist, group, proofs, device)
     parts_c = _all_gather_bytes(dist, group, commits, device)

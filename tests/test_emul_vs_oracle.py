@@ -403,3 +403,23 @@ def test_concurrent_callers_share_one_context(api, oracle):
     assert not errs, errs
     for (rc0, p0, c0), (rc, p, c, ok, okbad) in zip(want, got):
         assert rc == rc0 == 0 and (p == p0).all() and (c == c0).all() and ok == 1 and okbad == 0
+
+
+def test_host_absorb_fallback_gives_the_same_bytes(api, oracle):
+    """Chunks with very many commitments (resnet18-full: 2^18 per chunk) absorb them on the host instead of the device (engine.cuh
+    absorb_commitments); forced here at a tiny size: same proof bytes, same verdicts."""
+    rng = np.random.default_rng(81)
+    D, P = 12, 2
+    v = rng.uniform(-0.9, 0.9, D).astype(np.float32); bl = oracle.rnd_scalar_vec(b"\x74" * 32, D); seed = b"\x75" * 32
+    rc0, p0, c0 = api.range_prove(v, bl, 8, P, 16, 7, seed)
+    api.set_option("ts_host_m", 0)
+    try:
+        rc, p, c = api.range_prove(v, bl, 8, P, 16, 7, seed)
+        assert rc == rc0 == 0 and (p == p0).all() and (c == c0).all()
+        assert api.range_verify(p, c, 8, seed) == 1
+        bad = c.copy(); bad[3] = c[4]
+        assert api.range_verify(p, bad, 8, seed) == 0
+    finally:
+        api.set_option("ts_host_m", 8192)
+    rc_o, p_o, _ = oracle.range_prove(v, bl, 8, P, 16, 7, seed)
+    assert (p0 == p_o).all()

@@ -47,7 +47,13 @@ def _worker(rank, world, port, q):
         x = np.array([[0.25, 1.25, -1.5, 2.0, -0.5], [-0.75, 1.25, -2.0, 1.0, 0.5], [0.5, 1.25, -3.0, -1.0, 0.25]], np.float32)
         cs = np.stack([api.commit(r, None, 16, 7) for r in x])
         rc_d, f = sh.decrypt_sharded(api, cs, 0, 1 << 10, 16, 16, 7, dist=dist)
-        q.put((rank, rc, proofs.tobytes(), commits.tobytes(), ok, ok_bad, rc_d, f.tolist()))
+        # a value outside the range in rank 1's slice only (element 9 lies in chunk 2): EVERY rank must report ValueOutOfRangeError (2), and a
+        # negative error of one rank must win over the zeros of the others (MAX alone turned -98 / -1 into "ok")
+        v2 = v.copy(); v2[9] = 5.0
+        rc_oor = sh.prove_range_sharded(api, v2, bl, rb, P, nb, 7, seed, dist=dist)[0]
+        v3 = v.copy(); v3[9] = np.nan
+        rc_nan = sh.prove_range_sharded(api, v3, bl, rb, P, nb, 7, seed, dist=dist)[0]
+        q.put((rank, rc, proofs.tobytes(), commits.tobytes(), ok, ok_bad, rc_d, f.tolist(), rc_oor, rc_nan))
         api.close()
     finally:
         dist.destroy_process_group()
@@ -65,8 +71,8 @@ def test_chunk_sharded_prove_verify_decrypt_two_ranks(oracle):
     for p in procs: p.start()
     res = sorted(q.get(timeout=600) for _ in range(2))
     for p in procs: p.join(timeout=60)
-    for rank, rc, pb, cb, ok, ok_bad, rc_d, f in res:
-        assert rc == 0
+    for rank, rc, pb, cb, ok, ok_bad, rc_d, f, rc_oor, rc_nan in res:
+        assert rc == 0 and rc_oor == 2 and rc_nan == -98
         assert pb == np.asarray(p_o).tobytes(), "sharded proofs differ from the single-process oracle bytes"
         assert cb == np.asarray(c_o).tobytes()
         assert ok == 1 and ok_bad == 0
