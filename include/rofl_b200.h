@@ -52,13 +52,16 @@ enum {
 };
 
 /* process-wide context: device, stream, cached generator tables and BSGS tables (SURVEY.md section 8b "threading").
- * Thread-safe: concurrent callers are serialised per context; create one context per GPU (or per worker thread). */
+ * Thread-safe: concurrent callers of one context run on separate lanes (stream sets, up to "max_lanes", further callers wait);
+ * the generator / BSGS tables are cached per DEVICE and shared by every context and caller on it (server.rs:54,84 shares one Arc<BSGSTable>). */
 int rofl_ctx_create(rofl_ctx **out, int device);
 void rofl_ctx_destroy(rofl_ctx *ctx);
 const char *rofl_last_error(void);
 void rofl_set_host_threads(rofl_ctx *ctx, int n);          /* host threads used for the per-chunk Merlin transcripts */
 /* tuning knobs (results never depend on them): "use_rt" 0/1 generator tables, "rt_unfold" unfolded IPP rounds, "groups" chunk
- * groups on separate streams, "tail_np" largest half-size handled by the fused tail kernel (0 = off).  returns 0, -2 unknown name */
+ * groups on separate queues, "tail_np" largest half-size handled by the fused tail kernel (0 = off), "rt_bits" table radix, "rt_per" table-MSM
+ * terms per thread, "ts_host_m" chunk size above which commitments are absorbed on the host, "max_lanes" concurrent callers, "drop_tables".
+ * returns 0, -2 unknown name */
 int rofl_set_option(rofl_ctx *ctx, const char *name, long value);
 
 /* ---- sizes ---------------------------------------------------------------------------------------------------- */
@@ -169,6 +172,18 @@ int rofl_square_prove_dev(rofl_ctx *, const float *v, const uint8_t *value_com32
                           const uint8_t seed[32], uint8_t *out_proofs160, uint8_t *out_commits64);     /* all arrays [dev] */
 int rofl_square_verify(rofl_ctx *, const uint8_t *proofs160, const uint8_t *commits64, size_t D);
 int rofl_square_verify_dev(rofl_ctx *, const uint8_t *proofs160 /*dev*/, const uint8_t *commits64 /*dev*/, size_t D);
+
+/* ---- server side, all clients of a round at once.  rofl_service fans EncModelParams::verify out over a rayon pool, one task per client
+ *      (server.rs:516-522,666-667 -> params.rs:181-291); here the n_clients updates of one round (same D, range and partition) share ONE
+ *      batched check: one random linear combination over all clients x chunks, one generator MSM, one bucket MSM over all commitments.
+ *      Arrays are client-major (proofs: n_clients x n_proofs x proof_len; commits32: n_clients x D x 32; ...).
+ *      out_ok[k] = 1 valid, 0 invalid, < 0 the error of that client's update; if the combined check fails the clients are re-checked one by one,
+ *      so the result names the offending client exactly like the reference's per-client verdicts.  Return value: 0, or < 0 for bad arguments. */
+int rofl_range_verify_batch(rofl_ctx *, const uint8_t *proofs, size_t proof_len, size_t n_proofs, const uint8_t *commits32, size_t D, size_t n_clients, int range,
+                            const uint8_t seed[32], int *out_ok);
+int rofl_enc_l2_compressed_verify_batch(rofl_ctx *, size_t n_clients, const uint8_t *enc_values96, size_t D, const uint8_t *square_proofs160, const uint8_t *range_proofs,
+                                        size_t proof_len, size_t n_proofs, const uint8_t *square_range_proofs, size_t sq_proof_len, int prove_range, int l2_range,
+                                        const uint8_t seed[32], int *out_ok);
 
 /* ---- aggregation: EncModelParamsAccumulator::accumulate_other (params.rs:81-124) / pedersen_ops::add_rp_vec_vec
  *      (pedersen_ops.rs:56-69; bindings32.rs:64 `add_commitments`).  points32: n_clients x D encodings, client-major.

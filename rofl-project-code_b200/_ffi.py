@@ -63,6 +63,8 @@ _SIGS = {
     "rofl_probe_imad_wide": (C.c_double, [c_vp]),
     "rofl_prof_launches": (C.c_long, [C.c_int]),
     "rofl_ctx_stream": (c_vp, [c_vp]),
+    "rofl_range_verify_batch": (C.c_int, [c_vp, c_u8p, c_sz, c_sz, c_u8p, c_sz, c_sz, C.c_int, c_u8p, c_vp]),
+    "rofl_enc_l2_compressed_verify_batch": (C.c_int, [c_vp, c_sz, c_u8p, c_sz, c_u8p, c_u8p, c_sz, c_sz, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_vp]),
     "rofl_debug_ts_absorb": (C.c_int, [c_vp, c_u8p, c_sz, C.c_int, C.c_int]),
     "rofl_debug_verify_weights": (C.c_int, [c_vp, c_u8p, c_sz, c_sz, c_u8p, c_sz, C.c_int, c_u8p, c_u8p]),
 }
@@ -228,6 +230,21 @@ class Api:
         rc = self.lib.rofl_enc_l2_verify(self.h, _ptr(enc), enc.shape[0], _ptr(sp), _ptr(p), p.shape[1], p.shape[0], _ptr(sq), sq.size, msg["range_bits"], msg["l2_range_bits"], _ptr(_seed(seed)))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
+
+    # ---- server side: all clients of a round in one batched check; returns the per-client verdicts (1 / 0 / < 0)
+    def range_verify_batch(self, proofs, commits, rng, seed=None):
+        p = _u8(proofs); K = p.shape[0]; p = p.reshape(K, p.shape[1], -1); c = _u8(commits).reshape(K, -1, 32); ok = np.zeros(K, np.int32)
+        rc = self.lib.rofl_range_verify_batch(self.h, _ptr(p), p.shape[2], p.shape[1], _ptr(c), c.shape[1], K, rng, _ptr(_seed(seed)), _ptr(ok))
+        if rc < 0: raise self._err(rc)
+        return ok
+    def enc_l2_compressed_verify_batch(self, msgs, seed=None):
+        K = len(msgs); enc = _u8(np.stack([m["enc_values"] for m in msgs])).reshape(K, -1, 96); sp = _u8(np.stack([m["square_proof"] for m in msgs])).reshape(K, -1, 160)
+        rp = _u8(np.stack([m["range_proof"] for m in msgs])); rp = rp.reshape(K, rp.shape[1], -1); sq = _u8(np.stack([m["square_range_proof"] for m in msgs])).reshape(K, -1)
+        ok = np.zeros(K, np.int32)
+        rc = self.lib.rofl_enc_l2_compressed_verify_batch(self.h, K, _ptr(enc), enc.shape[1], _ptr(sp), _ptr(rp), rp.shape[2], rp.shape[1], _ptr(sq), sq.shape[1], msgs[0]["range_bits"], msgs[0]["l2_range_bits"],
+                                                          _ptr(_seed(seed)), _ptr(ok))
+        if rc < 0: raise self._err(rc)
+        return ok
 
     # ---- test hooks
     def debug_ts_absorb(self, V32, n, label_id=0):

@@ -21,6 +21,7 @@ extern "C" int rofl_set_option(rofl_ctx *c, const char *name, long value) {
     else if (n == "groups") c->e.groups = (int)std::max<long>(1, std::min<long>(ROFL_MAX_GROUPS, value));
     else if (n == "rt_bits") { c->e.rt_bits = (int)std::max<long>(8, std::min<long>(RT_MAX_BITS, value)); engine_drop_rt(c->e); }      // the cached tables of the device are rebuilt at the new radix on next use
     else if (n == "drop_tables") engine_drop_rt(c->e);
+    else if (n == "trim") rt_trim();                                                  // hand the cached scratch blocks of this device back to CUDA
     else if (n == "frozen") c->e.use_frz = value != 0;
     else if (n == "tail_np") c->e.tail_np = (int)std::max<long>(0, std::min<long>(TAIL_MAX_F / 2, value));
     else if (n == "rt_per") c->e.rt_per = (int)std::max<long>(0, std::min<long>(64, value));
@@ -275,7 +276,7 @@ extern "C" int rofl_enc_l2_compressed_verify(rofl_ctx *c, const uint8_t *enc_val
     // decode_l2enc_vec (params.rs:560-571): every record must deserialise -- c.L, c_sq and also c.R, which this arm never uses afterwards
     // (SquareRandProofCommitments::from_bytes -> ElGamalPair::from_bytes; the reference unwrap()s = panics, here the message is refused with ROFL_ERR_POINT)
     rt_memset(dbad.p, 0, sizeof(int), s);
-    LAUNCH(k_validate_points, dim3((unsigned)((3 * D + 127) / 128)), dim3(128), s, de.b.as<uint8_t>(), (size_t)32, (size_t)0, 3 * D, dbad.as<int>());
+    LAUNCH(k_validate_points, dim3((unsigned)((3 * D + 127) / 128)), dim3(128), s, de.b.as<uint8_t>(), (size_t)32, (size_t)0, 3 * D, dbad.as<int>(), (size_t)0);
     LAUNCH(k_split96, dim3((unsigned)((D + 255) / 256)), dim3(256), s, dL.as<uint8_t>(), dSc.as<uint8_t>(), dCsq.as<uint8_t>(), de.b.as<uint8_t>(), D);
     int bad = 0; rt_d2h(&bad, dbad.p, sizeof(int), s);
     const int sq = engine_square_verify(c->e, dsp.b.as<uint8_t>(), dSc.as<uint8_t>(), D);               // (synchronises the stream: `bad` is valid afterwards)
@@ -435,6 +436,54 @@ extern "C" int rofl_dlog(rofl_ctx *c, const uint8_t *pts, size_t D, uint64_t ts,
     int rc = engine_dlog(c->e, dp.b.as<uint8_t>(), D, ts, bb, n_bits, frac, o.as<uint8_t>(), f.as<float>());
     if (osc) rt_d2h(osc, o.p, 32 * D, s); if (of) rt_d2h(of, f.p, 4 * D, s); rt_sync(s);
     return rc;
+    API_CATCH
+}
+
+// ---- server side: all clients of a round in one call (rofl_service/src/flserver/server.rs:516-522,666-667 fans EncModelParams::verify out over a
+//      rayon pool, one task per client; on a GPU the clients share ONE batched check instead) ------------------------------------------------------
+extern "C" int rofl_range_verify_batch(rofl_ctx *c, const uint8_t *proofs, size_t plen, size_t n_proofs, const uint8_t *commits32, size_t D, size_t n_clients, int range,
+                                       const uint8_t seed[32], int *out_ok) {
+    API_TRY
+    if (!D || !n_clients || !out_ok) return ROFL_ERR_ARGS;
+    lane_guard lg(c->e);
+    staged_in dc(commits32, 32 * D * n_clients, lg.s());
+    return engine_range_verify_batch(c->e, proofs, plen, n_proofs, dc.b.as<uint8_t>(), D, n_clients, range, seed, out_ok);
+    API_CATCH
+}
+// EncModelParams::verify, EncL2Compressed arm (params.rs:257-290), for n_clients messages of the same shape.  out_ok[k]: 1 accept, 0 reject,
+// ROFL_ERR_POINT when one of the message's points does not decode.  Every array is client-major.
+extern "C" int rofl_enc_l2_compressed_verify_batch(rofl_ctx *c, size_t n_clients, const uint8_t *enc_values96, size_t D, const uint8_t *square_proofs160, const uint8_t *range_proofs,
+                                                   size_t plen, size_t n_proofs, const uint8_t *square_range_proofs, size_t sq_plen, int prove_range, int l2_range,
+                                                   const uint8_t seed[32], int *out_ok) {
+    API_TRY
+    const size_t K = n_clients;
+    if (!D || !n_proofs || !K || !out_ok) return ROFL_ERR_ARGS;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
+    staged_in de(enc_values96, 96 * D * K, s), dsp(square_proofs160, 160 * D * K, s);
+    dev_buf dL(32 * D * K, s), dSc(64 * D * K, s), dCsq(32 * D * K, s), dbad(sizeof(int) * K, s), dres(2 * sizeof(int) * K, s);
+    std::vector<int> bad(K, 0), res(2 * K), ok_range(K, 0), ok_sum(K, 0);
+    for (size_t k = 0; k < K; k++) { res[2 * k] = 1; res[2 * k + 1] = 0; }
+    rt_memset(dbad.p, 0, sizeof(int) * K, s); rt_h2d(dres.p, res.data(), sizeof(int) * 2 * K, s);
+    LAUNCH(k_validate_points, dim3((unsigned)((3 * D * K + 127) / 128)), dim3(128), s, de.b.as<uint8_t>(), (size_t)32, (size_t)0, 3 * D * K, dbad.as<int>(), 3 * D);
+    LAUNCH(k_split96, dim3((unsigned)((D * K + 255) / 256)), dim3(256), s, dL.as<uint8_t>(), dSc.as<uint8_t>(), dCsq.as<uint8_t>(), de.b.as<uint8_t>(), D * K);
+    LAUNCH(k_square_verify, dim3((unsigned)((D * K + 127) / 128)), dim3(128), s, dsp.b.as<uint8_t>(), dSc.as<uint8_t>(), D * K, c->e.sh->tabB, c->e.sh->tabH, dres.as<int>(), D);
+    // sum_i c_sq,i per client (params.rs:267)
+    const int nb = (int)std::max<size_t>(1, std::min<size_t>(64, (D + 127) / 128));
+    dev_buf dpart(sizeof(p3_st) * nb * K, s), dbad2(sizeof(int) * K, s), dsum(32 * K, s);
+    rt_memset(dbad2.p, 0, sizeof(int) * K, s);
+    LAUNCH_COOP(k_points_sum, dim3(nb, (unsigned)K), dim3(128), s, dpart.as<p3_st>(), dCsq.as<uint8_t>(), D, dbad2.as<int>());
+    { finalize_args f = {}; f.partial = dpart.as<p3_st>(); f.npartial = nb; f.tabB = c->e.sh->tabB; f.tabH = c->e.sh->tabH; f.out32 = dsum.as<uint8_t>(); f.count = (int)K; run_finalize(s, f); }
+    std::vector<uint8_t> sums(32 * K);
+    rt_d2h(bad.data(), dbad.p, sizeof(int) * K, s); rt_d2h(res.data(), dres.p, sizeof(int) * 2 * K, s); rt_d2h(sums.data(), dsum.p, 32 * K, s); rt_sync(s);
+    int rc = engine_range_verify_batch(c->e, range_proofs, plen, n_proofs, dL.as<uint8_t>(), D, K, prove_range, seed, ok_range.data());
+    if (rc < 0) return rc;
+    rc = engine_l2_verify_batch(c->e, square_range_proofs, sq_plen, sums.data(), K, l2_range, seed, ok_sum.data());
+    if (rc < 0) return rc;
+    for (size_t k = 0; k < K; k++) {
+        if (bad[k] || ok_range[k] == ROFL_ERR_POINT) out_ok[k] = ROFL_ERR_POINT;
+        else out_ok[k] = (res[2 * k] == 1 && res[2 * k + 1] == 0 && ok_range[k] == 1 && ok_sum[k] == 1) ? 1 : 0;
+    }
+    return 0;
     API_CATCH
 }
 

@@ -698,14 +698,14 @@ static inline int range_proof_format_check(const uint8_t *h_proofs, size_t plen,
     return 0;
 }
 static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, int m, int C, const gens_entry &g, const rt_tables *rt, const p3_st *d_Vp3, const uint8_t *d_V32,
-                         const uint8_t *h_proofs, size_t plen, const uint8_t seed[32], uint32_t dom, uint64_t c_off, std::vector<int> &verdict, const int *d_xbad = nullptr, int *h_xbad = nullptr, uint8_t *h_weights = nullptr) {
+                         const uint8_t *h_proofs, size_t plen, const uint8_t seed[32], uint32_t dom, uint64_t c_off, std::vector<int> &verdict, const int *d_xbad = nullptr, int *h_xbad = nullptr, uint8_t *h_weights = nullptr, size_t nx = 1) {
     verdict.assign(C, 0);
     phase_trace tr(s);
     size_t lg = 0;
     if (range_proof_format_check(h_proofs, plen, (size_t)C, &lg)) return -1;
     const size_t N = (size_t)n * m;
     if ((m & (m - 1)) || N != ((size_t)1 << lg)) {                      // verification_scalars: n != 1 << lg_n -> VerificationError (all chunks false)
-        if (d_xbad) { rt_d2h(h_xbad, d_xbad, sizeof(int), s); rt_sync(s); }
+        if (d_xbad) { rt_d2h(h_xbad, d_xbad, sizeof(int) * nx, s); rt_sync(s); }
         return 0;
     }
     const int lgN = (int)lg, nsmall = 6 + 2 * lgN, lgm = ilog2_sz((size_t)m);
@@ -768,7 +768,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, in
     }
     std::vector<int> h_bad(C); int h_id = 0;
     rt_d2h(&h_id, d_id.p, sizeof(int), s); rt_d2h(h_bad.data(), d_bad.p, sizeof(int) * C, s);
-    if (d_xbad) rt_d2h(h_xbad, d_xbad, sizeof(int), s);
+    if (d_xbad) rt_d2h(h_xbad, d_xbad, sizeof(int) * nx, s);
     if (h_weights) rt_d2h(h_weights, d_ccrho.p, sizeof(sc_st) * 2 * (size_t)C, s);
     rt_sync(s);
     tr.mark("v_var_msm");
@@ -812,6 +812,66 @@ static int engine_range_verify(rofl_engine &e, const uint8_t *h_proofs, size_t p
     if (rc < 0) return rc;
     int res = 1; for (int v : verdict) res &= v;                               // :183-190
     return res;
+}
+
+
+// =============================================================================================================================
+// Server side: K updates of the same shape (D, range, n_proofs) verified TOGETHER -- one random linear combination over all K x n_proofs
+// chunks, ONE generator MSM, one bucket MSM over all commitments (rofl_service verifies the clients one by one on a thread pool,
+// server.rs:516-522,666-667 -> params.rs:181-291).  d_commits: K x D encodings (device), h_proofs: K x n_proofs x plen.
+// out[k] = 1 valid, 0 invalid, < 0 that update's error.  When the combined check fails (or any update is malformed) the updates are
+// re-checked one by one, so that the verdict names the offender exactly as the reference's per-client results do.
+// =============================================================================================================================
+static int engine_range_verify_batch(rofl_engine &e, const uint8_t *h_proofs, size_t plen, size_t n_proofs, const uint8_t *d_commits, size_t D, size_t K,
+                                     int range, const uint8_t seed[32], int *out) {
+    if (n_proofs == 0 || D == 0 || range < 1 || range > 64 || !out) return -2;
+    if (K == 0) return 0;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
+    const size_t Dp = next_pow2_sz(D), m = Dp / n_proofs;
+    bool batch_ok = m != 0 && (range == 8 || range == 16 || range == 32 || range == 64) && n_proofs * m == Dp && K * n_proofs <= (1u << 20);
+    for (size_t k = 0; k < K && batch_ok; k++) if (range_proof_format_check(h_proofs + k * n_proofs * plen, plen, n_proofs, nullptr)) batch_ok = false;
+    if (batch_ok) {
+        dev_buf d_off(sizeof(p3_st), s), d_offs(sizeof(sc_st), s), d_Vp3(sizeof(p3_st) * Dp * K, s), d_V32(32 * Dp * K, s), d_bad(sizeof(int) * K, s);
+        { sc o; sc_from_u64(o, 1ULL << (range - 1)); sc_st os; sc_to_st(os, o); rt_h2d(d_offs.p, &os, sizeof(os), s);
+          finalize_args f = {}; f.sBa = d_offs.as<sc_st>(); f.tabB = e.sh->tabB; f.tabH = e.sh->tabH; f.out_p3 = d_off.as<p3_st>(); f.count = 1;
+          run_finalize(s, f); }
+        rt_memset(d_bad.p, 0, sizeof(int) * K, s);
+        LAUNCH(k_decompress_batch, dim3((unsigned)((K * Dp + 127) / 128)), dim3(128), s, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), d_commits, D, Dp, K, d_off.as<p3_st>(), d_bad.as<int>());
+        tables_use tu(*e.sh);
+        engine_gens(e, tu, s, range, (int)m);
+        rt_tables rt; const bool have_rt = engine_rt(e, tu, s, range, (int)m, rt);
+        const gens_entry g = engine_gens(e, tu, s, range, (int)m);
+        std::vector<int> verdict, bad(K, 0);
+        const int rc = verify_chunks(e, s, 0, range, (int)m, (int)(K * n_proofs), g, have_rt ? &rt : nullptr, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), h_proofs, plen, seed, DOM_RANGE_VERIFY, 0, verdict,
+                                     d_bad.as<int>(), bad.data(), nullptr, K);
+        bool all = rc == 0; for (int v : verdict) all = all && v == 1; for (int b : bad) all = all && !b;
+        if (all) { for (size_t k = 0; k < K; k++) out[k] = 1; return 0; }
+    }
+    for (size_t k = 0; k < K; k++) out[k] = engine_range_verify(e, h_proofs + k * n_proofs * plen, plen, n_proofs, d_commits + 32 * k * D, D, range, seed);
+    return 0;
+}
+static int engine_l2_verify(rofl_engine &e, const uint8_t *h_proof, size_t plen, const uint8_t *h_commit, int range, const uint8_t seed[32]);
+// K sum-of-squares proofs (l2_range_proof_vec::verify_rangeproof_l2, :185-228) in one batched check; h_commits: K x 32
+static int engine_l2_verify_batch(rofl_engine &e, const uint8_t *h_proofs, size_t plen, const uint8_t *h_commits, size_t K, int range, const uint8_t seed[32], int *out) {
+    if (!out) return -2;
+    if (K == 0) return 0;
+    lane_guard lg(e);
+    cudaStream_t s = lg.s();
+    bool batch_ok = (range == 8 || range == 16 || range == 32 || range == 64) && range_proof_format_check(h_proofs, plen, K, nullptr) == 0;
+    if (batch_ok) {
+        dev_buf d_c(32 * K, s), d_Vp3(sizeof(p3_st) * K, s), d_V32(32 * K, s), d_bad(sizeof(int) * K, s);
+        rt_h2d(d_c.p, h_commits, 32 * K, s); rt_memset(d_bad.p, 0, sizeof(int) * K, s);
+        LAUNCH(k_decompress_batch, dim3((unsigned)((K + 127) / 128)), dim3(128), s, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), d_c.as<uint8_t>(), (size_t)1, (size_t)1, K, (const p3_st *)nullptr, d_bad.as<int>());
+        tables_use tu(*e.sh);
+        const gens_entry g = engine_gens(e, tu, s, range, 1);
+        std::vector<int> verdict, bad(K, 0);
+        const int rc = verify_chunks(e, s, 1, range, 1, (int)K, g, nullptr, d_Vp3.as<p3_st>(), d_V32.as<uint8_t>(), h_proofs, plen, seed, DOM_L2_VERIFY, 0, verdict, d_bad.as<int>(), bad.data(), nullptr, K);
+        bool all = rc == 0; for (int v : verdict) all = all && v == 1; for (int b : bad) all = all && !b;
+        if (all) { for (size_t k = 0; k < K; k++) out[k] = 1; return 0; }
+    }
+    for (size_t k = 0; k < K; k++) out[k] = engine_l2_verify(e, h_proofs + k * plen, plen, h_commits + 32 * k, range, seed);
+    return 0;
 }
 
 // =============================================================================================================================
@@ -910,7 +970,7 @@ static int engine_square_verify(rofl_engine &e, const uint8_t *d_proofs, const u
     cudaStream_t s = lg.s();
     dev_buf d_res(2 * sizeof(int), s); int init[2] = {1, 0}; rt_h2d(d_res.p, init, sizeof(init), s);
     void *tk = rt_prof_begin(PROF_SQUARE, s);
-    LAUNCH(k_square_verify, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_proofs, d_commits, D, e.sh->tabB, e.sh->tabH, d_res.as<int>());
+    LAUNCH(k_square_verify, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_proofs, d_commits, D, e.sh->tabB, e.sh->tabH, d_res.as<int>(), (size_t)0);
     rt_prof_end(PROF_SQUARE, tk, s);
     int res[2]; rt_d2h(res, d_res.p, sizeof(res), s); rt_sync(s);
     if (res[1]) return -1;

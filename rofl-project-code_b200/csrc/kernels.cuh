@@ -643,6 +643,22 @@ KERNEL void LB(128, 2) k_decompress(p3_st *out, uint8_t *out32, const uint8_t *i
     if (out32) { uint8_t o[32]; ge_compress(o, p); st_bytes32(out32 + 32 * i, o); }
 }
 KLAUNCH(k_decompress, false, (p3_st *out, uint8_t *out32, const uint8_t *in, size_t count_in, size_t count_out, const p3_st *offset, int *bad, size_t bad_group), (out, out32, in, count_in, count_out, offset, bad, bad_group))
+// the same for K updates in one launch (server side, one update per client): update k's D encodings start at in + 32 k D and fill entries
+// [k Dp, k Dp + D) of the outputs, the rest of its Dp entries is identity padding; bad[k] is set if one of ITS encodings does not decode
+KERNEL void LB(128, 2) k_decompress_batch(p3_st *out, uint8_t *out32, const uint8_t *in, size_t D, size_t Dp, size_t K, const p3_st *offset, int *bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * Dp) return;
+    const size_t k = i / Dp, j = i % Dp;
+    ge_p3 p; ge_p3_0(p);
+    if (j < D) {
+        uint8_t b[32]; ld_bytes32(b, in + 32 * (k * D + j));
+        if (!ge_decompress(p, b)) { atomicOr(bad + k, 1); ge_p3_0(p); }
+        if (offset) { ge_p3 o; ld_p3(o, offset); ge_add(p, p, o); }
+    }
+    st_p3(out + i, p);
+    if (out32) { uint8_t o[32]; ge_compress(o, p); st_bytes32(out32 + 32 * i, o); }
+}
+KLAUNCH(k_decompress_batch, false, (p3_st *out, uint8_t *out32, const uint8_t *in, size_t D, size_t Dp, size_t K, const p3_st *offset, int *bad), (out, out32, in, D, Dp, K, offset, bad))
 #endif
 // Batched verification: all C chunks of a call share the generators, so the verifier takes one random weight rho_c per chunk
 // and checks  sum_c rho_c * (chunk c's verification equation) == 0  with ONE 2N-term generator MSM (soundness error 2^-252;
@@ -749,9 +765,11 @@ KLAUNCH(k_square_prove, false, (square_args a), (a))
 #endif
 // result[0] &= all valid ; result[1] |= format error
 #ifdef KG_SQUARE
-KERNEL void LB(128, 1) k_square_verify(const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result) {
+//   group: elements per update when several updates are checked in one launch (result = 2 ints per update); 0 = one update
+KERNEL void LB(128, 1) k_square_verify(const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result, size_t group) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D) return;
+    if (group) result += 2 * (i / group);
     uint8_t proof[160], com[64];
     for (int k = 0; k < 5; k++) ld_bytes32(proof + 32 * k, proofs + 160 * i + 32 * k);
     ld_bytes32(com, commits + 64 * i); ld_bytes32(com + 32, commits + 64 * i + 32);
@@ -759,7 +777,7 @@ KERNEL void LB(128, 1) k_square_verify(const uint8_t *proofs, const uint8_t *com
     if (rc < 0) atomicOr(result + 1, 1);
     else if (rc == 0) atomicAnd(result, 0);
 }
-KLAUNCH(k_square_verify, false, (const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result), (proofs, commits, D, tabB, tabH, result))
+KLAUNCH(k_square_verify, false, (const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result, size_t group), (proofs, commits, D, tabB, tabH, result, group))
 #endif
 
 // the un-optimised encodings' per-element proofs (enc types 2 and 3): same shape as K8, one thread per element.
@@ -996,17 +1014,20 @@ KERNEL void LB(256, 2) k_split96(uint8_t *L, uint8_t *sq64, uint8_t *csq, const 
 KLAUNCH(k_split96, false, (uint8_t *L, uint8_t *sq64, uint8_t *csq, const uint8_t *in96, size_t D), (L, sq64, csq, in96, D))
 // from_bytes validation of one column of compressed points inside fixed-width wire records: *bad = 1 if record i's 32 bytes at `offset` do
 // not decode (ElGamalPair::from_bytes, rand_proof/el_gamal.rs:112-123; SquareRandProofCommitments::from_bytes, square_rand_proof/pedersen.rs:33-45)
-KERNEL void LB(128, 2) k_validate_points(const uint8_t *rec, size_t stride, size_t offset, size_t D, int *bad) {
+//   group: records per update when several updates are validated in one launch (one flag per update); 0 = one update
+KERNEL void LB(128, 2) k_validate_points(const uint8_t *rec, size_t stride, size_t offset, size_t D, int *bad, size_t group) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D) return;
     uint8_t b[32]; ld_bytes32(b, rec + stride * i + offset);
-    ge_p3 p; if (!ge_decompress(p, b)) atomicOr(bad, 1);
+    ge_p3 p; if (!ge_decompress(p, b)) atomicOr(bad + (group ? i / group : 0), 1);
 }
-KLAUNCH(k_validate_points, false, (const uint8_t *rec, size_t stride, size_t offset, size_t D, int *bad), (rec, stride, offset, D, bad))
+KLAUNCH(k_validate_points, false, (const uint8_t *rec, size_t stride, size_t offset, size_t D, int *bad, size_t group), (rec, stride, offset, D, bad, group))
 // partial[blockIdx.x] = sum of this block's share of D compressed points (params.rs:267: enc_values.iter().map(|x| x.c_sq).sum())
+//   blockIdx.y = update k when several are summed in one launch: points pts32 + 32 k D, partial[k gridDim.x + blockIdx.x], bad[k]
 KERNEL void LB(128, 2) k_points_sum(p3_st *partial, const uint8_t *pts32, size_t D, int *bad) {
     __shared__ p3_st buf[128];
     const int tid = threadIdx.x;
+    pts32 += 32 * (size_t)blockIdx.y * D; partial += (size_t)blockIdx.y * gridDim.x; bad += blockIdx.y;
     ge_p3 acc; ge_p3_0(acc);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < D; i += (size_t)gridDim.x * blockDim.x) {
         uint8_t b[32]; ld_bytes32(b, pts32 + 32 * i);
@@ -1036,13 +1057,14 @@ void launch_k_lr(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *l0, sc_st *r0, const 
 void launch_k_ipp_scalars(dim3 g_, dim3 b_, cudaStream_t s_, const sc_st *a, const sc_st *b, const sc_st *yinv, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np);
 void launch_k_ipp_fold_scalars(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *a, sc_st *b, const sc_st *u2, const sc_st *uinv2, size_t N, uint32_t np);
 void launch_k_ipp_fold_points(dim3 g_, dim3 b_, cudaStream_t s_, fold_args a);
+void launch_k_decompress_batch(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *out, uint8_t *out32, const uint8_t *in, size_t D, size_t Dp, size_t K, const p3_st *offset, int *bad);
 void launch_k_decompress(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *out, uint8_t *out32, const uint8_t *in, size_t count_in, size_t count_out, const p3_st *offset, int *bad, size_t bad_group);
 void launch_k_verify_tables(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *tab, vtab_layout t, sc_st *var, uint32_t var_stride, const sc_st *chal, int chal_stride, const sc_st *yinvpow2, const sc_st *zpow2, int m);
 void launch_k_verify_scalars(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *gh, const sc_st *tab, vtab_layout t, const sc_st *chal, int chal_stride, int n, int C);
 void launch_k_square_prove(dim3 g_, dim3 b_, cudaStream_t s_, square_args a);
 void launch_k_sigma_prove(dim3 g_, dim3 b_, cudaStream_t s_, sigma_args a);
 void launch_k_sigma_verify(dim3 g_, dim3 b_, cudaStream_t s_, int kind, const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result);
-void launch_k_square_verify(dim3 g_, dim3 b_, cudaStream_t s_, const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result);
+void launch_k_square_verify(dim3 g_, dim3 b_, cudaStream_t s_, const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result, size_t group);
 void launch_k_aggregate(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const uint8_t *pts, size_t n_clients, size_t D, int init_base, int *bad);
 void launch_k_bsgs_build(dim3 g_, dim3 b_, cudaStream_t s_, unsigned long long *keys, uint32_t *vals, uint32_t cap, uint32_t m, const niels_st *tabB, int *distinct);
 void launch_k_bsgs_solve(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out_sc, float *out_f32, const uint8_t *pts, size_t D, const unsigned long long *keys, const uint32_t *vals, uint32_t cap, uint32_t m, uint64_t size, uint64_t max_it, int bsgs_bits, int n_bits, int frac, const niels_st *tabB, int *flags);
@@ -1050,7 +1072,7 @@ void launch_k_f32_to_scalar(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, con
 void launch_k_scalar_to_f32(dim3 g_, dim3 b_, cudaStream_t s_, float *out, const uint8_t *in, size_t D, int n_bits, int frac);
 void launch_k_l2_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, int *flags);
 void launch_k_join96(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out96, const uint8_t *pairs64, const uint8_t *sq64, size_t D);
-void launch_k_validate_points(dim3 g_, dim3 b_, cudaStream_t s_, const uint8_t *rec, size_t stride, size_t offset, size_t D, int *bad);
+void launch_k_validate_points(dim3 g_, dim3 b_, cudaStream_t s_, const uint8_t *rec, size_t stride, size_t offset, size_t D, int *bad, size_t group);
 void launch_k_split96(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *L, uint8_t *sq64, uint8_t *csq, const uint8_t *in96, size_t D);
 void launch_k_points_sum(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *partial, const uint8_t *pts32, size_t D, int *bad);
 void launch_k_crp_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const float *v, const uint8_t *blind, size_t D, int n_bits, int frac, pow_tab ctab, int *flags);

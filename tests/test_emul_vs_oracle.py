@@ -423,3 +423,31 @@ def test_host_absorb_fallback_gives_the_same_bytes(api, oracle):
         api.set_option("ts_host_m", 8192)
     rc_o, p_o, _ = oracle.range_prove(v, bl, 8, P, 16, 7, seed)
     assert (p0 == p_o).all()
+
+
+def test_server_batch_verification_names_the_offending_client(api, oracle):
+    """rofl_range_verify_batch / rofl_enc_l2_compressed_verify_batch: all clients of a round in ONE random linear combination (server.rs:516-522,
+    666-667 verifies them one by one); the per-client verdicts must be exactly those of the per-client calls, for honest and tampered clients."""
+    rng = np.random.default_rng(82)
+    K, D, P = 3, 6, 2
+    proofs, commits, msgs, seeds = [], [], [], []
+    for k in range(K):
+        v = (rng.integers(-24, 25, D) / 128).astype(np.float32); bl = oracle.rnd_scalar_vec(bytes([0x76 + k]) * 32, D); seed = bytes([0x30 + k]) * 32
+        rc, p, c = api.range_prove(v, bl, 8, P, 32, 7, seed); assert rc == 0
+        proofs.append(p); commits.append(c)
+        rc, m = api.enc_l2_compressed_encrypt(v, bl, 8, P, 32, 32, 7, seed); assert rc == 0
+        msgs.append(m)
+    vs = b"\x44" * 32
+    assert api.range_verify_batch(np.stack(proofs), np.stack(commits), 8, vs).tolist() == [1, 1, 1]
+    bad_c = [c.copy() for c in commits]; bad_c[1][2] = commits[1][3]
+    assert api.range_verify_batch(np.stack(proofs), np.stack(bad_c), 8, vs).tolist() == [1, 0, 1]
+    bad_p = [p.copy() for p in proofs]; bad_p[2][0, 128:160] = 0xff                      # non-canonical t_x: FormatError for that client only
+    assert api.range_verify_batch(np.stack(bad_p), np.stack(commits), 8, vs).tolist() == [1, 1, -1]
+    bad_c = [c.copy() for c in commits]; bad_c[0][0] = 0xff
+    assert api.range_verify_batch(np.stack(proofs), np.stack(bad_c), 8, vs).tolist() == [-4, 1, 1]
+    # whole messages
+    assert api.enc_l2_compressed_verify_batch(msgs, vs).tolist() == [1, 1, 1]
+    for field, idx, want in [("enc_values", (2, 70), (0, -4)), ("square_proof", (3, 100), (0,)), ("range_proof", (1, 40), (0,)), ("square_range_proof", (50,), (0,)), ("enc_values", (1, 33), (0, -4, 1))]:
+        tam = [dict(m) for m in msgs]; tam[1][field] = msgs[1][field].copy(); tam[1][field][idx] ^= 1
+        got = api.enc_l2_compressed_verify_batch(tam, vs).tolist()
+        assert got[0] == 1 and got[2] == 1 and got[1] in want and got[1] == api.enc_l2_compressed_verify(tam[1], vs), (field, got)

@@ -538,3 +538,36 @@ def test_concurrent_callers_share_one_context(api, oracle):      # VERDICT r01 i
     assert not errs, errs
     for (rc0, p0, c0), (rc, p, c, ok, okbad) in zip(want, got):
         assert rc == rc0 == 0 and (p == p0).all() and (c == c0).all() and ok == 1 and okbad == 0
+
+
+def test_config4_server_batch_path_48_clients(api, oracle):
+    """BASELINE.json configs[4] through the batch entry points: 48 EncL2Compressed messages of 50 000 parameters verified in ONE call
+    (rofl_enc_l2_compressed_verify_batch: one random linear combination over 48 x 64 chunks, one generator MSM), then aggregated and decrypted;
+    a tampered client is named, the others still pass; the verdicts equal the per-client calls' (server.rs:516-522,666-667, params.rs:81-147,257-290)."""
+    rng = np.random.default_rng(83)
+    K, D, P = 48, 50000, 64
+    vs_, msgs = [], []
+    bls = [np.frombuffer(api.rnd_scalar_vec(bytes([0x10 + k]) * 32, D).tobytes(), np.uint8).reshape(D, 32).copy() for k in range(K - 1)]
+    tot = np.zeros(D, dtype=object)
+    for b in bls:
+        tot = (tot + np.array([int.from_bytes(row.tobytes(), "little") for row in b], dtype=object)) % L
+    bls.append(np.frombuffer(b"".join(int((L - t) % L).to_bytes(32, "little") for t in tot), np.uint8).reshape(D, 32).copy())
+    for k in range(K):
+        v = (rng.integers(-24, 25, D) / 128).astype(np.float32); vs_.append(v)
+        rc, m = api.enc_l2_compressed_encrypt(v, bls[k], 8, P, 32, 32, 7, bytes([0x50 + k]) * 32)
+        assert rc == 0
+        msgs.append(m)
+    seed = b"\x66" * 32
+    assert api.enc_l2_compressed_verify_batch(msgs, seed).tolist() == [1] * K
+    proofs = np.stack([m["range_proof"] for m in msgs]); commits = np.stack([m["enc_values"][:, :32] for m in msgs])
+    assert api.range_verify_batch(proofs, commits, 8, seed).tolist() == [1] * K
+    tam = [dict(m) for m in msgs]; tam[17]["enc_values"] = msgs[17]["enc_values"].copy(); tam[17]["enc_values"][40000, :32] = msgs[17]["enc_values"][40001, :32]
+    tam[30]["square_proof"] = msgs[30]["square_proof"].copy(); tam[30]["square_proof"][123, 70] ^= 1
+    got = api.enc_l2_compressed_verify_batch(tam, seed).tolist()
+    assert got[17] == 0 and got[30] in (0, -1) and all(g == 1 for i, g in enumerate(got) if i not in (17, 30))
+    assert api.enc_l2_compressed_verify(tam[17], seed) == 0 and api.enc_l2_compressed_verify(msgs[3], seed) == 1
+    aggL = api.aggregate(np.stack([m["enc_values"][:, :32].copy() for m in msgs]), 0)
+    aggR = api.aggregate(np.stack([m["enc_values"][:, 32:64].copy() for m in msgs]), 1)
+    assert (aggR == np.frombuffer(oracle.basepoint(), np.uint8)).all()
+    rc, s, f = api.dlog(aggL, 1 << 16, 16, 32, 7)
+    assert rc == 0 and (f == np.sum(np.stack(vs_), axis=0, dtype=np.float64).astype(np.float32)).all()
