@@ -80,6 +80,8 @@ void rofl_clip_bounds(int range, int n_bits, int frac, float *mn, float *mx);   
 float rofl_l2_clip_bound(int range, int n_bits, int frac);                                                            /* conversion32.rs:62-64 */
 void rofl_clip_f32_to_range_vec(const float *v, size_t D, int range, int n_bits, int frac, float *out);              /* range_proof_vec/mod.rs:104-111 (host; O(D) f32 min/max) */
 void rofl_rnd_scalar_vec(const uint8_t seed[32], size_t D, uint8_t *out_scalars32);                                  /* pedersen_ops.rs:124-127, seeded   */
+/* element-wise scalar arithmetic mod l (host): op 0 = a + b, 1 = -a   (bindings32.rs:727 `add_scalars`, pedersen_ops.rs:110-122 cancelling blindings) */
+int rofl_scalar_ops(int op, const uint8_t *a32, const uint8_t *b32, size_t n, uint8_t *out32);
 
 /* ---- commitments: pedersen_ops::commit_vec / commit_no_blinding_vec (pedersen_ops.rs:9-25) and the ElGamal right
  *      halves R = r*B (el_gamal.rs:57-69, compressed_rand_proof/party.rs:23-24).  blind32 may be NULL (zero blinding,

@@ -24,6 +24,7 @@ _SIGS = {
     "rofl_l2_clip_bound": (C.c_float, [C.c_int, C.c_int, C.c_int]),
     "rofl_clip_f32_to_range_vec": (None, [c_f32p, c_sz, C.c_int, C.c_int, C.c_int, c_f32p]),
     "rofl_rnd_scalar_vec": (None, [c_u8p, c_sz, c_u8p]),
+    "rofl_scalar_ops": (C.c_int, [C.c_int, c_u8p, c_u8p, c_sz, c_u8p]),
     "rofl_commit": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p]),
     "rofl_commit_dev": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, C.c_int, c_u8p, c_u8p]),
     "rofl_range_prove": (C.c_int, [c_vp, c_f32p, c_u8p, c_sz, C.c_int, c_sz, C.c_int, C.c_int, c_u8p, c_u8p, C.POINTER(c_sz), C.POINTER(c_sz), c_u8p]),

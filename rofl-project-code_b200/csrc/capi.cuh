@@ -48,6 +48,17 @@ extern "C" void rofl_rnd_scalar_vec(const uint8_t seed[32], size_t D, uint8_t *o
     for (size_t i = 0; i < D; i++) { sc s; nonce_scalar(s, kw, i); sc_tobytes(out + 32 * i, s); }
 }
 
+// element-wise scalar arithmetic mod l on the host (bindings32.rs `add_scalars`, pedersen_ops::generate_cancelling_scalar_vec): op 0 = a + b, 1 = -a
+extern "C" int rofl_scalar_ops(int op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out) {
+    if (!a || !out || (op == 0 && !b) || (op != 0 && op != 1)) return ROFL_ERR_ARGS;
+    for (size_t i = 0; i < n; i++) {
+        sc x, y, r; sc_from_bytes_mod_order(x, a + 32 * i);
+        if (op == 0) { sc_from_bytes_mod_order(y, b + 32 * i); sc_add(r, x, y); } else sc_neg(r, x);
+        sc_tobytes(out + 32 * i, r);
+    }
+    return 0;
+}
+
 // host <-> device staging helpers
 struct staged_in { dev_buf b; staged_in(const void *h, size_t n, cudaStream_t s) : b(n ? n : 16, s) { if (h && n) rt_h2d(b.p, h, n, s); } };
 

@@ -77,10 +77,10 @@ struct rofl_engine {
 static thread_local lane *tl_lane = nullptr; static thread_local rofl_engine *tl_lane_engine = nullptr; static thread_local int tl_lane_depth = 0;
 static inline lane *lane_new() {
     lane *l = new lane();
-    // the short kernels of every group's Fiat-Shamir chain run at the greatest priority; the bulk streams are ORDERED (group 0 before group 1
-    // before ..): equal priorities make the groups march in lock step (all in a bulk kernel, then all in a small one -- no overlap at all),
-    // ordered ones let group 0 race ahead, so that its latency-bound last rounds run under the bulk kernels of the groups behind it
-    static const int ordered = getenv("ROFL_PRIO_ORDERED") ? atoi(getenv("ROFL_PRIO_ORDERED")) : 1, flat = getenv("ROFL_PRIO_FLAT") != nullptr;
+    // the short kernels of every group's Fiat-Shamir chain run at the greatest priority, the bulk kernels one level below.  (ROFL_PRIO_ORDERED=1
+    // orders the bulk streams of the groups as well -- group 0 races ahead so that its latency-bound last rounds run under the bulk kernels of
+    // the groups behind it; measured on B200 it is 3 ms SLOWER per proof than equal priorities: the last group ends up alone.  DESIGN.md section 3)
+    static const int ordered = getenv("ROFL_PRIO_ORDERED") ? atoi(getenv("ROFL_PRIO_ORDERED")) : 0, flat = getenv("ROFL_PRIO_FLAT") != nullptr;
     for (int g = 0; g < ROFL_MAX_GROUPS; g++) { cudaStream_t hi = rt_stream_create(flat ? 1 : 0), lo = rt_stream_create(ordered ? 1 + g : 1); l->q[g] = chain(hi, lo); l->side[g] = rt_stream_create(0); }
     return l;
 }

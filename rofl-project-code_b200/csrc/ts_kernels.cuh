@@ -56,44 +56,80 @@ DEV void keccak_coop(strobe_sh &h, int lane) {
 // where the two pos_begin bytes are (begin position of the PREVIOUS operation) + 1 if that operation began in the current sponge
 // block and 0 otherwise (Strobe128::begin_op / run_f).  Byte k of the stream lands at absolute position A0 + k
 // (A0 = position at entry), so every byte is a function of k alone and the lanes fill a 166-byte block together.
+// byte at absolute stream position A (which lies in the sponge block starting at `base`)
+DEV uint8_t absorb_stream_byte(uint32_t A, uint32_t base, uint32_t A0, uint8_t pb0, uint8_t label, const uint8_t *msgs) {
+    const uint32_t k = A - A0, j = k / 41u, r = k - 41u * j, a1 = A0 + 41u * j;
+    if (r >= 9) return msgs[32 * (size_t)j + (r - 9)];
+    if (r == 0) { const uint32_t ap = a1 - 34; return j == 0 ? pb0 : (ap >= base ? (uint8_t)(ap - base + 1) : 0); }      // a1 = A lies in this block
+    if (r == 1) return 0x12;
+    if (r == 2) return label;
+    if (r == 3) return 32;
+    if (r < 7) return 0;
+    if (r == 7) return a1 >= base ? (uint8_t)(a1 - base + 1) : 0;                                                         // a2 = A lies in this block
+    return 0x02;
+}
+// pos_begin at the run_f that closes the block starting at `base`: (begin of the last operation) + 1 if it lies in this block
+DEV uint8_t absorb_close_pb(uint32_t base, uint32_t A0) {
+    const uint32_t last = base + (STROBE_R - 1), k = last - A0, j = k / 41u, r = k - 41u * j, a = A0 + 41u * j + (r >= 7 ? 7 : 0);
+    return a >= base ? (uint8_t)(a - base + 1) : 0;
+}
 DEV void strobe_absorb_many_coop(strobe_sh &h, int lane, uint8_t label, const uint8_t *msgs, uint32_t m) {
     if (m == 0) return;
-    // 32-bit positions (m < 2^26 commitments per chunk): constant divisions become multiply-shifts, a 64-bit division costs ~100 instructions
-    const uint32_t A0 = h.pos, total = 41u * m, A_end = A0 + total, nfull = A_end / STROBE_R;
+    // 32-bit positions (m < 2^26 commitments per chunk): constant divisions become multiply-shifts
+    const uint32_t A0 = h.pos, A_end = A0 + 41u * m, nfull = A_end / STROBE_R;
     const uint8_t pb0 = (uint8_t)h.pos_begin;
+#ifdef ROFL_EMUL
+    // portable form (CUDA-on-CPU emulation): state in shared memory, one lane per Keccak word with barriers between the steps
     uint8_t *st8 = (uint8_t *)h.st;
     for (uint32_t e = 0; e <= nfull; e++) {
         const uint32_t base = STROBE_R * e;
         for (uint32_t p = lane; p < STROBE_R; p += TS_THREADS) {
             const uint32_t A = base + p;
-            if (A < A0 || A >= A_end) continue;
-            const uint32_t k = A - A0, j = k / 41u, r = k - 41u * j, a1 = A0 + 41u * j, a2 = a1 + 7;
-            uint8_t b;
-            if (r >= 9) b = msgs[32 * (size_t)j + (r - 9)];
-            else if (r == 0) { const uint32_t ap = a1 - 34; b = j == 0 ? pb0 : (ap >= base ? (uint8_t)(ap - base + 1) : 0); }      // a1 lies in block e (it IS position A)
-            else if (r == 1) b = 0x12;
-            else if (r == 2) b = label;
-            else if (r == 3) b = 32;
-            else if (r < 7) b = 0;
-            else if (r == 7) b = a1 >= base ? (uint8_t)(a1 - base + 1) : 0;                                                     // a2 = A lies in block e
-            else b = 0x02;
-            st8[p] ^= b;
+            if (A >= A0 && A < A_end) st8[p] ^= absorb_stream_byte(A, base, A0, pb0, label, msgs);
         }
         TS_WSYNC();
-        if (e < nfull) {                      // run_f closing block e: pos = 166, pos_begin = begin of the last operation if it lies in this block
-            if (lane == 0) {
-                const uint32_t last = base + (STROBE_R - 1), k = last - A0, j = k / 41u, r = k - 41u * j;
-                const uint32_t a = A0 + 41u * j + (r >= 7 ? 7 : 0);
-                st8[STROBE_R] ^= a >= base ? (uint8_t)(a - base + 1) : 0;
-                st8[STROBE_R + 1] ^= 0x04 ^ 0x80;
-            }
+        if (e < nfull) {                      // run_f closing block e: pos = 166
+            if (lane == 0) { st8[STROBE_R] ^= absorb_close_pb(base, A0); st8[STROBE_R + 1] ^= 0x04 ^ 0x80; }
             TS_WSYNC();
-            // the permutation itself runs in lane 0's registers (keccak_f1600: 25 x u64, instruction-level parallelism inside a round): measured on B200
-            // 2.5x faster than one lane per word with shared-memory exchanges (72 dependent LDS/STS round trips per permutation)
-            if (lane == 0) { uint64_t st[25]; for (int i = 0; i < 25; i++) st[i] = h.st[i]; keccak_f1600(st); for (int i = 0; i < 25; i++) h.st[i] = st[i]; }
-            TS_WSYNC();
+            keccak_coop(h, lane);
         }
     }
+#else
+    // device form: lane t < 25 keeps word t of the state in registers, builds its own 8 bytes of every block and the permutation exchanges
+    // words with warp shuffles (9 64-bit shuffles in 4 dependent steps per round; the shared-memory form needs 72 LDS/STS round trips per
+    // permutation and measured 6.7 us per block on B200, this one ~2 us)
+    const int x = lane % 5, row = lane - x;
+    const int src = lane < 25 ? KC_SRC_[lane] : 0, rot = lane < 25 ? KC_ROT_[lane] : 0;
+    const int l5 = (lane + 5) % 25, l10 = (lane + 10) % 25, l15 = (lane + 15) % 25, l20 = (lane + 20) % 25;
+    const int dm = row + (x + 4) % 5, dp = row + (x + 1) % 5, c1 = row + (x + 1) % 5, c2 = row + (x + 2) % 5;
+    uint64_t a = lane < 25 ? h.st[lane] : 0;
+    auto sh64 = [](uint64_t v, int from) { const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, from), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), from); return ((uint64_t)hi << 32) | lo; };
+    for (uint32_t e = 0; e <= nfull; e++) {
+        const uint32_t base = STROBE_R * e;
+        if (lane < 21) {
+            uint64_t w = 0;
+            for (uint32_t b = 0; b < 8; b++) {
+                const uint32_t p = 8 * lane + b, A = base + p;
+                if (p < STROBE_R && A >= A0 && A < A_end) w |= (uint64_t)absorb_stream_byte(A, base, A0, pb0, label, msgs) << (8 * b);
+            }
+            if (lane == 20 && e < nfull) w ^= ((uint64_t)absorb_close_pb(base, A0) << 48) | ((uint64_t)(0x04 ^ 0x80) << 56);      // bytes 166, 167
+            a ^= w;
+        }
+        if (e < nfull) {
+            for (int r = 0; r < 24; r++) {
+                uint64_t c = a ^ sh64(a, l5) ^ sh64(a, l10) ^ sh64(a, l15) ^ sh64(a, l20);                 // column parity (every lane of the column gets it)
+                const uint64_t cm = sh64(c, dm), cp = sh64(c, dp);
+                a ^= cm ^ ((cp << 1) | (cp >> 63));
+                uint64_t bsrc = sh64(a, src);
+                bsrc = (bsrc << rot) | (bsrc >> ((64 - rot) & 63));
+                const uint64_t b1 = sh64(bsrc, c1), b2 = sh64(bsrc, c2);
+                a = bsrc ^ (~b1 & b2);
+                if (lane == 0) a ^= KECCAK_RC_[r];
+            }
+        }
+    }
+    if (lane < 25) h.st[lane] = a;
+#endif
     if (lane == 0) {
         const uint32_t a2l = A0 + 41u * (m - 1) + 7, cur = A_end / STROBE_R * STROBE_R;
         h.pos = A_end - cur;
