@@ -25,6 +25,8 @@ extern "C" int rofl_set_option(rofl_ctx *c, const char *name, long value) {
     else if (n == "frozen") c->e.use_frz = value != 0;
     else if (n == "tail_np") c->e.tail_np = (int)std::max<long>(0, std::min<long>(TAIL_MAX_F / 2, value));
     else if (n == "rt_per") c->e.rt_per = (int)std::max<long>(0, std::min<long>(64, value));
+    else if (n == "nt_unfold") c->e.nt_unfold = (int)std::max<long>(0, std::min<long>(4, value));
+    else if (n == "nt_unfold_min") c->e.nt_unfold_min = (int)std::max<long>(2, std::min<long>(1 << 30, value));
     else if (n == "ts_host_m") c->e.ts_host_m = (int)std::max<long>(0, std::min<long>(1 << 30, value));
     else if (n == "max_lanes") c->e.max_lanes = (int)std::max<long>(1, std::min<long>(64, value));
     else return ROFL_ERR_ARGS;

@@ -27,7 +27,8 @@ enum { DOM_RANGE_PROVE = 1, DOM_RANGE_VERIFY = 2, DOM_SQUARE = 3, DOM_L2_PROVE =
 enum { PROF_FOLD = 0, PROF_MSM = 1, PROF_COMMIT = 2, PROF_SQUARE = 3, PROF_RTMSM = 4, PROF_TAIL = 5, PROF_FRZ = 6, PROF_SLOTS = 8 };
 
 struct gens_entry { int n = 0; int cap = 0; niels_st *G = nullptr, *H = nullptr;
-                    int rt_cap = 0, rt_c = 8; niels_st *RTG = nullptr, *RTH = nullptr; size_t rt_bytes = 0; uint64_t last_use = 0; };     // radix-2^rt_c tables (RT path)
+                    int rt_cap = 0, rt_c = 8; niels_st *RTG = nullptr, *RTH = nullptr; size_t rt_bytes = 0; uint64_t last_use = 0;
+                    int rt_nofit = 0; };     // smallest party count whose tables did NOT fit the device (0 = none yet): not tried again until tables are dropped     // radix-2^rt_c tables (RT path)
 struct bsgs_entry { unsigned long long *keys = nullptr; uint32_t *vals = nullptr; uint32_t cap = 0; uint64_t size = 0; };
 // Everything that is a function of the DEVICE alone lives once per device and process and is shared by all contexts on it: the fixed-base
 // tables of B / B_blinding, the Bulletproofs generators, their radix-2^c tables (tens of GB) and the BSGS tables (server.rs:54,84 shares one
@@ -70,6 +71,7 @@ struct rofl_engine {
     int use_frz = 1;                      // middle IPP rounds over frozen generators with on-the-fly Straus tables (kernels.cuh K6c)
     int rt_bits = RT_MAX_BITS;            // widest generator-table radix to try (8..11)
     double group_w[ROFL_MAX_GROUPS] = {1.0, 1.0, 1.0, 1.0};      // relative chunk counts of the groups
+    int nt_unfold = 4, nt_unfold_min = 1 << 16;      // unfolded IPP rounds without generator tables, for chunks of at least that many bit positions
     int ts_host_m = 8192;                 // chunks with more commitments than this absorb them on the host (absorb_commitments)
     int rt_per = 2;                       // table-MSM terms per thread and block: short blocks let the other groups' small kernels in quickly
     double rt_mem_frac = 0.45;            // tables may take this fraction of the free device memory
@@ -246,8 +248,10 @@ static inline bool engine_rt(rofl_engine &e, tables_use &tu, cudaStream_t s, int
     for (;;) {
         gens_entry &g = sh.gens[n];                          // exists: engine_gens ran first
         if (g.rt_cap >= m) { g.last_use = ++sh.clock; out.G = g.RTG; out.H = g.RTH; rt_fill(out, g.rt_c); return true; }
+        if (g.rt_nofit && m >= g.rt_nofit) return false;         // (resnet18-full chunks: 2^22 generators would need terabytes; asking again would trim the scratch cache on every call)
         if (!tu.excl) { tu.upgrade(); continue; }
         const size_t cnt = (size_t)n * m;
+        if ((double)rt_table_bytes(cnt, 8) > 170e9) { g.rt_nofit = m; return false; }          // cannot fit any B200 even at the narrowest radix: keep what is cached
         rt_sync(s); rt_raw_free(g.RTG); rt_raw_free(g.RTH); g.RTG = g.RTH = nullptr; g.rt_cap = 0; g.rt_bytes = 0;
         rt_trim();
         const int want = std::max(8, std::min(RT_MAX_BITS, e.rt_bits));
@@ -261,7 +265,7 @@ static inline bool engine_rt(rofl_engine &e, tables_use &tu, cudaStream_t s, int
             if (!victim) break;
             rt_raw_free(victim->RTG); rt_raw_free(victim->RTH); victim->RTG = victim->RTH = nullptr; victim->rt_cap = 0; victim->rt_bytes = 0;
         }
-        if (c < 8) { sh.free_hint = rt_free_mem(); return false; }
+        if (c < 8) { g.rt_nofit = m; sh.free_hint = rt_free_mem(); return false; }
         rt_tables t; rt_fill(t, c);
         const size_t bytes = cnt * rt_row_entries(t) * sizeof(niels_st);
         niels_st *RTG = (niels_st *)rt_raw_malloc(bytes), *RTH = (niels_st *)rt_raw_malloc(bytes);
@@ -282,7 +286,7 @@ static inline bool engine_rt(rofl_engine &e, tables_use &tu, cudaStream_t s, int
 // drop every cached generator table of the device (they are rebuilt on next use)
 static inline void engine_drop_rt(rofl_engine &e) {
     std::unique_lock<std::shared_mutex> ex(e.sh->tab_mu);
-    for (auto &g : e.sh->gens) { rt_raw_free(g.second.RTG); rt_raw_free(g.second.RTH); g.second.RTG = g.second.RTH = nullptr; g.second.rt_cap = 0; g.second.rt_bytes = 0; }
+    for (auto &g : e.sh->gens) { rt_raw_free(g.second.RTG); rt_raw_free(g.second.RTH); g.second.RTG = g.second.RTH = nullptr; g.second.rt_cap = 0; g.second.rt_bytes = 0; g.second.rt_nofit = 0; }
 }
 // blocks per msm for the direct table MSM: every block of a wave runs ceil(T / (nb*128)) terms per thread, so pick the nb whose
 // waves (148 SMs x 4 resident blocks) x terms-per-thread product is smallest (+ a block-sum epilogue worth ~half a term)
@@ -310,18 +314,26 @@ static inline void run_rt_msm(rofl_engine &e, cudaStream_t s, rt_msm_args a, int
 
 // ---- MSM front end ----------------------------------------------------------------------------------------------------------
 // window width and term slicing for an MSM of T terms run as n_msm independent instances (kernels.cuh, k_msm)
-struct msm_plan { int c, nw; uint32_t slices, slice_len; size_t out_count(size_t n_msm) const { return n_msm * slices * (size_t)nw; } };
+struct msm_plan { int c, nw; uint32_t slices, slice_len; bool big = false; uint32_t parts = 1; size_t out_count(size_t n_msm) const { return n_msm * slices * (size_t)nw; } };
 static inline int msm_pick_c(size_t T) {
     int best = 8; double bc = 1e300;
     for (int c = 3; c <= 8; c++) { const double B = (double)(1 << (c - 1)), cost = (double)msm_nw(c) * ((double)T + B * c); if (cost < bc) { bc = cost; best = c; } }
     return best;
 }
+static inline size_t bm_min_terms() { static const size_t v = getenv("ROFL_BM_MIN") ? (size_t)atoll(getenv("ROFL_BM_MIN")) : (size_t)32768; return v; }
 static inline msm_plan msm_plan_for(size_t T, size_t n_msm) {
     msm_plan p; p.c = msm_pick_c(T); p.slices = 1; p.slice_len = (uint32_t)T;
     if (const char *fc = getenv("ROFL_MSM_C")) {       // test hook: force the window width / slicing
-        p.c = std::max(3, std::min(8, atoi(fc)));
+        p.c = std::max(3, std::min(16, atoi(fc)));
+        if (p.c > 8) { p.big = true; p.parts = getenv("ROFL_MSM_SLICES") ? (uint32_t)std::max(1, std::min(8, atoi(getenv("ROFL_MSM_SLICES")))) : 1; p.nw = msm_nw(p.c); return p; }
         if (const char *fs = getenv("ROFL_MSM_SLICES")) { p.slices = (uint32_t)std::max<size_t>(1, std::min<size_t>(atoi(fs), T)); p.slice_len = (uint32_t)((T + p.slices - 1) / p.slices); p.slices = (uint32_t)((T + p.slice_len - 1) / p.slice_len); }
         p.nw = msm_nw(p.c); return p;
+    }
+    if (T >= bm_min_terms()) {                         // wide windows, buckets sorted in global memory (kernels.cuh K4b): ~64 terms per bucket
+        p.big = true; p.c = std::max(9, std::min(16, ilog2_sz(T + 1) - 6)); p.nw = msm_nw(p.c);
+        const size_t threads = n_msm * (size_t)p.nw * ((size_t)1 << (p.c - 1));
+        p.parts = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (148 * 1024 + threads - 1) / threads));
+        return p;
     }
     const size_t wpb = MSM_THREADS >> (p.c - 1), blocks = n_msm * ((msm_nw(p.c) + wpb - 1) / wpb), slots = 148 * 4;
     if (blocks < slots && T >= 4096) {
@@ -335,12 +347,28 @@ static inline msm_plan msm_plan_for(size_t T, size_t n_msm) {
 // a: v[], split, nseg, T, scalar_stride, out filled by the caller
 static inline void run_msm(rofl_engine &e, cudaStream_t s, msm_args a, const msm_plan &p, uint32_t n_msm) {
     a.c = p.c; a.nw = p.nw; a.slices = p.slices; a.slice_len = p.slice_len; msm_recode_const(a.K, p.c);
-    const int wpb = MSM_THREADS >> (p.c - 1);
     void *tk = rt_prof_begin(PROF_MSM, s);
-    LAUNCH_COOP(k_msm, dim3((p.nw + wpb - 1) / wpb, n_msm, p.slices), dim3(MSM_THREADS), s, a);
+    if (p.big) {
+        const size_t B = (size_t)1 << (p.c - 1), nslot = (size_t)n_msm * p.nw * (B + 1);
+        dev_buf d_start(4 * nslot, s), d_cur(4 * nslot, s), d_sorted(4 * (size_t)n_msm * p.nw * a.T, s), d_bkt(sizeof(p3_st) * (size_t)n_msm * p.nw * B * p.parts, s);
+        a.bm_start = d_start.as<uint32_t>(); a.bm_cur = d_cur.as<uint32_t>(); a.bm_sorted = d_sorted.as<uint32_t>(); a.bm_bkt = d_bkt.as<p3_st>(); a.parts = p.parts;
+        // top window: 254 - c (nw - 1) bits.  Fewer than c - 4 -> at most B / 16 of its buckets can be hit: deal its B * parts threads out over those
+        a.top_bits = (uint32_t)(254 - p.c * (p.nw - 1)); a.parts_top = 0;
+        if ((int)a.top_bits < p.c - 4) a.parts_top = (uint32_t)((B * p.parts) >> (a.top_bits + 1));
+        rt_memset(d_start.p, 0, 4 * nslot, s);
+        const dim3 gt((unsigned)((a.T + 255) / 256), n_msm);
+        LAUNCH(k_bm_hist, gt, dim3(256), s, a, 0);
+        LAUNCH_COOP(k_bm_scan, dim3(p.nw, n_msm), dim3(256), s, a);
+        LAUNCH(k_bm_hist, gt, dim3(256), s, a, 1);
+        LAUNCH(k_bm_accum, dim3((unsigned)(((size_t)p.nw * B * p.parts + 127) / 128), n_msm), dim3(128), s, a);
+        LAUNCH_COOP(k_bm_reduce, dim3(p.nw, n_msm), dim3(128), s, a);
+    } else {
+        const int wpb = MSM_THREADS >> (p.c - 1);
+        LAUNCH_COOP(k_msm, dim3((p.nw + wpb - 1) / wpb, n_msm, p.slices), dim3(MSM_THREADS), s, a);
+    }
     rt_prof_end(PROF_MSM, tk, s);
 }
-static inline msm_seg mk_seg(const void *base, uint32_t count, uint32_t stride, int kind) { msm_seg s; s.base = base; s.count = count; s.stride = stride; s.kind = kind; return s; }
+static inline msm_seg mk_seg(const void *base, uint32_t count, uint32_t stride, int kind, uint32_t np = 0, int hi = 0) { msm_seg s; s.base = base; s.count = count; s.stride = stride; s.kind = kind; s.np = np; s.hi = hi; return s; }
 static inline void run_finalize(cudaStream_t s, const finalize_args &f) { LAUNCH_COOP(k_finalize, dim3(f.count), dim3(FIN_THREADS), s, f); }
 static inline void fin_windows(finalize_args &f, const p3_st *win, const msm_plan &p) { f.windows = win; f.c = p.c; f.nw = p.nw; f.slices = p.slices; }
 
@@ -382,7 +410,11 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
     dev_buf d_keys(32 * (size_t)C, q), d_sLR(sizeof(sc_st) * 2 * NT, q), d_sums(sizeof(sc_st) * 5 * C, q);
     { std::vector<uint32_t> kw(8 * (size_t)C); for (int c = 0; c < C; c++) key_words(&kw[8 * c], &keys[32 * c]); rt_h2d(d_keys.p, kw.data(), 32 * (size_t)C, q.small()); }
     LAUNCH(k_nonces, dim3((unsigned)((NT + 255) / 256)), dim3(256), q.big(), d_sLR.as<sc_st>(), d_keys.as<uint32_t>(), n, m, NT);
-    LAUNCH_COOP(k_party_sums, dim3(C), dim3(256), q.small(), d_sums.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, (const sc_st *)nullptr, n, m, 0);
+    const int nbPS = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)m + 1023) / 1024));          // blocks per chunk of the per-party sums
+    dev_buf d_partPS(sizeof(sc_st) * 3 * (size_t)C * nbPS, q);
+    { pow_tab none = {nullptr, 0, 0};
+      LAUNCH_COOP(k_party_sums, dim3(nbPS, C), dim3(256), q.small(), d_partPS.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, (const sc_st *)nullptr, none, n, m, 0);
+      LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), q.small(), d_sums.as<sc_st>(), d_partPS.as<sc_st>(), nbPS, 2); }
     // ---- A
     const int nbA = (int)std::min<size_t>(64, (N + 511) / 512);
     dev_buf d_partA(sizeof(p3_st) * (size_t)C * nbA, q), d_AS(64 * (size_t)C, q);
@@ -431,7 +463,8 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
     LAUNCH(k_pow_tables, dim3((pow_tab_size(ztab) + 255) / 256, C), dim3(256), q.small(), (sc_st *)ztab.tab, d_zpow2.as<sc_st>(), ztab.L, ztab.H);
     LAUNCH_COOP(k_poly, dim3(nbP, C), dim3(256), q.big(), d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_part.as<sc_st>(), d_vals, ytab, ztab, d_zpow2.as<sc_st>(), n, m);
     LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), q.small(), d_tsum.as<sc_st>(), d_part.as<sc_st>(), nbP, 3);
-    LAUNCH_COOP(k_party_sums, dim3(C), dim3(256), q.small(), d_sums.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, d_z.as<sc_st>(), n, m, 1);
+    LAUNCH_COOP(k_party_sums, dim3(nbPS, C), dim3(256), q.small(), d_partPS.as<sc_st>(), d_keys.as<uint32_t>(), d_blind, d_z.as<sc_st>(), ztab, n, m, 1);
+    LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), q.small(), d_sums.as<sc_st>() + 2 * (size_t)C, d_partPS.as<sc_st>(), nbPS, 3);
     dev_buf d_t12(sizeof(sc_st) * 2 * C, q), d_T12(64 * (size_t)C, q);
     LAUNCH(k_ts_t12, dim3((unsigned)((C + 63) / 64)), dim3(64), q.small(), d_t12.as<sc_st>(), d_tsum.as<sc_st>(), (uint32_t)C);
     {
@@ -458,7 +491,9 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
     // rounds with half-size <= tail_np run in the fused on-device tail kernel; `pre` rounds come before it
     const size_t tail_np = (size_t)std::min(e.tail_np, TAIL_MAX_F / 2);
     int pre = 0; while (pre < lgN && ((N / 2) >> pre) > tail_np) pre++;
-    const int r_unf = rt ? std::min({e.rt_unfold, lgN, pre}) : 0;
+    // without tables (chunks of 2^18 values and more): the same unfolded rounds as wide-window Pippenger MSMs over the original generators, then a
+    // joint double-and-add catch-up (k_catchup_naf) -- 2^r bases per output share 252 doublings instead of a fold ladder per base and level
+    const int r_unf = rt ? std::min({e.rt_unfold, lgN, pre}) : ((N >= (size_t)e.nt_unfold_min && e.nt_unfold > 0) ? std::min({e.nt_unfold, lgN, pre, 4}) : 0);
     const int nbU = rt ? rt_blocks(N, 2 * C, e.rt_per) : 1;
     const uint32_t cstride = 1u << (r_unf > 0 ? r_unf : 0);
     // coefficient tables of the unfolded rounds [G | H][C][cstride], kept on the device: k_ts_round doubles them after every challenge
@@ -467,7 +502,7 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
         for (size_t c = 0; c < 2 * (size_t)C; c++) h[c * stride].w[0] = 1;
         rt_h2d(d.p, h.data(), sizeof(sc_st) * h.size(), q.small());
     };
-    dev_buf d_cGH(sizeof(sc_st) * 2 * (size_t)C * cstride, q), d_partU(sizeof(p3_st) * 2 * (size_t)C * nbU, q), d_digs(sizeof(int16_t) * 2 * (size_t)C * cstride * RT_MAXW, q);
+    dev_buf d_cGH(sizeof(sc_st) * 2 * (size_t)C * cstride, q), d_partU(sizeof(p3_st) * 2 * (size_t)C * nbU, q), d_digs(rt ? sizeof(int16_t) * 2 * (size_t)C * cstride * RT_MAXW : 256 * 2 * (size_t)C * cstride, q);
     coef_init(d_cGH, cstride);
     const int nbQ = (int)std::min<size_t>(256, (N / 2 + 255) / 256);
     dev_buf d_partQ(sizeof(sc_st) * 2 * (size_t)C * nbQ, q);
@@ -549,12 +584,25 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
             LAUNCH_COOP(k_ipp_scalars_unf, dim3(nbQ, C), dim3(256), q.big(), d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), d_cGH.as<sc_st>(), d_cGH.as<sc_st>() + (size_t)C * cstride, cstride,
                         msmL, msmR, d_partQ.as<sc_st>(), N, (uint32_t)np, (uint32_t)N);
             LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), q.small(), d_cLR.as<sc_st>(), d_partQ.as<sc_st>(), nbQ, 2);
-            rt_msm_args aL = {}; aL.scalars = msmL; aL.T = (uint32_t)N; aL.scalar_stride = (uint32_t)N; aL.nG = (uint32_t)(N / 2); aL.np = (uint32_t)np; aL.mode = 1; aL.rt = *rt; aL.partial = d_partU.as<p3_st>();
-            rt_msm_args aR = aL; aR.scalars = msmR; aR.mode = 2; aR.partial = d_partU.as<p3_st>() + (size_t)C * nbU;
-            run_rt_msm(e, q.big(), aL, nbU, C); run_rt_msm(e, q.big(), aR, nbU, C);
-            finalize_args f = {}; f.partial = d_partU.as<p3_st>(); f.npartial = nbU; f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.sh->tabB; f.tabH = e.sh->tabH;
-            f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
-            run_finalize(q.small(), f);
+            if (rt) {
+                rt_msm_args aL = {}; aL.scalars = msmL; aL.T = (uint32_t)N; aL.scalar_stride = (uint32_t)N; aL.nG = (uint32_t)(N / 2); aL.np = (uint32_t)np; aL.mode = 1; aL.rt = *rt; aL.partial = d_partU.as<p3_st>();
+                rt_msm_args aR = aL; aR.scalars = msmR; aR.mode = 2; aR.partial = d_partU.as<p3_st>() + (size_t)C * nbU;
+                run_rt_msm(e, q.big(), aL, nbU, C); run_rt_msm(e, q.big(), aR, nbU, C);
+                finalize_args f = {}; f.partial = d_partU.as<p3_st>(); f.npartial = nbU; f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.sh->tabB; f.tabH = e.sh->tabH;
+                f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
+                run_finalize(q.small(), f);
+            } else {
+                // L: G-terms on the hi halves, H-terms on the lo halves of the 2np-blocks of the ORIGINAL generators; R: the other way round
+                const msm_plan pl = msm_plan_for(N, 2 * (size_t)C);
+                dev_buf d_win(sizeof(p3_st) * pl.out_count(2 * (size_t)C), q);
+                msm_args a = {}; a.v[0].scalars = msmL; a.v[1].scalars = msmR; a.split = (uint32_t)C; a.T = (uint32_t)N; a.scalar_stride = (uint32_t)N; a.nseg = 2; a.out = d_win.as<p3_st>();
+                a.v[0].seg[0] = mk_seg(g.G, (uint32_t)(N / 2), 0, 0, (uint32_t)np, 1); a.v[0].seg[1] = mk_seg(g.H, (uint32_t)(N / 2), 0, 0, (uint32_t)np, 0);
+                a.v[1].seg[0] = mk_seg(g.G, (uint32_t)(N / 2), 0, 0, (uint32_t)np, 0); a.v[1].seg[1] = mk_seg(g.H, (uint32_t)(N / 2), 0, 0, (uint32_t)np, 1);
+                run_msm(e, q.big(), a, pl, 2 * (uint32_t)C);
+                finalize_args f = {}; fin_windows(f, d_win.as<p3_st>(), pl); f.sBa = d_cLR.as<sc_st>(); f.sBb = d_w2.as<sc_st>(); f.tabB = e.sh->tabB; f.tabH = e.sh->tabH;
+                f.out32 = d_LR.as<uint8_t>(); f.count = 2 * C;
+                run_finalize(q.small(), f);
+            }
         } else {
             LAUNCH_COOP(k_ipp_scalars, dim3(nbI, C), dim3(256), q.small(), d_a.as<sc_st>(), d_b.as<sc_st>(), d_yinv.as<sc_st>(), msmL, msmR, d_part.as<sc_st>(), N, (uint32_t)np);
             LAUNCH_COOP(k_sc_sum, dim3(C), dim3(256), q.small(), d_cLR.as<sc_st>(), d_part.as<sc_st>(), nbI, 2);
@@ -582,16 +630,23 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
             t.yinvpow2 = d_yinvpow2.as<sc_st>(); t.lgnp = ilog2_sz(np); t.u2 = d_u2.as<sc_st>(); t.uinv2 = d_uinv2.as<sc_st>(); t.up = d_up.as<sc_st>();
             if (frozen) { t.coefG = d_cA.as<sc_st>(); t.coefH = d_cA.as<sc_st>() + (size_t)C * cAstride; t.cstride = cAstride; t.nblk = (uint32_t)(FA / (2 * np)); if (round + 1 == pre && pre < lgN) { t.emit = 3; t.digs8 = d_dg.as<int8_t>(); } }
             else if (unfolded) { t.coefG = d_cGH.as<sc_st>(); t.coefH = d_cGH.as<sc_st>() + (size_t)C * cstride; t.cstride = cstride; t.nblk = 1u << round;
-                                 if (catchup) { t.emit = 2; t.digs16 = d_digs.as<int16_t>(); for (int i = 0; i < 9; i++) t.rtK[i] = rt->K[i]; t.rtc = rt->c; t.rtnw = rt->nw; } }
+                                 if (catchup && rt) { t.emit = 2; t.digs16 = d_digs.as<int16_t>(); for (int i = 0; i < 9; i++) t.rtK[i] = rt->K[i]; t.rtc = rt->c; t.rtnw = rt->nw; }
+                                 else if (catchup) { t.emit = 4; t.nafs = d_digs.as<int8_t>(); } }
             else if (fold) { t.emit = 1; t.nafs = d_nafs.as<int8_t>(); }
             LAUNCH_COOP(k_ts_round, dim3(C), dim3(TS_THREADS), q.small(), t);
         }
         LAUNCH(k_ipp_fold_scalars, dim3((unsigned)((np + 255) / 256), C), dim3(256), q.small(), d_a.as<sc_st>(), d_b.as<sc_st>(), d_u2.as<sc_st>(), d_uinv2.as<sc_st>(), N, (uint32_t)np);
-        if (catchup) {               // G", H" of length np straight from the tables
+        if (catchup && rt) {         // G", H" of length np straight from the tables
             catchup_args ca = {}; ca.rt = *rt; ca.Gf = d_Gf.as<p3_st>(); ca.Hf = d_Hf.as<p3_st>(); ca.digits = d_digs.as<int16_t>(); ca.nr = (uint32_t)np; ca.nblk = 1u << r_unf; ca.stride = (uint32_t)half;
             q.big();
             void *tk = rt_prof_begin(PROF_FOLD, q.cur ? q.lo : q.hi);
             LAUNCH_COOP(k_rt_catchup, dim3((unsigned)((np + 127) / 128), C, 2), dim3(128), q.big(), ca);
+            rt_prof_end(PROF_FOLD, tk, q.cur ? q.lo : q.hi);
+        } else if (catchup) {        // ... or by one joint double-and-add over the 2^r_unf original generators of every output
+            catchup_naf_args ca = {}; ca.G = g.G; ca.H = g.H; ca.Gf = d_Gf.as<p3_st>(); ca.Hf = d_Hf.as<p3_st>(); ca.nafs = d_digs.as<int8_t>(); ca.nr = (uint32_t)np; ca.nblk = 1u << r_unf; ca.stride = (uint32_t)half;
+            q.big();
+            void *tk = rt_prof_begin(PROF_FOLD, q.cur ? q.lo : q.hi);
+            LAUNCH_COOP(k_catchup_naf, dim3((unsigned)((np + 127) / 128), C, 2), dim3(128), q.big(), ca);
             rt_prof_end(PROF_FOLD, tk, q.cur ? q.lo : q.hi);
         } else if (fold) {
             fold_args fa = {}; fa.Gn = round == 0 ? g.G : nullptr; fa.Hn = round == 0 ? g.H : nullptr;

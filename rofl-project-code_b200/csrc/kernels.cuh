@@ -229,17 +229,29 @@ KERNEL void LB(256, 2) k_nonces(sc_st *sLR, const uint32_t *keys, int n, int m, 
 }
 KLAUNCH(k_nonces, false, (sc_st *sLR, const uint32_t *keys, int n, int m, size_t total), (sLR, keys, n, m, total))
 #endif
-// per-chunk sums over parties.  out[q*C + c] (C = gridDim.x): q=0 sum a_bl, 1 sum s_bl, 2 sum t1_bl, 3 sum t2_bl, 4 sum z^(j+2) gamma_j
-// phase 0 computes q=0,1 ; phase 1 computes q=2,3,4 (needs z)
+// split power tables: b^e = lo[e & (2^L - 1)] * hi[e >> L] -- one multiplication per position instead of a square-and-multiply.
+//   tab[c*(2^L + 2^H) + ..] = lo[2^L] | hi[2^H] for base b_c given as pow2[c*32 + i] = b_c^(2^i)
+struct pow_tab { const sc_st *tab; int L, H; };
+HD uint32_t pow_tab_size(const pow_tab &t) { return (1u << t.L) + (1u << t.H); }
+HD void sc_pow_tab(sc &r, const sc_st *pow2, uint64_t e) {
+    sc_from_u64(r, 1);
+    for (int b = 0; e; b++, e >>= 1) if (e & 1) { sc t; ld_sc(t, pow2 + b); sc_mul(r, r, t); }
+}
+HD void pow_tab_get(sc &r, const pow_tab &t, int c, uint64_t e) {
+    const sc_st *b = t.tab + (size_t)c * pow_tab_size(t);
+    sc lo, hi; ld_sc(lo, b + (e & ((1u << t.L) - 1))); ld_sc(hi, b + (1u << t.L) + (e >> t.L)); sc_mul(r, lo, hi);
+}
+// per-chunk sums over parties, block partials: partial[(c*gridDim.x + blockIdx.x)*q + s] (grid (blocks, C); k_sc_sum adds the blocks up).
+//   phase 0 (q = 2): s=0 sum a_bl, 1 sum s_bl ;  phase 1 (q = 3, needs z and the split power table of z): s=0 sum t1_bl, 1 sum t2_bl, 2 sum z^(j+2) gamma_j
 #ifdef KG_SCALAR
-KERNEL void LB(256, 1) k_party_sums(sc_st *out, const uint32_t *keys, const sc_st *blind, const sc_st *z, int n, int m, int phase) {
+KERNEL void LB(256, 1) k_party_sums(sc_st *partial, const uint32_t *keys, const sc_st *blind, const sc_st *z, pow_tab ztab, int n, int m, int phase) {
     __shared__ sc_st buf[256];
-    int c = blockIdx.x, tid = threadIdx.x;
+    int c = blockIdx.y, tid = threadIdx.x;
     uint32_t kk[8]; for (int t = 0; t < 8; t++) kk[t] = keys[8 * c + t];
     sc s0, s1, s2; sc_0(s0); sc_0(s1); sc_0(s2);
     sc zc, zz; sc_0(zc); sc_0(zz);
     if (phase == 1) { ld_sc(zc, z + c); sc_mul(zz, zc, zc); }
-    for (int j = tid; j < m; j += blockDim.x) {
+    for (int j = blockIdx.x * blockDim.x + tid; j < m; j += gridDim.x * blockDim.x) {
         sc t;
         if (phase == 0) {
             nonce_scalar(t, kk, (uint64_t)j * (2 * n + 2)); sc_add(s0, s0, t);
@@ -248,19 +260,19 @@ KERNEL void LB(256, 1) k_party_sums(sc_st *out, const uint32_t *keys, const sc_s
             uint64_t base = (uint64_t)m * (2 * n + 2);
             nonce_scalar(t, kk, base + 2 * (uint64_t)j); sc_add(s0, s0, t);
             nonce_scalar(t, kk, base + 2 * (uint64_t)j + 1); sc_add(s1, s1, t);
-            sc zj, g; sc_pow_u64(zj, zc, (uint64_t)j); sc_mul(zj, zj, zz);
+            sc zj, g; pow_tab_get(zj, ztab, c, (uint64_t)j); sc_mul(zj, zj, zz);
             ld_sc(g, blind + (size_t)c * m + j); sc_mul(g, g, zj); sc_add(s2, s2, g);
         }
     }
     block_sum_sc(s0, buf, tid, blockDim.x); block_sum_sc(s1, buf, tid, blockDim.x);
     if (phase == 1) block_sum_sc(s2, buf, tid, blockDim.x);
     if (tid == 0) {
-        int C = gridDim.x;
-        if (phase == 0) { st_sc(out + 0 * C + c, s0); st_sc(out + 1 * C + c, s1); }
-        else { st_sc(out + 2 * C + c, s0); st_sc(out + 3 * C + c, s1); st_sc(out + 4 * C + c, s2); }
+        const int q = phase == 0 ? 2 : 3;
+        sc_st *o = partial + ((size_t)c * gridDim.x + blockIdx.x) * q;
+        st_sc(o, s0); st_sc(o + 1, s1); if (phase == 1) st_sc(o + 2, s2);
     }
 }
-KLAUNCH(k_party_sums, true, (sc_st *out, const uint32_t *keys, const sc_st *blind, const sc_st *z, int n, int m, int phase), (out, keys, blind, z, n, m, phase))
+KLAUNCH(k_party_sums, true, (sc_st *partial, const uint32_t *keys, const sc_st *blind, const sc_st *z, pow_tab ztab, int n, int m, int phase), (partial, keys, blind, z, ztab, n, m, phase))
 #endif
 
 // ===================================================================================================================
@@ -296,7 +308,8 @@ KLAUNCH(k_bits_sum, true, (p3_st *partial, const uint64_t *vals, const niels_st 
 #define MSM_THREADS 128
 #define MSM_SORT 8192
 #define MSM_MAXW 85
-struct msm_seg { const void *base; uint32_t count; uint32_t stride; int kind; };     // kind 0 = niels_st, 1 = p3_st; stride = records per msm (0: shared)
+struct msm_seg { const void *base; uint32_t count; uint32_t stride; int kind; uint32_t np; int hi; };     // kind 0 = niels_st, 1 = p3_st; stride = records per msm (0: shared)
+//   np > 0: term q of the segment is record (q / np) * 2 np + (hi ? np : 0) + q % np -- the hi / lo halves of consecutive 2np-blocks (unfolded IPP round over the original generators)
 struct msm_var { const sc_st *scalars; msm_seg seg[4]; };                            // scalars[idx*scalar_stride + t]
 struct msm_args {
     msm_var v[2]; uint32_t split;            // msm < split: v[0] with idx = msm; else v[1] with idx = msm - split   (L / R in one launch)
@@ -304,6 +317,12 @@ struct msm_args {
     int c, nw; uint32_t K[9];                // window bits, window count = ceil(254/c), recoding constant
     uint32_t slices, slice_len;              // slice s covers terms [s*slice_len, min(T, (s+1)*slice_len))
     p3_st *out;                              // out[(msm*slices + slice)*nw + w]
+    // big-window path (k_bm_*): per (msm, window) B = 2^(c-1) buckets; start[(msm*nw + w)*(B+1) + b], cursors likewise, sorted[(msm*nw + w)*T + ..],
+    // bucket sums bkt[((msm*nw + w)*B + b)*parts + part]
+    uint32_t *bm_start, *bm_cur, *bm_sorted; p3_st *bm_bkt; uint32_t parts;
+    // the TOP window holds only 254 - c (nw-1) bits: when that is far less than c its few buckets are enormous (every term falls into one of
+    // 2^top_bits + 1 buckets) -- they are cut into parts_top pieces each instead of `parts` (0 = the top window is treated like the others)
+    uint32_t top_bits, parts_top;
 };
 HD int msm_nw(int c) { return (254 + c - 1) / c; }
 HD void msm_recode_const(uint32_t K[9], int c) {
@@ -328,7 +347,7 @@ HD void msm_add_term(ge_p3 &acc, const msm_var &v, int nseg, uint32_t idx, uint3
     for (int s = 0; s < nseg; s++) {
         const msm_seg &g = v.seg[s];
         const bool here = kind < 0 && t < start + g.count;
-        if (here) { base = g.base; rec = (size_t)idx * g.stride + (t - start); kind = g.kind; }
+        if (here) { const uint32_t q = t - start, j = g.np ? (q / g.np) * 2 * g.np + (g.hi ? g.np : 0) + q % g.np : q; base = g.base; rec = (size_t)idx * g.stride + j; kind = g.kind; }
         start += g.count;
     }
     if (kind == 0) acc_add_niels(acc, (const niels_st *)base + rec, neg);
@@ -393,6 +412,95 @@ KERNEL void LB(MSM_THREADS, 4) k_msm(msm_args a) {
     if (b_mine == 0 && wl_mine < nwl) { ge_p3 r; ld_p3(r, bk + tid); st_p3(a.out + ((size_t)msm * a.slices + slice) * a.nw + w0 + wl_mine, r); }
 }
 KLAUNCH(k_msm, true, (msm_args a), (a))
+#endif
+
+// ===================================================================================================================
+// K4b: Pippenger with WIDE windows (c = 9 .. 16) for long multiscalar multiplications -- resnet18-full chunks (2^22 generators per
+//   chunk: no table fits), the server's batched check over all clients' commitments, the verifier's commitment MSM.
+//   k_msm keeps its buckets in one block (c <= 8: 32 additions per term, bucket lists of uneven length walked by the lanes of a warp);
+//   here the (term, window) pairs are counting-sorted by bucket in global memory, so that
+//     * a term costs ceil(254/c) additions (16 at c = 16 instead of 32),
+//     * every thread owns one bucket (or 1/parts of it) and walks a list of Poisson-equal length: lanes of a warp stay in step,
+//     * the bucket reduction sum_b b*B_b is a segmented running sum (128 threads per window).
+//   k_bm_hist -> k_bm_scan -> k_bm_scatter -> k_bm_accum -> k_bm_reduce; the window sums go to k_finalize like k_msm's (slices = 1).
+//   The order of the entries inside a bucket depends on the atomics' timing; the bucket SUM does not (same group element, and every
+//   consumer compresses to the canonical encoding).
+// ===================================================================================================================
+#ifdef KG_MSM
+KERNEL void LB(256, 2) k_bm_hist(msm_args a, int scatter) {
+    const uint32_t msm = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.T) return;
+    const msm_var &v = msm < a.split ? a.v[0] : a.v[1];
+    const uint32_t idx = msm < a.split ? msm : msm - a.split, B = 1u << (a.c - 1);
+    sc x; ld_sc(x, v.scalars + (size_t)idx * a.scalar_stride + t);
+    uint32_t xk[9]; msm_recode(xk, x, a.K);
+    for (int w = 0; w < a.nw; w++) {
+        const int d = msm_digit(xk, w, a.c);
+        if (d == 0) continue;
+        const size_t slot = ((size_t)msm * a.nw + w) * (B + 1) + (uint32_t)(d > 0 ? d : -d) - 1;
+        if (!scatter) atomicAdd(a.bm_start + slot, 1u);
+        else { const uint32_t pos = atomicAdd(a.bm_cur + slot, 1u); a.bm_sorted[((size_t)msm * a.nw + w) * a.T + pos] = t | (d < 0 ? 0x80000000u : 0u); }
+    }
+}
+KLAUNCH(k_bm_hist, false, (msm_args a, int scatter), (a, scatter))
+// counts -> exclusive start offsets (B + 1 entries per (msm, window), the last one = number of non-zero digits), copied to the cursors.  grid (nw, n_msm)
+KERNEL void LB(256, 1) k_bm_scan(msm_args a) {
+    __shared__ uint32_t part[256];
+    const uint32_t B = 1u << (a.c - 1), tid = threadIdx.x, per = (B + 1 + 255) / 256;
+    uint32_t *st = a.bm_start + ((size_t)blockIdx.y * a.nw + blockIdx.x) * (B + 1), *cu = a.bm_cur + ((size_t)blockIdx.y * a.nw + blockIdx.x) * (B + 1);
+    uint32_t sum = 0;
+    for (uint32_t i = tid * per; i < (tid + 1) * per && i <= B; i++) sum += i < B ? st[i] : 0;
+    part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) { uint32_t o = 0; for (int i = 0; i < 256; i++) { const uint32_t c = part[i]; part[i] = o; o += c; } }
+    __syncthreads();
+    uint32_t o = part[tid];
+    for (uint32_t i = tid * per; i < (tid + 1) * per && i <= B; i++) { const uint32_t c = i < B ? st[i] : 0; st[i] = o; cu[i] = o; o += c; }
+}
+KLAUNCH(k_bm_scan, true, (msm_args a), (a))
+// one thread per (window, bucket, part): the sum of its share of the bucket's points.  B * parts threads per window; in a "fat" top window they
+// are dealt out as parts_top threads for each of its 2^(top_bits + 1) possible buckets.
+KERNEL void LB(128, 3) k_bm_accum(msm_args a) {
+    const uint32_t msm = blockIdx.y, B = 1u << (a.c - 1);
+    const size_t per_w = (size_t)B * a.parts, gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, total = (size_t)a.nw * per_w;
+    if (gid >= total) return;
+    const uint32_t w = (uint32_t)(gid / per_w), local = (uint32_t)(gid % per_w);
+    const bool fat = a.parts_top && w == (uint32_t)a.nw - 1;
+    const uint32_t np = fat ? a.parts_top : a.parts, part = local % np, b = local / np;
+    const msm_var &v = msm < a.split ? a.v[0] : a.v[1];
+    const uint32_t idx = msm < a.split ? msm : msm - a.split;
+    const uint32_t *st = a.bm_start + ((size_t)msm * a.nw + w) * (B + 1), *lst = a.bm_sorted + ((size_t)msm * a.nw + w) * a.T;
+    ge_p3 acc; ge_p3_0(acc);
+    if (b < B) {
+        const uint32_t e1 = st[b + 1];
+        for (uint32_t e = st[b] + part; e < e1; e += np) { const uint32_t ent = lst[e]; msm_add_term(acc, v, a.nseg, idx, ent & 0x7fffffffu, (ent >> 31) != 0); }
+    }
+    st_p3(a.bm_bkt + ((size_t)msm * a.nw + w) * per_w + local, acc);
+}
+KLAUNCH(k_bm_accum, false, (msm_args a), (a))
+// out[msm*nw + w] = sum_b (b+1) * bucket_b: thread j takes the buckets [lo, hi) of its segment -- a descending running sum gives
+// sum (b - lo + 1) B_b, plus lo * (sum of the segment) by double-and-add -- and the 128 segments are added up by the block.  grid (nw, n_msm)
+KERNEL void LB(128, 2) k_bm_reduce(msm_args a) {
+    __shared__ p3_st buf[128];
+    const uint32_t B = 1u << (a.c - 1), tid = threadIdx.x, w = blockIdx.x, msm = blockIdx.y;
+    const bool fat = a.parts_top && w == (uint32_t)a.nw - 1;
+    const uint32_t np = fat ? a.parts_top : a.parts, nb = fat ? (2u << a.top_bits) : B;          // buckets that can be non-empty
+    const uint32_t per = (nb + 127) / 128, lo = tid * per, hi = lo + per < nb ? lo + per : nb;
+    const p3_st *bk = a.bm_bkt + ((size_t)msm * a.nw + w) * B * a.parts;
+    ge_p3 run, acc; ge_p3_0(run); ge_p3_0(acc);
+    for (uint32_t b = hi; b-- > lo;) {
+        for (uint32_t p = 0; p < np; p++) acc_add_p3(run, bk + (size_t)b * np + p, false);
+        ge_add(acc, acc, run);
+    }
+    if (lo > 0 && lo < hi) {                       // + lo * run
+        ge_p3 m; ge_p3_0(m);
+        for (int bit = 15; bit >= 0; bit--) { ge_p3_dbl(m, m); if ((lo >> bit) & 1) ge_add(m, m, run); }
+        ge_add(acc, acc, m);
+    }
+    block_sum_p3(acc, buf, (int)tid, 128);
+    if (tid == 0) st_p3(a.out + (size_t)msm * a.nw + w, acc);
+}
+KLAUNCH(k_bm_reduce, true, (msm_args a), (a))
 #endif
 
 // combine, one block per output idx:
@@ -469,18 +577,6 @@ KLAUNCH(k_finalize, true, (finalize_args a), (a))
 //   t1' = <l0+l1, r0+r1>.   ypow2[c*32+b] = y^(2^b), zpow2 likewise.  r1 overwrites sR.
 //   partial[(c*gridDim.x + blockIdx.x)*3 + q]
 // ===================================================================================================================
-// split power tables: b^e = lo[e & (2^L - 1)] * hi[e >> L] -- one multiplication per position instead of a square-and-multiply.
-//   tab[c*(2^L + 2^H) + ..] = lo[2^L] | hi[2^H] for base b_c given as pow2[c*32 + i] = b_c^(2^i)
-struct pow_tab { const sc_st *tab; int L, H; };
-HD uint32_t pow_tab_size(const pow_tab &t) { return (1u << t.L) + (1u << t.H); }
-HD void sc_pow_tab(sc &r, const sc_st *pow2, uint64_t e) {
-    sc_from_u64(r, 1);
-    for (int b = 0; e; b++, e >>= 1) if (e & 1) { sc t; ld_sc(t, pow2 + b); sc_mul(r, r, t); }
-}
-HD void pow_tab_get(sc &r, const pow_tab &t, int c, uint64_t e) {
-    const sc_st *b = t.tab + (size_t)c * pow_tab_size(t);
-    sc lo, hi; ld_sc(lo, b + (e & ((1u << t.L) - 1))); ld_sc(hi, b + (1u << t.L) + (e >> t.L)); sc_mul(r, lo, hi);
-}
 #ifdef KG_SCALAR
 KERNEL void LB(256, 1) k_pow_tables(sc_st *tab, const sc_st *pow2, int L, int H) {
     const int c = blockIdx.y; const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x, nlo = 1u << L, n = nlo + (1u << H);
@@ -1046,9 +1142,13 @@ void launch_k_gens_build(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *G, niels_s
 void launch_k_commit(dim3 g_, dim3 b_, cudaStream_t s_, commit_args a);
 void launch_k_field_selftest(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const uint8_t *a32, const uint8_t *b32, size_t n);
 void launch_k_nonces(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *sLR, const uint32_t *keys, int n, int m, size_t total);
-void launch_k_party_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *out, const uint32_t *keys, const sc_st *blind, const sc_st *z, int n, int m, int phase);
+void launch_k_party_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const uint32_t *keys, const sc_st *blind, const sc_st *z, pow_tab ztab, int n, int m, int phase);
 void launch_k_bits_sum(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *partial, const uint64_t *vals, const niels_st *G, const niels_st *H, int n, int m);
 void launch_k_msm(dim3 g_, dim3 b_, cudaStream_t s_, msm_args a);
+void launch_k_bm_hist(dim3 g_, dim3 b_, cudaStream_t s_, msm_args a, int scatter);
+void launch_k_bm_scan(dim3 g_, dim3 b_, cudaStream_t s_, msm_args a);
+void launch_k_bm_accum(dim3 g_, dim3 b_, cudaStream_t s_, msm_args a);
+void launch_k_bm_reduce(dim3 g_, dim3 b_, cudaStream_t s_, msm_args a);
 void launch_k_finalize(dim3 g_, dim3 b_, cudaStream_t s_, finalize_args a);
 void launch_k_pow_tables(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *tab, const sc_st *pow2, int L, int H);
 void launch_k_poly(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *l0, sc_st *r0, sc_st *sLR, sc_st *partial, const uint64_t *vals, pow_tab ytab, pow_tab ztab, const sc_st *zpow2, int n, int m);
@@ -1307,6 +1407,43 @@ KLAUNCH(k_rt_catchup, true, (catchup_args a), (a))
 #endif
 void launch_k_ipp_scalars_unf(dim3 g_, dim3 b_, cudaStream_t s_, const sc_st *a, const sc_st *b, const sc_st *yinv, const sc_st *cG, const sc_st *cH, uint32_t cstride, sc_st *msmL, sc_st *msmR, sc_st *partial, size_t N, uint32_t np, uint32_t live);
 void launch_k_rt_catchup(dim3 g_, dim3 b_, cudaStream_t s_, catchup_args a);
+
+
+// catch-up fold WITHOUT generator tables (chunks too large for them): out[c][i] = sum_{t < nblk} coef[t] * Gen[t*nr + i], i < nr, as ONE joint double-and-add
+// per output: the coefficients are the same for every i (and coef[0] = 1), so all lanes follow the same width-3 NAF digit pattern;
+// per base only P and 3P are kept.  252 doublings + ~63 additions per base instead of a 253-step fold ladder per base and level.
+//   nafs[((c*2 + which)*nblk + t)*256 + bit] (k_ts_round, emit 4).  grid (blocks, C, 2): z = 0 -> G, 1 -> H
+#define CATCHUP_MAX_BASES 16
+struct catchup_naf_args { const niels_st *G, *H; p3_st *Gf, *Hf; const int8_t *nafs; uint32_t nr, nblk, stride; };
+#ifdef KG_FOLD
+KERNEL void LB(128, 2) k_catchup_naf(catchup_naf_args a) {
+    __shared__ int8_t naf[CATCHUP_MAX_BASES][256];
+    const int c = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
+    for (uint32_t t = tid; t < a.nblk * 256; t += blockDim.x) naf[t >> 8][t & 255] = a.nafs[(((size_t)c * 2 + which) * a.nblk) * 256 + t];
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + tid;
+    if (i >= a.nr) return;
+    const niels_st *src = which ? a.H : a.G;
+    ge_cached p1[CATCHUP_MAX_BASES], p3[CATCHUP_MAX_BASES];
+    for (uint32_t t = 0; t < a.nblk; t++) {
+        ge_niels n; ld_niels(n, src + (size_t)t * a.nr + i);
+        ge_p3 P, P2, P3; ge_niels_to_p3(P, n); ge_p3_dbl(P2, P); ge_p3_to_cached(p1[t], P); ge_add_cached(P3, P2, p1[t]); ge_p3_to_cached(p3[t], P3);
+    }
+    int top = 255;
+    for (; top > 0; top--) { bool any = false; for (uint32_t t = 0; t < a.nblk; t++) any = any || naf[t][top] != 0; if (any) break; }
+    ge_p3 r; ge_p3_0(r);
+    for (int bit = top; bit >= 0; bit--) {
+        ge_p3_dbl(r, r);
+        for (uint32_t t = 0; t < a.nblk; t++) {
+            const int d = naf[t][bit];
+            if (d != 0) ge_add_cached_signed(r, r, (d == 1 || d == -1) ? p1[t] : p3[t], d < 0);
+        }
+    }
+    st_p3((which ? a.Hf : a.Gf) + (size_t)c * a.stride + i, r);
+}
+KLAUNCH(k_catchup_naf, true, (catchup_naf_args a), (a))
+#endif
+void launch_k_catchup_naf(dim3 g_, dim3 b_, cudaStream_t s_, catchup_naf_args a);
 
 // ===================================================================================================================
 // K6c: FROZEN LEVEL.  After the catch-up the folded generators of a chunk (F = N/16 of G" and of H") stay frozen for the

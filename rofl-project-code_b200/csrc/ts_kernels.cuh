@@ -151,7 +151,7 @@ struct ts_round_args {
     const sc_st *yinvpow2; int lgnp;
     sc_st *u2, *uinv2, *up;                        // [C], [C], [2C] (prod u | prod u^-1)
     sc_st *coefG, *coefH; uint32_t cstride, nblk;  // coefficient tables (nullable): c'[2t] = c[t], c'[2t+1] = c[t] s when 2 nblk <= cstride
-    int emit;                                      // 0 nothing, 1 width-FOLD_W NAFs of (u^2, u^-2 y^-n'), 2 table digits of the coefficients, 3 radix-16 digits of them
+    int emit;                                      // 0 nothing, 1 width-FOLD_W NAFs of (u^2, u^-2 y^-n'), 2 table digits of the coefficients, 3 radix-16 digits of them, 4 width-3 NAFs of them
     uint32_t rtK[9]; int rtc, rtnw;
     int8_t *nafs; int16_t *digs16; int8_t *digs8;
 };
@@ -266,7 +266,8 @@ KERNEL void LB(TS_THREADS, 1) k_ts_round(ts_round_args a) {
             if (a.emit == 2) {
                 uint32_t xk[9]; msm_recode(xk, v, a.rtK); int16_t *d = a.digs16 + (((size_t)c * 2 + which) * nout + i) * RT_MAXW;
                 for (int w = 0; w < a.rtnw; w++) d[w] = (int16_t)msm_digit(xk, w, a.rtc);
-            } else sc_radix16(a.digs8 + (((size_t)c * 2 + which) * nout + i) * 64, v);
+            } else if (a.emit == 3) sc_radix16(a.digs8 + (((size_t)c * 2 + which) * nout + i) * 64, v);
+            else sc_naf(a.nafs + (((size_t)c * 2 + which) * nout + i) * 256, v, 3);
         }
     }
 }

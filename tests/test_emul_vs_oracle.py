@@ -104,10 +104,11 @@ def test_aggregate_and_dlog(api, oracle):
     assert api.dlog(far, 1 << 4, 8, 8, 7)[0] == -5 and oracle.dlog(far, 1 << 4, 8)[0] == -5
 
 
-@pytest.mark.parametrize("c,slices,rt", [(3, 1, 1), (4, 3, 0), (5, 1, 0), (6, 2, 1), (7, 1, 0), (8, 2, 0)])
+@pytest.mark.parametrize("c,slices,rt", [(3, 1, 1), (4, 3, 0), (5, 1, 0), (6, 2, 1), (7, 1, 0), (8, 2, 0), (9, 1, 0), (10, 3, 0), (11, 2, 1)])
 def test_msm_window_widths(api, oracle, monkeypatch, c, slices, rt):
-    """Every window width / slicing of the bucket MSM (k_msm) gives the oracle's bytes; rt=0 also exercises the path without
-    generator tables (generic MSM for S and the verifier, folded IPP from round 0)."""
+    """Every window width / slicing of the bucket MSM (k_msm, c <= 8) and of the wide-window sorted Pippenger (k_bm_*, c >= 9; `slices` = parts per
+    bucket there) gives the oracle's bytes; rt=0 also exercises the path without generator tables (generic MSM for S and the verifier, folded IPP
+    from round 0)."""
     monkeypatch.setenv("ROFL_MSM_C", str(c)); monkeypatch.setenv("ROFL_MSM_SLICES", str(slices))
     api.set_use_rt(rt)
     try:
@@ -451,3 +452,35 @@ def test_server_batch_verification_names_the_offending_client(api, oracle):
         tam = [dict(m) for m in msgs]; tam[1][field] = msgs[1][field].copy(); tam[1][field][idx] ^= 1
         got = api.enc_l2_compressed_verify_batch(tam, vs).tolist()
         assert got[0] == 1 and got[2] == 1 and got[1] in want and got[1] == api.enc_l2_compressed_verify(tam[1], vs), (field, got)
+
+
+@pytest.mark.parametrize("unf,tail_np,frz,D,P", [(1, 0, 0, 8, 2), (2, 2, 1, 16, 2), (3, 0, 1, 16, 1), (4, 4, 0, 32, 2), (4, 1, 1, 64, 1), (2, 32, 1, 6, 4)])
+def test_unfolded_rounds_without_generator_tables(api, oracle, unf, tail_np, frz, D, P):
+    """Chunks too large for generator tables (resnet18-full: 2^21 bit positions per chunk) run their first IPP rounds UNFOLDED as Pippenger MSMs over the
+    original generators (hi / lo halves of the 2np-blocks addressed through the MSM segments) and then catch up with ONE joint double-and-add per folded
+    generator (k_catchup_naf) instead of a fold ladder per round; forced here at tiny sizes: same proof bytes for every schedule."""
+    rng = np.random.default_rng(100 + unf)
+    v = rng.uniform(-0.99, 0.99, D).astype(np.float32); bl = oracle.rnd_scalar_vec(b"\x77" * 32, D); seed = bytes([0x40 + unf]) * 32
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, 8, P, 16, 7, seed); assert rc_o == 0
+    api.set_use_rt(0); api.set_option("nt_unfold_min", 2); api.set_option("nt_unfold", unf); api.set_option("tail_np", tail_np); api.set_option("frozen", frz)
+    try:
+        rc, p, c = api.range_prove(v, bl, 8, P, 16, 7, seed)
+        assert rc == 0 and (c == c_o).all() and (p == p_o).all()
+        assert api.range_verify(p, c, 8, seed) == 1
+    finally:
+        api.set_use_rt(1); api.set_option("nt_unfold_min", 1 << 16); api.set_option("nt_unfold", 4); api.set_option("tail_np", 32); api.set_option("frozen", 1)
+
+
+def test_unfolded_rounds_through_the_wide_window_msm(api, oracle, monkeypatch):
+    """The same schedule with the wide-window sorted Pippenger (k_bm_*) forced for every MSM: mapped segments + bucket sort + fat top window."""
+    monkeypatch.setenv("ROFL_MSM_C", "9"); monkeypatch.setenv("ROFL_MSM_SLICES", "2")
+    rng = np.random.default_rng(111)
+    D, P = 32, 2
+    v = rng.uniform(-0.99, 0.99, D).astype(np.float32); bl = oracle.rnd_scalar_vec(b"\x78" * 32, D); seed = b"\x79" * 32
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, 8, P, 16, 7, seed); assert rc_o == 0
+    api.set_use_rt(0); api.set_option("nt_unfold_min", 2); api.set_option("nt_unfold", 3)
+    try:
+        rc, p, c = api.range_prove(v, bl, 8, P, 16, 7, seed)
+        assert rc == 0 and (c == c_o).all() and (p == p_o).all() and api.range_verify(p, c, 8, seed) == 1
+    finally:
+        api.set_use_rt(1); api.set_option("nt_unfold_min", 1 << 16); api.set_option("nt_unfold", 4)
