@@ -485,17 +485,26 @@ KERNEL void LB(128, 2) k_bm_reduce(msm_args a) {
     const uint32_t B = 1u << (a.c - 1), tid = threadIdx.x, w = blockIdx.x, msm = blockIdx.y;
     const bool fat = a.parts_top && w == (uint32_t)a.nw - 1;
     const uint32_t np = fat ? a.parts_top : a.parts, nb = fat ? (2u << a.top_bits) : B;          // buckets that can be non-empty
-    const uint32_t per = (nb + 127) / 128, lo = tid * per, hi = lo + per < nb ? lo + per : nb;
     const p3_st *bk = a.bm_bkt + ((size_t)msm * a.nw + w) * B * a.parts;
     ge_p3 run, acc; ge_p3_0(run); ge_p3_0(acc);
-    for (uint32_t b = hi; b-- > lo;) {
-        for (uint32_t p = 0; p < np; p++) acc_add_p3(run, bk + (size_t)b * np + p, false);
-        ge_add(acc, acc, run);
-    }
-    if (lo > 0 && lo < hi) {                       // + lo * run
-        ge_p3 m; ge_p3_0(m);
-        for (int bit = 15; bit >= 0; bit--) { ge_p3_dbl(m, m); if ((lo >> bit) & 1) ge_add(m, m, run); }
-        ge_add(acc, acc, m);
+    if (nb < 128) {
+        // few, heavily split buckets (fat top window): 128 / nb threads share a bucket's partial sums, then weight their share with (b + 1)
+        const uint32_t tpb = 128 / nb, b = tid / tpb, lane = tid % tpb;
+        if (b < nb) {
+            for (uint32_t p = lane; p < np; p += tpb) acc_add_p3(run, bk + (size_t)b * np + p, false);
+            for (int bit = 15; bit >= 0; bit--) { ge_p3_dbl(acc, acc); if (((b + 1) >> bit) & 1) ge_add(acc, acc, run); }
+        }
+    } else {
+        const uint32_t per = (nb + 127) / 128, lo = tid * per, hi = lo + per < nb ? lo + per : nb;
+        for (uint32_t b = hi; b-- > lo;) {
+            for (uint32_t p = 0; p < np; p++) acc_add_p3(run, bk + (size_t)b * np + p, false);
+            ge_add(acc, acc, run);
+        }
+        if (lo > 0 && lo < hi) {                       // + lo * run
+            ge_p3 m; ge_p3_0(m);
+            for (int bit = 15; bit >= 0; bit--) { ge_p3_dbl(m, m); if ((lo >> bit) & 1) ge_add(m, m, run); }
+            ge_add(acc, acc, m);
+        }
     }
     block_sum_p3(acc, buf, (int)tid, 128);
     if (tid == 0) st_p3(a.out + (size_t)msm * a.nw + w, acc);
