@@ -319,11 +319,14 @@ class Api:
         rc = self.lib.rofl_range_verify(self.h, _ptr(p), p.shape[1], p.shape[0], _ptr(c), c.shape[0], rng, _ptr(_seed(seed)))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc
-    def range_prove_shard(self, v, blind, chunk_len, chunk_begin, n_chunks, rng, n_bits, frac, seed=None):
-        """Chunks [chunk_begin, chunk_begin + n_chunks) of a larger update; v / blind hold the real elements of that slice."""
+    def range_prove_shard(self, v, blind, chunk_len, chunk_begin, n_chunks, rng, n_bits, frac, seed=None, out_commits=None):
+        """Chunks [chunk_begin, chunk_begin + n_chunks) of a larger update; v / blind hold the real elements of that slice.  out_commits: optional
+        caller-owned uint8 [D, 32] buffer (e.g. a view of pinned memory) the commitments are written to."""
         v = _f32(v); D = v.size; b = _u8(blind, 32 * D)
         plen = self.range_proof_len(rng * chunk_len)
-        proofs = np.zeros((n_chunks, plen), np.uint8); commits = np.zeros((D, 32), np.uint8); a = c_sz()
+        proofs = np.zeros((n_chunks, plen), np.uint8); a = c_sz()
+        commits = np.zeros((D, 32), np.uint8) if out_commits is None else out_commits
+        assert commits.dtype == np.uint8 and commits.shape == (D, 32) and commits.flags["C_CONTIGUOUS"]
         rc = self.lib.rofl_range_prove_shard(self.h, _ptr(v), _ptr(b), D, chunk_len, chunk_begin, n_chunks, rng, n_bits, frac, _ptr(_seed(seed)), _ptr(proofs), C.byref(a), _ptr(commits))
         if rc <= ROFL_ERR_CUDA: raise self._err(rc)
         return rc, proofs, commits

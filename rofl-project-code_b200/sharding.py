@@ -50,18 +50,43 @@ def _all_gather_bytes(dist, group, arr, device):
     return [o[:int(k.item())].cpu().numpy() for o, k in zip(outs, ns)]
 
 
+_PINNED = {}
+
+
+def _pinned(name, nbytes):
+    """A cached pinned host buffer (torch) of at least nbytes: host<->device copies of the gathered commitments run at full PCIe / NVLink-C2C speed."""
+    import torch
+    t = _PINNED.get(name)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1), dtype=torch.uint8)
+        try:
+            t = t.pin_memory()
+        except Exception:  # noqa: BLE001  (no CUDA: the gloo tests)
+            pass
+        _PINNED[name] = t
+    return t[:nbytes]
+
+
 def prove_range_sharded(api, values, blind, range_bits, n_partition, n_bits, frac, seed, dist=None, group=None, device="cpu"):
     """create_rangeproof of ONE update over all ranks of `group`.  Every rank holds the full update (or at least its slice) and
-    returns (rc, proofs[C, plen], commits[D, 32]) identical on all ranks and byte-identical to the single-GPU call."""
+    returns (rc, proofs[C, plen], commits[D, 32]) identical on all ranks and byte-identical to the single-GPU call.
+    The gather moves every rank's chunk range as ONE equal-sized block (its padding rows are zero = the identity encoding the reference pads with,
+    range_proof_vec/mod.rs:163-165), so the result lands in its final layout: pinned buffer -> device -> all_gather_into_tensor -> pinned buffer."""
     values = np.ascontiguousarray(values, np.float32); D = values.size
     blind = np.ascontiguousarray(blind, np.uint8).reshape(D, 32)
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist is not None else (0, 1)
     sh = shard_of(D, n_partition, rank, world)
     e0, e1 = sh["elem_begin"], sh["elem_end"]
-    err = None
+    Dp, C, m = chunk_layout(D, n_partition)
+    equal = world > 1 and C % world == 0              # every rank owns the same number of chunks: one fixed-size block per rank
+    err, out_c = None, None
+    if equal:
+        rows = sh["n_chunks"] * m
+        blk = _pinned("commit_block", rows * 32); blk.zero_()
+        out_c = blk.numpy().reshape(rows, 32)[:e1 - e0]
     try:
         if sh["n_chunks"]:
-            rc, proofs, commits = api.range_prove_shard(values[e0:e1], blind[e0:e1], sh["chunk_len"], sh["chunk_begin"], sh["n_chunks"], range_bits, n_bits, frac, seed)
+            rc, proofs, commits = api.range_prove_shard(values[e0:e1], blind[e0:e1], sh["chunk_len"], sh["chunk_begin"], sh["n_chunks"], range_bits, n_bits, frac, seed, out_commits=out_c)
         else:
             rc, proofs, commits = 0, np.zeros((0, 0), np.uint8), np.zeros((0, 32), np.uint8)
     except Exception as ex:  # noqa: BLE001  (a CUDA error on one rank must not leave the others hanging in the collective below)
@@ -80,8 +105,17 @@ def prove_range_sharded(api, values, blind, range_bits, n_partition, n_bits, fra
         return (int(lo.item()) if int(lo.item()) < 0 else int(hi.item())), None, None
     plen = api.range_proof_len(range_bits * sh["chunk_len"])
     parts_p = _all_gather_bytes(dist, group, proofs, device)
-    parts_c = _all_gather_bytes(dist, group, commits, device)
     all_p = np.concatenate([p.reshape(-1, plen) for p in parts_p if p.size], axis=0)
+    if equal:
+        src = blk.to(device, non_blocking=True)
+        out = torch.empty(Dp * 32, dtype=torch.uint8, device=device)
+        if hasattr(dist, "all_gather_into_tensor") and str(device) != "cpu":
+            dist.all_gather_into_tensor(out, src, group=group)
+        else:
+            dist.all_gather(list(out.chunk(world)), src, group=group)
+        host = _pinned("commit_all", Dp * 32); host.copy_(out)
+        return 0, all_p, host.numpy().reshape(Dp, 32)[:D]
+    parts_c = _all_gather_bytes(dist, group, commits, device)
     all_c = np.concatenate([c.reshape(-1, 32) for c in parts_c if c.size], axis=0)
     return 0, all_p, all_c
 
