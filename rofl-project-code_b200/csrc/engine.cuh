@@ -82,11 +82,12 @@ static inline lane *lane_new() {
     // the short kernels of every group's Fiat-Shamir chain run at the greatest priority, the bulk kernels one level below.  (ROFL_PRIO_ORDERED=1
     // orders the bulk streams of the groups as well -- group 0 races ahead so that its latency-bound last rounds run under the bulk kernels of
     // the groups behind it; measured on B200 it is 3 ms SLOWER per proof than equal priorities: the last group ends up alone.  DESIGN.md section 3)
-    static const int ordered = getenv("ROFL_PRIO_ORDERED") ? atoi(getenv("ROFL_PRIO_ORDERED")) : 0, flat = getenv("ROFL_PRIO_FLAT") != nullptr;
-    for (int g = 0; g < ROFL_MAX_GROUPS; g++) { cudaStream_t hi = rt_stream_create(flat ? 1 : 0), lo = rt_stream_create(ordered ? 1 + g : 1); l->q[g] = chain(hi, lo); l->side[g] = rt_stream_create(0); }
+    static const int ordered = getenv("ROFL_PRIO_ORDERED") ? atoi(getenv("ROFL_PRIO_ORDERED")) : 0, flat = getenv("ROFL_PRIO_FLAT") ? atoi(getenv("ROFL_PRIO_FLAT")) : 0;
+    static const int own_side = getenv("ROFL_SIDE") ? atoi(getenv("ROFL_SIDE")) : 1;
+    for (int g = 0; g < ROFL_MAX_GROUPS; g++) { cudaStream_t hi = rt_stream_create(flat ? 1 : 0), lo = rt_stream_create(ordered ? 1 + g : 1); l->q[g] = chain(hi, lo); l->side[g] = own_side ? rt_stream_create(0) : hi; }
     return l;
 }
-static inline void lane_delete(lane *l) { for (int g = 0; g < ROFL_MAX_GROUPS; g++) { rt_stream_destroy(l->q[g].hi); if (l->q[g].lo != l->q[g].hi) rt_stream_destroy(l->q[g].lo); rt_stream_destroy(l->side[g]); } delete l; }
+static inline void lane_delete(lane *l) { for (int g = 0; g < ROFL_MAX_GROUPS; g++) { rt_stream_destroy(l->q[g].hi); if (l->q[g].lo != l->q[g].hi) rt_stream_destroy(l->q[g].lo); if (l->side[g] != l->q[g].hi) rt_stream_destroy(l->side[g]); } delete l; }
 // the calling thread's lane for the duration of an API call (nested engine calls of the same thread share it)
 struct lane_guard {
     rofl_engine &e; lane *ln = nullptr;
@@ -104,6 +105,7 @@ struct lane_guard {
     }
     ~lane_guard() {
         if (--tl_lane_depth > 0) return;
+        rt_d2h_finish();
         { std::lock_guard<std::mutex> lk(e.lane_mu); ln->busy = false; }
         e.lane_cv.notify_one(); tl_lane = nullptr; tl_lane_engine = nullptr;
     }

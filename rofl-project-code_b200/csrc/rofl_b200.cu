@@ -15,14 +15,16 @@ static std::atomic<long> g_launches{0};
 
 void rt_count_launch(const char *) { g_launches++; }
 // ---- ROFL_TIMELINE=1: start / end of every kernel on its stream (events), relative to the first launch after the last dump
-struct tl_rec { const char *name; cudaStream_t s; unsigned blocks; cudaEvent_t a, b; };
+struct tl_rec { const char *name; cudaStream_t s; unsigned blocks; cudaEvent_t a, b; double host_ms; };
+static double g_tl_host0 = 0;
+static inline double tl_now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 static std::mutex g_tl_mu; static std::vector<tl_rec *> g_tl; static cudaEvent_t g_tl_base = nullptr;
 static const bool g_tl_on = getenv("ROFL_TIMELINE") != nullptr;
 void *rt_timeline_begin(const char *name, cudaStream_t s, unsigned blocks) {
     if (!g_tl_on) return nullptr;
-    tl_rec *r = new tl_rec{name, s, blocks, nullptr, nullptr};
+    tl_rec *r = new tl_rec{name, s, blocks, nullptr, nullptr, tl_now_ms()};
     cudaEventCreate(&r->a); cudaEventCreate(&r->b);
-    { std::lock_guard<std::mutex> lk(g_tl_mu); if (!g_tl_base) { cudaEventCreate(&g_tl_base); cudaEventRecord(g_tl_base, s); } g_tl.push_back(r); }
+    { std::lock_guard<std::mutex> lk(g_tl_mu); if (!g_tl_base) { cudaEventCreate(&g_tl_base); cudaEventRecord(g_tl_base, s); g_tl_host0 = r->host_ms; } g_tl.push_back(r); }
     cudaEventRecord(r->a, s);
     return r;
 }
@@ -32,8 +34,8 @@ extern "C" void rofl_timeline_dump(const char *path) {
     cudaDeviceSynchronize();
     std::lock_guard<std::mutex> lk(g_tl_mu);
     FILE *f = fopen(path, "a"); if (!f) return;
-    fprintf(f, "# name stream blocks start_ms end_ms\n");
-    for (tl_rec *r : g_tl) { float t0 = 0, t1 = 0; cudaEventElapsedTime(&t0, g_tl_base, r->a); cudaEventElapsedTime(&t1, g_tl_base, r->b); fprintf(f, "%s %p %u %.3f %.3f\n", r->name, (void *)r->s, r->blocks, t0, t1); cudaEventDestroy(r->a); cudaEventDestroy(r->b); delete r; }
+    fprintf(f, "# name stream blocks start_ms end_ms host_enqueue_ms\n");
+    for (tl_rec *r : g_tl) { float t0 = 0, t1 = 0; cudaEventElapsedTime(&t0, g_tl_base, r->a); cudaEventElapsedTime(&t1, g_tl_base, r->b); fprintf(f, "%s %p %u %.3f %.3f %.3f\n", r->name, (void *)r->s, r->blocks, t0, t1, r->host_ms - g_tl_host0); cudaEventDestroy(r->a); cudaEventDestroy(r->b); delete r; }
     g_tl.clear(); if (g_tl_base) { cudaEventDestroy(g_tl_base); g_tl_base = nullptr; }
     fclose(f);
 }

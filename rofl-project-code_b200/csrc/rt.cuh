@@ -7,6 +7,7 @@
 #include <mutex>
 #include <cstdlib>
 #include <cstdio>
+#include <cstring>
 // Diagnostic (ROFL_HOSTPROF=1): where a proof's HOST time goes -- stream waits, kernel launches, copies, allocation -- per calling
 // thread; prove_chunks prints one line per call.
 #include <chrono>
@@ -26,7 +27,8 @@ struct rt_host_timer {
     }
     ~rt_host_timer() {
         if (!slot) return;
-        auto t1 = std::chrono::steady_clock::now(); *slot += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        auto t1 = std::chrono::steady_clock::now(); const double dt = std::chrono::duration<double, std::milli>(t1 - t0).count(); *slot += dt;
+        if (dt > 1.0 && slot != &rt_hostprof().sync && slot != &rt_hostprof().par && slot != &rt_hostprof().ser) fprintf(stderr, "[rofl long] %.2f ms inside %s (call #%d)\n", dt, label, rt_hostgap().ordinal);
         rt_host_gap &g = rt_hostgap(); g.last_end = t1; g.last_label = label;
     }
 };
@@ -40,6 +42,7 @@ inline void rt_d2h(void *h, const void *d, size_t n, cudaStream_t) { memcpy(h, d
 inline void rt_d2d(void *d, const void *s, size_t n, cudaStream_t) { memcpy(d, s, n); }
 inline void rt_memset(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); }
 inline void rt_sync(cudaStream_t) {}
+inline void rt_d2h_finish() {}
 inline size_t rt_free_mem() { return (size_t)8 << 30; }
 inline void rt_stream_after(cudaStream_t, cudaStream_t) {}
 inline cudaStream_t rt_stream_create(int) { return nullptr; }
@@ -128,7 +131,44 @@ inline rt_big_cache &rt_bigs() { static rt_big_cache c; return c; }
 inline void *rt_malloc(size_t n, cudaStream_t s) { rt_host_timer t(&rt_host_prof::alloc, "rt_malloc"); return rt_bigs().take(n, s); }
 inline void rt_free(void *p, cudaStream_t s) { rt_host_timer t(&rt_host_prof::alloc, "rt_free"); if (p && !rt_bigs().give(p, s)) cudaFreeAsync(p, s); }
 inline void rt_h2d(void *d, const void *h, size_t n, cudaStream_t s) { rt_host_timer t(&rt_host_prof::copy, "h2d"); rt_check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s), "h2d"); }
-inline void rt_d2h(void *h, const void *d, size_t n, cudaStream_t s) { rt_host_timer t(&rt_host_prof::copy, "d2h"); rt_check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "d2h"); }
+// Device -> host results.  cudaMemcpyAsync into PAGEABLE memory blocks the calling thread until the stream gets there -- and, measured on
+// B200 (driver 580), it does so holding a driver lock: while one chunk group's thread sat in the copy of its finished proofs, the other
+// groups' threads were stuck inside cudaLaunchKernel / cudaMalloc / cudaEventQuery, their last kernels reached the GPU only when the first
+// group's had finished, and one proof in three took 44 ms instead of 38 (profiles/r02_scheduling.md).  So results always land in a pinned
+// staging block first (or directly in the caller's buffer when that is pinned) and are handed over by the rt_sync() of that stream.
+struct rt_pin_pool {
+    std::mutex mu; std::vector<std::pair<void *, size_t>> free_;
+    void *take(size_t n, size_t &cap) {
+        { std::lock_guard<std::mutex> lk(mu);
+          size_t best = free_.size();
+          for (size_t i = 0; i < free_.size(); i++) if (free_[i].second >= n && (best == free_.size() || free_[i].second < free_[best].second)) best = i;
+          if (best < free_.size() && free_[best].second <= 4 * n + 4096) { void *p = free_[best].first; cap = free_[best].second; free_.erase(free_.begin() + best); return p; } }
+        cap = n < 4096 ? 4096 : (n + 4095) / 4096 * 4096;
+        void *p = nullptr; rt_check(cudaHostAlloc(&p, cap, cudaHostAllocPortable), "cudaHostAlloc"); return p;
+    }
+    void give(void *p, size_t cap) { std::lock_guard<std::mutex> lk(mu); free_.emplace_back(p, cap); }
+};
+inline rt_pin_pool &rt_pins() { static rt_pin_pool p; return p; }
+struct rt_pending_d2h { cudaStream_t s; void *h, *stage; size_t n, cap; };
+inline std::vector<rt_pending_d2h> &rt_pending() { static thread_local std::vector<rt_pending_d2h> v; return v; }
+inline bool rt_host_is_pinned(const void *h) { cudaPointerAttributes a; if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { cudaGetLastError(); return false; } return a.type == cudaMemoryTypeHost; }
+inline void rt_d2h(void *h, const void *d, size_t n, cudaStream_t s) {
+    rt_host_timer t(&rt_host_prof::copy, "d2h");
+    if (!n) return;
+    if (n >= 65536 && rt_host_is_pinned(h)) { rt_check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s), "d2h"); return; }
+    size_t cap = 0; void *st = rt_pins().take(n, cap);
+    rt_check(cudaMemcpyAsync(st, d, n, cudaMemcpyDeviceToHost, s), "d2h");
+    rt_pending().push_back({s, h, st, n, cap});
+}
+// hand over the staged results of stream s (all streams: s == nullptr && all) -- the caller has just synchronised it
+inline void rt_d2h_deliver(cudaStream_t s, bool all = false) {
+    auto &v = rt_pending();
+    for (size_t i = 0; i < v.size();) {
+        if (all || v[i].s == s) { memcpy(v[i].h, v[i].stage, v[i].n); rt_pins().give(v[i].stage, v[i].cap); v.erase(v.begin() + i); } else i++;
+    }
+}
+// end of an API call: nothing may stay staged (a result copy without a matching rt_sync would otherwise be lost silently)
+inline void rt_d2h_finish() { auto &v = rt_pending(); if (v.empty()) return; for (auto &p : v) cudaStreamSynchronize(p.s); rt_d2h_deliver(nullptr, true); }
 inline void rt_d2d(void *d, const void *s_, size_t n, cudaStream_t s) { rt_check(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s), "d2d"); }
 inline void rt_memset(void *d, int v, size_t n, cudaStream_t s) { rt_check(cudaMemsetAsync(d, v, n, s), "memset"); }
 // Stream wait.  ROFL_SYNC=spin polls cudaStreamQuery instead (a proof has ~20 host round trips; measured on B200: no gain over the
@@ -136,10 +176,10 @@ inline void rt_memset(void *d, int v, size_t n, cudaStream_t s) { rt_check(cudaM
 inline void rt_sync(cudaStream_t s) {
     rt_host_timer t(&rt_host_prof::sync, "sync");
     static const int spin = [] { const char *m = getenv("ROFL_SYNC"); return m && m[0] == 's' ? 1 : 0; }();
-    if (!spin) { rt_check(cudaStreamSynchronize(s), "sync"); return; }
+    if (!spin) { rt_check(cudaStreamSynchronize(s), "sync"); rt_d2h_deliver(s); return; }
     for (;;) {
         cudaError_t e = cudaStreamQuery(s);
-        if (e == cudaSuccess) return;
+        if (e == cudaSuccess) { rt_d2h_deliver(s); return; }
         if (e != cudaErrorNotReady) rt_check(e, "sync");
 #if defined(__x86_64__)
         __builtin_ia32_pause();

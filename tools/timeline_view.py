@@ -4,7 +4,7 @@ import sys, collections
 rows = []
 for l in open(sys.argv[1]):
     if l.startswith("#") or not l.strip(): continue
-    n, s, b, t0, t1 = l.split(); rows.append((n, s, int(b), float(t0), float(t1)))
+    f = l.split(); n, s, b, t0, t1 = f[:5]; rows.append((n, s, int(b), float(t0), float(t1), float(f[5]) if len(f) > 5 else float("nan")))
 streams = collections.OrderedDict()
 for r in sorted(rows, key=lambda r: r[3]): streams.setdefault(r[1], []).append(r)
 end = max(r[4] for r in rows); start = min(r[3] for r in rows)
@@ -15,4 +15,4 @@ for i, (s, rs) in enumerate(streams.items()):
 if len(sys.argv) > 2:
     sid = {s: i for i, s in enumerate(streams)}
     for r in sorted(rows, key=lambda r: r[3]):
-        print("%8.3f %8.3f  s%-2d %-22s blocks %-6d dur %.3f" % (r[3], r[4], sid[r[1]], r[0], r[2], r[4] - r[3]))
+        print("%8.3f %8.3f  s%-2d %-22s blocks %-6d dur %.3f  enq %.3f" % (r[3], r[4], sid[r[1]], r[0], r[2], r[4] - r[3], r[5]))
