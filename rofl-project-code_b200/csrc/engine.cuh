@@ -478,7 +478,7 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
     dev_buf d_x(sizeof(sc_st) * C, q), d_w2(sizeof(sc_st) * 2 * C, q), d_yinv(sizeof(sc_st) * NT, q);
     { ts_x_args xa = {}; xa.ts = d_ts.as<transcript>(); xa.T12 = d_T12.as<uint8_t>(); xa.proofs = d_proofs.as<uint8_t>(); xa.plen = (uint32_t)plen; xa.C = (uint32_t)C;
       xa.tsum = d_tsum.as<sc_st>(); xa.sums = d_sums.as<sc_st>(); xa.x = d_x.as<sc_st>(); xa.w2 = d_w2.as<sc_st>(); xa.N = (uint64_t)N;
-      LAUNCH(k_ts_x, dim3((unsigned)((C + TS_THREADS - 1) / TS_THREADS)), dim3(TS_THREADS), q.small(), xa); }
+      LAUNCH_COOP(k_ts_x, dim3(C), dim3(TS_THREADS), q.small(), xa); }
     LAUNCH(k_lr, dim3((unsigned)((NT + 255) / 256)), dim3(256), q.big(), d_a.as<sc_st>(), d_b.as<sc_st>(), d_sLR.as<sc_st>(), d_yinv.as<sc_st>(), d_x.as<sc_st>(), yitab, N, NT);
     tr.mark("pre_ipp");
     // ---- inner product argument
@@ -779,7 +779,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, in
     absorb_commitments(e, s, d_ts.as<transcript>(), d_V32, label_id, n, m, C);
     { ts_verify_args va = {}; va.ts = d_ts.as<transcript>(); va.proofs = d_proofs.as<uint8_t>(); va.plen = (uint32_t)plen; va.C = (uint32_t)C; va.lgN = lgN; va.N = (uint64_t)N;
       va.chal = d_vch.as<sc_st>(); va.digest = d_digest.as<uint8_t>(); va.bad = d_bad.as<int>(); va.sp32 = d_sp32.as<uint8_t>(); memcpy(va.B32, e.sh->B32, 32); memcpy(va.H32, e.sh->H32, 32);
-      LAUNCH(k_ts_verify, dim3((unsigned)((C + TS_THREADS - 1) / TS_THREADS)), dim3(TS_THREADS), s, va); }
+      LAUNCH_COOP(k_ts_verify, dim3((unsigned)C), dim3(TS_THREADS), s, va); }
     { verify_keys_args ka = {}; ka.digest = d_digest.as<uint8_t>(); ka.C = (uint32_t)C; ka.dom = dom; ka.c_off = c_off; memcpy(ka.seed, seed, 32); ka.ccrho = d_ccrho.as<sc_st>();
       LAUNCH_COOP(k_verify_keys, dim3(1), dim3(256), s, ka); }
     { verify_prep_args pa = {}; pa.proofs = d_proofs.as<uint8_t>(); pa.plen = (uint32_t)plen; pa.C = (uint32_t)C; pa.lgN = lgN; pa.lgm = lgm; pa.n = n; pa.vch = d_vch.as<sc_st>(); pa.ccrho = d_ccrho.as<sc_st>();
@@ -790,27 +790,28 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, in
     LAUNCH_COOP(k_verify_scalars, dim3((unsigned)((N + 63) / 64)), dim3(256), s, d_gh.as<sc_st>(), d_tab.as<sc_st>(), vt, d_chal.as<sc_st>(), chs, n, C);
     LAUNCH(k_decompress, dim3((unsigned)(((size_t)C * nsmall + 127) / 128)), dim3(128), s, d_sp.as<p3_st>(), (uint8_t *)nullptr, d_sp32.as<uint8_t>(), (size_t)C * nsmall, (size_t)C * nsmall, (const p3_st *)nullptr, d_bad.as<int>(), (size_t)nsmall);
     tr.mark("v_scalar_kernels");
-    // fixed generators: one 2N-term MSM (radix-256 tables when they exist, bucket MSM otherwise) -> d_fix
+    // fixed generators: one 2N-term MSM (radix-2^c tables when they exist, bucket MSM otherwise) -> d_fix.  It runs on the lane's side stream,
+    // beside the MSM over the commitments and proof points below (both need only the scalars); the last finalize joins them.
+    cudaStream_t side = (tl_lane && tl_lane_engine == &e && tl_lane->q[0].hi == s) ? tl_lane->side[0] : s;
+    rt_stream_after(side, s);
+    const int nbV = rt ? rt_blocks(2 * N, 1) : 0;
+    const msm_plan plF = rt ? msm_plan() : msm_plan_for(2 * N, 1);
+    dev_buf d_partV(rt ? sizeof(p3_st) * (size_t)nbV : 16, s), d_winF(rt ? 16 : sizeof(p3_st) * plF.out_count(1), s);
     {
         finalize_args f = {}; f.tabB = e.sh->tabB; f.tabH = e.sh->tabH; f.out_p3 = d_fix.as<p3_st>(); f.count = 1;
         if (rt) {
-            const int nbV = rt_blocks(2 * N, 1);
-            dev_buf d_partV(sizeof(p3_st) * (size_t)nbV, s);
             rt_msm_args ra = {}; ra.scalars = d_gh.as<sc_st>(); ra.T = (uint32_t)(2 * N); ra.scalar_stride = (uint32_t)(2 * N); ra.nG = (uint32_t)N; ra.mode = 0; ra.rt = *rt; ra.partial = d_partV.as<p3_st>();
-            run_rt_msm(e, s, ra, nbV, 1);
+            run_rt_msm(e, side, ra, nbV, 1);
             f.partial = d_partV.as<p3_st>(); f.npartial = nbV;
-            run_finalize(s, f);
+            run_finalize(side, f);
         } else {
-            const msm_plan pl = msm_plan_for(2 * N, 1);
-            dev_buf d_winF(sizeof(p3_st) * pl.out_count(1), s);
             msm_args a = {}; a.v[0].scalars = d_gh.as<sc_st>(); a.split = 1; a.T = (uint32_t)(2 * N); a.scalar_stride = (uint32_t)(2 * N); a.nseg = 2; a.out = d_winF.as<p3_st>();
             a.v[0].seg[0] = mk_seg(g.G, (uint32_t)N, 0, 0); a.v[0].seg[1] = mk_seg(g.H, (uint32_t)N, 0, 0);
-            run_msm(e, s, a, pl, 1);
-            fin_windows(f, d_winF.as<p3_st>(), pl);
-            run_finalize(s, f);
+            run_msm(e, side, a, plF, 1);
+            fin_windows(f, d_winF.as<p3_st>(), plF);
+            run_finalize(side, f);
         }
     }
-    tr.mark("v_gen_msm");
     // commitments and proof points of ALL chunks: one sliced MSM over C*m + C*nsmall terms (scalars laid out the same way)
     {
         const uint32_t TV = (uint32_t)((size_t)C * m + (size_t)C * nsmall);
@@ -819,6 +820,8 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, in
         msm_args a = {}; a.v[0].scalars = d_var.as<sc_st>(); a.split = 1; a.T = TV; a.scalar_stride = TV; a.nseg = 2; a.out = d_winV.as<p3_st>();
         a.v[0].seg[0] = mk_seg(d_Vp3, (uint32_t)((size_t)C * m), 0, 1); a.v[0].seg[1] = mk_seg(d_sp.p, (uint32_t)((size_t)C * nsmall), 0, 1);
         run_msm(e, s, a, pl, 1);
+        rt_stream_after(s, side);
+        tr.mark("v_msms");
         finalize_args f = {}; fin_windows(f, d_winV.as<p3_st>(), pl);
         f.partial = d_fix.as<p3_st>(); f.npartial = 1; f.tabB = e.sh->tabB; f.tabH = e.sh->tabH; f.is_id = d_id.as<int>(); f.count = 1;
         run_finalize(s, f);
@@ -828,7 +831,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, in
     if (d_xbad) rt_d2h(h_xbad, d_xbad, sizeof(int) * nx, s);
     if (h_weights) rt_d2h(h_weights, d_ccrho.p, sizeof(sc_st) * 2 * (size_t)C, s);
     rt_sync(s);
-    tr.mark("v_var_msm");
+    tr.mark("v_final");
     int all_ok = h_id;
     for (int c = 0; c < C; c++) all_ok &= h_bad[c] ? 0 : 1;
     for (int c = 0; c < C; c++) verdict[c] = all_ok;

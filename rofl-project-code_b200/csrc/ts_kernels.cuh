@@ -27,9 +27,15 @@ HASH_CONST uint8_t KC_SRC_[25] = {0, 6, 12, 18, 24, 3, 9, 10, 16, 22, 1, 7, 13, 
 HASH_CONST uint8_t KC_ROT_[25] = {0, 44, 43, 21, 14, 28, 20, 3, 45, 61, 1, 6, 25, 8, 18, 27, 36, 10, 15, 56, 62, 55, 39, 41, 2};
 
 // STROBE state of one transcript in shared memory while a warp works on it
-struct strobe_sh { uint64_t st[25]; uint64_t C[5]; uint64_t B[25]; uint32_t pos, pos_begin; };
+#ifdef ROFL_EMUL
+struct strobe_sh { uint64_t st[25]; uint64_t C[5]; uint64_t B[25]; uint32_t pos, pos_begin, cur_flags; uint8_t io[64]; };
+#else
+#define TS_RING 2048                   // bytes of absorb stream composed ahead in shared memory (ring, indexed by absolute stream position)
+struct strobe_sh { uint64_t st[25]; uint32_t pos, pos_begin, cur_flags; uint8_t io[64]; uint64_t ring[TS_RING / 8]; };
+#endif
 
 #ifdef KG_TS
+#ifdef ROFL_EMUL
 // Keccak-f[1600], lane t < 25 owns word t; every lane of the warp must call
 DEV void keccak_coop(strobe_sh &h, int lane) {
     const int x = lane % 5, row = lane - x;
@@ -51,15 +57,142 @@ DEV void keccak_coop(strobe_sh &h, int lane) {
         TS_WSYNC();
     }
 }
+#else
+// Keccak-f[1600] over a warp: lane t < 25 holds word t = A[x, y] (t = x + 5 y) in a register; every lane of the warp must call.  Per round 9
+// 64-bit shuffles in THREE dependent steps: (1) the four other words of the column (-> column parity c, known to every lane of the column)
+// together with the word rho+pi will move here; (2) the parities of the two neighbour columns OF THAT SOURCE word; (3) the two chi operands.
+DEV uint64_t keccak_shfl(uint64_t a, int lane) {
+    const int x = lane % 5, row = lane - x;
+    const int src = lane < 25 ? KC_SRC_[lane] : 0, rot = lane < 25 ? KC_ROT_[lane] : 0, sx = src % 5;
+    const int l5 = (lane + 5) % 25, l10 = (lane + 10) % 25, l15 = (lane + 15) % 25, l20 = (lane + 20) % 25;
+    const int dm = (sx + 4) % 5, dp = (sx + 1) % 5, c1 = row + (x + 1) % 5, c2 = row + (x + 2) % 5;
+    auto sh64 = [](uint64_t v, int from) { const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, from), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), from); return ((uint64_t)hi << 32) | lo; };
+#pragma unroll 1
+    for (int r = 0; r < 24; r++) {
+        const uint64_t p1 = sh64(a, l5), p2 = sh64(a, l10), p3 = sh64(a, l15), p4 = sh64(a, l20), as = sh64(a, src);
+        const uint64_t c = a ^ p1 ^ p2 ^ p3 ^ p4;                                     // parity of column x (lanes 0..4 hold columns 0..4)
+        const uint64_t cm = sh64(c, dm), cp = sh64(c, dp);
+        uint64_t b = as ^ cm ^ ((cp << 1) | (cp >> 63));                              // theta applied to the source word
+        b = (b << rot) | (b >> ((64 - rot) & 63));                                    // rho (pi is the choice of src)
+        const uint64_t b1 = sh64(b, c1), b2 = sh64(b, c2);
+        a = b ^ (~b1 & b2);                                                           // chi
+        if (lane == 0) a ^= KECCAK_RC_[r];                                            // iota
+    }
+    return a;
+}
+#endif
+// ---- STROBE / Merlin operations carried out by a whole warp on a state in shared memory -----------------------------------------------
+// The 200 state bytes live in strobe_sh::st, the lanes XOR / read message bytes side by side (one byte per lane), the permutation is the warp
+// one above (a lone lane running keccak_f1600 on a state in local memory needs 8-15 us per permutation, the warp 2 us).  Control flow is
+// uniform: EVERY lane of the warp calls these with the same arguments; `d` must be readable by all lanes (or hold the same bytes in each).
+struct wts { uint32_t pos, pos_begin, cur_flags; };                                  // warp-uniform registers
+DEV void wt_permute(strobe_sh &h, int lane) {
+#ifdef ROFL_EMUL
+    keccak_coop(h, lane);
+#else
+    __syncwarp();
+    uint64_t a = lane < 25 ? h.st[lane] : 0;
+    a = keccak_shfl(a, lane);
+    if (lane < 25) h.st[lane] = a;
+    __syncwarp();
+#endif
+}
+DEV void wt_run_f(strobe_sh &h, wts &w, int lane) {
+    TS_WSYNC();
+    if (lane == 0) { uint8_t *st8 = (uint8_t *)h.st; st8[w.pos] ^= (uint8_t)w.pos_begin; st8[w.pos + 1] ^= 0x04; st8[STROBE_R + 1] ^= 0x80; }
+    TS_WSYNC();
+    wt_permute(h, lane);
+    w.pos = 0; w.pos_begin = 0;
+}
+DEV void wt_absorb(strobe_sh &h, wts &w, int lane, const uint8_t *d, uint32_t n) {
+    uint8_t *st8 = (uint8_t *)h.st;
+    for (uint32_t off = 0; off < n;) {
+        const uint32_t room = STROBE_R - w.pos, chunk = n - off < room ? n - off : room;
+        for (uint32_t i = lane; i < chunk; i += TS_THREADS) st8[w.pos + i] ^= d[off + i];
+        w.pos += chunk; off += chunk;
+        if (w.pos == STROBE_R) wt_run_f(h, w, lane);
+    }
+    TS_WSYNC();
+}
+DEV void wt_squeeze(strobe_sh &h, wts &w, int lane, uint8_t *out, uint32_t n) {       // out: shared memory
+    uint8_t *st8 = (uint8_t *)h.st;
+    for (uint32_t off = 0; off < n;) {
+        const uint32_t room = STROBE_R - w.pos, chunk = n - off < room ? n - off : room;
+        for (uint32_t i = lane; i < chunk; i += TS_THREADS) { out[off + i] = st8[w.pos + i]; st8[w.pos + i] = 0; }
+        w.pos += chunk; off += chunk;
+        if (w.pos == STROBE_R) wt_run_f(h, w, lane);
+    }
+    TS_WSYNC();
+}
+DEV void wt_begin_op(strobe_sh &h, wts &w, int lane, uint8_t flags) {
+    const uint8_t hdr[2] = {(uint8_t)w.pos_begin, flags};
+    w.pos_begin = w.pos + 1; w.cur_flags = flags;
+    wt_absorb(h, w, lane, hdr, 2);
+    if ((flags & (4 | 32)) && w.pos != 0) wt_run_f(h, w, lane);
+}
+DEV uint32_t wt_strlen(const char *s) { uint32_t n = 0; while (s[n]) n++; return n; }
+DEV void wt_append(strobe_sh &h, wts &w, int lane, const char *label, const uint8_t *msg, uint32_t n) {
+    const uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+    wt_begin_op(h, w, lane, 16 | 2); wt_absorb(h, w, lane, (const uint8_t *)label, wt_strlen(label)); wt_absorb(h, w, lane, len, 4);
+    wt_begin_op(h, w, lane, 2); wt_absorb(h, w, lane, msg, n);
+}
+DEV void wt_append_u64(strobe_sh &h, wts &w, int lane, const char *label, uint64_t x) {
+    uint8_t b[8]; for (int i = 0; i < 8; i++) b[i] = (uint8_t)(x >> (8 * i));
+    wt_append(h, w, lane, label, b, 8);
+}
+DEV void wt_challenge(strobe_sh &h, wts &w, int lane, const char *label, uint8_t *out, uint32_t n) {      // out: shared memory
+    const uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+    wt_begin_op(h, w, lane, 16 | 2); wt_absorb(h, w, lane, (const uint8_t *)label, wt_strlen(label)); wt_absorb(h, w, lane, len, 4);
+    wt_begin_op(h, w, lane, 1 | 2 | 4); wt_squeeze(h, w, lane, out, n);
+}
+// challenge scalar (64 bytes reduced mod l) through h.io; every lane gets it
+DEV void wt_challenge_sc(strobe_sh &h, wts &w, int lane, const char *label, sc &out) {
+    wt_challenge(h, w, lane, label, h.io, 64);
+    uint8_t b[64]; for (int i = 0; i < 64; i++) b[i] = h.io[i];
+    TS_WSYNC();
+    sc_from_bytes_wide(out, b);
+}
+// 32 bytes from global memory -> h.io (all lanes see them afterwards); returns whether they are all zero
+DEV bool wt_load32(strobe_sh &h, int lane, const uint8_t *g, uint32_t at = 0) {
+    TS_WSYNC();
+    h.io[at + lane] = g[lane];
+    TS_WSYNC();
+    uint8_t z = 0; for (int i = 0; i < 32; i++) z |= h.io[at + i];
+    return z == 0;
+}
+DEV void wt_load(strobe_sh &h, wts &w, int lane, const transcript &t) {
+    TS_WSYNC();
+    if (lane < 25) h.st[lane] = t.st[lane];
+    w.pos = t.pos; w.pos_begin = t.pos_begin; w.cur_flags = t.cur_flags;
+    TS_WSYNC();
+}
+DEV void wt_store(const strobe_sh &h, const wts &w, int lane, transcript &t) {
+    TS_WSYNC();
+    if (lane < 25) t.st[lane] = h.st[lane];
+    if (lane == 0) { t.pos = (uint8_t)w.pos; t.pos_begin = (uint8_t)w.pos_begin; t.cur_flags = (uint8_t)w.cur_flags; }
+}
+DEV void wt_init(strobe_sh &h, wts &w, int lane, const char *label) {
+    const uint8_t hdr[18] = {1, STROBE_R + 2, 1, 0, 1, 96, 'S', 'T', 'R', 'O', 'B', 'E', 'v', '1', '.', '0', '.', '2'};
+    TS_WSYNC();
+    if (lane < 25) h.st[lane] = 0;
+    TS_WSYNC();
+    if (lane < 18) ((uint8_t *)h.st)[lane] ^= hdr[lane];
+    TS_WSYNC();
+    wt_permute(h, lane);
+    w.pos = 0; w.pos_begin = 0; w.cur_flags = 0;
+    wt_begin_op(h, w, lane, 16 | 2); wt_absorb(h, w, lane, (const uint8_t *)"Merlin v1.0", 11);
+    wt_append(h, w, lane, "dom-sep", (const uint8_t *)label, wt_strlen(label));
+}
 // m x Transcript::append_message(label (1 byte), 32-byte message) = per message the 41 stream bytes
 //   [pos_begin'] [M|A = 0x12] [label] [32 0 0 0]   [pos_begin''] [A = 0x02] [32 message bytes]
 // where the two pos_begin bytes are (begin position of the PREVIOUS operation) + 1 if that operation began in the current sponge
 // block and 0 otherwise (Strobe128::begin_op / run_f).  Byte k of the stream lands at absolute position A0 + k
 // (A0 = position at entry), so every byte is a function of k alone and the lanes fill a 166-byte block together.
 // byte at absolute stream position A (which lies in the sponge block starting at `base`)
-DEV uint8_t absorb_stream_byte(uint32_t A, uint32_t base, uint32_t A0, uint8_t pb0, uint8_t label, const uint8_t *msgs) {
+// (msgs points at message `joff`: the whole array with joff = 0, or the staged window)
+DEV uint8_t absorb_stream_byte(uint32_t A, uint32_t base, uint32_t A0, uint8_t pb0, uint8_t label, const uint8_t *msgs, uint32_t joff = 0) {
     const uint32_t k = A - A0, j = k / 41u, r = k - 41u * j, a1 = A0 + 41u * j;
-    if (r >= 9) return msgs[32 * (size_t)j + (r - 9)];
+    if (r >= 9) return msgs[32 * (size_t)(j - joff) + (r - 9)];
     if (r == 0) { const uint32_t ap = a1 - 34; return j == 0 ? pb0 : (ap >= base ? (uint8_t)(ap - base + 1) : 0); }      // a1 = A lies in this block
     if (r == 1) return 0x12;
     if (r == 2) return label;
@@ -95,38 +228,50 @@ DEV void strobe_absorb_many_coop(strobe_sh &h, int lane, uint8_t label, const ui
         }
     }
 #else
-    // device form: lane t < 25 keeps word t of the state in registers, builds its own 8 bytes of every block and the permutation exchanges
-    // words with warp shuffles (9 64-bit shuffles in 4 dependent steps per round; the shared-memory form needs 72 LDS/STS round trips per
-    // permutation and measured 6.7 us per block on B200, this one ~2 us)
-    const int x = lane % 5, row = lane - x;
-    const int src = lane < 25 ? KC_SRC_[lane] : 0, rot = lane < 25 ? KC_ROT_[lane] : 0;
-    const int l5 = (lane + 5) % 25, l10 = (lane + 10) % 25, l15 = (lane + 15) % 25, l20 = (lane + 20) % 25;
-    const int dm = row + (x + 4) % 5, dp = row + (x + 1) % 5, c1 = row + (x + 1) % 5, c2 = row + (x + 2) % 5;
+    // device form: lane t < 25 keeps word t of the state in a register and the permutation exchanges words with warp shuffles (keccak_shfl).
+    // The absorbed byte stream is composed in shared memory 32 messages at a time -- one lane per message: its 9 framing bytes and 32 message
+    // bytes (two 16-byte loads) go to a ring indexed by the absolute stream position -- so that a block costs every lane two aligned 8-byte reads
+    // and a funnel shift.  (Composing each lane's 8 bytes of every block separately, 8 divisions and data-dependent branches per lane and block,
+    // took as long as the permutation: 6 us per block in total.)
     uint64_t a = lane < 25 ? h.st[lane] : 0;
-    auto sh64 = [](uint64_t v, int from) { const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, from), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), from); return ((uint64_t)hi << 32) | lo; };
+    uint8_t *ring8 = (uint8_t *)h.ring;
+    const bool al16 = (((uintptr_t)msgs) & 15) == 0;
+    for (uint32_t i = lane; i < TS_RING / 8; i += TS_THREADS) h.ring[i] = 0;           // positions before A0 (block 0) read as zero
+    __syncwarp();
+    uint32_t jnext = 0, filled = A0;                                                     // stream composed up to absolute position `filled`
     for (uint32_t e = 0; e <= nfull; e++) {
-        const uint32_t base = STROBE_R * e;
-        if (lane < 21) {
-            uint64_t w = 0;
-            for (uint32_t b = 0; b < 8; b++) {
-                const uint32_t p = 8 * lane + b, A = base + p;
-                if (p < STROBE_R && A >= A0 && A < A_end) w |= (uint64_t)absorb_stream_byte(A, base, A0, pb0, label, msgs) << (8 * b);
+        const uint32_t base = STROBE_R * e, need = base + STROBE_R < A_end ? base + STROBE_R : A_end;
+        while (filled < need) {                                                          // (at most 165 composed bytes are still unread here)
+            const uint32_t j = jnext + lane;
+            if (j < m) {
+                const uint32_t a1 = A0 + 41u * j, b1 = a1 / STROBE_R * STROBE_R, b7 = (a1 + 7) / STROBE_R * STROBE_R, ap = a1 - 34;
+                uint8_t hdr[9] = {(uint8_t)(j == 0 ? pb0 : (ap >= b1 ? ap - b1 + 1 : 0)), 0x12, label, 32, 0, 0, 0, (uint8_t)(a1 >= b7 ? a1 - b7 + 1 : 0), 0x02};
+                for (int i = 0; i < 9; i++) ring8[(a1 + i) & (TS_RING - 1)] = hdr[i];
+                const uint8_t *mp = msgs + 32 * (size_t)j;
+                if (al16) {
+                    const uint4 q0 = ((const uint4 *)mp)[0], q1 = ((const uint4 *)mp)[1];
+                    const uint32_t wv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                    for (int i = 0; i < 32; i++) ring8[(a1 + 9 + i) & (TS_RING - 1)] = (uint8_t)(wv[i >> 2] >> (8 * (i & 3)));
+                } else
+                    for (int i = 0; i < 32; i++) ring8[(a1 + 9 + i) & (TS_RING - 1)] = mp[i];
             }
-            if (lane == 20 && e < nfull) w ^= ((uint64_t)absorb_close_pb(base, A0) << 48) | ((uint64_t)(0x04 ^ 0x80) << 56);      // bytes 166, 167
+            jnext += TS_THREADS;
+            filled = jnext < m ? A0 + 41u * jnext : A_end;
+            if (jnext >= m) for (uint32_t i = lane; i < STROBE_R + 16; i += TS_THREADS) ring8[(A_end + i) & (TS_RING - 1)] = 0;      // the last block reads past the end
+            __syncwarp();
+        }
+        if (lane < 21) {
+            const uint32_t idx = (base + 8 * lane) & (TS_RING - 1), sh = (idx & 7) * 8;
+            const uint64_t lo = h.ring[idx >> 3], hi = h.ring[((idx >> 3) + 1) & (TS_RING / 8 - 1)];
+            uint64_t w = sh ? (lo >> sh) | (hi << (64 - sh)) : lo;
+            if (lane == 20) {
+                w &= 0x0000ffffffffffffULL;                                                // bytes 166, 167 of the block are not rate bytes
+                if (e < nfull) w ^= ((uint64_t)absorb_close_pb(base, A0) << 48) | ((uint64_t)(0x04 ^ 0x80) << 56);
+            }
             a ^= w;
         }
-        if (e < nfull) {
-            for (int r = 0; r < 24; r++) {
-                uint64_t c = a ^ sh64(a, l5) ^ sh64(a, l10) ^ sh64(a, l15) ^ sh64(a, l20);                 // column parity (every lane of the column gets it)
-                const uint64_t cm = sh64(c, dm), cp = sh64(c, dp);
-                a ^= cm ^ ((cp << 1) | (cp >> 63));
-                uint64_t bsrc = sh64(a, src);
-                bsrc = (bsrc << rot) | (bsrc >> ((64 - rot) & 63));
-                const uint64_t b1 = sh64(bsrc, c1), b2 = sh64(bsrc, c2);
-                a = bsrc ^ (~b1 & b2);
-                if (lane == 0) a ^= KECCAK_RC_[r];
-            }
-        }
+        if (e < nfull) a = keccak_shfl(a, lane);
+        __syncwarp();                                                                    // every lane has read block e before the ring is written again
     }
     if (lane < 25) h.st[lane] = a;
 #endif
@@ -136,6 +281,14 @@ DEV void strobe_absorb_many_coop(strobe_sh &h, int lane, uint8_t label, const ui
         h.pos_begin = a2l >= cur ? a2l - cur + 1 : 0;
     }
     TS_WSYNC();
+}
+DEV void wt_absorb_many(strobe_sh &h, wts &w, int lane, uint8_t label, const uint8_t *msgs, uint32_t m) {
+    if (m == 0) return;
+    TS_WSYNC();
+    if (lane == 0) { h.pos = w.pos; h.pos_begin = w.pos_begin; }
+    TS_WSYNC();
+    strobe_absorb_many_coop(h, lane, label, msgs, m);
+    w.pos = h.pos; w.pos_begin = h.pos_begin; w.cur_flags = 2;
 }
 DEV bool is_zero32_(const uint8_t *b) { uint8_t z = 0; for (int i = 0; i < 32; i++) z |= b[i]; return z == 0; }
 DEV void ts_challenge_sc(transcript &t, const char *label, sc &out) { uint8_t b[64]; transcript_challenge(t, label, b, 64); sc_from_bytes_wide(out, b); }
@@ -160,34 +313,27 @@ struct ts_final_args { const sc_st *a, *b, *up; uint8_t *proofs; uint32_t plen, 
 KERNEL void LB(TS_THREADS, 1) k_ts_absorbV(ts_absorb_args a) {
     __shared__ strobe_sh h;
     const int c = blockIdx.x, lane = threadIdx.x;
-    if (lane == 0) {
-        transcript t; transcript_init(t, a.label_id ? "L2RangeProof" : "RangeProof");
-        transcript_append(t, "dom-sep", (const uint8_t *)"rangeproof v1", 13);
-        transcript_append_u64(t, "n", (uint64_t)a.n); transcript_append_u64(t, "m", (uint64_t)a.m);
-        for (int i = 0; i < 25; i++) h.st[i] = t.st[i];
-        h.pos = t.pos; h.pos_begin = t.pos_begin;
-    }
-    TS_WSYNC();
-    strobe_absorb_many_coop(h, lane, (uint8_t)'V', a.V32 + 32 * (size_t)c * a.m, a.m);
-    if (lane < 25) a.ts[c].st[lane] = h.st[lane];
-    if (lane == 0) { a.ts[c].pos = (uint8_t)h.pos; a.ts[c].pos_begin = (uint8_t)h.pos_begin; a.ts[c].cur_flags = 2; }
+    wts w;
+    wt_init(h, w, lane, a.label_id ? "L2RangeProof" : "RangeProof");
+    wt_append(h, w, lane, "dom-sep", (const uint8_t *)"rangeproof v1", 13);
+    wt_append_u64(h, w, lane, "n", (uint64_t)a.n); wt_append_u64(h, w, lane, "m", (uint64_t)a.m);
+    wt_absorb_many(h, w, lane, (uint8_t)'V', a.V32 + 32 * (size_t)c * a.m, a.m);
+    wt_store(h, w, lane, a.ts[c]);
 }
 KLAUNCH(k_ts_absorbV, true, (ts_absorb_args a), (a))
 KERNEL void LB(TS_THREADS, 1) k_ts_yz(ts_yz_args a) {
-    __shared__ sc_st sh[3];
+    __shared__ strobe_sh h;
     const uint32_t c = blockIdx.x; const int lane = threadIdx.x;
-    if (lane == 0) {
-        transcript t = a.ts[c];
-        uint8_t A[32], S[32]; ld_bytes32(A, a.AS + 32 * (size_t)c); ld_bytes32(S, a.AS + 32 * (size_t)(a.C + c));
-        uint8_t *o = a.proofs + (size_t)a.plen * c; st_bytes32(o, A); st_bytes32(o + 32, S);
-        ts_append32(t, "A", A); ts_append32(t, "S", S);
-        sc y, z, yi; ts_challenge_sc(t, "y", y); ts_challenge_sc(t, "z", z); sc_invert_vartime(yi, y);
-        a.ts[c] = t;
-        st_sc(sh, y); st_sc(sh + 1, z); st_sc(sh + 2, yi); st_sc(a.z + c, z);
-    }
-    TS_WSYNC();
-    if (lane < 3) {
-        sc cur; ld_sc(cur, sh + lane);
+    wts w; wt_load(h, w, lane, a.ts[c]);
+    uint8_t *o = a.proofs + (size_t)a.plen * c;
+    wt_load32(h, lane, a.AS + 32 * (size_t)c); o[lane] = h.io[lane]; wt_append(h, w, lane, "A", h.io, 32);
+    wt_load32(h, lane, a.AS + 32 * (size_t)(a.C + c)); o[32 + lane] = h.io[lane]; wt_append(h, w, lane, "S", h.io, 32);
+    sc y, z; wt_challenge_sc(h, w, lane, "y", y); wt_challenge_sc(h, w, lane, "z", z);
+    wt_store(h, w, lane, a.ts[c]);
+    if (lane == 1) st_sc(a.z + c, z);
+    if (lane < 3) {                                                // y^(2^b), z^(2^b), y^-(2^b)
+        sc cur = lane == 1 ? z : y;
+        if (lane == 2) sc_invert_vartime(cur, y);
         sc_st *tab = (lane == 0 ? a.ypow2 : lane == 1 ? a.zpow2 : a.yinvpow2) + 32 * (size_t)c;
         for (int b = 0; b < 32; b++) { st_sc(tab + b, cur); sc_mul(cur, cur, cur); }
     }
@@ -203,41 +349,48 @@ KERNEL void k_ts_t12(sc_st *t12, const sc_st *tsum, uint32_t C) {
 }
 KLAUNCH(k_ts_t12, false, (sc_st *t12, const sc_st *tsum, uint32_t C), (t12, tsum, C))
 KERNEL void LB(TS_THREADS, 1) k_ts_x(ts_x_args a) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x, C = a.C;
-    if (c >= C) return;
-    transcript t = a.ts[c];
+    __shared__ strobe_sh h;
+    __shared__ uint8_t sb[96];                                     // t_x | t_x_blinding | e_blinding
+    const uint32_t c = blockIdx.x, C = a.C; const int lane = threadIdx.x;
+    wts w; wt_load(h, w, lane, a.ts[c]);
     uint8_t *o = a.proofs + (size_t)a.plen * c;
-    uint8_t T1[32], T2[32]; ld_bytes32(T1, a.T12 + 32 * (size_t)c); ld_bytes32(T2, a.T12 + 32 * (size_t)(C + c));
-    st_bytes32(o + 64, T1); st_bytes32(o + 96, T2);
-    ts_append32(t, "T_1", T1); ts_append32(t, "T_2", T2);
-    sc x, w; ts_challenge_sc(t, "x", x);
-    sc t0, t1, t2, sa, ss, st1, st2, szg, xx, tx, txb, eb, tmp;
-    ld_sc(t0, a.tsum + c); ld_sc(t1, a.tsum + C + c); ld_sc(t2, a.tsum + 2 * C + c); sc_sub(t1, t1, t0); sc_sub(t1, t1, t2);
-    ld_sc(sa, a.sums + c); ld_sc(ss, a.sums + C + c); ld_sc(st1, a.sums + 2 * C + c); ld_sc(st2, a.sums + 3 * C + c); ld_sc(szg, a.sums + 4 * C + c);
-    sc_mul(xx, x, x);
-    sc_mul(tmp, t1, x); sc_add(tx, t0, tmp); sc_mul(tmp, t2, xx); sc_add(tx, tx, tmp);
-    sc_mul(tmp, st1, x); sc_add(txb, szg, tmp); sc_mul(tmp, st2, xx); sc_add(txb, txb, tmp);
-    sc_mul(tmp, ss, x); sc_add(eb, sa, tmp);
-    uint8_t b[32];
-    sc_tobytes(b, tx); st_bytes32(o + 128, b); ts_append32(t, "t_x", b);
-    sc_tobytes(b, txb); st_bytes32(o + 160, b); ts_append32(t, "t_x_blinding", b);
-    sc_tobytes(b, eb); st_bytes32(o + 192, b); ts_append32(t, "e_blinding", b);
-    ts_challenge_sc(t, "w", w);
-    transcript_append(t, "dom-sep", (const uint8_t *)"ipp v1", 6); transcript_append_u64(t, "n", a.N);
-    a.ts[c] = t;
-    st_sc(a.x + c, x); st_sc(a.w2 + c, w); st_sc(a.w2 + C + c, w);
+    wt_load32(h, lane, a.T12 + 32 * (size_t)c); o[64 + lane] = h.io[lane]; wt_append(h, w, lane, "T_1", h.io, 32);
+    wt_load32(h, lane, a.T12 + 32 * (size_t)(C + c)); o[96 + lane] = h.io[lane]; wt_append(h, w, lane, "T_2", h.io, 32);
+    sc x, wch; wt_challenge_sc(h, w, lane, "x", x);
+    if (lane == 0) {
+        sc t0, t1, t2, sa, ss, st1, st2, szg, xx, tx, txb, eb, tmp;
+        ld_sc(t0, a.tsum + c); ld_sc(t1, a.tsum + C + c); ld_sc(t2, a.tsum + 2 * C + c); sc_sub(t1, t1, t0); sc_sub(t1, t1, t2);
+        ld_sc(sa, a.sums + c); ld_sc(ss, a.sums + C + c); ld_sc(st1, a.sums + 2 * C + c); ld_sc(st2, a.sums + 3 * C + c); ld_sc(szg, a.sums + 4 * C + c);
+        sc_mul(xx, x, x);
+        sc_mul(tmp, t1, x); sc_add(tx, t0, tmp); sc_mul(tmp, t2, xx); sc_add(tx, tx, tmp);
+        sc_mul(tmp, st1, x); sc_add(txb, szg, tmp); sc_mul(tmp, st2, xx); sc_add(txb, txb, tmp);
+        sc_mul(tmp, ss, x); sc_add(eb, sa, tmp);
+        uint8_t b[32];
+        sc_tobytes(b, tx); for (int i = 0; i < 32; i++) sb[i] = b[i];
+        sc_tobytes(b, txb); for (int i = 0; i < 32; i++) sb[32 + i] = b[i];
+        sc_tobytes(b, eb); for (int i = 0; i < 32; i++) sb[64 + i] = b[i];
+    }
+    TS_WSYNC();
+    for (int i = lane; i < 96; i += TS_THREADS) o[128 + i] = sb[i];
+    wt_append(h, w, lane, "t_x", sb, 32); wt_append(h, w, lane, "t_x_blinding", sb + 32, 32); wt_append(h, w, lane, "e_blinding", sb + 64, 32);
+    wt_challenge_sc(h, w, lane, "w", wch);
+    wt_append(h, w, lane, "dom-sep", (const uint8_t *)"ipp v1", 6); wt_append_u64(h, w, lane, "n", a.N);
+    wt_store(h, w, lane, a.ts[c]);
+    if (lane == 0) { st_sc(a.x + c, x); st_sc(a.w2 + c, wch); st_sc(a.w2 + C + c, wch); }
 }
-KLAUNCH(k_ts_x, false, (ts_x_args a), (a))
+KLAUNCH(k_ts_x, true, (ts_x_args a), (a))
 KERNEL void LB(TS_THREADS, 1) k_ts_round(ts_round_args a) {
     __shared__ sc_st sf[2];                                       // u^2 | u^-2 y^-n'
+    __shared__ strobe_sh h;
     const uint32_t c = blockIdx.x, C = a.C; const int lane = threadIdx.x;
+    wts w; wt_load(h, w, lane, a.ts[c]);
+    uint8_t *o = a.proofs + (size_t)a.plen * c + a.off;
+    wt_load32(h, lane, a.LR + 32 * (size_t)c); o[lane] = h.io[lane]; wt_append(h, w, lane, "L", h.io, 32);
+    wt_load32(h, lane, a.LR + 32 * (size_t)(C + c)); o[32 + lane] = h.io[lane]; wt_append(h, w, lane, "R", h.io, 32);
+    sc u; wt_challenge_sc(h, w, lane, "u", u);
+    wt_store(h, w, lane, a.ts[c]);
     if (lane == 0) {
-        transcript t = a.ts[c];
-        uint8_t L[32], R[32]; ld_bytes32(L, a.LR + 32 * (size_t)c); ld_bytes32(R, a.LR + 32 * (size_t)(C + c));
-        uint8_t *o = a.proofs + (size_t)a.plen * c + a.off; st_bytes32(o, L); st_bytes32(o + 32, R);
-        ts_append32(t, "L", L); ts_append32(t, "R", R);
-        sc u, ui, u2, ui2, sH, yp, p; ts_challenge_sc(t, "u", u); sc_invert_vartime(ui, u);
-        a.ts[c] = t;
+        sc ui, u2, ui2, sH, yp, p; sc_invert_vartime(ui, u);
         sc_mul(u2, u, u); sc_mul(ui2, ui, ui); ld_sc(yp, a.yinvpow2 + 32 * (size_t)c + a.lgnp); sc_mul(sH, ui2, yp);
         st_sc(a.u2 + c, u2); st_sc(a.uinv2 + c, ui2); st_sc(sf, u2); st_sc(sf + 1, sH);
         ld_sc(p, a.up + c); sc_mul(p, p, u); st_sc(a.up + c, p);
@@ -306,34 +459,40 @@ struct verify_prep_args {
 };
 #ifdef KG_TS
 KERNEL void LB(TS_THREADS, 1) k_ts_verify(ts_verify_args a) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.C) return;
+    __shared__ strobe_sh h;
+    const uint32_t c = blockIdx.x; const int lane = threadIdx.x;          // one warp per chunk
     const int lgN = a.lgN, nsmall = 6 + 2 * lgN;
     const uint8_t *p = a.proofs + (size_t)a.plen * c, *ipp = p + 224;
     uint8_t *sp = a.sp32 + 32 * (size_t)c * nsmall;
     sc_st *ch = a.chal + (size_t)c * (4 + lgN);
-    transcript t = a.ts[c];
-    uint8_t b[32]; int ok = 1; sc s;
-    ld_bytes32(b, p); ok &= !is_zero32_(b); st_bytes32(sp, b); ts_append32(t, "A", b);
-    ld_bytes32(b, p + 32); ok &= !is_zero32_(b); st_bytes32(sp + 32, b); ts_append32(t, "S", b);
-    ts_challenge_sc(t, "y", s); st_sc(ch, s); ts_challenge_sc(t, "z", s); st_sc(ch + 1, s);
-    ld_bytes32(b, p + 64); ok &= !is_zero32_(b); st_bytes32(sp + 64, b); ts_append32(t, "T_1", b);
-    ld_bytes32(b, p + 96); ok &= !is_zero32_(b); st_bytes32(sp + 96, b); ts_append32(t, "T_2", b);
-    ts_challenge_sc(t, "x", s); st_sc(ch + 2, s);
-    ld_bytes32(b, p + 128); ts_append32(t, "t_x", b); ld_bytes32(b, p + 160); ts_append32(t, "t_x_blinding", b); ld_bytes32(b, p + 192); ts_append32(t, "e_blinding", b);
-    ts_challenge_sc(t, "w", s); st_sc(ch + 3, s);
-    transcript_append(t, "dom-sep", (const uint8_t *)"ipp v1", 6); transcript_append_u64(t, "n", a.N);
+    wts w; wt_load(h, w, lane, a.ts[c]);
+    int ok = 1; sc s;
+    // validate_and_append_point: the identity encoding is refused
+    ok &= !wt_load32(h, lane, p); sp[lane] = h.io[lane]; wt_append(h, w, lane, "A", h.io, 32);
+    ok &= !wt_load32(h, lane, p + 32); sp[32 + lane] = h.io[lane]; wt_append(h, w, lane, "S", h.io, 32);
+    wt_challenge_sc(h, w, lane, "y", s); if (lane == 0) st_sc(ch, s);
+    wt_challenge_sc(h, w, lane, "z", s); if (lane == 0) st_sc(ch + 1, s);
+    ok &= !wt_load32(h, lane, p + 64); sp[64 + lane] = h.io[lane]; wt_append(h, w, lane, "T_1", h.io, 32);
+    ok &= !wt_load32(h, lane, p + 96); sp[96 + lane] = h.io[lane]; wt_append(h, w, lane, "T_2", h.io, 32);
+    wt_challenge_sc(h, w, lane, "x", s); if (lane == 0) st_sc(ch + 2, s);
+    wt_load32(h, lane, p + 128); wt_append(h, w, lane, "t_x", h.io, 32);
+    wt_load32(h, lane, p + 160); wt_append(h, w, lane, "t_x_blinding", h.io, 32);
+    wt_load32(h, lane, p + 192); wt_append(h, w, lane, "e_blinding", h.io, 32);
+    wt_challenge_sc(h, w, lane, "w", s); if (lane == 0) st_sc(ch + 3, s);
+    wt_append(h, w, lane, "dom-sep", (const uint8_t *)"ipp v1", 6); wt_append_u64(h, w, lane, "n", a.N);
     for (int k = 0; k < lgN; k++) {
-        ld_bytes32(b, ipp + 64 * k); ok &= !is_zero32_(b); st_bytes32(sp + 32 * (4 + k), b); ts_append32(t, "L", b);
-        ld_bytes32(b, ipp + 64 * k + 32); ok &= !is_zero32_(b); st_bytes32(sp + 32 * (4 + lgN + k), b); ts_append32(t, "R", b);
-        ts_challenge_sc(t, "u", s); st_sc(ch + 4 + k, s);
+        ok &= !wt_load32(h, lane, ipp + 64 * k); sp[32 * (4 + k) + lane] = h.io[lane]; wt_append(h, w, lane, "L", h.io, 32);
+        ok &= !wt_load32(h, lane, ipp + 64 * k + 32); sp[32 * (4 + lgN + k) + lane] = h.io[lane]; wt_append(h, w, lane, "R", h.io, 32);
+        wt_challenge_sc(h, w, lane, "u", s); if (lane == 0) st_sc(ch + 4 + k, s);
     }
-    st_bytes32(sp + 32 * (4 + 2 * lgN), a.H32); st_bytes32(sp + 32 * (5 + 2 * lgN), a.B32);
-    ld_bytes32(b, ipp + 64 * lgN); ts_append32(t, "a", b); ld_bytes32(b, ipp + 64 * lgN + 32); ts_append32(t, "b", b);
-    transcript_challenge(t, "rofl-batch", b, 32); st_bytes32(a.digest + 32 * (size_t)c, b);
-    if (!ok) a.bad[c] = 1;
+    sp[32 * (4 + 2 * lgN) + lane] = a.H32[lane]; sp[32 * (5 + 2 * lgN) + lane] = a.B32[lane];
+    wt_load32(h, lane, ipp + 64 * lgN); wt_append(h, w, lane, "a", h.io, 32);
+    wt_load32(h, lane, ipp + 64 * lgN + 32); wt_append(h, w, lane, "b", h.io, 32);
+    wt_challenge(h, w, lane, "rofl-batch", h.io, 32);
+    a.digest[32 * (size_t)c + lane] = h.io[lane];
+    if (!ok && lane == 0) a.bad[c] = 1;
 }
-KLAUNCH(k_ts_verify, false, (ts_verify_args a), (a))
+KLAUNCH(k_ts_verify, true, (ts_verify_args a), (a))
 KERNEL void LB(256, 1) k_verify_keys(verify_keys_args a) {
     __shared__ uint8_t glob[32];
     if (threadIdx.x == 0) {

@@ -8,6 +8,7 @@ import struct
 import subprocess
 import numpy as np
 import pytest
+from conftest import locked_make
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -214,14 +215,14 @@ def run_suite(lib, oracle):
 
 def test_bindings32_exports_by_reference_names_emulated(oracle):
     d = os.path.join(HERE, "hostsim")
-    subprocess.check_call(["make", "-C", d, "-s", "libemul.so", "libbindings32_emul.so"], env={**os.environ, "CXX": "g++"})
+    locked_make(d, "libemul.so", "libbindings32_emul.so", env={"CXX": "g++"})
     run_suite(bind(C.CDLL(os.path.join(d, "libbindings32_emul.so"))), oracle)
 
 
 def test_shipped_bindings32_library_exports_every_reference_symbol():
     """No compute (no GPU here): the shipped library exists after build() and exports every `#[no_mangle] pub extern "C"` name of bindings32.rs."""
     path = os.path.join(ROOT, "rofl-project-code_b200", "librofl_b200_bindings32.so")
-    subprocess.check_call(["make", "-C", os.path.join(ROOT, "rofl-project-code_b200", "csrc"), "-s", "-j", "8"])
+    locked_make(os.path.join(ROOT, "rofl-project-code_b200", "csrc"), jobs=8)
     out = subprocess.check_output(["nm", "-D", "--defined-only", path], text=True)
     names = {l.split()[-1] for l in out.splitlines() if l.strip()}
     missing = [n for n in SIGS if n not in names]

@@ -7,6 +7,7 @@ import os
 import subprocess
 import numpy as np
 import pytest
+from conftest import locked_make
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -15,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 @pytest.fixture(scope="module")
 def api():
     d = os.path.join(HERE, "hostsim")
-    subprocess.check_call(["make", "-C", d, "-s", "libemul.so"], env={**os.environ, "CXX": "g++"})
+    locked_make(d, "libemul.so", env={"CXX": "g++"})
     spec = importlib.util.spec_from_file_location("rofl_ffi", os.path.join(ROOT, "rofl-project-code_b200", "_ffi.py"))
     ffi = importlib.util.module_from_spec(spec); spec.loader.exec_module(ffi)
     a = ffi.Api(C.CDLL(os.path.join(d, "libemul.so")))

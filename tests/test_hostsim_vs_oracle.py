@@ -8,6 +8,7 @@ import os
 import subprocess
 import numpy as np
 import pytest
+from conftest import locked_make
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 L = 2**252 + 27742317777372353535851937790883648493
@@ -17,7 +18,7 @@ P = 2**255 - 19
 @pytest.fixture(scope="module")
 def hs():
     d = os.path.join(HERE, "hostsim")
-    subprocess.check_call(["make", "-C", d, "-s"], env={**os.environ, "CXX": "g++"})
+    locked_make(d, env={"CXX": "g++"})
     return C.CDLL(os.path.join(d, "libhostsim.so"))
 
 

@@ -8,6 +8,7 @@ import subprocess
 import sys
 import numpy as np
 import pytest
+from conftest import locked_make
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -61,7 +62,7 @@ def _worker(rank, world, port, q):
 
 def test_chunk_sharded_prove_verify_decrypt_two_ranks(oracle):
     import torch.multiprocessing as mp
-    subprocess.check_call(["make", "-C", os.path.join(HERE, "hostsim"), "-s", "libemul.so"], env={**os.environ, "CXX": "g++"})
+    locked_make(os.path.join(HERE, "hostsim"), "libemul.so", env={"CXX": "g++"})
     D, rb, P, nb, v, bl, seed = _inputs()
     rc_o, p_o, c_o = oracle.range_prove(v, bl, rb, P, nb, 7, seed)
     assert rc_o == 0
