@@ -784,7 +784,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, in
       LAUNCH_COOP(k_verify_keys, dim3(1), dim3(256), s, ka); }
     { verify_prep_args pa = {}; pa.proofs = d_proofs.as<uint8_t>(); pa.plen = (uint32_t)plen; pa.C = (uint32_t)C; pa.lgN = lgN; pa.lgm = lgm; pa.n = n; pa.vch = d_vch.as<sc_st>(); pa.ccrho = d_ccrho.as<sc_st>();
       pa.chal = d_chal.as<sc_st>(); pa.chs = chs; pa.small = d_var.as<sc_st>() + (size_t)C * m; pa.nsmall = nsmall; pa.yinvpow2 = d_yinvpow2.as<sc_st>(); pa.zpow2 = d_zpow2.as<sc_st>();
-      LAUNCH_COOP(k_verify_prep, dim3(C), dim3(TS_THREADS), s, pa); }
+      LAUNCH_COOP(k_verify_prep, dim3(C), dim3(2 * TS_THREADS), s, pa); }
     tr.mark("v_transcripts");
     LAUNCH(k_verify_tables, dim3((vt.total + m + 255) / 256, C), dim3(256), s, d_tab.as<sc_st>(), vt, d_var.as<sc_st>(), (uint32_t)m, d_chal.as<sc_st>(), chs, d_yinvpow2.as<sc_st>(), d_zpow2.as<sc_st>(), m);
     LAUNCH_COOP(k_verify_scalars, dim3((unsigned)((N + 63) / 64)), dim3(256), s, d_gh.as<sc_st>(), d_tab.as<sc_st>(), vt, d_chal.as<sc_st>(), chs, n, C);

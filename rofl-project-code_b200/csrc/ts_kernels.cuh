@@ -494,14 +494,27 @@ KERNEL void LB(TS_THREADS, 1) k_ts_verify(ts_verify_args a) {
 }
 KLAUNCH(k_ts_verify, true, (ts_verify_args a), (a))
 KERNEL void LB(256, 1) k_verify_keys(verify_keys_args a) {
+    __shared__ strobe_sh h;                                       // (used as a plain SHA3-256 sponge here: rate 136)
     __shared__ uint8_t glob[32];
-    if (threadIdx.x == 0) {
-        sponge s; sponge_init(s, 136); sponge_absorb(s, a.seed, 32);
-        uint8_t cb[8]; for (int i = 0; i < 8; i++) cb[i] = (uint8_t)((uint64_t)a.C >> (8 * i));
-        sponge_absorb(s, cb, 8);
-        for (uint32_t c = 0; c < a.C; c++) { uint8_t d[32]; ld_bytes32(d, a.digest + 32 * (size_t)c); sponge_absorb(s, d, 32); }
-        sponge_finish(s, 0x06); sponge_squeeze(s, glob, 32);
+    // glob = SHA3-256(seed | C | digest_0 .. digest_(C-1)): warp 0 absorbs the bytes side by side and permutes with shuffles.  (Control flow is
+    // uniform over the block -- the other warps walk through the same barriers and permute nothing -- so that the CPU emulation, whose warp
+    // barrier is the block barrier, runs the same code.)
+    const int lane = threadIdx.x; const bool w0 = threadIdx.x < TS_THREADS;
+    uint8_t *st8 = (uint8_t *)h.st;
+    if (lane < 25) h.st[lane] = 0;
+    TS_WSYNC();
+    const uint64_t total = 40 + 32 * (uint64_t)a.C;
+    for (uint64_t base = 0;; base += 136) {
+        const uint64_t left = total - base; const uint32_t n = left < 136 ? (uint32_t)left : 136;
+        if (w0) for (uint32_t i = lane; i < n; i += TS_THREADS) {
+            const uint64_t k = base + i;
+            st8[i] ^= k < 32 ? a.seed[k] : k < 40 ? (uint8_t)((uint64_t)a.C >> (8 * (k - 32))) : a.digest[k - 40];
+        }
+        TS_WSYNC();
+        if (n < 136) { if (lane == 0) { st8[n] ^= 0x06; st8[135] ^= 0x80; } TS_WSYNC(); wt_permute(h, lane); break; }
+        wt_permute(h, lane);
     }
+    if (w0) glob[lane] = st8[lane];
     __syncthreads();
     for (uint32_t c = threadIdx.x; c < a.C; c += blockDim.x) {
         uint8_t buf[44], key[32]; for (int i = 0; i < 32; i++) buf[i] = glob[i];
@@ -514,31 +527,26 @@ KERNEL void LB(256, 1) k_verify_keys(verify_keys_args a) {
     }
 }
 KLAUNCH(k_verify_keys, true, (verify_keys_args a), (a))
-KERNEL void LB(TS_THREADS, 1) k_verify_prep(verify_prep_args a) {
+KERNEL void LB(2 * TS_THREADS, 1) k_verify_prep(verify_prep_args a) {
+    // two warps per chunk: thread 0 inverts y and the u_k (Montgomery's trick, one inversion) while warp 1 computes what needs no inverse
+    // (thread 32: the constant block and delta, thread 33: the powers z^(2^b)); different paths of ONE warp would run one after the other
     __shared__ sc_st inv[34];                                     // y^-1, u_k^-1
-    const uint32_t c = blockIdx.x, C = a.C; const int lane = threadIdx.x, lgN = a.lgN;
+    const uint32_t c = blockIdx.x, C = a.C; const int tid = threadIdx.x, lgN = a.lgN;
     const sc_st *vch = a.vch + (size_t)c * (4 + lgN);
-    if (lane == 0) {                                             // Montgomery's trick over y, u_0 .. u_(lgN-1) (zero, probability 2^-252, is replaced by 1)
+    sc rho, cc; ld_sc(cc, a.ccrho + c); ld_sc(rho, a.ccrho + C + c);
+    sc_st *ch = a.chal + (size_t)c * a.chs, *sm = a.small + (size_t)c * a.nsmall;
+    if (tid == 0) {                                              // (zero, probability 2^-252, is replaced by 1)
         sc pre[34], v[34], acc, one; sc_from_u64(one, 1); acc = one;
         for (int i = 0; i <= lgN; i++) { ld_sc(v[i], i == 0 ? vch : vch + 3 + i); if (sc_iszero(v[i])) v[i] = one; pre[i] = acc; sc_mul(acc, acc, v[i]); }
         sc iv; sc_invert_vartime(iv, acc);
         for (int i = lgN; i >= 0; i--) { sc t; sc_mul(t, iv, pre[i]); sc_mul(iv, iv, v[i]); st_sc(inv + i, t); }
     }
-    TS_WSYNC();
-    sc rho, cc; ld_sc(cc, a.ccrho + c); ld_sc(rho, a.ccrho + C + c);
-    sc_st *ch = a.chal + (size_t)c * a.chs, *sm = a.small + (size_t)c * a.nsmall;
-    if (lane == 1 || lane == 2) {
-        sc cur; ld_sc(cur, lane == 1 ? inv : vch + 1);
-        sc_st *tab = (lane == 1 ? a.yinvpow2 : a.zpow2) + 32 * (size_t)c;
+    if (tid == TS_THREADS + 1) {
+        sc cur; ld_sc(cur, vch + 1);
+        sc_st *tab = a.zpow2 + 32 * (size_t)c;
         for (int b = 0; b < 32; b++) { st_sc(tab + b, cur); sc_mul(cur, cur, cur); }
     }
-    for (int k = lane - 3; k >= 0 && k < lgN; k += TS_THREADS - 3) {
-        sc u, ui, t; ld_sc(u, vch + 4 + k); ld_sc(ui, inv + 1 + k);
-        st_sc(ch + 5 + k, u); st_sc(ch + 5 + lgN + k, ui);
-        sc_mul(t, u, u); sc_mul(t, t, rho); st_sc(sm + 4 + k, t);
-        sc_mul(t, ui, ui); sc_mul(t, t, rho); st_sc(sm + 4 + lgN + k, t);
-    }
-    if (lane == 0) {
+    if (tid == TS_THREADS) {
         const uint8_t *p = a.proofs + (size_t)a.plen * c, *ipp = p + 224; uint8_t b32[32];
         sc y, z, x, w, t_x, t_xb, e_bl, pa, pb, zz, tmp, tmp2, cx;
         ld_sc(y, vch); ld_sc(z, vch + 1); ld_sc(x, vch + 2); ld_sc(w, vch + 3);
@@ -559,6 +567,18 @@ KERNEL void LB(TS_THREADS, 1) k_verify_prep(verify_prep_args a) {
         sc_mul(tmp, zz, z); sc_mul(tmp, tmp, s2); sc_mul(tmp, tmp, sum_z); sc_sub(delta, delta, tmp);
         sc_mul(tmp, pa, pb); sc_sub(tmp, t_x, tmp); sc_mul(tmp, w, tmp);                                              // w (t_x - a b)
         sc_sub(tmp2, delta, t_x); sc_mul(tmp2, cc, tmp2); sc_add(tmp, tmp, tmp2); sc_mul(tmp, tmp, rho); st_sc(sm + 5 + 2 * lgN, tmp);      // B
+    }
+    __syncthreads();
+    if (tid == 1) {
+        sc cur; ld_sc(cur, inv);
+        sc_st *tab = a.yinvpow2 + 32 * (size_t)c;
+        for (int b = 0; b < 32; b++) { st_sc(tab + b, cur); sc_mul(cur, cur, cur); }
+    }
+    for (int k = tid - TS_THREADS; k >= 0 && k < lgN; k += TS_THREADS) {        // warp 1, beside the power table of warp 0
+        sc u, ui, t; ld_sc(u, vch + 4 + k); ld_sc(ui, inv + 1 + k);
+        st_sc(ch + 5 + k, u); st_sc(ch + 5 + lgN + k, ui);
+        sc_mul(t, u, u); sc_mul(t, t, rho); st_sc(sm + 4 + k, t);
+        sc_mul(t, ui, ui); sc_mul(t, t, rho); st_sc(sm + 4 + lgN + k, t);
     }
 }
 KLAUNCH(k_verify_prep, true, (verify_prep_args a), (a))
