@@ -66,6 +66,11 @@ def test_scalars(hs, oracle):
         ai = int.from_bytes(a, "little")
         assert int.from_bytes(call(hs, "hs_sc_invert_vartime", 32, a)[1], "little") == pow(ai, L - 2, L)
     assert call(hs, "hs_sc_invert_vartime", 32, bytes(32))[1] == bytes(32)
+    # division-step inversion (62-bit signed limbs): limb boundaries, both ends of the range, many random values
+    more = [1, 2, L - 1, L - 2, (L + 1) // 2, 2**62 - 1, 2**62, 2**124, 2**186, 2**248, 2**252] + [int(rng.integers(1, 2**62)) << (62 * k) for k in range(4) for _ in range(8)]
+    more += [int.from_bytes(rng.bytes(32), "little") % L or 1 for _ in range(3000)] + [(int.from_bytes(rng.bytes(32), "little") % 2**k) or 1 for k in range(1, 253, 3) for _ in range(3)]
+    for ai in more:
+        assert int.from_bytes(call(hs, "hs_sc_invert_vartime", 32, (ai % L).to_bytes(32, "little"))[1], "little") == pow(ai % L, L - 2, L)
 
 
 def test_ristretto(hs, oracle):
