@@ -563,7 +563,15 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
             ta.ts = d_ts.as<transcript>(); ta.w = d_w2.as<sc_st>(); ta.uprod = d_up.as<sc_st>(); ta.uinvprod = d_up.as<sc_st>() + C; ta.tabB = e.sh->tabB;
             dev_buf d_tscr(sizeof(p3_st) * 512 * (size_t)C, q); ta.scratch = d_tscr.as<p3_st>();
             ta.out = d_proofs.as<uint8_t>() + 224 + 64 * (size_t)round; ta.out_stride = (uint32_t)plen; ta.F = Ft;
+            static const bool tail_dbg = getenv("ROFL_TAIL_DBG") != nullptr;
+            dev_buf d_tdbg(tail_dbg ? 8 * 8 * sizeof(long long) : 16, q);
+            if (tail_dbg) { rt_memset(d_tdbg.p, 0, 8 * 8 * sizeof(long long), q.small()); ta.dbg = d_tdbg.as<long long>(); }
             LAUNCH_COOP(k_ipp_tail, dim3(C), dim3(TAIL_THREADS), q.small(), ta);
+            if (tail_dbg) {
+                long long h[64]; rt_d2h(h, d_tdbg.p, sizeof(h), q.small()); rt_sync(q.small());
+                static const char *nm[7] = {"digits", "c_tree", "table_adds", "point_tree", "chain+compress", "transcript+invert", "folds"};
+                for (int r = 0; r < 8 && h[8 * r]; r++) { fprintf(stderr, "[rofl tail] round %d:", r); for (int k = 0; k < 7; k++) fprintf(stderr, " %s=%lld", nm[k], h[8 * r + k + 1] - h[8 * r + k]); fprintf(stderr, "\n"); }
+            }
             rt_prof_end(PROF_TAIL, tk, q.cur ? q.lo : q.hi);
             tail_done = true;
             break;

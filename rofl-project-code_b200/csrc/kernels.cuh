@@ -37,6 +37,7 @@
 #define KG_BSGS 1
 #define KG_TS 1
 #endif
+#include "wtranscript.cuh"
 
 // a point operand that is either a fixed generator (niels) or a variable point (p3)
 // the sign is applied to the operand (swap y+x / y-x, negate 2dxy resp. X and T) so that lanes of a warp with different
@@ -1584,8 +1585,14 @@ struct tail_args {
     p3_st *scratch;                          // [C][512] partial sums
     uint8_t *out; uint32_t out_stride;
     uint32_t F;
+    long long *dbg;                          // diagnostic (ROFL_TAIL_DBG): clock64 of block 0 at the 8 phase boundaries of every round
 };
 #ifdef KG_FOLD
+#if defined(__CUDA_ARCH__)
+#define TAIL_STAMP(k) do { if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[8 * round + (k)] = clock64(); } while (0)
+#else
+#define TAIL_STAMP(k) do { } while (0)
+#endif
 KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
     __shared__ sc_st sa[TAIL_MAX_F], sb[TAIL_MAX_F], sy[TAIL_MAX_F], scg[TAIL_MAX_F], sch[TAIL_MAX_F], red[64], sfac[3];
     __shared__ p3_st ptB[2];
@@ -1600,8 +1607,16 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
         sa[i] = a.a[(size_t)c * a.N + i]; sb[i] = a.b[(size_t)c * a.N + i]; sy[i] = a.yinv[(size_t)c * a.N + i];
     }
     if (tid == 0) { sc one; sc_from_u64(one, 1); st_sc(scg, one); st_sc(sch, one); }
-    transcript t; sc up, uip, wc;
-    if (tid == 0) { t = a.ts[c]; ld_sc(up, a.uprod + c); ld_sc(uip, a.uinvprod + c); }
+    sc up, uip, wc;
+#ifdef ROFL_EMUL
+    transcript t;                                                      // (the emulation's warp barrier is the block barrier: one lane runs the transcript there)
+    if (tid == 0) t = a.ts[c];
+#else
+    __shared__ strobe_sh hts;                                          // the transcript is run by warp 0 (wtranscript.cuh)
+    wts wt = {0, 0, 0};
+    if (tid < TS_THREADS) wt_load(hts, wt, tid, a.ts[c]);
+#endif
+    if (tid == 0) { ld_sc(up, a.uprod + c); ld_sc(uip, a.uinvprod + c); }
     if (tid >= tB) ld_sc(wc, a.w + c);
     uint8_t *out = a.out + (size_t)c * a.out_stride;
     // accumulation role: side (L / R), digit position, group
@@ -1609,6 +1624,7 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
     __syncthreads();
     int round = 0;
     for (uint32_t np = F >> 1; np >= 1; np >>= 1, round++) {
+        TAIL_STAMP(0);
         // c_L = <a^_lo, b^_hi>, c_R = <a^_hi, b^_lo>
         if (tid < 64) {
             sc v; sc_0(v);
@@ -1628,30 +1644,54 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
             side_of[p] = toL ? 0 : 1;
         }
         __syncthreads();
+        TAIL_STAMP(1);
         for (int s2 = 16; s2 > 0; s2 >>= 1) {
             if (tid < 64 && (tid & 31) < s2) { sc x, y; ld_sc(x, red + tid); ld_sc(y, red + tid + s2); sc_add(x, x, y); st_sc(red + tid, x); }
             __syncthreads();
         }
+        TAIL_STAMP(2);
         if (tid < 512) {
             // pairs (point, octant) of my side, strided over the 32 groups of my (side, position)
+            // the F points of my side (G" blocks with h = 1 and H" blocks with h = 0 feed L, the others R) x 8 octants, dealt to the 32 lanes of
+            // my (side, position): 16 pairs each in every round (striding over ALL points and skipping the other side's left half of the lanes
+            // idle once np < 4: the last two rounds took twice as long)
             ge_p3 acc; ge_p3_0(acc);
-            for (uint32_t pr = a_g; pr < NP * FRZ_Q; pr += 32) {
-                const uint32_t p = pr / FRZ_Q, q = pr % FRZ_Q;
-                if (side_of[p] != a_side) continue;
+            for (uint32_t pr = a_g; pr < F * FRZ_Q; pr += 32) {
+                const uint32_t idx = pr / FRZ_Q, q = pr % FRZ_Q;
+                const bool isH = idx >= F / 2; const uint32_t tt = isH ? idx - F / 2 : idx;
+                const uint32_t hsel = isH ? a_side : 1 - a_side;
+                const uint32_t j = ((tt / np) * 2 + hsel) * np + tt % np, p = isH ? F + j : j;
                 const int d = dig[p][8 * q + a_pos];
                 if (d != 0) acc_add_cached(acc, T + ((size_t)p * FRZ_Q + q) * FRZ_E + (d > 0 ? d : -d) - 1, d < 0);
             }
+#ifdef ROFL_EMUL
             st_p3(pts + tid, acc);
+#else
+            // 32-way sum of my (side, position) = my warp: shuffle tree, no memory round trips and no block barriers
+            for (int s2 = 16; s2 > 0; s2 >>= 1) {
+                ge_p3 y;
+                for (int k = 0; k < 8; k++) {
+                    y.X.v[k] = __shfl_down_sync(0xffffffffu, acc.X.v[k], s2); y.Y.v[k] = __shfl_down_sync(0xffffffffu, acc.Y.v[k], s2);
+                    y.Z.v[k] = __shfl_down_sync(0xffffffffu, acc.Z.v[k], s2); y.T.v[k] = __shfl_down_sync(0xffffffffu, acc.T.v[k], s2);
+                }
+                ge_add(acc, acc, y);
+            }
+            if (a_g == 0) st_p3(pts + tid, acc);
+#endif
         } else if (tid == tB || tid == tB + 1) {
             sc s; ld_sc(s, red + 32 * (tid - tB)); sc_mul(s, s, wc);
             ge_p3 r; ge_p3_0(r); fb_mul_acc(r, a.tabB, s, 32);
             st_p3(ptB + (tid - tB), r);
         }
         __syncthreads();
+        TAIL_STAMP(3);
+#ifdef ROFL_EMUL
         for (uint32_t s2 = 16; s2 > 0; s2 >>= 1) {          // 32-way tree inside every (side, position) group
             if (tid < 512 && a_g < s2) { ge_p3 x, y; ld_p3(x, pts + tid); ld_p3(y, pts + tid + s2); ge_add(x, x, y); st_p3(pts + tid, x); }
             __syncthreads();
         }
+#endif
+        TAIL_STAMP(4);
         if (tid == 0 || tid == 256) {                        // 16^pos chain of my side, + c w B, compress
             const int lr = tid ? 1 : 0;
             ge_p3 h; ld_p3(h, pts + tid + 7 * 32);
@@ -1661,17 +1701,31 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
             for (int k = 0; k < 32; k++) out[64 * round + 32 * lr + k] = enc[k];
         }
         __syncthreads();
+        TAIL_STAMP(5);
+#ifndef ROFL_EMUL
+        sc u;
+        if (tid < TS_THREADS) {
+            wt_load32(hts, tid, out + 64 * round); wt_append(hts, wt, tid, "L", hts.io, 32);
+            wt_load32(hts, tid, out + 64 * round + 32); wt_append(hts, wt, tid, "R", hts.io, 32);
+            wt_challenge_sc(hts, wt, tid, "u", u);
+        }
+#endif
         if (tid == 0) {
+            sc ui, u2, ui2, sH, ynp;
+#ifdef ROFL_EMUL
+            sc u;
             uint8_t lrb[64]; for (int k = 0; k < 64; k++) lrb[k] = out[64 * round + k];
             transcript_append(t, "L", lrb, 32); transcript_append(t, "R", lrb + 32, 32);
             uint8_t ub[64]; transcript_challenge(t, "u", ub, 64);
-            sc u, ui, u2, ui2, sH, ynp;
-            sc_from_bytes_wide(u, ub); sc_invert_vartime(ui, u);
+            sc_from_bytes_wide(u, ub);
+#endif
+            sc_invert_vartime(ui, u);
             sc_mul(u2, u, u); sc_mul(ui2, ui, ui); ld_sc(ynp, sy + np); sc_mul(sH, ui2, ynp);          // u^-2 y^-np
             sc_mul(up, up, u); sc_mul(uip, uip, ui);
             st_sc(sfac, u2); st_sc(sfac + 1, ui2); st_sc(sfac + 2, sH);
         }
         __syncthreads();
+        TAIL_STAMP(6);
         // fold a^ / b^ and extend the coefficient tables: c'[2t] = c[t], c'[2t+1] = c[t] * s
         sc cgv, chv; const uint32_t nblk = F / (2 * np);
         if ((uint32_t)tid < nblk) { ld_sc(cgv, scg + tid); ld_sc(chv, sch + tid); }
@@ -1687,6 +1741,7 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
             ld_sc(f, sfac + 2); sc_mul(x, chv, f); st_sc(sch + 2 * tid, chv); st_sc(sch + 2 * tid + 1, x);
         }
         __syncthreads();
+        TAIL_STAMP(7);
     }
     if (tid == 0) {            // a = a^ prod u_k, b = b^ prod u_k^-1
         sc x, y; ld_sc(x, sa); ld_sc(y, sb); sc_mul(x, x, up); sc_mul(y, y, uip);
