@@ -74,6 +74,8 @@ void rofl_range_proof_shape(size_t D, int range, size_t n_partition, size_t *n_p
 /* self test of the device field arithmetic (GF(2^255-19), curve25519-dalek-ng FieldElement semantics): n raw 256-bit inputs,
  * out = n x 6 x 32 canonical encodings of a*b, a^2, a+b, a-b, (a+b)(a-b), 1/a */
 int rofl_field_selftest(rofl_ctx *, const uint8_t *a32, const uint8_t *b32, size_t n, uint8_t *out);
+/* out: n x 96 bytes = a*b mod l for RAW 256-bit a, b | (a mod l)^-1 (division steps) | (a mod l)^-1 (Fermat); 0 for a = 0 */
+int rofl_scalar_selftest(rofl_ctx *, const uint8_t *a32, const uint8_t *b32, size_t n, uint8_t *out);
 int rofl_f32_to_scalar_vec(rofl_ctx *, const float *v, size_t D, int n_bits, int frac, uint8_t *out_scalars32);       /* conversion32.rs:11-22 */
 int rofl_scalar_to_f32_vec(rofl_ctx *, const uint8_t *scalars32, size_t D, int n_bits, int frac, float *out);         /* conversion32.rs:24-38 */
 void rofl_clip_bounds(int range, int n_bits, int frac, float *mn, float *mx);                                        /* conversion32.rs:56-60 */

@@ -18,6 +18,7 @@ _SIGS = {
     "rofl_range_proof_len": (c_sz, [c_sz]),
     "rofl_range_proof_shape": (None, [c_sz, C.c_int, c_sz, C.POINTER(c_sz), C.POINTER(c_sz)]),
     "rofl_field_selftest": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz, c_u8p]),
+    "rofl_scalar_selftest": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz, c_u8p]),
     "rofl_f32_to_scalar_vec": (C.c_int, [c_vp, c_f32p, c_sz, C.c_int, C.c_int, c_u8p]),
     "rofl_scalar_to_f32_vec": (C.c_int, [c_vp, c_u8p, c_sz, C.c_int, C.c_int, c_f32p]),
     "rofl_clip_bounds": (None, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -134,6 +135,14 @@ class Api:
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8); n = a.shape[0]
         out = np.zeros((n, 6, 32), np.uint8)
         rc = self.lib.rofl_field_selftest(self.h, _ptr(a), _ptr(b), n, _ptr(out))
+        if rc != 0:
+            raise self._err(rc)
+        return out
+
+    def scalar_selftest(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8); n = a.shape[0]
+        out = np.zeros((n, 3, 32), np.uint8)
+        rc = self.lib.rofl_scalar_selftest(self.h, _ptr(a), _ptr(b), n, _ptr(out))
         if rc != 0:
             raise self._err(rc)
         return out

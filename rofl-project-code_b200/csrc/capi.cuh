@@ -75,6 +75,17 @@ extern "C" int rofl_field_selftest(rofl_ctx *c, const uint8_t *a32, const uint8_
     return 0;
     API_CATCH
 }
+// device scalar-arithmetic self test (a32, b32: n raw 256-bit values; out: n x 3 x 32: a*b mod l, (a mod l)^-1 by division steps and by Fermat)
+extern "C" int rofl_scalar_selftest(rofl_ctx *c, const uint8_t *a32, const uint8_t *b32, size_t n, uint8_t *out) {
+    API_TRY
+    if (!n) return 0;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
+    staged_in da(a32, 32 * n, s), db(b32, 32 * n, s); dev_buf o(96 * n, s);
+    LAUNCH(k_scalar_selftest, dim3((unsigned)((n + 127) / 128)), dim3(128), s, o.as<uint8_t>(), da.b.as<uint8_t>(), db.b.as<uint8_t>(), n);
+    rt_d2h(out, o.p, 96 * n, s); rt_sync(s);
+    return 0;
+    API_CATCH
+}
 extern "C" int rofl_f32_to_scalar_vec(rofl_ctx *c, const float *v, size_t D, int n_bits, int frac, uint8_t *out) {
     API_TRY
     if (!fp_ok(n_bits, frac)) return ROFL_ERR_ARGS;

@@ -182,6 +182,19 @@ KERNEL void LB(128, 1) k_field_selftest(uint8_t *out, const uint8_t *a32, const 
     fe_invert(r, a); fe_tobytes(o + 160, r);
 }
 KLAUNCH(k_field_selftest, false, (uint8_t *out, const uint8_t *a32, const uint8_t *b32, size_t n), (out, a32, b32, n))
+// scalar arithmetic mod l as the device computes it: a*b for RAW 256-bit a, b (sc_mul's fold reduction), (a mod l)^-1 by division steps, a^-1 by Fermat
+KERNEL void LB(128, 1) k_scalar_selftest(uint8_t *out, const uint8_t *a32, const uint8_t *b32, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sc a, b, r;
+    sc_frombytes(a, a32 + 32 * i); sc_frombytes(b, b32 + 32 * i);
+    uint8_t *o = out + 96 * i;
+    sc_mul(r, a, b); sc_tobytes(o, r);
+    sc am; sc_from_bytes_mod_order(am, a32 + 32 * i);
+    sc_invert_vartime(r, am); sc_tobytes(o + 32, r);
+    sc_invert(r, am); sc_tobytes(o + 64, r);
+}
+KLAUNCH(k_scalar_selftest, false, (uint8_t *out, const uint8_t *a32, const uint8_t *b32, size_t n), (out, a32, b32, n))
 #endif
 
 // ===================================================================================================================
@@ -1151,6 +1164,7 @@ void launch_k_fb_table_build(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *tab, c
 void launch_k_gens_build(dim3 g_, dim3 b_, cudaStream_t s_, niels_st *G, niels_st *H, int n, int party_begin, int party_end);
 void launch_k_commit(dim3 g_, dim3 b_, cudaStream_t s_, commit_args a);
 void launch_k_field_selftest(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const uint8_t *a32, const uint8_t *b32, size_t n);
+void launch_k_scalar_selftest(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const uint8_t *a32, const uint8_t *b32, size_t n);
 void launch_k_nonces(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *sLR, const uint32_t *keys, int n, int m, size_t total);
 void launch_k_party_sums(dim3 g_, dim3 b_, cudaStream_t s_, sc_st *partial, const uint32_t *keys, const sc_st *blind, const sc_st *z, pow_tab ztab, int n, int m, int phase);
 void launch_k_bits_sum(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *partial, const uint64_t *vals, const niels_st *G, const niels_st *H, int n, int m);

@@ -70,10 +70,54 @@ HDNI void sc_montmul(uint32_t r[8], const uint32_t a[8], const uint32_t b[8]) {
     sc_cond_sub_l(t, t[8]);
     for (int i = 0; i < 8; i++) r[i] = t[i];
 }
+#if defined(__CUDA_ARCH__)
+// Device: the 512-bit product by the field's row-wise IMAD.WIDE routine, then l = 2^252 + c (c < 2^125) folded twice:
+//   x = xl + 2^252 xh  ==  xl - c xh;   c xh = p1l + 2^252 p1h  ==  p1l - c p1h   =>   x == xl - p1l + c p1h  in (-2^252, 2^253)
+// 64 + 32 + 16 multiplications instead of the 256 of two Montgomery passes (measured, one lane: 3683 -> ~900 cycles).
+__device__ __forceinline__ void sc_mul_small(uint32_t *out, const uint32_t *cw, const uint32_t *x, int nx) {      // out[0 .. nx+4) = c[0..4) * x[0..nx)
+    for (int i = 0; i < nx + 4; i++) out[i] = 0;
+    for (int i = 0; i < 4; i++) {
+        uint32_t carry = 0;
+        for (int j = 0; j < nx; j++) {
+            const uint64_t acc = (uint64_t)cw[i] * x[j] + out[i + j] + carry;
+            out[i + j] = (uint32_t)acc; carry = (uint32_t)(acc >> 32);
+        }
+        out[i + nx] = carry;
+    }
+}
+__device__ __forceinline__ void sc_mul_dev(sc &r, const sc &a, const sc &b) {        // any 256-bit a, b
+    uint32_t t[16];
+    { fe fa, fb; for (int i = 0; i < 8; i++) { fa.v[i] = a.v[i]; fb.v[i] = b.v[i]; } fe_mul_rows(t, fa, fb); }
+    uint32_t cw[4]; for (int i = 0; i < 4; i++) cw[i] = SC_L_[i];
+    uint32_t xh[9], p1[13], p1h[5], p2[9];
+    for (int i = 0; i < 8; i++) xh[i] = (t[7 + i] >> 28) | (t[8 + i] << 4);
+    xh[8] = t[15] >> 28;
+    sc_mul_small(p1, cw, xh, 9);                                  // < 2^385
+    for (int i = 0; i < 5; i++) p1h[i] = (p1[7 + i] >> 28) | (7 + i + 1 < 13 ? p1[8 + i] << 4 : 0);
+    sc_mul_small(p2, cw, p1h, 5);                                 // < 2^258
+    const uint32_t p2h = (p2[7] >> 28) | (p2[8] << 4);            // < 2^6:  p2 == p2l - c p2h
+    int64_t acc = 0; uint32_t o[8];
+    uint64_t cp = 0;                                              // running c * p2h
+    for (int i = 0; i < 8; i++) {
+        const uint32_t xl = i < 7 ? t[i] : (t[7] & 0x0fffffffu), pl = i < 7 ? p1[i] : (p1[7] & 0x0fffffffu), ql = i < 7 ? p2[i] : (p2[7] & 0x0fffffffu);
+        if (i < 4) cp += (uint64_t)cw[i] * p2h;
+        acc += (int64_t)xl - (int64_t)pl + (int64_t)ql - (int64_t)(uint32_t)cp;
+        cp >>= 32;
+        o[i] = (uint32_t)acc; acc >>= 32;
+    }
+    for (int k = 0; k < 2 && acc < 0; k++) { uint64_t c = 0; for (int i = 0; i < 8; i++) { c += (uint64_t)o[i] + SC_L_[i]; o[i] = (uint32_t)c; c >>= 32; } acc += (int64_t)c; }
+    sc_cond_sub_l(o);
+    for (int i = 0; i < 8; i++) r.v[i] = o[i];
+}
+#endif
 HD void sc_mul(sc &r, const sc &a, const sc &b) {
+#if defined(__CUDA_ARCH__)
+    sc_mul_dev(r, a, b);
+#else
     uint32_t t[8];
     sc_montmul(t, a.v, b.v);          // a b / R
     sc_montmul(r.v, t, SC_R2_);       // a b
+#endif
 }
 HD void sc_muladd(sc &r, const sc &a, const sc &b, const sc &c) { sc t; sc_mul(t, a, b); sc_add(r, t, c); }
 HD void sc_sq(sc &r, const sc &a) { sc_mul(r, a, a); }

@@ -44,6 +44,22 @@ def test_field_arithmetic_device_paths(api):
         assert got == exp, (i, hex(x), hex(y), [hex(g) for g in got], [hex(e) for e in exp])
 
 
+def test_device_scalar_arithmetic_against_python_integers(api):
+    """sc_mul's fold reduction (any 256-bit operands) and the division-step inversion, as compiled for the device, against Python integers."""
+    L = 2**252 + 27742317777372353535851937790883648493
+    rng = np.random.default_rng(11)
+    edge = [0, 1, 2, L - 1, L, L + 1, 2 * L - 1, 2 * L, 2**252 - 1, 2**252, 2**253 - 1, 2**255 - 19, 2**256 - 1, 2**256 - 2**224, 2**124, 2**125 - 1, 2**62, 2**186]
+    vals_a = [x for x in edge for _ in edge] + [int.from_bytes(rng.bytes(32), "little") for _ in range(6000)] + [int.from_bytes(rng.bytes(32), "little") % L for _ in range(2000)]
+    vals_b = [y for _ in edge for y in edge] + [int.from_bytes(rng.bytes(32), "little") for _ in range(6000)] + [int.from_bytes(rng.bytes(32), "little") % L for _ in range(2000)]
+    a = np.frombuffer(b"".join(x.to_bytes(32, "little") for x in vals_a), np.uint8).reshape(-1, 32)
+    b = np.frombuffer(b"".join(x.to_bytes(32, "little") for x in vals_b), np.uint8).reshape(-1, 32)
+    out = api.scalar_selftest(a, b)
+    for i, (x, y) in enumerate(zip(vals_a, vals_b)):
+        inv = pow(x % L, L - 2, L)
+        got = [int.from_bytes(out[i, k].tobytes(), "little") for k in range(3)]
+        assert got == [x * y % L, inv, inv], (i, hex(x), hex(y), [hex(g) for g in got])
+
+
 def test_commit_conversion_parity(api, oracle):
     rng = np.random.default_rng(0)
     v = np.concatenate([rng.uniform(-300, 300, 2000), [0.0, -0.0, 0.25, -1.5, 600.0, -600.0, 0.5 / 128, 1.5 / 128]]).astype(np.float32)
