@@ -67,6 +67,8 @@ struct rofl_engine {
     int use_rt = 1;                       // 0: never build generator tables (generic Pippenger / fold path only)
     int rt_unfold = 4;                    // IPP rounds computed over the original generators before the catch-up fold
     int tail_np = 32;                     // IPP rounds with half-size <= tail_np run in the fused on-device tail kernel (0 = off)
+    int tail_ncta = 2;                    // thread blocks (one cluster) per chunk in the tail kernel: 1, 2, 4, 8.  Measured with three chunk groups: 2 -> 36.15 ms,
+                                          // 1 -> 36.35, 4 -> 38.1 (a 4-block cluster of 544-thread blocks waits for room beside the other groups' bulk kernels)
     std::mutex pin_mu; std::vector<std::pair<void *, size_t>> pins;      // pool of pinned host blocks
     int use_frz = 1;                      // middle IPP rounds over frozen generators with on-the-fly Straus tables (kernels.cuh K6c)
     int rt_bits = RT_MAX_BITS;            // widest generator-table radix to try (8..11)
@@ -564,13 +566,20 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
             dev_buf d_tscr(sizeof(p3_st) * 512 * (size_t)C, q); ta.scratch = d_tscr.as<p3_st>();
             ta.out = d_proofs.as<uint8_t>() + 224 + 64 * (size_t)round; ta.out_stride = (uint32_t)plen; ta.F = Ft;
             static const bool tail_dbg = getenv("ROFL_TAIL_DBG") != nullptr;
-            dev_buf d_tdbg(tail_dbg ? 8 * 8 * sizeof(long long) : 16, q);
-            if (tail_dbg) { rt_memset(d_tdbg.p, 0, 8 * 8 * sizeof(long long), q.small()); ta.dbg = d_tdbg.as<long long>(); }
-            LAUNCH_COOP(k_ipp_tail, dim3(C), dim3(TAIL_THREADS), q.small(), ta);
+            dev_buf d_tdbg(tail_dbg ? 128 * sizeof(long long) : 16, q);
+            if (tail_dbg) { rt_memset(d_tdbg.p, 0, 128 * sizeof(long long), q.small()); ta.dbg = d_tdbg.as<long long>(); }
+#ifdef ROFL_EMUL
+            ta.ncta = 1;
+#else
+            ta.ncta = (uint32_t)e.tail_ncta;
+#endif
+            dev_buf d_gfac(sizeof(sc_st) * 3 * (size_t)C, q); ta.gfac = d_gfac.as<sc_st>();
+            LAUNCH_COOP(k_ipp_tail, dim3((unsigned)(C * ta.ncta)), dim3(TAIL_THREADS), q.small(), ta);
             if (tail_dbg) {
-                long long h[64]; rt_d2h(h, d_tdbg.p, sizeof(h), q.small()); rt_sync(q.small());
+                long long h[128]; rt_d2h(h, d_tdbg.p, sizeof(h), q.small()); rt_sync(q.small());
                 static const char *nm[7] = {"digits", "c_tree", "table_adds", "point_tree", "chain+compress", "transcript+invert", "folds"};
                 for (int r = 0; r < 8 && h[8 * r]; r++) { fprintf(stderr, "[rofl tail] round %d:", r); for (int k = 0; k < 7; k++) fprintf(stderr, " %s=%lld", nm[k], h[8 * r + k + 1] - h[8 * r + k]); fprintf(stderr, "\n"); }
+                fprintf(stderr, "[rofl tail] round 2, per warp (table loop, shuffle tree):"); for (int w = 0; w < 16; w++) fprintf(stderr, " (%lld, %lld)", h[64 + 2 * w], h[64 + 2 * w + 1]); fprintf(stderr, "  c w B threads: %lld\n", h[96]);
             }
             rt_prof_end(PROF_TAIL, tk, q.cur ? q.lo : q.hi);
             tail_done = true;

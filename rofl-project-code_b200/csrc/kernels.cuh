@@ -1599,6 +1599,8 @@ struct tail_args {
     p3_st *scratch;                          // [C][512] partial sums
     uint8_t *out; uint32_t out_stride;
     uint32_t F;
+    uint32_t ncta;                           // blocks (= cluster size) per chunk: 1, 2, 4 or 8
+    sc_st *gfac;                             // [C][3] the round's fold factors, leader -> the other blocks of the cluster
     long long *dbg;                          // diagnostic (ROFL_TAIL_DBG): clock64 of block 0 at the 8 phase boundaries of every round
 };
 #ifdef KG_FOLD
@@ -1607,15 +1609,26 @@ struct tail_args {
 #else
 #define TAIL_STAMP(k) do { } while (0)
 #endif
+#if defined(__CUDA_ARCH__)
+#define TAIL_CSYNC() do { if (ncta > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); else __syncthreads(); } while (0)
+#else
+#define TAIL_CSYNC() __syncthreads()
+#endif
 KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
     __shared__ sc_st sa[TAIL_MAX_F], sb[TAIL_MAX_F], sy[TAIL_MAX_F], scg[TAIL_MAX_F], sch[TAIL_MAX_F], red[64], sfac[3];
     __shared__ p3_st ptB[2];
     __shared__ int8_t dig[2 * TAIL_MAX_F][64];
     __shared__ uint8_t side_of[2 * TAIL_MAX_F];                         // 0: the point feeds L this round, 1: R
-    const int c = blockIdx.x, tid = threadIdx.x;
+    // a.ncta blocks (one thread-block cluster) per chunk: the table sums of a round are dealt to all of them, block 0 (the leader) runs the
+    // serial part -- chains, compression, transcript -- and publishes the round's three fold factors; every block keeps its own copy of the
+    // scalar vectors and folds it.  Two cluster barriers per round order the exchanges through global memory.
+    const uint32_t ncta = a.ncta, rank = blockIdx.x % ncta;
+    const int c = blockIdx.x / ncta, tid = threadIdx.x;
+    const bool leader = rank == 0;
     const uint32_t F = a.F, NP = 2 * F;
     const int tB = 512;                                                // lanes 0 / 1 of the last warp: the c_L w B and c_R w B terms
-    p3_st *pts = a.scratch + (size_t)c * 512;
+    p3_st *pts = a.scratch + (size_t)c * 512;                          // [16 warps][32]: slot 32 w + r = warp w's sum of block r
+    sc_st *gfac = a.gfac + 3 * (size_t)c;
     const p3_st *T = a.T + (size_t)c * NP * FRZ_Q * FRZ_E;
     for (uint32_t i = tid; i < F; i += TAIL_THREADS) {
         sa[i] = a.a[(size_t)c * a.N + i]; sb[i] = a.b[(size_t)c * a.N + i]; sy[i] = a.yinv[(size_t)c * a.N + i];
@@ -1628,9 +1641,9 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
 #else
     __shared__ strobe_sh hts;                                          // the transcript is run by warp 0 (wtranscript.cuh)
     wts wt = {0, 0, 0};
-    if (tid < TS_THREADS) wt_load(hts, wt, tid, a.ts[c]);
+    if (leader && tid < TS_THREADS) wt_load(hts, wt, tid, a.ts[c]);
 #endif
-    if (tid == 0) { ld_sc(up, a.uprod + c); ld_sc(uip, a.uinvprod + c); }
+    if (leader && tid == 0) { ld_sc(up, a.uprod + c); ld_sc(uip, a.uinvprod + c); }
     if (tid >= tB) ld_sc(wc, a.w + c);
     uint8_t *out = a.out + (size_t)c * a.out_stride;
     // accumulation role: side (L / R), digit position, group
@@ -1664,13 +1677,16 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
             __syncthreads();
         }
         TAIL_STAMP(2);
+        ge_p3 acc; ge_p3_0(acc);
+#ifndef ROFL_EMUL
+        long long w_t0 = 0, w_t1 = 0; if (a.dbg) w_t0 = clock64();
+#endif
         if (tid < 512) {
             // pairs (point, octant) of my side, strided over the 32 groups of my (side, position)
             // the F points of my side (G" blocks with h = 1 and H" blocks with h = 0 feed L, the others R) x 8 octants, dealt to the 32 lanes of
             // my (side, position): 16 pairs each in every round (striding over ALL points and skipping the other side's left half of the lanes
             // idle once np < 4: the last two rounds took twice as long)
-            ge_p3 acc; ge_p3_0(acc);
-            for (uint32_t pr = a_g; pr < F * FRZ_Q; pr += 32) {
+            for (uint32_t pr = rank * 32 + a_g; pr < F * FRZ_Q; pr += 32 * ncta) {
                 const uint32_t idx = pr / FRZ_Q, q = pr % FRZ_Q;
                 const bool isH = idx >= F / 2; const uint32_t tt = isH ? idx - F / 2 : idx;
                 const uint32_t hsel = isH ? a_side : 1 - a_side;
@@ -1681,6 +1697,7 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
 #ifdef ROFL_EMUL
             st_p3(pts + tid, acc);
 #else
+            if (a.dbg) w_t1 = clock64();
             // 32-way sum of my (side, position) = my warp: shuffle tree, no memory round trips and no block barriers
             for (int s2 = 16; s2 > 0; s2 >>= 1) {
                 ge_p3 y;
@@ -1690,14 +1707,48 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
                 }
                 ge_add(acc, acc, y);
             }
-            if (a_g == 0) st_p3(pts + tid, acc);
+            if (a_g == 0) st_p3(pts + tid + rank, acc);
+            if (a.dbg && blockIdx.x == 0 && a_g == 0 && round == 2) { a.dbg[64 + 2 * (tid >> 5)] = w_t1 - w_t0; a.dbg[64 + 2 * (tid >> 5) + 1] = clock64() - w_t1; }
 #endif
-        } else if (tid == tB || tid == tB + 1) {
+        } else if (leader) {
+#ifdef ROFL_EMUL
+          if (tid == tB || tid == tB + 1) {
             sc s; ld_sc(s, red + 32 * (tid - tB)); sc_mul(s, s, wc);
             ge_p3 r; ge_p3_0(r); fb_mul_acc(r, a.tabB, s, 32);
             st_p3(ptB + (tid - tB), r);
+          }
+#else
+            // c_L w B and c_R w B by the whole spare warp: lane i takes radix-256 window i (one table entry), shuffle tree over the 32 windows.
+            // (One lane walking the 32 windows was the longest path of this phase: 250-370 k cycles beside 16 busy warps.)
+            const int ln = tid - tB;
+            for (int lr = 0; lr < 2; lr++) {
+                sc s; ld_sc(s, red + 32 * lr); sc_mul(s, s, wc);
+                int16_t d[32]; sc_radix256(d, s);
+                int di = 0;
+#pragma unroll
+                for (int i = 0; i < 32; i++) if (i == ln) di = d[i];
+                ge_p3 r; ge_p3_0(r);
+                if (di != 0) { ge_niels n; ld_niels(n, a.tabB + ln * FB_ENTRIES + (di > 0 ? di : -di) - 1); ge_madd_signed(r, r, n, di < 0); }
+                for (int s2 = 16; s2 > 0; s2 >>= 1) {
+                    ge_p3 y;
+                    for (int k = 0; k < 8; k++) {
+                        y.X.v[k] = __shfl_down_sync(0xffffffffu, r.X.v[k], s2); y.Y.v[k] = __shfl_down_sync(0xffffffffu, r.Y.v[k], s2);
+                        y.Z.v[k] = __shfl_down_sync(0xffffffffu, r.Z.v[k], s2); y.T.v[k] = __shfl_down_sync(0xffffffffu, r.T.v[k], s2);
+                    }
+                    ge_add(r, r, y);
+                }
+                if (ln == 0) st_p3(ptB + lr, r);
+            }
+#endif
+#ifndef ROFL_EMUL
+            if (a.dbg && blockIdx.x == 0 && tid == tB && round == 2) a.dbg[64 + 32] = clock64() - w_t0;
+#endif
         }
-        __syncthreads();
+        TAIL_CSYNC();
+        if (ncta > 1) {                                       // the leader adds up the blocks' partial sums of every (side, position)
+            if (leader && tid < 512 && a_g == 0) { for (uint32_t r = 1; r < ncta; r++) { ge_p3 y; ld_p3(y, pts + tid + r); ge_add(acc, acc, y); } st_p3(pts + tid, acc); }
+            __syncthreads();
+        }
         TAIL_STAMP(3);
 #ifdef ROFL_EMUL
         for (uint32_t s2 = 16; s2 > 0; s2 >>= 1) {          // 32-way tree inside every (side, position) group
@@ -1706,7 +1757,7 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
         }
 #endif
         TAIL_STAMP(4);
-        if (tid == 0 || tid == 256) {                        // 16^pos chain of my side, + c w B, compress
+        if (leader && (tid == 0 || tid == 256)) {            // 16^pos chain of my side, + c w B, compress
             const int lr = tid ? 1 : 0;
             ge_p3 h; ld_p3(h, pts + tid + 7 * 32);
             for (int w = 6; w >= 0; w--) { for (int k = 0; k < 4; k++) ge_p3_dbl(h, h); acc_add_p3(h, pts + tid + w * 32, false); }
@@ -1718,13 +1769,13 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
         TAIL_STAMP(5);
 #ifndef ROFL_EMUL
         sc u;
-        if (tid < TS_THREADS) {
+        if (leader && tid < TS_THREADS) {
             wt_load32(hts, tid, out + 64 * round); wt_append(hts, wt, tid, "L", hts.io, 32);
             wt_load32(hts, tid, out + 64 * round + 32); wt_append(hts, wt, tid, "R", hts.io, 32);
             wt_challenge_sc(hts, wt, tid, "u", u);
         }
 #endif
-        if (tid == 0) {
+        if (leader && tid == 0) {
             sc ui, u2, ui2, sH, ynp;
 #ifdef ROFL_EMUL
             sc u;
@@ -1737,8 +1788,10 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
             sc_mul(u2, u, u); sc_mul(ui2, ui, ui); ld_sc(ynp, sy + np); sc_mul(sH, ui2, ynp);          // u^-2 y^-np
             sc_mul(up, up, u); sc_mul(uip, uip, ui);
             st_sc(sfac, u2); st_sc(sfac + 1, ui2); st_sc(sfac + 2, sH);
+            if (ncta > 1) { st_sc(gfac, u2); st_sc(gfac + 1, ui2); st_sc(gfac + 2, sH); }
         }
-        __syncthreads();
+        TAIL_CSYNC();
+        if (ncta > 1) { if (!leader && tid < 3) sfac[tid] = gfac[tid]; __syncthreads(); }
         TAIL_STAMP(6);
         // fold a^ / b^ and extend the coefficient tables: c'[2t] = c[t], c'[2t+1] = c[t] * s
         sc cgv, chv; const uint32_t nblk = F / (2 * np);
@@ -1757,13 +1810,25 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
         __syncthreads();
         TAIL_STAMP(7);
     }
-    if (tid == 0) {            // a = a^ prod u_k, b = b^ prod u_k^-1
+    if (leader && tid == 0) {  // a = a^ prod u_k, b = b^ prod u_k^-1
         sc x, y; ld_sc(x, sa); ld_sc(y, sb); sc_mul(x, x, up); sc_mul(y, y, uip);
         uint8_t e[32]; sc_tobytes(e, x); for (int k = 0; k < 32; k++) out[64 * round + k] = e[k];
         sc_tobytes(e, y); for (int k = 0; k < 32; k++) out[64 * round + 32 + k] = e[k];
     }
 }
+#ifdef ROFL_EMUL
 KLAUNCH(k_ipp_tail, true, (tail_args a), (a))
+#else
+// launched as thread-block clusters of a.ncta blocks (grid = chunks x ncta)
+void launch_k_ipp_tail(dim3 g_, dim3 b_, cudaStream_t s_, tail_args a) {
+    rt_host_timer t_(&rt_host_prof::launch, "k_ipp_tail"); void *tl_ = rt_timeline_begin("k_ipp_tail", s_, g_.x * g_.y * g_.z);
+    cudaLaunchConfig_t cfg = {}; cfg.gridDim = g_; cfg.blockDim = b_; cfg.dynamicSmemBytes = 0; cfg.stream = s_;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = a.ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    rt_check(cudaLaunchKernelEx(&cfg, k_ipp_tail, a), "k_ipp_tail");
+    rt_timeline_end(tl_, s_); rt_count_launch("k_ipp_tail");
+}
+#endif
 // the shared niels generators as extended points (a tail that starts at round 0 freezes the original generators)
 KERNEL void LB(128, 4) k_niels_to_p3(p3_st *Gf, p3_st *Hf, const niels_st *G, const niels_st *H, uint32_t F, uint32_t stride) {
     const int c = blockIdx.y; const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -152,6 +152,7 @@ extern "C" int rofl_ctx_create(rofl_ctx **out, int device) {
         if (const char *gv = getenv("ROFL_RT_BITS")) c->e.rt_bits = std::max(8, std::min(RT_MAX_BITS, atoi(gv)));              // generator-table radix
         if (const char *gv = getenv("ROFL_FRZ")) c->e.use_frz = atoi(gv) != 0;                                            // frozen-level middle rounds
         if (const char *gv = getenv("ROFL_TAIL")) c->e.tail_np = std::max(0, std::min(TAIL_MAX_F / 2, atoi(gv)));    // 0 disables the fused IPP tail
+        if (const char *gv = getenv("ROFL_TAIL_NCTA")) { const int v = atoi(gv); c->e.tail_ncta = v >= 8 ? 8 : v >= 4 ? 4 : v >= 2 ? 2 : 1; }
         engine_init(c->e);
         *out = c;
         return ROFL_OK;
