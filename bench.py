@@ -173,6 +173,26 @@ def extra_configs(api, torch, steps):
         verified_eps=K * D / batch_ms * 1e3, round_eps=K * D / (batch_ms + agg_ms + dlog_ms) * 1e3)
     del msgs, Ls
     api.set_option("trim", 1)
+    # ---- several callers of ONE context (rofl_service proves / verifies several clients per process: bin/basic_client.rs:136-161, server.rs:516-522): every
+    #      caller runs on its own lane of streams, the tables are shared; one chunk group per call, the callers overlap each other's Fiat-Shamir chains
+    import threading
+    w = WORKLOAD; K, R = 3, 4
+    def caller(k, res):
+        vv = np.random.default_rng(500 + k).uniform(-255.9, 255.9, w["D"]).astype(np.float32); bb = api.rnd_scalar_vec(bytes([40 + k]) * 32, w["D"])
+        for it in range(R):
+            rc, pp, cc = api.range_prove(vv, bb, w["range_bits"], w["n_partition"], w["n_bits"], w["frac"], bytes([it + 1]) * 32)
+            res[k] = rc == 0 and api.range_verify(pp, cc, w["range_bits"], seed) == 1
+    res = {}; caller(0, res)                                      # warm-up (generator tables of configs[1] are rebuilt after configs[3] evicted them)
+    api.set_option("groups", 1)
+    ths = [threading.Thread(target=caller, args=(k, res)) for k in range(K)]
+    t0 = time.perf_counter()
+    for t in ths: t.start()
+    for t in ths: t.join()
+    dt = time.perf_counter() - t0
+    api.set_option("groups", int(os.environ.get("BENCH_GROUPS", os.environ.get("ROFL_GROUPS", "3"))))
+    assert all(res.get(k) for k in range(K))
+    out["configs[1] with %d concurrent callers of one context (one lane of streams each, host buffers, Python threads)" % K] = dict(
+        callers=K, D=w["D"], ms_per_prove_verify_per_caller=dt / R * 1e3, e2e_eps=K * R * w["D"] / dt)
     return out
 
 
@@ -201,9 +221,53 @@ def strong_block(api, pkg, torch, dist, rank, world, local):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         res[tag] = tt.tolist()
     tp, tv = res["warm"]
-    return dict(workload="configs[3] resnet18 full: ONE update of 11 689 512 parameters, 8-bit, 64 chunks of 2^18, sharded by chunk over the ranks", scaling="strong", n_gpus=world, D=D,
-                prove_s=tp, verify_s=tv, prove_eps=D / tp, verify_eps=D / tv, e2e_eps=D / (tp + tv), cold_prove_s=res["cold"][0], cold_verify_s=res["cold"][1],
-                collectives="all_gather(proof bytes, commitments) + all_reduce(MIN) of the verdicts over NCCL, inside the timed region; host buffers in and out")
+    out = dict(workload="configs[3] resnet18 full: ONE update of 11 689 512 parameters, 8-bit, 64 chunks of 2^18, sharded by chunk over the ranks", scaling="strong", n_gpus=world, D=D,
+               prove_s=tp, verify_s=tv, prove_eps=D / tp, verify_eps=D / tv, e2e_eps=D / (tp + tv), cold_prove_s=res["cold"][0], cold_verify_s=res["cold"][1],
+               collectives="all_gather(proof bytes, commitments) + all_reduce(MIN) of the verdicts over NCCL, inside the timed region; host buffers in and out")
+    del v, bl, p, c
+    api.set_option("trim", 1)
+    out["server"] = strong_server(api, pkg, torch, dist, rank, world, local)
+    return out
+
+
+def strong_server(api, pkg, torch, dist, rank, world, local):
+    """configs[4] over the ranks: ONE server round of 48 clients x resnet18_intrinsic_50k.  Verification is sharded by CLIENT (every rank checks its
+    contiguous share in one batched call, verdicts MIN-reduced), aggregate + bsgs32 decrypt by PARAMETER range (sharding.decrypt_sharded, the f32
+    slices all-gathered).  Every rank holds all 48 messages, as a server process per GPU fed by the same gRPC stream would."""
+    sh = pkg.sharding
+    K, D = 48, 50000
+    rng = np.random.default_rng(77)
+    bl = api.rnd_scalar_vec(b"\x21" * 32, D)
+    msgs = []
+    for k in range(K):
+        vk = (rng.integers(-24, 25, D) / 128).astype(np.float32)
+        rc, mk = api.enc_l2_compressed_encrypt(vk, bl, 8, 64, 32, 32, 7, bytes([k + 1]) * 32); assert rc == 0
+        msgs.append(mk)
+    Ls = np.stack([x["enc_values"][:, :32].copy() for x in msgs])
+    b, e = sh.split_range(K, world)[rank]
+    dev = torch.device("cuda", local)
+    res = {}
+    for tag in ("cold", "warm"):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ok = api.enc_l2_compressed_verify_batch(msgs[b:e], b"\x0b" * 32) if e > b else np.ones(0, np.int32)
+        good = torch.tensor([int((ok == 1).all())], device=dev, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(good, op=dist.ReduceOp.MIN)
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        rc, f = sh.decrypt_sharded(api, Ls, 1, 1 << 16, 16, 32, 7, dist=dist if world > 1 else None, device=dev)
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+        assert int(good.item()) == 1 and rc == 0 and f.size == D
+        tt = torch.tensor([t1 - t0, t2 - t1], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        res[tag] = tt.tolist()
+    tv, td = res["warm"]
+    return dict(workload="configs[4] server round: 48 clients x resnet18_intrinsic_50k, verification sharded by client, aggregate + bsgs32 decrypt by parameter range",
+                scaling="strong", n_gpus=world, clients=K, D=D, verify_s=tv, aggregate_decrypt_s=td, round_s=tv + td, verified_eps=K * D / tv, round_eps=K * D / (tv + td),
+                collectives="all_reduce(MIN) of the verdicts, all_gather of the decrypted f32 slices over NCCL, inside the timed region")
 
 
 def main():
