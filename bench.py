@@ -157,10 +157,11 @@ def extra_configs(api, torch, steps):
         D=D, prove_ms=prove_ms, verify_ms=verify_ms, cold_prove_ms=cold_ms, prove_eps=D / prove_ms * 1e3, verify_eps=D / verify_ms * 1e3, e2e_eps=D / (prove_ms + verify_ms) * 1e3)
     # ---- configs[4]: server side, 48 clients x configs[2]: batch verification of all 48 messages in one call + homomorphic aggregate + bsgs32 decrypt (table 2^16)
     K = 48
-    msgs = [m]
-    for k in range(1, K):
-        vk = (rng.integers(-24, 25, D) / 128).astype(np.float32)
-        rc, mk = api.enc_l2_compressed_encrypt(vk, bl, 8, 64, 32, 32, 7, bytes([k]) * 32); assert rc == 0
+    bls = api.cancelling_blindings(K, D)                  # the clients' blindings sum to zero, so the aggregate decrypts (pedersen_ops.rs:110-122)
+    msgs, vsum = [], np.zeros(D, np.float64)
+    for k in range(K):
+        vk = (rng.integers(-24, 25, D) / 128).astype(np.float32); vsum += vk
+        rc, mk = api.enc_l2_compressed_encrypt(vk, bls[k], 8, 64, 32, 32, 7, bytes([k + 1]) * 32); assert rc == 0
         msgs.append(mk)
     ok = api.enc_l2_compressed_verify_batch(msgs, seed); assert (ok == 1).all()
     batch_ms = warm(lambda: api.enc_l2_compressed_verify_batch(msgs, seed), 2)
@@ -168,6 +169,7 @@ def extra_configs(api, torch, steps):
     Ls = np.stack([x["enc_values"][:, :32].copy() for x in msgs])
     agg_ms = warm(lambda: api.aggregate(Ls, 1), 3); agg = api.aggregate(Ls, 0)
     dlog_ms = warm(lambda: api.dlog(agg, 1 << 16, 16, 32, 7), 3)
+    rc, _, dec = api.dlog(agg, 1 << 16, 16, 32, 7); assert rc == 0 and (dec == vsum.astype(np.float32)).all()      # the decrypted aggregate is the exact sum
     out["configs[4] server: 48 clients x resnet18_intrinsic_50k -- batch verify + aggregate + bsgs32 decrypt"] = dict(
         clients=K, D=D, verify_batch_ms=batch_ms, verify_one_by_one_ms=one_by_one_ms, aggregate_ms=agg_ms, dlog_ms=dlog_ms, round_ms=batch_ms + agg_ms + dlog_ms,
         verified_eps=K * D / batch_ms * 1e3, round_eps=K * D / (batch_ms + agg_ms + dlog_ms) * 1e3)
@@ -237,11 +239,11 @@ def strong_server(api, pkg, torch, dist, rank, world, local):
     sh = pkg.sharding
     K, D = 48, 50000
     rng = np.random.default_rng(77)
-    bl = api.rnd_scalar_vec(b"\x21" * 32, D)
-    msgs = []
+    bls = api.cancelling_blindings(K, D, 0x60)
+    msgs, vsum = [], np.zeros(D, np.float64)
     for k in range(K):
-        vk = (rng.integers(-24, 25, D) / 128).astype(np.float32)
-        rc, mk = api.enc_l2_compressed_encrypt(vk, bl, 8, 64, 32, 32, 7, bytes([k + 1]) * 32); assert rc == 0
+        vk = (rng.integers(-24, 25, D) / 128).astype(np.float32); vsum += vk
+        rc, mk = api.enc_l2_compressed_encrypt(vk, bls[k], 8, 64, 32, 32, 7, bytes([k + 1]) * 32); assert rc == 0
         msgs.append(mk)
     Ls = np.stack([x["enc_values"][:, :32].copy() for x in msgs])
     b, e = sh.split_range(K, world)[rank]
@@ -257,9 +259,9 @@ def strong_server(api, pkg, torch, dist, rank, world, local):
         if world > 1:
             dist.all_reduce(good, op=dist.ReduceOp.MIN)
         torch.cuda.synchronize(); t1 = time.perf_counter()
-        rc, f = sh.decrypt_sharded(api, Ls, 1, 1 << 16, 16, 32, 7, dist=dist if world > 1 else None, device=dev)
+        rc, f = sh.decrypt_sharded(api, Ls, 0, 1 << 16, 16, 32, 7, dist=dist if world > 1 else None, device=dev)
         torch.cuda.synchronize(); t2 = time.perf_counter()
-        assert int(good.item()) == 1 and rc == 0 and f.size == D
+        assert int(good.item()) == 1 and rc == 0 and (f == vsum.astype(np.float32)).all()
         tt = torch.tensor([t1 - t0, t2 - t1], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -139,6 +139,27 @@ class Api:
             raise self._err(rc)
         return out
 
+    def scalar_add(self, a, b):
+        """element-wise a + b mod l on 32-byte scalars (host; bindings32.rs `add_scalars`)"""
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32); b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32); o = np.zeros_like(a)
+        rc = self.lib.rofl_scalar_ops(0, _ptr(a), _ptr(b), a.shape[0], _ptr(o))
+        if rc: raise self._err(rc)
+        return o
+
+    def scalar_neg(self, a):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32); o = np.zeros_like(a)
+        rc = self.lib.rofl_scalar_ops(1, _ptr(a), None, a.shape[0], _ptr(o))
+        if rc: raise self._err(rc)
+        return o
+
+    def cancelling_blindings(self, n_clients, D, seed_byte=0x40):
+        """n_clients blinding vectors that sum to zero (pedersen_ops.rs:110-122 generate_cancelling_blindings: the last one is minus the sum of the others)"""
+        bls = [np.frombuffer(self.rnd_scalar_vec(bytes([(seed_byte + k) & 0xff]) * 32, D).tobytes(), np.uint8).reshape(D, 32).copy() for k in range(n_clients - 1)]
+        tot = np.zeros((D, 32), np.uint8)
+        for b in bls:
+            tot = self.scalar_add(tot, b)
+        return bls + [self.scalar_neg(tot)]
+
     def scalar_selftest(self, a, b):
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8); n = a.shape[0]
         out = np.zeros((n, 3, 32), np.uint8)
