@@ -534,7 +534,7 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
             dev_buf d_bases(sizeof(p3_st) * (size_t)C * 2 * FA * FRZ_Q, q);      // returned stream-ordered: the kernels below may still be running
             q.big();
             void *tk = rt_prof_begin(PROF_FRZ, q.cur ? q.lo : q.hi);
-            LAUNCH(k_frz_bases, dim3((unsigned)((2 * FA + 127) / 128), C), dim3(128), q.big(), d_bases.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), (uint32_t)FA, (uint32_t)half);
+            LAUNCH(k_frz_bases, dim3((unsigned)((2 * FA + 127) / 128), C), dim3(128), q.big(), d_bases.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), (uint32_t)FA, (uint32_t)half, (uint32_t)FRZ_Q, 32u);
             const size_t cnt = (size_t)C * 2 * FA * FRZ_Q;
             LAUNCH(k_frz_tables, dim3((unsigned)((cnt + 127) / 128)), dim3(128), q.big(), d_frzT.as<p3_st>(), d_bases.as<p3_st>(), cnt);
             rt_prof_end(PROF_FRZ, tk, q.cur ? q.lo : q.hi);
@@ -556,10 +556,12 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
             // freeze the 2*np generators the tail works on: Straus tables (kernels.cuh K6c), built once for all its rounds
             const uint32_t Ft = (uint32_t)(2 * np);
             if (round == 0) LAUNCH(k_niels_to_p3, dim3((Ft + 127) / 128, C), dim3(128), q.small(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), g.G, g.H, Ft, (uint32_t)half);
-            dev_buf d_tb(sizeof(p3_st) * (size_t)C * 2 * Ft * FRZ_Q, q), d_tT(sizeof(p3_st) * (size_t)C * 2 * Ft * FRZ_Q * FRZ_E, q);
+            // tables of the tail: (k+1) 16^pos P for every radix-16 digit position (TAIL_Q = 64 per point; 8 MB per chunk): a round is then a plain sum
+            // of table entries -- the 28-doubling chain per round that octant tables need was 215 k cycles of one lane in each of the six rounds
+            dev_buf d_tb(sizeof(p3_st) * (size_t)C * 2 * Ft * TAIL_Q, q), d_tT(sizeof(p3_st) * (size_t)C * 2 * Ft * TAIL_Q * FRZ_E, q);
             void *tk = rt_prof_begin(PROF_TAIL, q.cur ? q.lo : q.hi);
-            LAUNCH(k_frz_bases, dim3((2 * Ft + 127) / 128, C), dim3(128), q.small(), d_tb.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), Ft, (uint32_t)half);
-            LAUNCH(k_frz_tables, dim3((unsigned)(((size_t)C * 2 * Ft * FRZ_Q + 127) / 128)), dim3(128), q.small(), d_tT.as<p3_st>(), d_tb.as<p3_st>(), (size_t)C * 2 * Ft * FRZ_Q);
+            LAUNCH(k_frz_bases, dim3((2 * Ft + 127) / 128, C), dim3(128), q.small(), d_tb.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), Ft, (uint32_t)half, (uint32_t)TAIL_Q, 4u);
+            LAUNCH(k_frz_tables, dim3((unsigned)(((size_t)C * 2 * Ft * TAIL_Q + 127) / 128)), dim3(128), q.small(), d_tT.as<p3_st>(), d_tb.as<p3_st>(), (size_t)C * 2 * Ft * TAIL_Q);
             tail_args ta = {}; ta.T = d_tT.as<p3_st>();
             ta.a = d_a.as<sc_st>(); ta.b = d_b.as<sc_st>(); ta.yinv = d_yinv.as<sc_st>(); ta.N = N;
             ta.ts = d_ts.as<transcript>(); ta.w = d_w2.as<sc_st>(); ta.uprod = d_up.as<sc_st>(); ta.uinvprod = d_up.as<sc_st>() + C; ta.tabB = e.sh->tabB;
@@ -579,7 +581,7 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
                 long long h[128]; rt_d2h(h, d_tdbg.p, sizeof(h), q.small()); rt_sync(q.small());
                 static const char *nm[7] = {"digits", "c_tree", "table_adds", "point_tree", "chain+compress", "transcript+invert", "folds"};
                 for (int r = 0; r < 8 && h[8 * r]; r++) { fprintf(stderr, "[rofl tail] round %d:", r); for (int k = 0; k < 7; k++) fprintf(stderr, " %s=%lld", nm[k], h[8 * r + k + 1] - h[8 * r + k]); fprintf(stderr, "\n"); }
-                fprintf(stderr, "[rofl tail] round 2, per warp (table loop, shuffle tree):"); for (int w = 0; w < 16; w++) fprintf(stderr, " (%lld, %lld)", h[64 + 2 * w], h[64 + 2 * w + 1]); fprintf(stderr, "  c w B threads: %lld\n", h[96]);
+                fprintf(stderr, "[rofl tail] round 2, per warp (table loop, shuffle tree):"); for (int w = 0; w < 16; w++) fprintf(stderr, " (%lld, %lld)", h[64 + 2 * w], h[64 + 2 * w + 1]); fprintf(stderr, "  c w B threads: %lld  chain: %lld  compress + store: %lld\n", h[96], h[100], h[101]);
             }
             rt_prof_end(PROF_TAIL, tk, q.cur ? q.lo : q.hi);
             tail_done = true;

@@ -1488,17 +1488,18 @@ struct frz_reduce_args { const p3_st *T; const sc_st *msmL, *msmR; p3_st *V; uin
 struct frz_exit_args { const p3_st *T; const int8_t *digs; p3_st *Gf, *Hf, *V; uint32_t F, Fo, nblk, stride; };
 #ifdef KG_FOLD
 // bases[(c*2F + p)*8 + q] = 2^(32 q) * P_p ; P = G"[c][0..F) then H"[c][0..F).  grid (blocks, C)
-KERNEL void LB(128, 4) k_frz_bases(p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride) {
+// Q bases per point, `step` doublings apart: (FRZ_Q, 32) for the frozen level, (TAIL_Q, 4) = one base per radix-16 digit for the tail
+KERNEL void LB(128, 4) k_frz_bases(p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride, uint32_t Q, uint32_t step) {
     const int c = blockIdx.y; const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= 2 * F) return;
     ge_p3 P; ld_p3(P, (p < F ? Gf + (size_t)c * stride + p : Hf + (size_t)c * stride + (p - F)));
-    p3_st *o = bases + ((size_t)c * 2 * F + p) * FRZ_Q;
-    for (int q = 0; q < FRZ_Q; q++) {
+    p3_st *o = bases + ((size_t)c * 2 * F + p) * Q;
+    for (uint32_t q = 0; q < Q; q++) {
         st_p3(o + q, P);
-        if (q + 1 < FRZ_Q) for (int k = 0; k < 32; k++) ge_p3_dbl(P, P);
+        if (q + 1 < Q) for (uint32_t k = 0; k < step; k++) ge_p3_dbl(P, P);
     }
 }
-KLAUNCH(k_frz_bases, false, (p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride), (bases, Gf, Hf, F, stride))
+KLAUNCH(k_frz_bases, false, (p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride, uint32_t Q, uint32_t step), (bases, Gf, Hf, F, stride, Q, step))
 // T[idx*8 + k] = (k+1) * bases[idx]   (cached form), one thread per (point, octant)
 KERNEL void LB(128, 4) k_frz_tables(p3_st *T, const p3_st *bases, size_t count) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1571,27 +1572,31 @@ KERNEL void LB(128, 1) k_frz_exit_chain(frz_exit_args a, uint32_t C) {
 }
 KLAUNCH(k_frz_exit_chain, false, (frz_exit_args a, uint32_t C), (a, C))
 #endif
-void launch_k_frz_bases(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride);
+void launch_k_frz_bases(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride, uint32_t Q, uint32_t step);
 void launch_k_frz_tables(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *T, const p3_st *bases, size_t count);
 void launch_k_frz_reduce(dim3 g_, dim3 b_, cudaStream_t s_, frz_reduce_args a);
 void launch_k_frz_exit(dim3 g_, dim3 b_, cudaStream_t s_, frz_exit_args a);
 void launch_k_frz_exit_chain(dim3 g_, dim3 b_, cudaStream_t s_, frz_exit_args a, uint32_t C);
 
 // ===================================================================================================================
-// K6b: the last rounds of the inner-product argument (half-size np <= TAIL_MAX_F/2) in ONE launch, one block per chunk,
-// nothing leaves the SM between rounds: the Merlin transcript, the challenge inversion and the scalar folds run on the
-// device.  The generators are frozen at their F = 2 np0 entry values (their Straus tables T are built by k_frz_bases /
-// k_frz_tables right before the launch) and every round is the frozen-level round of K6c inside the block:
+// K6b: the last rounds of the inner-product argument (half-size np <= TAIL_MAX_F/2) in ONE launch, one thread-block cluster per chunk,
+// nothing leaves the SMs between rounds: the Merlin transcript, the challenge inversion and the scalar folds run on the device.
+// The generators are frozen at their F = 2 np0 entry values; their tables T[p][pos][k] = (k+1) 16^pos P_p -- one position per radix-16
+// digit, built by k_frz_bases / k_frz_tables right before the launch -- make every round a plain sum of table entries:
 //   128 threads recode the scalars of the 2F points into signed radix-16 digits (shared memory);
-//   512 threads (side, digit position, group) add up table entries: 16 sums of 8F entries each, 32-way tree per sum;
-//   2 threads run the 28-doubling chains of L and R, add c_L w B / c_R w B (computed meanwhile by a spare warp) and compress;
-//   thread 0 appends L, R to the transcript, draws u, inverts it (binary Euclid) and publishes u^2, u^-2, u^-2 y^-np.
+//   512 threads (side, lane) add up their 16 table entries each (dealt over the blocks of the cluster), shuffle tree per warp,
+//   the leader block sums the 8 warp results of a side (shuffle tree over 8 lanes), adds c_L w B / c_R w B (computed meanwhile by a
+//   spare warp, one radix-256 window per lane) and compresses; warp 0 appends L, R to the transcript and draws u (wtranscript.cuh);
+//   lane 0 inverts it (division steps) and publishes u^2, u^-2, u^-2 y^-np; every block folds its copy of a^, b^ and the coefficients.
 //   out[c]: rounds x (L | R) compressed, then a | b (the proof's last two scalars)
+// Per round on B200 (ROFL_TAIL_DBG, cycles at 1.965 GHz): table sums 330 k, sums + compress 275 k (the compression alone 186 k), transcript +
+// inversion 160 k.  History: octant tables with a 28-doubling Horner chain per round 400 k; one lane walking the 32 windows of c w B 370 k.
 // ===================================================================================================================
 #define TAIL_MAX_F 64
+#define TAIL_Q 64                            // table positions per point in the tail: one per radix-16 digit, so that a round needs NO doubling chain
 #define TAIL_THREADS (512 + 32)
 struct tail_args {
-    const p3_st *T;                          // [C][2F][FRZ_Q][FRZ_E] Straus tables of G"[0..F) then H"[0..F)
+    const p3_st *T;                          // [C][2F][TAIL_Q][FRZ_E] tables (k+1) 16^pos P of G"[0..F) then H"[0..F)
     const sc_st *a, *b, *yinv; size_t N;     // [C][N] lazy-factor vectors a^, b^ and y^-i (first F entries live)
     const transcript *ts;                    // [C] transcript states after the previous challenge
     const sc_st *w, *uprod, *uinvprod;       // [C] w; products of the earlier u_k and u_k^-1
@@ -1629,7 +1634,7 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
     const int tB = 512;                                                // lanes 0 / 1 of the last warp: the c_L w B and c_R w B terms
     p3_st *pts = a.scratch + (size_t)c * 512;                          // [16 warps][32]: slot 32 w + r = warp w's sum of block r
     sc_st *gfac = a.gfac + 3 * (size_t)c;
-    const p3_st *T = a.T + (size_t)c * NP * FRZ_Q * FRZ_E;
+    const p3_st *T = a.T + (size_t)c * NP * TAIL_Q * FRZ_E;
     for (uint32_t i = tid; i < F; i += TAIL_THREADS) {
         sa[i] = a.a[(size_t)c * a.N + i]; sb[i] = a.b[(size_t)c * a.N + i]; sy[i] = a.yinv[(size_t)c * a.N + i];
     }
@@ -1647,7 +1652,7 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
     if (tid >= tB) ld_sc(wc, a.w + c);
     uint8_t *out = a.out + (size_t)c * a.out_stride;
     // accumulation role: side (L / R), digit position, group
-    const uint32_t a_side = (uint32_t)tid >> 8, a_pos = ((uint32_t)tid >> 5) & 7, a_g = (uint32_t)tid & 31;
+    const uint32_t a_side = (uint32_t)tid >> 8, a_lin = (uint32_t)tid & 255, a_g = (uint32_t)tid & 31;
     __syncthreads();
     int round = 0;
     for (uint32_t np = F >> 1; np >= 1; np >>= 1, round++) {
@@ -1686,13 +1691,13 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
             // the F points of my side (G" blocks with h = 1 and H" blocks with h = 0 feed L, the others R) x 8 octants, dealt to the 32 lanes of
             // my (side, position): 16 pairs each in every round (striding over ALL points and skipping the other side's left half of the lanes
             // idle once np < 4: the last two rounds took twice as long)
-            for (uint32_t pr = rank * 32 + a_g; pr < F * FRZ_Q; pr += 32 * ncta) {
-                const uint32_t idx = pr / FRZ_Q, q = pr % FRZ_Q;
+            for (uint32_t pr = rank * 256 + a_lin; pr < F * TAIL_Q; pr += 256 * ncta) {
+                const uint32_t idx = pr / TAIL_Q, pos = pr % TAIL_Q;
                 const bool isH = idx >= F / 2; const uint32_t tt = isH ? idx - F / 2 : idx;
                 const uint32_t hsel = isH ? a_side : 1 - a_side;
                 const uint32_t j = ((tt / np) * 2 + hsel) * np + tt % np, p = isH ? F + j : j;
-                const int d = dig[p][8 * q + a_pos];
-                if (d != 0) acc_add_cached(acc, T + ((size_t)p * FRZ_Q + q) * FRZ_E + (d > 0 ? d : -d) - 1, d < 0);
+                const int d = dig[p][pos];
+                if (d != 0) acc_add_cached(acc, T + ((size_t)p * TAIL_Q + pos) * FRZ_E + (d > 0 ? d : -d) - 1, d < 0);
             }
 #ifdef ROFL_EMUL
             st_p3(pts + tid, acc);
@@ -1757,14 +1762,35 @@ KERNEL void LB(TAIL_THREADS, 1) k_ipp_tail(tail_args a) {
         }
 #endif
         TAIL_STAMP(4);
-        if (leader && (tid == 0 || tid == 256)) {            // 16^pos chain of my side, + c w B, compress
+        // my side's 8 warp sums (every table entry already carries its 16^pos), + c w B, compress
+#ifdef ROFL_EMUL
+        if (leader && (tid == 0 || tid == 256)) {
             const int lr = tid ? 1 : 0;
-            ge_p3 h; ld_p3(h, pts + tid + 7 * 32);
-            for (int w = 6; w >= 0; w--) { for (int k = 0; k < 4; k++) ge_p3_dbl(h, h); acc_add_p3(h, pts + tid + w * 32, false); }
+            ge_p3 h; ld_p3(h, pts + tid);
+            for (int w = 1; w < 8; w++) acc_add_p3(h, pts + tid + w * 32, false);
             ge_p3 y; ld_p3(y, ptB + lr); ge_add(h, h, y);
             uint8_t enc[32]; ge_compress(enc, h);
             for (int k = 0; k < 32; k++) out[64 * round + 32 * lr + k] = enc[k];
         }
+#else
+        if (leader && (tid < 32 || (tid >= 256 && tid < 288))) {
+            const int lr = tid >= 256 ? 1 : 0, ln = tid & 31;
+            ge_p3 h; if (ln < 8) ld_p3(h, pts + 256 * lr + 32 * ln); else ge_p3_0(h);
+            for (int s2 = 4; s2 > 0; s2 >>= 1) {
+                ge_p3 y;
+                for (int k = 0; k < 8; k++) {
+                    y.X.v[k] = __shfl_down_sync(0xffffffffu, h.X.v[k], s2); y.Y.v[k] = __shfl_down_sync(0xffffffffu, h.Y.v[k], s2);
+                    y.Z.v[k] = __shfl_down_sync(0xffffffffu, h.Z.v[k], s2); y.T.v[k] = __shfl_down_sync(0xffffffffu, h.T.v[k], s2);
+                }
+                ge_add(h, h, y);
+            }
+            if (ln == 0) {
+                ge_p3 y; ld_p3(y, ptB + lr); ge_add(h, h, y);
+                uint8_t enc[32]; ge_compress(enc, h);
+                for (int k = 0; k < 32; k++) out[64 * round + 32 * lr + k] = enc[k];
+            }
+        }
+#endif
         __syncthreads();
         TAIL_STAMP(5);
 #ifndef ROFL_EMUL
