@@ -560,7 +560,11 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
             // of table entries -- the 28-doubling chain per round that octant tables need was 215 k cycles of one lane in each of the six rounds
             dev_buf d_tb(sizeof(p3_st) * (size_t)C * 2 * Ft * TAIL_Q, q), d_tT(sizeof(p3_st) * (size_t)C * 2 * Ft * TAIL_Q * FRZ_E, q);
             void *tk = rt_prof_begin(PROF_TAIL, q.cur ? q.lo : q.hi);
+#ifdef ROFL_EMUL
             LAUNCH(k_frz_bases, dim3((2 * Ft + 127) / 128, C), dim3(128), q.small(), d_tb.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), Ft, (uint32_t)half, (uint32_t)TAIL_Q, 4u);
+#else
+            LAUNCH(k_frz_bases4, dim3((4 * 2 * Ft + 127) / 128, C), dim3(128), q.small(), d_tb.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), Ft, (uint32_t)half, (uint32_t)TAIL_Q, 4u);
+#endif
             LAUNCH(k_frz_tables, dim3((unsigned)(((size_t)C * 2 * Ft * TAIL_Q + 127) / 128)), dim3(128), q.small(), d_tT.as<p3_st>(), d_tb.as<p3_st>(), (size_t)C * 2 * Ft * TAIL_Q);
             tail_args ta = {}; ta.T = d_tT.as<p3_st>();
             ta.a = d_a.as<sc_st>(); ta.b = d_b.as<sc_st>(); ta.yinv = d_yinv.as<sc_st>(); ta.N = N;

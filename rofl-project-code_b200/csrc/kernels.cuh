@@ -1500,6 +1500,36 @@ KERNEL void LB(128, 4) k_frz_bases(p3_st *bases, const p3_st *Gf, const p3_st *H
     }
 }
 KLAUNCH(k_frz_bases, false, (p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride, uint32_t Q, uint32_t step), (bases, Gf, Hf, F, stride, Q, step))
+#ifndef ROFL_EMUL
+// The same bases with FOUR lanes per point (device only): lane k of a quad owns coordinate k of (X : Y : Z : T).  A doubling is 4 independent
+// squarings followed by 4 independent multiplications (ge_dbl_p1p1 / ge_p1p1_to_p3), so the quad does it in the time of one squaring + one
+// multiplication + 48 shuffles -- one lane alone needs 3500 cycles per doubling (tools/microbench_lat.cu) and the tail's 252-doubling chain per
+// point is pure latency at the exposed end of a proof.  Bit-identical coordinates to k_frz_bases.
+KERNEL void LB(128, 4) k_frz_bases4(p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride, uint32_t Q, uint32_t step) {
+    const int c = blockIdx.y; const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, k = t & 3;
+    const bool live = (t >> 2) < 2 * F; const uint32_t p = live ? (t >> 2) : 2 * F - 1;
+    const int qb = (int)(threadIdx.x & 31u) & ~3;
+    const p3_st *src = p < F ? Gf + (size_t)c * stride + p : Hf + (size_t)c * stride + (p - F);
+    fe mine; { const uint32_t *w = (const uint32_t *)src + 8 * k; for (int i = 0; i < 8; i++) mine.v[i] = w[i]; }
+    p3_st *o = bases + ((size_t)c * 2 * F + p) * Q;
+    auto bc = [&](const fe &v, int from) { fe r; for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], qb + from); return r; };
+    for (uint32_t q = 0; q < Q; q++) {
+        if (live) { uint32_t *w = (uint32_t *)(o + q) + 8 * k; for (int i = 0; i < 8; i++) w[i] = mine.v[i]; }
+        if (q + 1 < Q) for (uint32_t it = 0; it < step; it++) {
+            const fe X = bc(mine, 0), Y = bc(mine, 1);
+            fe in = mine; if (k == 3) fe_add(in, X, Y);
+            fe sq; fe_sq(sq, in);                                   // XX | YY | ZZ | (X+Y)^2
+            const fe xx = bc(sq, 0), yy = bc(sq, 1), zz = bc(sq, 2), xy = bc(sq, 3);
+            fe Yp, Zp, Xp, Tp, tt;
+            fe_add(Yp, yy, xx); fe_sub(Zp, yy, xx); fe_sub4(Xp, xy, Yp); fe_carry(Xp, Xp);
+            fe_add(tt, zz, zz); fe_add(tt, tt, xx); fe_sub(Tp, tt, yy);
+            const fe &A = (k == 0 || k == 2) ? Tp : (k == 1 ? Yp : Xp), &B = k == 0 ? Xp : (k == 3 ? Yp : Zp);
+            fe_mul(mine, A, B);                                     // X3 = T'X' | Y3 = Y'Z' | Z3 = T'Z' | T3 = X'Y'
+        }
+    }
+}
+KLAUNCH(k_frz_bases4, false, (p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride, uint32_t Q, uint32_t step), (bases, Gf, Hf, F, stride, Q, step))
+#endif
 // T[idx*8 + k] = (k+1) * bases[idx]   (cached form), one thread per (point, octant)
 KERNEL void LB(128, 4) k_frz_tables(p3_st *T, const p3_st *bases, size_t count) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1573,6 +1603,9 @@ KERNEL void LB(128, 1) k_frz_exit_chain(frz_exit_args a, uint32_t C) {
 KLAUNCH(k_frz_exit_chain, false, (frz_exit_args a, uint32_t C), (a, C))
 #endif
 void launch_k_frz_bases(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride, uint32_t Q, uint32_t step);
+#ifndef ROFL_EMUL
+void launch_k_frz_bases4(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *bases, const p3_st *Gf, const p3_st *Hf, uint32_t F, uint32_t stride, uint32_t Q, uint32_t step);
+#endif
 void launch_k_frz_tables(dim3 g_, dim3 b_, cudaStream_t s_, p3_st *T, const p3_st *bases, size_t count);
 void launch_k_frz_reduce(dim3 g_, dim3 b_, cudaStream_t s_, frz_reduce_args a);
 void launch_k_frz_exit(dim3 g_, dim3 b_, cudaStream_t s_, frz_exit_args a);
