@@ -98,6 +98,8 @@ def cpu_reference_run(steps, warmup, sample_chunks=None):
     m = Dp // w["n_partition"]
     chunks = sample_chunks or 1 << (max(1, min(cores, w["n_partition"])).bit_length() - 1)      # a power of two (range_proof_vec/mod.rs:25-28), one chunk per thread
     Ds = m * chunks
+    if chunks < cores:                                   # one chunk per thread: the threads actually used
+        oracle.set_num_threads(chunks); cores = oracle.num_threads()
     v = synth(Ds, w["range_bits"], w["n_bits"], w["frac"], 1)
     bl = oracle.rnd_scalar_vec(b"\x01" * 32, Ds)
     times = []
