@@ -55,6 +55,10 @@ HD void acc_add_p3(ge_p3 &acc, const p3_st *p, bool neg) {
     fe_cmov(q.X, nq.X, neg); fe_cmov(q.T, nq.T, neg);
     ge_add(acc, acc, q);
 }
+// the cached form (Y+X | Y-X | Z | 2dT) in a p3_st record
+HD void st_cached(p3_st *p, const ge_cached &c) { uint4 *q = (uint4 *)p; st_fe1(q, c.YplusX); st_fe1(q + 2, c.YminusX); st_fe1(q + 4, c.Z); st_fe1(q + 6, c.T2d); }
+HD void ld_cached(ge_cached &c, const p3_st *p) { const uint4 *q = (const uint4 *)p; ld_fe2(c.YplusX, c.YminusX, q); ld_fe2(c.Z, c.T2d, q + 4); }
+HD void acc_add_cached(ge_p3 &acc, const p3_st *p, bool neg) { ge_cached c; ld_cached(c, p); ge_add_cached_signed(acc, acc, c, neg); }
 
 // ===================================================================================================================
 // K0: tables
@@ -549,7 +553,8 @@ KERNEL void LB(FIN_THREADS, 1) k_finalize(finalize_args a) {
         const p3_st *src = a.windows + (size_t)idx * a.slices * a.nw + tid;
         ge_p3 r; ld_p3(r, src);
         for (uint32_t s = 1; s < a.slices; s++) acc_add_p3(r, src + (size_t)s * a.nw, false);
-        st_p3(sw + tid, r);
+        if (tid == a.nw - 1) st_p3(sw + tid, r);                       // the chain starts from the top window (extended), the others are added (cached)
+        else { ge_cached cr; ge_p3_to_cached(cr, r); st_cached(sw + tid, cr); }
     }
     // 96 helper threads: one radix-256 window of sB*B each (32), one of sH*H each (32), the extra points (32, strided); then a tree over the 96
     if (tid >= 32) {
@@ -574,6 +579,7 @@ KERNEL void LB(FIN_THREADS, 1) k_finalize(finalize_args a) {
         __syncthreads();
         n = half;
     }
+#ifdef ROFL_EMUL
     if (tid != 0) return;
     ge_p3 r; ld_p3(r, ex);
     if (a.windows) {
@@ -583,10 +589,50 @@ KERNEL void LB(FIN_THREADS, 1) k_finalize(finalize_args a) {
             ge_dbl_p1p1(t, h.X, h.Y, h.Z); ge_dbl_fix(t);
             for (int k = 1; k < a.c; k++) { ge_p1p1_to_p2(q, t); ge_dbl_p1p1(t, q.X, q.Y, q.Z); ge_dbl_fix(t); }
             ge_p1p1_to_p3(h, t);
-            acc_add_p3(h, sw + w, false);
+            acc_add_cached(h, sw + w, false);
         }
         ge_add(r, r, h);
     }
+#else
+    // The chain sum_w 2^(cw) W_w by FOUR lanes (device): lane k owns coordinate k of (X : Y : Z : T).  A doubling is four independent squarings and
+    // four independent multiplications, an addition two rounds of four independent multiplications, so the quad needs two multiplication
+    // latencies + shuffles per step where one lane needs 7-9 (3076 / 4134 cycles, tools/microbench_lat.cu): the verifier's last finalize
+    // (242 doublings) 0.43 -> 0.16 ms.  Warp 0 runs it (the lanes above 3 only keep the shuffles convergent).
+    if (tid >= 32) return;
+    ge_p3 r; ld_p3(r, ex);
+    if (a.windows) {
+        const int k = tid & 3, qb = tid & ~3;
+        auto bc = [&](const fe &v, int from) { fe o; for (int i = 0; i < 8; i++) o.v[i] = __shfl_sync(0xffffffffu, v.v[i], qb + from); return o; };
+        fe mine; { const uint32_t *wp = (const uint32_t *)(sw + a.nw - 1) + 8 * k; for (int i = 0; i < 8; i++) mine.v[i] = wp[i]; }
+        for (int w = a.nw - 2; w >= 0; w--) {
+            for (int it = 0; it < a.c; it++) {
+                const fe X = bc(mine, 0), Y = bc(mine, 1);
+                fe in = mine; if (k == 3) fe_add(in, X, Y);
+                fe sq; fe_sq(sq, in);                               // XX | YY | ZZ | (X+Y)^2
+                const fe xx = bc(sq, 0), yy = bc(sq, 1), zz = bc(sq, 2), xy = bc(sq, 3);
+                fe Yp, Zp, Xp, Tp, tt;
+                fe_add(Yp, yy, xx); fe_sub(Zp, yy, xx); fe_sub(Xp, xy, Yp);
+                fe_add(tt, zz, zz); fe_add(tt, tt, xx); fe_sub(Tp, tt, yy);
+                const fe &A = (k == 0 || k == 2) ? Tp : (k == 1 ? Yp : Xp), &B = k == 0 ? Xp : (k == 3 ? Yp : Zp);
+                fe_mul(mine, A, B);                                 // X3 = T'X' | Y3 = Y'Z' | Z3 = T'Z' | T3 = X'Y'
+            }
+            {   // + W_w (cached: Y+X | Y-X | Z | 2dT)
+                const fe X = bc(mine, 0), Y = bc(mine, 1);
+                fe op1 = mine; if (k == 0) fe_sub(op1, Y, X); else if (k == 1) fe_add(op1, Y, X);
+                fe op2; { const uint32_t *wp = (const uint32_t *)(sw + w) + 8 * (k == 0 ? 1 : k == 1 ? 0 : k); for (int i = 0; i < 8; i++) op2.v[i] = wp[i]; }
+                fe pr; fe_mul(pr, op1, op2);                        // a = (Y1-X1)(Y2-X2) | b = (Y1+X1)(Y2+X2) | Z1 Z2 | c = T1 2dT2
+                const fe pa = bc(pr, 0), pb = bc(pr, 1), pz = bc(pr, 2), pc = bc(pr, 3);
+                fe d, E, H, G, F;
+                fe_add(d, pz, pz); fe_sub(E, pb, pa); fe_add(H, pb, pa); fe_add(G, d, pc); fe_sub(F, d, pc);
+                const fe &A = (k == 0 || k == 2) ? F : (k == 1 ? H : E), &B = k == 0 ? E : (k == 3 ? H : G);
+                fe_mul(mine, A, B);                                 // X3 = F E | Y3 = H G | Z3 = F G | T3 = E H
+            }
+        }
+        ge_p3 h; h.X = bc(mine, 0); h.Y = bc(mine, 1); h.Z = bc(mine, 2); h.T = bc(mine, 3);
+        if (tid == 0) ge_add(r, r, h);
+    }
+    if (tid != 0) return;
+#endif
     if (a.out32) { uint8_t o[32]; ge_compress(o, r); st_bytes32(a.out32 + 32 * (size_t)idx, o); }
     if (a.out_p3) st_p3(a.out_p3 + idx, r);
     if (a.is_id) a.is_id[idx] = ge_is_identity(r) ? 1 : 0;
@@ -1481,9 +1527,6 @@ void launch_k_catchup_naf(dim3 g_, dim3 b_, cudaStream_t s_, catchup_naf_args a)
 #define FRZ_Q 8
 #define FRZ_E 8
 #define FRZ_MAX_F 1024
-HD void st_cached(p3_st *p, const ge_cached &c) { uint4 *q = (uint4 *)p; st_fe1(q, c.YplusX); st_fe1(q + 2, c.YminusX); st_fe1(q + 4, c.Z); st_fe1(q + 6, c.T2d); }
-HD void ld_cached(ge_cached &c, const p3_st *p) { const uint4 *q = (const uint4 *)p; ld_fe2(c.YplusX, c.YminusX, q); ld_fe2(c.Z, c.T2d, q + 4); }
-HD void acc_add_cached(ge_p3 &acc, const p3_st *p, bool neg) { ge_cached c; ld_cached(c, p); ge_add_cached_signed(acc, acc, c, neg); }
 struct frz_reduce_args { const p3_st *T; const sc_st *msmL, *msmR; p3_st *V; uint32_t F, np, C; };
 struct frz_exit_args { const p3_st *T; const int8_t *digs; p3_st *Gf, *Hf, *V; uint32_t F, Fo, nblk, stride; };
 #ifdef KG_FOLD
