@@ -107,7 +107,7 @@ struct lane_guard {
     }
     ~lane_guard() {
         if (--tl_lane_depth > 0) return;
-        rt_d2h_finish();
+        rt_d2h_finish(std::uncaught_exceptions() > 0);
         { std::lock_guard<std::mutex> lk(e.lane_mu); ln->busy = false; }
         e.lane_cv.notify_one(); tl_lane = nullptr; tl_lane_engine = nullptr;
     }

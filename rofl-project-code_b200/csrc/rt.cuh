@@ -2,6 +2,7 @@
 // engine with -DROFL_EMUL against tests/hostsim/cuda_emul.h to execute it on CPU threads (test tool only).
 #pragma once
 #include <stdexcept>
+#include <exception>
 #include <string>
 #include <vector>
 #include <mutex>
@@ -42,7 +43,7 @@ inline void rt_d2h(void *h, const void *d, size_t n, cudaStream_t) { memcpy(h, d
 inline void rt_d2d(void *d, const void *s, size_t n, cudaStream_t) { memcpy(d, s, n); }
 inline void rt_memset(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); }
 inline void rt_sync(cudaStream_t) {}
-inline void rt_d2h_finish() {}
+inline void rt_d2h_finish(bool = false) {}
 inline size_t rt_free_mem() { return (size_t)8 << 30; }
 inline void rt_stream_after(cudaStream_t, cudaStream_t) {}
 inline cudaStream_t rt_stream_create(int) { return nullptr; }
@@ -168,7 +169,13 @@ inline void rt_d2h_deliver(cudaStream_t s, bool all = false) {
     }
 }
 // end of an API call: nothing may stay staged (a result copy without a matching rt_sync would otherwise be lost silently)
-inline void rt_d2h_finish() { auto &v = rt_pending(); if (v.empty()) return; for (auto &p : v) cudaStreamSynchronize(p.s); rt_d2h_deliver(nullptr, true); }
+// (while an exception unwinds the call, the destinations may be dead stack frames: the staged results are dropped, not delivered)
+inline void rt_d2h_finish(bool discard = false) {
+    auto &v = rt_pending(); if (v.empty()) return;
+    for (auto &p : v) cudaStreamSynchronize(p.s);
+    if (discard) { for (auto &p : v) rt_pins().give(p.stage, p.cap); v.clear(); }
+    else rt_d2h_deliver(nullptr, true);
+}
 inline void rt_d2d(void *d, const void *s_, size_t n, cudaStream_t s) { rt_check(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s), "d2d"); }
 inline void rt_memset(void *d, int v, size_t n, cudaStream_t s) { rt_check(cudaMemsetAsync(d, v, n, s), "memset"); }
 // Stream wait.  ROFL_SYNC=spin polls cudaStreamQuery instead (a proof has ~20 host round trips; measured on B200: no gain over the
