@@ -285,6 +285,25 @@ def test_every_table_radix_gives_the_same_bytes(api, oracle):
         api.set_option("use_rt", 1); api.set_option("rt_bits", 11)
 
 
+def test_tail_cluster_sizes_and_entry_points_give_the_same_bytes(api, oracle):
+    """k_ipp_tail runs as a thread-block cluster (1, 2, 4 or 8 blocks per chunk: the table sums are dealt over the blocks, the leader runs the serial
+    part) and may start at half-size 32, 16, 8 ... : every combination must give the oracle's bytes, the chunk-group count as well."""
+    rng = np.random.default_rng(79)
+    D, rb, P, nb = 900, 16, 8, 16
+    mn, mx = oracle.clip_bounds(rb, nb, 7)
+    v = rng.uniform(mn, mx, D).astype(np.float32); bl = oracle.rnd_scalar_vec(b"\x73" * 32, D); seed = bytes([23] * 32)
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, rb, P, nb, 7, seed)
+    assert rc_o == 0
+    try:
+        for ncta, tail_np, groups in [(1, 32, 3), (2, 32, 3), (4, 32, 1), (8, 32, 2), (2, 16, 3), (4, 4, 1), (2, 1, 2), (2, 0, 3)]:
+            api.set_option("tail_ncta", ncta); api.set_option("tail_np", tail_np); api.set_option("groups", groups)
+            rc, p, c = api.range_prove(v, bl, rb, P, nb, 7, seed)
+            assert rc == 0 and (c == c_o).all() and (p == p_o).all(), (ncta, tail_np, groups)
+            assert api.range_verify(p, c, rb, seed) == 1
+    finally:
+        api.set_option("tail_ncta", 2); api.set_option("tail_np", 32); api.set_option("groups", 3)
+
+
 def test_rand_and_square_rand_proof_parity_and_full_size(api, oracle):
     """Per-element proofs of the un-optimised encodings (enc types 2 and 3): byte parity at 3 000 elements, then configs[0]'s 5 000 x 4
     on the GPU alone with existing commitments (as params.rs creates them), tamper and format rejection."""
