@@ -60,7 +60,9 @@ const char *rofl_last_error(void);
 void rofl_set_host_threads(rofl_ctx *ctx, int n);          /* host threads used for the per-chunk Merlin transcripts */
 /* tuning knobs (results never depend on them): "use_rt" 0/1 generator tables, "rt_unfold" unfolded IPP rounds, "groups" chunk
  * groups on separate queues, "tail_np" largest half-size handled by the fused tail kernel (0 = off), "rt_bits" table radix, "rt_per" table-MSM
- * terms per thread, "ts_host_m" chunk size above which commitments are absorbed on the host, "max_lanes" concurrent callers, "drop_tables".
+ * terms per thread, "tail_ncta" thread blocks (one cluster) per chunk in the tail kernel (1, 2, 4, 8), "frozen" 0/1 frozen-level middle rounds,
+ * "nt_unfold" / "nt_unfold_min" unfolded rounds without tables, "ts_host_m" chunk size above which commitments are absorbed on the host,
+ * "max_lanes" concurrent callers, "drop_tables", "trim" (hand cached scratch back to CUDA).
  * returns 0, -2 unknown name */
 int rofl_set_option(rofl_ctx *ctx, const char *name, long value);
 

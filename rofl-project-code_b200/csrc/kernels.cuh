@@ -533,7 +533,7 @@ KLAUNCH(k_bm_reduce, true, (msm_args a), (a))
 // combine, one block per output idx:
 //   R = sum_w 2^(cw) (sum_s W[idx][s][w])  +  sum of `npartial` extra points  +  sB*B + sH*H
 //   sB = sBa[idx] (* sBb[idx] if sBb), same for sH; any pointer may be null.  The window sums, the extra points and the two
-//   fixed-base products are computed by different threads, then thread 0 runs the doubling chain and compresses.
+//   fixed-base products are computed by different threads, then four lanes run the doubling chain (one coordinate each) and thread 0 compresses.
 //   out32: compressed result (nullable); out_p3: extended result (nullable); is_id: 1 if the result is the identity (nullable)
 #define FIN_THREADS 128
 struct finalize_args {
