@@ -177,92 +177,102 @@ HD void sc_invert_euclid(sc &r, const sc &a) {
     }
 }
 // a^-1 by Bernstein-Yang division steps ("safegcd"), variable time -- used on public Fiat-Shamir challenges only.  The binary Euclid above
-// walks ~750 dependent steps over 8-word integers (90 us for one thread on B200, and every IPP round waits for one inversion); here 62 division
-// steps at a time run on the low 64 bits of (f, g) alone and are applied to the 5 x 62-bit signed-limb integers f, g, d, e as one 2x2 matrix
-// (d a = f, e a = g mod l throughout; f ends as +-1).  At most 12 batches for 256-bit inputs ((49 * 256 + 57) / 17 = 741 steps).
-typedef __int128 sc_i128;
-struct sc_s62 { int64_t v[5]; };                    // sum v[i] 2^(62 i); v[0..3] in [0, 2^62), v[4] signed
-#define SC_M62 ((int64_t)((1ULL << 62) - 1))
-HD void sc_to_s62(sc_s62 &o, const uint32_t w[8]) {
-    uint64_t q[4]; for (int i = 0; i < 4; i++) q[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
-    o.v[0] = (int64_t)(q[0] & SC_M62);
-    o.v[1] = (int64_t)(((q[0] >> 62) | (q[1] << 2)) & SC_M62);
-    o.v[2] = (int64_t)(((q[1] >> 60) | (q[2] << 4)) & SC_M62);
-    o.v[3] = (int64_t)(((q[2] >> 58) | (q[3] << 6)) & SC_M62);
-    o.v[4] = (int64_t)(q[3] >> 56);
+// walks ~750 dependent steps over 8-word integers (90 us for one lane on B200, and every IPP round waits for one inversion).  Here 30 division
+// steps at a time run on the low 32 bits of (f, g) alone -- several per iteration: a run of zeros is shifted out at once and up to six bits of g
+// are cancelled by one multiple of f -- and are applied to the 9 x 30-bit signed-limb integers f, g, d, e as one 2x2 matrix of 32-bit entries, so
+// that every product is a single 32 x 32 -> 64 multiply-add (d a = f, e a = g mod l throughout; f ends as +-1).  At most 25 batches for 256-bit
+// inputs ((49 * 256 + 57) / 17 = 741 steps).  The first version (62-bit limbs, one step per iteration, 128-bit products) took 49 us on one lane.
+struct sc_s30 { int32_t v[9]; };                    // sum v[i] 2^(30 i); v[0..7] in [0, 2^30), v[8] signed
+#define SC_M30 0x3fffffff
+HD void sc_to_s30(sc_s30 &o, const uint32_t w[8]) {
+    for (int i = 0; i < 9; i++) {
+        const int bit = 30 * i, wi = bit >> 5, sh = bit & 31;
+        uint64_t x = (uint64_t)w[wi] >> sh;
+        if (wi + 1 < 8) x |= (uint64_t)w[wi + 1] << (32 - sh);
+        o.v[i] = (int32_t)((uint32_t)x & (uint32_t)SC_M30);
+    }
 }
-HD void sc_s62_add(sc_s62 &d, const sc_s62 &m, int64_t sign) {       // d += sign * m  (sign = +-1)
-    int64_t c = 0;
-    for (int i = 0; i < 4; i++) { const int64_t t = d.v[i] + sign * m.v[i] + c; d.v[i] = t & SC_M62; c = t >> 62; }
-    d.v[4] += sign * m.v[4] + c;
+HD void sc_s30_add(sc_s30 &d, const sc_s30 &m, int32_t sign) {       // d += sign * m  (sign = +-1)
+    int32_t c = 0;
+    for (int i = 0; i < 8; i++) { const int32_t t = d.v[i] + sign * m.v[i] + c; d.v[i] = t & SC_M30; c = t >> 30; }
+    d.v[8] += sign * m.v[8] + c;
 }
-// t = {u, v, q, r} with 2^62 f' = u f + v g, 2^62 g' = q f + r g after 62 division steps on the low words; returns the new delta
-HD int64_t sc_divsteps62(int64_t delta, uint64_t f, uint64_t g, int64_t t[4]) {
-    int64_t u = 1, v = 0, q = 0, r = 1;
-    for (int i = 0; i < 62; i++) {
-        if (g & 1) {
-            if (delta > 0) {                          // (delta, f, g) -> (1 - delta, g, (g - f) / 2)
-                const uint64_t nf = g; g = (g - f) >> 1; f = nf;
-                const int64_t nq = q - u, nr = r - v; u = 2 * q; v = 2 * r; q = nq; r = nr;
-                delta = 1 - delta;
-            } else {                                  // (1 + delta, f, (g + f) / 2)
-                g = (g + f) >> 1; q += u; r += v; u *= 2; v *= 2; delta += 1;
-            }
-        } else { g >>= 1; u *= 2; v *= 2; delta += 1; }
+HD int sc_ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+// t = {u, v, q, r} with 2^30 f' = u f + v g, 2^30 g' = q f + r g after 30 division steps on the low words; returns the new delta
+HD int32_t sc_divsteps30(int32_t delta, uint32_t f, uint32_t g, int32_t t[4]) {
+    int32_t u = 1, v = 0, q = 0, r = 1; int i = 30;
+    for (;;) {
+        const int z = sc_ctz32(g | (~0u << i));       // the even steps: (delta, f, g) -> (1 + delta, f, g / 2)
+        g >>= z; u = (int32_t)((uint32_t)u << z); v = (int32_t)((uint32_t)v << z); delta += z; i -= z;
+        if (i == 0) break;
+        if (delta > 0) {                              // g odd, delta > 0: (delta, f, g) -> (1 - delta, g, (g - f) / 2); the halving is counted above
+            const uint32_t tf = f; f = g; g = 0u - tf;
+            const int32_t tu = u, tv = v; u = q; v = r; q = -tu; r = -tv;
+            delta = -delta;
+        }
+        // delta <= 0: the next 1 - delta steps cannot swap; cancel up to 6 bits of g with w = -g / f mod 2^k  (f^-1 = f (2 - f^2) mod 64)
+        int lim = 1 - delta; if (lim > i) lim = i; if (lim > 6) lim = 6;
+        const uint32_t w = (f * g * (f * f - 2u)) & ((1u << lim) - 1u);
+        g += f * w; q += u * (int32_t)w; r += v * (int32_t)w;
     }
     t[0] = u; t[1] = v; t[2] = q; t[3] = r;
     return delta;
 }
 HD void sc_invert_vartime(sc &r, const sc &a) {
     if (sc_iszero(a)) { sc_0(r); return; }
-    sc_s62 L, f, g, d, e;
-    { uint32_t lw[8]; for (int i = 0; i < 8; i++) lw[i] = SC_L_[i]; sc_to_s62(L, lw); }
-    f = L; sc_to_s62(g, a.v);
-    for (int i = 0; i < 5; i++) { d.v[i] = 0; e.v[i] = 0; }
+    sc_s30 L, f, g, d, e;
+    { uint32_t lw[8]; for (int i = 0; i < 8; i++) lw[i] = SC_L_[i]; sc_to_s30(L, lw); }
+    f = L; sc_to_s30(g, a.v);
+    for (int i = 0; i < 9; i++) { d.v[i] = 0; e.v[i] = 0; }
     e.v[0] = 1;
-    uint64_t linv = (uint64_t)L.v[0];                 // l^-1 mod 2^64 by Newton (l odd), used mod 2^62
-    for (int i = 0; i < 6; i++) linv *= 2 - (uint64_t)L.v[0] * linv;
-    int64_t delta = 1;
-    for (int it = 0; it < 13; it++) {
-        int64_t t[4];
-        delta = sc_divsteps62(delta, (uint64_t)f.v[0] | ((uint64_t)f.v[1] << 62), (uint64_t)g.v[0] | ((uint64_t)g.v[1] << 62), t);
+    uint32_t linv = (uint32_t)L.v[0];                 // l^-1 mod 2^32 by Newton (l odd), used mod 2^30
+    for (int i = 0; i < 5; i++) linv *= 2u - (uint32_t)L.v[0] * linv;
+    int32_t delta = 1;
+    for (int it = 0; it < 26; it++) {
+        int32_t t[4];
+        delta = sc_divsteps30(delta, (uint32_t)f.v[0] | ((uint32_t)f.v[1] << 30), (uint32_t)g.v[0] | ((uint32_t)g.v[1] << 30), t);
         const int64_t u = t[0], v = t[1], q = t[2], rr = t[3];
-        {   // (d, e) <- (u d + v e, q d + r e) / 2^62 mod l: a multiple of l makes the low 62 bits vanish
-            sc_i128 cd = (sc_i128)u * d.v[0] + (sc_i128)v * e.v[0], ce = (sc_i128)q * d.v[0] + (sc_i128)rr * e.v[0];
-            const int64_t kd = (int64_t)((0 - (uint64_t)cd * linv) & (uint64_t)SC_M62), ke = (int64_t)((0 - (uint64_t)ce * linv) & (uint64_t)SC_M62);
-            cd += (sc_i128)kd * L.v[0]; ce += (sc_i128)ke * L.v[0];
-            cd >>= 62; ce >>= 62;
-            for (int i = 1; i < 5; i++) {
-                cd += (sc_i128)u * d.v[i] + (sc_i128)v * e.v[i] + (sc_i128)kd * L.v[i];
-                ce += (sc_i128)q * d.v[i] + (sc_i128)rr * e.v[i] + (sc_i128)ke * L.v[i];
-                if (i < 4) { d.v[i - 1] = (int64_t)cd & SC_M62; e.v[i - 1] = (int64_t)ce & SC_M62; cd >>= 62; ce >>= 62; }
-                else {
-                    const int64_t d3 = (int64_t)cd & SC_M62, e3 = (int64_t)ce & SC_M62; cd >>= 62; ce >>= 62;
-                    // (d.v[i-1] must stay readable until both sums have used d.v[i], hence the late stores)
-                    d.v[3] = d3; e.v[3] = e3; d.v[4] = (int64_t)cd; e.v[4] = (int64_t)ce;
-                }
+        {   // (d, e) <- (u d + v e, q d + r e) / 2^30 mod l: a multiple of l makes the low 30 bits vanish
+            int64_t cd = u * d.v[0] + v * e.v[0], ce = q * d.v[0] + rr * e.v[0];
+            const int64_t kd = (int64_t)(((0u - (uint32_t)cd) * linv) & (uint32_t)SC_M30), ke = (int64_t)(((0u - (uint32_t)ce) * linv) & (uint32_t)SC_M30);
+            cd += kd * L.v[0]; ce += ke * L.v[0];
+            cd >>= 30; ce >>= 30;
+            for (int i = 1; i < 9; i++) {
+                cd += u * d.v[i] + v * e.v[i] + kd * L.v[i];
+                ce += q * d.v[i] + rr * e.v[i] + ke * L.v[i];
+                if (i < 8) { d.v[i - 1] = (int32_t)(cd & SC_M30); e.v[i - 1] = (int32_t)(ce & SC_M30); cd >>= 30; ce >>= 30; }
+                else { d.v[7] = (int32_t)(cd & SC_M30); e.v[7] = (int32_t)(ce & SC_M30); d.v[8] = (int32_t)(cd >> 30); e.v[8] = (int32_t)(ce >> 30); }
             }
-            if (d.v[4] >= 0) sc_s62_add(d, L, -1);   // keep |d|, |e| < 2 l
-            if (e.v[4] >= 0) sc_s62_add(e, L, -1);
+            if (d.v[8] >= 0) sc_s30_add(d, L, -1);   // keep |d|, |e| < 2 l
+            if (e.v[8] >= 0) sc_s30_add(e, L, -1);
         }
-        {   // (f, g) <- (u f + v g, q f + r g) / 2^62, exact
-            sc_i128 cf = (sc_i128)u * f.v[0] + (sc_i128)v * g.v[0], cg = (sc_i128)q * f.v[0] + (sc_i128)rr * g.v[0];
-            cf >>= 62; cg >>= 62;
-            for (int i = 1; i < 5; i++) {
-                cf += (sc_i128)u * f.v[i] + (sc_i128)v * g.v[i]; cg += (sc_i128)q * f.v[i] + (sc_i128)rr * g.v[i];
-                if (i < 4) { f.v[i - 1] = (int64_t)cf & SC_M62; g.v[i - 1] = (int64_t)cg & SC_M62; cf >>= 62; cg >>= 62; }
-                else { const int64_t f3 = (int64_t)cf & SC_M62, g3 = (int64_t)cg & SC_M62; cf >>= 62; cg >>= 62; f.v[3] = f3; g.v[3] = g3; f.v[4] = (int64_t)cf; g.v[4] = (int64_t)cg; }
+        {   // (f, g) <- (u f + v g, q f + r g) / 2^30, exact
+            int64_t cf = u * f.v[0] + v * g.v[0], cg = q * f.v[0] + rr * g.v[0];
+            cf >>= 30; cg >>= 30;
+            for (int i = 1; i < 9; i++) {
+                cf += u * f.v[i] + v * g.v[i]; cg += q * f.v[i] + rr * g.v[i];
+                if (i < 8) { f.v[i - 1] = (int32_t)(cf & SC_M30); g.v[i - 1] = (int32_t)(cg & SC_M30); cf >>= 30; cg >>= 30; }
+                else { f.v[7] = (int32_t)(cf & SC_M30); g.v[7] = (int32_t)(cg & SC_M30); f.v[8] = (int32_t)(cf >> 30); g.v[8] = (int32_t)(cg >> 30); }
             }
         }
-        if ((g.v[0] | g.v[1] | g.v[2] | g.v[3] | g.v[4]) == 0) break;
+        int32_t nz = 0; for (int i = 0; i < 9; i++) nz |= g.v[i];
+        if (nz == 0) break;
     }
-    if (f.v[4] < 0) { sc_s62 z; for (int i = 0; i < 5; i++) { z.v[i] = d.v[i]; d.v[i] = 0; } sc_s62_add(d, z, -1); }       // f = -1: negate
-    for (int k = 0; k < 3 && d.v[4] < 0; k++) sc_s62_add(d, L, 1);
-    for (int k = 0; k < 3; k++) { sc_s62 t2 = d; sc_s62_add(t2, L, -1); if (t2.v[4] < 0) break; d = t2; }
-    const uint64_t q0 = (uint64_t)d.v[0] | ((uint64_t)d.v[1] << 62), q1 = ((uint64_t)d.v[1] >> 2) | ((uint64_t)d.v[2] << 60),
-                   q2 = ((uint64_t)d.v[2] >> 4) | ((uint64_t)d.v[3] << 58), q3 = ((uint64_t)d.v[3] >> 6) | ((uint64_t)d.v[4] << 56);
-    r.v[0] = (uint32_t)q0; r.v[1] = (uint32_t)(q0 >> 32); r.v[2] = (uint32_t)q1; r.v[3] = (uint32_t)(q1 >> 32);
-    r.v[4] = (uint32_t)q2; r.v[5] = (uint32_t)(q2 >> 32); r.v[6] = (uint32_t)q3; r.v[7] = (uint32_t)(q3 >> 32);
+    if (f.v[8] < 0) { sc_s30 z; for (int i = 0; i < 9; i++) { z.v[i] = d.v[i]; d.v[i] = 0; } sc_s30_add(d, z, -1); }       // f = -1: negate
+    for (int k = 0; k < 3 && d.v[8] < 0; k++) sc_s30_add(d, L, 1);
+    for (int k = 0; k < 3; k++) { sc_s30 t2 = d; sc_s30_add(t2, L, -1); if (t2.v[8] < 0) break; d = t2; }
+    uint64_t acc = 0; int bits = 0, wi = 0;
+    for (int i = 0; i < 9; i++) {
+        acc |= (uint64_t)(uint32_t)d.v[i] << bits; bits += 30;
+        while (bits >= 32 && wi < 8) { r.v[wi++] = (uint32_t)acc; acc >>= 32; bits -= 32; }
+    }
+    if (wi < 8) r.v[wi] = (uint32_t)acc;
 }
 HD void sc_pow_u64(sc &r, const sc &a, uint64_t e) {
     sc acc, base = a; sc_from_u64(acc, 1);
