@@ -215,6 +215,7 @@ void *rofl_ctx_stream(rofl_ctx *);        /* the cudaStream_t the context launch
 /* ---- test hooks: the warp-cooperative transcript absorb against the sequential code (0 equal / 1 different), and the Fiat-Shamir batching
  *      scalars (c_i | rho_i, 2 x n_proofs x 32 bytes) rofl_range_verify derives for a call (return value as rofl_range_verify) */
 int rofl_debug_ts_absorb(rofl_ctx *, const uint8_t *V32, size_t m, int n, int label_id);
+int rofl_debug_square_rlc(rofl_ctx *, const uint8_t *proofs160, const uint8_t *commits64, size_t D);   /* the batched square-proof check alone: 1 holds, 0 does not */
 int rofl_debug_verify_weights(rofl_ctx *, const uint8_t *proofs, size_t proof_len, size_t n_proofs, const uint8_t *commits32, size_t D, int range, const uint8_t seed[32], uint8_t *out_weights);
 #ifdef __cplusplus
 }

@@ -19,6 +19,7 @@ _SIGS = {
     "rofl_range_proof_shape": (None, [c_sz, C.c_int, c_sz, C.POINTER(c_sz), C.POINTER(c_sz)]),
     "rofl_field_selftest": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz, c_u8p]),
     "rofl_scalar_selftest": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz, c_u8p]),
+    "rofl_debug_square_rlc": (C.c_int, [c_vp, c_u8p, c_u8p, c_sz]),
     "rofl_f32_to_scalar_vec": (C.c_int, [c_vp, c_f32p, c_sz, C.c_int, C.c_int, c_u8p]),
     "rofl_scalar_to_f32_vec": (C.c_int, [c_vp, c_u8p, c_sz, C.c_int, C.c_int, c_f32p]),
     "rofl_clip_bounds": (None, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
@@ -138,6 +139,10 @@ class Api:
         if rc != 0:
             raise self._err(rc)
         return out
+
+    def debug_square_rlc(self, proofs, commits):
+        p = _u8(proofs).reshape(-1, 160); c = _u8(commits).reshape(-1, 64)
+        return self.lib.rofl_debug_square_rlc(self.h, _ptr(p), _ptr(c), p.shape[0])
 
     def scalar_add(self, a, b):
         """element-wise a + b mod l on 32-byte scalars (host; bindings32.rs `add_scalars`)"""

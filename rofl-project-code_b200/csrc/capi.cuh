@@ -491,7 +491,7 @@ extern "C" int rofl_enc_l2_compressed_verify_batch(rofl_ctx *c, size_t n_clients
     rt_memset(dbad.p, 0, sizeof(int) * K, s); rt_h2d(dres.p, res.data(), sizeof(int) * 2 * K, s);
     LAUNCH(k_validate_points, dim3((unsigned)((3 * D * K + 127) / 128)), dim3(128), s, de.b.as<uint8_t>(), (size_t)32, (size_t)0, 3 * D * K, dbad.as<int>(), 3 * D);
     LAUNCH(k_split96, dim3((unsigned)((D * K + 255) / 256)), dim3(256), s, dL.as<uint8_t>(), dSc.as<uint8_t>(), dCsq.as<uint8_t>(), de.b.as<uint8_t>(), D * K);
-    LAUNCH(k_square_verify, dim3((unsigned)((D * K + 127) / 128)), dim3(128), s, dsp.b.as<uint8_t>(), dSc.as<uint8_t>(), D * K, c->e.sh->tabB, c->e.sh->tabH, dres.as<int>(), D);
+    square_verify_groups(c->e, s, dsp.b.as<uint8_t>(), dSc.as<uint8_t>(), D * K, D, dres.as<int>());     // all K x D square proofs in one batched check, else element by element
     // sum_i c_sq,i per client (params.rs:267)
     const int nb = (int)std::max<size_t>(1, std::min<size_t>(64, (D + 127) / 128));
     dev_buf dpart(sizeof(p3_st) * nb * K, s), dbad2(sizeof(int) * K, s), dsum(32 * K, s);
@@ -526,6 +526,16 @@ extern "C" int rofl_debug_ts_absorb(rofl_ctx *c, const uint8_t *V32, size_t m, i
     transcript_append_u64(t, "n", (uint64_t)n); transcript_append_u64(t, "m", (uint64_t)m);
     for (size_t j = 0; j < m; j++) transcript_append(t, "V", V32 + 32 * j, 32);
     return (memcmp(t.st, got.st, sizeof(t.st)) || t.pos != got.pos || t.pos_begin != got.pos_begin) ? 1 : 0;
+    API_CATCH
+}
+// the batched square-proof check alone (engine.cuh, square_verify_rlc): 1 = the random linear combination over all D proofs holds and every element is
+// well-formed, 0 = it does not (rofl_square_verify then decides element by element).  proofs D x 160, commits D x 64, host buffers.
+extern "C" int rofl_debug_square_rlc(rofl_ctx *c, const uint8_t *proofs, const uint8_t *commits, size_t D) {
+    API_TRY
+    if (!D) return ROFL_ERR_ARGS;
+    lane_guard lg(c->e); cudaStream_t s = lg.s();
+    staged_in dp(proofs, 160 * D, s), dc(commits, 64 * D, s);
+    return square_verify_rlc(c->e, s, dp.b.as<uint8_t>(), dc.b.as<uint8_t>(), D);
     API_CATCH
 }
 // the batching scalars (c_i | rho_i, 2 x n_proofs x 32 bytes) the verifier derives for this call; return value as rofl_range_verify

@@ -1047,14 +1047,54 @@ static int engine_square_prove(rofl_engine &e, const float *d_values, const uint
     if (flags & 1) return -98;
     return 0;
 }
+// All D square proofs of a call in ONE random linear combination (kernels.cuh, k_sq_rlc_*): 1 = every proof valid and well-formed, 0 = ask the
+// per-element kernel (the combination failed or some element is malformed: the exact verdict, per update, comes from k_square_verify).
+static int square_verify_rlc(rofl_engine &e, cudaStream_t s, const uint8_t *d_proofs, const uint8_t *d_commits, size_t D) {
+    static const int on = getenv("ROFL_SQ_RLC") ? atoi(getenv("ROFL_SQ_RLC")) : 1;
+    if (!on || D < 256 || 4 * D > 0x7fffffffu) return 0;
+    const unsigned nb = (unsigned)((D + 127) / 128);
+    const size_t n1 = (D + 63) / 64, n2 = (n1 + 63) / 64;
+    dev_buf d_dig(32 * D, s), d_chal(sizeof(sc_st) * D, s), d_scal(sizeof(sc_st) * 4 * D, s), d_part(sizeof(sc_st) * 2 * nb, s), d_pts(sizeof(p3_st) * 4 * D, s);
+    dev_buf d_l1(32 * n1, s), d_l2(32 * n2, s), d_flags(sizeof(int), s), d_sum(sizeof(sc_st) * 2, s), d_id(sizeof(int), s);
+    rt_memset(d_flags.p, 0, sizeof(int), s);
+    sq_rlc_args a = {}; a.proofs = d_proofs; a.commits = d_commits; a.D = D; a.digest = d_dig.as<uint8_t>(); a.chal = d_chal.as<sc_st>(); a.scal = d_scal.as<sc_st>();
+    a.partial = d_part.as<sc_st>(); a.pts = d_pts.as<p3_st>(); a.flags = d_flags.as<int>();
+    LAUNCH(k_sq_rlc_prep, dim3(nb), dim3(128), s, a);
+    const uint8_t *cur = d_dig.as<uint8_t>(); size_t n = D; uint8_t *bufs[2] = {d_l1.as<uint8_t>(), d_l2.as<uint8_t>()}; int which = 0;
+    do {                                                   // hash tree, 64 digests per node
+        const size_t nn = (n + 63) / 64;
+        LAUNCH(k_hash_tree, dim3((unsigned)((nn + 127) / 128)), dim3(128), s, bufs[which], cur, n);
+        cur = bufs[which]; which ^= 1; n = nn;
+    } while (n > 1);
+    a.root = cur;
+    const msm_plan pl = msm_plan_for(4 * D, 1);
+    a.wbits = pl.c * ((125 + pl.c - 1) / pl.c) - 1;
+    LAUNCH_COOP(k_sq_rlc_scalars, dim3(nb), dim3(128), s, a);
+    LAUNCH_COOP(k_sc_sum, dim3(1), dim3(256), s, d_sum.as<sc_st>(), d_part.as<sc_st>(), (int)nb, 2);
+    LAUNCH(k_sq_rlc_points, dim3((unsigned)((4 * D + 127) / 128)), dim3(128), s, a);
+    dev_buf d_win(sizeof(p3_st) * pl.out_count(1), s);
+    msm_args m = {}; m.v[0].scalars = d_scal.as<sc_st>(); m.split = 1; m.T = (uint32_t)(4 * D); m.scalar_stride = (uint32_t)(4 * D); m.nseg = 1; m.out = d_win.as<p3_st>();
+    m.v[0].seg[0] = mk_seg(d_pts.p, (uint32_t)(4 * D), 0, 1);
+    run_msm(e, s, m, pl, 1);
+    finalize_args f = {}; fin_windows(f, d_win.as<p3_st>(), pl); f.sBa = d_sum.as<sc_st>(); f.sHa = d_sum.as<sc_st>() + 1; f.tabB = e.sh->tabB; f.tabH = e.sh->tabH; f.is_id = d_id.as<int>(); f.count = 1;
+    run_finalize(s, f);
+    int flags = 0, id = 0; rt_d2h(&flags, d_flags.p, sizeof(int), s); rt_d2h(&id, d_id.p, sizeof(int), s); rt_sync(s);
+    return (flags == 0 && id == 1) ? 1 : 0;
+}
+// verdicts of the square proofs of `D` elements in updates of `group` elements each (group = 0: one update): d_res = (all valid, format error) per
+// update, initialised to (1, 0) by the caller.  The batched check first; the per-element kernel only when it does not hold.
+static void square_verify_groups(rofl_engine &e, cudaStream_t s, const uint8_t *d_proofs, const uint8_t *d_commits, size_t D, size_t group, int *d_res) {
+    void *tk = rt_prof_begin(PROF_SQUARE, s);
+    if (square_verify_rlc(e, s, d_proofs, d_commits, D) != 1)
+        LAUNCH(k_square_verify, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_proofs, d_commits, D, e.sh->tabB, e.sh->tabH, d_res, group);
+    rt_prof_end(PROF_SQUARE, tk, s);
+}
 static int engine_square_verify(rofl_engine &e, const uint8_t *d_proofs, const uint8_t *d_commits, size_t D) {
     if (D == 0) return 1;
     lane_guard lg(e);
     cudaStream_t s = lg.s();
     dev_buf d_res(2 * sizeof(int), s); int init[2] = {1, 0}; rt_h2d(d_res.p, init, sizeof(init), s);
-    void *tk = rt_prof_begin(PROF_SQUARE, s);
-    LAUNCH(k_square_verify, dim3((unsigned)((D + 127) / 128)), dim3(128), s, d_proofs, d_commits, D, e.sh->tabB, e.sh->tabH, d_res.as<int>(), (size_t)0);
-    rt_prof_end(PROF_SQUARE, tk, s);
+    square_verify_groups(e, s, d_proofs, d_commits, D, 0, d_res.as<int>());
     int res[2]; rt_d2h(res, d_res.p, sizeof(res), s); rt_sync(s);
     if (res[1]) return -1;
     return res[0] ? 1 : 0;

@@ -945,6 +945,98 @@ KERNEL void LB(128, 1) k_square_verify(const uint8_t *proofs, const uint8_t *com
 KLAUNCH(k_square_verify, false, (const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result, size_t group), (proofs, commits, D, tabB, tabH, result, group))
 #endif
 
+// ---- the same verdict for ALL square proofs of a call with ONE random linear combination (square_proof/mod.rs:77-112 checks, per element,
+//        z_m B + z_r1 H == C'_l + c C_l          and          z_m C_l + z_r2 H == C'_sq + c C_sq ):
+//   sum_i rho_i [first] + sigma_i [second]  <=>
+//   sum_i [ rho_i C'_l,i + (rho_i c_i - sigma_i z_m,i) C_l,i + sigma_i C'_sq,i + sigma_i c_i C_sq,i ] - (sum rho_i z_m,i) B - (sum rho_i z_r1,i + sigma_i z_r2,i) H == 0
+//   with ~128-bit weights (rho_i, sigma_i) = ChaCha20(SHA3-256(root | "sqrl" | i)), root = a hash tree over SHA3-256(commitments_i | proof_i) of every
+//   element: the weights are Fiat-Shamir outputs over ALL proofs of the call.  One MSM over 4 D points replaces, per element, two fixed-base and two
+//   variable-base scalar multiplications (~7 100 field multiplications -> ~1 700 incl. the four decompressions).  A failing combination (or any
+//   malformed element) sends the caller to k_square_verify for the exact per-update verdicts.
+//   k_sq_rlc_prep:    format checks, challenge c_i, digest_i                         (one thread per element)
+//   k_hash_tree:      out[j] = SHA3-256(in[64 j .. 64 j + 63])                        (levels until one digest is left)
+//   k_sq_rlc_scalars: weights, the four point scalars of the element, block sums of the B and H scalars
+//   k_sq_rlc_points:  the 4 D points, extended coordinates                           (one thread per point)
+struct sq_rlc_args { const uint8_t *proofs, *commits; size_t D; uint8_t *digest; sc_st *chal; const uint8_t *root; sc_st *scal, *partial; p3_st *pts; int *flags; int wbits; };
+#ifdef KG_SQUARE
+KERNEL void LB(128, 1) k_sq_rlc_prep(sq_rlc_args a) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.D) return;
+    uint8_t buf[224];
+    ld_bytes32(buf, a.commits + 64 * i); ld_bytes32(buf + 32, a.commits + 64 * i + 32);
+    for (int k = 0; k < 5; k++) ld_bytes32(buf + 64 + 32 * k, a.proofs + 160 * i + 32 * k);
+    sc z; bool ok = true;
+    for (int k = 0; k < 3; k++) { sc_frombytes(z, buf + 128 + 32 * k); ok = ok && sc_is_canonical(z); }
+    if (!ok) atomicOr(a.flags, 1);
+    sc c; sq_transcript_challenge(c, buf, buf + 32, buf + 64, buf + 96);
+    st_sc(a.chal + i, c);
+    uint8_t dg[32]; sha3_256(dg, buf, 224);
+    st_bytes32(a.digest + 32 * i, dg);
+}
+KLAUNCH(k_sq_rlc_prep, false, (sq_rlc_args a), (a))
+KERNEL void LB(128, 1) k_hash_tree(uint8_t *out, const uint8_t *in, size_t n) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x, lo = 64 * j;
+    if (lo >= n) return;
+    const size_t cnt = n - lo < 64 ? n - lo : 64;
+    sponge sp; sponge_init(sp, 136);
+    for (size_t k = 0; k < cnt; k++) { uint8_t d[32]; ld_bytes32(d, in + 32 * (lo + k)); sponge_absorb(sp, d, 32); }
+    sponge_finish(sp, 0x06);
+    uint8_t o[32]; sponge_squeeze(sp, o, 32); st_bytes32(out + 32 * j, o);
+}
+KLAUNCH(k_hash_tree, false, (uint8_t *out, const uint8_t *in, size_t n), (out, in, n))
+KERNEL void LB(128, 1) k_sq_rlc_scalars(sq_rlc_args a) {
+    __shared__ sc_st buf[128];
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int tid = threadIdx.x;
+    sc sB, sH; sc_0(sB); sc_0(sH);
+    if (i < a.D) {
+        uint8_t kb[44], key[32]; ld_bytes32(kb, a.root);
+        kb[32] = 's'; kb[33] = 'q'; kb[34] = 'r'; kb[35] = 'l';
+        for (int k = 0; k < 8; k++) kb[36 + k] = (uint8_t)((uint64_t)i >> (8 * k));
+        sha3_256(key, kb, 44);
+        uint32_t kw[8], w[16];
+        for (int k = 0; k < 8; k++) kw[k] = (uint32_t)key[4 * k] | ((uint32_t)key[4 * k + 1] << 8) | ((uint32_t)key[4 * k + 2] << 16) | ((uint32_t)key[4 * k + 3] << 24);
+        chacha20_block_words(w, kw, 0);
+        // weights of wbits = c * ceil(125 / c) - 1 bits (125 .. 134) for the MSM's window width c: their top window then holds c - 1 uniform bits and the
+        // recoding never carries out of it.  (With 128-bit weights at c = 16 half of all short scalars got the digit +1 in the window above -- ONE bucket
+        // with millions of points, seconds of serial additions; at other widths the few-bit top window had the same effect on a smaller scale.)
+        sc rho, sig; sc_0(rho); sc_0(sig);
+        for (int k = 0; k < 5; k++) { rho.v[k] = w[k]; sig.v[k] = w[5 + k]; }
+        { const int full = a.wbits >> 5, rem = a.wbits & 31;
+          for (int k = 0; k < 5; k++) { const uint32_t m = k < full ? 0xffffffffu : (k == full ? ((1u << rem) - 1u) : 0u); rho.v[k] &= m; sig.v[k] &= m; } }
+        uint8_t zb[32]; sc zm, zr1, zr2, c, t, u;
+        ld_bytes32(zb, a.proofs + 160 * i + 64); sc_frombytes(zm, zb);
+        ld_bytes32(zb, a.proofs + 160 * i + 96); sc_frombytes(zr1, zb);
+        ld_bytes32(zb, a.proofs + 160 * i + 128); sc_frombytes(zr2, zb);
+        ld_sc(c, a.chal + i);
+        sc_st *o = a.scal + 4 * i;
+        // (the whole combination is negated so that the 128-bit weights stay SHORT scalars: their upper windows are zero digits and are skipped.  Negated
+        //  weights l - rho share their upper 125 bits: every term fell into the same bucket of the upper windows and one thread added millions of points.)
+        st_sc(o, rho);                                                             // C'_l:  rho
+        sc_mul(t, rho, c); sc_mul(u, sig, zm); sc_sub(t, t, u); st_sc(o + 1, t);   // C_l:   rho c - sigma z_m
+        st_sc(o + 2, sig);                                                         // C'_sq: sigma
+        sc_mul(t, sig, c); st_sc(o + 3, t);                                        // C_sq:  sigma c
+        sc_mul(sB, rho, zm); sc_neg(sB, sB);                                       // B:     -rho z_m
+        sc_mul(t, rho, zr1); sc_mul(u, sig, zr2); sc_add(sH, t, u); sc_neg(sH, sH); // H:     -(rho z_r1 + sigma z_r2)
+    }
+    block_sum_sc(sB, buf, tid, 128);
+    if (tid == 0) st_sc(a.partial + 2 * (size_t)blockIdx.x, sB);
+    block_sum_sc(sH, buf, tid, 128);
+    if (tid == 0) st_sc(a.partial + 2 * (size_t)blockIdx.x + 1, sH);
+}
+KLAUNCH(k_sq_rlc_scalars, true, (sq_rlc_args a), (a))
+KERNEL void LB(128, 2) k_sq_rlc_points(sq_rlc_args a) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 4 * a.D) return;
+    const size_t i = t >> 2; const int w = (int)(t & 3);
+    const uint8_t *src = w == 0 ? a.proofs + 160 * i : w == 1 ? a.commits + 64 * i : w == 2 ? a.proofs + 160 * i + 32 : a.commits + 64 * i + 32;
+    uint8_t enc[32]; ld_bytes32(enc, src);
+    ge_p3 P;
+    if (!ge_decompress(P, enc)) { atomicOr(a.flags, 1); ge_p3_0(P); }
+    st_p3(a.pts + t, P);
+}
+KLAUNCH(k_sq_rlc_points, false, (sq_rlc_args a), (a))
+#endif
+
 // the un-optimised encodings' per-element proofs (enc types 2 and 3): same shape as K8, one thread per element.
 //   kind 1 = RandProof (pair 64 B, proof 128 B), kind 2 = SquareRandProof (commitments 96 B, proof 192 B)
 struct sigma_args {
@@ -1235,6 +1327,10 @@ void launch_k_square_prove(dim3 g_, dim3 b_, cudaStream_t s_, square_args a);
 void launch_k_sigma_prove(dim3 g_, dim3 b_, cudaStream_t s_, sigma_args a);
 void launch_k_sigma_verify(dim3 g_, dim3 b_, cudaStream_t s_, int kind, const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result);
 void launch_k_square_verify(dim3 g_, dim3 b_, cudaStream_t s_, const uint8_t *proofs, const uint8_t *commits, size_t D, const niels_st *tabB, const niels_st *tabH, int *result, size_t group);
+void launch_k_sq_rlc_prep(dim3 g_, dim3 b_, cudaStream_t s_, sq_rlc_args a);
+void launch_k_hash_tree(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const uint8_t *in, size_t n);
+void launch_k_sq_rlc_scalars(dim3 g_, dim3 b_, cudaStream_t s_, sq_rlc_args a);
+void launch_k_sq_rlc_points(dim3 g_, dim3 b_, cudaStream_t s_, sq_rlc_args a);
 void launch_k_aggregate(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out, const uint8_t *pts, size_t n_clients, size_t D, int init_base, int *bad);
 void launch_k_bsgs_build(dim3 g_, dim3 b_, cudaStream_t s_, unsigned long long *keys, uint32_t *vals, uint32_t cap, uint32_t m, const niels_st *tabB, int *distinct);
 void launch_k_bsgs_solve(dim3 g_, dim3 b_, cudaStream_t s_, uint8_t *out_sc, float *out_f32, const uint8_t *pts, size_t D, const unsigned long long *keys, const uint32_t *vals, uint32_t cap, uint32_t m, uint64_t size, uint64_t max_it, int bsgs_bits, int n_bits, int frac, const niels_st *tabB, int *flags);

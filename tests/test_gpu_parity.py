@@ -154,6 +154,35 @@ def test_l2_and_square_parity(api, oracle):
     assert api.square_verify(bad, sc) == -1
 
 
+def test_square_proofs_batched_check(api, oracle):
+    """All square proofs of a call in ONE random linear combination (k_sq_rlc_*): it holds for honest proofs, fails when any element is tampered with
+    (commitment, proof point or response) or malformed, and rofl_square_verify's verdict stays the reference's in every case."""
+    rng = np.random.default_rng(15)
+    D = 3000
+    v = (rng.integers(-24, 25, D) / 128).astype(np.float32)
+    r1 = oracle.rnd_scalar_vec(b"\x35" * 32, D); r2 = oracle.rnd_scalar_vec(b"\x36" * 32, D)
+    cl = oracle.commit_f32(v, r1, 32, 7)
+    rc, sp, sc = api.square_prove(v, cl, r1, r2, 32, 7, bytes([11] * 32))
+    assert rc == 0
+    assert api.debug_square_rlc(sp, sc) == 1 and api.square_verify(sp, sc) == 1
+    k = D - 3
+    bad = sc.copy(); bad[k, 32:] = sc[k - 1, 32:]                       # another element's c_sq
+    assert api.debug_square_rlc(sp, bad) == 0 and api.square_verify(sp, bad) == 0
+    bad = sp.copy(); bad[k, :32] = sp[k - 1, :32]                       # another element's C'_l
+    assert api.debug_square_rlc(bad, sc) == 0 and api.square_verify(bad, sc) == 0
+    bad = sp.copy(); bad[k, 64] ^= 1                                    # z_m
+    assert api.debug_square_rlc(bad, sc) == 0 and api.square_verify(bad, sc) == 0
+    bad = sp.copy(); bad[k, 128] ^= 1                                   # z_r2
+    assert api.debug_square_rlc(bad, sc) == 0 and api.square_verify(bad, sc) == 0
+    bad = sp.copy(); bad[0, 64:96] = 0xff                               # non-canonical scalar -> FormatError
+    assert api.debug_square_rlc(bad, sc) == 0 and api.square_verify(bad, sc) == -1
+    bad = sc.copy(); bad[5, :32] = 0xff; bad[5, 31] = 0x7f              # undecodable point -> FormatError
+    assert api.debug_square_rlc(sp, bad) == 0 and api.square_verify(sp, bad) == -1
+    # two proofs whose errors would cancel under EQUAL weights do not cancel under the Fiat-Shamir weights: swap the responses of two elements
+    bad = sp.copy(); bad[[1, 2], 64:] = sp[[2, 1], 64:]
+    assert api.debug_square_rlc(bad, sc) == 0 and api.square_verify(bad, sc) == 0
+
+
 def test_aggregate_dlog_parity(api, oracle):
     rng = np.random.default_rng(6)
     n_clients, D = 6, 400
