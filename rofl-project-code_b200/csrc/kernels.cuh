@@ -949,7 +949,7 @@ KLAUNCH(k_square_verify, false, (const uint8_t *proofs, const uint8_t *commits, 
 //        z_m B + z_r1 H == C'_l + c C_l          and          z_m C_l + z_r2 H == C'_sq + c C_sq ):
 //   sum_i rho_i [first] + sigma_i [second]  <=>
 //   sum_i [ rho_i C'_l,i + (rho_i c_i - sigma_i z_m,i) C_l,i + sigma_i C'_sq,i + sigma_i c_i C_sq,i ] - (sum rho_i z_m,i) B - (sum rho_i z_r1,i + sigma_i z_r2,i) H == 0
-//   with ~128-bit weights (rho_i, sigma_i) = ChaCha20(SHA3-256(root | "sqrl" | i)), root = a hash tree over SHA3-256(commitments_i | proof_i) of every
+//   with ~128-bit weights (rho_i, sigma_i) = ChaCha20(SHA3-256(root | "sqrl" | D | i)), root = a hash tree (leaves and inner nodes tagged) over SHA3-256(commitments_i | proof_i) of every
 //   element: the weights are Fiat-Shamir outputs over ALL proofs of the call.  One MSM over 4 D points replaces, per element, two fixed-base and two
 //   variable-base scalar multiplications (~7 100 field multiplications -> ~1 700 incl. the four decompressions).  A failing combination (or any
 //   malformed element) sends the caller to k_square_verify for the exact per-update verdicts.
@@ -970,7 +970,8 @@ KERNEL void LB(128, 1) k_sq_rlc_prep(sq_rlc_args a) {
     if (!ok) atomicOr(a.flags, 1);
     sc c; sq_transcript_challenge(c, buf, buf + 32, buf + 64, buf + 96);
     st_sc(a.chal + i, c);
-    uint8_t dg[32]; sha3_256(dg, buf, 224);
+    // leaf of the hash tree: tag 0x00 (inner nodes absorb 0x01 first, so that no element's bytes can pass for a node of the tree)
+    uint8_t dg[32]; { sponge sp; sponge_init(sp, 136); const uint8_t tag = 0x00; sponge_absorb(sp, &tag, 1); sponge_absorb(sp, buf, 224); sponge_finish(sp, 0x06); sponge_squeeze(sp, dg, 32); }
     st_bytes32(a.digest + 32 * i, dg);
 }
 KLAUNCH(k_sq_rlc_prep, false, (sq_rlc_args a), (a))
@@ -979,6 +980,7 @@ KERNEL void LB(128, 1) k_hash_tree(uint8_t *out, const uint8_t *in, size_t n) {
     if (lo >= n) return;
     const size_t cnt = n - lo < 64 ? n - lo : 64;
     sponge sp; sponge_init(sp, 136);
+    { const uint8_t tag = 0x01; sponge_absorb(sp, &tag, 1); }
     for (size_t k = 0; k < cnt; k++) { uint8_t d[32]; ld_bytes32(d, in + 32 * (lo + k)); sponge_absorb(sp, d, 32); }
     sponge_finish(sp, 0x06);
     uint8_t o[32]; sponge_squeeze(sp, o, 32); st_bytes32(out + 32 * j, o);
@@ -989,10 +991,10 @@ KERNEL void LB(128, 1) k_sq_rlc_scalars(sq_rlc_args a) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int tid = threadIdx.x;
     sc sB, sH; sc_0(sB); sc_0(sH);
     if (i < a.D) {
-        uint8_t kb[44], key[32]; ld_bytes32(kb, a.root);
+        uint8_t kb[52], key[32]; ld_bytes32(kb, a.root);
         kb[32] = 's'; kb[33] = 'q'; kb[34] = 'r'; kb[35] = 'l';
-        for (int k = 0; k < 8; k++) kb[36 + k] = (uint8_t)((uint64_t)i >> (8 * k));
-        sha3_256(key, kb, 44);
+        for (int k = 0; k < 8; k++) { kb[36 + k] = (uint8_t)((uint64_t)a.D >> (8 * k)); kb[44 + k] = (uint8_t)((uint64_t)i >> (8 * k)); }
+        sha3_256(key, kb, 52);
         uint32_t kw[8], w[16];
         for (int k = 0; k < 8; k++) kw[k] = (uint32_t)key[4 * k] | ((uint32_t)key[4 * k + 1] << 8) | ((uint32_t)key[4 * k + 2] << 16) | ((uint32_t)key[4 * k + 3] << 24);
         chacha20_block_words(w, kw, 0);
