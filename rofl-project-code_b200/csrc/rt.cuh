@@ -148,6 +148,7 @@ struct rt_pin_pool {
         void *p = nullptr; rt_check(cudaHostAlloc(&p, cap, cudaHostAllocPortable), "cudaHostAlloc"); return p;
     }
     void give(void *p, size_t cap) { std::lock_guard<std::mutex> lk(mu); free_.emplace_back(p, cap); }
+    void trim() { std::vector<std::pair<void *, size_t>> out; { std::lock_guard<std::mutex> lk(mu); out.swap(free_); } for (auto &b : out) cudaFreeHost(b.first); }
 };
 inline rt_pin_pool &rt_pins() { static rt_pin_pool p; return p; }
 struct rt_pending_d2h { cudaStream_t s; void *h, *stage; size_t n, cap; };
@@ -194,7 +195,7 @@ inline void rt_sync(cudaStream_t s) {
     }
 }
 inline size_t rt_free_mem() { size_t f = 0, t = 0; cudaMemGetInfo(&f, &t); return f; }
-inline void rt_trim() { rt_bigs().trim(); }
+inline void rt_trim() { rt_bigs().trim(); rt_pins().trim(); }
 // long-lived allocations (generator tables, BSGS tables): straight from / back to CUDA, never through the scratch cache
 inline void *rt_raw_malloc(size_t n) { void *p = nullptr; if (cudaMalloc(&p, n ? n : 256) != cudaSuccess) { cudaGetLastError(); rt_trim(); rt_check(cudaMalloc(&p, n ? n : 256), "cudaMalloc"); } return p; }
 inline void rt_raw_free(void *p) { if (p) cudaFree(p); }
