@@ -236,10 +236,21 @@ extern "C" int rofl_enc_range_compressed_encrypt(rofl_ctx *c, const float *v, co
     std::vector<float> clipped(D); rofl_clip_f32_to_range_vec(v, D, prove_range, n_bits, frac, clipped.data());                 // :709
     staged_in dv(clipped.data(), 4 * D, s), db(blind, 32 * D, s); dev_buf dC(32 * D, s);
     size_t a = 0, b = 0;
+    // the compressed rand proof (helper_prove_existing: one sequential transcript over all D pairs on a host core) as a second caller of the context,
+    // beside the range proofs; it commits L = v B + r H itself -- the same points the range proofs publish
+    rt_sync(s);
+    int rc_crp = 0; std::string err_crp;
+    std::thread crp([&] {
+        try { rt_set_device(c->e.device); rc_crp = engine_crp_prove(c->e, dv.b.as<float>(), nullptr, db.b.as<uint8_t>(), D, n_bits, frac, seed, rand_proof128, enc_values64); }
+        catch (const std::exception &ex) { rc_crp = ROFL_ERR_CUDA; err_crp = ex.what(); }
+    });
+    struct joiner { std::thread &t; ~joiner() { if (t.joinable()) t.join(); } } jn{crp};
     int rc = engine_range_prove(c->e, dv.b.as<float>(), db.b.as<uint8_t>(), D, prove_range, n_partition, n_bits, frac, seed, range_proofs, &a, &b, dC.as<uint8_t>());
     if (plen) *plen = a; if (n_proofs) *n_proofs = b;
+    crp.join();
     if (rc) return rc;
-    return engine_crp_prove(c->e, dv.b.as<float>(), dC.as<uint8_t>(), db.b.as<uint8_t>(), D, n_bits, frac, seed, rand_proof128, enc_values64);      // helper_prove_existing
+    if (rc_crp == ROFL_ERR_CUDA && !err_crp.empty()) throw std::runtime_error(err_crp);
+    return rc_crp;
     API_CATCH
 }
 // EncModelParams::verify, EncRangeCompressed arm (params.rs:236-256): rand proof over ALL pairs, range proofs over the first
