@@ -325,7 +325,9 @@ static inline int msm_pick_c(size_t T) {
     return best;
 }
 static inline size_t bm_min_terms() { static const size_t v = getenv("ROFL_BM_MIN") ? (size_t)atoll(getenv("ROFL_BM_MIN")) : (size_t)32768; return v; }
-static inline msm_plan msm_plan_for(size_t T, size_t n_msm) {
+// big_min: smallest T for the sorted wide-window form (0 = the default bm_min_terms(); single verifier-side MSMs pass 2048: k_msm needs 3.6 ms for
+// the 10 000 terms of a configs[0] verification -- 76 blocks walking 32 windows -- the sorted form 0.5 ms)
+static inline msm_plan msm_plan_for(size_t T, size_t n_msm, size_t big_min = 0) {
     msm_plan p; p.c = msm_pick_c(T); p.slices = 1; p.slice_len = (uint32_t)T;
     if (const char *fc = getenv("ROFL_MSM_C")) {       // test hook: force the window width / slicing
         p.c = std::max(3, std::min(16, atoi(fc)));
@@ -333,7 +335,7 @@ static inline msm_plan msm_plan_for(size_t T, size_t n_msm) {
         if (const char *fs = getenv("ROFL_MSM_SLICES")) { p.slices = (uint32_t)std::max<size_t>(1, std::min<size_t>(atoi(fs), T)); p.slice_len = (uint32_t)((T + p.slices - 1) / p.slices); p.slices = (uint32_t)((T + p.slice_len - 1) / p.slice_len); }
         p.nw = msm_nw(p.c); return p;
     }
-    if (T >= bm_min_terms()) {                         // wide windows, buckets sorted in global memory (kernels.cuh K4b): ~64 terms per bucket
+    if (T >= (big_min ? big_min : bm_min_terms())) {   // wide windows, buckets sorted in global memory (kernels.cuh K4b): ~64 terms per bucket
         p.big = true; p.c = std::max(9, std::min(16, ilog2_sz(T + 1) - 6)); p.nw = msm_nw(p.c);
         const size_t threads = n_msm * (size_t)p.nw * ((size_t)1 << (p.c - 1));
         p.parts = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (148 * 1024 + threads - 1) / threads));
@@ -838,7 +840,7 @@ static int verify_chunks(rofl_engine &e, cudaStream_t s, int label_id, int n, in
     // commitments and proof points of ALL chunks: one sliced MSM over C*m + C*nsmall terms (scalars laid out the same way)
     {
         const uint32_t TV = (uint32_t)((size_t)C * m + (size_t)C * nsmall);
-        const msm_plan pl = msm_plan_for(TV, 1);
+        const msm_plan pl = msm_plan_for(TV, 1, 2048);
         dev_buf d_winV(sizeof(p3_st) * pl.out_count(1), s);
         msm_args a = {}; a.v[0].scalars = d_var.as<sc_st>(); a.split = 1; a.T = TV; a.scalar_stride = TV; a.nseg = 2; a.out = d_winV.as<p3_st>();
         a.v[0].seg[0] = mk_seg(d_Vp3, (uint32_t)((size_t)C * m), 0, 1); a.v[0].seg[1] = mk_seg(d_sp.p, (uint32_t)((size_t)C * nsmall), 0, 1);
@@ -1067,7 +1069,7 @@ static int square_verify_rlc(rofl_engine &e, cudaStream_t s, const uint8_t *d_pr
         cur = bufs[which]; which ^= 1; n = nn;
     } while (n > 1);
     a.root = cur;
-    const msm_plan pl = msm_plan_for(4 * D, 1);
+    const msm_plan pl = msm_plan_for(4 * D, 1, 2048);
     a.wbits = pl.c * ((125 + pl.c - 1) / pl.c) - 1;
     LAUNCH_COOP(k_sq_rlc_scalars, dim3(nb), dim3(128), s, a);
     LAUNCH_COOP(k_sc_sum, dim3(1), dim3(256), s, d_sum.as<sc_st>(), d_part.as<sc_st>(), (int)nb, 2);
