@@ -24,6 +24,7 @@ extern "C" int rofl_set_option(rofl_ctx *c, const char *name, long value) {
     else if (n == "trim") rt_trim();                                                  // hand the cached scratch blocks of this device back to CUDA
     else if (n == "frozen") c->e.use_frz = value != 0;
     else if (n == "tail_np") c->e.tail_np = (int)std::max<long>(0, std::min<long>(TAIL_MAX_F / 2, value));
+    else if (n == "tail_batch_mb") c->e.tail_batch_mb = (int)std::max<long>(1, std::min<long>(65536, value));
     else if (n == "tail_ncta") c->e.tail_ncta = value >= 8 ? 8 : value >= 4 ? 4 : value >= 2 ? 2 : 1;
     else if (n == "rt_per") c->e.rt_per = (int)std::max<long>(0, std::min<long>(64, value));
     else if (n == "nt_unfold") c->e.nt_unfold = (int)std::max<long>(0, std::min<long>(4, value));

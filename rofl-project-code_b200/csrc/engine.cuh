@@ -67,6 +67,7 @@ struct rofl_engine {
     int use_rt = 1;                       // 0: never build generator tables (generic Pippenger / fold path only)
     int rt_unfold = 4;                    // IPP rounds computed over the original generators before the catch-up fold
     int tail_np = 32;                     // IPP rounds with half-size <= tail_np run in the fused on-device tail kernel (0 = off)
+    int tail_batch_mb = 2048;             // the tail's per-digit tables (8 MB per chunk) are built and used for this many MB of chunks at a time
     int tail_ncta = 2;                    // thread blocks (one cluster) per chunk in the tail kernel: 1, 2, 4, 8.  Measured with three chunk groups: 2 -> 36.15 ms,
                                           // 1 -> 36.35, 4 -> 38.1 (a 4-block cluster of 544-thread blocks waits for room beside the other groups' bulk kernels)
     std::mutex pin_mu; std::vector<std::pair<void *, size_t>> pins;      // pool of pinned host blocks
@@ -560,34 +561,41 @@ static void prove_chunks(rofl_engine &e, chain &q, cudaStream_t side, int label_
             if (round == 0) LAUNCH(k_niels_to_p3, dim3((Ft + 127) / 128, C), dim3(128), q.small(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), g.G, g.H, Ft, (uint32_t)half);
             // tables of the tail: (k+1) 16^pos P for every radix-16 digit position (TAIL_Q = 64 per point; 8 MB per chunk): a round is then a plain sum
             // of table entries -- the 28-doubling chain per round that octant tables need was 215 k cycles of one lane in each of the six rounds
-            dev_buf d_tb(sizeof(p3_st) * (size_t)C * 2 * Ft * TAIL_Q, q), d_tT(sizeof(p3_st) * (size_t)C * 2 * Ft * TAIL_Q * FRZ_E, q);
-            void *tk = rt_prof_begin(PROF_TAIL, q.cur ? q.lo : q.hi);
-#ifdef ROFL_EMUL
-            LAUNCH(k_frz_bases, dim3((2 * Ft + 127) / 128, C), dim3(128), q.small(), d_tb.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), Ft, (uint32_t)half, (uint32_t)TAIL_Q, 4u);
-#else
-            LAUNCH(k_frz_bases4, dim3((4 * 2 * Ft + 127) / 128, C), dim3(128), q.small(), d_tb.as<p3_st>(), d_Gf.as<p3_st>(), d_Hf.as<p3_st>(), Ft, (uint32_t)half, (uint32_t)TAIL_Q, 4u);
-#endif
-            LAUNCH(k_frz_tables, dim3((unsigned)(((size_t)C * 2 * Ft * TAIL_Q + 127) / 128)), dim3(128), q.small(), d_tT.as<p3_st>(), d_tb.as<p3_st>(), (size_t)C * 2 * Ft * TAIL_Q);
-            tail_args ta = {}; ta.T = d_tT.as<p3_st>();
-            ta.a = d_a.as<sc_st>(); ta.b = d_b.as<sc_st>(); ta.yinv = d_yinv.as<sc_st>(); ta.N = N;
-            ta.ts = d_ts.as<transcript>(); ta.w = d_w2.as<sc_st>(); ta.uprod = d_up.as<sc_st>(); ta.uinvprod = d_up.as<sc_st>() + C; ta.tabB = e.sh->tabB;
-            dev_buf d_tscr(sizeof(p3_st) * 512 * (size_t)C, q); ta.scratch = d_tscr.as<p3_st>();
-            ta.out = d_proofs.as<uint8_t>() + 224 + 64 * (size_t)round; ta.out_stride = (uint32_t)plen; ta.F = Ft;
+            // (the tables are built and used for at most Cb chunks at a time: 2 GB of them however many chunks a call has)
+            const size_t per_chunk = sizeof(p3_st) * 2 * (size_t)Ft * TAIL_Q * (FRZ_E + 1);
+            const size_t Cb = std::max<size_t>(1, std::min<size_t>((size_t)C, ((size_t)e.tail_batch_mb << 20) / per_chunk));
+            dev_buf d_tb(sizeof(p3_st) * Cb * 2 * Ft * TAIL_Q, q), d_tT(sizeof(p3_st) * Cb * 2 * Ft * TAIL_Q * FRZ_E, q);
+            dev_buf d_tscr(sizeof(p3_st) * 512 * Cb, q), d_gfac(sizeof(sc_st) * 3 * Cb, q);
             static const bool tail_dbg = getenv("ROFL_TAIL_DBG") != nullptr;
             dev_buf d_tdbg(tail_dbg ? 128 * sizeof(long long) : 16, q);
-            if (tail_dbg) { rt_memset(d_tdbg.p, 0, 128 * sizeof(long long), q.small()); ta.dbg = d_tdbg.as<long long>(); }
+            void *tk = rt_prof_begin(PROF_TAIL, q.cur ? q.lo : q.hi);
+            for (size_t c0 = 0; c0 < (size_t)C; c0 += Cb) {
+                const unsigned Cn = (unsigned)std::min<size_t>(Cb, (size_t)C - c0);
+                const p3_st *Gb = d_Gf.as<p3_st>() + c0 * half, *Hb = d_Hf.as<p3_st>() + c0 * half;
 #ifdef ROFL_EMUL
-            ta.ncta = 1;
+                LAUNCH(k_frz_bases, dim3((2 * Ft + 127) / 128, Cn), dim3(128), q.small(), d_tb.as<p3_st>(), Gb, Hb, Ft, (uint32_t)half, (uint32_t)TAIL_Q, 4u);
 #else
-            ta.ncta = (uint32_t)e.tail_ncta;
+                LAUNCH(k_frz_bases4, dim3((4 * 2 * Ft + 127) / 128, Cn), dim3(128), q.small(), d_tb.as<p3_st>(), Gb, Hb, Ft, (uint32_t)half, (uint32_t)TAIL_Q, 4u);
 #endif
-            dev_buf d_gfac(sizeof(sc_st) * 3 * (size_t)C, q); ta.gfac = d_gfac.as<sc_st>();
-            LAUNCH_COOP(k_ipp_tail, dim3((unsigned)(C * ta.ncta)), dim3(TAIL_THREADS), q.small(), ta);
+                LAUNCH(k_frz_tables, dim3((unsigned)(((size_t)Cn * 2 * Ft * TAIL_Q + 127) / 128)), dim3(128), q.small(), d_tT.as<p3_st>(), d_tb.as<p3_st>(), (size_t)Cn * 2 * Ft * TAIL_Q);
+                tail_args ta = {}; ta.T = d_tT.as<p3_st>();
+                ta.a = d_a.as<sc_st>() + c0 * N; ta.b = d_b.as<sc_st>() + c0 * N; ta.yinv = d_yinv.as<sc_st>() + c0 * N; ta.N = N;
+                ta.ts = d_ts.as<transcript>() + c0; ta.w = d_w2.as<sc_st>() + c0; ta.uprod = d_up.as<sc_st>() + c0; ta.uinvprod = d_up.as<sc_st>() + C + c0; ta.tabB = e.sh->tabB;
+                ta.scratch = d_tscr.as<p3_st>(); ta.gfac = d_gfac.as<sc_st>();
+                ta.out = d_proofs.as<uint8_t>() + c0 * plen + 224 + 64 * (size_t)round; ta.out_stride = (uint32_t)plen; ta.F = Ft;
+                if (tail_dbg && c0 == 0) { rt_memset(d_tdbg.p, 0, 128 * sizeof(long long), q.small()); ta.dbg = d_tdbg.as<long long>(); }
+#ifdef ROFL_EMUL
+                ta.ncta = 1;
+#else
+                ta.ncta = (uint32_t)e.tail_ncta;
+#endif
+                LAUNCH_COOP(k_ipp_tail, dim3((unsigned)(Cn * ta.ncta)), dim3(TAIL_THREADS), q.small(), ta);
+            }
             if (tail_dbg) {
                 long long h[128]; rt_d2h(h, d_tdbg.p, sizeof(h), q.small()); rt_sync(q.small());
                 static const char *nm[7] = {"digits", "c_tree", "table_adds", "point_tree", "chain+compress", "transcript+invert", "folds"};
                 for (int r = 0; r < 8 && h[8 * r]; r++) { fprintf(stderr, "[rofl tail] round %d:", r); for (int k = 0; k < 7; k++) fprintf(stderr, " %s=%lld", nm[k], h[8 * r + k + 1] - h[8 * r + k]); fprintf(stderr, "\n"); }
-                fprintf(stderr, "[rofl tail] round 2, per warp (table loop, shuffle tree):"); for (int w = 0; w < 16; w++) fprintf(stderr, " (%lld, %lld)", h[64 + 2 * w], h[64 + 2 * w + 1]); fprintf(stderr, "  c w B threads: %lld  chain: %lld  compress + store: %lld\n", h[96], h[100], h[101]);
+                fprintf(stderr, "[rofl tail] round 2, per warp (table loop, shuffle tree):"); for (int w = 0; w < 16; w++) fprintf(stderr, " (%lld, %lld)", h[64 + 2 * w], h[64 + 2 * w + 1]); fprintf(stderr, "  c w B threads: %lld\n", h[96]);
             }
             rt_prof_end(PROF_TAIL, tk, q.cur ? q.lo : q.hi);
             tail_done = true;

@@ -91,6 +91,20 @@ def test_l2_and_square(api, oracle):
     assert api.square_verify(bad, sc) == -1
 
 
+def test_tail_tables_in_batches_of_chunks(api, oracle):
+    """The tail's per-digit tables are built for a bounded number of chunks at a time (tail_batch_mb): one chunk per batch here, same bytes."""
+    rng = np.random.default_rng(16)
+    D, rb, P = 40, 8, 8
+    v = rng.uniform(-0.9, 0.9, D).astype(np.float32); bl = oracle.rnd_scalar_vec(b"\x37" * 32, D); seed = bytes([12] * 32)
+    rc_o, p_o, c_o = oracle.range_prove(v, bl, rb, P, 16, 7, seed)
+    try:
+        api.set_option("tail_batch_mb", 1)
+        rc, p, c = api.range_prove(v, bl, rb, P, 16, 7, seed)
+        assert rc == rc_o == 0 and (p == p_o).all() and (c == c_o).all()
+    finally:
+        api.set_option("tail_batch_mb", 2048)
+
+
 def test_square_proofs_batched_check(api, oracle):
     """All square proofs of a call in ONE random linear combination (k_sq_rlc_*): it holds for honest proofs, fails when any element is tampered with
     (commitment, proof point or response) or malformed, and rofl_square_verify's verdict stays the reference's in every case."""

@@ -329,8 +329,12 @@ def test_tail_cluster_sizes_and_entry_points_give_the_same_bytes(api, oracle):
             rc, p, c = api.range_prove(v, bl, rb, P, nb, 7, seed)
             assert rc == 0 and (c == c_o).all() and (p == p_o).all(), (ncta, tail_np, groups)
             assert api.range_verify(p, c, rb, seed) == 1
-    finally:
         api.set_option("tail_ncta", 2); api.set_option("tail_np", 32); api.set_option("groups", 3)
+        api.set_option("tail_batch_mb", 10)                                   # the tail's tables for one chunk at a time
+        rc, p, c = api.range_prove(v, bl, rb, P, nb, 7, seed)
+        assert rc == 0 and (c == c_o).all() and (p == p_o).all()
+    finally:
+        api.set_option("tail_ncta", 2); api.set_option("tail_np", 32); api.set_option("groups", 3); api.set_option("tail_batch_mb", 2048)
 
 
 def test_rand_and_square_rand_proof_parity_and_full_size(api, oracle):
